@@ -1,0 +1,212 @@
+/* include/subread_cuda.h -- C ABI of libsubread_cuda.so
+ *
+ * B200-native (sm_100a) replacement for the seed-and-vote step of subread-align / subjunc.
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference's src/).  Plain pointers and sizes only; no C++ or torch types.  All functions
+ * return 0 on success and a non-zero code on failure (the reference's own convention,
+ * core.c:906-914); the message is available from srcuda_last_error().  Nothing here ever
+ * calls exit() and there is no CPU fallback: without a usable GPU every compute entry point
+ * fails with SRCUDA_ERR_NO_DEVICE.
+ *
+ * Threading model: the reference runs do_voting on up to 40 pthreads that share one input
+ * mutex (core.c:3404-3456).  Here one host thread drives one handle (= one GPU); several
+ * handles (one per GPU) may be driven concurrently from different threads or processes on
+ * disjoint fragment ranges of the same chunk.
+ */
+#ifndef SUBREAD_CUDA_H
+#define SUBREAD_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRCUDA_OK 0
+#define SRCUDA_ERR_NO_DEVICE 1
+#define SRCUDA_ERR_CUDA 2
+#define SRCUDA_ERR_IO 3
+#define SRCUDA_ERR_FORMAT 4
+#define SRCUDA_ERR_ARG 5
+#define SRCUDA_ERR_UNSUPPORTED 6
+#define SRCUDA_ERR_NOMEM 7
+#define SRCUDA_ERR_NO_INDEX 8
+
+typedef struct srcuda_handle srcuda_handle;
+
+/* Byte-identical to the reference's mapping_result_t (core.h:350-370): 68 bytes.  This is the
+ * bigtable element (core-bigtable.c:84-125); out_align buffers can be the reference's own
+ * bigtable_cache_malloc_ptr. */
+typedef struct {
+	uint32_t selected_position;
+	int16_t result_flags;
+	int16_t read_length;
+	int16_t selected_votes;
+	int16_t used_subreads_in_vote;
+	uint8_t noninformative_subreads_in_vote;
+	int8_t indels_in_confident_coverage;
+	int8_t is_fully_covered;
+	uint8_t _pad0;
+	int16_t selected_indel_record[22];
+	uint16_t confident_coverage_start;
+	uint16_t confident_coverage_end;
+	int16_t subread_quality;
+	uint16_t _pad1;
+} srcuda_mapping_result;
+
+/* Byte-identical to subjunc_result_t (core.h:397-410): 16 bytes. */
+typedef struct {
+	int16_t split_point;
+	int16_t minor_votes;
+	int8_t double_indel_offset;
+	int8_t indel_at_junction;
+	int8_t small_side_increasing_coordinate;
+	int8_t large_side_increasing_coordinate;
+	uint32_t minor_position;
+	uint16_t minor_coverage_start;
+	uint16_t minor_coverage_end;
+} srcuda_subjunc_result;
+
+/* The scalars do_voting (core.c:3049-3235) and process_voting_junction_PE_topK
+ * (core-junction.c:2199-2530) read from configuration_t (core.h:128-253), same names. */
+typedef struct {
+	int32_t total_subreads;                  /* -n; 10 subread-align, 14 subjunc */
+	int32_t top_scores;                      /* 3 */
+	int32_t max_vote_simples;                /* 3 SE / 64 PE (core.c:4075-4084) */
+	int32_t max_vote_combinations;           /* 3 */
+	int32_t max_vote_number_cutoff;          /* 2 */
+	int32_t multi_best_reads;                /* 3 */
+	int32_t minimum_subread_for_first_read;  /* -m; 3 */
+	int32_t minimum_subread_for_second_read; /* -p; 1 */
+	int32_t max_indel_length;                /* -I; 5.  Voting uses min(16, this), core.c:3059 */
+	int32_t minimum_pair_distance;           /* -d; 50 */
+	int32_t maximum_pair_distance;           /* -D; 600 */
+	int32_t is_first_read_reversed;          /* -S; 0 */
+	int32_t is_second_read_reversed;         /* -S; 1 */
+	int32_t do_breakpoint_detection;         /* subjunc */
+	int32_t do_big_margin_filtering_for_junctions;
+	int32_t big_margin_record_size;          /* 9 */
+	int32_t maximum_intron_length;           /* 500000 */
+	int32_t limited_tree_scan;
+	int32_t check_donor_at_junctions;
+	int32_t reserved[5];
+} srcuda_params;
+
+/* What the host needs back from the loaded block to compute low/high border exactly as
+ * core.c:3081-3082 does, and to size its loops. */
+typedef struct {
+	int32_t index_gap;            /* gehash_t.index_gap  (subread.h:300-310) */
+	int32_t padding;              /* gehash_t.padding */
+	uint32_t buckets_number;
+	uint64_t n_items;
+	uint32_t start_point;         /* gene_value_index_t (subread.h:313-322) */
+	uint32_t length;
+	uint32_t start_base_offset;
+	uint32_t values_bytes;
+	int32_t total_offsets;        /* gene_offset_t.total_offsets (subread.h:395-401) */
+	uint64_t device_bytes;        /* HBM held by this block */
+} srcuda_index_desc;
+
+/* Device-side timing and counters of the last srcuda_vote_chunk* call (CUDA events on the
+ * library's own stream). */
+typedef struct {
+	float ms_total;          /* first H2D to last D2H (or kernels only for the device variant) */
+	float ms_kernel_vote;    /* fused pack+lookup+vote+topK(+verify) kernel, summed over batches */
+	float ms_kernel_overflow;/* exact slow path for fragments whose vote table left shared memory */
+	uint64_t n_overflow;     /* fragments that took the slow path */
+	uint64_t h2d_bytes;
+	uint64_t d2h_bytes;
+	uint32_t n_launches;     /* kernels launched */
+	uint32_t n_batches;
+} srcuda_timing;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int srcuda_device_count(void);
+
+/* Bind a handle to one GPU.  Replaces nothing in the reference (it has no device). */
+int srcuda_open(int device, srcuda_handle **out);
+void srcuda_close(srcuda_handle *h);
+
+/* Thread-safe: message of the last failure on this handle (h may be NULL for open errors).
+ * Replaces the SUBREADprintf diagnostics (subread.h:143). */
+const char *srcuda_last_error(const srcuda_handle *h);
+
+/* ---- index ----------------------------------------------------------------------------- */
+
+/* Load one index block from the reference's on-disk files and keep it resident in HBM.
+ * Replaces gehash_load (sorted-hashtable.c:1390), gvindex_load (gene-value-index.c:190) and
+ * load_offsets (gene-algorithms.c:1293) for block `block_no` of `index_prefix`
+ * (<prefix>.NN.b.tab, <prefix>.NN.b.array, <prefix>.reads). */
+int srcuda_index_load(srcuda_handle *h, const char *index_prefix, int block_no);
+
+/* Same, from structures the caller already holds in host memory (what a reference-side
+ * binding would pass from gehash_t / gene_value_index_t / gene_offset_t).  bucket_start has
+ * buckets_number+1 entries; keys/vals are the buckets' items back to back. */
+int srcuda_index_upload(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t buckets_number,
+                        uint64_t n_items, const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals,
+                        uint32_t start_point, uint32_t length, const uint8_t *values, uint32_t values_bytes,
+                        const uint32_t *read_offsets, int32_t total_offsets);
+
+/* Copy the resident block of `src` to the GPU of `dst` with a peer copy over NVLink
+ * (no host round trip).  Both handles live in this process. */
+int srcuda_index_replicate(srcuda_handle *dst, const srcuda_handle *src);
+
+int srcuda_index_describe(const srcuda_handle *h, srcuda_index_desc *out);
+void srcuda_index_unload(srcuda_handle *h);
+
+/* ---- pinned host memory (optional, recommended for the chunk buffers) ------------------- */
+void *srcuda_host_alloc(size_t bytes);
+void srcuda_host_free(void *p);
+
+/* ---- the voting step -------------------------------------------------------------------- */
+
+/* One chunk of reads against the resident index block: everything do_voting (core.c:3049)
+ * does per read up to and including the bigtable update, i.e. genekey2int / reverse_read
+ * (input-files.c:1232,1113), gehash_go_X (sorted-hashtable.c:937) and
+ * process_voting_junction_PE_topK (core-junction.c:2199).  find_new_indels /
+ * find_new_junctions stay with the caller.
+ *
+ *   text, off, len  reads as they are in the input file after trimming; read r of fragment f
+ *                   is mate m = r % mates of fragment f = r / mates (mates = 1 + is_paired),
+ *                   characters text[off[r]] .. text[off[r]+len[r]-1].  Mate strands are
+ *                   handled inside (is_first/second_read_reversed), like fetch_next_read_pair
+ *                   (core.c:1187-1199).
+ *   out_align       read-modify-write, [(f*mates+m)*multi_best_reads + k], the layout of
+ *                   core-bigtable.c:161-166: successive index blocks merge into it.  Pass
+ *                   out_align_is_zero != 0 when the buffer is known to be all zero (first
+ *                   block of a chunk) to skip its upload.
+ *   out_junc, out_big_margin   subjunc only (do_breakpoint_detection); may be NULL otherwise.
+ *   out_verify      optional, one uint16 per out_align slot: number of read bases equal to
+ *                   the genome at selected_position in the slot's orientation (match_chro,
+ *                   gene-value-index.c:856), 0xffff for an unused slot.
+ */
+int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char *text, const uint64_t *off,
+                      const uint16_t *len, int64_t n_frags, int is_paired, int out_align_is_zero,
+                      srcuda_mapping_result *out_align, srcuda_subjunc_result *out_junc, uint16_t *out_big_margin,
+                      uint16_t *out_verify);
+
+/* Same computation with every buffer already resident on the handle's GPU (device pointers);
+ * no host<->device traffic.  out_align must be initialised by the caller (cudaMemset 0 for a
+ * first block).  Used by bench.py for the HBM-resident figure. */
+int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, const char *d_text, const uint64_t *d_off,
+                             const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len,
+                             srcuda_mapping_result *d_out_align, srcuda_subjunc_result *d_out_junc,
+                             uint16_t *d_out_big_margin, uint16_t *d_out_verify);
+
+int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out);
+
+/* Debug/validation switch: route every fragment through the exact slow path (one thread per
+ * fragment, full 30x24 table) instead of the warp kernel.  Results must not change. */
+int srcuda_set_force_slow_path(srcuda_handle *h, int on);
+
+/* Measured random 32-byte-sector gather bandwidth over `table_bytes` of HBM (GB/s): the
+ * "HBM-gather roofline" denominator of SURVEY.md section 8(d). */
+int srcuda_measure_gather_bandwidth(srcuda_handle *h, uint64_t table_bytes, int iters, double *gbps_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -191,8 +191,9 @@ uint32_t or_genekey2int(const char *s)
 	return key;
 }
 
-/* The 256-entry table at input-files.c:1111 as a rule: A<->T, C<->G, U->A (either case is NOT
- * folded: lowercase letters are "everything else"), everything else -> N. */
+/* The 256-entry table at input-files.c:1111 as a rule: A<->T, C<->G, U->A, everything else
+ * (lowercase letters included: the second "TNGNNNC" group of the table sits at 0xC1.., not at
+ * 'a'..) -> N.  Checked for every byte 1..127 against the reference in tests/test_oracle_vs_ref.py. */
 static inline char complement_char(unsigned char c)
 {
 	switch (c) {
@@ -201,11 +202,6 @@ static inline char complement_char(unsigned char c)
 	case 'U': return 'A';
 	case 'C': return 'G';
 	case 'G': return 'C';
-	case 'a': return 'T';
-	case 't': return 'A';
-	case 'u': return 'A';
-	case 'c': return 'G';
-	case 'g': return 'C';
 	default: return 'N';
 	}
 }

@@ -1,0 +1,151 @@
+// sr_common.cuh -- types and small helpers shared by the warp kernel, the exact scalar path and
+// the host API.  Everything marked SR_HD compiles both as device code (nvcc) and as plain host
+// C++ (g++ with -DSR_HOST_ONLY), the latter only so that tests can run the scalar path on a CPU
+// box; the shipped library never executes it on the host.
+//
+// Reference citations are relative to the reference's src/ directory.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
+#define SR_HD __host__ __device__ __forceinline__
+#define SR_D __device__ __forceinline__
+#else
+#define SR_HD inline
+#define SR_D inline
+#endif
+
+namespace sr {
+
+constexpr int kVoteRows = 30;        // GENE_VOTE_TABLE_SIZE   subread.h:217
+constexpr int kVoteSpace = 24;       // GENE_VOTE_SPACE        subread.h:216
+constexpr int kMaxSections = 7;      // MAX_INDEL_SECTIONS     subread.h:88
+constexpr int kRecLen = 21;          // MAX_INDEL_TOLERANCE*3  subread.h:231
+constexpr int kSeg = 5;              // INDEL_SEGMENT_SIZE     sorted-hashtable.c:344
+constexpr int kCoreNegStrand = 8;    // CORE_IS_NEGATIVE_STRAND core.h:258
+constexpr int kLongRead = 160;       // EXON_LONG_READ_LENGTH  subread.h:83
+constexpr int kMaxReadLen = 1210;    // MAX_READ_LENGTH        subread.h:73
+constexpr int kMaxLookups = 63 * 3;  // <= 63 subreads (core.c:3122-3126) x gap <= 3
+constexpr int kMaxBest = 3;          // multi_best_reads (core.c:4075-4084)
+constexpr int kMaxTop = 3;           // top_scores (core-indel.c:4415)
+constexpr int kMaxSimples = 64;      // max_vote_simples PE (core.c:4077)
+constexpr int kMaxCombos = 16;       // max_vote_combinations, raised by -B up to 16
+constexpr int kResultWords = 17;     // sizeof(mapping_result_t) / 4
+
+// One index block resident in HBM (SoA form of gehash_t + gene_value_index_t + gene_offset_t).
+struct DevIndex {
+	uint32_t buckets_number;
+	int32_t index_gap;
+	int32_t padding;
+	uint32_t start_point, length, start_base_offset, values_bytes;
+	int32_t total_offsets;
+	const uint32_t *bucket_start;  // buckets_number + 1
+	const int16_t *keys;           // n_items, ascending inside a bucket (signed compare)
+	const uint32_t *vals;          // n_items
+	const uint32_t *genome;        // 2-bit bases, LSB first, as u32 words (padded)
+	const uint32_t *chr_offsets;   // total_offsets cumulative END offsets
+};
+
+// The voting scalars, validated and pre-digested on the host (see srcuda_params).
+struct VoteConfig {
+	int32_t total_subreads, top_scores, max_vote_simples, max_vote_combinations, max_vote_number_cutoff;
+	int32_t multi_best_reads, min_first, min_second, indel_tolerance;  // indel_tolerance = min(16, max_indel_length)
+	int32_t min_pair_dist, max_pair_dist, first_reversed, second_reversed;
+	int32_t is_paired;
+	uint32_t low_border, high_border;  // core.c:3081-3082
+};
+
+// mapping_result_t as 17 little-endian words:
+//  w0 pos | w1 flags,read_length | w2 votes,used | w3 noninf,indels,full,pad | w4..w14 record[22]
+//  w15 cov_start,cov_end | w16 subread_quality,pad
+struct ResultWords { uint32_t w[kResultWords]; };
+
+SR_HD int16_t result_votes(const ResultWords &r) { return (int16_t)(r.w[2] & 0xffff); }
+
+// base2int (subread.h:238) on a *signed* char, as genekey2int passes it (input-files.c:1241).
+SR_HD int base_code(int c /* sign-extended char */) { return c < 'G' ? (c == 'A' ? 0 : 2) : (c == 'G' ? 1 : 3); }
+
+// Characters the reverse-complement table (input-files.c:1111) maps to a base rather than 'N'.
+SR_HD bool is_table_base(int c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'U'; }
+
+// 2-bit code of reverse_read(c) (input-files.c:1171-1186): A<->T, C<->G, U->A, others -> 'N' -> 3.
+SR_HD int rc_code(int c) { return is_table_base(c) ? 3 - base_code(c) : 3; }
+
+// 2-bit code of reverse_read(reverse_read(c)): bases keep their code ('U' becomes 'T', code 3
+// either way), everything else has become 'N' -> 3.
+SR_HD int rcrc_code(int c) { return is_table_base(c) ? base_code(c) : 3; }
+
+// _index_vote_tol, sorted-hashtable.c:347
+SR_HD uint32_t vote_row(uint32_t kv) { return (kv / kSeg) % kVoteRows; }
+
+// Subread schedule of do_voting (core.c:3117-3130).  Returns applied_subreads and the 16.16 step.
+SR_HD int subread_schedule(int rlen, int gap, int total_subreads, int *step_out)
+{
+	int cr15 = (rlen - 15 - gap) * 65536;
+	int step;
+	if (rlen <= kLongRead) {
+		step = cr15 / (total_subreads - 1);
+		if (step < gap * 65536) step = gap * 65536;
+	} else {
+		step = 6 * 65536;
+		if (cr15 / step > 62) step = cr15 / 62;
+	}
+	*step_out = step;
+	return 1 + cr15 / step;
+}
+
+// Offset of lookup l = subread_no * gap + xk1 (core.c:3169-3171).
+SR_HD int lookup_offset(int l, int gap, int step)
+{
+	int s = l / gap, x = l - s * gap;
+	int o = (step * s) >> 16;
+	if (gap > 1) o -= o % gap - x;
+	return o;
+}
+
+// locate_gene_position_max with NULL cuts and rl 0 (gene-algorithms.c:441-510): 0 when `linear`
+// lies inside a chromosome body; then *chr is the chromosome number and *pos the 0-based offset.
+SR_HD int locate_position(const uint32_t *offs, int total, int padding, uint32_t linear, int *chr, int *pos)
+{
+	int n, lo = 0, hi = total;
+	*chr = -1;
+	*pos = -1;
+	for (;;) {
+		if (hi <= lo + 1) { n = lo - 2 > 0 ? lo - 2 : 0; break; }
+		int mid = (lo + hi) / 2;
+		if (offs[mid] > linear) hi = mid; else lo = mid + 1;
+	}
+	for (; n < total; n++) {
+		uint32_t end = offs[n];
+		if (end > linear) {
+			int p = (int)(n == 0 ? linear : linear - offs[n - 1]);
+			*pos = p;
+			if (linear > end + 15 - (uint32_t)padding) return 1;
+			if (p < padding) return 1;
+			*pos = p - padding;
+			*chr = n;
+			return 0;
+		}
+	}
+	return -1;
+}
+
+// test_PE_and_same_chro (core.c:4819-4845) on pre-located mates.  Returns the pair weight of
+// core-junction.c:2337-2349 without annotation: 1300 proper pair, 1000 same chromosome, 800 else;
+// *is_pe tells whether the pair is within [min,max] distance.
+SR_HD int pair_weight(int re1, int chr1, int pos1, int re2, int chr2, int pos2, int rlen1, int rlen2, int min_dist,
+                      int max_dist, int *is_pe)
+{
+	*is_pe = 0;
+	if (re1 == 0 && re2 == 0 && chr1 == chr2) {
+		long long t = (long long)pos1 - pos2;
+		if (t < 0) t = -t;
+		t += pos1 > pos2 ? rlen1 : rlen2;
+		uint32_t tl = (uint32_t)t;
+		if (tl >= (uint32_t)min_dist && tl <= (uint32_t)max_dist) { *is_pe = 1; return 1300; }
+		return 1000;
+	}
+	return 800;
+}
+
+}  // namespace sr
