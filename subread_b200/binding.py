@@ -1,0 +1,218 @@
+"""ctypes binding of libsubread_cuda.so (C ABI: include/subread_cuda.h).
+
+This is the Python mirror of the drop-in boundary: a ``Mapper`` owns one ``srcuda_handle``
+(= one GPU), holds one index block resident in HBM and runs the voting step of
+``do_voting`` (reference src/core.c:3049) over chunks of reads.  There is no CPU fallback:
+if the library is not built, or no B200 is visible, construction raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from .layout import MAPPING_RESULT, VoteParams
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsubread_cuda.so")
+_LIB = None
+
+EXPORTS = [
+    "srcuda_device_count", "srcuda_open", "srcuda_close", "srcuda_last_error", "srcuda_index_load",
+    "srcuda_index_upload", "srcuda_index_replicate", "srcuda_index_describe", "srcuda_index_unload",
+    "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device",
+    "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth",
+]
+
+
+class IndexDesc(ctypes.Structure):
+    _fields_ = [
+        ("index_gap", ctypes.c_int32), ("padding", ctypes.c_int32), ("buckets_number", ctypes.c_uint32),
+        ("n_items", ctypes.c_uint64), ("start_point", ctypes.c_uint32), ("length", ctypes.c_uint32),
+        ("start_base_offset", ctypes.c_uint32), ("values_bytes", ctypes.c_uint32),
+        ("total_offsets", ctypes.c_int32), ("device_bytes", ctypes.c_uint64),
+    ]
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [
+        ("ms_total", ctypes.c_float), ("ms_kernel_vote", ctypes.c_float), ("ms_kernel_overflow", ctypes.c_float),
+        ("n_overflow", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
+        ("n_launches", ctypes.c_uint32), ("n_batches", ctypes.c_uint32),
+    ]
+
+
+def build_library(force: bool = False) -> str:
+    """Compile libsubread_cuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_PKG, "csrc")
+    if force:
+        subprocess.check_call(["make", "-C", src, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", src], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u32, u64, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64
+    L.srcuda_device_count.restype = ctypes.c_int
+    L.srcuda_open.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.srcuda_close.argtypes = [vp]
+    L.srcuda_close.restype = None
+    L.srcuda_last_error.argtypes = [vp]
+    L.srcuda_last_error.restype = ctypes.c_char_p
+    L.srcuda_index_load.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    L.srcuda_index_upload.argtypes = [vp, i32, i32, u32, u64, vp, vp, vp, u32, u32, vp, u32, vp, i32]
+    L.srcuda_index_replicate.argtypes = [vp, vp]
+    L.srcuda_index_describe.argtypes = [vp, ctypes.POINTER(IndexDesc)]
+    L.srcuda_index_unload.argtypes = [vp]
+    L.srcuda_index_unload.restype = None
+    L.srcuda_host_alloc.argtypes = [ctypes.c_size_t]
+    L.srcuda_host_alloc.restype = vp
+    L.srcuda_host_free.argtypes = [vp]
+    L.srcuda_host_free.restype = None
+    L.srcuda_vote_chunk.argtypes = [vp, ctypes.POINTER(VoteParams), vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.srcuda_vote_chunk_device.argtypes = [vp, ctypes.POINTER(VoteParams), vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.srcuda_get_timing.argtypes = [vp, ctypes.POINTER(Timing)]
+    L.srcuda_set_force_slow_path.argtypes = [vp, ctypes.c_int]
+    L.srcuda_measure_gather_bandwidth.argtypes = [vp, u64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    _LIB = L
+    return L
+
+
+class SubreadCudaError(RuntimeError):
+    pass
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (srcuda_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(np.atleast_1d(shape))
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._lib = load_library()
+        self.ptr = self._lib.srcuda_host_alloc(max(n, 1))
+        if not self.ptr:
+            raise SubreadCudaError("srcuda_host_alloc failed")
+        buf = (ctypes.c_uint8 * max(n, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.srcuda_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Mapper:
+    """One GPU, one resident index block."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.srcuda_open(device, ctypes.byref(self.h))
+        if rc:
+            raise SubreadCudaError(f"srcuda_open({device}) -> {rc}: {self.lib.srcuda_last_error(None).decode()}")
+        self.device = device
+
+    def _check(self, rc, what):
+        if rc:
+            raise SubreadCudaError(f"{what} -> {rc}: {self.lib.srcuda_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.srcuda_close(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- index -------------------------------------------------------------------------------
+    def index_load(self, prefix: str, block: int = 0):
+        self._check(self.lib.srcuda_index_load(self.h, str(prefix).encode(), block), "srcuda_index_load")
+
+    def index_upload(self, index_gap, padding, bucket_start, keys, vals, start_point, length, values, read_offsets):
+        bucket_start = np.ascontiguousarray(bucket_start, dtype=np.uint32)
+        keys = np.ascontiguousarray(keys, dtype=np.int16)
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.uint8)
+        read_offsets = np.ascontiguousarray(read_offsets, dtype=np.uint32)
+        self._check(self.lib.srcuda_index_upload(
+            self.h, int(index_gap), int(padding), bucket_start.shape[0] - 1, keys.shape[0], _ptr(bucket_start), _ptr(keys),
+            _ptr(vals), int(start_point), int(length), _ptr(values), values.shape[0], _ptr(read_offsets),
+            read_offsets.shape[0]), "srcuda_index_upload")
+
+    def index_replicate_from(self, other: "Mapper"):
+        self._check(self.lib.srcuda_index_replicate(self.h, other.h), "srcuda_index_replicate")
+
+    def describe(self) -> IndexDesc:
+        d = IndexDesc()
+        self._check(self.lib.srcuda_index_describe(self.h, ctypes.byref(d)), "srcuda_index_describe")
+        return d
+
+    # -- voting ------------------------------------------------------------------------------
+    def vote_chunk(self, chunk, params: VoteParams, out_align=None, want_verify=False):
+        """Host-buffer entry point (copies inside).  Returns (align[n_frags, mates, multi_best], verify|None)."""
+        mb = params.multi_best_reads
+        n = chunk.n_frags * chunk.mates * mb
+        is_zero = out_align is None
+        if out_align is None:
+            out_align = np.zeros(n, dtype=MAPPING_RESULT)
+        out_align = out_align.reshape(-1)
+        assert out_align.flags["C_CONTIGUOUS"] and out_align.shape[0] == n and out_align.dtype == MAPPING_RESULT
+        verify = np.zeros(n, dtype=np.uint16) if want_verify else None
+        text = np.ascontiguousarray(chunk.text, dtype=np.uint8)
+        off = np.ascontiguousarray(chunk.off, dtype=np.uint64)
+        ln = np.ascontiguousarray(chunk.len, dtype=np.uint16)
+        if text.shape[0] == 0:
+            text = np.zeros(1, np.uint8)
+        rc = self.lib.srcuda_vote_chunk(self.h, ctypes.byref(params), _ptr(text), _ptr(off), _ptr(ln), chunk.n_frags,
+                                        int(chunk.is_paired), int(is_zero), _ptr(out_align), None, None, _ptr(verify))
+        self._check(rc, "srcuda_vote_chunk")
+        return out_align.reshape(chunk.n_frags, chunk.mates, mb), verify
+
+    def vote_chunk_raw(self, params, text_ptr, off_ptr, len_ptr, n_frags, is_paired, out_is_zero, out_ptr, verify_ptr=None):
+        """Pointer-level call (host pointers, e.g. pinned buffers) used by bench.py's e2e timing."""
+        rc = self.lib.srcuda_vote_chunk(self.h, ctypes.byref(params), text_ptr, off_ptr, len_ptr, n_frags, int(is_paired),
+                                        int(out_is_zero), out_ptr, None, None, verify_ptr)
+        self._check(rc, "srcuda_vote_chunk")
+
+    def vote_chunk_device(self, params, d_text, d_off, d_len, n_frags, is_paired, max_read_len, d_out, d_verify=None):
+        """All pointers are device addresses on this mapper's GPU (e.g. torch tensors' data_ptr())."""
+        rc = self.lib.srcuda_vote_chunk_device(self.h, ctypes.byref(params), d_text, d_off, d_len, n_frags, int(is_paired),
+                                               int(max_read_len), d_out, None, None, d_verify)
+        self._check(rc, "srcuda_vote_chunk_device")
+
+    def timing(self) -> Timing:
+        t = Timing()
+        self.lib.srcuda_get_timing(self.h, ctypes.byref(t))
+        return t
+
+    def set_force_slow_path(self, on: bool):
+        self.lib.srcuda_set_force_slow_path(self.h, int(bool(on)))
+
+    def gather_bandwidth(self, table_bytes: int, iters: int = 3) -> float:
+        out = ctypes.c_double()
+        self._check(self.lib.srcuda_measure_gather_bandwidth(self.h, int(table_bytes), iters, ctypes.byref(out)),
+                    "srcuda_measure_gather_bandwidth")
+        return out.value

@@ -1,0 +1,677 @@
+// sr_api.cu -- libsubread_cuda.so: kernels' launchers and the C ABI of include/subread_cuda.h.
+//
+// Data layout in HBM (one index block, resident for the life of the handle):
+//   bucket_start u32[buckets+1] | keys i16[items] | vals u32[items] | genome 2-bit (u32 words) |
+//   chr_offsets u32[chromosomes]
+// Per chunk batch (double-buffered on two streams so that H2D, kernels and D2H overlap):
+//   text u8[...] | off u64[reads] | len u16[reads] | out 68 B x reads x 3 | verify u16 x reads x 3 |
+//   overflow queue u32[frags] + counter
+#include "../../include/subread_cuda.h"
+#include "sr_config.h"
+#include "sr_index.h"
+#include "sr_scalar.cuh"
+#include "sr_warp.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace sr {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kScalarThreads = 32;
+constexpr int kScalarBlocksPerSM = 1;
+
+// ------------------------------------------------------------------------------------ kernels
+
+struct ChunkArgs {
+	const uint8_t *text;       // device
+	uint64_t text_origin;      // off[] values are relative to this
+	uint64_t text_bytes;       // bytes available at `text`
+	const uint64_t *off;       // device, per read of this launch
+	const uint16_t *len;       // device
+	int64_t n_frags;
+	ResultWords *out;          // device, [frag][mate][multi_best]
+	uint16_t *verify;          // device or null
+	uint32_t *queue;           // overflow queue
+	uint32_t *queue_count;
+	uint32_t *bad_reads;       // counter of reads whose (off,len) fall outside the text buffer
+};
+
+template <int MATES>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_words, int chars_stride, int warp_bytes)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint8_t *mine = smem + (size_t)warp * warp_bytes;
+	WarpShared<MATES> &ws = *reinterpret_cast<WarpShared<MATES> *>(mine);
+	uint32_t *packed = reinterpret_cast<uint32_t *>(mine + ((sizeof(WarpShared<MATES>) + 15) & ~size_t(15)));
+	uint8_t *chars = reinterpret_cast<uint8_t *>(packed + MATES * 3 * n_words);
+	const int mb = cfg.multi_best_reads;
+
+	for (int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + warp; f < a.n_frags; f += (int64_t)gridDim.x * kWarpsPerBlock) {
+		const int64_t r0 = f * MATES;
+		const uint64_t o0 = a.off[r0] - a.text_origin;
+		const int l0 = a.len[r0];
+		uint64_t o1 = 0;
+		int l1 = 0;
+		bool bad = o0 + (uint64_t)l0 > a.text_bytes || l0 > kMaxReadLen;
+		if (MATES == 2) {
+			o1 = a.off[r0 + 1] - a.text_origin;
+			l1 = a.len[r0 + 1];
+			bad = bad || o1 + (uint64_t)l1 > a.text_bytes || l1 > kMaxReadLen;
+		}
+		if (bad) {
+			if (lane == 0) atomicAdd(a.bad_reads, 1u);
+			continue;
+		}
+		bool ok = map_fragment<MATES>(ix, cfg, ws, chars, chars_stride, packed, n_words, a.text + o0, l0, a.text + o1, l1,
+		                              a.out + (size_t)f * MATES * mb, a.verify ? a.verify + (size_t)f * MATES * mb : nullptr, lane);
+		if (!ok && lane == 0) a.queue[atomicAdd(a.queue_count, 1u)] = (uint32_t)f;
+		__syncwarp();
+	}
+}
+
+// Exact slow path: one thread per queued fragment (or per fragment when use_queue == 0).
+__global__ void __launch_bounds__(kScalarThreads)
+k_map_scalar(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int use_queue, ScalarScratch *scratch)
+{
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+	const int mates = 1 + cfg.is_paired, mb = cfg.multi_best_reads;
+	const int64_t n = use_queue ? (int64_t)*a.queue_count : a.n_frags;
+	for (int64_t i = tid; i < n; i += nthreads) {
+		const int64_t f = use_queue ? (int64_t)a.queue[i] : i;
+		const int64_t r0 = f * mates;
+		const uint64_t o0 = a.off[r0] - a.text_origin;
+		const int l0 = a.len[r0];
+		uint64_t o1 = 0;
+		int l1 = 0;
+		bool bad = o0 + (uint64_t)l0 > a.text_bytes || l0 > kMaxReadLen;
+		if (mates == 2) {
+			o1 = a.off[r0 + 1] - a.text_origin;
+			l1 = a.len[r0 + 1];
+			bad = bad || o1 + (uint64_t)l1 > a.text_bytes || l1 > kMaxReadLen;
+		}
+		if (bad) {
+			if (!use_queue) atomicAdd(a.bad_reads, 1u);
+			continue;
+		}
+		scalar_vote_fragment(ix, cfg, a.text + o0, l0, a.text + o1, l1, a.out + (size_t)f * mates * mb,
+		                     a.verify ? a.verify + (size_t)f * mates * mb : nullptr, scratch + tid);
+	}
+}
+
+// Random 32-byte-sector gather: the "HBM-gather roofline" probe.
+__global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_thread, uint32_t seed, uint32_t *sink)
+{
+	uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + seed;
+	uint32_t acc = 0;
+	for (int i = 0; i < per_thread; i += 8) {
+		uint4 v[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 29;  // cheap mixer
+			uint64_t s = x % n_sectors;
+			v[u] = __ldg(table + 2 * s);
+		}
+#pragma unroll
+		for (int u = 0; u < 8; u++) acc ^= v[u].x ^ v[u].w;
+	}
+	if (acc == 0x12345678u) *sink = acc;
+}
+
+}  // namespace sr
+
+// ------------------------------------------------------------------------------------ handle
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_open_error;
+
+struct DeviceBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct BatchSet {  // one of two buffer sets; used by one stream
+	cudaStream_t stream = nullptr;
+	DeviceBuf text, off, len, out, verify, queue;
+	uint32_t *counters = nullptr;       // device: [0] queue_count, [1] bad_reads
+	uint32_t *h_counters = nullptr;     // pinned host mirror, 2 per batch slot
+	sr::ScalarScratch *scratch = nullptr;
+};
+
+}  // namespace
+
+struct srcuda_handle {
+	int device = -1;
+	int sm_count = 0;
+	mutable std::mutex mu;
+	std::string err;
+	bool has_index = false;
+	sr::DevIndex ix{};
+	srcuda_index_desc desc{};
+	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
+	size_t genome_words = 0;
+	BatchSet set[2];
+	std::vector<cudaEvent_t> events;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	srcuda_timing timing{};
+	bool force_slow = false;
+	int64_t batch_frags = 1 << 20;
+	uint32_t *d_sink = nullptr;
+};
+
+namespace {
+
+int fail(srcuda_handle *h, int code, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (h) {
+		std::lock_guard<std::mutex> g(h->mu);
+		h->err = buf;
+	} else {
+		std::lock_guard<std::mutex> g(g_err_mutex);
+		g_open_error = buf;
+	}
+	return code;
+}
+
+#define CU(h, call)                                                                                        \
+	do {                                                                                                   \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess) return fail(h, SRCUDA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+int ensure(srcuda_handle *h, DeviceBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap) return 0;
+	if (b.p) {
+		CU(h, cudaDeviceSynchronize());
+		CU(h, cudaFree(b.p));
+		b.p = nullptr;
+		b.cap = 0;
+	}
+	size_t want = bytes + bytes / 8 + 256;
+	CU(h, cudaMalloc(&b.p, want));
+	b.cap = want;
+	return 0;
+}
+
+void free_index(srcuda_handle *h)
+{
+	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr);
+	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = nullptr;
+	h->has_index = false;
+	memset(&h->ix, 0, sizeof(h->ix));
+	memset(&h->desc, 0, sizeof(h->desc));
+}
+
+int upload_index(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t nb, uint64_t n_items, const uint32_t *bucket_start,
+                 const int16_t *keys, const uint32_t *vals, uint32_t start_point, uint32_t length, const uint8_t *values,
+                 uint32_t values_bytes, const uint32_t *read_offsets, int32_t total_offsets)
+{
+	if (!bucket_start || !keys || !vals || !values || !read_offsets || nb < 1 || total_offsets < 1)
+		return fail(h, SRCUDA_ERR_ARG, "srcuda_index_upload: null array or empty table");
+	if (index_gap < 1 || index_gap > 3) return fail(h, SRCUDA_ERR_UNSUPPORTED, "index gap %d not in 1..3", index_gap);
+	if (bucket_start[nb] != (uint32_t)n_items) return fail(h, SRCUDA_ERR_ARG, "bucket_start[buckets] != n_items");
+	CU(h, cudaSetDevice(h->device));
+	free_index(h);
+	size_t gw = ((size_t)values_bytes + 3) / 4 + 8;  // +8 words so funnel shifts may read one word ahead
+	CU(h, cudaMalloc(&h->d_bucket_start, sizeof(uint32_t) * ((size_t)nb + 1)));
+	CU(h, cudaMalloc(&h->d_keys, sizeof(int16_t) * (size_t)n_items + 64));
+	CU(h, cudaMalloc(&h->d_vals, sizeof(uint32_t) * (size_t)n_items + 64));
+	CU(h, cudaMalloc(&h->d_genome, sizeof(uint32_t) * gw));
+	CU(h, cudaMalloc(&h->d_chr, sizeof(uint32_t) * (size_t)total_offsets));
+	CU(h, cudaMemcpy(h->d_bucket_start, bucket_start, sizeof(uint32_t) * ((size_t)nb + 1), cudaMemcpyHostToDevice));
+	CU(h, cudaMemcpy(h->d_keys, keys, sizeof(int16_t) * (size_t)n_items, cudaMemcpyHostToDevice));
+	CU(h, cudaMemcpy(h->d_vals, vals, sizeof(uint32_t) * (size_t)n_items, cudaMemcpyHostToDevice));
+	CU(h, cudaMemset(h->d_genome, 0, sizeof(uint32_t) * gw));
+	CU(h, cudaMemcpy(h->d_genome, values, values_bytes, cudaMemcpyHostToDevice));
+	CU(h, cudaMemcpy(h->d_chr, read_offsets, sizeof(uint32_t) * (size_t)total_offsets, cudaMemcpyHostToDevice));
+	h->genome_words = gw;
+	sr::DevIndex &ix = h->ix;
+	ix.buckets_number = nb; ix.index_gap = index_gap; ix.padding = padding;
+	ix.start_point = start_point; ix.length = length; ix.start_base_offset = start_point - start_point % 4;
+	ix.values_bytes = values_bytes; ix.total_offsets = total_offsets;
+	ix.bucket_start = (const uint32_t *)h->d_bucket_start; ix.keys = (const int16_t *)h->d_keys;
+	ix.vals = (const uint32_t *)h->d_vals; ix.genome = (const uint32_t *)h->d_genome; ix.chr_offsets = (const uint32_t *)h->d_chr;
+	srcuda_index_desc &d = h->desc;
+	d.index_gap = index_gap; d.padding = padding; d.buckets_number = nb; d.n_items = n_items;
+	d.start_point = start_point; d.length = length; d.start_base_offset = ix.start_base_offset; d.values_bytes = values_bytes;
+	d.total_offsets = total_offsets;
+	d.device_bytes = sizeof(uint32_t) * ((uint64_t)nb + 1) + 6 * n_items + sizeof(uint32_t) * gw + sizeof(uint32_t) * (uint64_t)total_offsets;
+	h->has_index = true;
+	return SRCUDA_OK;
+}
+
+struct LaunchPlan {
+	int n_words, chars_stride, warp_bytes, smem_bytes, grid;
+};
+
+template <int MATES>
+int plan_warp_launch(srcuda_handle *h, int max_len, LaunchPlan *p)
+{
+	p->n_words = (max_len + 15) / 16 + 1;
+	p->chars_stride = (max_len + 15) & ~15;
+	size_t wb = ((sizeof(sr::WarpShared<MATES>) + 15) & ~size_t(15)) + (size_t)MATES * 3 * p->n_words * 4 + (size_t)MATES * p->chars_stride;
+	p->warp_bytes = (int)((wb + 15) & ~size_t(15));
+	p->smem_bytes = p->warp_bytes * sr::kWarpsPerBlock;
+	if (p->smem_bytes > 227 * 1024) return fail(h, SRCUDA_ERR_UNSUPPORTED, "shared memory plan %d B exceeds 227 KB", p->smem_bytes);
+	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+	int per_sm = 0;
+	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES>, sr::kWarpsPerBlock * 32, p->smem_bytes));
+	if (per_sm < 1) return fail(h, SRCUDA_ERR_CUDA, "warp kernel does not fit on an SM");
+	p->grid = h->sm_count * per_sm;  // persistent grid: a whole number of resident waves
+	return 0;
+}
+
+// Enqueue the kernels of one launch on `s`.  ev[0..3] (optional) bracket warp and scalar kernels.
+int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len, BatchSet &bs,
+                cudaEvent_t *ev)
+{
+	const int scalar_grid = h->sm_count * sr::kScalarBlocksPerSM;
+	if (!bs.scratch)
+		CU(h, cudaMalloc((void **)&bs.scratch, sizeof(sr::ScalarScratch) * (size_t)scalar_grid * sr::kScalarThreads));
+	if (ev) CU(h, cudaEventRecord(ev[0], s));
+	if (!h->force_slow) {
+		LaunchPlan p;
+		int rc = cfg.is_paired ? plan_warp_launch<2>(h, max_len, &p) : plan_warp_launch<1>(h, max_len, &p);
+		if (rc) return rc;
+		int64_t blocks_needed = (a.n_frags + sr::kWarpsPerBlock - 1) / sr::kWarpsPerBlock;
+		int grid = (int)std::min<int64_t>(p.grid, std::max<int64_t>(blocks_needed, 1));
+		if (cfg.is_paired)
+			sr::k_map_warp<2><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.chars_stride, p.warp_bytes);
+		else
+			sr::k_map_warp<1><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.chars_stride, p.warp_bytes);
+		CU(h, cudaGetLastError());
+		h->timing.n_launches++;
+	}
+	if (ev) CU(h, cudaEventRecord(ev[1], s));
+	sr::k_map_scalar<<<scalar_grid, sr::kScalarThreads, 0, s>>>(h->ix, cfg, a, h->force_slow ? 0 : 1, bs.scratch);
+	CU(h, cudaGetLastError());
+	h->timing.n_launches++;
+	if (ev) CU(h, cudaEventRecord(ev[2], s));
+	return 0;
+}
+
+int init_sets(srcuda_handle *h)
+{
+	for (int i = 0; i < 2; i++) {
+		BatchSet &b = h->set[i];
+		if (b.stream) continue;
+		CU(h, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+		CU(h, cudaMalloc((void **)&b.counters, 2 * sizeof(uint32_t)));
+	}
+	if (!h->ev_begin) {
+		CU(h, cudaEventCreate(&h->ev_begin));
+		CU(h, cudaEventCreate(&h->ev_end));
+	}
+	return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int srcuda_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int srcuda_open(int device, srcuda_handle **out)
+{
+	if (!out) return fail(nullptr, SRCUDA_ERR_ARG, "srcuda_open: out is NULL");
+	*out = nullptr;
+	int n = srcuda_device_count();
+	if (n < 1) return fail(nullptr, SRCUDA_ERR_NO_DEVICE, "no CUDA device is visible (there is no CPU fallback)");
+	if (device < 0 || device >= n) return fail(nullptr, SRCUDA_ERR_ARG, "device %d out of range 0..%d", device, n - 1);
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, SRCUDA_ERR_CUDA, "cudaGetDeviceProperties failed");
+	if (prop.major < 10) return fail(nullptr, SRCUDA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+	srcuda_handle *h = new srcuda_handle();
+	h->device = device;
+	h->sm_count = prop.multiProcessorCount;
+	if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SRCUDA_ERR_CUDA, "cudaSetDevice(%d) failed", device); }
+	const char *bf = getenv("SRCUDA_BATCH_FRAGS");
+	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
+	*out = h;
+	return SRCUDA_OK;
+}
+
+void srcuda_close(srcuda_handle *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	cudaDeviceSynchronize();
+	free_index(h);
+	for (int i = 0; i < 2; i++) {
+		BatchSet &b = h->set[i];
+		for (DeviceBuf *d : {&b.text, &b.off, &b.len, &b.out, &b.verify, &b.queue}) cudaFree(d->p);
+		cudaFree(b.counters);
+		cudaFree(b.scratch);
+		if (b.h_counters) cudaFreeHost(b.h_counters);
+		if (b.stream) cudaStreamDestroy(b.stream);
+	}
+	for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+	if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+	if (h->ev_end) cudaEventDestroy(h->ev_end);
+	cudaFree(h->d_sink);
+	delete h;
+}
+
+const char *srcuda_last_error(const srcuda_handle *h)
+{
+	if (!h) {
+		std::lock_guard<std::mutex> g(g_err_mutex);
+		static thread_local std::string copy;
+		copy = g_open_error;
+		return copy.c_str();
+	}
+	std::lock_guard<std::mutex> g(h->mu);
+	static thread_local std::string copy;
+	copy = h->err;
+	return copy.c_str();
+}
+
+int srcuda_index_load(srcuda_handle *h, const char *index_prefix, int block_no)
+{
+	if (!h || !index_prefix) return fail(h, SRCUDA_ERR_ARG, "srcuda_index_load: null argument");
+	CU(h, cudaSetDevice(h->device));
+	sr::HostIndex hi;
+	std::string err;
+	int rc = sr::load_index_block(index_prefix, block_no, &hi, &err);
+	if (rc) return fail(h, rc, "%s", err.c_str());
+	return upload_index(h, hi.index_gap, hi.padding, hi.buckets_number, hi.n_items, hi.bucket_start, hi.keys, hi.vals, hi.start_point,
+	                    hi.length, hi.values.data(), hi.values_bytes, hi.read_offsets.data(), (int32_t)hi.read_offsets.size());
+}
+
+int srcuda_index_upload(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t buckets_number, uint64_t n_items,
+                        const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t start_point, uint32_t length,
+                        const uint8_t *values, uint32_t values_bytes, const uint32_t *read_offsets, int32_t total_offsets)
+{
+	if (!h) return fail(h, SRCUDA_ERR_ARG, "srcuda_index_upload: null handle");
+	return upload_index(h, index_gap, padding, buckets_number, n_items, bucket_start, keys, vals, start_point, length, values,
+	                    values_bytes, read_offsets, total_offsets);
+}
+
+int srcuda_index_replicate(srcuda_handle *dst, const srcuda_handle *src)
+{
+	if (!dst || !src) return fail(dst, SRCUDA_ERR_ARG, "srcuda_index_replicate: null handle");
+	if (!src->has_index) return fail(dst, SRCUDA_ERR_NO_INDEX, "source handle holds no index");
+	CU(dst, cudaSetDevice(dst->device));
+	free_index(dst);
+	const srcuda_index_desc &d = src->desc;
+	size_t nb1 = sizeof(uint32_t) * ((size_t)d.buckets_number + 1), nk = sizeof(int16_t) * (size_t)d.n_items,
+	       nv = sizeof(uint32_t) * (size_t)d.n_items, ng = sizeof(uint32_t) * src->genome_words,
+	       nc = sizeof(uint32_t) * (size_t)d.total_offsets;
+	int can = 0;
+	if (dst->device != src->device) {
+		cudaDeviceCanAccessPeer(&can, dst->device, src->device);
+		if (can) {
+			cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+			cudaGetLastError();
+		}
+	}
+	CU(dst, cudaMalloc(&dst->d_bucket_start, nb1));
+	CU(dst, cudaMalloc(&dst->d_keys, nk + 64));
+	CU(dst, cudaMalloc(&dst->d_vals, nv + 64));
+	CU(dst, cudaMalloc(&dst->d_genome, ng));
+	CU(dst, cudaMalloc(&dst->d_chr, nc));
+	// cudaMemcpyPeer goes over NVLink when peer access is possible and stages through the host otherwise
+	CU(dst, cudaMemcpyPeer(dst->d_bucket_start, dst->device, src->d_bucket_start, src->device, nb1));
+	CU(dst, cudaMemcpyPeer(dst->d_keys, dst->device, src->d_keys, src->device, nk));
+	CU(dst, cudaMemcpyPeer(dst->d_vals, dst->device, src->d_vals, src->device, nv));
+	CU(dst, cudaMemcpyPeer(dst->d_genome, dst->device, src->d_genome, src->device, ng));
+	CU(dst, cudaMemcpyPeer(dst->d_chr, dst->device, src->d_chr, src->device, nc));
+	dst->genome_words = src->genome_words;
+	dst->ix = src->ix;
+	dst->ix.bucket_start = (const uint32_t *)dst->d_bucket_start; dst->ix.keys = (const int16_t *)dst->d_keys;
+	dst->ix.vals = (const uint32_t *)dst->d_vals; dst->ix.genome = (const uint32_t *)dst->d_genome;
+	dst->ix.chr_offsets = (const uint32_t *)dst->d_chr;
+	dst->desc = src->desc;
+	dst->has_index = true;
+	return SRCUDA_OK;
+}
+
+int srcuda_index_describe(const srcuda_handle *h, srcuda_index_desc *out)
+{
+	if (!h || !out) return SRCUDA_ERR_ARG;
+	if (!h->has_index) return SRCUDA_ERR_NO_INDEX;
+	*out = h->desc;
+	return SRCUDA_OK;
+}
+
+void srcuda_index_unload(srcuda_handle *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	cudaDeviceSynchronize();
+	free_index(h);
+}
+
+void *srcuda_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+void srcuda_host_free(void *p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+int srcuda_set_force_slow_path(srcuda_handle *h, int on)
+{
+	if (!h) return SRCUDA_ERR_ARG;
+	h->force_slow = on != 0;
+	return SRCUDA_OK;
+}
+
+int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out)
+{
+	if (!h || !out) return SRCUDA_ERR_ARG;
+	*out = h->timing;
+	return SRCUDA_OK;
+}
+
+int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, const char *d_text, const uint64_t *d_off,
+                             const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len,
+                             srcuda_mapping_result *d_out_align, srcuda_subjunc_result *d_out_junc, uint16_t *d_out_big_margin,
+                             uint16_t *d_out_verify)
+{
+	(void)d_out_junc; (void)d_out_big_margin;
+	if (!h || !params || !d_text || !d_off || !d_len || !d_out_align) return fail(h, SRCUDA_ERR_ARG, "srcuda_vote_chunk_device: null argument");
+	if (!h->has_index) return fail(h, SRCUDA_ERR_NO_INDEX, "no index block is loaded");
+	if (n_frags < 0 || n_frags > 0x7fffffffLL) return fail(h, SRCUDA_ERR_ARG, "n_frags %lld out of range", (long long)n_frags);
+	if (max_read_len < 1 || max_read_len > sr::kMaxReadLen) return fail(h, SRCUDA_ERR_ARG, "max_read_len %d not in 1..%d", max_read_len, sr::kMaxReadLen);
+	CU(h, cudaSetDevice(h->device));
+	sr::VoteConfig cfg;
+	char msg[256];
+	int rc = sr::make_vote_config(*params, is_paired, h->ix.index_gap, h->ix.start_base_offset, h->ix.length, &cfg, msg, sizeof(msg));
+	if (rc) return fail(h, rc, "%s", msg);
+	rc = init_sets(h);
+	if (rc) return rc;
+	memset(&h->timing, 0, sizeof(h->timing));
+	if (n_frags == 0) return SRCUDA_OK;
+	BatchSet &bs = h->set[0];
+	rc = ensure(h, bs.queue, sizeof(uint32_t) * (size_t)n_frags);
+	if (rc) return rc;
+	if (h->events.size() < 3) {
+		while (h->events.size() < 3) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
+	}
+	CU(h, cudaMemsetAsync(bs.counters, 0, 2 * sizeof(uint32_t), bs.stream));
+	sr::ChunkArgs a;
+	a.text = (const uint8_t *)d_text; a.text_origin = 0; a.text_bytes = ~0ull >> 1;
+	a.off = d_off; a.len = d_len; a.n_frags = n_frags;
+	a.out = (sr::ResultWords *)d_out_align; a.verify = d_out_verify;
+	a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
+	rc = launch_vote(h, bs.stream, cfg, a, max_read_len, bs, h->events.data());
+	if (rc) return rc;
+	uint32_t counters[2] = {0, 0};
+	CU(h, cudaMemcpyAsync(counters, bs.counters, sizeof(counters), cudaMemcpyDeviceToHost, bs.stream));
+	CU(h, cudaStreamSynchronize(bs.stream));
+	float ms = 0;
+	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[1]));
+	h->timing.ms_kernel_vote = ms;
+	CU(h, cudaEventElapsedTime(&ms, h->events[1], h->events[2]));
+	h->timing.ms_kernel_overflow = ms;
+	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[2]));
+	h->timing.ms_total = ms;
+	h->timing.n_overflow = h->force_slow ? (uint64_t)n_frags : counters[0];
+	h->timing.n_batches = 1;
+	if (counters[1]) return fail(h, SRCUDA_ERR_ARG, "%u reads have (off,len) outside the text buffer or len > %d", counters[1], sr::kMaxReadLen);
+	return SRCUDA_OK;
+}
+
+int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char *text, const uint64_t *off, const uint16_t *len,
+                      int64_t n_frags, int is_paired, int out_align_is_zero, srcuda_mapping_result *out_align,
+                      srcuda_subjunc_result *out_junc, uint16_t *out_big_margin, uint16_t *out_verify)
+{
+	(void)out_junc; (void)out_big_margin;
+	if (!h || !params || !text || !off || !len || !out_align) return fail(h, SRCUDA_ERR_ARG, "srcuda_vote_chunk: null argument");
+	if (!h->has_index) return fail(h, SRCUDA_ERR_NO_INDEX, "no index block is loaded");
+	if (n_frags < 0) return fail(h, SRCUDA_ERR_ARG, "n_frags < 0");
+	CU(h, cudaSetDevice(h->device));
+	sr::VoteConfig cfg;
+	char msg[256];
+	int rc = sr::make_vote_config(*params, is_paired, h->ix.index_gap, h->ix.start_base_offset, h->ix.length, &cfg, msg, sizeof(msg));
+	if (rc) return fail(h, rc, "%s", msg);
+	rc = init_sets(h);
+	if (rc) return rc;
+	memset(&h->timing, 0, sizeof(h->timing));
+	if (n_frags == 0) return SRCUDA_OK;
+
+	const int mates = 1 + (is_paired ? 1 : 0), mb = cfg.multi_best_reads;
+	const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->batch_frags, 0x7fffffffLL));
+	const int64_t n_batches = (n_frags + batch - 1) / batch;
+	while ((int64_t)h->events.size() < 3 * n_batches) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
+	for (int i = 0; i < 2; i++) {
+		BatchSet &b = h->set[i];
+		size_t need = sizeof(uint32_t) * 2 * (size_t)((n_batches + 1) / 2 + 1);
+		if (b.h_counters) { cudaFreeHost(b.h_counters); b.h_counters = nullptr; }
+		CU(h, cudaHostAlloc((void **)&b.h_counters, need, cudaHostAllocDefault));
+		memset(b.h_counters, 0, need);
+	}
+
+	CU(h, cudaEventRecord(h->ev_begin, h->set[0].stream));
+	CU(h, cudaStreamWaitEvent(h->set[1].stream, h->ev_begin, 0));
+	for (int64_t bi = 0; bi < n_batches; bi++) {
+		BatchSet &bs = h->set[bi & 1];
+		cudaStream_t s = bs.stream;
+		const int64_t f0 = bi * batch, f1 = std::min(n_frags, f0 + batch), nf = f1 - f0;
+		const int64_t r0 = f0 * mates, nr = nf * mates;
+		// the batch's reads must lie in text[off[r0] .. off[last]+len[last]) -- offsets non-decreasing
+		int max_len = 1;
+		for (int64_t r = r0; r < r0 + nr; r++) max_len = std::max<int>(max_len, len[r]);
+		if (max_len > sr::kMaxReadLen) return fail(h, SRCUDA_ERR_ARG, "a read is longer than %d", sr::kMaxReadLen);
+		const uint64_t origin = off[r0];
+		const uint64_t text_bytes = off[r0 + nr - 1] + len[r0 + nr - 1] - origin;
+		if (off[r0 + nr - 1] < origin) return fail(h, SRCUDA_ERR_ARG, "read offsets must be non-decreasing");
+		const size_t n_slots = (size_t)nr * mb;
+		if ((rc = ensure(h, bs.text, text_bytes + 16))) return rc;
+		if ((rc = ensure(h, bs.off, sizeof(uint64_t) * (size_t)nr))) return rc;
+		if ((rc = ensure(h, bs.len, sizeof(uint16_t) * (size_t)nr))) return rc;
+		if ((rc = ensure(h, bs.out, sizeof(srcuda_mapping_result) * n_slots))) return rc;
+		if ((rc = ensure(h, bs.queue, sizeof(uint32_t) * (size_t)nf))) return rc;
+		if (out_verify && (rc = ensure(h, bs.verify, sizeof(uint16_t) * n_slots))) return rc;
+
+		CU(h, cudaMemcpyAsync(bs.text.p, text + origin, text_bytes, cudaMemcpyHostToDevice, s));
+		CU(h, cudaMemcpyAsync(bs.off.p, off + r0, sizeof(uint64_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
+		CU(h, cudaMemcpyAsync(bs.len.p, len + r0, sizeof(uint16_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
+		h->timing.h2d_bytes += text_bytes + 10 * (uint64_t)nr;
+		if (out_align_is_zero) {
+			CU(h, cudaMemsetAsync(bs.out.p, 0, sizeof(srcuda_mapping_result) * n_slots, s));
+		} else {
+			CU(h, cudaMemcpyAsync(bs.out.p, out_align + (size_t)r0 * mb, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyHostToDevice, s));
+			h->timing.h2d_bytes += sizeof(srcuda_mapping_result) * n_slots;
+		}
+		CU(h, cudaMemsetAsync(bs.counters, 0, 2 * sizeof(uint32_t), s));
+		sr::ChunkArgs a;
+		a.text = (const uint8_t *)bs.text.p; a.text_origin = origin; a.text_bytes = text_bytes;
+		a.off = (const uint64_t *)bs.off.p; a.len = (const uint16_t *)bs.len.p; a.n_frags = nf;
+		a.out = (sr::ResultWords *)bs.out.p; a.verify = out_verify ? (uint16_t *)bs.verify.p : nullptr;
+		a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
+		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[3 * bi]))) return rc;
+		CU(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
+		h->timing.d2h_bytes += sizeof(srcuda_mapping_result) * n_slots;
+		if (out_verify) {
+			CU(h, cudaMemcpyAsync(out_verify + (size_t)r0 * mb, bs.verify.p, sizeof(uint16_t) * n_slots, cudaMemcpyDeviceToHost, s));
+			h->timing.d2h_bytes += sizeof(uint16_t) * n_slots;
+		}
+		CU(h, cudaMemcpyAsync(bs.h_counters + 2 * (bi / 2), bs.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	}
+	CU(h, cudaEventRecord(h->ev_end, h->set[1].stream));
+	CU(h, cudaStreamWaitEvent(h->set[0].stream, h->ev_end, 0));
+	CU(h, cudaEventRecord(h->ev_end, h->set[0].stream));
+	CU(h, cudaStreamSynchronize(h->set[0].stream));
+	CU(h, cudaStreamSynchronize(h->set[1].stream));
+
+	float ms = 0;
+	CU(h, cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end));
+	h->timing.ms_total = ms;
+	uint64_t bad = 0;
+	for (int64_t bi = 0; bi < n_batches; bi++) {
+		CU(h, cudaEventElapsedTime(&ms, h->events[3 * bi], h->events[3 * bi + 1]));
+		h->timing.ms_kernel_vote += ms;
+		CU(h, cudaEventElapsedTime(&ms, h->events[3 * bi + 1], h->events[3 * bi + 2]));
+		h->timing.ms_kernel_overflow += ms;
+		const uint32_t *c = h->set[bi & 1].h_counters + 2 * (bi / 2);
+		h->timing.n_overflow += h->force_slow ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
+		bad += c[1];
+	}
+	h->timing.n_batches = (uint32_t)n_batches;
+	if (bad) return fail(h, SRCUDA_ERR_ARG, "%llu reads have (off,len) outside the text buffer", (unsigned long long)bad);
+	return SRCUDA_OK;
+}
+
+int srcuda_measure_gather_bandwidth(srcuda_handle *h, uint64_t table_bytes, int iters, double *gbps_out)
+{
+	if (!h || !gbps_out || table_bytes < (1u << 20)) return fail(h, SRCUDA_ERR_ARG, "srcuda_measure_gather_bandwidth: bad argument");
+	CU(h, cudaSetDevice(h->device));
+	void *table = nullptr;
+	CU(h, cudaMalloc(&table, table_bytes));
+	CU(h, cudaMemset(table, 1, table_bytes));
+	if (!h->d_sink) CU(h, cudaMalloc((void **)&h->d_sink, 4));
+	const int threads = 256, blocks = h->sm_count * 8, per_thread = 256;
+	const uint64_t n_sectors = table_bytes / 32;
+	cudaEvent_t e0, e1;
+	CU(h, cudaEventCreate(&e0));
+	CU(h, cudaEventCreate(&e1));
+	double best = 0;
+	for (int it = 0; it < std::max(1, iters) + 1; it++) {
+		CU(h, cudaEventRecord(e0, 0));
+		sr::k_gather_probe<<<blocks, threads>>>((const uint4 *)table, n_sectors, per_thread, 1234u + it, h->d_sink);
+		CU(h, cudaEventRecord(e1, 0));
+		CU(h, cudaEventSynchronize(e1));
+		float ms = 0;
+		CU(h, cudaEventElapsedTime(&ms, e0, e1));
+		double gbps = 32.0 * blocks * threads * per_thread / (ms * 1e-3) / 1e9;
+		if (it > 0 && gbps > best) best = gbps;  // first iteration is the warm-up
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(table);
+	*gbps_out = best;
+	return SRCUDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,611 @@
+// sr_warp.cuh -- the fused seed-and-vote kernel body: one warp maps one fragment.
+//
+//   pack      ASCII -> 2-bit codes for both strand passes (genekey2int / reverse_read semantics,
+//             input-files.c:1232,1113), staged in shared memory
+//   lookup    lane l owns lookup l of the subread schedule (core.c:3117-3171): bucket header
+//             gather, the reference's own (imin+imax)/2 search over the sorted int16 keys and the
+//             equal-key run (sorted-hashtable.c:947-981,1109-1119) -- up to 32 gathers in flight
+//             per warp, all from HBM-resident SoA arrays
+//   vote      the compact vote table lives in shared memory, slot s owned by lane s; every hit is
+//             broadcast and matched by all lanes at once, the first *accepting* slot in the
+//             reference's probe order is elected with __reduce_min_sync, so the sequential
+//             semantics of gehash_go_X (sorted-hashtable.c:984-1107) are reproduced exactly
+//   top-K     process_voting_junction_PE_topK (core-junction.c:2199-2530) with warp reductions;
+//             pair combinations are scored lane-parallel
+//   verify    XOR + __popc of packed read vs packed genome (match_chro, gene-value-index.c:856)
+//
+// A table that needs a 33rd slot sets `overflow`; the fragment is then finished by the exact
+// scalar path (sr_scalar.cuh) and nothing of it is written here.
+#pragma once
+#include "sr_common.cuh"
+
+namespace sr {
+
+constexpr int kWarpSlots = 32;
+constexpr int kRecStride = 22;   // int16 per slot; 11 words -> odd stride, conflict-free
+constexpr int kMaxCand = 40;     // <= 32 slots + 3 old results per mate (SE/PE alike)
+constexpr unsigned kFull = 0xffffffffu;
+
+struct WarpTable {  // one (mate) vote table, slot s <-> lane s
+	uint32_t pos[kWarpSlots];
+	int16_t votes[kWarpSlots];
+	int16_t last_cluster[kWarpSlots];
+	int16_t cov_start[kWarpSlots];
+	int16_t cov_end[kWarpSlots];
+	int8_t cursor[kWarpSlots];
+	int8_t toli[kWarpSlots];
+	uint8_t row[kWarpSlots];
+	uint8_t j[kWarpSlots];
+	int16_t rec[kWarpSlots][kRecStride];
+};
+
+template <int MATES>
+struct WarpShared {
+	WarpTable tab[MATES];
+	ResultWords res[MATES][kMaxBest];
+	ResultWords tmp[MATES][kMaxBest];
+	uint32_t shift_locs[kWarpSlots];
+	uint32_t cand_pos[MATES][kMaxCand];
+	int32_t cand_lpos[MATES][kMaxCand];   // locate_position results (PE only)
+	int16_t cand_chr[MATES][kMaxCand];
+	int16_t cand_votes[MATES][kMaxCand];
+	uint8_t cand_src[MATES][kMaxCand];    // slot lane, or 32+k for old result k
+	int8_t cand_re[MATES][kMaxCand];
+	uint32_t comb[kMaxCombos];            // packed (score, r1, r2) after selection
+};
+
+struct WarpCtx {
+	int lane;
+	int nslots[2];
+	int max_vote[2];
+	bool overflow;
+};
+
+// 16-mer starting at base `o` of an MSB-first packed array (16 bases per word).
+SR_D uint32_t extract_key(const uint32_t *packed, int o)
+{
+#if defined(__CUDA_ARCH__)
+	int w = o >> 4, s = (o & 15) * 2;
+	return __funnelshift_l(packed[w + 1], packed[w], s);
+#else
+	(void)packed; (void)o; return 0;
+#endif
+}
+
+#if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
+
+// ---- pack ------------------------------------------------------------------------------------
+// arrays: [0] pass 0 (as fetched), [1] pass 1 (after reverse_read), [2] pass 1 reversed again
+// (what find_new_indels / verification see for a positive-strand hit).  n_words per array.
+__device__ __forceinline__ void pack_read(const uint8_t *chars, int L, bool fetched_reversed, uint32_t *packed, int n_words,
+                                          int lane)
+{
+	for (int k = lane; k < n_words; k += 32) {
+		uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll 4
+		for (int t = 0; t < 16; t++) {
+			int i = 16 * k + t;
+			int a = 2, b = 2, c = 2;  // beyond the read: NUL -> base2int 2
+			if (i < L) {
+				int cf = (int)(int8_t)chars[i], cr = (int)(int8_t)chars[L - 1 - i];
+				if (!fetched_reversed) { a = base_code(cf); b = rc_code(cr); c = rcrc_code(cf); }
+				else { a = rc_code(cr); b = rcrc_code(cf); c = a; }
+			}
+			int sh = 30 - 2 * t;
+			w0 |= (uint32_t)a << sh; w1 |= (uint32_t)b << sh; w2 |= (uint32_t)c << sh;
+		}
+		packed[k] = w0; packed[n_words + k] = w1; packed[2 * n_words + k] = w2;
+	}
+}
+
+// ---- one hit through the vote table ----------------------------------------------------------
+struct HitEnv {
+	int tol, ii_end, round, lane;
+	uint32_t low_border, high_border;
+};
+
+// Lane-private slot registers of the table being built (the rest of the slot is in WarpTable).
+struct SlotRegs {
+	uint32_t pos;
+	int row, j, marked;
+};
+
+__device__ __forceinline__ void vote_hit(WarpTable &T, SlotRegs &S, uint32_t *shift_locs, int &shift_n, int &nslots, int &max_vote,
+                                         bool &overflow, const HitEnv &E, uint32_t kv, int offset, int sub_p1)
+{
+	const int lane = E.lane;
+	const bool valid = lane < nslots;
+	const int d = (int)(kv - S.pos);
+	const int t = (E.round > 0 && S.marked) ? 0 : E.tol;
+	const uint32_t home = vote_row(kv);
+
+	// probe order of sorted-hashtable.c:1007: iix = 0,+5,-5,+10,-10,... ; rank = position of my row
+	int rank = 99;
+	{
+		int p = 0;
+		for (int iix = 0; iix <= E.ii_end; iix = iix > 0 ? -iix : (-iix + kSeg), p++) {
+			uint32_t r = iix ? vote_row(kv + (uint32_t)iix) : home;
+			if (rank == 99 && (uint32_t)S.row == r) rank = p;
+		}
+	}
+	bool cand = valid && d >= -t && d <= t && rank != 99;
+	const int key = rank * 32 + S.j;
+	bool accepted = false;
+
+	unsigned cm = __ballot_sync(kFull, cand);
+	while (cm) {
+		int best = __reduce_min_sync(kFull, cand ? key : 0x7fffffff);
+		bool is_w = cand && key == best;
+		int acc = 0, mk = 0, nv = 0;
+		if (is_w) {  // exactly one lane: the reference's body of :1020-1070 on its own slot
+			int toli = T.toli[lane];
+			if (E.round == 0 && toli > 0 && d == 0 && !S.marked) {
+				S.marked = 1;
+				shift_locs[shift_n] = S.pos;
+				mk = 1;
+			}
+			int last = T.last_cluster[lane];
+			if (sub_p1 == last && toli > 0) {
+				int move = toli >= 3 ? T.rec[lane][toli - 1] : 0;
+				int nd = move;
+				move -= T.rec[lane][toli + 2];
+				nd -= d;
+				if (abs(move) > abs(nd)) {
+					toli -= 3;
+					T.toli[lane] = (int8_t)toli;
+					last--;
+					T.last_cluster[lane] = (int16_t)last;
+					T.votes[lane]--;
+				}
+			}
+			if (!(sub_p1 <= last)) {
+				nv = T.votes[lane] + 1;
+				T.votes[lane] = (int16_t)nv;
+				if (offset + 16 > T.cov_end[lane]) T.cov_end[lane] = (int16_t)(offset + 16);
+				if (d == T.cursor[lane]) {
+					T.rec[lane][toli + 1] = (int16_t)sub_p1;
+				} else {
+					toli += 3;
+					if (toli < kMaxSections * 3) {
+						T.toli[lane] = (int8_t)toli;
+						T.rec[lane][toli] = (int16_t)sub_p1;
+						T.rec[lane][toli + 1] = (int16_t)sub_p1;
+						T.rec[lane][toli + 2] = (int16_t)d;
+						if (toli < kMaxSections * 3 - 3) T.rec[lane][toli + 3] = 0;
+					}
+					T.cursor[lane] = (int8_t)d;
+				}
+				T.last_cluster[lane] = (int16_t)sub_p1;
+				acc = 1;
+			}
+		}
+		unsigned wm = __ballot_sync(kFull, is_w);
+		int w = __ffs(wm) - 1;
+		acc = __shfl_sync(kFull, acc, w);
+		mk = __shfl_sync(kFull, mk, w);
+		nv = __shfl_sync(kFull, nv, w);
+		if (mk) shift_n++;
+		if (acc) {
+			if (max_vote < nv) max_vote = nv;
+			accepted = true;
+			break;
+		}
+		cand = cand && !is_w;
+		cm = __ballot_sync(kFull, cand);
+	}
+	if (accepted) return;
+
+	// no accepting slot: open a new one in the home row (:1074-1106)
+	if (!(kv >= E.low_border && kv <= E.high_border)) return;
+	int in_home = __popc(__ballot_sync(kFull, valid && (uint32_t)S.row == home));
+	if (in_home >= kVoteSpace) return;
+	if (nslots == kWarpSlots) { overflow = true; return; }
+	int mk = 0;
+	if (E.round > 0) {
+		bool near = lane < shift_n && kv >= shift_locs[lane] - (uint32_t)E.tol && kv <= shift_locs[lane] + (uint32_t)E.tol;
+		mk = __any_sync(kFull, near) ? 1 : 0;
+	}
+	if (lane == nslots) {
+		S.pos = kv; S.row = (int)home; S.j = in_home; S.marked = mk;
+		T.votes[lane] = 1;
+		T.toli[lane] = 0;
+		T.rec[lane][0] = (int16_t)sub_p1; T.rec[lane][1] = (int16_t)sub_p1; T.rec[lane][2] = 0; T.rec[lane][3] = 0;
+		T.cursor[lane] = 0;
+		T.cov_start[lane] = (int16_t)offset;
+		T.cov_end[lane] = (int16_t)(offset + 16);
+		T.last_cluster[lane] = (int16_t)sub_p1;
+	}
+	nslots++;
+	if (max_vote == 0) max_vote = 1;
+}
+
+// ---- lookup + vote for one mate and one strand pass --------------------------------------------
+// Returns applied_subreads.  Leaves the table in T (pos/row/j flushed from registers).
+__device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *packed /* this pass */, int L,
+                                         WarpTable &T, uint32_t *shift_locs, int lane, int &nslots_out, int &max_vote_out,
+                                         bool &overflow)
+{
+	nslots_out = 0;
+	max_vote_out = 0;
+	if (L < 16) return 0;  // core.c:3116 (the reference leaves a stale table here; we define it empty)
+	const int gap = ix.index_gap;
+	int step;
+	const int applied = subread_schedule(L, gap, cfg.total_subreads, &step);
+	const int n_lk = applied * gap;
+	HitEnv E;
+	E.tol = cfg.indel_tolerance;
+	E.ii_end = kSeg;
+	if (E.tol > 5) E.ii_end = (E.tol % kSeg) ? (E.tol - E.tol % kSeg + kSeg) : E.tol;
+	E.lane = lane;
+	E.low_border = cfg.low_border;
+	E.high_border = cfg.high_border - (uint32_t)L;
+	const uint32_t nb = ix.buckets_number;
+
+	int shift_n = 0;
+	int nslots = 0, max_vote = 0;
+	SlotRegs S;
+	for (int round = 0; round < 2; round++) {  // core.c:3153-3186
+		E.round = round;
+		nslots = 0; max_vote = 0;
+		S.pos = 0; S.row = 255; S.j = 0; S.marked = 0;
+		for (int base = 0; base < n_lk; base += 32) {
+			const int l = base + lane;
+			int o = 0, h = 0, land = 0;
+			uint32_t run_abs = 0, firstval = 0;
+			if (l < n_lk) {
+				o = lookup_offset(l, gap, step);
+				const uint32_t key = extract_key(packed, o);
+				const uint32_t b = key % nb;
+				const int k16 = (int)(int16_t)(key / nb);
+				const uint32_t lo = __ldg(ix.bucket_start + b);
+				const int items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
+				if (items > 0) {
+					const int16_t *kp = ix.keys + lo;
+					int imin = 0, imax = items - 1, at;
+					bool found = false;
+					for (;;) {  // sorted-hashtable.c:960-981
+						at = (imin + imax) >> 1;
+						int kk = (int)__ldg(kp + at);
+						if (kk > k16) imax = at - 1;
+						else if (kk < k16) imin = at + 1;
+						else { found = true; break; }
+						if (imax < imin) break;
+					}
+					if (found) {
+						int e = at + 1, s = at;
+						while (e < items && (int)__ldg(kp + e) == k16) e++;
+						while (s > 0 && (int)__ldg(kp + s - 1) == k16) s--;
+						h = e - s;
+						land = at - s;
+						run_abs = lo + (uint32_t)s;
+						firstval = __ldg(ix.vals + lo + at);
+					}
+				}
+			}
+			// replay the hits of this batch of lookups in lookup order, each run in visit order
+			unsigned fm = __ballot_sync(kFull, h > 0);
+			while (fm) {
+				const int src = __ffs(fm) - 1;
+				fm &= fm - 1;
+				const int o_s = __shfl_sync(kFull, o, src);
+				const int h_s = __shfl_sync(kFull, h, src);
+				const int sub_p1 = (base + src) / gap + 1;
+				if (h_s == 1) {
+					const uint32_t v = __shfl_sync(kFull, firstval, src);
+					vote_hit(T, S, shift_locs, shift_n, nslots, max_vote, overflow, E, v - (uint32_t)o_s, o_s, sub_p1);
+					if (overflow) return applied;
+				} else {
+					const int land_s = __shfl_sync(kFull, land, src);
+					const uint32_t run_s = __shfl_sync(kFull, run_abs, src);
+					const int nfwd = h_s - land_s;  // landing .. end of run, then landing-1 .. start (:1109-1119)
+					for (int c = 0; c < h_s; c += 32) {
+						const int tt = c + lane;
+						uint32_t v = 0;
+						if (tt < h_s) {
+							int idx = tt < nfwd ? land_s + tt : land_s - 1 - (tt - nfwd);
+							v = __ldg(ix.vals + run_s + idx);
+						}
+						const int cnt = min(32, h_s - c);
+						for (int u = 0; u < cnt; u++) {
+							const uint32_t vu = __shfl_sync(kFull, v, u);
+							vote_hit(T, S, shift_locs, shift_n, nslots, max_vote, overflow, E, vu - (uint32_t)o_s, o_s, sub_p1);
+							if (overflow) return applied;
+						}
+					}
+				}
+			}
+		}
+		__syncwarp();
+		if (shift_n == 0) break;
+	}
+	T.pos[lane] = S.pos;
+	T.row[lane] = (uint8_t)S.row;
+	T.j[lane] = (uint8_t)S.j;
+	__syncwarp();
+	nslots_out = nslots;
+	max_vote_out = max_vote;
+	return applied;
+}
+
+// ---- vote table -> bigtable (top-K) ------------------------------------------------------------
+
+// Build the mapping_result_t image of slot s into dst, word `lane` by lane `lane`
+// (copy_vote_to_alignment_res core-junction.c:1058-1072 + indel_recorder_copy).
+__device__ __forceinline__ void emit_slot(ResultWords &dst, const WarpTable &T, int s, int used_subreads, uint32_t strand_flag, int lane)
+{
+	const int16_t *rec = T.rec[s];
+	bool sec = lane < kMaxSections && rec[3 * lane] != 0;
+	unsigned m = __ballot_sync(kFull, sec) & 0x7fu;
+	int z = __ffs(~m) - 1;  // first empty section (7 when all are in use)
+	int ncopy = 3 * z;
+	if (lane < kResultWords) {
+		uint32_t w = 0;
+		if (lane == 0) w = T.pos[s];
+		else if (lane == 1) w = strand_flag;
+		else if (lane == 2) w = (uint32_t)(uint16_t)T.votes[s] | ((uint32_t)(uint16_t)used_subreads << 16);
+		else if (lane == 3) w = ncopy > 0 ? ((uint32_t)(uint8_t)(int8_t)rec[ncopy - 1]) << 8 : 0u;
+		else if (lane < 15) {
+			int a = 2 * (lane - 4), b = a + 1;
+			uint32_t lo16 = a < ncopy ? (uint32_t)(uint16_t)rec[a] : 0u;
+			uint32_t hi16 = b < ncopy ? (uint32_t)(uint16_t)rec[b] : 0u;
+			w = lo16 | (hi16 << 16);
+		} else if (lane == 15) w = (uint32_t)(uint16_t)T.cov_start[s] | ((uint32_t)(uint16_t)T.cov_end[s] << 16);
+		dst.w[lane] = w;
+	}
+}
+
+template <int MATES>
+__device__ __forceinline__ void emit_candidate(WarpShared<MATES> &ws, int m, int s, int &cursor, int used_subreads,
+                                               uint32_t strand_flag, int lane)
+{
+	const uint32_t pos = ws.cand_pos[m][s];
+	bool exist = false;
+	for (int k = 0; k < cursor; k++)
+		if (ws.tmp[m][k].w[0] == pos) exist = true;
+	if (exist) return;
+	const int src = ws.cand_src[m][s];
+	if (src < 32) emit_slot(ws.tmp[m][cursor], ws.tab[m], src, used_subreads, strand_flag, lane);
+	else if (lane < kResultWords) ws.tmp[m][cursor].w[lane] = ws.res[m][src - 32].w[lane];
+	cursor++;
+	__syncwarp();
+}
+
+// process_voting_junction_PE_topK, core-junction.c:2199-2530 (DNA mode).
+template <int MATES>
+__device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, int strand,
+                                          const int nslots[2], const int rlen[2], const int all_subreads[2], int lane)
+{
+	const int mb = cfg.multi_best_reads;
+	int n_cand[2] = {0, 0};
+
+	for (int m = 0; m < MATES; m++) {
+		const WarpTable &T = ws.tab[m];
+		const bool valid = lane < nslots[m];
+		const int v = valid ? (int)T.votes[lane] : 0;
+		int ov = lane < mb ? (int)result_votes(ws.res[m][lane]) : 0;
+		if (ov < 0) ov = 0;
+		// update_top_three (:908): the top_scores largest distinct positive values
+		int top[kMaxTop];
+		int bound = 0x7fffffff;
+		for (int k = 0; k < kMaxTop; k++) {
+			int x = max(v < bound ? v : 0, ov < bound ? ov : 0);
+			top[k] = k < cfg.top_scores ? __reduce_max_sync(kFull, x) : 0;
+			bound = top[k] > 0 ? top[k] : 0;  // once 0, nothing more qualifies
+			if (bound == 0) { for (int k2 = k + 1; k2 < kMaxTop; k2++) top[k2] = 0; break; }
+		}
+		// candidate ("simple") list, :2256-2316
+		int n = 0;
+		const int key = valid ? (int)T.row[lane] * 32 + (int)T.j[lane] : 0x7fffffff;
+		for (int lv = 0; lv < cfg.top_scores; lv++) {
+			if (n >= cfg.max_vote_simples) break;
+			const int want = top[lv];
+			if (want < 1 || top[0] - want > cfg.max_vote_number_cutoff) break;
+			bool q = valid && v == want && v >= cfg.min_second;
+			unsigned qm = __ballot_sync(kFull, q);
+			while (qm && n < cfg.max_vote_simples) {  // (row, j) ascending = the reference's i, j loops
+				int best = __reduce_min_sync(kFull, q ? key : 0x7fffffff);
+				if (q && key == best) {
+					ws.cand_pos[m][n] = T.pos[lane];
+					ws.cand_votes[m][n] = (int16_t)want;
+					ws.cand_src[m][n] = (uint8_t)lane;
+					q = false;
+				}
+				n++;
+				qm = __ballot_sync(kFull, q);
+			}
+			for (int k = 0; k < mb; k++) {
+				if (n >= cfg.max_vote_simples) break;
+				if ((int)result_votes(ws.res[m][k]) == want) {
+					if (lane == 0) {
+						ws.cand_pos[m][n] = ws.res[m][k].w[0];
+						ws.cand_votes[m][n] = (int16_t)want;
+						ws.cand_src[m][n] = (uint8_t)(32 + k);
+					}
+					n++;
+				}
+			}
+		}
+		n_cand[m] = n;
+	}
+	__syncwarp();
+
+	int n_comb = 0;
+	if (MATES == 2) {  // :2321-2372
+		const int n0 = n_cand[0], n1 = n_cand[1];
+		for (int c = lane; c < n0 + n1; c += 32) {
+			int m = c >= n0 ? 1 : 0, i = c - (m ? n0 : 0), chr, lp;
+			int re = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, ws.cand_pos[m][i], &chr, &lp);
+			ws.cand_re[m][i] = (int8_t)re;
+			ws.cand_chr[m][i] = (int16_t)chr;
+			ws.cand_lpos[m][i] = lp;
+		}
+		__syncwarp();
+		// The reference keeps the max_vote_combinations best pairs ordered by (score desc, visiting
+		// order asc) through a stable insertion; that is a strict total order, so we select them one
+		// by one with a packed key  score * 4096 + (4095 - q),  q = i * n1 + j.
+		const int total = n0 * n1;
+		uint32_t prev = 0xffffffffu;
+		for (int r = 0; r < cfg.max_vote_combinations; r++) {
+			uint32_t best = 0;
+			for (int q = lane; q < total; q += 32) {
+				int i = q / n1, j = q - i * n1;
+				int v1 = ws.cand_votes[0][i], v2 = ws.cand_votes[1][j];
+				if (max(v1, v2) < cfg.min_first) continue;
+				int is_pe;
+				int weight = pair_weight(ws.cand_re[0][i], ws.cand_chr[0][i], ws.cand_lpos[0][i], ws.cand_re[1][j], ws.cand_chr[1][j],
+				                         ws.cand_lpos[1][j], rlen[0], rlen[1], cfg.min_pair_dist, cfg.max_pair_dist, &is_pe);
+				if (!is_pe && min(v1, v2) < cfg.min_first) continue;
+				uint32_t k = (uint32_t)((v1 + v2) * weight) * 4096u + (uint32_t)(4095 - q);
+				if (k < prev && k > best) best = k;
+			}
+			best = __reduce_max_sync(kFull, best);
+			if (best == 0) break;
+			if (lane == 0) ws.comb[r] = best;
+			prev = best;
+			n_comb++;
+		}
+		__syncwarp();
+		if (n_comb > 1 && lane == 0) {
+			// merge_sort -> basic_sort_run (core.c:4716-4749): unstable selection sort, ascending score
+			for (int i = 0; i < n_comb - 1; i++) {
+				int mn = i;
+				for (int j = i + 1; j < n_comb; j++)
+					if ((int)(ws.comb[mn] >> 12) - (int)(ws.comb[j] >> 12) > 0) mn = j;
+				if (i != mn) { uint32_t t = ws.comb[i]; ws.comb[i] = ws.comb[mn]; ws.comb[mn] = t; }
+			}
+		}
+		__syncwarp();
+	}
+
+	// emission into zeroed temporaries (:2386-2495)
+	for (int w = lane; w < MATES * kMaxBest * kResultWords; w += 32) (&ws.tmp[0][0].w[0])[w] = 0;
+	__syncwarp();
+	int cursor[2] = {0, 0};
+	const uint32_t strand_flag = strand ? (uint32_t)kCoreNegStrand : 0u;
+	if (n_comb > 0) {
+		const int n1 = n_cand[1];
+		for (int m = 0; m < MATES; m++)
+			for (int c = n_comb - 1; c >= 0 && cursor[m] < mb; c--) {
+				int q = 4095 - (int)(ws.comb[c] & 4095u);
+				int i = q / n1, j = q - i * n1;
+				emit_candidate<MATES>(ws, m, m ? j : i, cursor[m], all_subreads[m], strand_flag, lane);
+			}
+	} else {
+		if (lane == 0) {
+			if (n_cand[0] == 0) ws.res[0][0].w[3] &= ~0xffu;
+			if (MATES == 2 && n_cand[1] == 0) ws.res[MATES - 1][0].w[3] &= ~0xffu;
+		}
+		__syncwarp();
+		if (n_cand[0] > 0 || n_cand[1] > 0)
+			for (int m = 0; m < MATES; m++)
+				for (int s = 0; s < n_cand[m] && cursor[m] < mb; s++) {
+					if (ws.cand_votes[m][s] < cfg.min_first) continue;
+					emit_candidate<MATES>(ws, m, s, cursor[m], all_subreads[m], strand_flag, lane);
+				}
+	}
+	__syncwarp();
+	for (int m = 0; m < MATES; m++)  // :2505-2527
+		for (int k = 0; k < mb; k++) {
+			if (k < cursor[m]) {
+				if (lane < kResultWords) ws.res[m][k].w[lane] = ws.tmp[m][k].w[lane];
+			} else if (lane == 0) ws.res[m][k].w[2] &= 0xffff0000u;
+		}
+	__syncwarp();
+}
+
+// ---- verification ------------------------------------------------------------------------------
+// Bases of the read (MSB-first packed codes, L bases) equal to the genome at `pos`: match_chro's
+// forward branch (gene-value-index.c:892-940).  Warp-wide; every lane returns the count.
+__device__ __forceinline__ int match_packed(const DevIndex &ix, const uint32_t *packed, int L, uint32_t pos, int lane)
+{
+	if ((uint32_t)(pos + (uint32_t)L) >= ix.length + ix.start_point) return 0;
+	if (pos > 0xffff0000u) return 0;
+	const uint32_t q0 = pos - ix.start_base_offset;
+	if ((q0 >> 2) >= ix.values_bytes) return 0;
+	int cnt = 0;
+	const int n_words = (L + 15) >> 4;
+	for (int k = lane; k < n_words; k += 32) {
+		uint32_t r = __brev(packed[k]);                                   // base order LSB-first ...
+		r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);          // ... bits inside a base restored
+		const uint32_t q = q0 + 16u * (uint32_t)k;
+		const uint32_t gw = q >> 4, sh = (q & 15u) * 2u;
+		const uint32_t g = __funnelshift_r(__ldg(ix.genome + gw), __ldg(ix.genome + gw + 1), sh);
+		uint32_t x = r ^ g;
+		x = (x | (x >> 1)) & 0x55555555u;
+		const int nbases = min(16, L - 16 * k);
+		if (nbases < 16) x &= (1u << (2 * nbases)) - 1u;
+		cnt += nbases - __popc(x);
+	}
+	return __reduce_add_sync(kFull, cnt);
+}
+
+// ---- one fragment ------------------------------------------------------------------------------
+// chars: MATES * chars_stride bytes; packed: MATES * 3 * n_words words (all per-warp shared memory).
+// Returns false when the fragment overflowed the shared-memory table (nothing was written).
+template <int MATES>
+__device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, uint8_t *chars,
+                                             int chars_stride, uint32_t *packed, int n_words, const uint8_t *raw0, int len0,
+                                             const uint8_t *raw1, int len1, ResultWords *out /* global, this fragment */,
+                                             uint16_t *verify /* global or null */, int lane)
+{
+	const int mb = cfg.multi_best_reads;
+	const int rlen[2] = {len0, len1};
+	const uint8_t *raw[2] = {raw0, raw1};
+
+	for (int w = lane; w < MATES * mb * kResultWords; w += 32) {  // old results (read-modify-write)
+		int s = w / kResultWords, k = w - s * kResultWords;
+		ws.res[s / mb][s % mb].w[k] = out[s].w[k];
+	}
+	for (int m = 0; m < MATES; m++) {
+		uint8_t *cm = chars + m * chars_stride;
+		for (int i = lane; i < rlen[m]; i += 32) cm[i] = raw[m][i];
+	}
+	__syncwarp();
+	for (int m = 0; m < MATES; m++)
+		pack_read(chars + m * chars_stride, rlen[m], m == 0 ? cfg.first_reversed != 0 : cfg.second_reversed != 0,
+		          packed + m * 3 * n_words, n_words, lane);
+	__syncwarp();
+
+	int all_subreads[2] = {0, 0};
+	bool overflow = false;
+	for (int strand = 0; strand < 2; strand++) {
+		int nslots[2] = {0, 0}, max_vote[2] = {0, 0};
+		int applied = 0;
+		for (int m = 0; m < MATES; m++) {
+			applied = vote_mate(ix, cfg, packed + (m * 3 + strand) * n_words, rlen[m], ws.tab[m], ws.shift_locs, lane, nslots[m],
+			                    max_vote[m], overflow);
+			if (rlen[m] >= 16) all_subreads[m] = applied;
+			if (overflow) return false;
+		}
+		if (MATES == 2 || max_vote[0] >= cfg.min_first) {
+			topk_warp<MATES>(ix, cfg, ws, strand, nslots, rlen, all_subreads, lane);
+		} else if (lane == 0 && result_votes(ws.res[0][0]) < 1) {  // core.c:3217-3225
+			ws.res[0][0].w[3] &= ~0xffu;
+			int16_t used = (int16_t)(ws.res[0][0].w[2] >> 16);
+			if (used < applied) ws.res[0][0].w[2] = (ws.res[0][0].w[2] & 0xffffu) | ((uint32_t)(uint16_t)applied << 16);
+		}
+		__syncwarp();
+	}
+
+	for (int w = lane; w < MATES * mb * kResultWords; w += 32) {
+		int s = w / kResultWords, k = w - s * kResultWords;
+		out[s].w[k] = ws.res[s / mb][s % mb].w[k];
+	}
+	if (verify) {
+		for (int m = 0; m < MATES; m++)
+			for (int k = 0; k < mb; k++) {
+				const ResultWords &r = ws.res[m][k];
+				int v = 0xffff;
+				if (result_votes(r) >= 1) {
+					bool neg = (r.w[1] & kCoreNegStrand) != 0;
+					v = match_packed(ix, packed + (m * 3 + (neg ? 1 : 2)) * n_words, rlen[m], r.w[0], lane);
+				}
+				if (lane == 0) verify[m * mb + k] = (uint16_t)v;
+			}
+	}
+	return true;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sr

@@ -7,7 +7,7 @@ reference's own host code unchanged:
 * ``SUBJUNC_RESULT`` -- ``subjunc_result_t``  (reference src/core.h:397-410), 16 bytes
 * ``VoteParams``     -- the scalars ``do_voting`` / ``process_voting_junction_PE_topK`` read from
   ``configuration_t`` (reference src/core.h:128-253); same field order as ``srcuda_params``
-  in include/subread_cuda.h and ``or_params_t`` in oracle/sr_oracle.h.
+  in include/subread_cuda.h.
 """
 import ctypes
 

@@ -1,0 +1,177 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the reference's
+golden bigtables.  Bit-exact bar: every byte of every used slot (and, against the golden files,
+every byte of the table)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REF_DIR, ROOT, describe_mismatch, have_ref, load_case
+from subread_b200 import MAPPING_RESULT, VoteParams, load_fastq, used_slots_equal
+
+pytestmark = pytest.mark.gpu
+
+CASE_NAMES = ["se_gapped", "pe_gapped", "se_full", "pe_full", "se_I16", "pe_n14_ff"]
+
+
+@pytest.fixture(scope="module")
+def mapper():
+    from subread_b200.binding import Mapper
+    m = Mapper(0)
+    yield m
+    m.close()
+
+
+@pytest.mark.parametrize("slow", [False, True], ids=["warp", "scalar"])
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_golden_bigtables(name, slow, mapper, golden_cases, golden_index_dir, oracle_mod):
+    case = next(c for c in golden_cases if c["name"] == name)
+    prefix, chunk, params, exp = load_case(case, golden_index_dir)
+    mapper.index_load(prefix, 0)
+    mapper.set_force_slow_path(slow)
+    try:
+        got, ver = mapper.vote_chunk(chunk, params, want_verify=True)
+    finally:
+        mapper.set_force_slow_path(False)
+    ok, bad = used_slots_equal(got, exp)
+    assert ok, describe_mismatch(got, exp, bad)
+    assert got.tobytes() == exp.tobytes()
+    idx = oracle_mod.OracleIndex(prefix)
+    _, over, _ = oracle_mod.vote_chunk(idx, params, chunk, want_verify=True)
+    assert (ver == over).all(), f"verify differs at {np.flatnonzero(ver != over)[:5]}"
+    t = mapper.timing()
+    assert t.n_launches >= 1
+    if slow:
+        assert t.n_overflow == chunk.n_frags
+
+
+def test_upload_from_arrays_equals_load_from_files(mapper, golden_cases, golden_index_dir, oracle_mod):
+    case = next(c for c in golden_cases if c["name"] == "pe_gapped")
+    prefix, chunk, params, exp = load_case(case, golden_index_dir)
+    a = oracle_mod.OracleIndex(prefix).arrays()
+    mapper.index_upload(a["index_gap"], a["padding"], a["bucket_start"], a["keys"], a["vals"], a["start_point"], a["length"],
+                        a["values"], a["read_offsets"])
+    d = mapper.describe()
+    assert (d.index_gap, d.buckets_number, d.n_items) == (a["index_gap"], a["buckets_number"], a["n_items"])
+    got, _ = mapper.vote_chunk(chunk, params)
+    assert got.tobytes() == exp.tobytes()
+
+
+def test_many_small_batches_and_ragged_input(golden_cases, golden_index_dir, oracle_mod):
+    """Double-buffered batching must not change anything; also covers empty chunks and reads < 16 bp."""
+    from subread_b200 import pack_reads
+    from subread_b200.binding import Mapper
+    os.environ["SRCUDA_BATCH_FRAGS"] = "97"
+    try:
+        m = Mapper(0)
+    finally:
+        del os.environ["SRCUDA_BATCH_FRAGS"]
+    case = next(c for c in golden_cases if c["name"] == "pe_gapped")
+    prefix, chunk, params, exp = load_case(case, golden_index_dir)
+    m.index_load(prefix, 0)
+    got, _ = m.vote_chunk(chunk, params)
+    assert got.tobytes() == exp.tobytes()
+    assert m.timing().n_batches == (chunk.n_frags + 96) // 97
+    # empty chunk
+    empty = pack_reads([], None)
+    got, _ = m.vote_chunk(empty, VoteParams.defaults(False))
+    assert got.shape[0] == 0
+    # ragged: very short reads (skipped by the reference, core.c:3116), 16..20 bp, and a maximum-length read
+    rng = np.random.default_rng(5)
+    import gzip
+    genome = b"".join(l.strip() for l in gzip.open(os.path.join(GOLDEN, "tiny.fa.gz")) if not l.startswith(b">"))
+    seqs = [b"ACGT", b"A" * 15, genome[100:116], genome[200:219], genome[300:320], genome[1000:2210], genome[5000:5100], b"N" * 50]
+    ragged = pack_reads(seqs, None)
+    p = VoteParams.defaults(False)
+    got, ver = m.vote_chunk(ragged, p, want_verify=True)
+    idx = oracle_mod.OracleIndex(prefix)
+    ora, over, _ = oracle_mod.vote_chunk(idx, p, ragged, want_verify=True)
+    assert got.tobytes() == ora.tobytes()
+    assert (ver == over).all()
+    m.close()
+
+
+def test_read_modify_write_merges_like_the_oracle(mapper, golden_cases, golden_index_dir, oracle_mod):
+    """Second pass over the same block with the first pass's table as input (multi-block merge path)."""
+    for name in ("se_gapped", "pe_gapped"):
+        case = next(c for c in golden_cases if c["name"] == name)
+        prefix, chunk, params, exp = load_case(case, golden_index_dir)
+        mapper.index_load(prefix, 0)
+        idx = oracle_mod.OracleIndex(prefix)
+        twice_ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=exp.copy())
+        twice_gpu, _ = mapper.vote_chunk(chunk, params, out_align=exp.copy().reshape(-1))
+        ok, bad = used_slots_equal(twice_gpu, twice_ora)
+        assert ok, describe_mismatch(twice_gpu, twice_ora, bad)
+
+
+def test_device_resident_entry_point(mapper, golden_cases, golden_index_dir):
+    import torch
+    case = next(c for c in golden_cases if c["name"] == "se_gapped")
+    prefix, chunk, params, exp = load_case(case, golden_index_dir)
+    mapper.index_load(prefix, 0)
+    dev = torch.device("cuda:0")
+    d_text = torch.from_numpy(chunk.text).to(dev)
+    d_off = torch.from_numpy(chunk.off.astype(np.int64)).to(dev)
+    d_len = torch.from_numpy(chunk.len.astype(np.int16)).to(dev)
+    n = chunk.n_frags * chunk.mates * params.multi_best_reads
+    d_out = torch.zeros(n * 68, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    mapper.vote_chunk_device(params, d_text.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), chunk.n_frags, False,
+                             int(chunk.len.max()), d_out.data_ptr())
+    got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=MAPPING_RESULT)
+    assert got.tobytes() == exp.tobytes()
+    assert mapper.timing().ms_kernel_vote > 0
+
+
+def test_errors_are_loud(mapper, golden_cases, golden_index_dir):
+    from subread_b200.binding import Mapper, SubreadCudaError
+    case = next(c for c in golden_cases if c["name"] == "se_gapped")
+    prefix, chunk, params, _ = load_case(case, golden_index_dir)
+    fresh = Mapper(0)
+    with pytest.raises(SubreadCudaError, match="no index"):
+        fresh.vote_chunk(chunk, params)
+    with pytest.raises(SubreadCudaError):
+        fresh.index_load("/nonexistent/prefix", 0)
+    fresh.close()
+    mapper.index_load(prefix, 0)
+    bad = VoteParams.defaults(False)
+    bad.multi_best_reads = 7
+    with pytest.raises(SubreadCudaError, match="multi_best_reads"):
+        mapper.vote_chunk(chunk, bad)
+    sub = VoteParams.defaults(False, is_subjunc=True)
+    with pytest.raises(SubreadCudaError, match="do_breakpoint_detection"):
+        mapper.vote_chunk(chunk, sub)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference binaries) not built")
+@pytest.mark.parametrize("kind", ["uniform", "repeats"])
+def test_larger_genome_against_oracle(kind, mapper, oracle_mod, tmp_path):
+    """2 Mbp genome indexed by the reference's own builder (gapped, one block), 30k SE + 15k PE reads
+    with errors and indels.  The repeat-rich variant drives tables past 32 slots, i.e. through the
+    overflow queue and the exact slow path."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 4, 500000, seed=77, repeats=600 if kind == "repeats" else 0)
+    prefix = str(tmp_path / "idx")
+    subprocess.check_call([os.path.join(REF_DIR, "bin", "subread-buildindex"), "-o", prefix, "-B", fa],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    gen_data.write_reads(fa, str(tmp_path / "se"), 30000, 150, 1, False, 0.01, 0.1, False, 0.001)
+    gen_data.write_reads(fa, str(tmp_path / "pe"), 15000, 100, 2, True, 0.01, 0.1, True, 0.001)
+    mapper.index_load(prefix, 0)
+    idx = oracle_mod.OracleIndex(prefix)
+    total_overflow = 0
+    for r1, r2 in ((str(tmp_path / "se_R1.fastq"), None), (str(tmp_path / "pe_R1.fastq"), str(tmp_path / "pe_R2.fastq"))):
+        chunk = load_fastq(r1, r2)
+        params = VoteParams.defaults(r2 is not None)
+        got, ver = mapper.vote_chunk(chunk, params, want_verify=True)
+        total_overflow += mapper.timing().n_overflow
+        ora, over, _ = oracle_mod.vote_chunk(idx, params, chunk, want_verify=True, threads=8)
+        ok, bad = used_slots_equal(got, ora)
+        assert ok, describe_mismatch(got, ora, bad)
+        assert got.tobytes() == ora.tobytes()
+        assert (ver == over).all()
+    if kind == "repeats":
+        assert total_overflow > 0, "the repeat-rich case is meant to exercise the overflow path"
