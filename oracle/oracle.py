@@ -104,6 +104,7 @@ class OracleIndex:
         c = self.c
         nb, ni = c.buckets_number, c.n_items
         return dict(
+            _owner=self,  # the views below point into memory this object frees in close()
             index_gap=c.index_gap, padding=c.padding, buckets_number=nb, n_items=ni,
             bucket_start=np.ctypeslib.as_array(c.bucket_start, shape=(nb + 1,)),
             keys=np.ctypeslib.as_array(c.keys, shape=(max(ni, 1),))[:ni],

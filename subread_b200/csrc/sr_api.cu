@@ -226,7 +226,13 @@ int upload_index(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t 
 	if (!bucket_start || !keys || !vals || !values || !read_offsets || nb < 1 || total_offsets < 1)
 		return fail(h, SRCUDA_ERR_ARG, "srcuda_index_upload: null array or empty table");
 	if (index_gap < 1 || index_gap > 3) return fail(h, SRCUDA_ERR_UNSUPPORTED, "index gap %d not in 1..3", index_gap);
-	if (bucket_start[nb] != (uint32_t)n_items) return fail(h, SRCUDA_ERR_ARG, "bucket_start[buckets] != n_items");
+	if (bucket_start[0] != 0 || bucket_start[nb] != (uint32_t)n_items) return fail(h, SRCUDA_ERR_ARG, "bucket_start does not span [0, n_items]");
+	for (uint32_t b = 0; b < nb; b++)  // the kernels trust this table: refuse a corrupt one here, not with a device fault
+		if (bucket_start[b] > bucket_start[b + 1]) return fail(h, SRCUDA_ERR_FORMAT, "bucket_start is not non-decreasing at bucket %u", b);
+	if ((uint64_t)values_bytes < (((uint64_t)length + start_point - (start_point - start_point % 4)) >> 2))
+		return fail(h, SRCUDA_ERR_FORMAT, "genome array shorter than its declared length");
+	for (int32_t c = 1; c < total_offsets; c++)
+		if (read_offsets[c] < read_offsets[c - 1]) return fail(h, SRCUDA_ERR_FORMAT, "chromosome offsets are not increasing");
 	CU(h, cudaSetDevice(h->device));
 	free_index(h);
 	size_t gw = ((size_t)values_bytes + 3) / 4 + 8;  // +8 words so funnel shifts may read one word ahead

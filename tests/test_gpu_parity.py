@@ -50,7 +50,8 @@ def test_golden_bigtables(name, slow, mapper, golden_cases, golden_index_dir, or
 def test_upload_from_arrays_equals_load_from_files(mapper, golden_cases, golden_index_dir, oracle_mod):
     case = next(c for c in golden_cases if c["name"] == "pe_gapped")
     prefix, chunk, params, exp = load_case(case, golden_index_dir)
-    a = oracle_mod.OracleIndex(prefix).arrays()
+    oidx = oracle_mod.OracleIndex(prefix)
+    a = oidx.arrays()
     mapper.index_upload(a["index_gap"], a["padding"], a["bucket_start"], a["keys"], a["vals"], a["start_point"], a["length"],
                         a["values"], a["read_offsets"])
     d = mapper.describe()
