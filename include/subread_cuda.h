@@ -154,6 +154,15 @@ int srcuda_index_upload(srcuda_handle *h, int32_t index_gap, int32_t padding, ui
  * (no host round trip).  Both handles live in this process. */
 int srcuda_index_replicate(srcuda_handle *dst, const srcuda_handle *src);
 
+/* The same replication when every GPU is driven by its own process (one process per GPU, as
+ * bench.py launches them): the owner exports CUDA IPC handles of its resident block into an
+ * opaque blob, the other processes import it -- the block is copied device to device over
+ * NVLink and the mapping is closed again.  The exporter must keep the block loaded until every
+ * importer returned.  SRCUDA_IPC_BLOB_BYTES bytes are enough for the blob. */
+#define SRCUDA_IPC_BLOB_BYTES 512
+int srcuda_index_export_ipc(const srcuda_handle *h, void *blob, size_t blob_bytes);
+int srcuda_index_import_ipc(srcuda_handle *h, const void *blob, size_t blob_bytes);
+
 int srcuda_index_describe(const srcuda_handle *h, srcuda_index_desc *out);
 void srcuda_index_unload(srcuda_handle *h);
 

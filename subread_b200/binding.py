@@ -19,7 +19,8 @@ _LIB = None
 
 EXPORTS = [
     "srcuda_device_count", "srcuda_open", "srcuda_close", "srcuda_last_error", "srcuda_index_load",
-    "srcuda_index_upload", "srcuda_index_replicate", "srcuda_index_describe", "srcuda_index_unload",
+    "srcuda_index_upload", "srcuda_index_replicate", "srcuda_index_export_ipc", "srcuda_index_import_ipc",
+    "srcuda_index_describe", "srcuda_index_unload",
     "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device",
     "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth",
 ]
@@ -70,6 +71,8 @@ def load_library():
     L.srcuda_index_load.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
     L.srcuda_index_upload.argtypes = [vp, i32, i32, u32, u64, vp, vp, vp, u32, u32, vp, u32, vp, i32]
     L.srcuda_index_replicate.argtypes = [vp, vp]
+    L.srcuda_index_export_ipc.argtypes = [vp, vp, ctypes.c_size_t]
+    L.srcuda_index_import_ipc.argtypes = [vp, vp, ctypes.c_size_t]
     L.srcuda_index_describe.argtypes = [vp, ctypes.POINTER(IndexDesc)]
     L.srcuda_index_unload.argtypes = [vp]
     L.srcuda_index_unload.restype = None
@@ -164,6 +167,17 @@ class Mapper:
 
     def index_replicate_from(self, other: "Mapper"):
         self._check(self.lib.srcuda_index_replicate(self.h, other.h), "srcuda_index_replicate")
+
+    IPC_BLOB_BYTES = 512
+
+    def index_export_ipc(self) -> bytes:
+        buf = ctypes.create_string_buffer(self.IPC_BLOB_BYTES)
+        self._check(self.lib.srcuda_index_export_ipc(self.h, buf, self.IPC_BLOB_BYTES), "srcuda_index_export_ipc")
+        return buf.raw
+
+    def index_import_ipc(self, blob: bytes):
+        buf = ctypes.create_string_buffer(blob, self.IPC_BLOB_BYTES)
+        self._check(self.lib.srcuda_index_import_ipc(self.h, buf, self.IPC_BLOB_BYTES), "srcuda_index_import_ipc")
 
     def describe(self) -> IndexDesc:
         d = IndexDesc()

@@ -457,6 +457,69 @@ int srcuda_index_replicate(srcuda_handle *dst, const srcuda_handle *src)
 	return SRCUDA_OK;
 }
 
+namespace {
+struct IpcBlob {
+	uint32_t magic;
+	int32_t src_device;
+	srcuda_index_desc desc;
+	uint64_t genome_words;
+	cudaIpcMemHandle_t mem[5];
+};
+static_assert(sizeof(IpcBlob) <= SRCUDA_IPC_BLOB_BYTES, "IPC blob too large");
+}  // namespace
+
+int srcuda_index_export_ipc(const srcuda_handle *h, void *blob, size_t blob_bytes)
+{
+	srcuda_handle *hm = const_cast<srcuda_handle *>(h);
+	if (!h || !blob || blob_bytes < sizeof(IpcBlob)) return fail(hm, SRCUDA_ERR_ARG, "srcuda_index_export_ipc: bad argument");
+	if (!h->has_index) return fail(hm, SRCUDA_ERR_NO_INDEX, "no index block is loaded");
+	CU(hm, cudaSetDevice(h->device));
+	IpcBlob b;
+	memset(&b, 0, sizeof(b));
+	b.magic = 0x53524950u;
+	b.src_device = h->device;
+	b.desc = h->desc;
+	b.genome_words = h->genome_words;
+	void *ptrs[5] = {h->d_bucket_start, h->d_keys, h->d_vals, h->d_genome, h->d_chr};
+	for (int i = 0; i < 5; i++) CU(hm, cudaIpcGetMemHandle(&b.mem[i], ptrs[i]));
+	memset(blob, 0, blob_bytes);
+	memcpy(blob, &b, sizeof(b));
+	return SRCUDA_OK;
+}
+
+int srcuda_index_import_ipc(srcuda_handle *h, const void *blob, size_t blob_bytes)
+{
+	if (!h || !blob || blob_bytes < sizeof(IpcBlob)) return fail(h, SRCUDA_ERR_ARG, "srcuda_index_import_ipc: bad argument");
+	IpcBlob b;
+	memcpy(&b, blob, sizeof(b));
+	if (b.magic != 0x53524950u) return fail(h, SRCUDA_ERR_ARG, "srcuda_index_import_ipc: not an index blob");
+	CU(h, cudaSetDevice(h->device));
+	free_index(h);
+	const srcuda_index_desc &d = b.desc;
+	size_t bytes[5] = {sizeof(uint32_t) * ((size_t)d.buckets_number + 1), sizeof(int16_t) * (size_t)d.n_items,
+	                   sizeof(uint32_t) * (size_t)d.n_items, sizeof(uint32_t) * (size_t)b.genome_words,
+	                   sizeof(uint32_t) * (size_t)d.total_offsets};
+	void **dst[5] = {&h->d_bucket_start, &h->d_keys, &h->d_vals, &h->d_genome, &h->d_chr};
+	for (int i = 0; i < 5; i++) {
+		void *remote = nullptr;
+		CU(h, cudaIpcOpenMemHandle(&remote, b.mem[i], cudaIpcMemLazyEnablePeerAccess));
+		cudaError_t e = cudaMalloc(dst[i], bytes[i] + 64);
+		if (e == cudaSuccess) e = cudaMemcpy(*dst[i], remote, bytes[i], cudaMemcpyDefault);  // peer copy over NVLink
+		cudaIpcCloseMemHandle(remote);
+		if (e != cudaSuccess) return fail(h, SRCUDA_ERR_CUDA, "peer copy of index array %d failed: %s", i, cudaGetErrorString(e));
+	}
+	h->genome_words = (size_t)b.genome_words;
+	sr::DevIndex &ix = h->ix;
+	ix.buckets_number = d.buckets_number; ix.index_gap = d.index_gap; ix.padding = d.padding;
+	ix.start_point = d.start_point; ix.length = d.length; ix.start_base_offset = d.start_base_offset;
+	ix.values_bytes = d.values_bytes; ix.total_offsets = d.total_offsets;
+	ix.bucket_start = (const uint32_t *)h->d_bucket_start; ix.keys = (const int16_t *)h->d_keys;
+	ix.vals = (const uint32_t *)h->d_vals; ix.genome = (const uint32_t *)h->d_genome; ix.chr_offsets = (const uint32_t *)h->d_chr;
+	h->desc = d;
+	h->has_index = true;
+	return SRCUDA_OK;
+}
+
 int srcuda_index_describe(const srcuda_handle *h, srcuda_index_desc *out)
 {
 	if (!h || !out) return SRCUDA_ERR_ARG;

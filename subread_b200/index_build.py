@@ -1,0 +1,209 @@
+"""Index construction in the reference's frozen on-disk format, one block.
+
+This is the "-B" (IS_FORCED_ONE_BLOCK) path of ``subread-buildindex`` re-stated as array
+operations: sanitise the FASTA (reference src/index-builder.c:789-970), sample a 16-mer every
+``gap`` bases from each contig's first base (``build_gene_index`` :150-417), drop 16-mers that
+occur more than ``threshold`` times among the sampled ones (``scan_gene_index`` :472-684), hash
+them into ``calculate_buckets_by_size`` buckets (src/sorted-hashtable.c:42-75) and sort every
+bucket by ``is_1_greater_than_2`` (src/sorted-hashtable.c:1689-1698).  The output files are
+byte-identical to the reference builder's (tests/test_index_build.py); the sort runs on the GPU
+when one is visible (torch, plumbing only) and in numpy otherwise.
+
+It exists so that benchmarks and tests can make indexes for synthetic genomes without the
+reference; multi-block indexes (no ``-B``) are still built by the reference's own tool.
+"""
+import gzip
+import os
+
+import numpy as np
+
+PADDING = 1210  # MAX_READ_LENGTH, index-builder.c:115
+GEHASH_BUCKET_LENGTH = 31  # sorted-hashtable.h:32 (64-bit builds)
+
+_CODE = np.full(256, 3, dtype=np.uint8)  # base2int, subread.h:238
+_CODE[: ord("G")] = 2
+_CODE[ord("A")] = 0
+_CODE[ord("G")] = 1
+
+
+def calculate_buckets_by_size(expected_size: int, index_gap: int) -> int:
+    """sorted-hashtable.c:42-75 for a VER2 table."""
+    n = int(expected_size) // GEHASH_BUCKET_LENGTH
+    if index_gap >= 3:
+        n //= 3
+    if n <= 0x3FFFF:
+        n = 0x3FFFF + 4
+    while any(n % j == 0 for j in range(2, 14)):
+        n += 1
+    return n
+
+
+def one_block_bucket_count(index_gap: int) -> int:
+    """``-B``: memory_limit 22000 (full) / 11500 (gapped) MB, index-builder.c:1173,1269-1271."""
+    memory_limit = 22000 if index_gap == 1 else 11500
+    expected = (int(memory_limit * 1024.0 / 8.0) * 1024) & 0xFFFFFFFF
+    return calculate_buckets_by_size(expected, index_gap)
+
+
+def read_fasta_sanitised(path):
+    """check_and_convert_FastA (index-builder.c:789-970): upper-case, every non-ACGT character
+    (N, '.', '-', IUPAC, ...) becomes 'A'; contigs of <= 16 bases are dropped; the name ends at the
+    first blank, tab or '|' is kept (ignore_bar_in_seqnames = 0)."""
+    names, seqs, cur, name = [], [], [], None
+    opener = gzip.open if str(path).endswith(".gz") else open
+
+    def flush():
+        if name is not None:
+            s = b"".join(cur)
+            if len(s) > 16:
+                names.append(name)
+                seqs.append(s)
+
+    with opener(path, "rb") as fh:
+        for line in fh:
+            line = line.rstrip(b"\r\n")
+            if not line:
+                continue
+            if line.startswith(b">"):
+                flush()
+                cur = []
+                hdr = line[1:]
+                for sep in (b" ", b"\t"):
+                    hdr = hdr.split(sep)[0]
+                name = hdr.decode()
+            else:
+                cur.append(line)
+        flush()
+    table = np.full(256, ord("A"), dtype=np.uint8)
+    for c in b"ACGT":
+        table[c] = c
+        table[c + 32] = c
+    return names, [table[np.frombuffer(s, dtype=np.uint8)] for s in seqs]
+
+
+def _sort_order(bucket, key16, value, parity, use_gpu):
+    """Order of (bucket asc, key16 signed asc, value asc if parity == 0 else desc)."""
+    tie = np.where(parity == 0, value, np.uint32(0xFFFFFFFF) - value).astype(np.uint32)
+    major = (bucket.astype(np.int64) << 16) | (key16.astype(np.int64) + 32768)
+    if use_gpu:
+        import torch
+        dev = torch.device("cuda")
+        o1 = torch.argsort(torch.from_numpy(tie.astype(np.int64)).to(dev), stable=True)
+        m = torch.from_numpy(major).to(dev)[o1]
+        o2 = torch.argsort(m, stable=True)
+        return o1[o2].cpu().numpy()
+    o1 = np.argsort(tie, kind="stable")
+    o2 = np.argsort(major[o1], kind="stable")
+    return o1[o2]
+
+
+def build_index_arrays(names, seqs, gapped=True, threshold=100, buckets=None, use_gpu=None):
+    """In-memory form of one index block from sanitised contigs (uint8 arrays of A/C/G/T).
+    Returns the SoA arrays ``srcuda_index_upload`` takes plus what the file writer needs."""
+    gap = 3 if gapped else 1
+    nb = int(buckets) if buckets else one_block_bucket_count(gap)
+    if use_gpu is None:
+        try:
+            import torch
+            use_gpu = torch.cuda.is_available()
+        except Exception:
+            use_gpu = False
+    if not seqs:
+        raise ValueError("no contig longer than 16 bases")
+
+    keys_l, vals_l, starts, ends = [], [], [], []
+    start = PADDING
+    for s in seqs:
+        L = s.shape[0]
+        codes = _CODE[s].astype(np.uint32)
+        p = np.arange(0, L - 15, gap, dtype=np.int64)  # window starts while p + 16 <= L
+        key = np.zeros(p.shape[0], dtype=np.uint32)
+        for i in range(16):
+            key |= codes[p + i] << np.uint32(30 - 2 * i)
+        keys_l.append(key)
+        vals_l.append((p + start).astype(np.uint32))
+        starts.append(start)
+        ends.append(start + L - 16 + PADDING)        # read_offsets[], index-builder.c:177,205
+        start = start + (L - 16) + 2 * PADDING       # next contig's first window, :206
+    total_end = starts[-1] + seqs[-1].shape[0]       # linear position after the last base
+    if total_end + PADDING > 0xFFFFFFFD:
+        raise ValueError("the reference sequences include more than 4 billion bases")
+    key = np.concatenate(keys_l)
+    val = np.concatenate(vals_l)
+    del keys_l, vals_l
+
+    # scan_gene_index: exact occurrence counts of the sampled 16-mers
+    srt = np.sort(key)
+    edge = np.flatnonzero(np.concatenate(([True], srt[1:] != srt[:-1], [True])))
+    run = np.diff(edge)
+    heavy = srt[edge[:-1][run > threshold]]
+    del srt
+    if heavy.shape[0]:
+        keep = ~np.isin(key, heavy)
+        key, val = key[keep], val[keep]
+
+    bucket = (key % np.uint32(nb)).astype(np.uint32)
+    key16 = (key // np.uint32(nb)).astype(np.uint16).view(np.int16)
+    parity = ((key % np.uint32(791)) % np.uint32(2)).astype(np.uint8)
+    order = _sort_order(bucket, key16, val, parity, use_gpu)
+    bucket, key16, val = bucket[order], key16[order], val[order]
+    counts = np.bincount(bucket, minlength=nb).astype(np.int64)
+    bucket_start = np.zeros(nb + 1, dtype=np.int64)
+    np.cumsum(counts, out=bucket_start[1:])
+
+    # 2-bit genome, gvindex_set / gvindex_dump (gene-value-index.c:135-187): start_point 0
+    length = total_end + PADDING
+    n_bytes = (length >> 2) + 1
+    bases = np.zeros(n_bytes * 4, dtype=np.uint8)
+    for s, st in zip(seqs, starts):
+        bases[st:st + s.shape[0]] = _CODE[s]
+    b4 = bases.reshape(-1, 4)
+    packed = (b4[:, 0] | (b4[:, 1] << 2) | (b4[:, 2] << 4) | (b4[:, 3] << 6)).astype(np.uint8)
+    return dict(index_gap=gap, padding=PADDING, buckets_number=nb, n_items=int(key16.shape[0]),
+                bucket_start=bucket_start.astype(np.uint32), keys=key16, vals=val.astype(np.uint32), item_bucket=bucket,
+                start_point=0, length=int(length), values=packed, read_offsets=np.array(ends, dtype=np.uint32),
+                names=list(names), contig_starts=np.array(starts, dtype=np.int64), removed_keys=int(heavy.shape[0]))
+
+
+def write_index_files(prefix, a):
+    """<prefix>.00.b.tab (gehash_dump, sorted-hashtable.c:1700-1908), .00.b.array and .reads."""
+    nb, n_items = a["buckets_number"], a["n_items"]
+    counts = np.diff(a["bucket_start"].astype(np.int64))
+    head = bytearray(b"2subindx")
+    head += np.array([0x0102, 2, a["padding"], 0x0101, 2, a["index_gap"], 0], dtype="<i2").tobytes()
+    head += np.array([n_items], dtype="<i8").tobytes() + np.array([nb], dtype="<i4").tobytes()
+    body = np.zeros(8 * nb + 6 * n_items + 1, dtype=np.uint8)  # trailing byte: is_small_table = 0
+    starts_items = a["bucket_start"].astype(np.int64)
+    hdr_at = 8 * np.arange(nb, dtype=np.int64) + 6 * starts_items[:-1]
+    cnt_bytes = counts.astype("<i4").view(np.uint8).reshape(nb, 4)
+    for k in range(4):
+        body[hdr_at + k] = cnt_bytes[:, k]
+        body[hdr_at + 4 + k] = cnt_bytes[:, k]  # space_size == current_items (sorted-hashtable.c:267)
+    item_bucket = a["item_bucket"].astype(np.int64)
+    within = np.arange(n_items, dtype=np.int64) - starts_items[item_bucket]
+    key_at = hdr_at[item_bucket] + 8 + 2 * within
+    val_at = hdr_at[item_bucket] + 8 + 2 * counts[item_bucket] + 4 * within
+    kb = a["keys"].astype("<i2").view(np.uint8).reshape(n_items, 2)
+    vb = a["vals"].astype("<u4").view(np.uint8).reshape(n_items, 4)
+    for k in range(2):
+        body[key_at + k] = kb[:, k]
+    for k in range(4):
+        body[val_at + k] = vb[:, k]
+    with open(prefix + ".00.b.tab", "wb") as fh:
+        fh.write(bytes(head))
+        fh.write(body.tobytes())
+    with open(prefix + ".00.b.array", "wb") as fh:
+        fh.write(np.array([a["start_point"], a["length"]], dtype="<u4").tobytes())
+        fh.write(a["values"].tobytes())
+    with open(prefix + ".reads", "wb") as fh:  # index-builder.c:189-194
+        for e, nm in zip(a["read_offsets"], a["names"]):
+            fh.write(b"%d\t%s\n" % (int(e), nm.encode()))
+
+
+def build_index(fasta_path, prefix, gapped=True, threshold=100, buckets=None, use_gpu=None):
+    """FASTA -> <prefix>.00.b.tab, <prefix>.00.b.array and <prefix>.reads.  Returns a summary dict."""
+    names, seqs = read_fasta_sanitised(fasta_path)
+    a = build_index_arrays(names, seqs, gapped, threshold, buckets, use_gpu)
+    write_index_files(prefix, a)
+    return dict(buckets=a["buckets_number"], items=a["n_items"], gap=a["index_gap"], removed_keys=a["removed_keys"],
+                length=a["length"], contigs=len(seqs))
