@@ -176,3 +176,45 @@ def test_larger_genome_against_oracle(kind, mapper, oracle_mod, tmp_path):
         assert (ver == over).all()
     if kind == "repeats":
         assert total_overflow > 0, "the repeat-rich case is meant to exercise the overflow path"
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference binaries) not built")
+def test_multi_block_index_merges_across_blocks(mapper, oracle_mod, tmp_path):
+    """read_chunk_circles (core.c:3567-3613) votes every chunk against each index block in turn and the
+    results merge in the bigtable; here the host loop reloads the block on the GPU and carries out_align."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 3, 400000, seed=5, repeats=150)
+    prefix = str(tmp_path / "idx")
+    subprocess.check_call([os.path.join(REF_DIR, "bin", "subread-buildindex"), "-o", prefix, "-M", "1", fa],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    n_blocks = len([f for f in os.listdir(tmp_path) if f.endswith(".b.tab")])
+    assert n_blocks > 1
+    gen_data.write_reads(fa, str(tmp_path / "pe"), 5000, 120, 2, True, 0.01, 0.2, True, 0.002)
+    chunk = load_fastq(str(tmp_path / "pe_R1.fastq"), str(tmp_path / "pe_R2.fastq"))
+    params = VoteParams.defaults(True)
+    got, ora = None, None
+    for b in range(n_blocks):
+        mapper.index_load(prefix, b)
+        got, _ = mapper.vote_chunk(chunk, params, out_align=None if got is None else got.reshape(-1))
+        idx = oracle_mod.OracleIndex(prefix, b)
+        ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora)
+        idx.close()
+        assert got.tobytes() == ora.tobytes(), f"block {b}"
+
+
+def test_index_builder_output_loads_and_maps(mapper, oracle_mod, tmp_path):
+    """An index written by subread_b200.index_build (GPU sort) is usable by both sides and gives the
+    golden result when built from the golden genome with the golden bucket count."""
+    from subread_b200.index_build import build_index, calculate_buckets_by_size
+    import json
+    nb = calculate_buckets_by_size(131072, 3)
+    prefix = str(tmp_path / "mine")
+    build_index(os.path.join(GOLDEN, "tiny.fa.gz"), prefix, gapped=True, buckets=nb, use_gpu=True)
+    cases = json.load(open(os.path.join(GOLDEN, "cases.json")))
+    case = next(c for c in cases if c["name"] == "pe_gapped")
+    _, chunk, params, exp = load_case(case, str(tmp_path))  # index dir unused
+    mapper.index_load(prefix, 0)
+    got, _ = mapper.vote_chunk(chunk, params)
+    assert got.tobytes() == exp.tobytes()
