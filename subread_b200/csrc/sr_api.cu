@@ -42,18 +42,21 @@ struct ChunkArgs {
 	uint32_t *queue;           // overflow queue
 	uint32_t *queue_count;
 	uint32_t *bad_reads;       // counter of reads whose (off,len) fall outside the text buffer
+	int out_zero;              // the bigtable slice is known to be all zero: do not read it
 };
 
-template <int MATES>
+template <int MATES, int GAP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_words, int chars_stride, int warp_bytes)
+k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_words, int warp_bytes)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
+	uint8_t *lut = smem;  // 256-entry character table shared by the block
+	fill_char_table(lut, threadIdx.x, blockDim.x);
+	__syncthreads();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	uint8_t *mine = smem + (size_t)warp * warp_bytes;
+	uint8_t *mine = smem + 256 + (size_t)warp * warp_bytes;
 	WarpShared<MATES> &ws = *reinterpret_cast<WarpShared<MATES> *>(mine);
-	uint32_t *packed = reinterpret_cast<uint32_t *>(mine + ((sizeof(WarpShared<MATES>) + 15) & ~size_t(15)));
-	uint8_t *chars = reinterpret_cast<uint8_t *>(packed + MATES * 3 * n_words);
+	uint32_t *area = reinterpret_cast<uint32_t *>(mine + ((sizeof(WarpShared<MATES>) + 15) & ~size_t(15)));
 	const int mb = cfg.multi_best_reads;
 
 	for (int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + warp; f < a.n_frags; f += (int64_t)gridDim.x * kWarpsPerBlock) {
@@ -72,8 +75,9 @@ k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_wor
 			if (lane == 0) atomicAdd(a.bad_reads, 1u);
 			continue;
 		}
-		bool ok = map_fragment<MATES>(ix, cfg, ws, chars, chars_stride, packed, n_words, a.text + o0, l0, a.text + o1, l1,
-		                              a.out + (size_t)f * MATES * mb, a.verify ? a.verify + (size_t)f * MATES * mb : nullptr, lane);
+		bool ok = map_fragment<MATES, GAP>(ix, cfg, ws, area, n_words, lut, a.text + o0, l0, a.text + o1, l1,
+		                                   a.out + (size_t)f * MATES * mb, a.out_zero != 0,
+		                                   a.verify ? a.verify + (size_t)f * MATES * mb : nullptr, lane);
 		if (!ok && lane == 0) a.queue[atomicAdd(a.queue_count, 1u)] = (uint32_t)f;
 		__syncwarp();
 	}
@@ -102,6 +106,11 @@ k_map_scalar(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int use
 		if (bad) {
 			if (!use_queue) atomicAdd(a.bad_reads, 1u);
 			continue;
+		}
+		if (a.out_zero) {
+			ResultWords *r = a.out + (size_t)f * mates * mb;
+			for (int k = 0; k < mates * mb; k++)
+				for (int w = 0; w < kResultWords; w++) r[k].w[w] = 0;
 		}
 		scalar_vote_fragment(ix, cfg, a.text + o0, l0, a.text + o1, l1, a.out + (size_t)f * mates * mb,
 		                     a.verify ? a.verify + (size_t)f * mates * mb : nullptr, scratch + tid);
@@ -226,6 +235,7 @@ int upload_index(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t 
 	if (!bucket_start || !keys || !vals || !values || !read_offsets || nb < 1 || total_offsets < 1)
 		return fail(h, SRCUDA_ERR_ARG, "srcuda_index_upload: null array or empty table");
 	if (index_gap < 1 || index_gap > 3) return fail(h, SRCUDA_ERR_UNSUPPORTED, "index gap %d not in 1..3", index_gap);
+	if (nb < 2) return fail(h, SRCUDA_ERR_UNSUPPORTED, "an index needs at least 2 buckets");
 	if (bucket_start[0] != 0 || bucket_start[nb] != (uint32_t)n_items) return fail(h, SRCUDA_ERR_ARG, "bucket_start does not span [0, n_items]");
 	for (uint32_t b = 0; b < nb; b++)  // the kernels trust this table: refuse a corrupt one here, not with a device fault
 		if (bucket_start[b] > bucket_start[b + 1]) return fail(h, SRCUDA_ERR_FORMAT, "bucket_start is not non-decreasing at bucket %u", b);
@@ -249,7 +259,7 @@ int upload_index(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t 
 	CU(h, cudaMemcpy(h->d_chr, read_offsets, sizeof(uint32_t) * (size_t)total_offsets, cudaMemcpyHostToDevice));
 	h->genome_words = gw;
 	sr::DevIndex &ix = h->ix;
-	ix.buckets_number = nb; ix.index_gap = index_gap; ix.padding = padding;
+	ix.buckets_number = nb; ix.buckets_magic = ~0ull / nb + 1; ix.index_gap = index_gap; ix.padding = padding;
 	ix.start_point = start_point; ix.length = length; ix.start_base_offset = start_point - start_point % 4;
 	ix.values_bytes = values_bytes; ix.total_offsets = total_offsets;
 	ix.bucket_start = (const uint32_t *)h->d_bucket_start; ix.keys = (const int16_t *)h->d_keys;
@@ -264,24 +274,47 @@ int upload_index(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t 
 }
 
 struct LaunchPlan {
-	int n_words, chars_stride, warp_bytes, smem_bytes, grid;
+	int n_words, warp_bytes, smem_bytes, grid;
 };
 
-template <int MATES>
+template <int MATES, int GAP>
 int plan_warp_launch(srcuda_handle *h, int max_len, LaunchPlan *p)
 {
 	p->n_words = (max_len + 15) / 16 + 1;
-	p->chars_stride = (max_len + 15) & ~15;
-	size_t wb = ((sizeof(sr::WarpShared<MATES>) + 15) & ~size_t(15)) + (size_t)MATES * 3 * p->n_words * 4 + (size_t)MATES * p->chars_stride;
+	size_t wb = ((sizeof(sr::WarpShared<MATES>) + 15) & ~size_t(15)) + (size_t)MATES * sr::packed_words_per_mate(p->n_words) * 4;
 	p->warp_bytes = (int)((wb + 15) & ~size_t(15));
-	p->smem_bytes = p->warp_bytes * sr::kWarpsPerBlock;
+	p->smem_bytes = 256 + p->warp_bytes * sr::kWarpsPerBlock;
 	if (p->smem_bytes > 227 * 1024) return fail(h, SRCUDA_ERR_UNSUPPORTED, "shared memory plan %d B exceeds 227 KB", p->smem_bytes);
-	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES, GAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
 	int per_sm = 0;
-	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES>, sr::kWarpsPerBlock * 32, p->smem_bytes));
+	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES, GAP>, sr::kWarpsPerBlock * 32, p->smem_bytes));
 	if (per_sm < 1) return fail(h, SRCUDA_ERR_CUDA, "warp kernel does not fit on an SM");
 	p->grid = h->sm_count * per_sm;  // persistent grid: a whole number of resident waves
 	return 0;
+}
+
+template <int MATES, int GAP>
+int launch_warp(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len)
+{
+	LaunchPlan p;
+	int rc = plan_warp_launch<MATES, GAP>(h, max_len, &p);
+	if (rc) return rc;
+	int64_t blocks_needed = (a.n_frags + sr::kWarpsPerBlock - 1) / sr::kWarpsPerBlock;
+	int grid = (int)std::min<int64_t>(p.grid, std::max<int64_t>(blocks_needed, 1));
+	sr::k_map_warp<MATES, GAP><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.warp_bytes);
+	CU(h, cudaGetLastError());
+	return 0;
+}
+
+template <int MATES>
+int launch_warp_gap(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len)
+{
+	switch (h->ix.index_gap) {
+	case 1: return launch_warp<MATES, 1>(h, s, cfg, a, max_len);
+	case 2: return launch_warp<MATES, 2>(h, s, cfg, a, max_len);
+	case 3: return launch_warp<MATES, 3>(h, s, cfg, a, max_len);
+	}
+	return fail(h, SRCUDA_ERR_UNSUPPORTED, "index gap %d not in 1..3", h->ix.index_gap);
 }
 
 // Enqueue the kernels of one launch on `s`.  ev[0..3] (optional) bracket warp and scalar kernels.
@@ -293,16 +326,8 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		CU(h, cudaMalloc((void **)&bs.scratch, sizeof(sr::ScalarScratch) * (size_t)scalar_grid * sr::kScalarThreads));
 	if (ev) CU(h, cudaEventRecord(ev[0], s));
 	if (!h->force_slow) {
-		LaunchPlan p;
-		int rc = cfg.is_paired ? plan_warp_launch<2>(h, max_len, &p) : plan_warp_launch<1>(h, max_len, &p);
+		int rc = cfg.is_paired ? launch_warp_gap<2>(h, s, cfg, a, max_len) : launch_warp_gap<1>(h, s, cfg, a, max_len);
 		if (rc) return rc;
-		int64_t blocks_needed = (a.n_frags + sr::kWarpsPerBlock - 1) / sr::kWarpsPerBlock;
-		int grid = (int)std::min<int64_t>(p.grid, std::max<int64_t>(blocks_needed, 1));
-		if (cfg.is_paired)
-			sr::k_map_warp<2><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.chars_stride, p.warp_bytes);
-		else
-			sr::k_map_warp<1><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.chars_stride, p.warp_bytes);
-		CU(h, cudaGetLastError());
 		h->timing.n_launches++;
 	}
 	if (ev) CU(h, cudaEventRecord(ev[1], s));
@@ -510,7 +535,7 @@ int srcuda_index_import_ipc(srcuda_handle *h, const void *blob, size_t blob_byte
 	}
 	h->genome_words = (size_t)b.genome_words;
 	sr::DevIndex &ix = h->ix;
-	ix.buckets_number = d.buckets_number; ix.index_gap = d.index_gap; ix.padding = d.padding;
+	ix.buckets_number = d.buckets_number; ix.buckets_magic = ~0ull / d.buckets_number + 1; ix.index_gap = d.index_gap; ix.padding = d.padding;
 	ix.start_point = d.start_point; ix.length = d.length; ix.start_base_offset = d.start_base_offset;
 	ix.values_bytes = d.values_bytes; ix.total_offsets = d.total_offsets;
 	ix.bucket_start = (const uint32_t *)h->d_bucket_start; ix.keys = (const int16_t *)h->d_keys;
@@ -563,7 +588,7 @@ int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out)
 }
 
 int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, const char *d_text, const uint64_t *d_off,
-                             const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len,
+                             const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len, int out_align_is_zero,
                              srcuda_mapping_result *d_out_align, srcuda_subjunc_result *d_out_junc, uint16_t *d_out_big_margin,
                              uint16_t *d_out_verify)
 {
@@ -593,6 +618,7 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	a.off = d_off; a.len = d_len; a.n_frags = n_frags;
 	a.out = (sr::ResultWords *)d_out_align; a.verify = d_out_verify;
 	a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
+	a.out_zero = out_align_is_zero ? 1 : 0;
 	rc = launch_vote(h, bs.stream, cfg, a, max_read_len, bs, h->events.data());
 	if (rc) return rc;
 	uint32_t counters[2] = {0, 0};
@@ -667,9 +693,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		CU(h, cudaMemcpyAsync(bs.off.p, off + r0, sizeof(uint64_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
 		CU(h, cudaMemcpyAsync(bs.len.p, len + r0, sizeof(uint16_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
 		h->timing.h2d_bytes += text_bytes + 10 * (uint64_t)nr;
-		if (out_align_is_zero) {
-			CU(h, cudaMemsetAsync(bs.out.p, 0, sizeof(srcuda_mapping_result) * n_slots, s));
-		} else {
+		if (!out_align_is_zero) {
 			CU(h, cudaMemcpyAsync(bs.out.p, out_align + (size_t)r0 * mb, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyHostToDevice, s));
 			h->timing.h2d_bytes += sizeof(srcuda_mapping_result) * n_slots;
 		}
@@ -679,6 +703,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		a.off = (const uint64_t *)bs.off.p; a.len = (const uint16_t *)bs.len.p; a.n_frags = nf;
 		a.out = (sr::ResultWords *)bs.out.p; a.verify = out_verify ? (uint16_t *)bs.verify.p : nullptr;
 		a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
+		a.out_zero = out_align_is_zero ? 1 : 0;
 		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[3 * bi]))) return rc;
 		CU(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
 		h->timing.d2h_bytes += sizeof(srcuda_mapping_result) * n_slots;

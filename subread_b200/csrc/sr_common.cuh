@@ -35,6 +35,7 @@ constexpr int kResultWords = 17;     // sizeof(mapping_result_t) / 4
 // One index block resident in HBM (SoA form of gehash_t + gene_value_index_t + gene_offset_t).
 struct DevIndex {
 	uint32_t buckets_number;
+	uint64_t buckets_magic;        // floor(2^64 / buckets_number) + 1: key / buckets = umul64hi(key, magic), exact for 32-bit keys
 	int32_t index_gap;
 	int32_t padding;
 	uint32_t start_point, length, start_base_offset, values_bytes;

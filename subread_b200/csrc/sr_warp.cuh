@@ -1,15 +1,17 @@
 // sr_warp.cuh -- the fused seed-and-vote kernel body: one warp maps one fragment.
 //
-//   pack      ASCII -> 2-bit codes for both strand passes (genekey2int / reverse_read semantics,
-//             input-files.c:1232,1113), staged in shared memory
-//   lookup    lane l owns lookup l of the subread schedule (core.c:3117-3171): bucket header
-//             gather, the reference's own (imin+imax)/2 search over the sorted int16 keys and the
-//             equal-key run (sorted-hashtable.c:947-981,1109-1119) -- up to 32 gathers in flight
-//             per warp, all from HBM-resident SoA arrays
-//   vote      the compact vote table lives in shared memory, slot s owned by lane s; every hit is
-//             broadcast and matched by all lanes at once, the first *accepting* slot in the
-//             reference's probe order is elected with __reduce_min_sync, so the sequential
-//             semantics of gehash_go_X (sorted-hashtable.c:984-1107) are reproduced exactly
+//   pack      ASCII -> 2-bit codes through a 256-entry shared-memory table (genekey2int / reverse_read
+//             semantics, input-files.c:1232,1113); the reverse-complement pass is derived from the
+//             forward words with bit operations (__brev + pair swap), never from the characters
+//   lookup    lane l owns lookup l of the subread schedule (core.c:3117-3171): bucket gather, the
+//             reference's own (imin+imax)/2 search over the sorted int16 keys and the equal-key run
+//             (sorted-hashtable.c:947-981,1109-1119) -- up to 32 gathers in flight per warp
+//   vote      the compact vote table lives in shared memory, slot s owned by lane s; a hit is
+//             broadcast and matched by all lanes at once.  When every hit of a batch of lookups
+//             agrees on one position the whole batch is applied at once (ballot / popc / reduce_max),
+//             which is provably what the sequential replay would leave; otherwise hits are replayed
+//             one by one and the first *accepting* slot in the reference's probe order is elected
+//             with __reduce_min_sync (gehash_go_X, sorted-hashtable.c:984-1107)
 //   top-K     process_voting_junction_PE_topK (core-junction.c:2199-2530) with warp reductions;
 //             pair combinations are scored lane-parallel
 //   verify    XOR + __popc of packed read vs packed genome (match_chro, gene-value-index.c:856)
@@ -54,48 +56,96 @@ struct WarpShared {
 	uint32_t comb[kMaxCombos];            // packed (score, r1, r2) after selection
 };
 
-struct WarpCtx {
-	int lane;
-	int nslots[2];
-	int max_vote[2];
-	bool overflow;
-};
-
-// 16-mer starting at base `o` of an MSB-first packed array (16 bases per word).
-SR_D uint32_t extract_key(const uint32_t *packed, int o)
-{
-#if defined(__CUDA_ARCH__)
-	int w = o >> 4, s = (o & 15) * 2;
-	return __funnelshift_l(packed[w + 1], packed[w], s);
-#else
-	(void)packed; (void)o; return 0;
-#endif
-}
+// Per-mate packed-read area in shared memory, in words: [pad][X: n_words][pad] [A0][A1][A2], see pack_read.
+__host__ __device__ constexpr int packed_words_per_mate(int n_words) { return 4 * n_words + 2; }
 
 #if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
 
-// ---- pack ------------------------------------------------------------------------------------
-// arrays: [0] pass 0 (as fetched), [1] pass 1 (after reverse_read), [2] pass 1 reversed again
-// (what find_new_indels / verification see for a positive-strand hit).  n_words per array.
-__device__ __forceinline__ void pack_read(const uint8_t *chars, int L, bool fetched_reversed, uint32_t *packed, int n_words,
-                                          int lane)
+// 256-entry character table: bits 0-1 base2int(c) on the sign-extended char (subread.h:238), bit 2 set
+// when reverse_read's table (input-files.c:1111) maps c to a base (A, C, G, T, U) rather than to 'N'.
+__device__ __forceinline__ void fill_char_table(uint8_t *lut, int tid, int nthreads)
 {
-	for (int k = lane; k < n_words; k += 32) {
-		uint32_t w0 = 0, w1 = 0, w2 = 0;
-#pragma unroll 4
-		for (int t = 0; t < 16; t++) {
-			int i = 16 * k + t;
-			int a = 2, b = 2, c = 2;  // beyond the read: NUL -> base2int 2
-			if (i < L) {
-				int cf = (int)(int8_t)chars[i], cr = (int)(int8_t)chars[L - 1 - i];
-				if (!fetched_reversed) { a = base_code(cf); b = rc_code(cr); c = rcrc_code(cf); }
-				else { a = rc_code(cr); b = rcrc_code(cf); c = a; }
-			}
-			int sh = 30 - 2 * t;
-			w0 |= (uint32_t)a << sh; w1 |= (uint32_t)b << sh; w2 |= (uint32_t)c << sh;
-		}
-		packed[k] = w0; packed[n_words + k] = w1; packed[2 * n_words + k] = w2;
+	for (int c = tid; c < 256; c += nthreads) {
+		int sc = (int)(int8_t)c;
+		lut[c] = (uint8_t)(base_code(sc) | (is_table_base(sc) ? 4 : 0));
 	}
+}
+
+// 16-mer starting at base `o` of an MSB-first packed array (16 bases per word).
+__device__ __forceinline__ uint32_t extract_key(const uint32_t *packed, int o)
+{
+	int w = o >> 4, s = (o & 15) * 2;
+	return __funnelshift_l(packed[w + 1], packed[w], s);
+}
+
+__device__ __forceinline__ uint32_t reverse_bases(uint32_t g)
+{
+	uint32_t r = __brev(g);
+	return ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+}
+
+// ---- pack ------------------------------------------------------------------------------------
+// Builds, for one mate, three MSB-first packed arrays of n_words words each:
+//   A0  pass 0 (the read as fetched: reversed at fetch when the mate's strand flag says so)
+//   A1  pass 1 (after do_voting's reverse_read, core.c:3229-3234)
+//   A2  pass 1 reversed once more = what find_new_indels and the verification see for a
+//       positive-strand hit (non-bases have become N, code 3)
+// With F = base2int codes of the raw characters and V = 11 per base where the character is a base:
+//   raw forward            F
+//   reverse_read(raw)      REV(~F | ~V)         (complement 3-f for bases, N=3 otherwise)
+//   reverse_read twice     F | ~V
+// Bases beyond the read are NUL in the reference's buffer, i.e. code 2.
+__device__ __forceinline__ void pack_read(const uint8_t *raw, int L, bool fetched_reversed, uint32_t *area, int n_words,
+                                          const uint8_t *lut, int lane)
+{
+	uint32_t *X = area + 1;                 // X[-1] and X[n_words] are zero pads
+	uint32_t *A0 = area + n_words + 2, *A1 = A0 + n_words, *A2 = A1 + n_words;
+	if (lane == 0) { area[0] = 0; area[n_words + 1] = 0; }
+	const uintptr_t p0 = (uintptr_t)raw, pend = p0 + (uintptr_t)L;
+	for (int k = lane; k < n_words; k += 32) {
+		uint32_t f = 0xAAAAAAAAu, v = 0;
+		const int nvalid = min(16, max(0, L - 16 * k));
+		if (nvalid > 0) {
+			const uintptr_t p = p0 + 16u * (uintptr_t)k;
+			const uintptr_t a = p & ~(uintptr_t)3;
+			const unsigned mis = (unsigned)(p & 3) * 8u;
+			uint32_t w[5];
+#pragma unroll
+			for (int q = 0; q < 5; q++) w[q] = (a + 4u * q < pend) ? __ldg((const uint32_t *)(a + 4u * q)) : 0u;
+			f = 0; v = 0;
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				uint32_t c4 = __funnelshift_r(w[q], w[q + 1], mis);
+#pragma unroll
+				for (int b = 0; b < 4; b++) {
+					const int t = 4 * q + b;
+					uint32_t ch = (c4 >> (8 * b)) & 0xffu;
+					if (t >= nvalid) ch = 0;
+					const uint32_t e = lut[ch];
+					f |= (e & 3u) << (30 - 2 * t);
+					v |= ((e >> 2) * 3u) << (30 - 2 * t);
+				}
+			}
+		}
+		const uint32_t keep = nvalid >= 16 ? 0xffffffffu : (nvalid <= 0 ? 0u : ~(0xffffffffu >> (2 * nvalid)));
+		const uint32_t d = ((f | ~v) & keep) | (0xAAAAAAAAu & ~keep);   // reversed twice
+		X[k] = ~f | ~v;
+		if (!fetched_reversed) { A0[k] = f; A2[k] = d; } else { A1[k] = d; }
+	}
+	__syncwarp();
+	for (int k = lane; k < n_words; k += 32) {
+		const int nvalid = min(16, max(0, L - 16 * k));
+		uint32_t r = 0xAAAAAAAAu;
+		if (nvalid > 0) {
+			const int s = L - 16 - 16 * k;              // first source base of this word (may be < 0)
+			const int w = s >> 4, sh = (s & 15) * 2;
+			r = reverse_bases(__funnelshift_l(X[w + 1], X[w], sh));
+			const uint32_t keep = nvalid >= 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * nvalid));
+			r = (r & keep) | (0xAAAAAAAAu & ~keep);
+		}
+		if (!fetched_reversed) A1[k] = r; else { A0[k] = r; A2[k] = r; }
+	}
+	__syncwarp();
 }
 
 // ---- one hit through the vote table ----------------------------------------------------------
@@ -110,102 +160,77 @@ struct SlotRegs {
 	int row, j, marked;
 };
 
-__device__ __forceinline__ void vote_hit(WarpTable &T, SlotRegs &S, uint32_t *shift_locs, int &shift_n, int &nslots, int &max_vote,
-                                         bool &overflow, const HitEnv &E, uint32_t kv, int offset, int sub_p1)
+struct TableState {
+	int nslots, max_vote, shift_n;
+	bool overflow;
+};
+
+// The reference's update of one matching slot (sorted-hashtable.c:1020-1070), executed by the lane
+// that owns the slot.  Returns acc | mk << 1 | new_votes << 2.
+__device__ __forceinline__ int slot_accept(WarpTable &T, SlotRegs &S, uint32_t *shift_locs, int shift_n, const HitEnv &E, int d,
+                                           int offset, int sub_p1)
 {
 	const int lane = E.lane;
-	const bool valid = lane < nslots;
-	const int d = (int)(kv - S.pos);
-	const int t = (E.round > 0 && S.marked) ? 0 : E.tol;
-	const uint32_t home = vote_row(kv);
-
-	// probe order of sorted-hashtable.c:1007: iix = 0,+5,-5,+10,-10,... ; rank = position of my row
-	int rank = 99;
-	{
-		int p = 0;
-		for (int iix = 0; iix <= E.ii_end; iix = iix > 0 ? -iix : (-iix + kSeg), p++) {
-			uint32_t r = iix ? vote_row(kv + (uint32_t)iix) : home;
-			if (rank == 99 && (uint32_t)S.row == r) rank = p;
+	int acc = 0, mk = 0, nv = 0;
+	int toli = T.toli[lane];
+	if (E.round == 0 && toli > 0 && d == 0 && !S.marked) {
+		S.marked = 1;
+		shift_locs[shift_n] = S.pos;
+		mk = 1;
+	}
+	int last = T.last_cluster[lane];
+	if (sub_p1 == last && toli > 0) {  // roll back the previous indel section (:1027-1039)
+		int move = toli >= 3 ? T.rec[lane][toli - 1] : 0;
+		int nd = move;
+		move -= T.rec[lane][toli + 2];
+		nd -= d;
+		if (abs(move) > abs(nd)) {
+			toli -= 3;
+			T.toli[lane] = (int8_t)toli;
+			last--;
+			T.last_cluster[lane] = (int16_t)last;
+			T.votes[lane]--;
 		}
 	}
-	bool cand = valid && d >= -t && d <= t && rank != 99;
-	const int key = rank * 32 + S.j;
-	bool accepted = false;
-
-	unsigned cm = __ballot_sync(kFull, cand);
-	while (cm) {
-		int best = __reduce_min_sync(kFull, cand ? key : 0x7fffffff);
-		bool is_w = cand && key == best;
-		int acc = 0, mk = 0, nv = 0;
-		if (is_w) {  // exactly one lane: the reference's body of :1020-1070 on its own slot
-			int toli = T.toli[lane];
-			if (E.round == 0 && toli > 0 && d == 0 && !S.marked) {
-				S.marked = 1;
-				shift_locs[shift_n] = S.pos;
-				mk = 1;
+	if (!(sub_p1 <= last)) {
+		nv = T.votes[lane] + 1;
+		T.votes[lane] = (int16_t)nv;
+		if (offset + 16 > T.cov_end[lane]) T.cov_end[lane] = (int16_t)(offset + 16);
+		if (d == T.cursor[lane]) {
+			T.rec[lane][toli + 1] = (int16_t)sub_p1;
+		} else {
+			toli += 3;
+			if (toli < kMaxSections * 3) {
+				T.toli[lane] = (int8_t)toli;
+				T.rec[lane][toli] = (int16_t)sub_p1;
+				T.rec[lane][toli + 1] = (int16_t)sub_p1;
+				T.rec[lane][toli + 2] = (int16_t)d;
+				if (toli < kMaxSections * 3 - 3) T.rec[lane][toli + 3] = 0;
 			}
-			int last = T.last_cluster[lane];
-			if (sub_p1 == last && toli > 0) {
-				int move = toli >= 3 ? T.rec[lane][toli - 1] : 0;
-				int nd = move;
-				move -= T.rec[lane][toli + 2];
-				nd -= d;
-				if (abs(move) > abs(nd)) {
-					toli -= 3;
-					T.toli[lane] = (int8_t)toli;
-					last--;
-					T.last_cluster[lane] = (int16_t)last;
-					T.votes[lane]--;
-				}
-			}
-			if (!(sub_p1 <= last)) {
-				nv = T.votes[lane] + 1;
-				T.votes[lane] = (int16_t)nv;
-				if (offset + 16 > T.cov_end[lane]) T.cov_end[lane] = (int16_t)(offset + 16);
-				if (d == T.cursor[lane]) {
-					T.rec[lane][toli + 1] = (int16_t)sub_p1;
-				} else {
-					toli += 3;
-					if (toli < kMaxSections * 3) {
-						T.toli[lane] = (int8_t)toli;
-						T.rec[lane][toli] = (int16_t)sub_p1;
-						T.rec[lane][toli + 1] = (int16_t)sub_p1;
-						T.rec[lane][toli + 2] = (int16_t)d;
-						if (toli < kMaxSections * 3 - 3) T.rec[lane][toli + 3] = 0;
-					}
-					T.cursor[lane] = (int8_t)d;
-				}
-				T.last_cluster[lane] = (int16_t)sub_p1;
-				acc = 1;
-			}
+			T.cursor[lane] = (int8_t)d;
 		}
-		unsigned wm = __ballot_sync(kFull, is_w);
-		int w = __ffs(wm) - 1;
-		acc = __shfl_sync(kFull, acc, w);
-		mk = __shfl_sync(kFull, mk, w);
-		nv = __shfl_sync(kFull, nv, w);
-		if (mk) shift_n++;
-		if (acc) {
-			if (max_vote < nv) max_vote = nv;
-			accepted = true;
-			break;
-		}
-		cand = cand && !is_w;
-		cm = __ballot_sync(kFull, cand);
+		T.last_cluster[lane] = (int16_t)sub_p1;
+		acc = 1;
 	}
-	if (accepted) return;
+	return acc | (mk << 1) | (nv << 2);
+}
 
-	// no accepting slot: open a new one in the home row (:1074-1106)
+// Open a new slot in the home row of kv (sorted-hashtable.c:1074-1106).  Warp-uniform.
+__device__ __forceinline__ void slot_create(WarpTable &T, SlotRegs &S, const uint32_t *shift_locs, TableState &st, const HitEnv &E,
+                                            uint32_t kv, int offset, int sub_p1)
+{
+	const int lane = E.lane;
 	if (!(kv >= E.low_border && kv <= E.high_border)) return;
-	int in_home = __popc(__ballot_sync(kFull, valid && (uint32_t)S.row == home));
+	const uint32_t home = vote_row(kv);
+	const int in_home = __popc(__ballot_sync(kFull, lane < st.nslots && (uint32_t)S.row == home));
 	if (in_home >= kVoteSpace) return;
-	if (nslots == kWarpSlots) { overflow = true; return; }
+	if (st.nslots == kWarpSlots) { st.overflow = true; return; }
 	int mk = 0;
 	if (E.round > 0) {
-		bool near = lane < shift_n && kv >= shift_locs[lane] - (uint32_t)E.tol && kv <= shift_locs[lane] + (uint32_t)E.tol;
+		bool near = lane < st.shift_n && kv >= shift_locs[lane] - (uint32_t)E.tol && kv <= shift_locs[lane] + (uint32_t)E.tol;
 		mk = __any_sync(kFull, near) ? 1 : 0;
 	}
-	if (lane == nslots) {
+	if (lane == st.nslots) {
 		S.pos = kv; S.row = (int)home; S.j = in_home; S.marked = mk;
 		T.votes[lane] = 1;
 		T.toli[lane] = 0;
@@ -215,12 +240,145 @@ __device__ __forceinline__ void vote_hit(WarpTable &T, SlotRegs &S, uint32_t *sh
 		T.cov_end[lane] = (int16_t)(offset + 16);
 		T.last_cluster[lane] = (int16_t)sub_p1;
 	}
-	nslots++;
-	if (max_vote == 0) max_vote = 1;
+	st.nslots++;
+	if (st.max_vote == 0) st.max_vote = 1;
+}
+
+// Position of my slot's row in the probe order iix = 0,+5,-5,+10,-10,... (sorted-hashtable.c:1007);
+// 99 when the row is not probed.  The closed form holds whenever kv +- ii_end does not wrap.
+__device__ __forceinline__ int probe_rank(uint32_t kv, int my_row, int ii_end)
+{
+	if (kv >= 32u && kv <= 0xffffffdfu) {
+		int r0 = (int)((kv / kSeg) % kVoteRows);
+		int delta = my_row - r0;
+		if (delta < 0) delta += kVoteRows;
+		int side = ii_end / kSeg;
+		if (delta == 0) return 0;
+		if (delta <= side) return 2 * delta - 1;
+		if (delta >= kVoteRows - side) return 2 * (kVoteRows - delta);
+		return 99;
+	}
+	int rank = 99, p = 0;
+	for (int iix = 0; iix <= ii_end; iix = iix > 0 ? -iix : (-iix + kSeg), p++) {
+		uint32_t r = vote_row(kv + (uint32_t)iix);
+		if (rank == 99 && (uint32_t)my_row == r) rank = p;
+	}
+	return rank;
+}
+
+__device__ __forceinline__ void vote_hit(WarpTable &T, SlotRegs &S, uint32_t *shift_locs, TableState &st, const HitEnv &E, uint32_t kv,
+                                         int offset, int sub_p1)
+{
+	const int lane = E.lane;
+	const bool valid = lane < st.nslots;
+	const int d = (int)(kv - S.pos);
+	const int t = (E.round > 0 && S.marked) ? 0 : E.tol;
+	bool cand = valid && d >= -t && d <= t;
+	unsigned cm = __ballot_sync(kFull, cand);
+	const bool edge = !(kv >= 32u && kv <= 0xffffffdfu);
+	if (cm != 0 && ((cm & (cm - 1)) != 0 || edge)) {
+		// two or more slots within tolerance (or u32 wrap-around): order them as the reference probes them
+		const int rank = probe_rank(kv, S.row, E.ii_end);
+		cand = cand && rank != 99;
+		const int key = rank * 32 + S.j;
+		cm = __ballot_sync(kFull, cand);
+		while (cm) {
+			const int best = __reduce_min_sync(kFull, cand ? key : 0x7fffffff);
+			const bool is_w = cand && key == best;
+			int res = 0;
+			if (is_w) res = slot_accept(T, S, shift_locs, st.shift_n, E, d, offset, sub_p1);
+			const int w = __ffs(__ballot_sync(kFull, is_w)) - 1;
+			res = __shfl_sync(kFull, res, w);
+			if (res & 2) st.shift_n++;
+			if (res & 1) {
+				if (st.max_vote < (res >> 2)) st.max_vote = res >> 2;
+				return;
+			}
+			cand = cand && !is_w;
+			cm = __ballot_sync(kFull, cand);
+		}
+	} else if (cm != 0) {
+		// exactly one slot within tolerance: it is necessarily in a probed row (|d| <= tol <= ii_end)
+		const int w = __ffs(cm) - 1;
+		int res = 0;
+		if (lane == w) res = slot_accept(T, S, shift_locs, st.shift_n, E, d, offset, sub_p1);
+		res = __shfl_sync(kFull, res, w);
+		if (res & 2) st.shift_n++;
+		if (res & 1) {
+			if (st.max_vote < (res >> 2)) st.max_vote = res >> 2;
+			return;
+		}
+	}
+	slot_create(T, S, shift_locs, st, E, kv, offset, sub_p1);
+}
+
+// A batch of hits (one per lane in `hm`, lanes in lookup order) that all point at the same kv and come
+// from strictly increasing subreads.  If no slot is within tolerance, or exactly one is and it sits
+// at distance 0 with indel cursor 0 and an older subread, the sequential replay of the batch is: (create
+// the slot with the first hit,) then every further hit takes the simple branch of :1041-1052 --
+// votes++, coverage_end = max, recorder[toli+1] = last_subread_cluster = its subread.  That end state
+// is written here in one step.  Returns false (and changes nothing) when the batch does not qualify.
+__device__ __forceinline__ bool vote_batch_uniform(WarpTable &T, SlotRegs &S, uint32_t *shift_locs, TableState &st, const HitEnv &E,
+                                                   unsigned hm, uint32_t kv, int my_offset, int my_sub_p1)
+{
+	const int lane = E.lane;
+	if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;
+	const bool valid = lane < st.nslots;
+	const int d = (int)(kv - S.pos);
+	const int t = (E.round > 0 && S.marked) ? 0 : E.tol;
+	const unsigned cm = __ballot_sync(kFull, valid && d >= -t && d <= t);
+	const int first = __ffs(hm) - 1, n_hits = __popc(hm);
+	const bool mine = (hm >> lane) & 1u;
+	const int sub_first = __shfl_sync(kFull, my_sub_p1, first);
+	const int off_first = __shfl_sync(kFull, my_offset, first);
+	const int off_max = __reduce_max_sync(kFull, mine ? my_offset : 0);
+	const int sub_last = __reduce_max_sync(kFull, mine ? my_sub_p1 : 0);
+	if (cm == 0) {
+		const int before = st.nslots;
+		slot_create(T, S, shift_locs, st, E, kv, off_first, sub_first);
+		if (st.overflow) return true;
+		if (st.nslots == before) return true;   // outside the block or row full: every hit of the batch is dropped alike
+		if (n_hits > 1) {
+			if (lane == before) {
+				T.votes[lane] = (int16_t)n_hits;
+				T.cov_end[lane] = (int16_t)(off_max + 16);
+				T.rec[lane][1] = (int16_t)sub_last;
+				T.last_cluster[lane] = (int16_t)sub_last;
+			}
+			if (st.max_vote < n_hits) st.max_vote = n_hits;
+		}
+		return true;
+	}
+	if (cm & (cm - 1)) return false;
+	const int w = __ffs(cm) - 1;
+	int ok = 0, res = 0;
+	if (lane == w) ok = (d == 0 && T.cursor[lane] == 0 && (int)T.last_cluster[lane] < sub_first) ? 1 : 0;
+	ok = __shfl_sync(kFull, ok, w);
+	if (!ok) return false;
+	if (lane == w) {
+		const int toli = T.toli[lane];
+		int mk = 0;
+		if (E.round == 0 && toli > 0 && !S.marked) {
+			S.marked = 1;
+			shift_locs[st.shift_n] = S.pos;
+			mk = 1;
+		}
+		const int nv = T.votes[lane] + n_hits;
+		T.votes[lane] = (int16_t)nv;
+		if (off_max + 16 > T.cov_end[lane]) T.cov_end[lane] = (int16_t)(off_max + 16);
+		T.rec[lane][toli + 1] = (int16_t)sub_last;
+		T.last_cluster[lane] = (int16_t)sub_last;
+		res = mk | (nv << 1);
+	}
+	res = __shfl_sync(kFull, res, w);
+	if (res & 1) st.shift_n++;
+	if (st.max_vote < (res >> 1)) st.max_vote = res >> 1;
+	return true;
 }
 
 // ---- lookup + vote for one mate and one strand pass --------------------------------------------
 // Returns applied_subreads.  Leaves the table in T (pos/row/j flushed from registers).
+template <int GAP>
 __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *packed /* this pass */, int L,
                                          WarpTable &T, uint32_t *shift_locs, int lane, int &nslots_out, int &max_vote_out,
                                          bool &overflow)
@@ -228,10 +386,9 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 	nslots_out = 0;
 	max_vote_out = 0;
 	if (L < 16) return 0;  // core.c:3116 (the reference leaves a stale table here; we define it empty)
-	const int gap = ix.index_gap;
 	int step;
-	const int applied = subread_schedule(L, gap, cfg.total_subreads, &step);
-	const int n_lk = applied * gap;
+	const int applied = subread_schedule(L, GAP, cfg.total_subreads, &step);
+	const int n_lk = applied * GAP;
 	HitEnv E;
 	E.tol = cfg.indel_tolerance;
 	E.ii_end = kSeg;
@@ -240,23 +397,27 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 	E.low_border = cfg.low_border;
 	E.high_border = cfg.high_border - (uint32_t)L;
 	const uint32_t nb = ix.buckets_number;
+	const uint64_t nb_magic = ix.buckets_magic;
 
-	int shift_n = 0;
-	int nslots = 0, max_vote = 0;
+	TableState st;
+	st.shift_n = 0;
+	st.overflow = false;
 	SlotRegs S;
 	for (int round = 0; round < 2; round++) {  // core.c:3153-3186
 		E.round = round;
-		nslots = 0; max_vote = 0;
+		st.nslots = 0; st.max_vote = 0;
 		S.pos = 0; S.row = 255; S.j = 0; S.marked = 0;
 		for (int base = 0; base < n_lk; base += 32) {
 			const int l = base + lane;
+			const int my_sub_p1 = l / GAP + 1;
 			int o = 0, h = 0, land = 0;
 			uint32_t run_abs = 0, firstval = 0;
 			if (l < n_lk) {
-				o = lookup_offset(l, gap, step);
+				o = lookup_offset(l, GAP, step);
 				const uint32_t key = extract_key(packed, o);
-				const uint32_t b = key % nb;
-				const int k16 = (int)(int16_t)(key / nb);
+				const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, nb_magic);   // key / nb, exact (sr_api.cu)
+				const uint32_t b = key - q * nb;
+				const int k16 = (int)(int16_t)q;
 				const uint32_t lo = __ldg(ix.bucket_start + b);
 				const int items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
 				if (items > 0) {
@@ -282,18 +443,37 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 					}
 				}
 			}
-			// replay the hits of this batch of lookups in lookup order, each run in visit order
 			unsigned fm = __ballot_sync(kFull, h > 0);
+			if (fm == 0) continue;
+			// fast path: every hit is a single value, all agree on one position, subreads strictly increase
+			{
+				const uint32_t kv = firstval - (uint32_t)o;
+				const int first = __ffs(fm) - 1;
+				const uint32_t kv0 = __shfl_sync(kFull, kv, first);
+				// two hit lanes of the same subread (GAP lookups each) must be replayed one by one
+				bool clash = h > 1 || (h > 0 && kv != kv0);
+				if (GAP > 1) {
+					const unsigned same_sub = __match_any_sync(kFull, h > 0 ? my_sub_p1 : 0x10000 + lane);
+					clash = clash || (same_sub & (same_sub - 1)) != 0;
+				}
+				if (!__any_sync(kFull, clash)) {
+					if (vote_batch_uniform(T, S, shift_locs, st, E, fm, kv0, o, my_sub_p1)) {
+						if (st.overflow) { overflow = true; return applied; }
+						continue;
+					}
+				}
+			}
+			// replay the hits of this batch of lookups in lookup order, each run in visit order
 			while (fm) {
 				const int src = __ffs(fm) - 1;
 				fm &= fm - 1;
 				const int o_s = __shfl_sync(kFull, o, src);
 				const int h_s = __shfl_sync(kFull, h, src);
-				const int sub_p1 = (base + src) / gap + 1;
+				const int sub_p1 = __shfl_sync(kFull, my_sub_p1, src);
 				if (h_s == 1) {
 					const uint32_t v = __shfl_sync(kFull, firstval, src);
-					vote_hit(T, S, shift_locs, shift_n, nslots, max_vote, overflow, E, v - (uint32_t)o_s, o_s, sub_p1);
-					if (overflow) return applied;
+					vote_hit(T, S, shift_locs, st, E, v - (uint32_t)o_s, o_s, sub_p1);
+					if (st.overflow) { overflow = true; return applied; }
 				} else {
 					const int land_s = __shfl_sync(kFull, land, src);
 					const uint32_t run_s = __shfl_sync(kFull, run_abs, src);
@@ -308,22 +488,22 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 						const int cnt = min(32, h_s - c);
 						for (int u = 0; u < cnt; u++) {
 							const uint32_t vu = __shfl_sync(kFull, v, u);
-							vote_hit(T, S, shift_locs, shift_n, nslots, max_vote, overflow, E, vu - (uint32_t)o_s, o_s, sub_p1);
-							if (overflow) return applied;
+							vote_hit(T, S, shift_locs, st, E, vu - (uint32_t)o_s, o_s, sub_p1);
+							if (st.overflow) { overflow = true; return applied; }
 						}
 					}
 				}
 			}
 		}
 		__syncwarp();
-		if (shift_n == 0) break;
+		if (st.shift_n == 0) break;
 	}
 	T.pos[lane] = S.pos;
 	T.row[lane] = (uint8_t)S.row;
 	T.j[lane] = (uint8_t)S.j;
 	__syncwarp();
-	nslots_out = nslots;
-	max_vote_out = max_vote;
+	nslots_out = st.nslots;
+	max_vote_out = st.max_vote;
 	return applied;
 }
 
@@ -525,8 +705,7 @@ __device__ __forceinline__ int match_packed(const DevIndex &ix, const uint32_t *
 	int cnt = 0;
 	const int n_words = (L + 15) >> 4;
 	for (int k = lane; k < n_words; k += 32) {
-		uint32_t r = __brev(packed[k]);                                   // base order LSB-first ...
-		r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);          // ... bits inside a base restored
+		const uint32_t r = reverse_bases(packed[k]);   // base order LSB-first like the genome array
 		const uint32_t q = q0 + 16u * (uint32_t)k;
 		const uint32_t gw = q >> 4, sh = (q & 15u) * 2u;
 		const uint32_t g = __funnelshift_r(__ldg(ix.genome + gw), __ldg(ix.genome + gw + 1), sh);
@@ -540,31 +719,31 @@ __device__ __forceinline__ int match_packed(const DevIndex &ix, const uint32_t *
 }
 
 // ---- one fragment ------------------------------------------------------------------------------
-// chars: MATES * chars_stride bytes; packed: MATES * 3 * n_words words (all per-warp shared memory).
+// area: MATES * packed_words_per_mate(n_words) words of per-warp shared memory.
 // Returns false when the fragment overflowed the shared-memory table (nothing was written).
-template <int MATES>
-__device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, uint8_t *chars,
-                                             int chars_stride, uint32_t *packed, int n_words, const uint8_t *raw0, int len0,
-                                             const uint8_t *raw1, int len1, ResultWords *out /* global, this fragment */,
+template <int MATES, int GAP>
+__device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, uint32_t *area,
+                                             int n_words, const uint8_t *lut, const uint8_t *raw0, int len0, const uint8_t *raw1,
+                                             int len1, ResultWords *out /* global, this fragment */, bool out_is_zero,
                                              uint16_t *verify /* global or null */, int lane)
 {
 	const int mb = cfg.multi_best_reads;
 	const int rlen[2] = {len0, len1};
 	const uint8_t *raw[2] = {raw0, raw1};
+	const int per_mate = packed_words_per_mate(n_words);
+	uint32_t *res_flat = &ws.res[0][0].w[0];
 
-	for (int w = lane; w < MATES * mb * kResultWords; w += 32) {  // old results (read-modify-write)
-		int s = w / kResultWords, k = w - s * kResultWords;
-		ws.res[s / mb][s % mb].w[k] = out[s].w[k];
+	// old results (read-modify-write): ws.res is [MATES][kMaxBest] slots, the bigtable [MATES][mb]
+	if (mb == kMaxBest) {
+		for (int w = lane; w < MATES * kMaxBest * kResultWords; w += 32) res_flat[w] = out_is_zero ? 0u : (&out[0].w[0])[w];
+	} else {
+		for (int w = lane; w < MATES * mb * kResultWords; w += 32) {
+			int s = w / kResultWords, k = w - s * kResultWords;
+			ws.res[s / mb][s % mb].w[k] = out_is_zero ? 0u : out[s].w[k];
+		}
 	}
-	for (int m = 0; m < MATES; m++) {
-		uint8_t *cm = chars + m * chars_stride;
-		for (int i = lane; i < rlen[m]; i += 32) cm[i] = raw[m][i];
-	}
-	__syncwarp();
 	for (int m = 0; m < MATES; m++)
-		pack_read(chars + m * chars_stride, rlen[m], m == 0 ? cfg.first_reversed != 0 : cfg.second_reversed != 0,
-		          packed + m * 3 * n_words, n_words, lane);
-	__syncwarp();
+		pack_read(raw[m], rlen[m], m == 0 ? cfg.first_reversed != 0 : cfg.second_reversed != 0, area + m * per_mate, n_words, lut, lane);
 
 	int all_subreads[2] = {0, 0};
 	bool overflow = false;
@@ -572,8 +751,8 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 		int nslots[2] = {0, 0}, max_vote[2] = {0, 0};
 		int applied = 0;
 		for (int m = 0; m < MATES; m++) {
-			applied = vote_mate(ix, cfg, packed + (m * 3 + strand) * n_words, rlen[m], ws.tab[m], ws.shift_locs, lane, nslots[m],
-			                    max_vote[m], overflow);
+			const uint32_t *pass = area + m * per_mate + n_words + 2 + strand * n_words;
+			applied = vote_mate<GAP>(ix, cfg, pass, rlen[m], ws.tab[m], ws.shift_locs, lane, nslots[m], max_vote[m], overflow);
 			if (rlen[m] >= 16) all_subreads[m] = applied;
 			if (overflow) return false;
 		}
@@ -587,9 +766,13 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 		__syncwarp();
 	}
 
-	for (int w = lane; w < MATES * mb * kResultWords; w += 32) {
-		int s = w / kResultWords, k = w - s * kResultWords;
-		out[s].w[k] = ws.res[s / mb][s % mb].w[k];
+	if (mb == kMaxBest) {
+		for (int w = lane; w < MATES * kMaxBest * kResultWords; w += 32) (&out[0].w[0])[w] = res_flat[w];
+	} else {
+		for (int w = lane; w < MATES * mb * kResultWords; w += 32) {
+			int s = w / kResultWords, k = w - s * kResultWords;
+			out[s].w[k] = ws.res[s / mb][s % mb].w[k];
+		}
 	}
 	if (verify) {
 		for (int m = 0; m < MATES; m++)
@@ -598,7 +781,8 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 				int v = 0xffff;
 				if (result_votes(r) >= 1) {
 					bool neg = (r.w[1] & kCoreNegStrand) != 0;
-					v = match_packed(ix, packed + (m * 3 + (neg ? 1 : 2)) * n_words, rlen[m], r.w[0], lane);
+					const uint32_t *arr = area + m * per_mate + n_words + 2 + (neg ? 1 : 2) * n_words;
+					v = match_packed(ix, arr, rlen[m], r.w[0], lane);
 				}
 				if (lane == 0) verify[m * mb + k] = (uint16_t)v;
 			}

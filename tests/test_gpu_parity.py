@@ -124,6 +124,13 @@ def test_device_resident_entry_point(mapper, golden_cases, golden_index_dir):
     got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=MAPPING_RESULT)
     assert got.tobytes() == exp.tobytes()
     assert mapper.timing().ms_kernel_vote > 0
+    # out_is_zero: the slice is not read, so stale contents must not matter
+    d_out.fill_(0xAB)
+    torch.cuda.synchronize()
+    mapper.vote_chunk_device(params, d_text.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), chunk.n_frags, False,
+                             int(chunk.len.max()), d_out.data_ptr(), out_is_zero=True)
+    got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=MAPPING_RESULT)
+    assert got.tobytes() == exp.tobytes()
 
 
 def test_errors_are_loud(mapper, golden_cases, golden_index_dir):
