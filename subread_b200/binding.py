@@ -14,7 +14,7 @@ import numpy as np
 from .layout import MAPPING_RESULT, VoteParams
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsubread_cuda.so")
+LIB_PATH = os.environ.get("SRCUDA_LIB") or os.path.join(_PKG, "libsubread_cuda.so")  # SRCUDA_LIB: A/B builds while tuning
 _LIB = None
 
 EXPORTS = [

@@ -25,6 +25,9 @@
 namespace sr {
 
 constexpr int kWarpsPerBlock = 8;
+#ifndef SR_MIN_BLOCKS
+#define SR_MIN_BLOCKS 5   // resident blocks (x 8 warps) per SM the register allocation is planned for: the kernel is latency-bound, 40 warps beat 24 (A/B in profiles/)
+#endif
 constexpr int kScalarThreads = 32;
 constexpr int kScalarBlocksPerSM = 1;
 
@@ -46,7 +49,7 @@ struct ChunkArgs {
 };
 
 template <int MATES, int GAP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, SR_MIN_BLOCKS)
 k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_words, int warp_bytes)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -117,6 +120,33 @@ k_map_scalar(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int use
 	}
 }
 
+// Derives the two lookup accelerators from the resident SoA index, one thread per bucket:
+// a 16-bit Bloom word (bit key16 & 15) and the 32-byte inline record (sr_common.cuh).
+__global__ void k_build_records(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, uint4 *records,
+                                uint16_t *bloom)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
+		if (bloom) {
+			uint32_t bl = 0;
+			for (uint32_t i = 0; i < n; i++) bl |= 1u << ((int)keys[lo + i] & 15);
+			bloom[b] = (uint16_t)bl;
+		}
+		if (records) {
+			uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+			w[0] = n > 0xffffu ? 0xffffu : n;
+			if (n <= (uint32_t)kInlineItems) {
+				uint32_t k[kInlineItems] = {0, 0, 0, 0, 0}, v[kInlineItems] = {0, 0, 0, 0, 0};
+				for (uint32_t i = 0; i < n; i++) { k[i] = (uint16_t)keys[lo + i]; v[i] = vals[lo + i]; }
+				w[0] |= k[0] << 16; w[1] = k[1] | (k[2] << 16); w[2] = k[3] | (k[4] << 16);
+				w[3] = v[0]; w[4] = v[1]; w[5] = v[2]; w[6] = v[3]; w[7] = v[4];
+			}
+			records[2 * (size_t)b] = make_uint4(w[0], w[1], w[2], w[3]);
+			records[2 * (size_t)b + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+		}
+	}
+}
+
 // Random 32-byte-sector gather: the "HBM-gather roofline" probe.
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_thread, uint32_t seed, uint32_t *sink)
 {
@@ -169,6 +199,8 @@ struct srcuda_handle {
 	sr::DevIndex ix{};
 	srcuda_index_desc desc{};
 	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
+	void *d_records = nullptr, *d_bloom = nullptr;
+	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both (SRCUDA_ACCEL)
 	size_t genome_words = 0;
 	BatchSet set[2];
 	std::vector<cudaEvent_t> events;
@@ -222,10 +254,35 @@ int ensure(srcuda_handle *h, DeviceBuf &b, size_t bytes)
 void free_index(srcuda_handle *h)
 {
 	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr);
-	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = nullptr;
+	cudaFree(h->d_records); cudaFree(h->d_bloom);
+	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = h->d_records = h->d_bloom = nullptr;
 	h->has_index = false;
 	memset(&h->ix, 0, sizeof(h->ix));
 	memset(&h->desc, 0, sizeof(h->desc));
+}
+
+// Build the lookup accelerators for the resident block.  They pay off for sparse tables (the Bloom
+// word filters lookups whose key16 is absent; the record needs <= 5 items per bucket), so "auto"
+// enables them when the mean bucket holds at most 4 items and leaves a human-sized table as it is.
+int build_accelerators(srcuda_handle *h)
+{
+	const uint32_t nb = h->ix.buckets_number;
+	const double mean = (double)h->desc.n_items / (double)nb;
+	int mode = h->accel_mode;
+	if (mode < 0) mode = mean <= 4.0 ? 3 : 0;
+	h->ix.bloom = nullptr;
+	h->ix.records = nullptr;
+	if (mode & 1) CU(h, cudaMalloc(&h->d_bloom, sizeof(uint16_t) * (size_t)nb));
+	if (mode & 2) CU(h, cudaMalloc(&h->d_records, 32 * (size_t)nb));
+	if (mode) {
+		sr::k_build_records<<<h->sm_count * 8, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, (uint4 *)h->d_records, (uint16_t *)h->d_bloom);
+		CU(h, cudaGetLastError());
+		CU(h, cudaDeviceSynchronize());
+	}
+	h->ix.bloom = (const uint16_t *)h->d_bloom;
+	h->ix.records = h->d_records;
+	h->desc.device_bytes += (mode & 1 ? 2ull * nb : 0) + (mode & 2 ? 32ull * nb : 0);
+	return 0;
 }
 
 int upload_index(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t nb, uint64_t n_items, const uint32_t *bucket_start,
@@ -269,6 +326,8 @@ int upload_index(srcuda_handle *h, int32_t index_gap, int32_t padding, uint32_t 
 	d.start_point = start_point; d.length = length; d.start_base_offset = ix.start_base_offset; d.values_bytes = values_bytes;
 	d.total_offsets = total_offsets;
 	d.device_bytes = sizeof(uint32_t) * ((uint64_t)nb + 1) + 6 * n_items + sizeof(uint32_t) * gw + sizeof(uint32_t) * (uint64_t)total_offsets;
+	int rc = build_accelerators(h);
+	if (rc) return rc;
 	h->has_index = true;
 	return SRCUDA_OK;
 }
@@ -382,6 +441,10 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SRCUDA_ERR_CUDA, "cudaSetDevice(%d) failed", device); }
 	const char *bf = getenv("SRCUDA_BATCH_FRAGS");
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
+	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both; default auto
+	if (ac && ac[0] >= '0' && ac[0] <= '3') h->accel_mode = ac[0] - '0';
+	const char *fg = getenv("SRCUDA_L2_FETCH");  // L2 fetch granularity hint in bytes: 32, 64 or 128
+	if (fg && atoi(fg) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
 	*out = h;
 	return SRCUDA_OK;
 }
@@ -478,6 +541,9 @@ int srcuda_index_replicate(srcuda_handle *dst, const srcuda_handle *src)
 	dst->ix.vals = (const uint32_t *)dst->d_vals; dst->ix.genome = (const uint32_t *)dst->d_genome;
 	dst->ix.chr_offsets = (const uint32_t *)dst->d_chr;
 	dst->desc = src->desc;
+	dst->desc.device_bytes = sizeof(uint32_t) * ((uint64_t)d.buckets_number + 1) + 6 * d.n_items + ng + nc;
+	int rc = build_accelerators(dst);
+	if (rc) return rc;
 	dst->has_index = true;
 	return SRCUDA_OK;
 }
@@ -541,6 +607,9 @@ int srcuda_index_import_ipc(srcuda_handle *h, const void *blob, size_t blob_byte
 	ix.bucket_start = (const uint32_t *)h->d_bucket_start; ix.keys = (const int16_t *)h->d_keys;
 	ix.vals = (const uint32_t *)h->d_vals; ix.genome = (const uint32_t *)h->d_genome; ix.chr_offsets = (const uint32_t *)h->d_chr;
 	h->desc = d;
+	h->desc.device_bytes = bytes[0] + bytes[1] + bytes[2] + bytes[3] + bytes[4];
+	int rc = build_accelerators(h);
+	if (rc) return rc;
 	h->has_index = true;
 	return SRCUDA_OK;
 }

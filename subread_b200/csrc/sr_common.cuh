@@ -45,7 +45,16 @@ struct DevIndex {
 	const uint32_t *vals;          // n_items
 	const uint32_t *genome;        // 2-bit bases, LSB first, as u32 words (padded)
 	const uint32_t *chr_offsets;   // total_offsets cumulative END offsets
+	// Lookup accelerators derived on the device at load time (sr_api.cu, k_build_records); both are
+	// exact: a filter without false negatives and a re-packed copy of small buckets.
+	const uint16_t *bloom;         // per bucket: bit (key16 & 15) set for every key16 in the bucket; null = off
+	const void *records;           // per bucket 32 B (two uint4): see below; null = off
 };
+
+// 32-byte bucket record (one sector): n <= kInlineItems items inline, otherwise only n is valid and
+// the lookup falls back to bucket_start / keys / vals.
+//   bytes 0-1  n (saturated at 0xffff)   bytes 2-11  key16[5]   bytes 12-31  value[5]
+constexpr int kInlineItems = 5;
 
 // The voting scalars, validated and pre-digested on the host (see srcuda_params).
 struct VoteConfig {

@@ -266,7 +266,10 @@ __device__ __forceinline__ int probe_rank(uint32_t kv, int my_row, int ii_end)
 	return rank;
 }
 
-__device__ __forceinline__ void vote_hit(WarpTable &T, SlotRegs &S, uint32_t *shift_locs, TableState &st, const HitEnv &E, uint32_t kv,
+#ifndef SR_VOTE_HIT_ATTR
+#define SR_VOTE_HIT_ATTR __forceinline__
+#endif
+__device__ SR_VOTE_HIT_ATTR void vote_hit(WarpTable &T, SlotRegs &S, uint32_t *shift_locs, TableState &st, const HitEnv &E, uint32_t kv,
                                          int offset, int sub_p1)
 {
 	const int lane = E.lane;
@@ -418,28 +421,64 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 				const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, nb_magic);   // key / nb, exact (sr_api.cu)
 				const uint32_t b = key - q * nb;
 				const int k16 = (int)(int16_t)q;
-				const uint32_t lo = __ldg(ix.bucket_start + b);
-				const int items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
-				if (items > 0) {
-					const int16_t *kp = ix.keys + lo;
-					int imin = 0, imax = items - 1, at;
-					bool found = false;
-					for (;;) {  // sorted-hashtable.c:960-981
-						at = (imin + imax) >> 1;
-						int kk = (int)__ldg(kp + at);
-						if (kk > k16) imax = at - 1;
-						else if (kk < k16) imin = at + 1;
-						else { found = true; break; }
-						if (imax < imin) break;
+				bool maybe = true;
+				if (ix.bloom) maybe = (__ldg(ix.bloom + b) >> (k16 & 15)) & 1;
+				if (maybe) {
+					int items = -1;
+					if (ix.records) {
+						// one 32-byte sector holds the whole bucket when it has <= 5 items
+						const uint4 *rp = reinterpret_cast<const uint4 *>(ix.records) + 2 * (size_t)b;
+						const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+						const int n = (int)(r0.x & 0xffffu);
+						if (n <= kInlineItems) {
+							items = 0;
+							const int k0 = (int)(int16_t)(r0.x >> 16), k1 = (int)(int16_t)(r0.y & 0xffffu), k2 = (int)(int16_t)(r0.y >> 16),
+							          k3 = (int)(int16_t)(r0.z & 0xffffu), k4 = (int)(int16_t)(r0.z >> 16);
+							// keys are sorted: the equal-key run is [lt, le)
+							const int lt = (n > 0 && k0 < k16) + (n > 1 && k1 < k16) + (n > 2 && k2 < k16) + (n > 3 && k3 < k16) + (n > 4 && k4 < k16);
+							const int le = (n > 0 && k0 <= k16) + (n > 1 && k1 <= k16) + (n > 2 && k2 <= k16) + (n > 3 && k3 <= k16) + (n > 4 && k4 <= k16);
+							if (le > lt) {
+								// where the reference's (imin+imax)/2 search lands inside the run (sorted-hashtable.c:960-981)
+								int imin = 0, imax = n - 1, at;
+								for (;;) {
+									at = (imin + imax) >> 1;
+									if (at >= le) imax = at - 1;
+									else if (at < lt) imin = at + 1;
+									else break;
+								}
+								h = le - lt;
+								land = at - lt;
+								firstval = at == 0 ? r0.w : (at == 1 ? r1.x : (at == 2 ? r1.y : (at == 3 ? r1.z : r1.w)));
+								if (h > 1) run_abs = __ldg(ix.bucket_start + b) + (uint32_t)lt;
+							}
+						}
 					}
-					if (found) {
-						int e = at + 1, s = at;
-						while (e < items && (int)__ldg(kp + e) == k16) e++;
-						while (s > 0 && (int)__ldg(kp + s - 1) == k16) s--;
-						h = e - s;
-						land = at - s;
-						run_abs = lo + (uint32_t)s;
-						firstval = __ldg(ix.vals + lo + at);
+					if (items < 0) {
+						const uint32_t lo = __ldg(ix.bucket_start + b);
+						items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
+						// (a record of a bucket with more than 5 items only carries its size)
+						if (items > 0) {
+							const int16_t *kp = ix.keys + lo;
+							int imin = 0, imax = items - 1, at;
+							bool found = false;
+							for (;;) {  // sorted-hashtable.c:960-981
+								at = (imin + imax) >> 1;
+								int kk = (int)__ldg(kp + at);
+								if (kk > k16) imax = at - 1;
+								else if (kk < k16) imin = at + 1;
+								else { found = true; break; }
+								if (imax < imin) break;
+							}
+							if (found) {
+								int e = at + 1, s = at;
+								while (e < items && (int)__ldg(kp + e) == k16) e++;
+								while (s > 0 && (int)__ldg(kp + s - 1) == k16) s--;
+								h = e - s;
+								land = at - s;
+								run_abs = lo + (uint32_t)s;
+								firstval = __ldg(ix.vals + lo + at);
+							}
+						}
 					}
 				}
 			}
@@ -470,27 +509,22 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 				const int o_s = __shfl_sync(kFull, o, src);
 				const int h_s = __shfl_sync(kFull, h, src);
 				const int sub_p1 = __shfl_sync(kFull, my_sub_p1, src);
-				if (h_s == 1) {
-					const uint32_t v = __shfl_sync(kFull, firstval, src);
-					vote_hit(T, S, shift_locs, st, E, v - (uint32_t)o_s, o_s, sub_p1);
-					if (st.overflow) { overflow = true; return applied; }
-				} else {
-					const int land_s = __shfl_sync(kFull, land, src);
-					const uint32_t run_s = __shfl_sync(kFull, run_abs, src);
-					const int nfwd = h_s - land_s;  // landing .. end of run, then landing-1 .. start (:1109-1119)
-					for (int c = 0; c < h_s; c += 32) {
-						const int tt = c + lane;
-						uint32_t v = 0;
-						if (tt < h_s) {
-							int idx = tt < nfwd ? land_s + tt : land_s - 1 - (tt - nfwd);
-							v = __ldg(ix.vals + run_s + idx);
-						}
-						const int cnt = min(32, h_s - c);
-						for (int u = 0; u < cnt; u++) {
-							const uint32_t vu = __shfl_sync(kFull, v, u);
-							vote_hit(T, S, shift_locs, st, E, vu - (uint32_t)o_s, o_s, sub_p1);
-							if (st.overflow) { overflow = true; return applied; }
-						}
+				const int land_s = __shfl_sync(kFull, land, src);
+				const uint32_t run_s = __shfl_sync(kFull, run_abs, src);
+				const uint32_t first_s = __shfl_sync(kFull, firstval, src);
+				const int nfwd = h_s - land_s;  // landing .. end of run, then landing-1 .. start (:1109-1119)
+				for (int c = 0; c < h_s; c += 32) {
+					const int tt = c + lane;
+					uint32_t v = first_s;
+					if (h_s > 1 && tt < h_s) {
+						int idx = tt < nfwd ? land_s + tt : land_s - 1 - (tt - nfwd);
+						v = __ldg(ix.vals + run_s + idx);
+					}
+					const int cnt = min(32, h_s - c);
+					for (int u = 0; u < cnt; u++) {
+						const uint32_t vu = __shfl_sync(kFull, v, u);
+						vote_hit(T, S, shift_locs, st, E, vu - (uint32_t)o_s, o_s, sub_p1);
+						if (st.overflow) { overflow = true; return applied; }
 					}
 				}
 			}
