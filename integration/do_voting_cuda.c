@@ -1,0 +1,260 @@
+/* integration/do_voting_cuda.c -- the reference-side binding of libsubread_cuda.so.
+ *
+ * This is what a Subread maintainer adds to run STEP_VOTING on a B200: a replacement for
+ * `do_voting` (core.c:3049) and for `gehash_load` (sorted-hashtable.c:1390) written against the
+ * reference's own headers, calling the C ABI of include/subread_cuda.h.  Everything else -- CLI,
+ * FASTQ/BAM input, chunk loop (read_chunk_circles, core.c:3539), indel/junction event tables,
+ * realignment, SAM/BAM output -- is the reference's unmodified code.
+ *
+ * In this repository it is built only as a demonstration/test vehicle (oracle/Makefile, target
+ * _ref/subread-align-cuda): the reference's CLI main + this file, linked against the -fPIC build
+ * of the reference (libsubread_ref.so).  Because the reference's cross-unit calls go through the
+ * PLT, defining do_voting / gehash_load here interposes on them without touching a reference
+ * source line.  A maintainer would instead compile this file into the tree and drop the two
+ * originals.  tests/test_integration_sam.py checks that the SAM output is byte-identical to the
+ * stock subread-align (minus @PG).
+ *
+ * Threading: run_maybe_threads (core.c:3379) starts config.all_threads workers that all enter
+ * do_voting.  Worker 0 reads the whole chunk through the reference's own fetch_next_read_pair and
+ * makes ONE srcuda_vote_chunk call that writes straight into the bigtable
+ * (bigtable_cache_malloc_ptr has exactly the out_align layout); then all workers share the
+ * per-read tail of do_voting (find_new_indels / find_new_junctions, core.c:3241-3290).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "subread.h"
+#include "core.h"
+#include "core-indel.h"
+#include "core-junction.h"
+#include "input-files.h"
+#include "sorted-hashtable.h"
+
+#include "../include/subread_cuda.h"
+
+static srcuda_handle *g_handle = NULL;
+
+static srcuda_handle *cuda_handle(void)
+{
+	if (!g_handle) {
+		const char *dev = getenv("SRCUDA_DEVICE");
+		if (srcuda_open(dev ? atoi(dev) : 0, &g_handle)) {
+			SUBREADprintf("ERROR: cannot open a CUDA device: %s\n", srcuda_last_error(NULL));
+			g_handle = NULL;
+		}
+	}
+	return g_handle;
+}
+
+/* ---- gehash_load: the block goes to HBM instead of host memory -------------------------------- */
+int gehash_load(gehash_t *the_table, const char fname[])
+{
+	memset(the_table, 0, sizeof(gehash_t));
+	size_t n = strlen(fname);
+	/* "<prefix>.NN.b.tab" */
+	if (n < 9 || strcmp(fname + n - 6, ".b.tab") != 0) {
+		SUBREADprintf("ERROR: unexpected index block name '%s'\n", fname);
+		return 1;
+	}
+	char prefix[MAX_FILE_NAME_LENGTH + 40];
+	strncpy(prefix, fname, sizeof(prefix) - 1);
+	prefix[n - 9] = 0;
+	int block_no = atoi(fname + n - 8);
+	srcuda_handle *h = cuda_handle();
+	if (!h) return 1;
+	if (srcuda_index_load(h, prefix, block_no)) {
+		SUBREADprintf("ERROR: %s\n", srcuda_last_error(h));
+		return 1;
+	}
+	srcuda_index_desc d;
+	srcuda_index_describe(h, &d);
+	the_table->version_number = SUBINDEX_VER2;
+	the_table->index_gap = d.index_gap;
+	the_table->padding = d.padding;
+	the_table->current_items = d.n_items;
+	the_table->buckets_number = 0; /* nothing on the host: gehash_destory has nothing to free */
+	the_table->buckets = NULL;
+	return 0;
+}
+
+/* ---- chunk buffers --------------------------------------------------------------------------- */
+typedef struct {
+	char *text, *qual, *names;
+	uint64_t *off;      /* per read, into text (and qual) */
+	uint64_t *name_off;
+	uint16_t *len;
+	size_t text_cap, text_used, names_cap, names_used, reads_cap, n_reads;
+} chunk_buf_t;
+
+static chunk_buf_t g_chunk;
+
+static void chunk_push(chunk_buf_t *c, const char *name, const char *text, const char *qual, int len)
+{
+	if (c->n_reads + 1 >= c->reads_cap) {
+		c->reads_cap = c->reads_cap ? c->reads_cap * 2 : (1u << 20);
+		c->off = realloc(c->off, sizeof(uint64_t) * (c->reads_cap + 1));
+		c->name_off = realloc(c->name_off, sizeof(uint64_t) * (c->reads_cap + 1));
+		c->len = realloc(c->len, sizeof(uint16_t) * c->reads_cap);
+	}
+	if (c->text_used + (size_t)len + 2 > c->text_cap) {
+		c->text_cap = c->text_cap ? c->text_cap * 2 : (256u << 20);
+		c->text = realloc(c->text, c->text_cap);
+		c->qual = realloc(c->qual, c->text_cap);
+	}
+	size_t nl = strlen(name) + 1;
+	if (c->names_used + nl > c->names_cap) {
+		c->names_cap = c->names_cap ? c->names_cap * 2 : (64u << 20);
+		c->names = realloc(c->names, c->names_cap);
+	}
+	c->off[c->n_reads] = c->text_used;
+	c->len[c->n_reads] = (uint16_t)len;
+	memcpy(c->text + c->text_used, text, (size_t)len);
+	c->text[c->text_used + len] = 0;
+	if (qual && qual[0]) memcpy(c->qual + c->text_used, qual, (size_t)len); else memset(c->qual + c->text_used, 0, (size_t)len);
+	c->qual[c->text_used + len] = 0;
+	c->text_used += (size_t)len + 1;
+	c->name_off[c->n_reads] = c->names_used;
+	memcpy(c->names + c->names_used, name, nl);
+	c->names_used += nl;
+	c->n_reads++;
+}
+
+/* ---- worker rendezvous ------------------------------------------------------------------------ */
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
+static int g_vote_done = 0, g_vote_rc = 0, g_departed = 0;
+static subread_read_number_t g_n_frags = 0;
+
+static int unsupported_mode(global_context_t *gc)
+{
+	return gc->config.do_breakpoint_detection || gc->config.do_fusion_detection || gc->config.do_long_del_detection ||
+	       gc->config.is_methylation_reads || gc->config.space_type != GENE_SPACE_BASE || gc->config.scRNA_input_mode ||
+	       gc->config.SAM_extra_columns;
+}
+
+/* Worker 0: read the chunk with the reference's reader and vote it on the GPU. */
+static int vote_chunk_on_gpu(global_context_t *gc, thread_context_t *tc)
+{
+	gene_input_t *ginp1 = &gc->input_reads.first_read_file, *ginp2 = NULL;
+	int is_paired = gc->input_reads.is_paired_end_reads;
+	if (is_paired) ginp2 = &gc->input_reads.second_read_file;
+	char *t1 = malloc(MAX_READ_LENGTH + 1), *t2 = malloc(MAX_READ_LENGTH + 1), *q1 = malloc(MAX_READ_LENGTH + 1), *q2 = malloc(MAX_READ_LENGTH + 1);
+	char n1[MAX_READ_NAME_LEN + 1], n2[MAX_READ_NAME_LEN + 1];
+	chunk_buf_t *c = &g_chunk;
+	c->n_reads = 0; c->text_used = 0; c->names_used = 0;
+	for (;;) {
+		int l1 = 0, l2 = 0;
+		subread_read_number_t no = 0;
+		fetch_next_read_pair(gc, tc, ginp1, ginp2, &l1, &l2, n1, n2, t1, t2, q1, q2, 1, &no);
+		if (no < 0) break;
+		chunk_push(c, n1, t1, q1, l1);
+		if (is_paired) chunk_push(c, n2, t2, q2, l2);
+	}
+	free(t1); free(t2); free(q1); free(q2);
+	g_n_frags = (subread_read_number_t)(c->n_reads / (1 + is_paired));
+	if (!g_n_frags) return 0;
+
+	srcuda_params p;
+	memset(&p, 0, sizeof(p));
+	p.total_subreads = gc->config.total_subreads;
+	p.top_scores = gc->config.top_scores;
+	p.max_vote_simples = gc->config.max_vote_simples;
+	p.max_vote_combinations = gc->config.max_vote_combinations;
+	p.max_vote_number_cutoff = gc->config.max_vote_number_cutoff;
+	p.multi_best_reads = gc->config.multi_best_reads;
+	p.minimum_subread_for_first_read = gc->config.minimum_subread_for_first_read;
+	p.minimum_subread_for_second_read = gc->config.minimum_subread_for_second_read;
+	p.max_indel_length = gc->config.max_indel_length;
+	p.minimum_pair_distance = gc->config.minimum_pair_distance;
+	p.maximum_pair_distance = gc->config.maximum_pair_distance;
+	p.is_first_read_reversed = 0;  /* fetch_next_read_pair already oriented both mates (core.c:1187-1199) */
+	p.is_second_read_reversed = 0;
+	srcuda_handle *h = cuda_handle();
+	if (!h) return 1;
+	int rc = srcuda_vote_chunk(h, &p, c->text, c->off, c->len, (int64_t)g_n_frags, is_paired,
+	                           gc->current_index_block_number == 0, (srcuda_mapping_result *)gc->bigtable_cache_malloc_ptr, NULL, NULL, NULL);
+	if (rc) SUBREADprintf("ERROR: srcuda_vote_chunk: %s\n", srcuda_last_error(h));
+	return rc;
+}
+
+/* The per-read tail of do_voting on the last index block (core.c:3236-3290), for fragments [f0, f1). */
+static void discover_events(global_context_t *gc, thread_context_t *tc, subread_read_number_t f0, subread_read_number_t f1)
+{
+	int mates = 1 + gc->input_reads.is_paired_end_reads;
+	int need_junction_step = gc->config.do_breakpoint_detection || gc->config.do_fusion_detection || gc->config.do_long_del_detection;
+	char *text = malloc(MAX_READ_LENGTH + 1), *qual = malloc(MAX_READ_LENGTH + 1);
+	chunk_buf_t *c = &g_chunk;
+	for (subread_read_number_t f = f0; f < f1; f++)
+		for (int m = 0; m < mates; m++) {
+			size_t r = (size_t)f * mates + m;
+			int rlen = c->len[r];
+			memcpy(text, c->text + c->off[r], (size_t)rlen + 1);
+			memcpy(qual, c->qual + c->off[r], (size_t)rlen + 1);
+			/* after its two strand passes do_voting holds the read reversed (core.c:3229-3234) and the
+			 * quality string as fetched; read_?_reversed starts at 1 (core.c:3237-3238) */
+			reverse_read(text, rlen, gc->config.space_type);
+			int has_reversed = 1;
+			char *current_qual = qual;
+			for (int best = 0; best < gc->config.multi_best_reads; best++) {
+				mapping_result_t *cur = _global_retrieve_alignment_ptr(gc, f, m, best);
+				if (cur->selected_votes < 1) continue;
+				int should = (cur->result_flags & CORE_IS_NEGATIVE_STRAND) ? 1 : 0;
+				if (should != has_reversed) {
+					has_reversed = !has_reversed;
+					reverse_read(text, rlen, gc->config.space_type);
+					reverse_quality(current_qual, rlen);
+				}
+				gene_value_index_t *saved = tc ? tc->current_value_index : gc->current_value_index;
+				locate_current_value_index(gc, tc, cur, rlen);
+				if (!has_better_mapping(gc, tc, f, m, best))
+					find_new_indels(gc, tc, f, c->names + c->name_off[r], text, current_qual, rlen, m, best);
+				if (need_junction_step)
+					find_new_junctions(gc, tc, f, c->names + c->name_off[r], text, current_qual, rlen, m, best);
+				if (tc) tc->current_value_index = saved; else gc->current_value_index = saved;
+			}
+		}
+	free(text);
+	free(qual);
+}
+
+int do_voting(global_context_t *gc, thread_context_t *tc)
+{
+	if (unsupported_mode(gc)) {
+		/* modes the GPU library refuses (subjunc, fusion, methylation, colour space ...): the
+		 * reference's own do_voting, loudly */
+		static int (*orig)(global_context_t *, thread_context_t *) = NULL;
+		static int told = 0;
+		if (!orig) orig = (int (*)(global_context_t *, thread_context_t *))dlsym(RTLD_NEXT, "do_voting");
+		if (!told) { told = 1; SUBREADprintf("NOTICE: this mode is not supported by libsubread_cuda; using the reference's CPU do_voting.\n"); }
+		return orig(gc, tc);
+	}
+	int n_threads = tc ? gc->config.all_threads : 1;
+	int me = tc ? tc->thread_id : 0;
+	if (tc) tc->current_value_index = gc->current_value_index;
+
+	if (me == 0) {
+		int rc = vote_chunk_on_gpu(gc, tc);
+		pthread_mutex_lock(&g_mu);
+		g_vote_rc = rc;
+		g_vote_done = 1;
+		pthread_cond_broadcast(&g_cv);
+		pthread_mutex_unlock(&g_mu);
+	} else {
+		pthread_mutex_lock(&g_mu);
+		while (!g_vote_done) pthread_cond_wait(&g_cv, &g_mu);
+		pthread_mutex_unlock(&g_mu);
+	}
+	int rc = g_vote_rc;
+	if (!rc && gc->is_final_voting_run && g_n_frags > 0) {
+		subread_read_number_t f0 = g_n_frags * me / n_threads, f1 = g_n_frags * (me + 1) / n_threads;
+		discover_events(gc, tc, f0, f1);
+	}
+	pthread_mutex_lock(&g_mu);
+	if (++g_departed == n_threads) { g_departed = 0; g_vote_done = 0; }  /* every worker is joined before the next call */
+	pthread_mutex_unlock(&g_mu);
+	return rc;
+}

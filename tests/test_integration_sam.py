@@ -1,0 +1,43 @@
+"""SAM-level parity through the reference's own host code: `subread-align-cuda` is the reference's CLI,
+chunk loop, event tables, realignment and SAM writer with STEP_VOTING bound to libsubread_cuda.so
+(integration/do_voting_cuda.c).  Its SAM output must be byte-identical to the stock subread-align's,
+apart from the @PG header line (north_star: "identical SAM records apart from the @PG header")."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import REF_DIR, ROOT
+
+pytestmark = pytest.mark.gpu
+
+STOCK = os.path.join(REF_DIR, "bin", "subread-align")
+CUDA = os.path.join(REF_DIR, "subread-align-cuda")
+
+
+def sam_body(path):
+    with open(path, "rb") as fh:
+        return b"".join(l for l in fh if not l.startswith(b"@PG"))
+
+
+@pytest.mark.skipif(not (os.path.exists(STOCK) and os.path.exists(CUDA)), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("kind,paired,threads", [("uniform", False, 1), ("uniform", True, 4), ("repeats", False, 4), ("repeats", True, 2)])
+def test_sam_identical_to_stock_subread_align(kind, paired, threads, tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    from subread_b200.index_build import build_index
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 4, 400000, seed=31, repeats=500 if kind == "repeats" else 0)
+    prefix = str(tmp_path / "idx")
+    build_index(fa, prefix, gapped=True, use_gpu=True)
+    gen_data.write_reads(fa, str(tmp_path / "r"), 20000, 120, 9, paired, 0.01, 0.15, True, 0.002)
+    reads = ["-r", str(tmp_path / "r_R1.fastq")] + (["-R", str(tmp_path / "r_R2.fastq")] if paired else [])
+    outs = []
+    for exe, tag in ((STOCK, "stock"), (CUDA, "cuda")):
+        out = str(tmp_path / f"{tag}.sam")
+        subprocess.run([exe, "-t", "1", "-T", str(threads), "-i", prefix] + reads + ["--SAMoutput", "-o", out], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        outs.append(sam_body(out))
+    assert len(outs[0]) > 1000
+    assert outs[0] == outs[1]
