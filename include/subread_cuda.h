@@ -89,8 +89,11 @@ typedef struct {
 	int32_t big_margin_record_size;          /* 9 */
 	int32_t maximum_intron_length;           /* 500000 */
 	int32_t limited_tree_scan;
-	int32_t check_donor_at_junctions;
-	int32_t reserved[5];
+	int32_t check_donor_at_junctions;        /* 1 */
+	int32_t more_accurate_fusions;           /* 0 unless fusion detection (core-interface-subjunc.c:671) */
+	int32_t max_insertion_at_junctions;      /* 0; other values are not supported */
+	int32_t prefer_donor_receptor_junctions; /* 1 */
+	int32_t reserved[2];
 } srcuda_params;
 
 /* What the host needs back from the loaded block to compute low/high border exactly as

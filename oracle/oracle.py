@@ -115,10 +115,22 @@ class OracleIndex:
         )
 
 
-def vote_chunk(index: OracleIndex, params: VoteParams, chunk, out_align=None, want_verify=False, threads=1):
-    """Run the oracle over a ReadChunk.  Returns (align[n_frags, mates, multi_best], verify|None, stats)."""
+def vote_chunk(index: OracleIndex, params: VoteParams, chunk, out_align=None, want_verify=False, threads=1, junc_state=None):
+    """Run the oracle over a ReadChunk.  Returns (align[n_frags, mates, multi_best], verify|None, stats).
+    With params.do_breakpoint_detection (subjunc) pass junc_state = {} (filled with 'junc' and 'big_margin'
+    arrays, read-modify-write across index blocks like out_align)."""
+    from subread_b200.layout import SUBJUNC_RESULT
     mb = params.multi_best_reads
     n = chunk.n_frags * chunk.mates * mb
+    junc_ptr = bm_ptr = None
+    if params.do_breakpoint_detection:
+        if junc_state is None:
+            junc_state = {}
+        if "junc" not in junc_state:
+            junc_state["junc"] = np.zeros(n, dtype=SUBJUNC_RESULT)
+            junc_state["big_margin"] = np.zeros(chunk.n_frags * chunk.mates * 27, dtype=np.uint16)
+        junc_ptr = junc_state["junc"].ctypes.data
+        bm_ptr = junc_state["big_margin"].ctypes.data
     if out_align is None:
         out_align = np.zeros(n, dtype=MAPPING_RESULT)
     out_align = np.ascontiguousarray(out_align).reshape(-1)
@@ -129,7 +141,7 @@ def vote_chunk(index: OracleIndex, params: VoteParams, chunk, out_align=None, wa
     off = np.ascontiguousarray(chunk.off, dtype=np.uint64)
     ln = np.ascontiguousarray(chunk.len, dtype=np.uint16)
     args = [ctypes.byref(index.c), ctypes.byref(params), text.ctypes.data, off.ctypes.data, ln.ctypes.data,
-            chunk.n_frags, int(chunk.is_paired), out_align.ctypes.data, None, None,
+            chunk.n_frags, int(chunk.is_paired), out_align.ctypes.data, junc_ptr, bm_ptr,
             verify.ctypes.data if want_verify else None, ctypes.byref(stats)]
     rc = lib().or_vote_chunk_mt(*args, threads) if threads > 1 else lib().or_vote_chunk(*args)
     if rc:

@@ -64,6 +64,7 @@ void or_default_params(or_params_t *p, int is_paired, int is_subjunc)
 	p->big_margin_record_size = 9;
 	p->maximum_intron_length = 500000;
 	p->check_donor_at_junctions = 1;
+	p->prefer_donor_receptor_junctions = 1;
 	/* load_global_context, core.c:4075-4084 */
 	p->max_vote_combinations = 3;
 	p->multi_best_reads = 3;
@@ -512,6 +513,171 @@ typedef struct { /* simple_mapping_t, core.h:414-424 */
 
 typedef struct { int r1, r2; unsigned long long score; } combo_t; /* vote_combination_t core.h:426-431 */
 
+
+/* ------------------------------------------------------------------ subjunc: minor half + donor site */
+
+#define CONFIRM_WINDOW 17 /* JUNCTION_CONFIRM_WINDOW core-junction.c:3569 */
+
+static uint32_t abs32(uint32_t x) { return x > 0x7fffffffu ? (0xffffffffu - x) + 1 : x; } /* abs32uint core-junction.c:42 */
+
+static void genome_string2(char *buf, const or_index_t *idx, uint32_t pos) /* gvindex_get_string, len 2, forward */
+{
+	buf[0] = (char)genome_base(idx, pos);
+	buf[1] = (char)genome_base(idx, pos + 1);
+}
+
+/* is_donor_chars_part / paired_chars_part_core(.., 0), core-junction.c:3472-3503 */
+static int donor_chars(const char *c) { return (c[0] == 'G' && c[1] == 'T') || (c[0] == 'A' && c[1] == 'G') || (c[0] == 'A' && c[1] == 'C') || (c[0] == 'C' && c[1] == 'T'); }
+static int ceq2(const char *c, const char *t) { return c[0] == t[0] && c[1] == t[1]; }
+static int donor_pair(const char *a, const char *b)
+{
+	int gtag = (ceq2(a, "GT") && ceq2(b, "AG")) || (ceq2(a, "AG") && ceq2(b, "GT"));
+	int ctac = (ceq2(a, "CT") && ceq2(b, "AC")) || (ceq2(a, "AC") && ceq2(b, "CT"));
+	if (gtag || ctac) return ceq2(a, "CT") || ceq2(a, "GT");
+	return 0;
+}
+
+/* donor_score, core-junction.c:3675-3832, for subjunc's configuration: prefer_donor_receptor_junctions,
+ * check_donor_at_junctions, no fusion / long deletion, max_insertion_at_junctions 0, more_accurate_fusions. */
+static int donor_score(const or_index_t *idx, const or_params_t *p, uint32_t left_pos, uint32_t right_pos, int left_indel, int right_indel,
+                       int normally_arranged, int guess_start, int guess_end, const char *text, int rlen, int *split_point,
+                       int *gt_ag_strand, int *donor_found, int *inserted_bases, int *small_inc, int *large_inc)
+{
+	int need_donor_test = p->check_donor_at_junctions ? 1 : 0;
+	int mism_allowed = p->more_accurate_fusions ? 0 : 1; /* mismatch_in_between_allowd :3735 */
+	*small_inc = !normally_arranged;
+	*large_inc = normally_arranged;
+	int most_likely = (guess_start + guess_end) / 2;
+	int sel_split = -1, sel_strand = -1, best = -111111;
+	char dl[3] = {0, 0, 0}, dr[3] = {0, 0, 0};
+	int n_points = guess_end - guess_start;
+	for (int k = 0; k < n_points; k++) {
+		int sp = ((k % 2) ? -((k + 1) / 2) : ((1 + k) / 2)) + most_likely;
+		int donor_ok = 0;
+		if (sp > rlen - CONFIRM_WINDOW) continue;
+		if (sp < CONFIRM_WINDOW) continue;
+		if (!p->prefer_donor_receptor_junctions) donor_ok = 0;
+		else if (normally_arranged) {
+			genome_string2(dl, idx, left_pos + (uint32_t)sp + (uint32_t)left_indel);
+			if (donor_chars(dl)) {
+				genome_string2(dr, idx, right_pos + (uint32_t)sp + (uint32_t)right_indel - 2);
+				if (donor_chars(dr)) donor_ok = donor_pair(dl, dr);
+			}
+		} else {
+			genome_string2(dl, idx, right_pos + (uint32_t)sp + (uint32_t)left_indel);
+			genome_string2(dr, idx, left_pos + (uint32_t)sp + (uint32_t)right_indel - 2);
+			donor_ok = donor_chars(dl) && donor_chars(dr) && donor_pair(dl, dr);
+		}
+		if (!(donor_ok || !need_donor_test)) continue;
+		if (normally_arranged) {
+			int lm = or_match_chro(text + sp - CONFIRM_WINDOW, idx, left_pos + (uint32_t)sp - CONFIRM_WINDOW + (uint32_t)left_indel, CONFIRM_WINDOW, 0);
+			if (lm > CONFIRM_WINDOW - 2) {
+				int rm = or_match_chro(text + sp, idx, right_pos + (uint32_t)sp + (uint32_t)right_indel, CONFIRM_WINDOW, 0);
+				if (rm >= 2 * CONFIRM_WINDOW - lm - mism_allowed) {
+					int lnm = or_match_chro(text + sp, idx, left_pos + (uint32_t)sp + (uint32_t)left_indel, CONFIRM_WINDOW, 0);
+					int rnm = or_match_chro(text + sp - CONFIRM_WINDOW, idx, right_pos + (uint32_t)sp + (uint32_t)right_indel - CONFIRM_WINDOW, CONFIRM_WINDOW, 0);
+					if (lnm <= CONFIRM_WINDOW - 5 && rnm <= CONFIRM_WINDOW - 5) {
+						int score = 100 * (donor_ok * 3000 + lm + rm - lnm - rnm);
+						if (score > best) { sel_strand = (dl[0] == 'G' || dr[1] == 'G'); sel_split = sp; best = score; }
+					}
+				}
+			}
+		} else {
+			int rm = or_match_chro(text + sp - CONFIRM_WINDOW, idx, right_pos + (uint32_t)right_indel + (uint32_t)sp - CONFIRM_WINDOW, CONFIRM_WINDOW, 0);
+			int lm = or_match_chro(text + sp, idx, left_pos + (uint32_t)sp + (uint32_t)left_indel, CONFIRM_WINDOW, 0);
+			int rnm = or_match_chro(text + sp, idx, right_pos + (uint32_t)sp + (uint32_t)right_indel, CONFIRM_WINDOW, 0);
+			int lnm = or_match_chro(text + sp - CONFIRM_WINDOW, idx, left_pos + (uint32_t)left_indel + (uint32_t)sp - CONFIRM_WINDOW, CONFIRM_WINDOW, 0);
+			if (lm + rm >= 2 * CONFIRM_WINDOW - mism_allowed && lnm <= CONFIRM_WINDOW - 5 && rnm <= CONFIRM_WINDOW - 5) {
+				int score = 100 * (donor_ok * 3000 + lm + rm - lnm - rnm);
+				if (score > best) { sel_strand = (dl[0] == 'G' || dr[1] == 'G'); sel_split = sp; best = score; }
+			}
+		}
+	}
+	if (best > 0) {
+		*split_point = sel_split;
+		*donor_found = best >= 290000;
+		*gt_ag_strand = sel_strand;
+		*inserted_bases = 0;
+		return (1 + best) / 100;
+	}
+	return 0;
+}
+
+/* insert_big_margin_record, core-junction.c:789-813 */
+static void big_margin_insert(const or_params_t *p, uint16_t *rec, unsigned char votes, short start, short end, int rlen, int is_negative)
+{
+	int n = p->big_margin_record_size;
+	if (n < 3) return;
+	uint16_t s2 = (uint16_t)(is_negative ? rlen - end : start), e2 = (uint16_t)(is_negative ? rlen - start : end);
+	int x;
+	for (x = 0; x < n / 3; x++)
+		if (votes >= rec[x * 3]) break;
+	if (x < n / 3) {
+		for (int y = n - 4; y >= x * 3; y--) rec[y + 3] = rec[y];
+		rec[x * 3] = votes; rec[x * 3 + 1] = s2; rec[x * 3 + 2] = e2;
+	}
+}
+
+/* The do_breakpoint_detection part of copy_vote_to_alignment_res, core-junction.c:1073-1334 (no fusion,
+ * no long deletion: one table holds one strand, so is_strand_jumpped is always 0). */
+static void minor_half_search(const or_index_t *idx, const or_params_t *p, or_mapping_result_t *r, or_subjunc_result_t *jr,
+                              const vote_table_t *v, int vi, int vj, int rlen, const char *text)
+{
+	for (int i = 0; i < VT_ROWS; i++)
+		for (int j = 0; j < v->items[i]; j++) {
+			if (i == vi && j == vj) continue;
+			if (r->selected_votes < v->votes[i][j]) continue;
+			long long dist = (long long)v->pos[vi][vj] - (long long)v->pos[i][j];
+			/* test_junction_minor, core-junction.c:889-906 */
+			if (abs((int)dist) > p->maximum_intron_length) continue; /* abs() on a long long: the reference truncates to int */
+			if (v->coverage_start[vi][vj] == v->coverage_start[i][j]) continue;
+			if (v->coverage_end[vi][vj] == v->coverage_end[i][j]) continue;
+			if (v->coverage_start[vi][vj] > v->coverage_start[i][j]) { if (v->pos[vi][vj] < v->pos[i][j]) continue; }
+			else { if (v->pos[vi][vj] > v->pos[i][j]) continue; }
+			/* is_better_inner, core-junction.c:975-983 */
+			int old_intron = (int)abs32(v->pos[vi][vj] - jr->minor_position), intron = (int)abs32(v->pos[vi][vj] - v->pos[i][j]);
+			int mv = v->votes[i][j], mcov = v->coverage_end[i][j] - v->coverage_start[i][j];
+			int jcov = jr->minor_coverage_end - jr->minor_coverage_start;
+			int better = mv > jr->minor_votes || (mv == jr->minor_votes && mcov > jcov) ||
+			             (mv == jr->minor_votes && mcov == jcov && intron < old_intron);
+			if (!better) continue;
+			int overlapped;
+			if (v->coverage_start[vi][vj] > v->coverage_start[i][j]) overlapped = v->coverage_end[i][j] - v->coverage_start[vi][vj];
+			else overlapped = v->coverage_end[vi][vj] - v->coverage_start[i][j];
+			if (overlapped > 14) continue;
+			if (abs((int)dist) < 6) continue;
+			int guess_start = (v->coverage_start[vi][vj] > v->coverage_start[i][j]) ? v->coverage_end[i][j] - 8 : v->coverage_end[vi][vj] - 8;
+			int guess_end = (v->coverage_start[vi][vj] < v->coverage_start[i][j]) ? v->coverage_start[i][j] + 8 : v->coverage_start[vi][vj] + 8;
+			int normally_arranged = 1 != (v->coverage_start[vi][vj] > v->coverage_start[i][j]) + (v->pos[vi][vj] > v->pos[i][j]);
+			int left_indel = 0, right_indel = 0, major_indels = 0, minor_indel_offset = 0;
+			if (rlen > LONG_READ) {
+				for (int k = 0; k < MAX_SECTIONS; k++) { if (!v->indel_recorder[vi][vj][k * 3]) break; major_indels += v->indel_recorder[vi][vj][k * 3 + 2]; }
+				for (int k = 0; k < MAX_SECTIONS; k++) { if (!v->indel_recorder[i][j][k * 3]) break; minor_indel_offset += v->indel_recorder[i][j][k * 3 + 2]; }
+				left_indel = v->pos[vi][vj] < v->pos[i][j] ? major_indels : minor_indel_offset;
+				right_indel = 0;
+			}
+			int split = 0, gt_ag = 0, donor_found = 0, inserted = 0, small_inc = 0, large_inc = 0;
+			uint32_t lo = v->pos[vi][vj] < v->pos[i][j] ? v->pos[vi][vj] : v->pos[i][j];
+			uint32_t hi = v->pos[vi][vj] > v->pos[i][j] ? v->pos[vi][vj] : v->pos[i][j];
+			int replace = donor_score(idx, p, lo, hi, left_indel, right_indel, normally_arranged, guess_start > 0 ? guess_start : 0,
+			                          guess_end < rlen ? guess_end : rlen, text, rlen, &split, &gt_ag, &donor_found, &inserted, &small_inc, &large_inc);
+			if (!replace) continue;
+			jr->minor_position = v->pos[i][j];
+			jr->minor_votes = v->votes[i][j];
+			jr->minor_coverage_start = (uint16_t)v->coverage_start[i][j];
+			jr->minor_coverage_end = (uint16_t)v->coverage_end[i][j];
+			jr->double_indel_offset = (int8_t)((minor_indel_offset & 0xf) | ((major_indels & 0xf) << 4));
+			jr->split_point = (int16_t)split;
+			jr->small_side_increasing_coordinate = (int8_t)small_inc;
+			jr->large_side_increasing_coordinate = (int8_t)large_inc;
+			jr->indel_at_junction = (int8_t)inserted;
+			r->result_flags &= ~0x3;
+			if (!donor_found || gt_ag > 2) r->result_flags |= 3;
+			else r->result_flags = gt_ag ? (r->result_flags | 1) : (r->result_flags & ~1);
+			r->result_flags &= ~4; /* CORE_IS_STRAND_JUMPED: never in this mode */
+		}
+}
+
 /* copy_vote_to_alignment_res, core-junction.c:1058-1072 (the DNA part). */
 static void slot_to_result(or_mapping_result_t *r, const vote_table_t *v, int i, int j, int used_subreads)
 {
@@ -540,7 +706,8 @@ static void combo_sort(combo_t *c, int n)
 
 /* process_voting_junction_PE_topK, core-junction.c:2199-2530 (DNA mode: no fusion, no junctions). */
 static void topk(const or_index_t *idx, const or_params_t *p, int is_paired, vote_table_t *vt[2], const int rlen[2],
-                 const int all_subreads[2], or_mapping_result_t *res /* [mates][multi_best] */)
+                 const int all_subreads[2], or_mapping_result_t *res /* [mates][multi_best] */, or_subjunc_result_t *jres /* same shape or NULL */,
+                 uint16_t *big_margin /* [mates][27] or NULL */, char *const text[2])
 {
 	int mates = 1 + is_paired, mb = p->multi_best_reads;
 	int top[2][MAX_TOP];
@@ -568,6 +735,9 @@ static void topk(const or_index_t *idx, const or_params_t *p, int is_paired, vot
 				for (int j = 0; j < vt[m]->items[i]; j++) {
 					if (n >= p->max_vote_simples) break;
 					int vv = vt[m]->votes[i][j];
+					if (p->do_big_margin_filtering_for_junctions && big_margin && lv == 0 && vv >= top[m][p->top_scores - 1]) /* :2281 */
+						big_margin_insert(p, big_margin + m * 27, (unsigned char)vv, vt[m]->coverage_start[i][j], vt[m]->coverage_end[i][j], rlen[m],
+						                  (vt[m]->masks[i][j] & NEG_STRAND_MASK) ? 1 : 0);
 					if (vv == want && vv >= p->minimum_subread_for_second_read) {
 						simple[m][n].is_vote_item = 1;
 						simple[m][n].i = i;
@@ -622,7 +792,20 @@ static void topk(const or_index_t *idx, const or_params_t *p, int is_paired, vot
 	}
 
 	or_mapping_result_t *tmp = (or_mapping_result_t *)calloc((size_t)mates * mb, sizeof(or_mapping_result_t));
+	or_subjunc_result_t *jtmp = (or_subjunc_result_t *)calloc((size_t)mates * mb, sizeof(or_subjunc_result_t));
+	const int junc = p->do_breakpoint_detection && jres;
 	int cursor[2] = {0, 0};
+#define EMIT_CANDIDATE(m, loc)                                                                                             \
+	do {                                                                                                               \
+		if ((loc)->is_vote_item) {                                                                                     \
+			slot_to_result(&tmp[(m) * mb + cursor[m]], vt[m], (loc)->i, (loc)->j, all_subreads[m]);                    \
+			if (junc) minor_half_search(idx, p, &tmp[(m) * mb + cursor[m]], &jtmp[(m) * mb + cursor[m]], vt[m], (loc)->i, (loc)->j, rlen[m], text[m]); \
+		} else {                                                                                                       \
+			tmp[(m) * mb + cursor[m]] = res[(m) * mb + (loc)->i];                                                      \
+			if (junc) jtmp[(m) * mb + cursor[m]] = jres[(m) * mb + (loc)->i];                                          \
+		}                                                                                                              \
+		cursor[m]++;                                                                                                   \
+	} while (0)
 
 	if (n_comb > 0) { /* :2394-2434 */
 		combo_sort(comb, n_comb);
@@ -634,9 +817,7 @@ static void topk(const or_index_t *idx, const or_params_t *p, int is_paired, vot
 				for (int j = 0; j < cursor[m]; j++)
 					if (tmp[m * mb + j].selected_position == loc->pos) { exist = 1; break; }
 				if (exist) continue;
-				if (loc->is_vote_item) slot_to_result(&tmp[m * mb + cursor[m]], vt[m], loc->i, loc->j, all_subreads[m]);
-				else tmp[m * mb + cursor[m]] = res[m * mb + loc->i];
-				cursor[m]++;
+				EMIT_CANDIDATE(m, loc);
 			}
 	} else { /* :2436-2495 */
 		if (n_simple[0] == 0) res[0].noninformative_subreads_in_vote = 0;
@@ -651,18 +832,22 @@ static void topk(const or_index_t *idx, const or_params_t *p, int is_paired, vot
 					for (int j = 0; j < cursor[m]; j++)
 						if (tmp[m * mb + j].selected_position == loc->pos) { exist = 1; break; }
 					if (exist) continue;
-					if (loc->is_vote_item) slot_to_result(&tmp[m * mb + cursor[m]], vt[m], loc->i, loc->j, all_subreads[m]);
-					else tmp[m * mb + cursor[m]] = res[m * mb + loc->i];
-					cursor[m]++;
+					EMIT_CANDIDATE(m, loc);
 				}
 	}
+#undef EMIT_CANDIDATE
 
 	for (int m = 0; m < mates; m++) /* :2505-2527 */
 		for (int k = 0; k < mb; k++) {
 			if (k < cursor[m]) res[m * mb + k] = tmp[m * mb + k];
 			else res[m * mb + k].selected_votes = 0;
+			if (junc) {
+				if (k < cursor[m]) jres[m * mb + k] = jtmp[m * mb + k];
+				else jres[m * mb + k].minor_votes = 0;
+			}
 		}
 	free(tmp);
+	free(jtmp);
 	free(comb);
 	free(simple[0]);
 }
@@ -678,7 +863,8 @@ typedef struct {
 
 /* One fragment through do_voting's body, core.c:3106-3235. */
 static void vote_fragment(const or_index_t *idx, const or_params_t *p, int is_paired, const char *const raw[2],
-                          const int rlen[2], or_mapping_result_t *res, uint16_t *verify, scratch_t *sc, or_stats_t *st)
+                          const int rlen[2], or_mapping_result_t *res, or_subjunc_result_t *jres, uint16_t *big_margin, uint16_t *verify,
+                          scratch_t *sc, or_stats_t *st)
 {
 	int mates = 1 + is_paired, mb = p->multi_best_reads;
 	int gap = idx->index_gap;
@@ -715,10 +901,11 @@ static void vote_fragment(const or_index_t *idx, const or_params_t *p, int is_pa
 			}
 		}
 
+		char *const texts[2] = {sc->text[0], sc->text[1]};
 		if (is_paired) {
-			topk(idx, p, 1, vt, rlen, all_subreads, res);
+			topk(idx, p, 1, vt, rlen, all_subreads, res, jres, big_margin, texts);
 		} else if (vt[0]->max_vote >= p->minimum_subread_for_first_read) { /* core.c:3214 */
-			topk(idx, p, 0, vt, rlen, all_subreads, res);
+			topk(idx, p, 0, vt, rlen, all_subreads, res, jres, big_margin, texts);
 		} else if (res[0].selected_votes < 1) { /* core.c:3217-3225 */
 			res[0].noninformative_subreads_in_vote = 0;
 			if (res[0].used_subreads_in_vote < applied) res[0].used_subreads_in_vote = (int16_t)applied;
@@ -744,8 +931,8 @@ static void vote_fragment(const or_index_t *idx, const or_params_t *p, int is_pa
 }
 
 static int vote_range(const or_index_t *idx, const or_params_t *p, const char *text, const uint64_t *off, const uint16_t *len,
-                      int64_t f0, int64_t f1, int is_paired, or_mapping_result_t *out_align, uint16_t *out_verify,
-                      or_stats_t *stats)
+                      int64_t f0, int64_t f1, int is_paired, or_mapping_result_t *out_align, or_subjunc_result_t *out_junc,
+                      uint16_t *out_big_margin, uint16_t *out_verify, or_stats_t *stats)
 {
 	int mates = 1 + is_paired, mb = p->multi_best_reads;
 	scratch_t *sc = (scratch_t *)malloc(sizeof(scratch_t));
@@ -759,6 +946,7 @@ static int vote_range(const or_index_t *idx, const or_params_t *p, const char *t
 			if (rlen[m] > MAX_RLEN) { free(sc); return 3; }
 		}
 		vote_fragment(idx, p, is_paired, raw, rlen, out_align + (size_t)f * mates * mb,
+		              out_junc ? out_junc + (size_t)f * mates * mb : NULL, out_big_margin ? out_big_margin + (size_t)f * mates * 27 : NULL,
 		              out_verify ? out_verify + (size_t)f * mates * mb : NULL, sc, stats);
 	}
 	free(sc);
@@ -770,7 +958,7 @@ static int check_params(const or_index_t *idx, const or_params_t *p)
 	if (!idx || !p || idx->index_gap < 1 || idx->index_gap > 3) return 1;
 	if (p->top_scores < 1 || p->top_scores > MAX_TOP || p->multi_best_reads < 1 || p->total_subreads < 2) return 1;
 	if (p->max_vote_simples < 1 || p->max_vote_combinations < 1) return 1;
-	if (p->do_breakpoint_detection) return 9; /* subjunc minor-half search: not restated yet */
+	if (p->do_breakpoint_detection && p->max_insertion_at_junctions != 0) return 9;
 	return 0;
 }
 
@@ -778,21 +966,23 @@ int or_vote_chunk(const or_index_t *idx, const or_params_t *p, const char *text,
                   int64_t n_frags, int is_paired, or_mapping_result_t *out_align, or_subjunc_result_t *out_junc,
                   uint16_t *out_big_margin, uint16_t *out_verify, or_stats_t *stats)
 {
-	(void)out_junc; (void)out_big_margin;
 	int r = check_params(idx, p);
 	if (r) return r;
-	return vote_range(idx, p, text, off, len, 0, n_frags, is_paired, out_align, out_verify, stats);
+	if (p->do_breakpoint_detection && !out_junc) return 8;
+	return vote_range(idx, p, text, off, len, 0, n_frags, is_paired, out_align, out_junc, out_big_margin, out_verify, stats);
 }
 
 typedef struct {
 	const or_index_t *idx; const or_params_t *p; const char *text; const uint64_t *off; const uint16_t *len;
-	int64_t f0, f1; int is_paired; or_mapping_result_t *out_align; uint16_t *out_verify; or_stats_t stats; int rc;
+	int64_t f0, f1; int is_paired; or_mapping_result_t *out_align; or_subjunc_result_t *out_junc; uint16_t *out_big_margin;
+	uint16_t *out_verify; or_stats_t stats; int rc;
 } mt_job_t;
 
 static void *mt_entry(void *arg)
 {
 	mt_job_t *j = (mt_job_t *)arg;
-	j->rc = vote_range(j->idx, j->p, j->text, j->off, j->len, j->f0, j->f1, j->is_paired, j->out_align, j->out_verify, &j->stats);
+	j->rc = vote_range(j->idx, j->p, j->text, j->off, j->len, j->f0, j->f1, j->is_paired, j->out_align, j->out_junc, j->out_big_margin,
+	                   j->out_verify, &j->stats);
 	return NULL;
 }
 
@@ -800,9 +990,9 @@ int or_vote_chunk_mt(const or_index_t *idx, const or_params_t *p, const char *te
                      int64_t n_frags, int is_paired, or_mapping_result_t *out_align, or_subjunc_result_t *out_junc,
                      uint16_t *out_big_margin, uint16_t *out_verify, or_stats_t *stats, int n_threads)
 {
-	(void)out_junc; (void)out_big_margin;
 	int r = check_params(idx, p);
 	if (r) return r;
+	if (p->do_breakpoint_detection && !out_junc) return 8;
 	if (n_threads < 1) n_threads = 1;
 	if (n_threads > 256) n_threads = 256;
 	pthread_t th[256];
@@ -811,7 +1001,7 @@ int or_vote_chunk_mt(const or_index_t *idx, const or_params_t *p, const char *te
 		mt_job_t *j = &jobs[t];
 		j->idx = idx; j->p = p; j->text = text; j->off = off; j->len = len; j->is_paired = is_paired;
 		j->f0 = n_frags * t / n_threads; j->f1 = n_frags * (t + 1) / n_threads;
-		j->out_align = out_align; j->out_verify = out_verify;
+		j->out_align = out_align; j->out_junc = out_junc; j->out_big_margin = out_big_margin; j->out_verify = out_verify;
 		pthread_create(&th[t], NULL, mt_entry, j);
 	}
 	for (int t = 0; t < n_threads; t++) {

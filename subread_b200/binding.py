@@ -185,11 +185,22 @@ class Mapper:
         return d
 
     # -- voting ------------------------------------------------------------------------------
-    def vote_chunk(self, chunk, params: VoteParams, out_align=None, want_verify=False):
-        """Host-buffer entry point (copies inside).  Returns (align[n_frags, mates, multi_best], verify|None)."""
+    def vote_chunk(self, chunk, params: VoteParams, out_align=None, want_verify=False, junc_state=None):
+        """Host-buffer entry point (copies inside).  Returns (align[n_frags, mates, multi_best], verify|None).
+        subjunc (params.do_breakpoint_detection): pass junc_state = {} -- it receives 'junc' and 'big_margin',
+        which are read-modify-write across index blocks together with out_align."""
+        from .layout import SUBJUNC_RESULT
         mb = params.multi_best_reads
         n = chunk.n_frags * chunk.mates * mb
         is_zero = out_align is None
+        junc = bm = None
+        if params.do_breakpoint_detection:
+            if junc_state is None:
+                junc_state = {}
+            if "junc" not in junc_state:
+                junc_state["junc"] = np.zeros(n, dtype=SUBJUNC_RESULT)
+                junc_state["big_margin"] = np.zeros(chunk.n_frags * chunk.mates * 27, dtype=np.uint16)
+            junc, bm = junc_state["junc"], junc_state["big_margin"]
         if out_align is None:
             out_align = np.zeros(n, dtype=MAPPING_RESULT)
         out_align = out_align.reshape(-1)
@@ -201,7 +212,7 @@ class Mapper:
         if text.shape[0] == 0:
             text = np.zeros(1, np.uint8)
         rc = self.lib.srcuda_vote_chunk(self.h, ctypes.byref(params), _ptr(text), _ptr(off), _ptr(ln), chunk.n_frags,
-                                        int(chunk.is_paired), int(is_zero), _ptr(out_align), None, None, _ptr(verify))
+                                        int(chunk.is_paired), int(is_zero), _ptr(out_align), _ptr(junc), _ptr(bm), _ptr(verify))
         self._check(rc, "srcuda_vote_chunk")
         return out_align.reshape(chunk.n_frags, chunk.mates, mb), verify
 

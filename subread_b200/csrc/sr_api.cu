@@ -46,6 +46,8 @@ struct ChunkArgs {
 	uint32_t *queue_count;
 	uint32_t *bad_reads;       // counter of reads whose (off,len) fall outside the text buffer
 	int out_zero;              // the bigtable slice is known to be all zero: do not read it
+	JuncWords *junc;           // subjunc only: [frag][mate][multi_best] subjunc_result_t, else null
+	uint16_t *big_margin;      // subjunc only: [frag][mate][27]
 };
 
 template <int MATES, int GAP>
@@ -110,12 +112,16 @@ k_map_scalar(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int use
 			if (!use_queue) atomicAdd(a.bad_reads, 1u);
 			continue;
 		}
+		JuncWords *jr = a.junc ? a.junc + (size_t)f * mates * mb : nullptr;
+		uint16_t *bm = a.big_margin ? a.big_margin + (size_t)f * mates * kBigMarginU16 : nullptr;
 		if (a.out_zero) {
 			ResultWords *r = a.out + (size_t)f * mates * mb;
 			for (int k = 0; k < mates * mb; k++)
 				for (int w = 0; w < kResultWords; w++) r[k].w[w] = 0;
+			if (jr) for (int k = 0; k < mates * mb; k++) for (int w = 0; w < 4; w++) jr[k].w[w] = 0;
+			if (bm) for (int k = 0; k < mates * kBigMarginU16; k++) bm[k] = 0;
 		}
-		scalar_vote_fragment(ix, cfg, a.text + o0, l0, a.text + o1, l1, a.out + (size_t)f * mates * mb,
+		scalar_vote_fragment(ix, cfg, a.text + o0, l0, a.text + o1, l1, a.out + (size_t)f * mates * mb, jr, bm,
 		                     a.verify ? a.verify + (size_t)f * mates * mb : nullptr, scratch + tid);
 	}
 }
@@ -182,7 +188,7 @@ struct DeviceBuf {
 
 struct BatchSet {  // one of two buffer sets; used by one stream
 	cudaStream_t stream = nullptr;
-	DeviceBuf text, off, len, out, verify, queue;
+	DeviceBuf text, off, len, out, verify, queue, junc, big_margin;
 	uint32_t *counters = nullptr;       // device: [0] queue_count, [1] bad_reads
 	uint32_t *h_counters = nullptr;     // pinned host mirror, 2 per batch slot
 	sr::ScalarScratch *scratch = nullptr;
@@ -383,14 +389,16 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	const int scalar_grid = h->sm_count * sr::kScalarBlocksPerSM;
 	if (!bs.scratch)
 		CU(h, cudaMalloc((void **)&bs.scratch, sizeof(sr::ScalarScratch) * (size_t)scalar_grid * sr::kScalarThreads));
+	// subjunc's minor-half / donor search (K_junc) is built on the exact scalar path only so far
+	const bool scalar_only = h->force_slow || cfg.do_junctions;
 	if (ev) CU(h, cudaEventRecord(ev[0], s));
-	if (!h->force_slow) {
+	if (!scalar_only) {
 		int rc = cfg.is_paired ? launch_warp_gap<2>(h, s, cfg, a, max_len) : launch_warp_gap<1>(h, s, cfg, a, max_len);
 		if (rc) return rc;
 		h->timing.n_launches++;
 	}
 	if (ev) CU(h, cudaEventRecord(ev[1], s));
-	sr::k_map_scalar<<<scalar_grid, sr::kScalarThreads, 0, s>>>(h->ix, cfg, a, h->force_slow ? 0 : 1, bs.scratch);
+	sr::k_map_scalar<<<scalar_grid, sr::kScalarThreads, 0, s>>>(h->ix, cfg, a, scalar_only ? 0 : 1, bs.scratch);
 	CU(h, cudaGetLastError());
 	h->timing.n_launches++;
 	if (ev) CU(h, cudaEventRecord(ev[2], s));
@@ -457,7 +465,7 @@ void srcuda_close(srcuda_handle *h)
 	free_index(h);
 	for (int i = 0; i < 2; i++) {
 		BatchSet &b = h->set[i];
-		for (DeviceBuf *d : {&b.text, &b.off, &b.len, &b.out, &b.verify, &b.queue}) cudaFree(d->p);
+		for (DeviceBuf *d : {&b.text, &b.off, &b.len, &b.out, &b.verify, &b.queue, &b.junc, &b.big_margin}) cudaFree(d->p);
 		cudaFree(b.counters);
 		cudaFree(b.scratch);
 		if (b.h_counters) cudaFreeHost(b.h_counters);
@@ -661,8 +669,8 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
                              srcuda_mapping_result *d_out_align, srcuda_subjunc_result *d_out_junc, uint16_t *d_out_big_margin,
                              uint16_t *d_out_verify)
 {
-	(void)d_out_junc; (void)d_out_big_margin;
 	if (!h || !params || !d_text || !d_off || !d_len || !d_out_align) return fail(h, SRCUDA_ERR_ARG, "srcuda_vote_chunk_device: null argument");
+	if (params->do_breakpoint_detection && (!d_out_junc || !d_out_big_margin)) return fail(h, SRCUDA_ERR_ARG, "do_breakpoint_detection needs out_junc and out_big_margin");
 	if (!h->has_index) return fail(h, SRCUDA_ERR_NO_INDEX, "no index block is loaded");
 	if (n_frags < 0 || n_frags > 0x7fffffffLL) return fail(h, SRCUDA_ERR_ARG, "n_frags %lld out of range", (long long)n_frags);
 	if (max_read_len < 1 || max_read_len > sr::kMaxReadLen) return fail(h, SRCUDA_ERR_ARG, "max_read_len %d not in 1..%d", max_read_len, sr::kMaxReadLen);
@@ -688,6 +696,8 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	a.out = (sr::ResultWords *)d_out_align; a.verify = d_out_verify;
 	a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
 	a.out_zero = out_align_is_zero ? 1 : 0;
+	a.junc = cfg.do_junctions ? (sr::JuncWords *)d_out_junc : nullptr;
+	a.big_margin = cfg.do_junctions ? d_out_big_margin : nullptr;
 	rc = launch_vote(h, bs.stream, cfg, a, max_read_len, bs, h->events.data());
 	if (rc) return rc;
 	uint32_t counters[2] = {0, 0};
@@ -700,7 +710,7 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	h->timing.ms_kernel_overflow = ms;
 	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[2]));
 	h->timing.ms_total = ms;
-	h->timing.n_overflow = h->force_slow ? (uint64_t)n_frags : counters[0];
+	h->timing.n_overflow = (h->force_slow || cfg.do_junctions) ? (uint64_t)n_frags : counters[0];
 	h->timing.n_batches = 1;
 	if (counters[1]) return fail(h, SRCUDA_ERR_ARG, "%u reads have (off,len) outside the text buffer or len > %d", counters[1], sr::kMaxReadLen);
 	return SRCUDA_OK;
@@ -710,8 +720,8 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
                       int64_t n_frags, int is_paired, int out_align_is_zero, srcuda_mapping_result *out_align,
                       srcuda_subjunc_result *out_junc, uint16_t *out_big_margin, uint16_t *out_verify)
 {
-	(void)out_junc; (void)out_big_margin;
 	if (!h || !params || !text || !off || !len || !out_align) return fail(h, SRCUDA_ERR_ARG, "srcuda_vote_chunk: null argument");
+	if (params->do_breakpoint_detection && (!out_junc || !out_big_margin)) return fail(h, SRCUDA_ERR_ARG, "do_breakpoint_detection needs out_junc and out_big_margin");
 	if (!h->has_index) return fail(h, SRCUDA_ERR_NO_INDEX, "no index block is loaded");
 	if (n_frags < 0) return fail(h, SRCUDA_ERR_ARG, "n_frags < 0");
 	CU(h, cudaSetDevice(h->device));
@@ -757,6 +767,11 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		if ((rc = ensure(h, bs.out, sizeof(srcuda_mapping_result) * n_slots))) return rc;
 		if ((rc = ensure(h, bs.queue, sizeof(uint32_t) * (size_t)nf))) return rc;
 		if (out_verify && (rc = ensure(h, bs.verify, sizeof(uint16_t) * n_slots))) return rc;
+		const size_t bm_bytes = sizeof(uint16_t) * sr::kBigMarginU16 * (size_t)nr;
+		if (cfg.do_junctions) {
+			if ((rc = ensure(h, bs.junc, sizeof(srcuda_subjunc_result) * n_slots))) return rc;
+			if ((rc = ensure(h, bs.big_margin, bm_bytes))) return rc;
+		}
 
 		CU(h, cudaMemcpyAsync(bs.text.p, text + origin, text_bytes, cudaMemcpyHostToDevice, s));
 		CU(h, cudaMemcpyAsync(bs.off.p, off + r0, sizeof(uint64_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
@@ -765,6 +780,11 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		if (!out_align_is_zero) {
 			CU(h, cudaMemcpyAsync(bs.out.p, out_align + (size_t)r0 * mb, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyHostToDevice, s));
 			h->timing.h2d_bytes += sizeof(srcuda_mapping_result) * n_slots;
+			if (cfg.do_junctions) {
+				CU(h, cudaMemcpyAsync(bs.junc.p, out_junc + (size_t)r0 * mb, sizeof(srcuda_subjunc_result) * n_slots, cudaMemcpyHostToDevice, s));
+				CU(h, cudaMemcpyAsync(bs.big_margin.p, out_big_margin + (size_t)r0 * sr::kBigMarginU16, bm_bytes, cudaMemcpyHostToDevice, s));
+				h->timing.h2d_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
+			}
 		}
 		CU(h, cudaMemsetAsync(bs.counters, 0, 2 * sizeof(uint32_t), s));
 		sr::ChunkArgs a;
@@ -773,12 +793,19 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		a.out = (sr::ResultWords *)bs.out.p; a.verify = out_verify ? (uint16_t *)bs.verify.p : nullptr;
 		a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
 		a.out_zero = out_align_is_zero ? 1 : 0;
+		a.junc = cfg.do_junctions ? (sr::JuncWords *)bs.junc.p : nullptr;
+		a.big_margin = cfg.do_junctions ? (uint16_t *)bs.big_margin.p : nullptr;
 		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[3 * bi]))) return rc;
 		CU(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
 		h->timing.d2h_bytes += sizeof(srcuda_mapping_result) * n_slots;
 		if (out_verify) {
 			CU(h, cudaMemcpyAsync(out_verify + (size_t)r0 * mb, bs.verify.p, sizeof(uint16_t) * n_slots, cudaMemcpyDeviceToHost, s));
 			h->timing.d2h_bytes += sizeof(uint16_t) * n_slots;
+		}
+		if (cfg.do_junctions) {
+			CU(h, cudaMemcpyAsync(out_junc + (size_t)r0 * mb, bs.junc.p, sizeof(srcuda_subjunc_result) * n_slots, cudaMemcpyDeviceToHost, s));
+			CU(h, cudaMemcpyAsync(out_big_margin + (size_t)r0 * sr::kBigMarginU16, bs.big_margin.p, bm_bytes, cudaMemcpyDeviceToHost, s));
+			h->timing.d2h_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 		}
 		CU(h, cudaMemcpyAsync(bs.h_counters + 2 * (bi / 2), bs.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	}
@@ -798,7 +825,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		CU(h, cudaEventElapsedTime(&ms, h->events[3 * bi + 1], h->events[3 * bi + 2]));
 		h->timing.ms_kernel_overflow += ms;
 		const uint32_t *c = h->set[bi & 1].h_counters + 2 * (bi / 2);
-		h->timing.n_overflow += h->force_slow ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
+		h->timing.n_overflow += (h->force_slow || cfg.do_junctions) ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
 		bad += c[1];
 	}
 	h->timing.n_batches = (uint32_t)n_batches;

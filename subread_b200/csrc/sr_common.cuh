@@ -63,7 +63,17 @@ struct VoteConfig {
 	int32_t min_pair_dist, max_pair_dist, first_reversed, second_reversed;
 	int32_t is_paired;
 	uint32_t low_border, high_border;  // core.c:3081-3082
+	// subjunc (do_breakpoint_detection): minor-half / donor-site search, core-junction.c:1073-1334, 3675-3832
+	int32_t do_junctions, big_margin_filtering, big_margin_record_size, maximum_intron_length;
+	int32_t check_donor, mismatch_allowed, prefer_donor;
 };
+
+// subjunc_result_t (core.h:397-410) as four little-endian words:
+//  w0 split_point,minor_votes | w1 double_indel_offset,indel_at_junction,small_inc,large_inc | w2 minor_position
+//  w3 minor_coverage_start,minor_coverage_end
+struct JuncWords { uint32_t w[4]; };
+constexpr int kBigMarginU16 = 27;    // bigtable_cached_result_t.big_margin_data, core.h:453
+constexpr int kConfirmWindow = 17;   // JUNCTION_CONFIRM_WINDOW core-junction.c:3569
 
 // mapping_result_t as 17 little-endian words:
 //  w0 pos | w1 flags,read_length | w2 votes,used | w3 noninf,indels,full,pad | w4..w14 record[22]

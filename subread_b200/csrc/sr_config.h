@@ -23,7 +23,8 @@ inline int make_vote_config(const srcuda_params &p, int is_paired, int index_gap
 	SR_REQUIRE(p.max_vote_combinations >= 1 && p.max_vote_combinations <= kMaxCombos, SRCUDA_ERR_UNSUPPORTED, "max_vote_combinations %d not in 1..%d", p.max_vote_combinations, kMaxCombos);
 	SR_REQUIRE(p.max_vote_number_cutoff >= 0, SRCUDA_ERR_ARG, "max_vote_number_cutoff %d < 0", p.max_vote_number_cutoff);
 	SR_REQUIRE(p.max_indel_length >= 0, SRCUDA_ERR_ARG, "max_indel_length %d < 0", p.max_indel_length);
-	SR_REQUIRE(!p.do_breakpoint_detection, SRCUDA_ERR_UNSUPPORTED, "do_breakpoint_detection (subjunc junction voting) is not built yet");
+	SR_REQUIRE(!p.do_breakpoint_detection || p.max_insertion_at_junctions == 0, SRCUDA_ERR_UNSUPPORTED, "max_insertion_at_junctions %d != 0 is not supported", p.max_insertion_at_junctions);
+	SR_REQUIRE(!p.do_breakpoint_detection || (p.big_margin_record_size >= 0 && p.big_margin_record_size <= kBigMarginU16), SRCUDA_ERR_ARG, "big_margin_record_size %d not in 0..27", p.big_margin_record_size);
 #undef SR_REQUIRE
 	c->total_subreads = p.total_subreads;
 	c->top_scores = p.top_scores;
@@ -41,6 +42,13 @@ inline int make_vote_config(const srcuda_params &p, int is_paired, int index_gap
 	c->is_paired = is_paired ? 1 : 0;
 	c->low_border = start_base_offset;            // core.c:3081
 	c->high_border = start_base_offset + length;  // core.c:3082
+	c->do_junctions = p.do_breakpoint_detection ? 1 : 0;
+	c->big_margin_filtering = p.do_big_margin_filtering_for_junctions ? 1 : 0;
+	c->big_margin_record_size = p.big_margin_record_size;
+	c->maximum_intron_length = p.maximum_intron_length;
+	c->check_donor = p.check_donor_at_junctions ? 1 : 0;
+	c->mismatch_allowed = p.more_accurate_fusions ? 0 : 1;  // mismatch_in_between_allowd, core-junction.c:3735
+	c->prefer_donor = p.prefer_donor_receptor_junctions ? 1 : 0;
 	return SRCUDA_OK;
 }
 

@@ -44,6 +44,7 @@ struct ScalarScratch {
 	ScalarSimple simple[2][kMaxSimples];
 	ScalarCombo comb[kMaxCombos + 1];
 	ResultWords tmp[2][kMaxBest];
+	JuncWords jtmp[2][kMaxBest];
 };
 
 SR_HD int sc_char(uint8_t c) { return (int)(int8_t)c; }
@@ -199,6 +200,161 @@ SR_HD void sc_go_X(const DevIndex &ix, uint32_t raw_key, int offset, ScalarTable
 	}
 }
 
+
+SR_HD int sc_match_forward(const DevIndex &ix, const uint8_t *text, uint32_t pos, int len);
+
+// ---- subjunc: minor half + donor site (core-junction.c:1073-1334, donor_score :3675-3832) --------------
+SR_HD int sc_genome_char(const DevIndex &ix, uint32_t p)  // gvindex_get, gene-value-index.c:96-107
+{
+	uint32_t q = p - ix.start_base_offset;
+	if ((q >> 2) >= ix.values_bytes - 1) return 'N';
+	int code = (ix.genome[q >> 4] >> (2 * (q & 15))) & 3;
+	return code == 0 ? 'A' : (code == 1 ? 'G' : (code == 2 ? 'C' : 'T'));
+}
+
+SR_HD bool sc_donor_chars(int a, int b) { return (a == 'G' && b == 'T') || (a == 'A' && b == 'G') || (a == 'A' && b == 'C') || (a == 'C' && b == 'T'); }
+
+SR_HD int sc_donor_pair(int a0, int a1, int b0, int b1)  // paired_chars_part_core(.., 0)
+{
+	bool a_gt = a0 == 'G' && a1 == 'T', a_ag = a0 == 'A' && a1 == 'G', a_ct = a0 == 'C' && a1 == 'T', a_ac = a0 == 'A' && a1 == 'C';
+	bool b_gt = b0 == 'G' && b1 == 'T', b_ag = b0 == 'A' && b1 == 'G', b_ct = b0 == 'C' && b1 == 'T', b_ac = b0 == 'A' && b1 == 'C';
+	if ((a_gt && b_ag) || (a_ag && b_gt) || (a_ct && b_ac) || (a_ac && b_ct)) return (a_ct || a_gt) ? 1 : 0;
+	return 0;
+}
+
+SR_HD int sc_donor_score(const DevIndex &ix, const VoteConfig &cfg, uint32_t left_pos, uint32_t right_pos, int left_indel, int right_indel,
+                         int normally_arranged, int guess_start, int guess_end, const uint8_t *text, int rlen, int *split_point,
+                         int *gt_ag_strand, int *donor_found)
+{
+	const int W = kConfirmWindow;
+	int most_likely = (guess_start + guess_end) / 2;
+	int sel_split = -1, sel_strand = -1, best = -111111;
+	int dl0 = 0, dl1 = 0, dr0 = 0, dr1 = 0;
+	int n_points = guess_end - guess_start;
+	for (int k = 0; k < n_points; k++) {
+		int sp = ((k % 2) ? -((k + 1) / 2) : ((1 + k) / 2)) + most_likely;
+		int donor_ok = 0;
+		if (sp > rlen - W) continue;
+		if (sp < W) continue;
+		if (cfg.prefer_donor) {
+			if (normally_arranged) {
+				uint32_t a = left_pos + (uint32_t)sp + (uint32_t)left_indel;
+				dl0 = sc_genome_char(ix, a); dl1 = sc_genome_char(ix, a + 1);
+				if (sc_donor_chars(dl0, dl1)) {
+					uint32_t b = right_pos + (uint32_t)sp + (uint32_t)right_indel - 2;
+					dr0 = sc_genome_char(ix, b); dr1 = sc_genome_char(ix, b + 1);
+					if (sc_donor_chars(dr0, dr1)) donor_ok = sc_donor_pair(dl0, dl1, dr0, dr1);
+				}
+			} else {
+				uint32_t a = right_pos + (uint32_t)sp + (uint32_t)left_indel, b = left_pos + (uint32_t)sp + (uint32_t)right_indel - 2;
+				dl0 = sc_genome_char(ix, a); dl1 = sc_genome_char(ix, a + 1);
+				dr0 = sc_genome_char(ix, b); dr1 = sc_genome_char(ix, b + 1);
+				donor_ok = (sc_donor_chars(dl0, dl1) && sc_donor_chars(dr0, dr1)) ? sc_donor_pair(dl0, dl1, dr0, dr1) : 0;
+			}
+		}
+		if (!(donor_ok || !cfg.check_donor)) continue;
+		if (normally_arranged) {
+			int lm = sc_match_forward(ix, text + sp - W, left_pos + (uint32_t)sp - W + (uint32_t)left_indel, W);
+			if (lm > W - 2) {
+				int rm = sc_match_forward(ix, text + sp, right_pos + (uint32_t)sp + (uint32_t)right_indel, W);
+				if (rm >= 2 * W - lm - cfg.mismatch_allowed) {
+					int lnm = sc_match_forward(ix, text + sp, left_pos + (uint32_t)sp + (uint32_t)left_indel, W);
+					int rnm = sc_match_forward(ix, text + sp - W, right_pos + (uint32_t)sp + (uint32_t)right_indel - W, W);
+					if (lnm <= W - 5 && rnm <= W - 5) {
+						int score = 100 * (donor_ok * 3000 + lm + rm - lnm - rnm);
+						if (score > best) { sel_strand = (dl0 == 'G' || dr1 == 'G') ? 1 : 0; sel_split = sp; best = score; }
+					}
+				}
+			}
+		} else {
+			int rm = sc_match_forward(ix, text + sp - W, right_pos + (uint32_t)right_indel + (uint32_t)sp - W, W);
+			int lm = sc_match_forward(ix, text + sp, left_pos + (uint32_t)sp + (uint32_t)left_indel, W);
+			int rnm = sc_match_forward(ix, text + sp, right_pos + (uint32_t)sp + (uint32_t)right_indel, W);
+			int lnm = sc_match_forward(ix, text + sp - W, left_pos + (uint32_t)left_indel + (uint32_t)sp - W, W);
+			if (lm + rm >= 2 * W - cfg.mismatch_allowed && lnm <= W - 5 && rnm <= W - 5) {
+				int score = 100 * (donor_ok * 3000 + lm + rm - lnm - rnm);
+				if (score > best) { sel_strand = (dl0 == 'G' || dr1 == 'G') ? 1 : 0; sel_split = sp; best = score; }
+			}
+		}
+	}
+	if (best > 0) {
+		*split_point = sel_split;
+		*donor_found = best >= 290000;
+		*gt_ag_strand = sel_strand;
+		return (1 + best) / 100;
+	}
+	return 0;
+}
+
+SR_HD void sc_big_margin_insert(const VoteConfig &cfg, uint16_t *rec, int votes, int start, int end, int rlen, bool negative)
+{   // insert_big_margin_record, core-junction.c:789-813 (votes is an unsigned char there)
+	const int n = cfg.big_margin_record_size;
+	if (n < 3) return;
+	const uint16_t v8 = (uint16_t)(uint8_t)votes;
+	const uint16_t s2 = (uint16_t)(negative ? rlen - end : start), e2 = (uint16_t)(negative ? rlen - start : end);
+	int x;
+	for (x = 0; x < n / 3; x++)
+		if (v8 >= rec[x * 3]) break;
+	if (x < n / 3) {
+		for (int y = n - 4; y >= x * 3; y--) rec[y + 3] = rec[y];
+		rec[x * 3] = v8; rec[x * 3 + 1] = s2; rec[x * 3 + 2] = e2;
+	}
+}
+
+// The do_breakpoint_detection part of copy_vote_to_alignment_res for one emitted slot.
+SR_HD void sc_minor_half(const DevIndex &ix, const VoteConfig &cfg, ResultWords *r, JuncWords *jr, const ScalarTable *v, int vi, int vj,
+                         int rlen, const uint8_t *text)
+{
+	const int sel_votes = (int16_t)(r->w[2] & 0xffffu);
+	for (int i = 0; i < kVoteRows; i++)
+		for (int j = 0; j < v->items[i]; j++) {
+			if (i == vi && j == vj) continue;
+			if (sel_votes < v->votes[i][j]) continue;
+			const uint32_t pm = v->pos[vi][vj], pn = v->pos[i][j];
+			const long long dist = (long long)pm - (long long)pn;
+			const int cs_m = v->cov_start[vi][vj], ce_m = v->cov_end[vi][vj], cs_n = v->cov_start[i][j], ce_n = v->cov_end[i][j];
+			if (sc_abs((int)dist) > cfg.maximum_intron_length) continue;  // test_junction_minor :889 (abs() truncates to int)
+			if (cs_m == cs_n) continue;
+			if (ce_m == ce_n) continue;
+			if (cs_m > cs_n) { if (pm < pn) continue; } else { if (pm > pn) continue; }
+			// is_better_inner :975
+			const int16_t jr_votes = (int16_t)(jr->w[0] >> 16);
+			const int jcov = (int)(uint16_t)(jr->w[3] >> 16) - (int)(uint16_t)(jr->w[3] & 0xffffu);
+			uint32_t oi = pm - jr->w[2]; if (oi > 0x7fffffffu) oi = (0xffffffffu - oi) + 1;
+			uint32_t ni = pm - pn; if (ni > 0x7fffffffu) ni = (0xffffffffu - ni) + 1;
+			const int mv = v->votes[i][j], mcov = ce_n - cs_n;
+			const bool better = mv > jr_votes || (mv == jr_votes && mcov > jcov) || (mv == jr_votes && mcov == jcov && (int)ni < (int)oi);
+			if (!better) continue;
+			const int overlapped = cs_m > cs_n ? ce_n - cs_m : ce_m - cs_n;
+			if (overlapped > 14) continue;
+			if (sc_abs((int)dist) < 6) continue;
+			const int guess_start = cs_m > cs_n ? ce_n - 8 : ce_m - 8;
+			const int guess_end = cs_m < cs_n ? cs_n + 8 : cs_m + 8;
+			const int normally_arranged = 1 != (cs_m > cs_n) + (pm > pn);
+			int left_indel = 0, major_indels = 0, minor_indel_offset = 0;
+			if (rlen > kLongRead) {
+				for (int k = 0; k < kMaxSections; k++) { if (!v->rec[vi][vj][k * 3]) break; major_indels += v->rec[vi][vj][k * 3 + 2]; }
+				for (int k = 0; k < kMaxSections; k++) { if (!v->rec[i][j][k * 3]) break; minor_indel_offset += v->rec[i][j][k * 3 + 2]; }
+				left_indel = pm < pn ? major_indels : minor_indel_offset;
+			}
+			int split = 0, gt_ag = 0, donor_found = 0;
+			const int replace = sc_donor_score(ix, cfg, pm < pn ? pm : pn, pm > pn ? pm : pn, left_indel, 0, normally_arranged,
+			                                   guess_start > 0 ? guess_start : 0, guess_end < rlen ? guess_end : rlen, text, rlen, &split, &gt_ag, &donor_found);
+			if (!replace) continue;
+			jr->w[0] = (uint32_t)(uint16_t)split | ((uint32_t)(uint16_t)mv << 16);
+			jr->w[1] = (uint32_t)(uint8_t)((minor_indel_offset & 0xf) | ((major_indels & 0xf) << 4)) | (0u << 8) |
+			           ((uint32_t)(uint8_t)(!normally_arranged) << 16) | ((uint32_t)(uint8_t)normally_arranged << 24);
+			jr->w[2] = pn;
+			jr->w[3] = (uint32_t)(uint16_t)cs_n | ((uint32_t)(uint16_t)ce_n << 16);
+			uint32_t flags = r->w[1] & 0xffffu;
+			flags &= ~0x3u;
+			if (!donor_found || gt_ag > 2) flags |= 3u;
+			else flags = gt_ag ? (flags | 1u) : (flags & ~1u);
+			flags &= ~4u;
+			r->w[1] = (r->w[1] & 0xffff0000u) | flags;
+		}
+}
+
 SR_HD void sc_update_top(int top_scores, int *top, int v)  // update_top_three core-junction.c:908
 {
 	if (v > top[top_scores - 1])
@@ -236,8 +392,9 @@ SR_HD void sc_slot_to_result(ResultWords *r, const ScalarTable *v, int i, int j,
 
 // process_voting_junction_PE_topK, core-junction.c:2199-2530, DNA mode.
 SR_HD void sc_topk(const DevIndex &ix, const VoteConfig &cfg, int strand, ScalarTable *const vt[2], const int rlen[2],
-                   const int all_subreads[2], ResultWords *res, ScalarScratch *sc)
+                   const int all_subreads[2], ResultWords *res, JuncWords *jres, uint16_t *big_margin, ScalarScratch *sc)
 {
+	const bool junc = cfg.do_junctions && jres != nullptr;
 	const int mates = 1 + cfg.is_paired, mb = cfg.multi_best_reads;
 	int top[2][kMaxTop];
 	int n_simple[2] = {0, 0};
@@ -259,6 +416,8 @@ SR_HD void sc_topk(const DevIndex &ix, const VoteConfig &cfg, int strand, Scalar
 			for (int i = 0; i < kVoteRows && n < cfg.max_vote_simples; i++)
 				for (int j = 0; j < vt[m]->items[i] && n < cfg.max_vote_simples; j++) {
 					int vv = vt[m]->votes[i][j];
+					if (cfg.big_margin_filtering && big_margin && lv == 0 && vv >= top[m][cfg.top_scores - 1])  // core-junction.c:2281
+						sc_big_margin_insert(cfg, big_margin + m * kBigMarginU16, vv, vt[m]->cov_start[i][j], vt[m]->cov_end[i][j], rlen[m], strand != 0);
 					if (vv == want && vv >= cfg.min_second) {
 						sp[n].is_vote_item = 1; sp[n].i = (int8_t)i; sp[n].j = (int8_t)j;
 						sp[n].pos = vt[m]->pos[i][j]; sp[n].votes = (int16_t)vv;
@@ -318,10 +477,15 @@ SR_HD void sc_topk(const DevIndex &ix, const VoteConfig &cfg, int strand, Scalar
 				for (int j = 0; j < cursor[m]; j++)
 					if (sc->tmp[m][j].w[0] == loc->pos) { exist = true; break; }
 				if (exist) continue;
+				if (junc) for (int w = 0; w < 4; w++) sc->jtmp[m][cursor[m]].w[w] = 0;
 				if (loc->is_vote_item) {
 					sc_slot_to_result(&sc->tmp[m][cursor[m]], vt[m], loc->i, loc->j, all_subreads[m]);
 					sc->tmp[m][cursor[m]].w[1] = strand_flag;
-				} else sc->tmp[m][cursor[m]] = res[m * mb + loc->i];
+					if (junc) sc_minor_half(ix, cfg, &sc->tmp[m][cursor[m]], &sc->jtmp[m][cursor[m]], vt[m], loc->i, loc->j, rlen[m], sc->text[m]);
+				} else {
+					sc->tmp[m][cursor[m]] = res[m * mb + loc->i];
+					if (junc) sc->jtmp[m][cursor[m]] = jres[m * mb + loc->i];
+				}
 				cursor[m]++;
 			}
 	} else {
@@ -336,10 +500,15 @@ SR_HD void sc_topk(const DevIndex &ix, const VoteConfig &cfg, int strand, Scalar
 					for (int j = 0; j < cursor[m]; j++)
 						if (sc->tmp[m][j].w[0] == loc->pos) { exist = true; break; }
 					if (exist) continue;
+					if (junc) for (int w = 0; w < 4; w++) sc->jtmp[m][cursor[m]].w[w] = 0;
 					if (loc->is_vote_item) {
 						sc_slot_to_result(&sc->tmp[m][cursor[m]], vt[m], loc->i, loc->j, all_subreads[m]);
 						sc->tmp[m][cursor[m]].w[1] = strand_flag;
-					} else sc->tmp[m][cursor[m]] = res[m * mb + loc->i];
+						if (junc) sc_minor_half(ix, cfg, &sc->tmp[m][cursor[m]], &sc->jtmp[m][cursor[m]], vt[m], loc->i, loc->j, rlen[m], sc->text[m]);
+					} else {
+						sc->tmp[m][cursor[m]] = res[m * mb + loc->i];
+						if (junc) sc->jtmp[m][cursor[m]] = jres[m * mb + loc->i];
+					}
 					cursor[m]++;
 				}
 	}
@@ -347,6 +516,10 @@ SR_HD void sc_topk(const DevIndex &ix, const VoteConfig &cfg, int strand, Scalar
 		for (int k = 0; k < mb; k++) {
 			if (k < cursor[m]) res[m * mb + k] = sc->tmp[m][k];
 			else res[m * mb + k].w[2] &= 0xffff0000u;  // selected_votes = 0 only (core-junction.c:2517)
+			if (junc) {
+				if (k < cursor[m]) jres[m * mb + k] = sc->jtmp[m][k];
+				else jres[m * mb + k].w[0] &= 0x0000ffffu;  // minor_votes = 0 (core-junction.c:2524)
+			}
 		}
 }
 
@@ -371,7 +544,8 @@ SR_HD int sc_match_forward(const DevIndex &ix, const uint8_t *text, uint32_t pos
 // One fragment through do_voting's body (core.c:3106-3235).  res is read-modify-write
 // [mates * multi_best_reads]; verify (optional) gets one count per result slot.
 SR_HD void scalar_vote_fragment(const DevIndex &ix, const VoteConfig &cfg, const uint8_t *raw0, int len0,
-                                const uint8_t *raw1, int len1, ResultWords *res, uint16_t *verify, ScalarScratch *sc)
+                                const uint8_t *raw1, int len1, ResultWords *res, JuncWords *jres, uint16_t *big_margin, uint16_t *verify,
+                                ScalarScratch *sc)
 {
 	const int mates = 1 + cfg.is_paired, mb = cfg.multi_best_reads, gap = ix.index_gap;
 	ScalarTable *vt[2] = {&sc->vt[0], &sc->vt[1]};
@@ -405,9 +579,9 @@ SR_HD void scalar_vote_fragment(const DevIndex &ix, const VoteConfig &cfg, const
 			}
 		}
 		if (cfg.is_paired) {
-			sc_topk(ix, cfg, strand, vt, rlen, all_subreads, res, sc);
+			sc_topk(ix, cfg, strand, vt, rlen, all_subreads, res, jres, big_margin, sc);
 		} else if (vt[0]->max_vote >= cfg.min_first) {
-			sc_topk(ix, cfg, strand, vt, rlen, all_subreads, res, sc);
+			sc_topk(ix, cfg, strand, vt, rlen, all_subreads, res, jres, big_margin, sc);
 		} else if (result_votes(res[0]) < 1) {  // core.c:3217-3225
 			res[0].w[3] &= ~0xffu;
 			int16_t used = (int16_t)(res[0].w[2] >> 16);

@@ -74,7 +74,10 @@ class VoteParams(ctypes.Structure):
         ("maximum_intron_length", ctypes.c_int32),
         ("limited_tree_scan", ctypes.c_int32),
         ("check_donor_at_junctions", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 5),
+        ("more_accurate_fusions", ctypes.c_int32),
+        ("max_insertion_at_junctions", ctypes.c_int32),
+        ("prefer_donor_receptor_junctions", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 2),
     ]
 
     @classmethod
@@ -102,6 +105,9 @@ class VoteParams(ctypes.Structure):
         p.maximum_intron_length = 500000
         p.limited_tree_scan = 0
         p.check_donor_at_junctions = 1
+        p.more_accurate_fusions = 0       # ... && do_fusion_detection, core-interface-subjunc.c:671 / -aligner.c:648
+        p.max_insertion_at_junctions = 0
+        p.prefer_donor_receptor_junctions = 1
         return p
 
 

@@ -13,7 +13,8 @@ extern "C" int sr_scalar_host_vote_chunk(int32_t index_gap, int32_t padding, uin
                                          uint32_t start_point, uint32_t length, const uint8_t *values, uint32_t values_bytes,
                                          const uint32_t *read_offsets, int32_t total_offsets, const srcuda_params *p,
                                          const uint8_t *text, const uint64_t *off, const uint16_t *len, int64_t n_frags,
-                                         int is_paired, srcuda_mapping_result *out_align, uint16_t *out_verify)
+                                         int is_paired, srcuda_mapping_result *out_align, srcuda_subjunc_result *out_junc, uint16_t *out_big_margin,
+                                         uint16_t *out_verify)
 {
 	sr::DevIndex ix{};
 	ix.buckets_number = buckets_number; ix.index_gap = index_gap; ix.padding = padding;
@@ -33,6 +34,8 @@ extern "C" int sr_scalar_host_vote_chunk(int32_t index_gap, int32_t padding, uin
 		const uint8_t *r0 = text + off[f * mates], *r1 = is_paired ? text + off[f * mates + 1] : nullptr;
 		int l0 = len[f * mates], l1 = is_paired ? len[f * mates + 1] : 0;
 		sr::scalar_vote_fragment(ix, cfg, r0, l0, r1, l1, (sr::ResultWords *)(out_align + (size_t)f * mates * mb),
+		                         out_junc ? (sr::JuncWords *)(out_junc + (size_t)f * mates * mb) : nullptr,
+		                         out_big_margin ? out_big_margin + (size_t)f * mates * sr::kBigMarginU16 : nullptr,
 		                         out_verify ? out_verify + (size_t)f * mates * mb : nullptr, sc);
 	}
 	free(sc);

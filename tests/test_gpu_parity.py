@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, REF_DIR, ROOT, describe_mismatch, have_ref, load_case
+from conftest import GOLDEN, REF_DIR, ROOT, describe_mismatch, have_ref, junc_tables_equal, load_case, load_case_junc
 from subread_b200 import MAPPING_RESULT, VoteParams, load_fastq, used_slots_equal
 
 pytestmark = pytest.mark.gpu
@@ -149,8 +149,9 @@ def test_errors_are_loud(mapper, golden_cases, golden_index_dir):
     with pytest.raises(SubreadCudaError, match="multi_best_reads"):
         mapper.vote_chunk(chunk, bad)
     sub = VoteParams.defaults(False, is_subjunc=True)
-    with pytest.raises(SubreadCudaError, match="do_breakpoint_detection"):
-        mapper.vote_chunk(chunk, sub)
+    sub.max_insertion_at_junctions = 3
+    with pytest.raises(SubreadCudaError, match="max_insertion_at_junctions"):
+        mapper.vote_chunk(chunk, sub, junc_state={})
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference binaries) not built")
@@ -225,3 +226,29 @@ def test_index_builder_output_loads_and_maps(mapper, oracle_mod, tmp_path):
     mapper.index_load(prefix, 0)
     got, _ = mapper.vote_chunk(chunk, params)
     assert got.tobytes() == exp.tobytes()
+
+
+@pytest.mark.parametrize("name", ["sj_se", "sj_pe"])
+def test_subjunc_junction_voting(name, mapper, golden_cases, golden_index_dir, oracle_mod):
+    """K_junc: subjunc's minor-half / donor-site search and big-margin records, through the
+    C ABI, against the reference's golden tables and the oracle; then a second pass (read-modify-write)."""
+    case = next(c for c in golden_cases if c["name"] == name)
+    prefix, chunk, params, exp = load_case(case, golden_index_dir)
+    exp_junc, exp_bm = load_case_junc(case, chunk, params)
+    mapper.index_load(prefix, 0)
+    js = {}
+    got, _ = mapper.vote_chunk(chunk, params, junc_state=js)
+    ok, bad = used_slots_equal(got, exp)
+    assert ok, describe_mismatch(got, exp, bad)
+    assert junc_tables_equal(got, js["junc"], js["big_margin"], exp_junc, exp_bm)
+    idx = oracle_mod.OracleIndex(prefix)
+    jo = {}
+    ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, junc_state=jo)
+    assert got.tobytes() == ora.tobytes()
+    assert js["junc"].tobytes() == jo["junc"].tobytes()
+    assert (js["big_margin"] == jo["big_margin"]).all()
+    got2, _ = mapper.vote_chunk(chunk, params, out_align=got.copy().reshape(-1), junc_state=js)
+    ora2, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora.copy(), junc_state=jo)
+    assert got2.tobytes() == ora2.tobytes()
+    assert js["junc"].tobytes() == jo["junc"].tobytes()
+    assert (js["big_margin"] == jo["big_margin"]).all()

@@ -2,7 +2,7 @@
 (tests/golden/make_golden.py): pins the checker itself.  CPU only."""
 import pytest
 
-from conftest import describe_mismatch, load_case
+from conftest import describe_mismatch, junc_tables_equal, load_case, load_case_junc
 from subread_b200 import used_slots_equal
 
 CASE_NAMES = ["se_gapped", "pe_gapped", "se_full", "pe_full", "se_I16", "pe_n14_ff"]
@@ -47,3 +47,19 @@ def test_oracle_second_pass_keeps_the_best_location(golden_cases, golden_index_d
         before = {int(p) for p, v in zip(once[f, 0]["selected_position"], once[f, 0]["selected_votes"]) if v > 0}
         after = {int(p) for p, v in zip(twice[f, 0]["selected_position"], twice[f, 0]["selected_votes"]) if v > 0}
         assert after <= before
+
+
+@pytest.mark.parametrize("name", ["sj_se", "sj_pe"])
+def test_oracle_subjunc_matches_reference(name, golden_cases, golden_index_dir, oracle_mod):
+    """subjunc (do_breakpoint_detection): alignment table, minor-half / donor results and big-margin records
+    against the reference's ref_dump_subjunc on reads spanning planted GT..AG / CT..AC introns."""
+    case = next(c for c in golden_cases if c["name"] == name)
+    prefix, chunk, params, exp = load_case(case, golden_index_dir)
+    exp_junc, exp_bm = load_case_junc(case, chunk, params)
+    assert (exp_junc["minor_votes"] > 0).sum() > 20
+    idx = oracle_mod.OracleIndex(prefix)
+    js = {}
+    got, _, _ = oracle_mod.vote_chunk(idx, params, chunk, junc_state=js)
+    ok, bad = used_slots_equal(got, exp)
+    assert ok, describe_mismatch(got, exp, bad)
+    assert junc_tables_equal(got, js["junc"], js["big_margin"], exp_junc, exp_bm)

@@ -128,6 +128,42 @@ def write_reads(genome_fa, prefix, n, rlen, seed, paired, err, indel_p, mixed_le
         f2.close()
 
 
+def write_spliced(genome_fa, out_genome_fa, prefix, n, rlen, seed, paired, err=0.005, mixed_len=False):
+    """RNA-seq-like input for subjunc: plants introns (GT..AG on the forward strand, CT..AC for genes on
+    the reverse strand) into the genome, writes the edited genome, and samples reads from the spliced
+    transcripts (introns removed), so that many reads span an exon-exon junction."""
+    names, seqs = read_fasta(genome_fa)
+    rng = np.random.default_rng(seed)
+    seqs = [s.copy() for s in seqs]
+    transcripts = []
+    for s in seqs:
+        pos, keep = 2000, []
+        last = 0
+        while pos + 4000 < s.shape[0]:
+            ilen = int(rng.integers(80, 3000))
+            if rng.random() < 0.5:
+                s[pos:pos + 2] = np.frombuffer(b"GT", np.uint8); s[pos + ilen - 2:pos + ilen] = np.frombuffer(b"AG", np.uint8)
+            else:
+                s[pos:pos + 2] = np.frombuffer(b"CT", np.uint8); s[pos + ilen - 2:pos + ilen] = np.frombuffer(b"AC", np.uint8)
+            keep.append((last, pos))
+            last = pos + ilen
+            pos = last + int(rng.integers(120, 1500))
+        keep.append((last, s.shape[0]))
+        transcripts.append(np.concatenate([s[a:b] for a, b in keep]))
+    with open(out_genome_fa, "wb") as fh:
+        for nm, s in zip(names, seqs):
+            fh.write(b">" + nm.encode() + b"\n")
+            for i in range(0, s.shape[0], 70):
+                fh.write(s[i:i + 70].tobytes() + b"\n")
+    tmp_fa = out_genome_fa + ".transcripts.fa"
+    with open(tmp_fa, "wb") as fh:
+        for nm, s in zip(names, transcripts):
+            fh.write(b">" + nm.encode() + b"\n")
+            for i in range(0, s.shape[0], 70):
+                fh.write(s[i:i + 70].tobytes() + b"\n")
+    write_reads(tmp_fa, prefix, n, rlen, seed + 1, paired, err, 0.0, mixed_len, 0.0)
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
