@@ -3,7 +3,7 @@
 // Data layout in HBM (one index block, resident for the life of the handle):
 //   bucket_start u32[buckets+1] | keys i16[items] | vals u32[items] | genome 2-bit (u32 words) |
 //   chr_offsets u32[chromosomes]
-// Per chunk batch (double-buffered on two streams so that H2D, kernels and D2H overlap):
+// Per chunk batch (kSets buffer sets on as many streams so that H2D, kernels and D2H overlap):
 //   text u8[...] | off u64[reads] | len u16[reads] | out 68 B x reads x 3 | verify u16 x reads x 3 |
 //   overflow queue u32[frags] + counter
 #include "../../include/subread_cuda.h"
@@ -196,6 +196,10 @@ struct BatchSet {  // one of two buffer sets; used by one stream
 
 }  // namespace
 
+// Buffer sets / streams a chunk's batches rotate over: each stream runs H2D -> kernels -> D2H in order, so
+// with k sets up to k batches are in different stages at once (PCIe up, SMs, PCIe down all busy).
+constexpr int kSets = 4;
+
 struct srcuda_handle {
 	int device = -1;
 	int sm_count = 0;
@@ -208,9 +212,9 @@ struct srcuda_handle {
 	void *d_records = nullptr, *d_bloom = nullptr;
 	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both (SRCUDA_ACCEL)
 	size_t genome_words = 0;
-	BatchSet set[2];
+	BatchSet set[kSets];
 	std::vector<cudaEvent_t> events;
-	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_join[kSets] = {};
 	srcuda_timing timing{};
 	bool force_slow = false;
 	int64_t batch_frags = 1 << 20;
@@ -407,7 +411,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 
 int init_sets(srcuda_handle *h)
 {
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < kSets; i++) {
 		BatchSet &b = h->set[i];
 		if (b.stream) continue;
 		CU(h, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
@@ -416,6 +420,7 @@ int init_sets(srcuda_handle *h)
 	if (!h->ev_begin) {
 		CU(h, cudaEventCreate(&h->ev_begin));
 		CU(h, cudaEventCreate(&h->ev_end));
+		for (int i = 0; i < kSets; i++) CU(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
 	}
 	return 0;
 }
@@ -463,7 +468,7 @@ void srcuda_close(srcuda_handle *h)
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
 	free_index(h);
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < kSets; i++) {
 		BatchSet &b = h->set[i];
 		for (DeviceBuf *d : {&b.text, &b.off, &b.len, &b.out, &b.verify, &b.queue, &b.junc, &b.big_margin}) cudaFree(d->p);
 		cudaFree(b.counters);
@@ -474,6 +479,7 @@ void srcuda_close(srcuda_handle *h)
 	for (cudaEvent_t e : h->events) cudaEventDestroy(e);
 	if (h->ev_begin) cudaEventDestroy(h->ev_begin);
 	if (h->ev_end) cudaEventDestroy(h->ev_end);
+	for (int i = 0; i < kSets; i++) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
 	cudaFree(h->d_sink);
 	delete h;
 }
@@ -738,18 +744,18 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 	const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->batch_frags, 0x7fffffffLL));
 	const int64_t n_batches = (n_frags + batch - 1) / batch;
 	while ((int64_t)h->events.size() < 3 * n_batches) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < kSets; i++) {
 		BatchSet &b = h->set[i];
-		size_t need = sizeof(uint32_t) * 2 * (size_t)((n_batches + 1) / 2 + 1);
+		size_t need = sizeof(uint32_t) * 2 * (size_t)(n_batches / kSets + 2);
 		if (b.h_counters) { cudaFreeHost(b.h_counters); b.h_counters = nullptr; }
 		CU(h, cudaHostAlloc((void **)&b.h_counters, need, cudaHostAllocDefault));
 		memset(b.h_counters, 0, need);
 	}
 
 	CU(h, cudaEventRecord(h->ev_begin, h->set[0].stream));
-	CU(h, cudaStreamWaitEvent(h->set[1].stream, h->ev_begin, 0));
+	for (int i = 1; i < kSets; i++) CU(h, cudaStreamWaitEvent(h->set[i].stream, h->ev_begin, 0));
 	for (int64_t bi = 0; bi < n_batches; bi++) {
-		BatchSet &bs = h->set[bi & 1];
+		BatchSet &bs = h->set[bi % kSets];
 		cudaStream_t s = bs.stream;
 		const int64_t f0 = bi * batch, f1 = std::min(n_frags, f0 + batch), nf = f1 - f0;
 		const int64_t r0 = f0 * mates, nr = nf * mates;
@@ -807,13 +813,14 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 			CU(h, cudaMemcpyAsync(out_big_margin + (size_t)r0 * sr::kBigMarginU16, bs.big_margin.p, bm_bytes, cudaMemcpyDeviceToHost, s));
 			h->timing.d2h_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 		}
-		CU(h, cudaMemcpyAsync(bs.h_counters + 2 * (bi / 2), bs.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CU(h, cudaMemcpyAsync(bs.h_counters + 2 * (bi / kSets), bs.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	}
-	CU(h, cudaEventRecord(h->ev_end, h->set[1].stream));
-	CU(h, cudaStreamWaitEvent(h->set[0].stream, h->ev_end, 0));
+	for (int i = 1; i < kSets; i++) {  // join every stream into stream 0, then stamp the end there
+		CU(h, cudaEventRecord(h->ev_join[i], h->set[i].stream));
+		CU(h, cudaStreamWaitEvent(h->set[0].stream, h->ev_join[i], 0));
+	}
 	CU(h, cudaEventRecord(h->ev_end, h->set[0].stream));
-	CU(h, cudaStreamSynchronize(h->set[0].stream));
-	CU(h, cudaStreamSynchronize(h->set[1].stream));
+	for (int i = 0; i < kSets; i++) CU(h, cudaStreamSynchronize(h->set[i].stream));
 
 	float ms = 0;
 	CU(h, cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end));
@@ -824,7 +831,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		h->timing.ms_kernel_vote += ms;
 		CU(h, cudaEventElapsedTime(&ms, h->events[3 * bi + 1], h->events[3 * bi + 2]));
 		h->timing.ms_kernel_overflow += ms;
-		const uint32_t *c = h->set[bi & 1].h_counters + 2 * (bi / 2);
+		const uint32_t *c = h->set[bi % kSets].h_counters + 2 * (bi / kSets);
 		h->timing.n_overflow += (h->force_slow || cfg.do_junctions) ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
 		bad += c[1];
 	}
