@@ -115,13 +115,16 @@ typedef struct {
  * library's own stream). */
 typedef struct {
 	float ms_total;          /* first H2D to last D2H (or kernels only for the device variant) */
-	float ms_kernel_vote;    /* fused pack+lookup+vote+topK(+verify) kernel, summed over batches */
+	float ms_kernel_vote;    /* k_map_simple + k_map_warp (pack+lookup+vote+topK(+verify)), summed over batches */
 	float ms_kernel_overflow;/* exact slow path for fragments whose vote table left shared memory */
 	uint64_t n_overflow;     /* fragments that took the slow path */
 	uint64_t h2d_bytes;
 	uint64_t d2h_bytes;
 	uint32_t n_launches;     /* kernels launched */
 	uint32_t n_batches;
+	float ms_kernel_simple;  /* part of ms_kernel_vote spent in the one-thread-per-fragment tier (k_map_simple) */
+	uint32_t _pad;
+	uint64_t n_simple_punted;/* fragments that tier handed on to the warp kernel */
 } srcuda_timing;
 
 /* ---- life cycle ------------------------------------------------------------------------ */

@@ -10,6 +10,7 @@
 #include "sr_config.h"
 #include "sr_index.h"
 #include "sr_scalar.cuh"
+#include "sr_simple.cuh"
 #include "sr_warp.cuh"
 
 #include <cuda_runtime.h>
@@ -46,11 +47,13 @@ struct ChunkArgs {
 	uint32_t *queue_count;
 	uint32_t *bad_reads;       // counter of reads whose (off,len) fall outside the text buffer
 	int out_zero;              // the bigtable slice is known to be all zero: do not read it
+	const uint32_t *in_list;   // fragments the warp kernel has to map (punted by k_map_simple), null = all
+	const uint32_t *in_count;
 	JuncWords *junc;           // subjunc only: [frag][mate][multi_best] subjunc_result_t, else null
 	uint16_t *big_margin;      // subjunc only: [frag][mate][27]
 };
 
-template <int MATES, int GAP>
+template <int MATES, int GAP, bool VERIFY>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, SR_MIN_BLOCKS)
 k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_words, int warp_bytes)
 {
@@ -64,7 +67,9 @@ k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_wor
 	uint32_t *area = reinterpret_cast<uint32_t *>(mine + ((sizeof(WarpShared<MATES>) + 15) & ~size_t(15)));
 	const int mb = cfg.multi_best_reads;
 
-	for (int64_t f = (int64_t)blockIdx.x * kWarpsPerBlock + warp; f < a.n_frags; f += (int64_t)gridDim.x * kWarpsPerBlock) {
+	const int64_t n_todo = a.in_list ? (int64_t)*a.in_count : a.n_frags;
+	for (int64_t it = (int64_t)blockIdx.x * kWarpsPerBlock + warp; it < n_todo; it += (int64_t)gridDim.x * kWarpsPerBlock) {
+		const int64_t f = a.in_list ? (int64_t)a.in_list[it] : it;
 		const int64_t r0 = f * MATES;
 		const uint64_t o0 = a.off[r0] - a.text_origin;
 		const int l0 = a.len[r0];
@@ -80,7 +85,7 @@ k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_wor
 			if (lane == 0) atomicAdd(a.bad_reads, 1u);
 			continue;
 		}
-		bool ok = map_fragment<MATES, GAP>(ix, cfg, ws, area, n_words, lut, a.text + o0, l0, a.text + o1, l1,
+		bool ok = map_fragment<MATES, GAP, VERIFY>(ix, cfg, ws, area, n_words, lut, a.text + o0, l0, a.text + o1, l1,
 		                                   a.out + (size_t)f * MATES * mb, a.out_zero != 0,
 		                                   a.verify ? a.verify + (size_t)f * MATES * mb : nullptr, lane);
 		if (!ok && lane == 0) a.queue[atomicAdd(a.queue_count, 1u)] = (uint32_t)f;
@@ -188,8 +193,8 @@ struct DeviceBuf {
 
 struct BatchSet {  // one of two buffer sets; used by one stream
 	cudaStream_t stream = nullptr;
-	DeviceBuf text, off, len, out, verify, queue, junc, big_margin;
-	uint32_t *counters = nullptr;       // device: [0] queue_count, [1] bad_reads
+	DeviceBuf text, off, len, out, verify, queue, queue0, junc, big_margin;
+	uint32_t *counters = nullptr;       // device: [0] queue_count (-> scalar), [1] bad_reads, [2] queue0_count (simple -> warp)
 	uint32_t *h_counters = nullptr;     // pinned host mirror, 2 per batch slot
 	sr::ScalarScratch *scratch = nullptr;
 };
@@ -217,6 +222,7 @@ struct srcuda_handle {
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_join[kSets] = {};
 	srcuda_timing timing{};
 	bool force_slow = false;
+	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
 	int64_t batch_frags = 1 << 20;
 	uint32_t *d_sink = nullptr;
 };
@@ -346,7 +352,7 @@ struct LaunchPlan {
 	int n_words, warp_bytes, smem_bytes, grid;
 };
 
-template <int MATES, int GAP>
+template <int MATES, int GAP, bool VERIFY>
 int plan_warp_launch(srcuda_handle *h, int max_len, LaunchPlan *p)
 {
 	p->n_words = (max_len + 15) / 16 + 1;
@@ -354,25 +360,31 @@ int plan_warp_launch(srcuda_handle *h, int max_len, LaunchPlan *p)
 	p->warp_bytes = (int)((wb + 15) & ~size_t(15));
 	p->smem_bytes = 256 + p->warp_bytes * sr::kWarpsPerBlock;
 	if (p->smem_bytes > 227 * 1024) return fail(h, SRCUDA_ERR_UNSUPPORTED, "shared memory plan %d B exceeds 227 KB", p->smem_bytes);
-	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES, GAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES, GAP, VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
 	int per_sm = 0;
-	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES, GAP>, sr::kWarpsPerBlock * 32, p->smem_bytes));
+	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES, GAP, VERIFY>, sr::kWarpsPerBlock * 32, p->smem_bytes));
 	if (per_sm < 1) return fail(h, SRCUDA_ERR_CUDA, "warp kernel does not fit on an SM");
 	p->grid = h->sm_count * per_sm;  // persistent grid: a whole number of resident waves
+	return 0;
+}
+
+template <int MATES, int GAP, bool VERIFY>
+int launch_warp_v(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len)
+{
+	LaunchPlan p;
+	int rc = plan_warp_launch<MATES, GAP, VERIFY>(h, max_len, &p);
+	if (rc) return rc;
+	int64_t blocks_needed = (a.n_frags + sr::kWarpsPerBlock - 1) / sr::kWarpsPerBlock;
+	int grid = (int)std::min<int64_t>(p.grid, std::max<int64_t>(blocks_needed, 1));
+	sr::k_map_warp<MATES, GAP, VERIFY><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.warp_bytes);
+	CU(h, cudaGetLastError());
 	return 0;
 }
 
 template <int MATES, int GAP>
 int launch_warp(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len)
 {
-	LaunchPlan p;
-	int rc = plan_warp_launch<MATES, GAP>(h, max_len, &p);
-	if (rc) return rc;
-	int64_t blocks_needed = (a.n_frags + sr::kWarpsPerBlock - 1) / sr::kWarpsPerBlock;
-	int grid = (int)std::min<int64_t>(p.grid, std::max<int64_t>(blocks_needed, 1));
-	sr::k_map_warp<MATES, GAP><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.warp_bytes);
-	CU(h, cudaGetLastError());
-	return 0;
+	return a.verify ? launch_warp_v<MATES, GAP, true>(h, s, cfg, a, max_len) : launch_warp_v<MATES, GAP, false>(h, s, cfg, a, max_len);
 }
 
 template <int MATES>
@@ -396,8 +408,27 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	// subjunc's minor-half / donor search (K_junc) is built on the exact scalar path only so far
 	const bool scalar_only = h->force_slow || cfg.do_junctions;
 	if (ev) CU(h, cudaEventRecord(ev[0], s));
+	sr::ChunkArgs aw = a;
+	// tier 0: one thread per single-end fragment of a chunk whose bigtable slice is zero (sr_simple.cuh)
+	const bool tier0 = !scalar_only && h->use_simple_tier && !cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	                   cfg.min_second <= cfg.min_first && cfg.top_scores >= 2 && cfg.max_vote_simples >= 2;
+	if (tier0) {
+		const int threads = 128;
+		const int64_t blocks = (a.n_frags + threads - 1) / threads;
+		uint32_t *q0 = (uint32_t *)bs.queue0.p;
+		switch (h->ix.index_gap) {
+		case 1: sr::k_map_simple<1><<<(unsigned)blocks, threads, 0, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, a.n_frags, a.out, q0, bs.counters + 2, a.bad_reads); break;
+		case 2: sr::k_map_simple<2><<<(unsigned)blocks, threads, 0, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, a.n_frags, a.out, q0, bs.counters + 2, a.bad_reads); break;
+		default: sr::k_map_simple<3><<<(unsigned)blocks, threads, 0, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, a.n_frags, a.out, q0, bs.counters + 2, a.bad_reads); break;
+		}
+		CU(h, cudaGetLastError());
+		h->timing.n_launches++;
+		aw.in_list = q0;
+		aw.in_count = bs.counters + 2;
+	}
+	if (ev) CU(h, cudaEventRecord(ev[3], s));
 	if (!scalar_only) {
-		int rc = cfg.is_paired ? launch_warp_gap<2>(h, s, cfg, a, max_len) : launch_warp_gap<1>(h, s, cfg, a, max_len);
+		int rc = cfg.is_paired ? launch_warp_gap<2>(h, s, cfg, aw, max_len) : launch_warp_gap<1>(h, s, cfg, aw, max_len);
 		if (rc) return rc;
 		h->timing.n_launches++;
 	}
@@ -415,7 +446,7 @@ int init_sets(srcuda_handle *h)
 		BatchSet &b = h->set[i];
 		if (b.stream) continue;
 		CU(h, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
-		CU(h, cudaMalloc((void **)&b.counters, 2 * sizeof(uint32_t)));
+		CU(h, cudaMalloc((void **)&b.counters, 4 * sizeof(uint32_t)));
 	}
 	if (!h->ev_begin) {
 		CU(h, cudaEventCreate(&h->ev_begin));
@@ -454,6 +485,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SRCUDA_ERR_CUDA, "cudaSetDevice(%d) failed", device); }
 	const char *bf = getenv("SRCUDA_BATCH_FRAGS");
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
+	const char *st = getenv("SRCUDA_SIMPLE_TIER");
+	if (st && st[0] == '0') h->use_simple_tier = false;
 	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both; default auto
 	if (ac && ac[0] >= '0' && ac[0] <= '3') h->accel_mode = ac[0] - '0';
 	const char *fg = getenv("SRCUDA_L2_FETCH");  // L2 fetch granularity hint in bytes: 32, 64 or 128
@@ -470,7 +503,7 @@ void srcuda_close(srcuda_handle *h)
 	free_index(h);
 	for (int i = 0; i < kSets; i++) {
 		BatchSet &b = h->set[i];
-		for (DeviceBuf *d : {&b.text, &b.off, &b.len, &b.out, &b.verify, &b.queue, &b.junc, &b.big_margin}) cudaFree(d->p);
+		for (DeviceBuf *d : {&b.text, &b.off, &b.len, &b.out, &b.verify, &b.queue, &b.queue0, &b.junc, &b.big_margin}) cudaFree(d->p);
 		cudaFree(b.counters);
 		cudaFree(b.scratch);
 		if (b.h_counters) cudaFreeHost(b.h_counters);
@@ -692,26 +725,30 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	BatchSet &bs = h->set[0];
 	rc = ensure(h, bs.queue, sizeof(uint32_t) * (size_t)n_frags);
 	if (rc) return rc;
-	if (h->events.size() < 3) {
-		while (h->events.size() < 3) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
-	}
-	CU(h, cudaMemsetAsync(bs.counters, 0, 2 * sizeof(uint32_t), bs.stream));
+	rc = ensure(h, bs.queue0, sizeof(uint32_t) * (size_t)n_frags);
+	if (rc) return rc;
+	while (h->events.size() < 4) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
+	CU(h, cudaMemsetAsync(bs.counters, 0, 4 * sizeof(uint32_t), bs.stream));
 	sr::ChunkArgs a;
 	a.text = (const uint8_t *)d_text; a.text_origin = 0; a.text_bytes = ~0ull >> 1;
 	a.off = d_off; a.len = d_len; a.n_frags = n_frags;
 	a.out = (sr::ResultWords *)d_out_align; a.verify = d_out_verify;
 	a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
 	a.out_zero = out_align_is_zero ? 1 : 0;
+	a.in_list = nullptr; a.in_count = nullptr;
 	a.junc = cfg.do_junctions ? (sr::JuncWords *)d_out_junc : nullptr;
 	a.big_margin = cfg.do_junctions ? d_out_big_margin : nullptr;
 	rc = launch_vote(h, bs.stream, cfg, a, max_read_len, bs, h->events.data());
 	if (rc) return rc;
-	uint32_t counters[2] = {0, 0};
+	uint32_t counters[4] = {0, 0, 0, 0};
 	CU(h, cudaMemcpyAsync(counters, bs.counters, sizeof(counters), cudaMemcpyDeviceToHost, bs.stream));
 	CU(h, cudaStreamSynchronize(bs.stream));
 	float ms = 0;
 	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[1]));
 	h->timing.ms_kernel_vote = ms;
+	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[3]));
+	h->timing.ms_kernel_simple = ms;
+	h->timing.n_simple_punted = counters[2];
 	CU(h, cudaEventElapsedTime(&ms, h->events[1], h->events[2]));
 	h->timing.ms_kernel_overflow = ms;
 	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[2]));
@@ -743,10 +780,10 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 	const int mates = 1 + (is_paired ? 1 : 0), mb = cfg.multi_best_reads;
 	const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->batch_frags, 0x7fffffffLL));
 	const int64_t n_batches = (n_frags + batch - 1) / batch;
-	while ((int64_t)h->events.size() < 3 * n_batches) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
+	while ((int64_t)h->events.size() < 4 * n_batches) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
 	for (int i = 0; i < kSets; i++) {
 		BatchSet &b = h->set[i];
-		size_t need = sizeof(uint32_t) * 2 * (size_t)(n_batches / kSets + 2);
+		size_t need = sizeof(uint32_t) * 4 * (size_t)(n_batches / kSets + 2);
 		if (b.h_counters) { cudaFreeHost(b.h_counters); b.h_counters = nullptr; }
 		CU(h, cudaHostAlloc((void **)&b.h_counters, need, cudaHostAllocDefault));
 		memset(b.h_counters, 0, need);
@@ -772,6 +809,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		if ((rc = ensure(h, bs.len, sizeof(uint16_t) * (size_t)nr))) return rc;
 		if ((rc = ensure(h, bs.out, sizeof(srcuda_mapping_result) * n_slots))) return rc;
 		if ((rc = ensure(h, bs.queue, sizeof(uint32_t) * (size_t)nf))) return rc;
+		if ((rc = ensure(h, bs.queue0, sizeof(uint32_t) * (size_t)nf))) return rc;
 		if (out_verify && (rc = ensure(h, bs.verify, sizeof(uint16_t) * n_slots))) return rc;
 		const size_t bm_bytes = sizeof(uint16_t) * sr::kBigMarginU16 * (size_t)nr;
 		if (cfg.do_junctions) {
@@ -792,16 +830,17 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 				h->timing.h2d_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 			}
 		}
-		CU(h, cudaMemsetAsync(bs.counters, 0, 2 * sizeof(uint32_t), s));
+		CU(h, cudaMemsetAsync(bs.counters, 0, 4 * sizeof(uint32_t), s));
 		sr::ChunkArgs a;
 		a.text = (const uint8_t *)bs.text.p; a.text_origin = origin; a.text_bytes = text_bytes;
 		a.off = (const uint64_t *)bs.off.p; a.len = (const uint16_t *)bs.len.p; a.n_frags = nf;
 		a.out = (sr::ResultWords *)bs.out.p; a.verify = out_verify ? (uint16_t *)bs.verify.p : nullptr;
 		a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;
 		a.out_zero = out_align_is_zero ? 1 : 0;
+		a.in_list = nullptr; a.in_count = nullptr;
 		a.junc = cfg.do_junctions ? (sr::JuncWords *)bs.junc.p : nullptr;
 		a.big_margin = cfg.do_junctions ? (uint16_t *)bs.big_margin.p : nullptr;
-		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[3 * bi]))) return rc;
+		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[4 * bi]))) return rc;
 		CU(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
 		h->timing.d2h_bytes += sizeof(srcuda_mapping_result) * n_slots;
 		if (out_verify) {
@@ -813,7 +852,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 			CU(h, cudaMemcpyAsync(out_big_margin + (size_t)r0 * sr::kBigMarginU16, bs.big_margin.p, bm_bytes, cudaMemcpyDeviceToHost, s));
 			h->timing.d2h_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 		}
-		CU(h, cudaMemcpyAsync(bs.h_counters + 2 * (bi / kSets), bs.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CU(h, cudaMemcpyAsync(bs.h_counters + 4 * (bi / kSets), bs.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	}
 	for (int i = 1; i < kSets; i++) {  // join every stream into stream 0, then stamp the end there
 		CU(h, cudaEventRecord(h->ev_join[i], h->set[i].stream));
@@ -827,11 +866,14 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 	h->timing.ms_total = ms;
 	uint64_t bad = 0;
 	for (int64_t bi = 0; bi < n_batches; bi++) {
-		CU(h, cudaEventElapsedTime(&ms, h->events[3 * bi], h->events[3 * bi + 1]));
+		CU(h, cudaEventElapsedTime(&ms, h->events[4 * bi], h->events[4 * bi + 1]));
 		h->timing.ms_kernel_vote += ms;
-		CU(h, cudaEventElapsedTime(&ms, h->events[3 * bi + 1], h->events[3 * bi + 2]));
+		CU(h, cudaEventElapsedTime(&ms, h->events[4 * bi], h->events[4 * bi + 3]));
+		h->timing.ms_kernel_simple += ms;
+		CU(h, cudaEventElapsedTime(&ms, h->events[4 * bi + 1], h->events[4 * bi + 2]));
 		h->timing.ms_kernel_overflow += ms;
-		const uint32_t *c = h->set[bi % kSets].h_counters + 2 * (bi / kSets);
+		const uint32_t *c = h->set[bi % kSets].h_counters + 4 * (bi / kSets);
+		h->timing.n_simple_punted += c[2];
 		h->timing.n_overflow += (h->force_slow || cfg.do_junctions) ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
 		bad += c[1];
 	}

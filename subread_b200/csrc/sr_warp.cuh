@@ -383,14 +383,12 @@ __device__ __forceinline__ bool vote_batch_uniform(WarpTable &T, SlotRegs &S, ui
 // Returns applied_subreads.  Leaves the table in T (pos/row/j flushed from registers).
 template <int GAP>
 __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *packed /* this pass */, int L,
-                                         WarpTable &T, uint32_t *shift_locs, int lane, int &nslots_out, int &max_vote_out,
-                                         bool &overflow)
+                                         int applied, int step, WarpTable &T, uint32_t *shift_locs, int lane, int &nslots_out,
+                                         int &max_vote_out, bool &overflow)
 {
 	nslots_out = 0;
 	max_vote_out = 0;
 	if (L < 16) return 0;  // core.c:3116 (the reference leaves a stale table here; we define it empty)
-	int step;
-	const int applied = subread_schedule(L, GAP, cfg.total_subreads, &step);
 	const int n_lk = applied * GAP;
 	HitEnv E;
 	E.tol = cfg.indel_tolerance;
@@ -406,6 +404,7 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 	st.shift_n = 0;
 	st.overflow = false;
 	SlotRegs S;
+#pragma unroll 1
 	for (int round = 0; round < 2; round++) {  // core.c:3153-3186
 		E.round = round;
 		st.nslots = 0; st.max_vote = 0;
@@ -574,6 +573,7 @@ __device__ __forceinline__ void emit_candidate(WarpShared<MATES> &ws, int m, int
 {
 	const uint32_t pos = ws.cand_pos[m][s];
 	bool exist = false;
+#pragma unroll 1
 	for (int k = 0; k < cursor; k++)
 		if (ws.tmp[m][k].w[0] == pos) exist = true;
 	if (exist) return;
@@ -718,7 +718,9 @@ __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &
 				}
 	}
 	__syncwarp();
+#pragma unroll 1
 	for (int m = 0; m < MATES; m++)  // :2505-2527
+#pragma unroll 1
 		for (int k = 0; k < mb; k++) {
 			if (k < cursor[m]) {
 				if (lane < kResultWords) ws.res[m][k].w[lane] = ws.tmp[m][k].w[lane];
@@ -755,7 +757,7 @@ __device__ __forceinline__ int match_packed(const DevIndex &ix, const uint32_t *
 // ---- one fragment ------------------------------------------------------------------------------
 // area: MATES * packed_words_per_mate(n_words) words of per-warp shared memory.
 // Returns false when the fragment overflowed the shared-memory table (nothing was written).
-template <int MATES, int GAP>
+template <int MATES, int GAP, bool VERIFY>
 __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, uint32_t *area,
                                              int n_words, const uint8_t *lut, const uint8_t *raw0, int len0, const uint8_t *raw1,
                                              int len1, ResultWords *out /* global, this fragment */, bool out_is_zero,
@@ -771,22 +773,30 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 	if (mb == kMaxBest) {
 		for (int w = lane; w < MATES * kMaxBest * kResultWords; w += 32) res_flat[w] = out_is_zero ? 0u : (&out[0].w[0])[w];
 	} else {
-		for (int w = lane; w < MATES * mb * kResultWords; w += 32) {
-			int s = w / kResultWords, k = w - s * kResultWords;
-			ws.res[s / mb][s % mb].w[k] = out_is_zero ? 0u : out[s].w[k];
-		}
+#pragma unroll 1
+		for (int m = 0; m < MATES; m++)
+#pragma unroll 1
+			for (int k = 0; k < mb; k++)
+				if (lane < kResultWords) ws.res[m][k].w[lane] = out_is_zero ? 0u : out[m * mb + k].w[lane];
 	}
 	for (int m = 0; m < MATES; m++)
 		pack_read(raw[m], rlen[m], m == 0 ? cfg.first_reversed != 0 : cfg.second_reversed != 0, area + m * per_mate, n_words, lut, lane);
 
 	int all_subreads[2] = {0, 0};
 	bool overflow = false;
+	// the schedule depends on the read length only: computed once per mate, reused by both strand passes
+	int sched_step[2] = {0, 0}, sched_applied[2] = {0, 0};
+	for (int m = 0; m < MATES; m++)
+		if (rlen[m] >= 16) sched_applied[m] = subread_schedule(rlen[m], GAP, cfg.total_subreads, &sched_step[m]);
+#pragma unroll 1
 	for (int strand = 0; strand < 2; strand++) {
 		int nslots[2] = {0, 0}, max_vote[2] = {0, 0};
 		int applied = 0;
+#pragma unroll 1
 		for (int m = 0; m < MATES; m++) {
 			const uint32_t *pass = area + m * per_mate + n_words + 2 + strand * n_words;
-			applied = vote_mate<GAP>(ix, cfg, pass, rlen[m], ws.tab[m], ws.shift_locs, lane, nslots[m], max_vote[m], overflow);
+			applied = vote_mate<GAP>(ix, cfg, pass, rlen[m], sched_applied[m], sched_step[m], ws.tab[m], ws.shift_locs, lane, nslots[m],
+			                         max_vote[m], overflow);
 			if (rlen[m] >= 16) all_subreads[m] = applied;
 			if (overflow) return false;
 		}
@@ -803,13 +813,16 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 	if (mb == kMaxBest) {
 		for (int w = lane; w < MATES * kMaxBest * kResultWords; w += 32) (&out[0].w[0])[w] = res_flat[w];
 	} else {
-		for (int w = lane; w < MATES * mb * kResultWords; w += 32) {
-			int s = w / kResultWords, k = w - s * kResultWords;
-			out[s].w[k] = ws.res[s / mb][s % mb].w[k];
-		}
-	}
-	if (verify) {
+#pragma unroll 1
 		for (int m = 0; m < MATES; m++)
+#pragma unroll 1
+			for (int k = 0; k < mb; k++)
+				if (lane < kResultWords) out[m * mb + k].w[lane] = ws.res[m][k].w[lane];
+	}
+	if (VERIFY && verify) {
+#pragma unroll 1
+		for (int m = 0; m < MATES; m++)
+#pragma unroll 1
 			for (int k = 0; k < mb; k++) {
 				const ResultWords &r = ws.res[m][k];
 				int v = 0xffff;
