@@ -319,7 +319,7 @@ def main():
         clocks.start()
     barrier()
     w0 = time.perf_counter()
-    ev_ms, kern_ms, over_ms, n_over, launches = 0.0, 0.0, 0.0, 0, 0
+    ev_ms, kern_ms, over_ms, n_over, launches, simple_ms, n_punted = 0.0, 0.0, 0.0, 0, 0, 0.0, 0
     for _ in range(args.steps):
         t = step_device()
         ev_ms += t.ms_total
@@ -327,6 +327,8 @@ def main():
         over_ms += t.ms_kernel_overflow
         n_over += t.n_overflow
         launches += t.n_launches
+        simple_ms += t.ms_kernel_simple
+        n_punted += t.n_simple_punted
     barrier()
     wall_dev = max_over_ranks(time.perf_counter() - w0)
     ev_ms = max_over_ranks(ev_ms)
@@ -421,7 +423,8 @@ def main():
                 pass
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                        "kernel": "k_map_warp<1>", "kernel_ms": kern_ms_step, "algorithmic_bytes_per_read": alg_bytes_per_read,
+                        "kernel": "k_map_simple<3> (tier 0, one thread per fragment) + k_map_warp<1,3> (punted fragments)",
+                        "kernel_ms": kern_ms_step, "tier0_ms": simple_ms / args.steps, "tier0_punted_fraction": n_punted / args.steps / R, "algorithmic_bytes_per_read": alg_bytes_per_read,
                         "gather_peak": gather_gbs, "frac_of_gather": (achieved / gather_gbs) if gather_gbs else None}
         out = {
             "metric": "reads/sec mapped", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

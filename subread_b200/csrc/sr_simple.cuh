@@ -1,23 +1,28 @@
 // sr_simple.cuh -- tier 0 of the voting step: one THREAD per single-end fragment.
 //
 // The warp kernel (sr_warp.cuh) spends most of its instructions on warp-uniform work; for the
-// common fragment that work is tiny.  A fragment is "simple" for a strand pass when every lookup
-// returns at most one position, all returned positions agree on one kv = position - offset, and the
-// hits come from distinct subreads.  Then gehash_go_X (sorted-hashtable.c:937-1123) builds exactly
-// one vote slot -- created by the first hit, every later hit taking the plain branch of :1041-1052 --
-// whose fields have a closed form:
+// common fragment that work is tiny.  A strand pass is "separable" when
+//   * every lookup returns at most one position,
+//   * the distinct values kv = position - offset that occur are pairwise more than the indel
+//     tolerance apart, and
+//   * the hits of one kv come from distinct subreads.
+// Then no hit is ever within tolerance of another slot, so gehash_go_X (sorted-hashtable.c:937-1123)
+// builds exactly one vote slot per distinct kv -- created by its first hit (or never, when kv lies
+// outside the block's border, :1074), every later hit taking the plain branch of :1041-1052 -- and
+// each slot has a closed form:
 //     votes = #hits, coverage = [offset(first hit), offset(last hit) + 16),
-//     indel recorder = {subread(first)+1, subread(last)+1, 0},
-// no shift-indel round (toli stays 0), or no slot at all when kv falls outside the block's border.
-// With an all-zero bigtable slice (first index block) process_voting_junction_PE_topK
-// (core-junction.c:2199-2530) then only ever merges at most one earlier slot (pass 0) with at
-// most one new slot (pass 1), which is enumerated below exactly as the reference orders it.
+//     indel recorder = {subread(first)+1, subread(last)+1, 0},    row = (kv/5)%30, j = creation rank in its row,
+// with no shift-indel round (toli stays 0).  Spurious single hits -- the usual companions of the true
+// cluster on a large index -- are just extra one-vote slots.  process_voting_junction_PE_topK
+// (core-junction.c:2199-2530) is then replayed on that small slot list and on the results of the first
+// strand pass (the chunk's bigtable slice must be all zero, i.e. the first index block).
 //
-// Everything else -- a lookup with several positions, disagreeing positions (indels, repeats),
-// two phases of one subread hitting, characters that are not A/C/G/T, reads longer than
-// kSimpleMaxLen -- is PUNTED untouched to the warp kernel through a queue, so the result of the
-// tiered path is the reference's for every input.  Paired-end and subjunc chunks, chunks merged
-// into a non-zero bigtable, and verification requests skip this tier altogether.
+// Everything else -- a lookup with several positions, kv values within tolerance of each other
+// (indels), two phases of one subread hitting one kv, more than kSimpleClusters distinct kv,
+// characters that are not A/C/G/T, reads longer than kSimpleMaxLen -- is PUNTED untouched to the
+// warp kernel through a queue, so the tiered path returns the reference's result for every input.
+// Paired-end and subjunc chunks, chunks merged into a non-zero bigtable, and verification requests
+// skip this tier altogether.
 #pragma once
 #include "sr_common.cuh"
 
@@ -25,26 +30,27 @@ namespace sr {
 
 constexpr int kSimpleMaxLen = 256;                       // longer reads go to the warp kernel
 constexpr int kSimpleWords = kSimpleMaxLen / 16 + 1;     // packed words per strand array
+constexpr int kSimpleClusters = 8;                       // distinct kv per strand pass
 
 #if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
 
-struct SimpleSlot {     // the one vote slot a simple strand pass can produce
-	uint32_t pos;
-	int votes;          // 0 = no slot
-	int cov_start, cov_end, first_sub_p1, last_sub_p1;
+struct SimpleClusters {     // the vote table of a separable pass, in creation order
+	int n;
+	uint32_t kv[kSimpleClusters];
+	int16_t votes[kSimpleClusters];        // 0: kv outside the border, no slot (its hits are dropped)
+	int16_t first_off[kSimpleClusters], last_off[kSimpleClusters];
+	uint8_t first_sub[kSimpleClusters], last_sub[kSimpleClusters];   // subread + 1
+	uint8_t row[kSimpleClusters], j[kSimpleClusters];
 };
 
-// mapping_result_t image of a simple slot (copy_vote_to_alignment_res core-junction.c:1058-1072).
-__device__ __forceinline__ void simple_slot_words(const SimpleSlot &s, int strand, int used_subreads, uint32_t *w)
-{
-#pragma unroll
-	for (int k = 0; k < kResultWords; k++) w[k] = 0;
-	w[0] = s.pos;
-	w[1] = strand ? (uint32_t)kCoreNegStrand : 0u;
-	w[2] = (uint32_t)(uint16_t)s.votes | ((uint32_t)(uint16_t)used_subreads << 16);
-	w[4] = (uint32_t)(uint16_t)s.first_sub_p1 | ((uint32_t)(uint16_t)s.last_sub_p1 << 16);
-	w[15] = (uint32_t)(uint16_t)s.cov_start | ((uint32_t)(uint16_t)s.cov_end << 16);
-}
+struct SimpleResult {       // one bigtable slot in compact form
+	uint8_t kind;           // 0 untouched (all zero), 1 a record, 2 only used_subreads_in_vote is set
+	uint8_t strand, first_sub, last_sub;
+	int16_t votes;          // selected_votes as stored (0 for a record that lost its place: stale bytes stay)
+	int16_t used;
+	uint32_t pos;
+	int16_t cov_start, cov_end;
+};
 
 // One bucket lookup by one thread: number of positions with key16 == k16 in bucket b, and the
 // position when there is exactly one.  Same accelerators as the warp kernel.
@@ -143,16 +149,16 @@ __device__ __forceinline__ bool simple_pack(const uint8_t *raw, int L, uint32_t 
 	return ok;
 }
 
-// One strand pass.  Returns false when the pass is not simple.
+// One strand pass.  Returns false when the pass is not separable.
 template <int GAP>
 __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *packed, int L, int applied, int step,
-                                            SimpleSlot *slot)
+                                            SimpleClusters &C)
 {
 	const uint32_t nb = ix.buckets_number;
 	const uint64_t magic = ix.buckets_magic;
-	const int n_lk = applied * GAP;
-	uint32_t kv0 = 0;
-	int nh = 0, first_off = 0, last_off = 0, first_sub = 0, last_sub = 0;
+	const int n_lk = applied * GAP, tol = cfg.indel_tolerance;
+	const uint32_t high = cfg.high_border - (uint32_t)L;
+	C.n = 0;
 	for (int l = 0; l < n_lk; l++) {
 		const int o = lookup_offset(l, GAP, step);
 		const int w = o >> 4, s = (o & 15) * 2;
@@ -164,28 +170,123 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 		if (h > 1) return false;
 		if (h == 1) {
 			const uint32_t kv = value - (uint32_t)o;
+			if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;   // u32 wrap-around of the probe rows
 			const int sub_p1 = l / GAP + 1;
-			if (nh == 0) { kv0 = kv; first_off = o; first_sub = sub_p1; }
-			else if (kv != kv0 || sub_p1 == last_sub) return false;
-			nh++;
-			last_off = o;
-			last_sub = sub_p1;
+			int found = -1;
+			for (int c = 0; c < C.n; c++) {
+				const int d = (int)(kv - C.kv[c]);
+				if (d == 0) found = c;
+				else if (d >= -tol && d <= tol) return false;          // within tolerance of another slot: an indel vote
+			}
+			if (found >= 0) {
+				if (C.votes[found] == 0) continue;                      // no slot for this kv: dropped again
+				if (sub_p1 == (int)C.last_sub[found]) return false;     // same subread twice: the reference opens a duplicate slot
+				C.votes[found]++;
+				C.last_off[found] = (int16_t)o;
+				C.last_sub[found] = (uint8_t)sub_p1;
+			} else {
+				if (C.n == kSimpleClusters) return false;
+				const int c = C.n++;
+				C.kv[c] = kv;
+				C.votes[c] = 0;
+				if (kv >= cfg.low_border && kv <= high) {               // :1074
+					const int row = (int)vote_row(kv);
+					int jj = 0;
+					for (int e = 0; e < c; e++) jj += (C.votes[e] > 0 && (int)C.row[e] == row) ? 1 : 0;
+					C.votes[c] = 1;
+					C.first_off[c] = C.last_off[c] = (int16_t)o;
+					C.first_sub[c] = C.last_sub[c] = (uint8_t)sub_p1;
+					C.row[c] = (uint8_t)row;
+					C.j[c] = (uint8_t)jj;
+				}
+			}
 		}
-	}
-	slot->votes = 0;
-	if (nh > 0 && kv0 >= cfg.low_border && kv0 <= cfg.high_border - (uint32_t)L) {  // :1074, otherwise every hit is dropped
-		slot->pos = kv0;
-		slot->votes = nh;
-		slot->cov_start = first_off;
-		slot->cov_end = last_off + 16;
-		slot->first_sub_p1 = first_sub;
-		slot->last_sub_p1 = last_sub;
 	}
 	return true;
 }
 
+__device__ __forceinline__ void simple_update_top(int top_scores, int *top, int v)   // update_top_three core-junction.c:908
+{
+	if (v > top[top_scores - 1])
+		for (int x = 0; x < top_scores; x++) {
+			if (v > top[x]) {
+				for (int y = top_scores - 1; y > x; y--) top[y] = top[y - 1];
+				top[x] = v;
+				break;
+			} else if (v == top[x]) break;
+		}
+}
+
+// process_voting_junction_PE_topK for one single-end pass over a separable table (core-junction.c:2199-2530,
+// the SE branch :2436-2495) and the hand-over logic of do_voting (core.c:3212-3226).
+__device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const SimpleClusters &C, int strand, int applied, SimpleResult *res)
+{
+	const int mb = cfg.multi_best_reads;
+	int max_vote = 0;
+	for (int c = 0; c < C.n; c++) max_vote = max(max_vote, (int)C.votes[c]);
+	if (max_vote < cfg.min_first) {                      // core.c:3217-3225
+		if (res[0].votes < 1) {
+			if (res[0].kind == 0) { res[0].kind = 2; res[0].used = 0; }
+			if (res[0].used < applied) res[0].used = (int16_t)applied;
+		}
+		return;
+	}
+	int top[kMaxTop] = {0, 0, 0};
+	for (int c = 0; c < C.n; c++)
+		if (C.votes[c] > 0) simple_update_top(cfg.top_scores, top, C.votes[c]);
+	for (int k = 0; k < mb; k++)
+		if (res[k].votes > 0) simple_update_top(cfg.top_scores, top, res[k].votes);
+
+	// candidate list: code < 16 = cluster index, 16 + k = bigtable slot k
+	int list[kMaxSimples > 16 ? 16 : kMaxSimples], n = 0;
+	const int max_simples = min(cfg.max_vote_simples, 16);   // <= 8 clusters + 3 slots can ever qualify
+	for (int lv = 0; lv < cfg.top_scores; lv++) {
+		if (n >= max_simples) break;
+		const int want = top[lv];
+		if (want < 1 || top[0] - want > cfg.max_vote_number_cutoff) break;
+		unsigned done = 0;
+		for (;;) {                                       // slots of this level in (row, j) order = the reference's i, j loops
+			int best = -1, best_key = 0x7fffffff;
+			for (int c = 0; c < C.n; c++)
+				if (!((done >> c) & 1u) && C.votes[c] == want) {
+					const int key = (int)C.row[c] * 32 + (int)C.j[c];
+					if (key < best_key) { best_key = key; best = c; }
+				}
+			if (best < 0 || n >= max_simples) break;
+			done |= 1u << best;
+			if (want >= cfg.min_second) list[n++] = best;
+		}
+		for (int k = 0; k < mb; k++) {
+			if (n >= max_simples) break;
+			if (res[k].votes == want) list[n++] = 16 + k;
+		}
+	}
+	SimpleResult tmp[kMaxBest];
+	int cursor = 0;
+	for (int s = 0; s < n && cursor < mb; s++) {
+		const int code = list[s];
+		const int votes = code < 16 ? (int)C.votes[code] : (int)res[code - 16].votes;
+		if (votes < cfg.min_first) continue;
+		const uint32_t pos = code < 16 ? C.kv[code] : res[code - 16].pos;
+		bool exist = false;
+		for (int e = 0; e < cursor; e++) exist = exist || tmp[e].pos == pos;
+		if (exist) continue;
+		if (code < 16) {
+			SimpleResult &t = tmp[cursor];
+			t.kind = 1; t.strand = (uint8_t)strand; t.first_sub = C.first_sub[code]; t.last_sub = C.last_sub[code];
+			t.votes = C.votes[code]; t.used = (int16_t)applied; t.pos = pos;
+			t.cov_start = C.first_off[code]; t.cov_end = (int16_t)(C.last_off[code] + 16);
+		} else tmp[cursor] = res[code - 16];
+		cursor++;
+	}
+	for (int k = 0; k < mb; k++) {                       // :2505-2527
+		if (k < cursor) res[k] = tmp[k];
+		else res[k].votes = 0;
+	}
+}
+
 // k_map_simple: thread f maps single-end fragment f of a chunk whose bigtable slice is all zero.
-// Writes the fragment's 3 result slots, or queues the fragment for the warp kernel.
+// Writes the fragment's result slots, or queues the fragment for the warp kernel.
 template <int GAP>
 __global__ void __launch_bounds__(128)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
@@ -195,9 +296,9 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
 	bool punt = false, active = f < n_frags;
-	uint32_t fw[kSimpleWords], rc[kSimpleWords];
-	SimpleSlot s0, s1;
-	s0.votes = s1.votes = 0;
+	SimpleResult res[kMaxBest];
+#pragma unroll
+	for (int k = 0; k < kMaxBest; k++) { res[k].kind = 0; res[k].votes = 0; res[k].used = 0; res[k].pos = 0; }
 	int applied = 0, L = 0;
 	if (active) {
 		const uint64_t o0 = off[f] - text_origin;
@@ -208,12 +309,24 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 		} else if (L > kSimpleMaxLen) {
 			punt = true;
 		} else if (L >= 16) {
+			uint32_t fw[kSimpleWords], rc[kSimpleWords];
 			if (!simple_pack(text + o0, L, fw, rc)) punt = true;
 			else {
 				int step;
 				applied = subread_schedule(L, GAP, cfg.total_subreads, &step);
-				if (!simple_pass<GAP>(ix, cfg, fw, L, applied, step, &s0) || !simple_pass<GAP>(ix, cfg, rc, L, applied, step, &s1)) punt = true;
+				SimpleClusters C;
+				if (!simple_pass<GAP>(ix, cfg, fw, L, applied, step, C)) punt = true;
+				else {
+					simple_merge(cfg, C, 0, applied, res);
+					if (!simple_pass<GAP>(ix, cfg, rc, L, applied, step, C)) punt = true;
+					else simple_merge(cfg, C, 1, applied, res);
+				}
 			}
+		} else {
+			SimpleClusters C;
+			C.n = 0;
+			simple_merge(cfg, C, 0, 0, res);   // a read shorter than 16 bases: two empty passes
+			simple_merge(cfg, C, 1, 0, res);
 		}
 	}
 	// queue the punted fragments (one atomic per warp)
@@ -226,39 +339,21 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	}
 	if (!active || punt) return;
 
-	// do_voting's per-strand hand-over (core.c:3212-3226) and the top-K merge for <= 1 old + <= 1 new slot.
-	// src: 0 = untouched zero slot, 1 = pass-0 slot, 2 = pass-1 slot, 3 = "unmapped" slot 0 that only
-	// carries used_subreads_in_vote (core.c:3217-3225).
 	const int mb = cfg.multi_best_reads;
-	int src0 = 3, src1 = 0;
-	const bool has0 = s0.votes >= cfg.min_first;      // pass 0: max_vote >= min_first -> topK with an empty bigtable
-	if (has0) src0 = 1;
-	if (s1.votes >= cfg.min_first) {                  // pass 1: merge the new slot with pass 0's result
-		// vote levels (update_top_three): distinct values of {new, old} descending; a level more than
-		// max_vote_number_cutoff below the best ends the list.  Inside a level the vote-table slot comes
-		// before bigtable entries (:2262-2314); emission keeps list order and drops a repeated position.
-		bool take_new = true, take_old = has0, new_first = true;
-		if (has0) {
-			if (s1.votes >= s0.votes) take_old = s1.votes - s0.votes <= cfg.max_vote_number_cutoff;
-			else { new_first = false; take_new = s0.votes - s1.votes <= cfg.max_vote_number_cutoff; }
-			if (take_new && take_old && s0.pos == s1.pos) { if (new_first) take_old = false; else take_new = false; }
-		}
-		if (take_new && take_old) {
-			if (mb >= 2) { src0 = new_first ? 2 : 1; src1 = new_first ? 1 : 2; }
-			else src0 = new_first ? 2 : 1;
-		} else if (take_new) src0 = 2;
-		// else: the pass-0 slot alone stays (the new one is cut off or repeats its position)
-	}
 	ResultWords *dst = out + (size_t)f * mb;
-	uint32_t w[kResultWords];
-	for (int k = 0; k < mb; k++) {
-		const int src = k == 0 ? src0 : (k == 1 ? src1 : 0);
-		if (src == 1) simple_slot_words(s0, 0, applied, w);
-		else if (src == 2) simple_slot_words(s1, 1, applied, w);
-		else {
+	for (int k = 0; k < mb; k++) {   // copy_vote_to_alignment_res image of each slot (core-junction.c:1058-1072)
+		uint32_t w[kResultWords];
 #pragma unroll
-			for (int i = 0; i < kResultWords; i++) w[i] = 0;
-			if (src == 3) w[2] = (uint32_t)(uint16_t)applied << 16;
+		for (int i = 0; i < kResultWords; i++) w[i] = 0;
+		const SimpleResult &r = res[k];
+		if (r.kind == 1) {
+			w[0] = r.pos;
+			w[1] = r.strand ? (uint32_t)kCoreNegStrand : 0u;
+			w[2] = (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16);
+			w[4] = (uint32_t)r.first_sub | ((uint32_t)r.last_sub << 16);
+			w[15] = (uint32_t)(uint16_t)r.cov_start | ((uint32_t)(uint16_t)r.cov_end << 16);
+		} else if (r.kind == 2) {
+			w[2] = (uint32_t)(uint16_t)r.used << 16;
 		}
 #pragma unroll
 		for (int i = 0; i < kResultWords; i++) dst[k].w[i] = w[i];
