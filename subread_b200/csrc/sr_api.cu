@@ -132,7 +132,7 @@ k_map_scalar(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int use
 }
 
 // Derives the two lookup accelerators from the resident SoA index, one thread per bucket:
-// a 16-bit Bloom word (bit key16 & 15) and the 32-byte inline record (sr_common.cuh).
+// a 16-bit Bloom word (bloom_bits of every key16) and the 32-byte inline record (sr_common.cuh).
 __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, uint4 *records,
                                 uint16_t *bloom)
 {
@@ -140,7 +140,7 @@ __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *key
 		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
 		if (bloom) {
 			uint32_t bl = 0;
-			for (uint32_t i = 0; i < n; i++) bl |= 1u << ((int)keys[lo + i] & 15);
+			for (uint32_t i = 0; i < n; i++) bl |= sr::bloom_bits((int)keys[lo + i]);
 			bloom[b] = (uint16_t)bl;
 		}
 		if (records) {
@@ -151,6 +151,9 @@ __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *key
 				for (uint32_t i = 0; i < n; i++) { k[i] = (uint16_t)keys[lo + i]; v[i] = vals[lo + i]; }
 				w[0] |= k[0] << 16; w[1] = k[1] | (k[2] << 16); w[2] = k[3] | (k[4] << 16);
 				w[3] = v[0]; w[4] = v[1]; w[5] = v[2]; w[6] = v[3]; w[7] = v[4];
+			} else if (n <= (uint32_t)sr::kRecordKeys) {
+				w[1] = lo;
+				for (uint32_t i = 0; i < n; i++) w[2 + (i >> 1)] |= (uint32_t)(uint16_t)keys[lo + i] << ((i & 1) * 16);
 			}
 			records[2 * (size_t)b] = make_uint4(w[0], w[1], w[2], w[3]);
 			records[2 * (size_t)b + 1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -216,6 +219,9 @@ struct srcuda_handle {
 	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
 	void *d_records = nullptr, *d_bloom = nullptr;
 	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both (SRCUDA_ACCEL)
+	bool l2_persist = true;        // keep the Bloom words resident in L2 (SRCUDA_L2_PERSIST=0 turns it off)
+	size_t l2_persist_max = 0, l2_window_max = 0;
+	const void *l2_policy_for = nullptr;   // Bloom array the streams' access-policy window currently covers
 	size_t genome_words = 0;
 	BatchSet set[kSets];
 	std::vector<cudaEvent_t> events;
@@ -223,6 +229,7 @@ struct srcuda_handle {
 	srcuda_timing timing{};
 	bool force_slow = false;
 	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
+	int simple_smem_set[4] = {0, 0, 0, 0};  // dynamic shared memory already granted to k_map_simple<GAP>
 	int64_t batch_frags = 1 << 20;
 	uint32_t *d_sink = nullptr;
 };
@@ -273,6 +280,7 @@ void free_index(srcuda_handle *h)
 	cudaFree(h->d_records); cudaFree(h->d_bloom);
 	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = h->d_records = h->d_bloom = nullptr;
 	h->has_index = false;
+	h->l2_policy_for = nullptr;
 	memset(&h->ix, 0, sizeof(h->ix));
 	memset(&h->desc, 0, sizeof(h->desc));
 }
@@ -413,14 +421,25 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	const bool tier0 = !scalar_only && h->use_simple_tier && !cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
 	                   cfg.min_second <= cfg.min_first && cfg.top_scores >= 2 && cfg.max_vote_simples >= 2;
 	if (tier0) {
-		const int threads = 128;
+		const int threads = sr::kSimpleThreads;
 		const int64_t blocks = (a.n_frags + threads - 1) / threads;
+		const int smem = sr::simple_smem_bytes(max_len);
 		uint32_t *q0 = (uint32_t *)bs.queue0.p;
+#define SR_LAUNCH_SIMPLE(G)                                                                                                          \
+	do {                                                                                                                             \
+		if (smem > h->simple_smem_set[G]) {                                                                                          \
+			CU(h, cudaFuncSetAttribute(sr::k_map_simple<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                      \
+			h->simple_smem_set[G] = smem;                                                                                            \
+		}                                                                                                                            \
+		sr::k_map_simple<G><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, \
+		                                                           a.n_frags, max_len, a.out, q0, bs.counters + 2, a.bad_reads);   \
+	} while (0)
 		switch (h->ix.index_gap) {
-		case 1: sr::k_map_simple<1><<<(unsigned)blocks, threads, 0, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, a.n_frags, a.out, q0, bs.counters + 2, a.bad_reads); break;
-		case 2: sr::k_map_simple<2><<<(unsigned)blocks, threads, 0, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, a.n_frags, a.out, q0, bs.counters + 2, a.bad_reads); break;
-		default: sr::k_map_simple<3><<<(unsigned)blocks, threads, 0, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, a.n_frags, a.out, q0, bs.counters + 2, a.bad_reads); break;
+		case 1: SR_LAUNCH_SIMPLE(1); break;
+		case 2: SR_LAUNCH_SIMPLE(2); break;
+		default: SR_LAUNCH_SIMPLE(3); break;
 		}
+#undef SR_LAUNCH_SIMPLE
 		CU(h, cudaGetLastError());
 		h->timing.n_launches++;
 		aw.in_list = q0;
@@ -440,6 +459,26 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	return 0;
 }
 
+// Best effort: the Bloom words (2 bytes per bucket, 32 MB for the one-block gapped table) are read 60 times per
+// read at random, everything else streams through; a persisting access-policy window keeps them in L2.
+void apply_l2_policy(srcuda_handle *h)
+{
+	if (!h->l2_persist || !h->d_bloom || h->l2_policy_for == h->d_bloom || !h->l2_persist_max || !h->l2_window_max) return;
+	const size_t bytes = sizeof(uint16_t) * (size_t)h->ix.buckets_number;
+	const size_t carve = std::min(bytes, h->l2_persist_max), window = std::min(bytes, h->l2_window_max);
+	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	v.accessPolicyWindow.base_ptr = h->d_bloom;
+	v.accessPolicyWindow.num_bytes = window;
+	v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+	for (int i = 0; i < kSets; i++)
+		if (h->set[i].stream && cudaStreamSetAttribute(h->set[i].stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+	h->l2_policy_for = h->d_bloom;
+}
+
 int init_sets(srcuda_handle *h)
 {
 	for (int i = 0; i < kSets; i++) {
@@ -453,6 +492,7 @@ int init_sets(srcuda_handle *h)
 		CU(h, cudaEventCreate(&h->ev_end));
 		for (int i = 0; i < kSets; i++) CU(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
 	}
+	apply_l2_policy(h);
 	return 0;
 }
 
@@ -482,6 +522,10 @@ int srcuda_open(int device, srcuda_handle **out)
 	srcuda_handle *h = new srcuda_handle();
 	h->device = device;
 	h->sm_count = prop.multiProcessorCount;
+	h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+	h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+	const char *lp = getenv("SRCUDA_L2_PERSIST");
+	if (lp && lp[0] == '0') h->l2_persist = false;
 	if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SRCUDA_ERR_CUDA, "cudaSetDevice(%d) failed", device); }
 	const char *bf = getenv("SRCUDA_BATCH_FRAGS");
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
@@ -490,7 +534,10 @@ int srcuda_open(int device, srcuda_handle **out)
 	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both; default auto
 	if (ac && ac[0] >= '0' && ac[0] <= '3') h->accel_mode = ac[0] - '0';
 	const char *fg = getenv("SRCUDA_L2_FETCH");  // L2 fetch granularity hint in bytes: 32, 64 or 128
-	if (fg && atoi(fg) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
+	// The hot loads are random 32-byte sectors (Bloom words, bucket records): fetching the neighbour sector too only
+	// doubles the DRAM traffic.  Default 32; the streaming loads are full lines either way.
+	cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, fg && atoi(fg) > 0 ? (size_t)atoi(fg) : (size_t)32);
+	cudaGetLastError();
 	*out = h;
 	return SRCUDA_OK;
 }

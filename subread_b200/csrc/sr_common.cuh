@@ -47,14 +47,24 @@ struct DevIndex {
 	const uint32_t *chr_offsets;   // total_offsets cumulative END offsets
 	// Lookup accelerators derived on the device at load time (sr_api.cu, k_build_records); both are
 	// exact: a filter without false negatives and a re-packed copy of small buckets.
-	const uint16_t *bloom;         // per bucket: bit (key16 & 15) set for every key16 in the bucket; null = off
+	const uint16_t *bloom;         // per bucket: bloom_bits(key16) set for every key16 in the bucket; null = off
 	const void *records;           // per bucket 32 B (two uint4): see below; null = off
 };
 
-// 32-byte bucket record (one sector): n <= kInlineItems items inline, otherwise only n is valid and
-// the lookup falls back to bucket_start / keys / vals.
-//   bytes 0-1  n (saturated at 0xffff)   bytes 2-11  key16[5]   bytes 12-31  value[5]
+// 32-byte bucket record (one sector), n = items in the bucket (saturated at 0xffff):
+//   n <= kInlineItems:  bytes 0-1 n   bytes 2-11 key16[5]   bytes 12-31 value[5]        (the whole bucket)
+//   n <= kRecordKeys:   bytes 0-1 n   bytes 4-7 bucket_start   bytes 8-31 key16[12]      (positions stay in vals[])
+//   larger:             only n is valid; the lookup falls back to bucket_start / keys / vals.
 constexpr int kInlineItems = 5;
+constexpr int kRecordKeys = 12;
+
+// The two bits a key16 sets in its bucket's 16-bit Bloom word (a 2-hash blocked Bloom filter: with two items per
+// bucket a quarter of the bits are set and a foreign key passes about one time in twenty).
+SR_HD uint32_t bloom_bits(int k16)
+{
+	const uint32_t q = (uint32_t)k16;
+	return (1u << (q & 15u)) | (1u << ((q >> 4) & 15u));
+}
 
 // The voting scalars, validated and pre-digested on the host (see srcuda_params).
 struct VoteConfig {

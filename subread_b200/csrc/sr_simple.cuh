@@ -1,8 +1,8 @@
-// sr_simple.cuh -- tier 0 of the voting step: one THREAD per single-end fragment.
+// sr_simple.cuh -- tier 0 of the voting step: one THREAD per single-end fragment, one block per
+// 128 consecutive fragments.
 //
 // The warp kernel (sr_warp.cuh) spends most of its instructions on warp-uniform work; for the
 // common fragment that work is tiny.  A strand pass is "separable" when
-//   * every lookup returns at most one position,
 //   * the distinct values kv = position - offset that occur are pairwise more than the indel
 //     tolerance apart, and
 //   * the hits of one kv come from distinct subreads.
@@ -13,106 +13,194 @@
 //     votes = #hits, coverage = [offset(first hit), offset(last hit) + 16),
 //     indel recorder = {subread(first)+1, subread(last)+1, 0},    row = (kv/5)%30, j = creation rank in its row,
 // with no shift-indel round (toli stays 0).  Spurious single hits -- the usual companions of the true
-// cluster on a large index -- are just extra one-vote slots.  process_voting_junction_PE_topK
-// (core-junction.c:2199-2530) is then replayed on that small slot list and on the results of the first
-// strand pass (the chunk's bigtable slice must be all zero, i.e. the first index block).
+// cluster on a large index -- are just extra one-vote slots, and a lookup that returns several
+// positions contributes them in the reference's visit order (:1109-1119).
+// process_voting_junction_PE_topK (core-junction.c:2199-2530) is then replayed on that small slot list
+// and on the results of the first strand pass (the chunk's bigtable slice must be all zero, i.e. the
+// first index block).
 //
-// Everything else -- a lookup with several positions, kv values within tolerance of each other
-// (indels), two phases of one subread hitting one kv, more than kSimpleClusters distinct kv,
-// characters that are not A/C/G/T, reads longer than kSimpleMaxLen -- is PUNTED untouched to the
-// warp kernel through a queue, so the tiered path returns the reference's result for every input.
-// Paired-end and subjunc chunks, chunks merged into a non-zero bigtable, and verification requests
-// skip this tier altogether.
+// Everything else -- kv values within tolerance of each other (indels), two phases of one subread
+// hitting one kv, more than kSimpleClusters distinct kv, characters that are not A/C/G/T, reads longer
+// than kSimpleMaxLen -- is PUNTED untouched to the warp kernel through a queue, so the tiered path
+// returns the reference's result for every input.  Paired-end and subjunc chunks, chunks merged into a
+// non-zero bigtable, and verification requests skip this tier altogether.
+//
+// Data movement is organised per block so that the per-thread work stays in registers and shared memory:
+//   1. the block's read text (contiguous in the chunk) is staged into shared memory with coalesced
+//      16-byte loads; every thread packs its own read from there (2 bits per base, both strands) into a
+//      word-interleaved shared array, so later key extraction never touches local memory;
+//   2. per strand pass, all Bloom words of a batch of 32 lookups are requested before any is tested
+//      (memory-level parallelism, no branch between the loads) and the bucket records of the survivors
+//      are prefetched into L2;
+//   3. only the survivors (the true hits plus ~12 % false positives) run the divergent vote code;
+//   4. the block's slice of the bigtable is zero-filled with coalesced stores and the handful of
+//      non-zero words per fragment is scattered on top.
 #pragma once
 #include "sr_common.cuh"
 
 namespace sr {
 
+constexpr int kSimpleThreads = 128;                      // fragments (threads) per block
 constexpr int kSimpleMaxLen = 256;                       // longer reads go to the warp kernel
-constexpr int kSimpleWords = kSimpleMaxLen / 16 + 1;     // packed words per strand array
 constexpr int kSimpleClusters = 8;                       // distinct kv per strand pass
+constexpr int kSimpleClusterWords = 4;                   // shared-memory words per cluster
+
+// Shared-memory plan of one block (host and device agree through these functions): the packed reads of the 128
+// threads, then one private area per warp that first stages the warp's text and later holds its vote clusters.
+SR_HD int simple_words(int max_len) { return ((max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen) + 15) / 16 + 1; }
+SR_HD int simple_warp_bytes(int max_len)
+{
+	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
+	int stage = 32 * (((ml + 3) & ~3) + 4) + 32;                             // text of 32 reads (+ alignment slack)
+	const int clus = kSimpleClusters * kSimpleClusterWords * 32 * 4;         // the vote clusters reuse the staging area
+	if (stage < clus) stage = clus;
+	return (stage + 15) & ~15;
+}
+SR_HD int simple_smem_bytes(int max_len) { return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_warp_bytes(max_len); }
 
 #if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
 
-struct SimpleClusters {     // the vote table of a separable pass, in creation order
-	int n;
-	uint32_t kv[kSimpleClusters];
-	int16_t votes[kSimpleClusters];        // 0: kv outside the border, no slot (its hits are dropped)
-	int16_t first_off[kSimpleClusters], last_off[kSimpleClusters];
-	uint8_t first_sub[kSimpleClusters], last_sub[kSimpleClusters];   // subread + 1
-	uint8_t row[kSimpleClusters], j[kSimpleClusters];
-};
-
-struct SimpleResult {       // one bigtable slot in compact form
-	uint8_t kind;           // 0 untouched (all zero), 1 a record, 2 only used_subreads_in_vote is set
-	uint8_t strand, first_sub, last_sub;
-	int16_t votes;          // selected_votes as stored (0 for a record that lost its place: stale bytes stay)
-	int16_t used;
+// One bigtable slot in compact form (registers).
+struct SimpleResult {
 	uint32_t pos;
-	int16_t cov_start, cov_end;
+	int votes;          // selected_votes as stored (0 for a record that lost its place: its other bytes stay)
+	int used;
+	uint32_t meta;      // kind | strand << 8 | first_sub << 16 | last_sub << 24; kind 0 untouched, 1 record, 2 only `used` is set
+	uint32_t cov;       // confident_coverage_start | end << 16
 };
 
-// One bucket lookup by one thread: number of positions with key16 == k16 in bucket b, and the
-// position when there is exactly one.  Same accelerators as the warp kernel.
-__device__ __forceinline__ int simple_lookup(const DevIndex &ix, uint32_t b, int k16, uint32_t *value)
+// One vote cluster = the slot gehash_go_X builds for one kv of a separable pass.  Nothing in it depends on the
+// order in which its hits are applied:
+//   w0  kv
+//   w1  first_l[0:8] last_l[8:16] first_u[16:23] row[24:29] has_slot[31]
+//       first_l / last_l: lookup index (subread * gap + phase) of the cluster's first / last hit in reference order --
+//       offset and subread number follow from it; first_u: visit index of the first hit inside its lookup's run
+//       (only ever compared between clusters created by the same lookup)
+//   w2, w3  bit s set = subread s voted; votes = popcount
+// The reference appends a new slot at the end of its row (row = (kv/5)%30), so the rank j of a slot inside its row
+// is its rank by creation time = by (first_l, first_u); candidates are visited in (row, j) order, i.e. in the order of
+// the key row << 15 | first_l << 7 | first_u.  has_slot == 0: kv lies outside the border (:1074), its hits are dropped.
+struct SimpleCluster {
+	uint32_t kv, w1;
+	unsigned long long subs;
+	__device__ __forceinline__ int votes() const { return (w1 >> 31) ? __popcll(subs) : 0; }
+	__device__ __forceinline__ int first_l() const { return (int)(w1 & 255u); }
+	__device__ __forceinline__ int last_l() const { return (int)((w1 >> 8) & 255u); }
+	__device__ __forceinline__ int order() const { return (int)(((w1 >> 24) & 31u) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u)); }
+};
+
+// The clusters of the running pass in shared memory, four words each, interleaved over the warp's lanes.
+struct SimpleClusters {
+	uint32_t *base;     // &clusters[0][0][lane] in the warp's private area
+	int n, cap;
+	__device__ __forceinline__ uint32_t &w(int c, int i) const { return base[(c * kSimpleClusterWords + i) * 32]; }
+	__device__ __forceinline__ int votes(int c) const { return (w(c, 1) >> 31) ? __popc(w(c, 2)) + __popc(w(c, 3)) : 0; }
+	__device__ __forceinline__ int order(int c) const
+	{
+		const uint32_t w1 = w(c, 1);
+		return (int)(((w1 >> 24) & 31u) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u));
+	}
+	__device__ __forceinline__ SimpleCluster get(int c) const
+	{
+		SimpleCluster r;
+		r.kv = w(c, 0); r.w1 = w(c, 1);
+		r.subs = (unsigned long long)w(c, 2) | ((unsigned long long)w(c, 3) << 32);
+		return r;
+	}
+	__device__ __forceinline__ void put(int c, const SimpleCluster &r) const
+	{
+		w(c, 0) = r.kv; w(c, 1) = r.w1; w(c, 2) = (uint32_t)r.subs; w(c, 3) = (uint32_t)(r.subs >> 32);
+	}
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Cache policy by role.  The Bloom words (32 MB, hit at random 60 times per read) are the only data worth keeping:
+// they are loaded evict-last; the bucket records (one random sector out of 0.5 GB, never reused) and the streamed
+// text / bigtable are evict-first, so they do not push the filter out of L2.
+__device__ __forceinline__ uint64_t policy_evict_last()
 {
-	if (ix.bloom && !((__ldg(ix.bloom + b) >> (k16 & 15)) & 1)) return 0;
-	if (ix.records) {
-		const uint4 *rp = reinterpret_cast<const uint4 *>(ix.records) + 2 * (size_t)b;
-		const uint4 r0 = __ldg(rp);
-		const int n = (int)(r0.x & 0xffffu);
-		if (n <= kInlineItems) {
-			if (n == 0) return 0;
-			const int k0 = (int)(int16_t)(r0.x >> 16), k1 = (int)(int16_t)(r0.y & 0xffffu), k2 = (int)(int16_t)(r0.y >> 16),
-			          k3 = (int)(int16_t)(r0.z & 0xffffu), k4 = (int)(int16_t)(r0.z >> 16);
-			const int e0 = k0 == k16, e1 = n > 1 && k1 == k16, e2 = n > 2 && k2 == k16, e3 = n > 3 && k3 == k16, e4 = n > 4 && k4 == k16;
-			const int h = e0 + e1 + e2 + e3 + e4;
-			if (h == 1) {
-				if (e0) *value = r0.w;
-				else {
-					const uint4 r1 = __ldg(rp + 1);
-					*value = e1 ? r1.x : (e2 ? r1.y : (e3 ? r1.z : r1.w));
-				}
-			}
-			return h;
-		}
-	}
-	const uint32_t lo = __ldg(ix.bucket_start + b);
-	const int items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
-	if (items <= 0) return 0;
-	const int16_t *kp = ix.keys + lo;
-	int imin = 0, imax = items - 1, at;
-	for (;;) {
-		at = (imin + imax) >> 1;
-		const int kk = (int)__ldg(kp + at);
-		if (kk > k16) imax = at - 1;
-		else if (kk < k16) imin = at + 1;
-		else break;
-		if (imax < imin) return 0;
-	}
-	if ((at + 1 < items && (int)__ldg(kp + at + 1) == k16) || (at > 0 && (int)__ldg(kp + at - 1) == k16)) return 2;  // a run: not simple
-	*value = __ldg(ix.vals + lo + at);
-	return 1;
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint32_t ld_bloom(const uint16_t *p, uint64_t pol)
+{
+	uint16_t v;
+	asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+	return v;
+}
+// One 32-byte bucket record in a single 256-bit load (sm_100), streaming.
+struct __align__(32) Record8 { uint32_t w[8]; };
+__device__ __forceinline__ Record8 ld_record(const uint4 *records, uint32_t b)
+{
+	Record8 r;
+	asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+	             : "l"(records + 2 * (size_t)b));
+	return r;
 }
 
-// Pack the thread's read: forward codes fw[] (MSB first, 16 bases per word, code 2 beyond the read like
-// the reference's NUL) and reverse-complement codes rc[].  Returns false when a character is not one
-// of A, C, G, T (then base2int / reverse_read quirks apply and the fragment is punted).
-__device__ __forceinline__ bool simple_pack(const uint8_t *raw, int L, uint32_t *fw, uint32_t *rc)
+// A fresh cluster for the hit (kv, lookup l, visit index u) of subread `sub`.
+__device__ __forceinline__ SimpleCluster simple_new_cluster(uint32_t kv, int l, int u, int sub, uint32_t low, uint32_t high)
 {
-	const int n_words = (L + 15) / 16 + 1;
-	const uintptr_t p0 = (uintptr_t)raw, a0 = p0 & ~(uintptr_t)3, pend = p0 + (uintptr_t)L;
-	const unsigned mis = (unsigned)(p0 & 3) * 8u;
-	bool ok = true;
-	uint32_t wprev = __ldg((const uint32_t *)a0);
-	for (int k = 0; k < n_words; k++) {
+	SimpleCluster c;
+	c.kv = kv;
+	c.w1 = 0;
+	c.subs = 0;
+	if (kv >= low && kv <= high) {                                 // :1074
+		c.w1 = (uint32_t)l | ((uint32_t)l << 8) | ((uint32_t)u << 16) | (vote_row(kv) << 24) | 0x80000000u;
+		c.subs = 1ull << sub;
+	}
+	return c;
+}
+
+// One hit on the general path (clusters in shared memory).  Returns false when the pass is not separable.
+__device__ __forceinline__ bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
+{
+	if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;           // u32 wrap-around of the probe rows
+	int found = -1;
+	for (int c = 0; c < C.n; c++) {
+		const int d = (int)(kv - C.w(c, 0));
+		if (d == 0) found = c;
+		else if (d >= -tol && d <= tol) return false;              // within tolerance of another slot: an indel vote
+	}
+	if (found >= 0) {
+		SimpleCluster c = C.get(found);
+		if (!(c.w1 >> 31)) return true;                            // no slot for this kv: dropped again
+		const unsigned long long bit = 1ull << sub;
+		if (c.subs & bit) return false;                            // one subread twice: the reference opens a duplicate slot
+		c.subs |= bit;
+		if (l < c.first_l()) c.w1 = (c.w1 & ~0x007f00ffu) | (uint32_t)l | ((uint32_t)u << 16);
+		if (l > c.last_l()) c.w1 = (c.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);
+		C.put(found, c);
+		return true;
+	}
+	if (C.n == C.cap) return false;
+	C.put(C.n++, simple_new_cluster(kv, l, u, sub, low, high));
+	return true;
+}
+
+// Pack the thread's read from the staging area: forward codes (MSB first, 16 bases per word, code 2 beyond
+// the read like the reference's NUL) into pk[k * 128], reverse-complement codes into pk[(n_words + k) * 128].
+// Returns false when a character is not one of A, C, G, T (then base2int / reverse_read quirks apply and the
+// fragment is punted).
+__device__ __forceinline__ bool simple_pack(const uint8_t *stage, unsigned so, int L, uint32_t *pk, int n_words)
+{
+	const int nw = (L + 15) / 16 + 1;
+	const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage + (so & ~3u));
+	const unsigned mis = (so & 3u) * 8u;
+	const int last_word = (int)(((so & 3u) + (unsigned)L + 3u) / 4u);    // words [0, last_word) hold characters
+	uint32_t bad = 0;
+	uint32_t wprev = sw[0];
+	for (int k = 0; k < nw; k++) {
 		uint32_t f = 0;
 		const int nvalid = min(16, max(0, L - 16 * k));
-		if (nvalid == 0) { fw[k] = 0xAAAAAAAAu; continue; }
+		if (nvalid == 0) { pk[k * kSimpleThreads] = 0xAAAAAAAAu; continue; }
 #pragma unroll
 		for (int q = 0; q < 4; q++) {
-			const uintptr_t an = a0 + 16u * (uintptr_t)k + 4u * (q + 1);
-			const uint32_t wnext = an < pend ? __ldg((const uint32_t *)an) : 0u;
+			const int j = 4 * k + q + 1;
+			const uint32_t wnext = j < last_word ? sw[j] : 0u;
 			const uint32_t c4 = __funnelshift_r(wprev, wnext, mis);
 			wprev = wnext;
 			// A 0x41, C 0x43, G 0x47, T 0x54: code bit0 = bit 2, code bit1 = bit 1 ^ bit 2  (A0 G1 C2 T3)
@@ -124,239 +212,513 @@ __device__ __forceinline__ bool simple_pack(const uint8_t *raw, int L, uint32_t 
 			const int nb = nvalid - 4 * q;  // characters of this group inside the read
 			uint32_t diff = rebuilt ^ c4;
 			if (nb < 4) diff = nb <= 0 ? 0u : (diff & (0xffffffffu >> (8 * (4 - nb))));
-			ok = ok && diff == 0;
+			bad |= diff;
 			f |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * q);
 		}
 		const uint32_t keep = nvalid >= 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * nvalid));
-		fw[k] = (f & keep) | (0xAAAAAAAAu & ~keep);
+		pk[k * kSimpleThreads] = (f & keep) | (0xAAAAAAAAu & ~keep);
 	}
 	// reverse complement of an all-base read: rc base i = 3 - f base (L-1-i)
-	for (int k = 0; k < n_words; k++) {
+	uint32_t *rc = pk + n_words * kSimpleThreads;
+	for (int k = 0; k < nw; k++) {
 		const int nvalid = min(16, max(0, L - 16 * k));
 		uint32_t r = 0xAAAAAAAAu;
 		if (nvalid > 0) {
 			const int s = L - 16 - 16 * k;
 			const int w = s >> 4, sh = (s & 15) * 2;
-			const uint32_t hi = w >= 0 ? ~fw[w] : 0u, lo = ~fw[w + 1];
+			const uint32_t hi = w >= 0 ? ~pk[w * kSimpleThreads] : 0u, lo = ~pk[(w + 1) * kSimpleThreads];
 			uint32_t g = __funnelshift_l(lo, hi, sh);
 			g = __brev(g);
 			g = ((g & 0x55555555u) << 1) | ((g >> 1) & 0x55555555u);
 			const uint32_t keep = nvalid >= 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * nvalid));
 			r = (g & keep) | (0xAAAAAAAAu & ~keep);
 		}
-		rc[k] = r;
+		rc[k * kSimpleThreads] = r;
 	}
-	return ok;
+	return bad == 0;
 }
 
-// One strand pass.  Returns false when the pass is not separable.
+// Offset of the first lookup of subread s (phase 0); lookup s * GAP + x sits at this offset + x (core.c:3169-3171).
 template <int GAP>
-__device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *packed, int L, int applied, int step,
+__device__ __forceinline__ int simple_sub_offset(int s, int step)
+{
+	unsigned o = ((unsigned)step * (unsigned)s) >> 16;        // step * s < 2^31: s <= 62, step < 2^24
+	if (GAP > 1) o -= o % (unsigned)GAP;
+	return (int)o;
+}
+template <int GAP>
+__device__ __forceinline__ int simple_offset(int l, int step, int *sub)
+{
+	const unsigned s = (unsigned)l / (unsigned)GAP, x = (unsigned)l - s * (unsigned)GAP;
+	*sub = (int)s;
+	return simple_sub_offset<GAP>((int)s, step) + (int)x;
+}
+
+__device__ __forceinline__ uint32_t simple_key(const uint32_t *pk, int o)
+{
+	const int w = o >> 4, sh = (o & 15) * 2;
+	return __funnelshift_l(pk[(w + 1) * kSimpleThreads], pk[w * kSimpleThreads], sh);
+}
+
+// What one survivor's bucket record says about key16 = k16.
+//   kind 0: the key is absent   1: exactly one position (*value)   2: anything else -- several positions, or a bucket
+//   whose record cannot answer -- which the general path sorts out.
+__device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r, int k16, uint32_t *value)
+{
+	const int n = (int)(r.w[0] & 0xffffu);
+	if (n <= kInlineItems) {
+		const int k0 = (int)(int16_t)(r.w[0] >> 16), k1 = (int)(int16_t)(r.w[1] & 0xffffu), k2 = (int)(int16_t)(r.w[1] >> 16),
+		          k3 = (int)(int16_t)(r.w[2] & 0xffffu), k4 = (int)(int16_t)(r.w[2] >> 16);
+		// keys are sorted: the equal-key run is [lt, le)
+		const int lt = (n > 0 && k0 < k16) + (n > 1 && k1 < k16) + (n > 2 && k2 < k16) + (n > 3 && k3 < k16) + (n > 4 && k4 < k16);
+		const int le = (n > 0 && k0 <= k16) + (n > 1 && k1 <= k16) + (n > 2 && k2 <= k16) + (n > 3 && k3 <= k16) + (n > 4 && k4 <= k16);
+		*value = lt == 0 ? r.w[3] : (lt == 1 ? r.w[4] : (lt == 2 ? r.w[5] : (lt == 3 ? r.w[6] : r.w[7])));
+		return min(le - lt, 2);
+	}
+	if (n <= kRecordKeys) {                                        // 6..12 items: the record lists the keys, the positions stay in vals[]
+		int lt = 0, le = 0;
+#pragma unroll
+		for (int i = 0; i < kRecordKeys; i++) {
+			const int k = (int)(int16_t)(r.w[2 + (i >> 1)] >> ((i & 1) * 16));
+			lt += (i < n && k < k16) ? 1 : 0;
+			le += (i < n && k <= k16) ? 1 : 0;
+		}
+		if (le - lt == 1) *value = __ldg(ix.vals + r.w[1] + lt);
+		return min(le - lt, 2);
+	}
+	return 2;
+}
+
+// One strand pass.  pk = the pass's packed words of this thread (stride 128).  Leaves the clusters in C (shared
+// memory).  Returns false when the pass is not separable.
+//
+// Per batch of up to 32 lookups: (1) filter -- all Bloom words are requested before any is tested; (2) a uniform loop
+// over the survivors reads each bucket record (the next one is in flight while the current one is applied) and takes
+// the hit if it is a single position that belongs to the "primary" cluster P, which lives in registers (the first such
+// hit creates P); (3) whatever else turned up -- a position away from P, a lookup with several positions, a bucket of
+// more than twelve items -- is replayed on the general path, lookup by lookup in schedule order and position by
+// position in the reference's visit order.  Applying P's hits before the others is exact because a cluster does not
+// depend on the order of application.
+template <int GAP>
+__device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
                                             SimpleClusters &C)
 {
+	constexpr int kSubsPerBatch = 32 / GAP;                        // whole subreads per batch of <= 32 lookups
+	constexpr int kGroup = GAP == 3 ? 2 : (GAP == 2 ? 3 : 6);     // subreads per group of 6 lookups in flight
 	const uint32_t nb = ix.buckets_number;
 	const uint64_t magic = ix.buckets_magic;
-	const int n_lk = applied * GAP, tol = cfg.indel_tolerance;
-	const uint32_t high = cfg.high_border - (uint32_t)L;
+	const int tol = cfg.indel_tolerance;
+	const uint32_t low = cfg.low_border, high = cfg.high_border - (uint32_t)L;
+	const uint4 *records = reinterpret_cast<const uint4 *>(ix.records);
+	const uint64_t pol = policy_evict_last();
 	C.n = 0;
-	for (int l = 0; l < n_lk; l++) {
-		const int o = lookup_offset(l, GAP, step);
-		const int w = o >> 4, s = (o & 15) * 2;
-		const uint32_t key = __funnelshift_l(packed[w + 1], packed[w], s);
-		const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
-		const uint32_t b = key - q * nb;
-		uint32_t value = 0;
-		const int h = simple_lookup(ix, b, (int)(int16_t)q, &value);
-		if (h > 1) return false;
-		if (h == 1) {
-			const uint32_t kv = value - (uint32_t)o;
-			if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;   // u32 wrap-around of the probe rows
-			const int sub_p1 = l / GAP + 1;
-			int found = -1;
-			for (int c = 0; c < C.n; c++) {
-				const int d = (int)(kv - C.kv[c]);
-				if (d == 0) found = c;
-				else if (d >= -tol && d <= tol) return false;          // within tolerance of another slot: an indel vote
-			}
-			if (found >= 0) {
-				if (C.votes[found] == 0) continue;                      // no slot for this kv: dropped again
-				if (sub_p1 == (int)C.last_sub[found]) return false;     // same subread twice: the reference opens a duplicate slot
-				C.votes[found]++;
-				C.last_off[found] = (int16_t)o;
-				C.last_sub[found] = (uint8_t)sub_p1;
-			} else {
-				if (C.n == kSimpleClusters) return false;
-				const int c = C.n++;
-				C.kv[c] = kv;
-				C.votes[c] = 0;
-				if (kv >= cfg.low_border && kv <= high) {               // :1074
-					const int row = (int)vote_row(kv);
-					int jj = 0;
-					for (int e = 0; e < c; e++) jj += (C.votes[e] > 0 && (int)C.row[e] == row) ? 1 : 0;
-					C.votes[c] = 1;
-					C.first_off[c] = C.last_off[c] = (int16_t)o;
-					C.first_sub[c] = C.last_sub[c] = (uint8_t)sub_p1;
-					C.row[c] = (uint8_t)row;
-					C.j[c] = (uint8_t)jj;
+	SimpleCluster P;                  // cluster 0 while have_p
+	P.kv = 0; P.w1 = 0; P.subs = 0;
+	bool have_p = false, ok = true;
+	for (int s_base = 0; s_base < applied; s_base += kSubsPerBatch) {
+		const int n_sub = min(kSubsPerBatch, applied - s_base), cnt = n_sub * GAP, base = s_base * GAP;
+		// ---- (1) filter ----
+		unsigned mask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+		if (ix.bloom) {
+			mask = 0;
+#pragma unroll 1
+			for (int g = 0; g < n_sub; g += kGroup) {
+				uint32_t bw[kGroup * GAP], bq[kGroup * GAP];
+#pragma unroll
+				for (int ss = 0; ss < kGroup; ss++) {
+					const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
+#pragma unroll
+					for (int x = 0; x < GAP; x++) {
+						const uint32_t key = simple_key(pk, ob + x);
+						const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
+						bq[ss * GAP + x] = q;
+						bw[ss * GAP + x] = key - q * nb;
+					}
+				}
+				uint32_t word[kGroup * GAP];
+#pragma unroll
+				for (int u = 0; u < kGroup * GAP; u++) word[u] = ld_bloom(ix.bloom + bw[u], pol);
+#pragma unroll
+				for (int u = 0; u < kGroup * GAP; u++) {
+					const uint32_t m = bloom_bits((int)bq[u]);
+					const bool in = g + u / GAP < n_sub && (word[u] & m) == m;
+					mask |= (in ? 1u : 0u) << ((g * GAP + u) & 31);
+					if (in && records) prefetch_l2(records + 2 * (size_t)bw[u]);
 				}
 			}
 		}
+		// ---- (2) survivors: single positions of the primary cluster ----
+		unsigned defer = mask;
+		if (records) {
+			defer = 0;
+			Record8 rn;
+			int i_next = -1, o_next = 0, sub_next = 0, k16_next = 0;
+			if (mask) {
+				i_next = __ffs(mask) - 1;
+				mask &= mask - 1;
+				o_next = simple_offset<GAP>(base + i_next, step, &sub_next);
+				const uint32_t key = simple_key(pk, o_next);
+				const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
+				k16_next = (int)(int16_t)q;
+				rn = ld_record(records, key - q * nb);
+			}
+			while (i_next >= 0) {
+				const Record8 r = rn;
+				const int i = i_next, o = o_next, sub = sub_next, k16 = k16_next, l = base + i;
+				i_next = -1;
+				if (mask) {                                              // the next record travels while this one is applied
+					i_next = __ffs(mask) - 1;
+					mask &= mask - 1;
+					o_next = simple_offset<GAP>(base + i_next, step, &sub_next);
+					const uint32_t key = simple_key(pk, o_next);
+					const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
+					k16_next = (int)(int16_t)q;
+					rn = ld_record(records, key - q * nb);
+				}
+				uint32_t value = 0;
+				const int kind = simple_probe(ix, r, k16, &value);
+				const uint32_t kv = value - (uint32_t)o;
+				if (kind == 1 && !have_p && C.n == 0) {                  // the first position of the pass founds P
+					if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
+					P = simple_new_cluster(kv, l, 0, sub, low, high);
+					have_p = true;
+					C.n = 1;
+				} else if (kind == 1 && have_p && kv == P.kv) {          // the plain branch :1041-1052
+					const unsigned long long bit = 1ull << sub;
+					if (P.w1 >> 31) {
+						if (P.subs & bit) ok = false;
+						P.subs |= bit;
+						P.w1 = (P.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);  // lookups come in increasing order here
+					}
+				} else if (kind != 0)
+					defer |= 1u << i;
+			}
+			if (!ok) return false;
+		}
+		// ---- (3) everything else, on the general path ----
+		if (defer) {
+			if (have_p) C.put(0, P);
+			while (defer) {
+				const int i = __ffs(defer) - 1;
+				defer &= defer - 1;
+				const int l = base + i;
+				int sub;
+				const int o = simple_offset<GAP>(l, step, &sub);
+				const uint32_t key = simple_key(pk, o);
+				const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
+				const uint32_t b = key - q * nb;
+				const int k16 = (int)(int16_t)q;
+				bool in_arrays = true;
+				if (records) {
+					const Record8 r = ld_record(records, b);
+					const int n = (int)(r.w[0] & 0xffffu);
+					if (n <= kInlineItems) {
+						in_arrays = false;
+						const int k0 = (int)(int16_t)(r.w[0] >> 16), k1 = (int)(int16_t)(r.w[1] & 0xffffu), k2 = (int)(int16_t)(r.w[1] >> 16),
+						          k3 = (int)(int16_t)(r.w[2] & 0xffffu), k4 = (int)(int16_t)(r.w[2] >> 16);
+						const int lt = (n > 0 && k0 < k16) + (n > 1 && k1 < k16) + (n > 2 && k2 < k16) + (n > 3 && k3 < k16) + (n > 4 && k4 < k16);
+						const int le = (n > 0 && k0 <= k16) + (n > 1 && k1 <= k16) + (n > 2 && k2 <= k16) + (n > 3 && k3 <= k16) + (n > 4 && k4 <= k16);
+						if (le > lt) {
+							// where the reference's (imin+imax)/2 search lands inside the run (sorted-hashtable.c:960-981)
+							int imin = 0, imax = n - 1, at;
+							for (;;) {
+								at = (imin + imax) >> 1;
+								if (at >= le) imax = at - 1;
+								else if (at < lt) imin = at + 1;
+								else break;
+							}
+							const int h = le - lt, nfwd = le - at;       // landing .. end of run, then landing-1 .. start (:1109-1119)
+							for (int u = 0; u < h; u++) {
+								const int idx = u < nfwd ? at + u : at - 1 - (u - nfwd);
+								const uint32_t v = idx == 0 ? r.w[3] : (idx == 1 ? r.w[4] : (idx == 2 ? r.w[5] : (idx == 3 ? r.w[6] : r.w[7])));
+								if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) return false;
+							}
+						}
+					}
+				}
+				if (in_arrays) {                                         // a bucket with more than 5 items, or no records at all
+					const uint32_t lo = __ldg(ix.bucket_start + b);
+					const int items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
+					if (items <= 0) continue;
+					const int16_t *kp = ix.keys + lo;
+					int imin = 0, imax = items - 1, at;
+					bool found = false;
+					for (;;) {                                           // sorted-hashtable.c:960-981
+						at = (imin + imax) >> 1;
+						const int kk = (int)__ldg(kp + at);
+						if (kk > k16) imax = at - 1;
+						else if (kk < k16) imin = at + 1;
+						else { found = true; break; }
+						if (imax < imin) break;
+					}
+					if (!found) continue;
+					int e = at + 1, st = at;
+					while (e < items && (int)__ldg(kp + e) == k16) e++;
+					while (st > 0 && (int)__ldg(kp + st - 1) == k16) st--;
+					const int h = e - st, nfwd = e - at;
+					if (h > C.cap) return false;                         // cannot stay separable
+					for (int u = 0; u < h; u++) {
+						const int idx = u < nfwd ? at + u : at - 1 - (u - nfwd);
+						const uint32_t v = __ldg(ix.vals + lo + idx);
+						if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) return false;
+					}
+				}
+			}
+			if (have_p) P = C.get(0);
+		}
 	}
+	if (have_p) C.put(0, P);
 	return true;
 }
 
-__device__ __forceinline__ void simple_update_top(int top_scores, int *top, int v)   // update_top_three core-junction.c:908
+// update_top_three (core-junction.c:908) on three registers; ts = top_scores.
+__device__ __forceinline__ void simple_update_top(int ts, int &t0, int &t1, int &t2, int v)
 {
-	if (v > top[top_scores - 1])
-		for (int x = 0; x < top_scores; x++) {
-			if (v > top[x]) {
-				for (int y = top_scores - 1; y > x; y--) top[y] = top[y - 1];
-				top[x] = v;
-				break;
-			} else if (v == top[x]) break;
-		}
+	const int last = ts == 1 ? t0 : (ts == 2 ? t1 : t2);
+	if (v <= last) return;
+	if (v > t0) {
+		if (ts > 2) t2 = t1;
+		if (ts > 1) t1 = t0;
+		t0 = v;
+	} else if (v == t0) {
+	} else if (ts > 1 && v > t1) {
+		if (ts > 2) t2 = t1;
+		t1 = v;
+	} else if (ts > 1 && v == t1) {
+	} else if (ts > 2 && v > t2) t2 = v;
 }
 
 // process_voting_junction_PE_topK for one single-end pass over a separable table (core-junction.c:2199-2530,
-// the SE branch :2436-2495) and the hand-over logic of do_voting (core.c:3212-3226).
-__device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const SimpleClusters &C, int strand, int applied, SimpleResult *res)
+// the SE branch :2436-2495) and the hand-over logic of do_voting (core.c:3212-3226).  res[] is fully unrolled so
+// that it stays in registers.
+template <int GAP>
+__device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const SimpleClusters &C, int strand, int applied, int step, SimpleResult (&res)[kMaxBest])
 {
-	const int mb = cfg.multi_best_reads;
+	const int mb = cfg.multi_best_reads, ts = cfg.top_scores;
 	int max_vote = 0;
-	for (int c = 0; c < C.n; c++) max_vote = max(max_vote, (int)C.votes[c]);
+	for (int c = 0; c < C.n; c++) max_vote = max(max_vote, C.votes(c));
 	if (max_vote < cfg.min_first) {                      // core.c:3217-3225
 		if (res[0].votes < 1) {
-			if (res[0].kind == 0) { res[0].kind = 2; res[0].used = 0; }
-			if (res[0].used < applied) res[0].used = (int16_t)applied;
+			if ((res[0].meta & 0xffu) == 0) { res[0].meta = 2u; res[0].used = 0; }
+			if (res[0].used < applied) res[0].used = applied;
 		}
 		return;
 	}
-	int top[kMaxTop] = {0, 0, 0};
-	for (int c = 0; c < C.n; c++)
-		if (C.votes[c] > 0) simple_update_top(cfg.top_scores, top, C.votes[c]);
-	for (int k = 0; k < mb; k++)
-		if (res[k].votes > 0) simple_update_top(cfg.top_scores, top, res[k].votes);
+	int t0 = 0, t1 = 0, t2 = 0;
+	for (int c = 0; c < C.n; c++) {
+		const int v = C.votes(c);
+		if (v > 0) simple_update_top(ts, t0, t1, t2, v);
+	}
+#pragma unroll
+	for (int k = 0; k < kMaxBest; k++)
+		if (k < mb && res[k].votes > 0) simple_update_top(ts, t0, t1, t2, res[k].votes);
 
-	// candidate list: code < 16 = cluster index, 16 + k = bigtable slot k
-	int list[kMaxSimples > 16 ? 16 : kMaxSimples], n = 0;
-	const int max_simples = min(cfg.max_vote_simples, 16);   // <= 8 clusters + 3 slots can ever qualify
-	for (int lv = 0; lv < cfg.top_scores; lv++) {
+	// The reference first lists the candidates level by level (:2251-2330) and then consumes the list in order
+	// (:2436-2495); consuming each candidate as soon as it is listed is the same thing.
+	SimpleResult tmp[kMaxBest];
+#pragma unroll
+	for (int k = 0; k < kMaxBest; k++) tmp[k].pos = 0;
+	int n = 0, cursor = 0;
+	const int max_simples = cfg.max_vote_simples;
+	auto exists = [&](uint32_t pos) {
+		bool e = false;
+#pragma unroll
+		for (int k = 0; k < kMaxBest; k++) e = e || (k < cursor && tmp[k].pos == pos);
+		return e;
+	};
+	auto put = [&](const SimpleResult &r) {
+#pragma unroll
+		for (int k = 0; k < kMaxBest; k++)
+			if (k == cursor) tmp[k] = r;
+		cursor++;
+	};
+	for (int lv = 0; lv < ts; lv++) {
 		if (n >= max_simples) break;
-		const int want = top[lv];
-		if (want < 1 || top[0] - want > cfg.max_vote_number_cutoff) break;
+		const int want = lv == 0 ? t0 : (lv == 1 ? t1 : t2);
+		if (want < 1 || t0 - want > cfg.max_vote_number_cutoff) break;
 		unsigned done = 0;
 		for (;;) {                                       // slots of this level in (row, j) order = the reference's i, j loops
 			int best = -1, best_key = 0x7fffffff;
 			for (int c = 0; c < C.n; c++)
-				if (!((done >> c) & 1u) && C.votes[c] == want) {
-					const int key = (int)C.row[c] * 32 + (int)C.j[c];
+				if (!((done >> c) & 1u) && C.votes(c) == want) {
+					const int key = C.order(c);
 					if (key < best_key) { best_key = key; best = c; }
 				}
 			if (best < 0 || n >= max_simples) break;
 			done |= 1u << best;
-			if (want >= cfg.min_second) list[n++] = best;
+			if (want >= cfg.min_second) {
+				n++;
+				const uint32_t pos = C.w(best, 0);
+				if (cursor < mb && want >= cfg.min_first && !exists(pos)) {
+					const uint32_t w1 = C.w(best, 1);
+					int s_first, s_last;
+					const int o_first = simple_offset<GAP>((int)(w1 & 255u), step, &s_first);
+					const int o_last = simple_offset<GAP>((int)((w1 >> 8) & 255u), step, &s_last);
+					SimpleResult r;
+					r.pos = pos; r.votes = want; r.used = applied;
+					r.meta = 1u | ((uint32_t)strand << 8) | ((uint32_t)(s_first + 1) << 16) | ((uint32_t)(s_last + 1) << 24);
+					r.cov = (uint32_t)o_first | ((uint32_t)(o_last + 16) << 16);
+					put(r);
+				}
+			}
 		}
-		for (int k = 0; k < mb; k++) {
-			if (n >= max_simples) break;
-			if (res[k].votes == want) list[n++] = 16 + k;
+#pragma unroll
+		for (int k = 0; k < kMaxBest; k++) {
+			if (k < mb && n < max_simples && res[k].votes == want) {
+				n++;
+				if (cursor < mb && want >= cfg.min_first && !exists(res[k].pos)) put(res[k]);
+			}
 		}
 	}
-	SimpleResult tmp[kMaxBest];
-	int cursor = 0;
-	for (int s = 0; s < n && cursor < mb; s++) {
-		const int code = list[s];
-		const int votes = code < 16 ? (int)C.votes[code] : (int)res[code - 16].votes;
-		if (votes < cfg.min_first) continue;
-		const uint32_t pos = code < 16 ? C.kv[code] : res[code - 16].pos;
-		bool exist = false;
-		for (int e = 0; e < cursor; e++) exist = exist || tmp[e].pos == pos;
-		if (exist) continue;
-		if (code < 16) {
-			SimpleResult &t = tmp[cursor];
-			t.kind = 1; t.strand = (uint8_t)strand; t.first_sub = C.first_sub[code]; t.last_sub = C.last_sub[code];
-			t.votes = C.votes[code]; t.used = (int16_t)applied; t.pos = pos;
-			t.cov_start = C.first_off[code]; t.cov_end = (int16_t)(C.last_off[code] + 16);
-		} else tmp[cursor] = res[code - 16];
-		cursor++;
-	}
-	for (int k = 0; k < mb; k++) {                       // :2505-2527
-		if (k < cursor) res[k] = tmp[k];
-		else res[k].votes = 0;
+#pragma unroll
+	for (int k = 0; k < kMaxBest; k++) {                 // :2505-2527
+		if (k < mb) {
+			if (k < cursor) res[k] = tmp[k];
+			else res[k].votes = 0;
+		}
 	}
 }
 
-// k_map_simple: thread f maps single-end fragment f of a chunk whose bigtable slice is all zero.
-// Writes the fragment's result slots, or queues the fragment for the warp kernel.
+// k_map_simple: thread t of block b maps single-end fragment 128 b + t of a chunk whose bigtable slice is all
+// zero.  Writes the fragment's result slots, or queues the fragment for the warp kernel (its slots are then zero).
+// Every warp works on its own 32 fragments and its own slice of shared memory: there is no block-wide barrier.
+// Dynamic shared memory: simple_smem_bytes(max_len).
 template <int GAP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSimpleThreads)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
-             const uint64_t *off, const uint16_t *len, int64_t n_frags, ResultWords *out, uint32_t *queue, uint32_t *queue_count,
+             const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, ResultWords *out, uint32_t *queue, uint32_t *queue_count,
              uint32_t *bad_reads)
 {
-	const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	bool punt = false, active = f < n_frags;
-	SimpleResult res[kMaxBest];
-#pragma unroll
-	for (int k = 0; k < kMaxBest; k++) { res[k].kind = 0; res[k].votes = 0; res[k].used = 0; res[k].pos = 0; }
-	int applied = 0, L = 0;
+	extern __shared__ uint4 smem4[];
+	constexpr unsigned kFullMask = 0xffffffffu;
+	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+	const int n_words = simple_words(max_len);
+	const int warp_cap = simple_warp_bytes(max_len);
+	uint32_t *pk = reinterpret_cast<uint32_t *>(smem4) + t;                                     // [2][n_words][128]
+	uint8_t *stage = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem4) + 2 * n_words * kSimpleThreads) + wid * warp_cap;
+	const int64_t fw0 = (int64_t)blockIdx.x * kSimpleThreads + 32 * wid, f = fw0 + lane;
+	const int mb = cfg.multi_best_reads;
+	if (fw0 >= n_frags) return;
+
+	// ---- 4a. zero-fill the warp's bigtable slice (coalesced; the non-zero words are scattered at the end) ----
+	{
+		const int64_t nf = min((int64_t)32, n_frags - fw0);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)fw0 * mb);
+		const int total = (int)nf * mb * kResultWords;
+		if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+			uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+			const int n4 = total >> 2;
+			for (int i = lane; i < n4; i += 32) __stcs(d4 + i, make_uint4(0u, 0u, 0u, 0u));
+			for (int i = (n4 << 2) + lane; i < total; i += 32) __stcs(dst + i, 0u);
+		} else
+			for (int i = lane; i < total; i += 32) __stcs(dst + i, 0u);
+	}
+
+	// ---- 1. stage the text ----
+	bool active = f < n_frags, punt = false;
+	uint64_t o0 = 0;
+	int L = 0;
 	if (active) {
-		const uint64_t o0 = off[f] - text_origin;
+		o0 = off[f] - text_origin;
 		L = len[f];
-		if (o0 + (uint64_t)L > text_bytes || L > kMaxReadLen) {
+		if (o0 > text_bytes || (uint64_t)L > text_bytes - o0 || L > kMaxReadLen) {
 			atomicAdd(bad_reads, 1u);
 			active = false;
-		} else if (L > kSimpleMaxLen) {
-			punt = true;
-		} else if (L >= 16) {
-			uint32_t fw[kSimpleWords], rc[kSimpleWords];
-			if (!simple_pack(text + o0, L, fw, rc)) punt = true;
-			else {
-				int step;
-				applied = subread_schedule(L, GAP, cfg.total_subreads, &step);
-				SimpleClusters C;
-				if (!simple_pass<GAP>(ix, cfg, fw, L, applied, step, C)) punt = true;
+		} else if (L > kSimpleMaxLen || L > max_len) punt = true;
+	}
+	const bool want = active && !punt && L >= 16;
+	unsigned long long lo = want ? o0 : ~0ull, hi = want ? o0 + (uint64_t)L : 0ull;
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		lo = min(lo, __shfl_xor_sync(kFullMask, lo, d));
+		hi = max(hi, __shfl_xor_sync(kFullMask, hi, d));
+	}
+	unsigned so = 0;
+	if (hi > lo) {
+		const uint8_t *g0 = text + lo;
+		const unsigned head = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
+		if (hi - lo + head <= (unsigned long long)warp_cap) {
+			// the usual layout: the warp's reads lie back to back
+			const uint4 *g4 = reinterpret_cast<const uint4 *>(g0 - head);
+			const int n4 = (int)((hi - lo + head + 15) >> 4);
+			uint4 *s4 = reinterpret_cast<uint4 *>(stage);
+			for (int i = lane; i < n4; i += 32) s4[i] = __ldcs(g4 + i);
+			so = (unsigned)(o0 - lo) + head;
+		} else {
+			// scattered reads: every thread copies its own into a private slot
+			const int slot = ((warp_cap - 16) / 32) & ~3;
+			if (want) {
+				const uint8_t *g = text + o0;
+				const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(g) & 3u);
+				const int nw4 = (int)((mis + (unsigned)L + 3u) >> 2);
+				if (nw4 * 4 > slot) punt = true;
 				else {
-					simple_merge(cfg, C, 0, applied, res);
-					if (!simple_pass<GAP>(ix, cfg, rc, L, applied, step, C)) punt = true;
-					else simple_merge(cfg, C, 1, applied, res);
+					const uint32_t *gw = reinterpret_cast<const uint32_t *>(g - mis);
+					uint32_t *sw = reinterpret_cast<uint32_t *>(stage + lane * slot);
+					for (int i = 0; i < nw4; i++) sw[i] = __ldg(gw + i);
+					so = (unsigned)(lane * slot) + mis;
 				}
 			}
-		} else {
-			SimpleClusters C;
-			C.n = 0;
-			simple_merge(cfg, C, 0, 0, res);   // a read shorter than 16 bases: two empty passes
-			simple_merge(cfg, C, 1, 0, res);
 		}
 	}
-	// queue the punted fragments (one atomic per warp)
-	const unsigned pm = __ballot_sync(0xffffffffu, active && punt);
-	if (pm) {
-		uint32_t base = 0;
-		if (lane == __ffs(pm) - 1) base = atomicAdd(queue_count, (uint32_t)__popc(pm));
-		base = __shfl_sync(0xffffffffu, base, __ffs(pm) - 1);
-		if (active && punt) queue[base + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)f;
-	}
-	if (!active || punt) return;
+	__syncwarp();
 
-	const int mb = cfg.multi_best_reads;
-	ResultWords *dst = out + (size_t)f * mb;
-	for (int k = 0; k < mb; k++) {   // copy_vote_to_alignment_res image of each slot (core-junction.c:1058-1072)
-		uint32_t w[kResultWords];
+	// ---- 1b. pack both strands ----
+	const bool run = active && !punt && L >= 16;
+	if (run && !simple_pack(stage, so, L, pk, n_words)) punt = true;
+	__syncwarp();   // the staging area becomes the cluster store
+
+	// ---- 2./3. two strand passes ----
+	SimpleResult res[kMaxBest];
 #pragma unroll
-		for (int i = 0; i < kResultWords; i++) w[i] = 0;
-		const SimpleResult &r = res[k];
-		if (r.kind == 1) {
-			w[0] = r.pos;
-			w[1] = r.strand ? (uint32_t)kCoreNegStrand : 0u;
-			w[2] = (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16);
-			w[4] = (uint32_t)r.first_sub | ((uint32_t)r.last_sub << 16);
-			w[15] = (uint32_t)(uint16_t)r.cov_start | ((uint32_t)(uint16_t)r.cov_end << 16);
-		} else if (r.kind == 2) {
-			w[2] = (uint32_t)(uint16_t)r.used << 16;
+	for (int k = 0; k < kMaxBest; k++) { res[k].pos = 0; res[k].votes = 0; res[k].used = 0; res[k].meta = 0; res[k].cov = 0; }
+	SimpleClusters C;
+	C.base = reinterpret_cast<uint32_t *>(stage) + lane;
+	C.n = 0;
+	C.cap = kSimpleClusters;
+	if (active && !punt) {
+		if (L >= 16) {
+			int step;
+			const int applied = subread_schedule(L, GAP, cfg.total_subreads, &step);
+			if (!simple_pass<GAP>(ix, cfg, pk, L, applied, step, C)) punt = true;
+			else {
+				simple_merge<GAP>(cfg, C, 0, applied, step, res);
+				if (!simple_pass<GAP>(ix, cfg, pk + n_words * kSimpleThreads, L, applied, step, C)) punt = true;
+				else simple_merge<GAP>(cfg, C, 1, applied, step, res);
+			}
+		} else {
+			simple_merge<GAP>(cfg, C, 0, 0, 65536, res);   // a read shorter than 16 bases: two empty passes
+			simple_merge<GAP>(cfg, C, 1, 0, 65536, res);
 		}
+	}
+	__syncwarp();
+	// queue the punted fragments (one atomic per warp)
+	const unsigned pm = __ballot_sync(kFullMask, active && punt);
+	if (pm) {
+		uint32_t qb = 0;
+		if (lane == __ffs(pm) - 1) qb = atomicAdd(queue_count, (uint32_t)__popc(pm));
+		qb = __shfl_sync(kFullMask, qb, __ffs(pm) - 1);
+		if (active && punt) queue[qb + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)f;
+	}
+
+	// ---- 4b. the non-zero words (copy_vote_to_alignment_res image of each slot, core-junction.c:1058-1072); the
+	// __syncwarp() calls above order them after the warp's zero-fill ----
+	if (!active || punt) return;
+	ResultWords *dst = out + (size_t)f * mb;
 #pragma unroll
-		for (int i = 0; i < kResultWords; i++) dst[k].w[i] = w[i];
+	for (int k = 0; k < kMaxBest; k++) {
+		if (k >= mb) break;
+		const SimpleResult &r = res[k];
+		const uint32_t kind = r.meta & 0xffu;
+		if (kind == 1) {
+			__stcs(&dst[k].w[0], r.pos);
+			__stcs(&dst[k].w[1], ((r.meta >> 8) & 0xffu) ? (uint32_t)kCoreNegStrand : 0u);
+			__stcs(&dst[k].w[2], (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16));
+			__stcs(&dst[k].w[4], ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16));
+			__stcs(&dst[k].w[15], r.cov);
+		} else if (kind == 2) {
+			__stcs(&dst[k].w[2], (uint32_t)(uint16_t)r.used << 16);
+		}
 	}
 }
 

@@ -421,7 +421,7 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 				const uint32_t b = key - q * nb;
 				const int k16 = (int)(int16_t)q;
 				bool maybe = true;
-				if (ix.bloom) maybe = (__ldg(ix.bloom + b) >> (k16 & 15)) & 1;
+				if (ix.bloom) { const uint32_t m = bloom_bits(k16); maybe = ((uint32_t)__ldg(ix.bloom + b) & m) == m; }
 				if (maybe) {
 					int items = -1;
 					if (ix.records) {

@@ -252,3 +252,73 @@ def test_subjunc_junction_voting(name, mapper, golden_cases, golden_index_dir, o
     assert got2.tobytes() == ora2.tobytes()
     assert js["junc"].tobytes() == jo["junc"].tobytes()
     assert (js["big_margin"] == jo["big_margin"]).all()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "repeats", "full"])
+def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_path):
+    """Tier 0 (k_map_simple, one thread per fragment) only runs for single-end chunks on a zero bigtable without
+    verification -- the shape of the bench.  2 Mbp genome (uniform / repeat-rich / full index); error-free reads,
+    reads with errors, indels, Ns and mixed lengths up to 300 bp (beyond the tier's 256), lower-case and IUPAC
+    characters, read text with gaps between the reads.  Bit-exact against the oracle, with and without the tier."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    from subread_b200 import pack_reads
+    from subread_b200.binding import Mapper
+    from subread_b200.index_build import build_index
+    from subread_b200.reads import ReadChunk
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 4, 500000, seed=91, repeats=600 if kind == "repeats" else 0)
+    prefix = str(tmp_path / "idx")
+    build_index(fa, prefix, gapped=(kind != "full"), use_gpu=True)
+    mapper.index_load(prefix, 0)
+    idx = oracle_mod.OracleIndex(prefix)
+    params = VoteParams.defaults(False)
+    gen_data.write_reads(fa, str(tmp_path / "clean"), 40000, 150, 3, False, 0.0, 0.0, False, 0.0)
+    gen_data.write_reads(fa, str(tmp_path / "noisy"), 30000, 150, 4, False, 0.01, 0.1, True, 0.002)
+    gen_data.write_reads(fa, str(tmp_path / "short"), 10000, 50, 5, False, 0.005, 0.0, False, 0.0)
+    os.environ["SRCUDA_SIMPLE_TIER"] = "0"
+    try:
+        plain = Mapper(0)
+    finally:
+        del os.environ["SRCUDA_SIMPLE_TIER"]
+    plain.index_load(prefix, 0)
+    chunks = {n: load_fastq(str(tmp_path / f"{n}_R1.fastq")) for n in ("clean", "noisy", "short")}
+    # mixed lengths 16..300, odd characters, and a scattered layout (reads far apart, unordered offsets)
+    rng = np.random.default_rng(8)
+    _, seqs = gen_data.read_fasta(fa)
+    g = seqs[1]
+    odd = []
+    for i in range(3000):
+        L = int(rng.integers(16, 301))
+        s = int(rng.integers(0, g.shape[0] - L))
+        r = bytearray(g[s:s + L].tobytes())
+        if i % 7 == 0:
+            r[int(rng.integers(0, L))] = ord("acgtnRYU."[int(rng.integers(0, 9))])
+        if i % 11 == 0:
+            r = bytearray(gen_data.revcomp(np.frombuffer(bytes(r), dtype=np.uint8)).tobytes())
+        odd.append(bytes(r))
+    odd += [b"ACGT", b"A" * 15, b"", g[100:116].tobytes(), g[5000:6210].tobytes()]
+    chunks["odd"] = pack_reads(odd, None)
+    c = chunks["clean"]
+    n = 5000
+    text = np.full(n * 700 + 64, ord("#"), dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    for i in range(n):
+        o = 3 + i * 700 + int(rng.integers(0, 500))
+        off[i] = o
+        text[o:o + 150] = c.text[int(c.off[i]):int(c.off[i]) + 150]
+    off[n] = text.shape[0]
+    chunks["scattered"] = ReadChunk(text, off, np.full(n, 150, np.uint16), n, False, [])
+    for name, chunk in chunks.items():
+        ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, threads=8)
+        got, _ = mapper.vote_chunk(chunk, params)
+        t = mapper.timing()
+        ok, bad = used_slots_equal(got, ora)
+        assert ok, name + ": " + describe_mismatch(got, ora, bad)
+        assert got.tobytes() == ora.tobytes(), name
+        ref, _ = plain.vote_chunk(chunk, params)
+        assert ref.tobytes() == ora.tobytes(), name + " (tier 0 off)"
+        assert plain.timing().n_simple_punted == 0
+        if name in ("clean", "scattered") and kind != "repeats":
+            assert t.n_simple_punted < chunk.n_frags // 20, f"{name}: tier 0 punted {t.n_simple_punted} of {chunk.n_frags}"
+    plain.close()
