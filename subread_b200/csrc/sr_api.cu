@@ -161,6 +161,34 @@ __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *key
 	}
 }
 
+// Third accelerator, one thread per bucket: the "unique position" bitmap.  Bit v - start_base_offset is set when the
+// table holds exactly one item for the key of the 16-mer that the resident genome array shows at position v, and that
+// item is v.  Then gehash_go_X's lookup of that 16-mer returns the single position v (sorted-hashtable.c:947-981), which
+// the tier-0 kernel may conclude from the genome (25 MB for 100 Mbp, L2 resident) without touching the bucket.  The bit
+// is only set after the key rebuilt from (bucket, key16) has been compared with the genome's 16-mer, so it never says
+// more than the table itself.
+__global__ void k_build_uniq(const sr::DevIndex ix, uint32_t *bits)
+{
+	const uint32_t nb = ix.buckets_number;
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = ix.bucket_start[b], n = ix.bucket_start[b + 1] - lo;
+		for (uint32_t i = 0; i < n; i++) {
+			const int16_t k = ix.keys[lo + i];
+			if ((i > 0 && ix.keys[lo + i - 1] == k) || (i + 1 < n && ix.keys[lo + i + 1] == k)) continue;
+			const uint32_t v = ix.vals[lo + i];
+			if (v < ix.start_point || v - ix.start_point > ix.length - 16u || ix.length < 16u) continue;
+			const uint32_t p = v - ix.start_base_offset;
+			if (p >= ix.uniq_n) continue;
+			const uint32_t key = (uint32_t)(uint16_t)k * nb + b;
+			if (key / nb != (uint32_t)(uint16_t)k) continue;                  // (only a tiny table can wrap)
+			const uint32_t g = __funnelshift_r(ix.genome[p >> 4], ix.genome[(p >> 4) + 1], (p & 15u) * 2u);
+			uint32_t r = __brev(g);
+			r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
+			if (r == key) atomicOr(bits + (p >> 5), 1u << (p & 31u));
+		}
+	}
+}
+
 // Random 32-byte-sector gather: the "HBM-gather roofline" probe.
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_thread, uint32_t seed, uint32_t *sink)
 {
@@ -217,8 +245,10 @@ struct srcuda_handle {
 	sr::DevIndex ix{};
 	srcuda_index_desc desc{};
 	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
-	void *d_records = nullptr, *d_bloom = nullptr;
+	void *d_records = nullptr, *d_bloom = nullptr, *d_uniq = nullptr;
 	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both (SRCUDA_ACCEL)
+	bool use_uniq = false;         // SRCUDA_UNIQ=1 builds the unique-position bitmap: halves the DRAM traffic of tier 0 but costs more
+	                               // instructions than it saves while the kernel is issue-bound (profiles/), so it is off by default
 	bool l2_persist = true;        // keep the Bloom words resident in L2 (SRCUDA_L2_PERSIST=0 turns it off)
 	size_t l2_persist_max = 0, l2_window_max = 0;
 	const void *l2_policy_for = nullptr;   // Bloom array the streams' access-policy window currently covers
@@ -229,7 +259,7 @@ struct srcuda_handle {
 	srcuda_timing timing{};
 	bool force_slow = false;
 	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
-	int simple_smem_set[4] = {0, 0, 0, 0};  // dynamic shared memory already granted to k_map_simple<GAP>
+	int simple_smem_set[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // dynamic shared memory already granted to k_map_simple<GAP, UNIQ>
 	int64_t batch_frags = 1 << 20;
 	uint32_t *d_sink = nullptr;
 };
@@ -277,7 +307,8 @@ int ensure(srcuda_handle *h, DeviceBuf &b, size_t bytes)
 void free_index(srcuda_handle *h)
 {
 	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr);
-	cudaFree(h->d_records); cudaFree(h->d_bloom);
+	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_uniq);
+	h->d_uniq = nullptr;
 	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = h->d_records = h->d_bloom = nullptr;
 	h->has_index = false;
 	h->l2_policy_for = nullptr;
@@ -306,6 +337,22 @@ int build_accelerators(srcuda_handle *h)
 	h->ix.bloom = (const uint16_t *)h->d_bloom;
 	h->ix.records = h->d_records;
 	h->desc.device_bytes += (mode & 1 ? 2ull * nb : 0) + (mode & 2 ? 32ull * nb : 0);
+	h->ix.uniq_bits = nullptr;
+	h->ix.uniq_n = 0;
+	if ((mode & 3) == 3 && h->use_uniq) {
+		const uint64_t n_bits = (uint64_t)h->ix.length + (h->ix.start_point - h->ix.start_base_offset);
+		if (n_bits < 0xffffffffull && (n_bits >> 4) + 2 <= h->genome_words) {
+			const size_t words = (size_t)((n_bits + 31) / 32) + 4;
+			CU(h, cudaMalloc(&h->d_uniq, sizeof(uint32_t) * words));
+			CU(h, cudaMemset(h->d_uniq, 0, sizeof(uint32_t) * words));
+			h->ix.uniq_n = (uint32_t)n_bits;
+			k_build_uniq<<<h->sm_count * 8, 256>>>(h->ix, (uint32_t *)h->d_uniq);
+			CU(h, cudaGetLastError());
+			CU(h, cudaDeviceSynchronize());
+			h->ix.uniq_bits = (const uint32_t *)h->d_uniq;
+			h->desc.device_bytes += sizeof(uint32_t) * words;
+		}
+	}
 	return 0;
 }
 
@@ -425,20 +472,27 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		const int64_t blocks = (a.n_frags + threads - 1) / threads;
 		const int smem = sr::simple_smem_bytes(max_len);
 		uint32_t *q0 = (uint32_t *)bs.queue0.p;
+#define SR_LAUNCH_SIMPLE_U(G, U)                                                                                                     \
+	do {                                                                                                                             \
+		if (smem > h->simple_smem_set[G][U]) {                                                                                       \
+			CU(h, cudaFuncSetAttribute(sr::k_map_simple<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
+			h->simple_smem_set[G][U] = smem;                                                                                         \
+		}                                                                                                                            \
+		sr::k_map_simple<G, U><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off,    \
+		                                                              a.len, a.n_frags, max_len, a.out, q0, bs.counters + 2,       \
+		                                                              a.bad_reads);                                                \
+	} while (0)
 #define SR_LAUNCH_SIMPLE(G)                                                                                                          \
 	do {                                                                                                                             \
-		if (smem > h->simple_smem_set[G]) {                                                                                          \
-			CU(h, cudaFuncSetAttribute(sr::k_map_simple<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                      \
-			h->simple_smem_set[G] = smem;                                                                                            \
-		}                                                                                                                            \
-		sr::k_map_simple<G><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, a.len, \
-		                                                           a.n_frags, max_len, a.out, q0, bs.counters + 2, a.bad_reads);   \
+		if (h->ix.uniq_bits) SR_LAUNCH_SIMPLE_U(G, true);                                                                            \
+		else SR_LAUNCH_SIMPLE_U(G, false);                                                                                           \
 	} while (0)
 		switch (h->ix.index_gap) {
 		case 1: SR_LAUNCH_SIMPLE(1); break;
 		case 2: SR_LAUNCH_SIMPLE(2); break;
 		default: SR_LAUNCH_SIMPLE(3); break;
 		}
+#undef SR_LAUNCH_SIMPLE_U
 #undef SR_LAUNCH_SIMPLE
 		CU(h, cudaGetLastError());
 		h->timing.n_launches++;
@@ -524,6 +578,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	h->sm_count = prop.multiProcessorCount;
 	h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
 	h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+	const char *uq = getenv("SRCUDA_UNIQ");
+	if (uq) h->use_uniq = uq[0] == '1';
 	const char *lp = getenv("SRCUDA_L2_PERSIST");
 	if (lp && lp[0] == '0') h->l2_persist = false;
 	if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SRCUDA_ERR_CUDA, "cudaSetDevice(%d) failed", device); }

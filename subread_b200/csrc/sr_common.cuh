@@ -49,6 +49,8 @@ struct DevIndex {
 	// exact: a filter without false negatives and a re-packed copy of small buckets.
 	const uint16_t *bloom;         // per bucket: bloom_bits(key16) set for every key16 in the bucket; null = off
 	const void *records;           // per bucket 32 B (two uint4): see below; null = off
+	const uint32_t *uniq_bits;     // bit (v - start_base_offset) set: looking up the 16-mer at genome position v returns {v} and nothing else; null = off
+	uint32_t uniq_n;               // bits in uniq_bits
 };
 
 // 32-byte bucket record (one sector), n = items in the bucket (saturated at 0xffff):

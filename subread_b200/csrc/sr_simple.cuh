@@ -38,6 +38,16 @@
 #pragma once
 #include "sr_common.cuh"
 
+#ifndef SR_SIMPLE_PREFETCH
+#define SR_SIMPLE_PREFETCH 0   // prefetch.global.L2 of the survivors' records from the filter loop (A/B switch)
+#endif
+#ifndef SR_SIMPLE_MIN_BLOCKS
+#define SR_SIMPLE_MIN_BLOCKS 7  // resident blocks per SM the register allocation aims at (shared memory allows 7 at 150 bp)
+#endif
+#ifndef SR_SIMPLE_SMEM_OUT
+#define SR_SIMPLE_SMEM_OUT 0   // compose the warp's bigtable slice in shared memory and store whole sectors (A/B switch)
+#endif
+
 namespace sr {
 
 constexpr int kSimpleThreads = 128;                      // fragments (threads) per block
@@ -54,6 +64,8 @@ SR_HD int simple_warp_bytes(int max_len)
 	int stage = 32 * (((ml + 3) & ~3) + 4) + 32;                             // text of 32 reads (+ alignment slack)
 	const int clus = kSimpleClusters * kSimpleClusterWords * 32 * 4;         // the vote clusters reuse the staging area
 	if (stage < clus) stage = clus;
+	const int outb = 16 * kMaxBest * kResultWords * 4;                       // ... and later half a warp's bigtable slots
+	if (stage < outb) stage = outb;
 	return (stage + 15) & ~15;
 }
 SR_HD int simple_smem_bytes(int max_len) { return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_warp_bytes(max_len); }
@@ -156,7 +168,8 @@ __device__ __forceinline__ SimpleCluster simple_new_cluster(uint32_t kv, int l, 
 }
 
 // One hit on the general path (clusters in shared memory).  Returns false when the pass is not separable.
-__device__ __forceinline__ bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
+// (Rare path: a real call keeps the hot loop small.)
+__device__ __noinline__ bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
 {
 	if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;           // u32 wrap-around of the probe rows
 	int found = -1;
@@ -299,7 +312,7 @@ __device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r
 // more than twelve items -- is replayed on the general path, lookup by lookup in schedule order and position by
 // position in the reference's visit order.  Applying P's hits before the others is exact because a cluster does not
 // depend on the order of application.
-template <int GAP>
+template <int GAP, bool UNIQ>
 __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
                                             SimpleClusters &C)
 {
@@ -343,41 +356,65 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					const uint32_t m = bloom_bits((int)bq[u]);
 					const bool in = g + u / GAP < n_sub && (word[u] & m) == m;
 					mask |= (in ? 1u : 0u) << ((g * GAP + u) & 31);
+#if SR_SIMPLE_PREFETCH
 					if (in && records) prefetch_l2(records + 2 * (size_t)bw[u]);
+#endif
 				}
 			}
 		}
 		// ---- (2) survivors: single positions of the primary cluster ----
+		// One step ahead of the survivor being applied, the loads of the next one are already under way: its bucket
+		// record, or -- once P exists and the index has the unique-position bitmap -- the bitmap word and the two genome
+		// words at P.kv + offset.  If the genome shows the survivor's own 16-mer there and the bit says that this 16-mer
+		// has exactly that one position in the table, the lookup is known to return it and the bucket is never read.
 		unsigned defer = mask;
 		if (records) {
 			defer = 0;
 			Record8 rn;
-			int i_next = -1, o_next = 0, sub_next = 0, k16_next = 0;
-			if (mask) {
+			int i_next = -1, o_next = 0, sub_next = 0, mode_next = 0;
+			uint32_t key_next = 0, q_next = 0, p_next = 0;
+			auto issue = [&]() {
+				i_next = -1;
+				if (!mask) return;
 				i_next = __ffs(mask) - 1;
 				mask &= mask - 1;
 				o_next = simple_offset<GAP>(base + i_next, step, &sub_next);
-				const uint32_t key = simple_key(pk, o_next);
-				const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
-				k16_next = (int)(int16_t)q;
-				rn = ld_record(records, key - q * nb);
-			}
-			while (i_next >= 0) {
-				const Record8 r = rn;
-				const int i = i_next, o = o_next, sub = sub_next, k16 = k16_next, l = base + i;
-				i_next = -1;
-				if (mask) {                                              // the next record travels while this one is applied
-					i_next = __ffs(mask) - 1;
-					mask &= mask - 1;
-					o_next = simple_offset<GAP>(base + i_next, step, &sub_next);
-					const uint32_t key = simple_key(pk, o_next);
-					const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
-					k16_next = (int)(int16_t)q;
-					rn = ld_record(records, key - q * nb);
+				key_next = simple_key(pk, o_next);
+				q_next = (uint32_t)__umul64hi((uint64_t)key_next, magic);
+				mode_next = 0;
+				if (UNIQ && have_p && ix.uniq_bits) {
+					p_next = P.kv + (uint32_t)o_next - ix.start_base_offset;
+					if (p_next < ix.uniq_n) {
+						mode_next = 1;
+						rn.w[0] = __ldg(ix.uniq_bits + (p_next >> 5));
+						rn.w[1] = __ldg(ix.genome + (p_next >> 4));
+						rn.w[2] = __ldg(ix.genome + (p_next >> 4) + 1);
+					}
 				}
-				uint32_t value = 0;
-				const int kind = simple_probe(ix, r, k16, &value);
-				const uint32_t kv = value - (uint32_t)o;
+				if (mode_next == 0) rn = ld_record(records, key_next - q_next * nb);
+			};
+			issue();
+			while (i_next >= 0) {
+				Record8 r = rn;
+				const int i = i_next, o = o_next, sub = sub_next, l = base + i, mode = mode_next;
+				const uint32_t key = key_next, q = q_next, p = p_next;
+				issue();
+				int kind;
+				uint32_t kv;
+				bool proven = false;
+				if (UNIQ && mode == 1) {
+					const uint32_t g = __funnelshift_r(r.w[1], r.w[2], (p & 15u) * 2u);
+					uint32_t gk = __brev(g);
+					gk = ((gk & 0x55555555u) << 1) | ((gk >> 1) & 0x55555555u);
+					proven = ((r.w[0] >> (p & 31u)) & 1u) && gk == key;
+					if (!proven) r = ld_record(records, key - q * nb);
+				}
+				if (proven) { kind = 1; kv = P.kv; }
+				else {
+					uint32_t value = 0;
+					kind = simple_probe(ix, r, (int)(int16_t)q, &value);
+					kv = value - (uint32_t)o;
+				}
 				if (kind == 1 && !have_p && C.n == 0) {                  // the first position of the pass founds P
 					if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
 					P = simple_new_cluster(kv, l, 0, sub, low, high);
@@ -468,6 +505,8 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 		}
 	}
 	if (have_p) C.put(0, P);
+#pragma unroll 1
+	for (int c = 0; c < C.n; c++) C.w(c, 2) = (uint32_t)C.votes(c);   // the subread sets have served: word 2 becomes the vote count
 	return true;
 }
 
@@ -490,13 +529,15 @@ __device__ __forceinline__ void simple_update_top(int ts, int &t0, int &t1, int 
 
 // process_voting_junction_PE_topK for one single-end pass over a separable table (core-junction.c:2199-2530,
 // the SE branch :2436-2495) and the hand-over logic of do_voting (core.c:3212-3226).  res[] is fully unrolled so
-// that it stays in registers.
+// that it stays in registers; the loops over clusters are kept rolled (small code matters more than their speed).
+// simple_pass has left every cluster's vote count in its word 2.
 template <int GAP>
 __device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const SimpleClusters &C, int strand, int applied, int step, SimpleResult (&res)[kMaxBest])
 {
 	const int mb = cfg.multi_best_reads, ts = cfg.top_scores;
 	int max_vote = 0;
-	for (int c = 0; c < C.n; c++) max_vote = max(max_vote, C.votes(c));
+#pragma unroll 1
+	for (int c = 0; c < C.n; c++) max_vote = max(max_vote, (int)C.w(c, 2));
 	if (max_vote < cfg.min_first) {                      // core.c:3217-3225
 		if (res[0].votes < 1) {
 			if ((res[0].meta & 0xffu) == 0) { res[0].meta = 2u; res[0].used = 0; }
@@ -505,13 +546,16 @@ __device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const Simple
 		return;
 	}
 	int t0 = 0, t1 = 0, t2 = 0;
-	for (int c = 0; c < C.n; c++) {
-		const int v = C.votes(c);
+#pragma unroll 1
+	for (int c = 0; c < C.n + kMaxBest; c++) {           // the table's slots, then the slots the bigtable already holds
+		int v;
+		if (c < C.n) v = (int)C.w(c, 2);
+		else {
+			const int k = c - C.n;
+			v = k >= mb ? 0 : (k == 0 ? res[0].votes : (k == 1 ? res[1].votes : res[2].votes));
+		}
 		if (v > 0) simple_update_top(ts, t0, t1, t2, v);
 	}
-#pragma unroll
-	for (int k = 0; k < kMaxBest; k++)
-		if (k < mb && res[k].votes > 0) simple_update_top(ts, t0, t1, t2, res[k].votes);
 
 	// The reference first lists the candidates level by level (:2251-2330) and then consumes the list in order
 	// (:2436-2495); consuming each candidate as soon as it is listed is the same thing.
@@ -532,15 +576,18 @@ __device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const Simple
 			if (k == cursor) tmp[k] = r;
 		cursor++;
 	};
+#pragma unroll 1
 	for (int lv = 0; lv < ts; lv++) {
 		if (n >= max_simples) break;
 		const int want = lv == 0 ? t0 : (lv == 1 ? t1 : t2);
 		if (want < 1 || t0 - want > cfg.max_vote_number_cutoff) break;
 		unsigned done = 0;
+#pragma unroll 1
 		for (;;) {                                       // slots of this level in (row, j) order = the reference's i, j loops
 			int best = -1, best_key = 0x7fffffff;
+#pragma unroll 1
 			for (int c = 0; c < C.n; c++)
-				if (!((done >> c) & 1u) && C.votes(c) == want) {
+				if (!((done >> c) & 1u) && (int)C.w(c, 2) == want) {
 					const int key = C.order(c);
 					if (key < best_key) { best_key = key; best = c; }
 				}
@@ -583,8 +630,8 @@ __device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const Simple
 // zero.  Writes the fragment's result slots, or queues the fragment for the warp kernel (its slots are then zero).
 // Every warp works on its own 32 fragments and its own slice of shared memory: there is no block-wide barrier.
 // Dynamic shared memory: simple_smem_bytes(max_len).
-template <int GAP>
-__global__ void __launch_bounds__(kSimpleThreads)
+template <int GAP, bool UNIQ>
+__global__ void __launch_bounds__(kSimpleThreads, SR_SIMPLE_MIN_BLOCKS)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
              const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, ResultWords *out, uint32_t *queue, uint32_t *queue_count,
              uint32_t *bad_reads)
@@ -599,20 +646,6 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	const int64_t fw0 = (int64_t)blockIdx.x * kSimpleThreads + 32 * wid, f = fw0 + lane;
 	const int mb = cfg.multi_best_reads;
 	if (fw0 >= n_frags) return;
-
-	// ---- 4a. zero-fill the warp's bigtable slice (coalesced; the non-zero words are scattered at the end) ----
-	{
-		const int64_t nf = min((int64_t)32, n_frags - fw0);
-		uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)fw0 * mb);
-		const int total = (int)nf * mb * kResultWords;
-		if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-			uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-			const int n4 = total >> 2;
-			for (int i = lane; i < n4; i += 32) __stcs(d4 + i, make_uint4(0u, 0u, 0u, 0u));
-			for (int i = (n4 << 2) + lane; i < total; i += 32) __stcs(dst + i, 0u);
-		} else
-			for (int i = lane; i < total; i += 32) __stcs(dst + i, 0u);
-	}
 
 	// ---- 1. stage the text ----
 	bool active = f < n_frags, punt = false;
@@ -642,6 +675,7 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 			const uint4 *g4 = reinterpret_cast<const uint4 *>(g0 - head);
 			const int n4 = (int)((hi - lo + head + 15) >> 4);
 			uint4 *s4 = reinterpret_cast<uint4 *>(stage);
+#pragma unroll 2
 			for (int i = lane; i < n4; i += 32) s4[i] = __ldcs(g4 + i);
 			so = (unsigned)(o0 - lo) + head;
 		} else {
@@ -655,6 +689,7 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 				else {
 					const uint32_t *gw = reinterpret_cast<const uint32_t *>(g - mis);
 					uint32_t *sw = reinterpret_cast<uint32_t *>(stage + lane * slot);
+#pragma unroll 1
 					for (int i = 0; i < nw4; i++) sw[i] = __ldg(gw + i);
 					so = (unsigned)(lane * slot) + mis;
 				}
@@ -677,18 +712,13 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	C.n = 0;
 	C.cap = kSimpleClusters;
 	if (active && !punt) {
-		if (L >= 16) {
-			int step;
-			const int applied = subread_schedule(L, GAP, cfg.total_subreads, &step);
-			if (!simple_pass<GAP>(ix, cfg, pk, L, applied, step, C)) punt = true;
-			else {
-				simple_merge<GAP>(cfg, C, 0, applied, step, res);
-				if (!simple_pass<GAP>(ix, cfg, pk + n_words * kSimpleThreads, L, applied, step, C)) punt = true;
-				else simple_merge<GAP>(cfg, C, 1, applied, step, res);
-			}
-		} else {
-			simple_merge<GAP>(cfg, C, 0, 0, 65536, res);   // a read shorter than 16 bases: two empty passes
-			simple_merge<GAP>(cfg, C, 1, 0, 65536, res);
+		// a read shorter than 16 bases goes through two empty passes (core.c:3116)
+		int step = 65536;
+		const int applied = L >= 16 ? subread_schedule(L, GAP, cfg.total_subreads, &step) : 0;
+#pragma unroll 1
+		for (int strand = 0; strand < 2 && !punt; strand++) {        // one copy of the pass in the instruction cache
+			if (!simple_pass<GAP, UNIQ>(ix, cfg, pk + strand * n_words * kSimpleThreads, L, applied, step, C)) punt = true;
+			else simple_merge<GAP>(cfg, C, strand, applied, step, res);
 		}
 	}
 	__syncwarp();
@@ -701,8 +731,75 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 		if (active && punt) queue[qb + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)f;
 	}
 
-	// ---- 4b. the non-zero words (copy_vote_to_alignment_res image of each slot, core-junction.c:1058-1072); the
-	// __syncwarp() calls above order them after the warp's zero-fill ----
+	// ---- 4. the warp's bigtable slice (copy_vote_to_alignment_res image of each slot, core-junction.c:1058-1072) ----
+#if SR_SIMPLE_SMEM_OUT
+	// Composed in the warp's shared area (the clusters are dead now) and stored as whole 16-byte pieces, half a warp
+	// at a time: no partial-sector writes, so nothing has to be read back from DRAM to merge them.
+	{
+		const int64_t nf = min((int64_t)32, n_frags - fw0);
+		uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
+		uint32_t *gdst = reinterpret_cast<uint32_t *>(out + (size_t)fw0 * mb);
+		const int words_per_frag = mb * kResultWords;
+		const bool vec = (reinterpret_cast<uintptr_t>(gdst) & 15u) == 0 && ((16 * words_per_frag) & 3) == 0;
+#pragma unroll 1
+		for (int half = 0; half < 2; half++) {
+			const int first = 16 * half, cnt = (int)min((int64_t)16, nf - first);
+			if (cnt <= 0) break;
+			const int total = cnt * words_per_frag;
+			__syncwarp();
+			for (int i = lane; i < total; i += 32) sw[i] = 0u;
+			__syncwarp();
+			if (active && !punt && lane >= first && lane < first + 16) {
+				uint32_t *d = sw + (lane - first) * words_per_frag;
+#pragma unroll
+				for (int k = 0; k < kMaxBest; k++) {
+					if (k >= mb) break;
+					const SimpleResult &r = res[k];
+					const uint32_t kind = r.meta & 0xffu;
+					uint32_t *dk = d + k * kResultWords;
+					if (kind == 1) {
+						dk[0] = r.pos;
+						dk[1] = ((r.meta >> 8) & 0xffu) ? (uint32_t)kCoreNegStrand : 0u;
+						dk[2] = (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16);
+						dk[4] = ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16);
+						dk[15] = r.cov;
+					} else if (kind == 2)
+						dk[2] = (uint32_t)(uint16_t)r.used << 16;
+				}
+			}
+			__syncwarp();
+			uint32_t *g = gdst + first * words_per_frag;
+			if (vec) {
+				const uint4 *s4 = reinterpret_cast<const uint4 *>(sw);
+				uint4 *g4 = reinterpret_cast<uint4 *>(g);
+				const int n4 = total >> 2;
+				for (int i = lane; i < n4; i += 32) __stcs(g4 + i, s4[i]);
+				for (int i = (n4 << 2) + lane; i < total; i += 32) __stcs(g + i, sw[i]);
+			} else
+				for (int i = lane; i < total; i += 32) __stcs(g + i, sw[i]);
+		}
+	}
+#else
+	// zero-fill the warp's slice with coalesced stores, then scatter the few non-zero words on top while the lines are
+	// still in L2 (done early, the zeroed lines are written back before the scatter and every 4-byte store has to read
+	// its sector back from DRAM)
+	{
+		const int64_t nf = min((int64_t)32, n_frags - fw0);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)fw0 * mb);
+		const int total = (int)nf * mb * kResultWords;
+		if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+			uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+			const int n4 = total >> 2;
+#pragma unroll 2
+			for (int i = lane; i < n4; i += 32) __stcs(d4 + i, make_uint4(0u, 0u, 0u, 0u));
+#pragma unroll 1
+			for (int i = (n4 << 2) + lane; i < total; i += 32) __stcs(dst + i, 0u);
+		} else {
+#pragma unroll 1
+			for (int i = lane; i < total; i += 32) __stcs(dst + i, 0u);
+		}
+	}
+	__syncwarp();   // orders the scattered stores after the zero-fill
 	if (!active || punt) return;
 	ResultWords *dst = out + (size_t)f * mb;
 #pragma unroll
@@ -720,6 +817,7 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 			__stcs(&dst[k].w[2], (uint32_t)(uint16_t)r.used << 16);
 		}
 	}
+#endif
 }
 
 #endif  // __CUDACC__
