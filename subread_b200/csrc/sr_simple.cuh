@@ -42,7 +42,10 @@
 #define SR_SIMPLE_PREFETCH 0   // prefetch.global.L2 of the survivors' records from the filter loop (A/B switch)
 #endif
 #ifndef SR_SIMPLE_MIN_BLOCKS
-#define SR_SIMPLE_MIN_BLOCKS 7  // resident blocks per SM the register allocation aims at (shared memory allows 7 at 150 bp)
+#define SR_SIMPLE_MIN_BLOCKS 6  // resident blocks per SM the register allocation aims at: 84 registers, no spills (7 and 8 measured slower)
+#endif
+#ifndef SR_SIMPLE_HIT_INLINE
+#define SR_SIMPLE_HIT_INLINE __forceinline__   // the general-path hit: inlined (a real call costs spills around it; A/B switch)
 #endif
 #ifndef SR_SIMPLE_SMEM_OUT
 #define SR_SIMPLE_SMEM_OUT 0   // compose the warp's bigtable slice in shared memory and store whole sectors (A/B switch)
@@ -169,7 +172,7 @@ __device__ __forceinline__ SimpleCluster simple_new_cluster(uint32_t kv, int l, 
 
 // One hit on the general path (clusters in shared memory).  Returns false when the pass is not separable.
 // (Rare path: a real call keeps the hot loop small.)
-__device__ __noinline__ bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
+__device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
 {
 	if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;           // u32 wrap-around of the probe rows
 	int found = -1;

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""tools/ncu_regions.py REPORT -- executed instructions / stall samples of k_map_simple grouped by code region of sr_simple.cuh."""
+import subprocess, re, collections, sys
+rep = sys.argv[1]
+out = subprocess.run(["python", "tools/ncu_lines.py", rep, "2000"], capture_output=True, text=True).stdout.split("\n")
+src = open('subread_b200/csrc/sr_simple.cuh').read().split("\n")
+def find(pat):
+    for i, l in enumerate(src):
+        if pat in l:
+            return i + 1
+marks = [("structs", 1), ("simple_hit", find("bool simple_hit(")), ("pack", find("bool simple_pack")), ("offsets/key", find("int simple_sub_offset")), ("probe", find("int simple_probe")),
+         ("pass-setup", find("bool simple_pass")), ("filter", find("// ---- (1) filter ----")), ("S1", find("// ---- (2) survivors")), ("S2", find("// ---- (3) everything else")),
+         ("update_top", find("// update_top_three")), ("merge", find("void simple_merge")), ("kernel", find("k_map_simple(const DevIndex ix"))]
+agg = collections.OrderedDict((m[0], [0, 0, 0]) for m in marks)
+other = [0, 0]
+print(out[0])
+for l in out[1:]:
+    m = re.match(r"\s*([\d.]+)% inst\s+([\d.]+)% smp\s+thr/inst\s+([\d.]+)\s+(\S+):(\d+)", l)
+    if not m:
+        continue
+    inst, smp, eff, f, line = float(m[1]), float(m[2]), float(m[3]), m[4], int(m[5])
+    text = l.split(f"{f}:{line}")[1].strip()[:25]
+    if line - 1 < len(src) and text and text in src[line - 1]:
+        name = [mk[0] for mk in marks if mk[1] and mk[1] <= line][-1]
+        agg[name][0] += inst; agg[name][1] += smp; agg[name][2] += inst * eff
+    else:
+        other[0] += inst; other[1] += smp
+for k, v in agg.items():
+    print(f"{k:14s} inst {v[0]:5.1f}%  smp {v[1]:5.1f}%  thr/inst {v[2]/max(v[0],1e-9):5.1f}")
+print("other files    inst %5.1f%%  smp %5.1f%%" % tuple(other))
