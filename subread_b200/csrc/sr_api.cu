@@ -134,14 +134,14 @@ k_map_scalar(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int use
 // Derives the two lookup accelerators from the resident SoA index, one thread per bucket:
 // a 16-bit Bloom word (bloom_bits of every key16) and the 32-byte inline record (sr_common.cuh).
 __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, uint4 *records,
-                                uint16_t *bloom)
+                                sr::bloom_t *bloom)
 {
 	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
 		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
 		if (bloom) {
 			uint32_t bl = 0;
 			for (uint32_t i = 0; i < n; i++) bl |= sr::bloom_bits((int)keys[lo + i]);
-			bloom[b] = (uint16_t)bl;
+			bloom[b] = (sr::bloom_t)bl;
 		}
 		if (records) {
 			uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -200,7 +200,8 @@ __global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_t
 		for (int u = 0; u < 8; u++) {
 			x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 29;  // cheap mixer
 			uint64_t s = x % n_sectors;
-			v[u] = __ldg(table + 2 * s);
+			const Record8 r = ld_record(table, (uint32_t)s);   // the lookup's own load: 64 bytes per DRAM miss
+			v[u] = make_uint4(r.w[0], r.w[1], r.w[6], r.w[7]);
 		}
 #pragma unroll
 		for (int u = 0; u < 8; u++) acc ^= v[u].x ^ v[u].w;
@@ -327,16 +328,16 @@ int build_accelerators(srcuda_handle *h)
 	if (mode < 0) mode = mean <= 4.0 ? 3 : 0;
 	h->ix.bloom = nullptr;
 	h->ix.records = nullptr;
-	if (mode & 1) CU(h, cudaMalloc(&h->d_bloom, sizeof(uint16_t) * (size_t)nb));
+	if (mode & 1) CU(h, cudaMalloc(&h->d_bloom, sizeof(sr::bloom_t) * (size_t)nb));
 	if (mode & 2) CU(h, cudaMalloc(&h->d_records, 32 * (size_t)nb));
 	if (mode) {
-		sr::k_build_records<<<h->sm_count * 8, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, (uint4 *)h->d_records, (uint16_t *)h->d_bloom);
+		sr::k_build_records<<<h->sm_count * 8, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, (uint4 *)h->d_records, (sr::bloom_t *)h->d_bloom);
 		CU(h, cudaGetLastError());
 		CU(h, cudaDeviceSynchronize());
 	}
-	h->ix.bloom = (const uint16_t *)h->d_bloom;
+	h->ix.bloom = (const sr::bloom_t *)h->d_bloom;
 	h->ix.records = h->d_records;
-	h->desc.device_bytes += (mode & 1 ? 2ull * nb : 0) + (mode & 2 ? 32ull * nb : 0);
+	h->desc.device_bytes += (mode & 1 ? (uint64_t)sizeof(sr::bloom_t) * nb : 0) + (mode & 2 ? 32ull * nb : 0);
 	h->ix.uniq_bits = nullptr;
 	h->ix.uniq_n = 0;
 	if ((mode & 3) == 3 && h->use_uniq) {
@@ -518,7 +519,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 void apply_l2_policy(srcuda_handle *h)
 {
 	if (!h->l2_persist || !h->d_bloom || h->l2_policy_for == h->d_bloom || !h->l2_persist_max || !h->l2_window_max) return;
-	const size_t bytes = sizeof(uint16_t) * (size_t)h->ix.buckets_number;
+	const size_t bytes = sizeof(sr::bloom_t) * (size_t)h->ix.buckets_number;
 	const size_t carve = std::min(bytes, h->l2_persist_max), window = std::min(bytes, h->l2_window_max);
 	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
 	cudaStreamAttrValue v;

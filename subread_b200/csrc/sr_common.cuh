@@ -32,6 +32,16 @@ constexpr int kMaxSimples = 64;      // max_vote_simples PE (core.c:4077)
 constexpr int kMaxCombos = 16;       // max_vote_combinations, raised by -B up to 16
 constexpr int kResultWords = 17;     // sizeof(mapping_result_t) / 4
 
+// Width of the per-bucket Bloom word (A/B switch): 16 bits = 32 MB for the one-block gapped table, 8 bits = 16 MB.
+#ifndef SR_BLOOM_BITS
+#define SR_BLOOM_BITS 16
+#endif
+#if SR_BLOOM_BITS == 8
+typedef uint8_t bloom_t;
+#else
+typedef uint16_t bloom_t;
+#endif
+
 // One index block resident in HBM (SoA form of gehash_t + gene_value_index_t + gene_offset_t).
 struct DevIndex {
 	uint32_t buckets_number;
@@ -47,7 +57,7 @@ struct DevIndex {
 	const uint32_t *chr_offsets;   // total_offsets cumulative END offsets
 	// Lookup accelerators derived on the device at load time (sr_api.cu, k_build_records); both are
 	// exact: a filter without false negatives and a re-packed copy of small buckets.
-	const uint16_t *bloom;         // per bucket: bloom_bits(key16) set for every key16 in the bucket; null = off
+	const bloom_t *bloom;          // per bucket: bloom_bits(key16) set for every key16 in the bucket; null = off
 	const void *records;           // per bucket 32 B (two uint4): see below; null = off
 	const uint32_t *uniq_bits;     // bit (v - start_base_offset) set: looking up the 16-mer at genome position v returns {v} and nothing else; null = off
 	uint32_t uniq_n;               // bits in uniq_bits
@@ -65,7 +75,11 @@ constexpr int kRecordKeys = 12;
 SR_HD uint32_t bloom_bits(int k16)
 {
 	const uint32_t q = (uint32_t)k16;
+#if SR_BLOOM_BITS == 8
+	return (1u << (q & 7u)) | (1u << ((q >> 3) & 7u));
+#else
 	return (1u << (q & 15u)) | (1u << ((q >> 4) & 15u));
+#endif
 }
 
 // The voting scalars, validated and pre-digested on the host (see srcuda_params).
@@ -83,6 +97,37 @@ struct VoteConfig {
 // subjunc_result_t (core.h:397-410) as four little-endian words:
 //  w0 split_point,minor_votes | w1 double_indel_offset,indel_at_junction,small_inc,large_inc | w2 minor_position
 //  w3 minor_coverage_start,minor_coverage_end
+#if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
+// Gather loads.  Measured on B200 (tools/micro/sector_fetch*.cu, profiles/): a load that misses L2 pulls the whole
+// 128-byte line from DRAM (3.6 sectors, 107 B per random 32-byte record; cudaLimitMaxL2FetchGranularity changes
+// nothing), unless the instruction carries the .L2::64B prefetch size -- then two sectors (58 B).  Every random
+// single-sector access of the lookup (bucket record, bucket header, positions) therefore asks for 64 B.
+#ifndef SR_GATHER_64B
+#define SR_GATHER_64B 1
+#endif
+#if SR_GATHER_64B
+#define SR_L2PF ".L2::64B"
+#else
+#define SR_L2PF ""
+#endif
+__device__ __forceinline__ uint32_t ld_gather(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.global.nc" SR_L2PF ".u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+// One 32-byte bucket record in a single 256-bit load (sm_100), streaming: not kept in L1, first to leave L2.
+struct __align__(32) Record8 { uint32_t w[8]; };
+__device__ __forceinline__ Record8 ld_record(const uint4 *records, uint32_t b)
+{
+	Record8 r;
+	asm volatile("ld.global.L1::no_allocate.L2::evict_first" SR_L2PF ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+	             : "l"(records + 2 * (size_t)b));
+	return r;
+}
+#endif
+
 struct JuncWords { uint32_t w[4]; };
 constexpr int kBigMarginU16 = 27;    // bigtable_cached_result_t.big_margin_data, core.h:453
 constexpr int kConfirmWindow = 17;   // JUNCTION_CONFIRM_WINDOW core-junction.c:3569

@@ -139,21 +139,17 @@ __device__ __forceinline__ uint64_t policy_evict_last()
 	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 	return pol;
 }
-__device__ __forceinline__ uint32_t ld_bloom(const uint16_t *p, uint64_t pol)
+__device__ __forceinline__ uint32_t ld_bloom(const bloom_t *p, uint64_t pol)
 {
+#if SR_BLOOM_BITS == 8
+	uint32_t v;
+	asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+	return v & 0xffu;
+#else
 	uint16_t v;
 	asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
 	return v;
-}
-// One 32-byte bucket record in a single 256-bit load (sm_100), streaming.
-struct __align__(32) Record8 { uint32_t w[8]; };
-__device__ __forceinline__ Record8 ld_record(const uint4 *records, uint32_t b)
-{
-	Record8 r;
-	asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
-	             : "l"(records + 2 * (size_t)b));
-	return r;
+#endif
 }
 
 // A fresh cluster for the hit (kv, lookup l, visit index u) of subread `sub`.
@@ -299,7 +295,7 @@ __device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r
 			lt += (i < n && k < k16) ? 1 : 0;
 			le += (i < n && k <= k16) ? 1 : 0;
 		}
-		if (le - lt == 1) *value = __ldg(ix.vals + r.w[1] + lt);
+		if (le - lt == 1) *value = ld_gather(ix.vals + r.w[1] + lt);
 		return min(le - lt, 2);
 	}
 	return 2;
@@ -477,8 +473,8 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					}
 				}
 				if (in_arrays) {                                         // a bucket with more than 5 items, or no records at all
-					const uint32_t lo = __ldg(ix.bucket_start + b);
-					const int items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
+					const uint32_t lo = ld_gather(ix.bucket_start + b);
+					const int items = (int)(ld_gather(ix.bucket_start + b + 1) - lo);
 					if (items <= 0) continue;
 					const int16_t *kp = ix.keys + lo;
 					int imin = 0, imax = items - 1, at;
@@ -499,7 +495,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					if (h > C.cap) return false;                         // cannot stay separable
 					for (int u = 0; u < h; u++) {
 						const int idx = u < nfwd ? at + u : at - 1 - (u - nfwd);
-						const uint32_t v = __ldg(ix.vals + lo + idx);
+						const uint32_t v = ld_gather(ix.vals + lo + idx);
 						if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) return false;
 					}
 				}

@@ -426,8 +426,8 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 					int items = -1;
 					if (ix.records) {
 						// one 32-byte sector holds the whole bucket when it has <= 5 items
-						const uint4 *rp = reinterpret_cast<const uint4 *>(ix.records) + 2 * (size_t)b;
-						const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+						const Record8 rec = ld_record(reinterpret_cast<const uint4 *>(ix.records), b);
+						const uint4 r0 = make_uint4(rec.w[0], rec.w[1], rec.w[2], rec.w[3]), r1 = make_uint4(rec.w[4], rec.w[5], rec.w[6], rec.w[7]);
 						const int n = (int)(r0.x & 0xffffu);
 						if (n <= kInlineItems) {
 							items = 0;
@@ -448,13 +448,13 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 								h = le - lt;
 								land = at - lt;
 								firstval = at == 0 ? r0.w : (at == 1 ? r1.x : (at == 2 ? r1.y : (at == 3 ? r1.z : r1.w)));
-								if (h > 1) run_abs = __ldg(ix.bucket_start + b) + (uint32_t)lt;
+								if (h > 1) run_abs = ld_gather(ix.bucket_start + b) + (uint32_t)lt;
 							}
 						}
 					}
 					if (items < 0) {
-						const uint32_t lo = __ldg(ix.bucket_start + b);
-						items = (int)(__ldg(ix.bucket_start + b + 1) - lo);
+						const uint32_t lo = ld_gather(ix.bucket_start + b);
+						items = (int)(ld_gather(ix.bucket_start + b + 1) - lo);
 						// (a record of a bucket with more than 5 items only carries its size)
 						if (items > 0) {
 							const int16_t *kp = ix.keys + lo;
@@ -475,7 +475,7 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 								h = e - s;
 								land = at - s;
 								run_abs = lo + (uint32_t)s;
-								firstval = __ldg(ix.vals + lo + at);
+								firstval = ld_gather(ix.vals + lo + at);
 							}
 						}
 					}
@@ -517,7 +517,7 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 					uint32_t v = first_s;
 					if (h_s > 1 && tt < h_s) {
 						int idx = tt < nfwd ? land_s + tt : land_s - 1 - (tt - nfwd);
-						v = __ldg(ix.vals + run_s + idx);
+						v = ld_gather(ix.vals + run_s + idx);
 					}
 					const int cnt = min(32, h_s - c);
 					for (int u = 0; u < cnt; u++) {
