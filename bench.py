@@ -303,7 +303,7 @@ def main():
 
     def step_device():
         # first index block of a chunk: the bigtable starts zeroed (core-bigtable.c:96), so it is not read
-        m.vote_chunk_device(params, d_text.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), R, False, READ_LEN, d_out.data_ptr(),
+        m.vote_chunk_device(params, d_text.data_ptr(), d_text.numel(), d_off.data_ptr(), d_len.data_ptr(), R, False, READ_LEN, d_out.data_ptr(),
                             out_is_zero=True)
         return m.timing()
 

@@ -204,11 +204,12 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
                       uint16_t *out_verify);
 
 /* Same computation with every buffer already resident on the handle's GPU (device pointers);
- * no host<->device traffic.  With out_align_is_zero != 0 the bigtable slice is not read (it is
+ * no host<->device traffic.  d_text_bytes is the size of the buffer at d_text: reads whose
+ * (off, len) leave it are reported as an error instead of being dereferenced.  With out_align_is_zero != 0 the bigtable slice is not read (it is
  * treated as all zero, the state of a chunk's first index block) and every slot is written.
  * Used by bench.py for the HBM-resident figure. */
-int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, const char *d_text, const uint64_t *d_off,
-                             const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len, int out_align_is_zero,
+int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, const char *d_text, uint64_t d_text_bytes,
+                             const uint64_t *d_off, const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len, int out_align_is_zero,
                              srcuda_mapping_result *d_out_align, srcuda_subjunc_result *d_out_junc,
                              uint16_t *d_out_big_margin, uint16_t *d_out_verify);
 

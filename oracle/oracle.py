@@ -88,9 +88,35 @@ class OracleIndex:
         if rc:
             raise RuntimeError(f"or_index_load({prefix}) failed with {rc}")
 
+    @classmethod
+    def from_arrays(cls, a):
+        """The same block from arrays already in host memory (the dict subread_b200.index_build returns): no file
+        round trip, for indexes of human size.  The arrays stay owned by Python."""
+        self = cls.__new__(cls)
+        keep = dict(bucket_start=np.ascontiguousarray(a["bucket_start"], dtype=np.uint32),
+                    keys=np.ascontiguousarray(a["keys"], dtype=np.int16), vals=np.ascontiguousarray(a["vals"], dtype=np.uint32),
+                    values=np.concatenate((np.asarray(a["values"], dtype=np.uint8), np.zeros(16, np.uint8))),  # slack like or_index_load
+                    read_offsets=np.ascontiguousarray(a["read_offsets"], dtype=np.uint32))
+        c = OrIndex()
+        c.index_gap, c.padding = int(a["index_gap"]), int(a["padding"])
+        c.buckets_number, c.n_items = keep["bucket_start"].shape[0] - 1, keep["keys"].shape[0]
+        c.bucket_start = keep["bucket_start"].ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+        c.keys = keep["keys"].ctypes.data_as(ctypes.POINTER(ctypes.c_int16))
+        c.vals = keep["vals"].ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+        c.start_point, c.length = int(a["start_point"]), int(a["length"])
+        c.start_base_offset = c.start_point - c.start_point % 4       # gvindex_load, gene-value-index.c:208
+        c.values_bytes = keep["values"].shape[0] - 16
+        c.values = keep["values"].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+        c.total_offsets = keep["read_offsets"].shape[0]
+        c.read_offsets = keep["read_offsets"].ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+        self.c, self._borrowed = c, keep
+        return self
+
     def close(self):
         if self.c is not None:
-            lib().or_index_free(ctypes.byref(self.c))
+            if getattr(self, "_borrowed", None) is None:
+                lib().or_index_free(ctypes.byref(self.c))
+            self._borrowed = None
             self.c = None
 
     def __del__(self):

@@ -82,7 +82,7 @@ def load_library():
     L.srcuda_host_free.argtypes = [vp]
     L.srcuda_host_free.restype = None
     L.srcuda_vote_chunk.argtypes = [vp, ctypes.POINTER(VoteParams), vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
-    L.srcuda_vote_chunk_device.argtypes = [vp, ctypes.POINTER(VoteParams), vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.srcuda_vote_chunk_device.argtypes = [vp, ctypes.POINTER(VoteParams), vp, u64, vp, vp, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     L.srcuda_get_timing.argtypes = [vp, ctypes.POINTER(Timing)]
     L.srcuda_set_force_slow_path.argtypes = [vp, ctypes.c_int]
     L.srcuda_measure_gather_bandwidth.argtypes = [vp, u64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
@@ -223,11 +223,12 @@ class Mapper:
                                         int(out_is_zero), out_ptr, None, None, verify_ptr)
         self._check(rc, "srcuda_vote_chunk")
 
-    def vote_chunk_device(self, params, d_text, d_off, d_len, n_frags, is_paired, max_read_len, d_out, d_verify=None,
-                          out_is_zero=False):
-        """All pointers are device addresses on this mapper's GPU (e.g. torch tensors' data_ptr())."""
-        rc = self.lib.srcuda_vote_chunk_device(self.h, ctypes.byref(params), d_text, d_off, d_len, n_frags, int(is_paired),
-                                               int(max_read_len), int(out_is_zero), d_out, None, None, d_verify)
+    def vote_chunk_device(self, params, d_text, d_text_bytes, d_off, d_len, n_frags, is_paired, max_read_len, d_out, d_verify=None,
+                          out_is_zero=False, d_junc=None, d_big_margin=None):
+        """All pointers are device addresses on this mapper's GPU (e.g. torch tensors' data_ptr()); the caller makes
+        sure the buffers are complete before the call (the library launches on its own streams)."""
+        rc = self.lib.srcuda_vote_chunk_device(self.h, ctypes.byref(params), d_text, int(d_text_bytes), d_off, d_len, n_frags, int(is_paired),
+                                               int(max_read_len), int(out_is_zero), d_out, d_junc, d_big_margin, d_verify)
         self._check(rc, "srcuda_vote_chunk_device")
 
     def timing(self) -> Timing:

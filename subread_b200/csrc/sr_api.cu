@@ -807,8 +807,8 @@ int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out)
 	return SRCUDA_OK;
 }
 
-int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, const char *d_text, const uint64_t *d_off,
-                             const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len, int out_align_is_zero,
+int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, const char *d_text, uint64_t d_text_bytes,
+                             const uint64_t *d_off, const uint16_t *d_len, int64_t n_frags, int is_paired, int max_read_len, int out_align_is_zero,
                              srcuda_mapping_result *d_out_align, srcuda_subjunc_result *d_out_junc, uint16_t *d_out_big_margin,
                              uint16_t *d_out_verify)
 {
@@ -834,7 +834,7 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	while (h->events.size() < 4) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
 	CU(h, cudaMemsetAsync(bs.counters, 0, 4 * sizeof(uint32_t), bs.stream));
 	sr::ChunkArgs a;
-	a.text = (const uint8_t *)d_text; a.text_origin = 0; a.text_bytes = ~0ull >> 1;
+	a.text = (const uint8_t *)d_text; a.text_origin = 0; a.text_bytes = d_text_bytes;
 	a.off = d_off; a.len = d_len; a.n_frags = n_frags;
 	a.out = (sr::ResultWords *)d_out_align; a.verify = d_out_verify;
 	a.queue = (uint32_t *)bs.queue.p; a.queue_count = bs.counters; a.bad_reads = bs.counters + 1;

@@ -207,3 +207,100 @@ def build_index(fasta_path, prefix, gapped=True, threshold=100, buckets=None, us
     write_index_files(prefix, a)
     return dict(buckets=a["buckets_number"], items=a["n_items"], gap=a["index_gap"], removed_keys=a["removed_keys"],
                 length=a["length"], contigs=len(seqs))
+
+
+def build_index_arrays_device(names, codes, contig_lens, gapped=True, threshold=100, buckets=None, device=None,
+                              chunk=1 << 26):
+    """The same one-block index as ``build_index_arrays`` for genomes of human size, built with torch on one
+    GPU (plumbing): ``codes`` is a uint8 tensor on the device holding the 2-bit codes (A0 G1 C2 T3, base2int) of all
+    contigs back to back, ``contig_lens`` their lengths.  Peak device memory is about 45 bytes per sampled 16-mer
+    (a 3.1 Gbp gapped index: 1.03 G items, ~50 GB).  Returns the same dict (numpy arrays on the host) without
+    ``item_bucket``; ``tests/test_index_build.py`` holds it to the file writer's byte-identical output on a small genome.
+
+    Order inside a bucket (sorted-hashtable.c:1689-1698): key16 ascending, ties by position ascending when
+    ``(key % 791) % 2 == 0`` and descending otherwise.  Windows are enumerated in ascending position, so one stable sort
+    by (bucket, key16) gives the ascending ties; listing the odd-parity windows in descending position first gives theirs."""
+    import torch
+    dev = codes.device if device is None else torch.device(device)
+    gap = 3 if gapped else 1
+    nb = int(buckets) if buckets else one_block_bucket_count(gap)
+    lens = [int(x) for x in contig_lens]
+    if not lens or min(lens) <= 16:
+        raise ValueError("every contig must be longer than 16 bases")
+    starts, ends = [], []
+    start = PADDING
+    for L in lens:
+        starts.append(start)
+        ends.append(start + L - 16 + PADDING)
+        start = start + (L - 16) + 2 * PADDING
+    total_end = starts[-1] + lens[-1]
+    if total_end + PADDING > 0xFFFFFFFD:
+        raise ValueError("the reference sequences include more than 4 billion bases")
+    n_win = [(L - 15 + gap - 1) // gap for L in lens]
+    win_first = np.concatenate(([0], np.cumsum(n_win))).astype(np.int64)
+    total = int(win_first[-1])
+    cat_first = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    t_win_first = torch.from_numpy(win_first).to(dev)
+    t_cat_first = torch.from_numpy(cat_first[:-1].copy()).to(dev)
+    t_lin_first = torch.tensor(starts, dtype=torch.int64, device=dev)
+
+    major = torch.empty(total, dtype=torch.int64, device=dev)      # bucket << 16 | key16
+    value = torch.empty(total, dtype=torch.int64, device=dev)      # linear position
+    odd = torch.empty(total, dtype=torch.bool, device=dev)
+    for lo in range(0, total, chunk):
+        hi = min(total, lo + chunk)
+        w = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+        c = torch.searchsorted(t_win_first, w, right=True) - 1
+        p = (w - t_win_first[c]) * gap
+        g = t_cat_first[c] + p
+        key = torch.zeros(hi - lo, dtype=torch.int64, device=dev)
+        for i in range(16):
+            key |= codes[g + i].to(torch.int64) << (30 - 2 * i)
+        major[lo:hi] = ((key % nb) << 16) | (key // nb)
+        value[lo:hi] = t_lin_first[c] + p
+        odd[lo:hi] = ((key % 791) % 2) == 1
+        del w, c, p, g, key
+    order0 = torch.cat((torch.nonzero(~odd).flatten(), torch.nonzero(odd).flatten().flip(0)))
+    del odd
+    m0 = major[order0]
+    del major
+    m_sorted, o2 = torch.sort(m0, stable=True)
+    del m0
+    order = order0[o2]
+    del order0, o2
+    val = value[order]
+    del value, order
+
+    # scan_gene_index: 16-mers sampled more than `threshold` times are left out altogether
+    removed = 0
+    _, counts = torch.unique_consecutive(m_sorted, return_counts=True)
+    heavy = counts > threshold
+    if bool(heavy.any()):
+        removed = int(heavy.sum().item())
+        keep = ~torch.repeat_interleave(heavy, counts)
+        m_sorted, val = m_sorted[keep], val[keep]
+    del counts, heavy
+
+    bucket = m_sorted >> 16
+    key16 = (m_sorted & 0xFFFF).to(torch.int16)
+    del m_sorted
+    bcount = torch.bincount(bucket, minlength=nb)
+    del bucket
+    bucket_start = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(bcount, 0, out=bucket_start[1:])
+
+    length = total_end + PADDING
+    n_bytes = (length >> 2) + 1
+    bases = torch.zeros(n_bytes * 4, dtype=torch.uint8, device=dev)
+    for ci, (st, L) in enumerate(zip(starts, lens)):
+        bases[st:st + L] = codes[int(cat_first[ci]):int(cat_first[ci]) + L]
+    b4 = bases.view(-1, 4)
+    packed = b4[:, 0] | (b4[:, 1] << 2) | (b4[:, 2] << 4) | (b4[:, 3] << 6)
+    del bases, b4
+
+    out = dict(index_gap=gap, padding=PADDING, buckets_number=nb, n_items=int(key16.shape[0]),
+               bucket_start=bucket_start.cpu().numpy().astype(np.uint32), keys=key16.cpu().numpy(),
+               vals=val.cpu().numpy().astype(np.uint32), start_point=0, length=int(length),
+               values=packed.cpu().numpy(), read_offsets=np.array(ends, dtype=np.uint32), names=list(names),
+               contig_starts=np.array(starts, dtype=np.int64), removed_keys=removed)
+    return out

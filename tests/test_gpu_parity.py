@@ -119,7 +119,7 @@ def test_device_resident_entry_point(mapper, golden_cases, golden_index_dir):
     n = chunk.n_frags * chunk.mates * params.multi_best_reads
     d_out = torch.zeros(n * 68, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
-    mapper.vote_chunk_device(params, d_text.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), chunk.n_frags, False,
+    mapper.vote_chunk_device(params, d_text.data_ptr(), d_text.numel(), d_off.data_ptr(), d_len.data_ptr(), chunk.n_frags, False,
                              int(chunk.len.max()), d_out.data_ptr())
     got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=MAPPING_RESULT)
     assert got.tobytes() == exp.tobytes()
@@ -127,10 +127,19 @@ def test_device_resident_entry_point(mapper, golden_cases, golden_index_dir):
     # out_is_zero: the slice is not read, so stale contents must not matter
     d_out.fill_(0xAB)
     torch.cuda.synchronize()
-    mapper.vote_chunk_device(params, d_text.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), chunk.n_frags, False,
+    mapper.vote_chunk_device(params, d_text.data_ptr(), d_text.numel(), d_off.data_ptr(), d_len.data_ptr(), chunk.n_frags, False,
                              int(chunk.len.max()), d_out.data_ptr(), out_is_zero=True)
     got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=MAPPING_RESULT)
     assert got.tobytes() == exp.tobytes()
+    # a read that leaves the text buffer is reported, never dereferenced
+    from subread_b200.binding import SubreadCudaError
+    d_off2 = d_off.clone()
+    d_off2[3] = d_text.numel() - 5
+    d_off2[7] = 1 << 62
+    torch.cuda.synchronize()
+    with pytest.raises(SubreadCudaError, match="outside the text buffer"):
+        mapper.vote_chunk_device(params, d_text.data_ptr(), d_text.numel(), d_off2.data_ptr(), d_len.data_ptr(), chunk.n_frags, False,
+                                 int(chunk.len.max()), d_out.data_ptr(), out_is_zero=True)
 
 
 def test_errors_are_loud(mapper, golden_cases, golden_index_dir):
