@@ -109,6 +109,9 @@ typedef struct {
 	uint32_t values_bytes;
 	int32_t total_offsets;        /* gene_offset_t.total_offsets (subread.h:395-401) */
 	uint64_t device_bytes;        /* HBM held by this block */
+	uint32_t accelerators;        /* lookup accelerators derived at load time: 1 Bloom words, 2 bucket records,
+	                                 4 direct filter (dense tables), 8 unique-position bitmap */
+	uint32_t _pad;
 } srcuda_index_desc;
 
 /* Device-side timing and counters of the last srcuda_vote_chunk* call (CUDA events on the

@@ -32,6 +32,7 @@ class IndexDesc(ctypes.Structure):
         ("n_items", ctypes.c_uint64), ("start_point", ctypes.c_uint32), ("length", ctypes.c_uint32),
         ("start_base_offset", ctypes.c_uint32), ("values_bytes", ctypes.c_uint32),
         ("total_offsets", ctypes.c_int32), ("device_bytes", ctypes.c_uint64),
+        ("accelerators", ctypes.c_uint32), ("_pad", ctypes.c_uint32),
     ]
 
 

@@ -14,6 +14,7 @@
 #include "sr_warp.cuh"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdarg>
@@ -30,7 +31,8 @@ constexpr int kWarpsPerBlock = 8;
 #define SR_MIN_BLOCKS 5   // resident blocks (x 8 warps) per SM the register allocation is planned for: the kernel is latency-bound, 40 warps beat 24 (A/B in profiles/)
 #endif
 constexpr int kScalarThreads = 32;
-constexpr int kScalarBlocksPerSM = 1;
+constexpr int kScalarBlocksPerSM = 1;        // overflow queue of the warp kernel: a handful of fragments
+constexpr int kScalarBlocksPerSMAll = 16;    // every fragment takes the scalar path (subjunc, forced): fill the SMs
 
 // ------------------------------------------------------------------------------------ kernels
 
@@ -189,6 +191,57 @@ __global__ void k_build_uniq(const sr::DevIndex ix, uint32_t *bits)
 	}
 }
 
+// Direct filter of a dense table (sr_common.cuh), built in four steps.  (1) one thread per bucket marks every distinct
+// key of its bucket: key = key16 * buckets + bucket, bit 0 present, bit 1 more than one position.
+__global__ void k_direct_mark(const uint32_t *bucket_start, const int16_t *keys, uint32_t nb, uint32_t *words)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
+		for (uint32_t i = 0; i < n;) {
+			const int16_t k = keys[lo + i];
+			uint32_t j = i + 1;
+			while (j < n && keys[lo + j] == k) j++;
+			const uint64_t key64 = (uint64_t)(uint16_t)k * nb + b;
+			if (key64 <= 0xffffffffull) {                                      // (a key no 16-mer can produce is never looked up)
+				const uint32_t key = (uint32_t)key64, u = direct_unit(key), e = key - u * kDirectKeys;
+				atomicOr(words + 4 * (size_t)u + 1 + (e >> 4), (j - i > 1 ? 3u : 1u) << (2 * (e & 15u)));
+			}
+			i = j;
+		}
+	}
+}
+// (2) present keys per unit; (3) after the exclusive scan the rank base goes into word 0 of every unit
+__global__ void k_direct_count(const uint4 *units, uint32_t n_units, uint32_t *counts)
+{
+	for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+		const uint4 v = units[u];
+		counts[u] = __popc(v.y & 0x55555555u) + __popc(v.z & 0x55555555u) + __popc(v.w & 0x55555555u);
+	}
+}
+__global__ void k_direct_base(uint4 *units, uint32_t n_units, const uint32_t *bases)
+{
+	for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) units[u].x = bases[u];
+}
+// (4) the position of every single-position key, by rank
+__global__ void k_direct_fill(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, const uint4 *units, uint32_t *first)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
+		for (uint32_t i = 0; i < n;) {
+			const int16_t k = keys[lo + i];
+			uint32_t j = i + 1;
+			while (j < n && keys[lo + j] == k) j++;
+			const uint64_t key64 = (uint64_t)(uint16_t)k * nb + b;
+			if (j - i == 1 && key64 <= 0xffffffffull) {
+				const uint32_t key = (uint32_t)key64, u = direct_unit(key);
+				uint32_t bits;
+				first[direct_rank(units[u], key, u, &bits)] = vals[lo + i];
+			}
+			i = j;
+		}
+	}
+}
+
 // Random 32-byte-sector gather: the "HBM-gather roofline" probe.
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_thread, uint32_t seed, uint32_t *sink)
 {
@@ -229,6 +282,7 @@ struct BatchSet {  // one of two buffer sets; used by one stream
 	uint32_t *counters = nullptr;       // device: [0] queue_count (-> scalar), [1] bad_reads, [2] queue0_count (simple -> warp)
 	uint32_t *h_counters = nullptr;     // pinned host mirror, 2 per batch slot
 	sr::ScalarScratch *scratch = nullptr;
+	size_t scratch_threads = 0;
 };
 
 }  // namespace
@@ -246,8 +300,8 @@ struct srcuda_handle {
 	sr::DevIndex ix{};
 	srcuda_index_desc desc{};
 	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
-	void *d_records = nullptr, *d_bloom = nullptr, *d_uniq = nullptr;
-	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both (SRCUDA_ACCEL)
+	void *d_records = nullptr, *d_bloom = nullptr, *d_uniq = nullptr, *d_direct = nullptr, *d_direct_first = nullptr;
+	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both, 4 direct filter (SRCUDA_ACCEL)
 	bool use_uniq = false;         // SRCUDA_UNIQ=1 builds the unique-position bitmap: halves the DRAM traffic of tier 0 but costs more
 	                               // instructions than it saves while the kernel is issue-bound (profiles/), so it is off by default
 	bool l2_persist = true;        // keep the Bloom words resident in L2 (SRCUDA_L2_PERSIST=0 turns it off)
@@ -260,7 +314,7 @@ struct srcuda_handle {
 	srcuda_timing timing{};
 	bool force_slow = false;
 	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
-	int simple_smem_set[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // dynamic shared memory already granted to k_map_simple<GAP, UNIQ>
+	int simple_smem_set[4][3] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
 	uint32_t *d_sink = nullptr;
 };
@@ -308,8 +362,8 @@ int ensure(srcuda_handle *h, DeviceBuf &b, size_t bytes)
 void free_index(srcuda_handle *h)
 {
 	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr);
-	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_uniq);
-	h->d_uniq = nullptr;
+	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_uniq); cudaFree(h->d_direct); cudaFree(h->d_direct_first);
+	h->d_uniq = h->d_direct = h->d_direct_first = nullptr;
 	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = h->d_records = h->d_bloom = nullptr;
 	h->has_index = false;
 	h->l2_policy_for = nullptr;
@@ -317,17 +371,62 @@ void free_index(srcuda_handle *h)
 	memset(&h->desc, 0, sizeof(h->desc));
 }
 
-// Build the lookup accelerators for the resident block.  They pay off for sparse tables (the Bloom
-// word filters lookups whose key16 is absent; the record needs <= 5 items per bucket), so "auto"
-// enables them when the mean bucket holds at most 4 items and leaves a human-sized table as it is.
+// The direct filter of a dense table (sr_common.cuh): mark, count, scan, fill.
+int build_direct(srcuda_handle *h)
+{
+	const uint32_t nb = h->ix.buckets_number, nu = sr::kDirectUnits;
+	const int grid = h->sm_count * 8;
+	CU(h, cudaMalloc(&h->d_direct, 16 * (size_t)nu));
+	CU(h, cudaMemset(h->d_direct, 0, 16 * (size_t)nu));
+	sr::k_direct_mark<<<grid, 256>>>(h->ix.bucket_start, h->ix.keys, nb, (uint32_t *)h->d_direct);
+	CU(h, cudaGetLastError());
+	uint32_t *counts = nullptr;
+	void *temp = nullptr;
+	size_t temp_bytes = 0;
+	CU(h, cudaMalloc((void **)&counts, sizeof(uint32_t) * (size_t)nu));
+	sr::k_direct_count<<<grid, 256>>>((const uint4 *)h->d_direct, nu, counts);
+	CU(h, cudaGetLastError());
+	uint32_t last_count = 0, last_base = 0;
+	CU(h, cudaMemcpy(&last_count, counts + (nu - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	CU(h, cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts, counts, (int)nu));
+	CU(h, cudaMalloc(&temp, temp_bytes));
+	CU(h, cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, counts, (int)nu));
+	CU(h, cudaMemcpy(&last_base, counts + (nu - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	sr::k_direct_base<<<grid, 256>>>((uint4 *)h->d_direct, nu, counts);
+	CU(h, cudaGetLastError());
+	CU(h, cudaDeviceSynchronize());
+	cudaFree(temp);
+	cudaFree(counts);
+	const uint64_t n_distinct = (uint64_t)last_base + last_count;
+	CU(h, cudaMalloc(&h->d_direct_first, sizeof(uint32_t) * (size_t)(n_distinct + 8)));
+	CU(h, cudaMemset(h->d_direct_first, 0, sizeof(uint32_t) * (size_t)(n_distinct + 8)));
+	sr::k_direct_fill<<<grid, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, (const uint4 *)h->d_direct, (uint32_t *)h->d_direct_first);
+	CU(h, cudaGetLastError());
+	CU(h, cudaDeviceSynchronize());
+	h->ix.direct = (const uint32_t *)h->d_direct;
+	h->ix.direct_first = (const uint32_t *)h->d_direct_first;
+	h->desc.device_bytes += 16ull * nu + 4ull * (n_distinct + 8);
+	h->desc.accelerators = 4;
+	return 0;
+}
+
+// Build the lookup accelerators for the resident block.  Sparse tables (mean bucket <= 4 items: the one-block
+// index of a 100 Mbp genome) get the per-bucket Bloom word, which stays in L2, and the 32-byte bucket record; dense
+// tables (a human-sized index, ~64 items per bucket) get the direct filter.  SRCUDA_ACCEL overrides (0 = none).
 int build_accelerators(srcuda_handle *h)
 {
 	const uint32_t nb = h->ix.buckets_number;
 	const double mean = (double)h->desc.n_items / (double)nb;
 	int mode = h->accel_mode;
-	if (mode < 0) mode = mean <= 4.0 ? 3 : 0;
+	if (mode < 0) mode = mean <= 4.0 ? 3 : 4;
 	h->ix.bloom = nullptr;
 	h->ix.records = nullptr;
+	h->ix.direct = nullptr;
+	h->ix.direct_first = nullptr;
+	h->ix.uniq_bits = nullptr;
+	h->ix.uniq_n = 0;
+	h->desc.accelerators = 0;
+	if (mode & 4) return build_direct(h);
 	if (mode & 1) CU(h, cudaMalloc(&h->d_bloom, sizeof(sr::bloom_t) * (size_t)nb));
 	if (mode & 2) CU(h, cudaMalloc(&h->d_records, 32 * (size_t)nb));
 	if (mode) {
@@ -338,6 +437,7 @@ int build_accelerators(srcuda_handle *h)
 	h->ix.bloom = (const sr::bloom_t *)h->d_bloom;
 	h->ix.records = h->d_records;
 	h->desc.device_bytes += (mode & 1 ? (uint64_t)sizeof(sr::bloom_t) * nb : 0) + (mode & 2 ? 32ull * nb : 0);
+	h->desc.accelerators = (uint32_t)(mode & 3);
 	h->ix.uniq_bits = nullptr;
 	h->ix.uniq_n = 0;
 	if ((mode & 3) == 3 && h->use_uniq) {
@@ -352,6 +452,7 @@ int build_accelerators(srcuda_handle *h)
 			CU(h, cudaDeviceSynchronize());
 			h->ix.uniq_bits = (const uint32_t *)h->d_uniq;
 			h->desc.device_bytes += sizeof(uint32_t) * words;
+			h->desc.accelerators |= 8;
 		}
 	}
 	return 0;
@@ -458,11 +559,18 @@ int launch_warp_gap(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg,
 int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len, BatchSet &bs,
                 cudaEvent_t *ev)
 {
-	const int scalar_grid = h->sm_count * sr::kScalarBlocksPerSM;
-	if (!bs.scratch)
-		CU(h, cudaMalloc((void **)&bs.scratch, sizeof(sr::ScalarScratch) * (size_t)scalar_grid * sr::kScalarThreads));
 	// subjunc's minor-half / donor search (K_junc) is built on the exact scalar path only so far
 	const bool scalar_only = h->force_slow || cfg.do_junctions;
+	int scalar_blocks = scalar_only ? sr::kScalarBlocksPerSMAll : sr::kScalarBlocksPerSM;
+	const char *sb = getenv("SRCUDA_SCALAR_BLOCKS");
+	if (sb && atoi(sb) > 0 && atoi(sb) <= 32) scalar_blocks = atoi(sb);
+	const int scalar_grid = h->sm_count * scalar_blocks;
+	const size_t scratch_threads = (size_t)scalar_grid * sr::kScalarThreads;
+	if (bs.scratch_threads < scratch_threads) {       // one private table area per resident thread
+		if (bs.scratch) { CU(h, cudaDeviceSynchronize()); CU(h, cudaFree(bs.scratch)); bs.scratch = nullptr; bs.scratch_threads = 0; }
+		CU(h, cudaMalloc((void **)&bs.scratch, sizeof(sr::ScalarScratch) * scratch_threads));
+		bs.scratch_threads = scratch_threads;
+	}
 	if (ev) CU(h, cudaEventRecord(ev[0], s));
 	sr::ChunkArgs aw = a;
 	// tier 0: one thread per single-end fragment of a chunk whose bigtable slice is zero (sr_simple.cuh)
@@ -471,7 +579,8 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	if (tier0) {
 		const int threads = sr::kSimpleThreads;
 		const int64_t blocks = (a.n_frags + threads - 1) / threads;
-		const int smem = sr::simple_smem_bytes(max_len);
+		const int clusters = h->ix.direct ? sr::kSimpleClustersDense : sr::kSimpleClusters;
+		const int smem = sr::simple_smem_bytes(max_len, clusters);
 		uint32_t *q0 = (uint32_t *)bs.queue0.p;
 #define SR_LAUNCH_SIMPLE_U(G, U)                                                                                                     \
 	do {                                                                                                                             \
@@ -480,13 +589,14 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			h->simple_smem_set[G][U] = smem;                                                                                         \
 		}                                                                                                                            \
 		sr::k_map_simple<G, U><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off,    \
-		                                                              a.len, a.n_frags, max_len, a.out, q0, bs.counters + 2,       \
-		                                                              a.bad_reads);                                                \
+		                                                              a.len, a.n_frags, max_len, clusters, a.out, q0,              \
+		                                                              bs.counters + 2, a.bad_reads);                               \
 	} while (0)
 #define SR_LAUNCH_SIMPLE(G)                                                                                                          \
 	do {                                                                                                                             \
-		if (h->ix.uniq_bits) SR_LAUNCH_SIMPLE_U(G, true);                                                                            \
-		else SR_LAUNCH_SIMPLE_U(G, false);                                                                                           \
+		if (h->ix.direct) SR_LAUNCH_SIMPLE_U(G, 2);                                                                                  \
+		else if (h->ix.uniq_bits) SR_LAUNCH_SIMPLE_U(G, 1);                                                                          \
+		else SR_LAUNCH_SIMPLE_U(G, 0);                                                                                               \
 	} while (0)
 		switch (h->ix.index_gap) {
 		case 1: SR_LAUNCH_SIMPLE(1); break;
@@ -588,8 +698,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
 	const char *st = getenv("SRCUDA_SIMPLE_TIER");
 	if (st && st[0] == '0') h->use_simple_tier = false;
-	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both; default auto
-	if (ac && ac[0] >= '0' && ac[0] <= '3') h->accel_mode = ac[0] - '0';
+	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both, 4 direct filter; default auto
+	if (ac && ac[0] >= '0' && ac[0] <= '4') h->accel_mode = ac[0] - '0';
 	const char *fg = getenv("SRCUDA_L2_FETCH");  // L2 fetch granularity hint in bytes: 32, 64 or 128
 	// The hot loads are random 32-byte sectors (Bloom words, bucket records): fetching the neighbour sector too only
 	// doubles the DRAM traffic.  Default 32; the streaming loads are full lines either way.

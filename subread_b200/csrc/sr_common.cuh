@@ -61,7 +61,23 @@ struct DevIndex {
 	const void *records;           // per bucket 32 B (two uint4): see below; null = off
 	const uint32_t *uniq_bits;     // bit (v - start_base_offset) set: looking up the 16-mer at genome position v returns {v} and nothing else; null = off
 	uint32_t uniq_n;               // bits in uniq_bits
+	// Dense tables (a human-sized index holds ~64 items per bucket): the direct filter, see below; null = off
+	const uint32_t *direct;        // one 16-byte unit (four words) per kDirectKeys consecutive 32-bit keys
+	const uint32_t *direct_first;  // position of every key with exactly one position, by rank among the present keys
 };
+
+// The direct filter answers a lookup of a dense table with one 64-byte DRAM fetch when the key is absent and two when it
+// has a single position, instead of bucket header + binary search over the bucket's keys + position (three dependent
+// fetches).  bucket = key % buckets and key16 = key / buckets are a bijection of the 32-bit key space, so the table's
+// keys can be addressed by the key itself.  Unit u covers keys [48 u, 48 u + 48):
+//   w0      number of distinct keys present in all lower units (rank base)
+//   w1..w3  two bits per key, key k at bit 2 (k % 16) of word 1 + (k % 48) / 16:  bit 0 = the table holds the key,
+//           bit 1 = with more than one position (those lookups take the bucket path: the reference's visit order
+//           starts at the landing index of its own binary search, sorted-hashtable.c:960-981, 1109-1119).
+// 2^32 / 48 units = 1.43 GB whatever the table; direct_first adds 4 bytes per distinct key.
+constexpr uint32_t kDirectKeys = 48;
+constexpr uint32_t kDirectUnits = 89478486u;   // ceil(2^32 / 48)
+SR_HD uint32_t direct_unit(uint32_t key) { return (uint32_t)(((uint64_t)key * 0xAAAAAAABull) >> 37); }   // key / 48
 
 // 32-byte bucket record (one sector), n = items in the bucket (saturated at 0xffff):
 //   n <= kInlineItems:  bytes 0-1 n   bytes 2-11 key16[5]   bytes 12-31 value[5]        (the whole bucket)
@@ -116,6 +132,32 @@ __device__ __forceinline__ uint32_t ld_gather(const uint32_t *p)
 	asm volatile("ld.global.nc" SR_L2PF ".u32 %0, [%1];" : "=r"(v) : "l"(p));
 	return v;
 }
+// Direct filter, step 1: the word that holds the key's two bits (one 64-byte fetch).  Returns the bits.
+__device__ __forceinline__ uint32_t direct_bits(const DevIndex &ix, uint32_t key, uint32_t *unit_out)
+{
+	const uint32_t u = direct_unit(key), e = key - u * kDirectKeys;
+	*unit_out = u;
+	const uint32_t w = ld_gather(ix.direct + 4 * (size_t)u + 1 + (e >> 4));
+	return (w >> (2 * (e & 15u))) & 3u;
+}
+// Step 2 for a present key: the whole unit (an L2 hit after step 1) -> rank among the present keys.
+__device__ __forceinline__ uint4 ld_direct_unit(const DevIndex &ix, uint32_t u)
+{
+	uint4 v;
+	asm volatile("ld.global.nc" SR_L2PF ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ix.direct + 4 * (size_t)u));
+	return v;
+}
+__device__ __forceinline__ uint32_t direct_rank(const uint4 &unit, uint32_t key, uint32_t u, uint32_t *bits_out)
+{
+	const uint32_t e = key - u * kDirectKeys, wi = e >> 4, sh = 2 * (e & 15u);
+	const uint32_t w = wi == 0 ? unit.y : (wi == 1 ? unit.z : unit.w);
+	*bits_out = (w >> sh) & 3u;
+	uint32_t r = unit.x + __popc(w & 0x55555555u & ((1u << sh) - 1u));
+	if (wi > 0) r += __popc(unit.y & 0x55555555u);
+	if (wi > 1) r += __popc(unit.z & 0x55555555u);
+	return r;
+}
+
 // One 32-byte bucket record in a single 256-bit load (sm_100), streaming: not kept in L1, first to leave L2.
 struct __align__(32) Record8 { uint32_t w[8]; };
 __device__ __forceinline__ Record8 ld_record(const uint4 *records, uint32_t b)

@@ -55,23 +55,27 @@ namespace sr {
 
 constexpr int kSimpleThreads = 128;                      // fragments (threads) per block
 constexpr int kSimpleMaxLen = 256;                       // longer reads go to the warp kernel
-constexpr int kSimpleClusters = 8;                       // distinct kv per strand pass
+constexpr int kSimpleClusters = 8;                       // distinct kv per strand pass (sparse table)
+constexpr int kSimpleClustersDense = 16;                 // ... on a dense table, where a quarter of all 16-mers has some position
 constexpr int kSimpleClusterWords = 4;                   // shared-memory words per cluster
 
 // Shared-memory plan of one block (host and device agree through these functions): the packed reads of the 128
 // threads, then one private area per warp that first stages the warp's text and later holds its vote clusters.
 SR_HD int simple_words(int max_len) { return ((max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen) + 15) / 16 + 1; }
-SR_HD int simple_warp_bytes(int max_len)
+SR_HD int simple_warp_bytes(int max_len, int clusters = kSimpleClusters)
 {
 	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
 	int stage = 32 * (((ml + 3) & ~3) + 4) + 32;                             // text of 32 reads (+ alignment slack)
-	const int clus = kSimpleClusters * kSimpleClusterWords * 32 * 4;         // the vote clusters reuse the staging area
+	const int clus = clusters * kSimpleClusterWords * 32 * 4;         // the vote clusters reuse the staging area
 	if (stage < clus) stage = clus;
 	const int outb = 16 * kMaxBest * kResultWords * 4;                       // ... and later half a warp's bigtable slots
 	if (stage < outb) stage = outb;
 	return (stage + 15) & ~15;
 }
-SR_HD int simple_smem_bytes(int max_len) { return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_warp_bytes(max_len); }
+SR_HD int simple_smem_bytes(int max_len, int clusters = kSimpleClusters)
+{
+	return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_warp_bytes(max_len, clusters);
+}
 
 #if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
 
@@ -311,10 +315,17 @@ __device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r
 // more than twelve items -- is replayed on the general path, lookup by lookup in schedule order and position by
 // position in the reference's visit order.  Applying P's hits before the others is exact because a cluster does not
 // depend on the order of application.
-template <int GAP, bool UNIQ>
+// MODE: 0 sparse table (Bloom word + bucket record), 1 the same with the unique-position bitmap, 2 dense table (direct filter)
+__device__ __noinline__ bool simple_hit_call(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
+{
+	return simple_hit(C, kv, l, u, sub, tol, low, high);
+}
+
+template <int GAP, int MODE>
 __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
                                             SimpleClusters &C)
 {
+	constexpr bool UNIQ = MODE == 1, DIRECT = MODE == 2;
 	constexpr int kSubsPerBatch = 32 / GAP;                        // whole subreads per batch of <= 32 lookups
 	constexpr int kGroup = GAP == 3 ? 2 : (GAP == 2 ? 3 : 6);     // subreads per group of 6 lookups in flight
 	const uint32_t nb = ix.buckets_number;
@@ -331,7 +342,34 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 		const int n_sub = min(kSubsPerBatch, applied - s_base), cnt = n_sub * GAP, base = s_base * GAP;
 		// ---- (1) filter ----
 		unsigned mask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-		if (ix.bloom) {
+		if (DIRECT) {
+			// dense table: the key's two bits in the direct filter, one 64-byte fetch per lookup, all of a group in flight
+			mask = 0;
+#pragma unroll 1
+			for (int g = 0; g < n_sub; g += kGroup) {
+				uint32_t sh[kGroup * GAP];
+				const uint32_t *wp[kGroup * GAP];
+#pragma unroll
+				for (int ss = 0; ss < kGroup; ss++) {
+					const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
+#pragma unroll
+					for (int x = 0; x < GAP; x++) {
+						const uint32_t key = simple_key(pk, ob + x);
+						const uint32_t u = direct_unit(key), e = key - u * kDirectKeys;
+						wp[ss * GAP + x] = ix.direct + 4 * (size_t)u + 1 + (e >> 4);
+						sh[ss * GAP + x] = 2 * (e & 15u);
+					}
+				}
+				uint32_t word[kGroup * GAP];
+#pragma unroll
+				for (int u = 0; u < kGroup * GAP; u++) word[u] = ld_gather(wp[u]);
+#pragma unroll
+				for (int u = 0; u < kGroup * GAP; u++) {
+					const bool in = g + u / GAP < n_sub && ((word[u] >> sh[u]) & 1u);
+					mask |= (in ? 1u : 0u) << ((g * GAP + u) & 31);
+				}
+			}
+		} else if (ix.bloom) {
 			mask = 0;
 #pragma unroll 1
 			for (int g = 0; g < n_sub; g += kGroup) {
@@ -367,7 +405,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 		// words at P.kv + offset.  If the genome shows the survivor's own 16-mer there and the bit says that this 16-mer
 		// has exactly that one position in the table, the lookup is known to return it and the bucket is never read.
 		unsigned defer = mask;
-		if (records) {
+		if (DIRECT || records) {
 			defer = 0;
 			Record8 rn;
 			int i_next = -1, o_next = 0, sub_next = 0, mode_next = 0;
@@ -390,7 +428,10 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 						rn.w[2] = __ldg(ix.genome + (p_next >> 4) + 1);
 					}
 				}
-				if (mode_next == 0) rn = ld_record(records, key_next - q_next * nb);
+				if (DIRECT) {
+					const uint4 un = ld_direct_unit(ix, direct_unit(key_next));   // an L2 hit: the filter pass fetched this line
+					rn.w[0] = un.x; rn.w[1] = un.y; rn.w[2] = un.z; rn.w[3] = un.w;
+				} else if (mode_next == 0) rn = ld_record(records, key_next - q_next * nb);
 			};
 			issue();
 			while (i_next >= 0) {
@@ -408,7 +449,12 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					proven = ((r.w[0] >> (p & 31u)) & 1u) && gk == key;
 					if (!proven) r = ld_record(records, key - q * nb);
 				}
-				if (proven) { kind = 1; kv = P.kv; }
+				if (DIRECT) {
+					uint32_t bits;
+					const uint32_t rank = direct_rank(make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]), key, direct_unit(key), &bits);
+					kind = bits == 1u ? 1 : (bits ? 2 : 0);
+					kv = kind == 1 ? ld_gather(ix.direct_first + rank) - (uint32_t)o : 0u;
+				} else if (proven) { kind = 1; kv = P.kv; }
 				else {
 					uint32_t value = 0;
 					kind = simple_probe(ix, r, (int)(int16_t)q, &value);
@@ -419,6 +465,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					P = simple_new_cluster(kv, l, 0, sub, low, high);
 					have_p = true;
 					C.n = 1;
+					if (DIRECT) C.w(0, 0) = kv;                          // simple_hit below measures its distance to P
 				} else if (kind == 1 && have_p && kv == P.kv) {          // the plain branch :1041-1052
 					const unsigned long long bit = 1ull << sub;
 					if (P.w1 >> 31) {
@@ -426,6 +473,10 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 						P.subs |= bit;
 						P.w1 = (P.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);  // lookups come in increasing order here
 					}
+				} else if (DIRECT && kind == 1 && have_p) {
+					// a single position away from P (on a dense table every fourth random 16-mer has one): its own
+					// cluster, applied at once -- clusters do not depend on the order of application
+					if (!simple_hit(C, kv, l, 0, sub, tol, low, high)) ok = false;
 				} else if (kind != 0)
 					defer |= 1u << i;
 			}
@@ -628,18 +679,18 @@ __device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const Simple
 // k_map_simple: thread t of block b maps single-end fragment 128 b + t of a chunk whose bigtable slice is all
 // zero.  Writes the fragment's result slots, or queues the fragment for the warp kernel (its slots are then zero).
 // Every warp works on its own 32 fragments and its own slice of shared memory: there is no block-wide barrier.
-// Dynamic shared memory: simple_smem_bytes(max_len).
-template <int GAP, bool UNIQ>
+// Dynamic shared memory: simple_smem_bytes(max_len, clusters).
+template <int GAP, int MODE>
 __global__ void __launch_bounds__(kSimpleThreads, SR_SIMPLE_MIN_BLOCKS)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
-             const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, ResultWords *out, uint32_t *queue, uint32_t *queue_count,
-             uint32_t *bad_reads)
+             const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int clusters, ResultWords *out, uint32_t *queue,
+             uint32_t *queue_count, uint32_t *bad_reads)
 {
 	extern __shared__ uint4 smem4[];
 	constexpr unsigned kFullMask = 0xffffffffu;
 	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
 	const int n_words = simple_words(max_len);
-	const int warp_cap = simple_warp_bytes(max_len);
+	const int warp_cap = simple_warp_bytes(max_len, clusters);
 	uint32_t *pk = reinterpret_cast<uint32_t *>(smem4) + t;                                     // [2][n_words][128]
 	uint8_t *stage = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem4) + 2 * n_words * kSimpleThreads) + wid * warp_cap;
 	const int64_t fw0 = (int64_t)blockIdx.x * kSimpleThreads + 32 * wid, f = fw0 + lane;
@@ -709,14 +760,14 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	SimpleClusters C;
 	C.base = reinterpret_cast<uint32_t *>(stage) + lane;
 	C.n = 0;
-	C.cap = kSimpleClusters;
+	C.cap = clusters;
 	if (active && !punt) {
 		// a read shorter than 16 bases goes through two empty passes (core.c:3116)
 		int step = 65536;
 		const int applied = L >= 16 ? subread_schedule(L, GAP, cfg.total_subreads, &step) : 0;
 #pragma unroll 1
 		for (int strand = 0; strand < 2 && !punt; strand++) {        // one copy of the pass in the instruction cache
-			if (!simple_pass<GAP, UNIQ>(ix, cfg, pk + strand * n_words * kSimpleThreads, L, applied, step, C)) punt = true;
+			if (!simple_pass<GAP, MODE>(ix, cfg, pk + strand * n_words * kSimpleThreads, L, applied, step, C)) punt = true;
 			else simple_merge<GAP>(cfg, C, strand, applied, step, res);
 		}
 	}

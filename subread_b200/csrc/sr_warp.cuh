@@ -422,6 +422,17 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 				const int k16 = (int)(int16_t)q;
 				bool maybe = true;
 				if (ix.bloom) { const uint32_t m = bloom_bits(k16); maybe = ((uint32_t)__ldg(ix.bloom + b) & m) == m; }
+				if (ix.direct) {
+					// dense table: the direct filter says absent / one position / several (sr_common.cuh)
+					uint32_t u;
+					const uint32_t bits = direct_bits(ix, key, &u);
+					maybe = bits == 3u;                                      // several positions: the bucket path below
+					if (bits == 1u) {
+						uint32_t again;
+						h = 1;
+						firstval = ld_gather(ix.direct_first + direct_rank(ld_direct_unit(ix, u), key, u, &again));
+					}
+				}
 				if (maybe) {
 					int items = -1;
 					if (ix.records) {

@@ -263,7 +263,7 @@ def test_subjunc_junction_voting(name, mapper, golden_cases, golden_index_dir, o
     assert (js["big_margin"] == jo["big_margin"]).all()
 
 
-@pytest.mark.parametrize("kind", ["uniform", "repeats", "full"])
+@pytest.mark.parametrize("kind", ["uniform", "repeats", "full", "dense", "dense_repeats"])
 def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_path):
     """Tier 0 (k_map_simple, one thread per fragment) only runs for single-end chunks on a zero bigtable without
     verification -- the shape of the bench.  2 Mbp genome (uniform / repeat-rich / full index); error-free reads,
@@ -276,10 +276,15 @@ def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_pa
     from subread_b200.index_build import build_index
     from subread_b200.reads import ReadChunk
     fa = str(tmp_path / "g.fa")
-    gen_data.write_genome(fa, 4, 500000, seed=91, repeats=600 if kind == "repeats" else 0)
+    gen_data.write_genome(fa, 4, 500000, seed=91, repeats=600 if kind.endswith("repeats") else 0)
     prefix = str(tmp_path / "idx")
-    build_index(fa, prefix, gapped=(kind != "full"), use_gpu=True)
+    if kind.startswith("dense"):
+        # 2 M items in 262 147 buckets (7.6 per bucket, the shape of a human-sized table): the direct filter is chosen
+        build_index(fa, prefix, gapped=False, buckets=262147, use_gpu=True)
+    else:
+        build_index(fa, prefix, gapped=(kind != "full"), use_gpu=True)
     mapper.index_load(prefix, 0)
+    assert mapper.describe().accelerators == (4 if kind.startswith("dense") else 3), "direct filter on dense tables only"
     idx = oracle_mod.OracleIndex(prefix)
     params = VoteParams.defaults(False)
     gen_data.write_reads(fa, str(tmp_path / "clean"), 40000, 150, 3, False, 0.0, 0.0, False, 0.0)
@@ -328,6 +333,46 @@ def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_pa
         ref, _ = plain.vote_chunk(chunk, params)
         assert ref.tobytes() == ora.tobytes(), name + " (tier 0 off)"
         assert plain.timing().n_simple_punted == 0
-        if name in ("clean", "scattered") and kind != "repeats":
+        if name in ("clean", "scattered") and not kind.endswith("repeats"):
             assert t.n_simple_punted < chunk.n_frags // 20, f"{name}: tier 0 punted {t.n_simple_punted} of {chunk.n_frags}"
     plain.close()
+
+
+@pytest.mark.parametrize("force", [False, True], ids=["auto", "forced_on_sparse"])
+def test_direct_filter_warp_kernel_pe_and_se(force, oracle_mod, tmp_path):
+    """The direct filter of dense tables in the warp kernel (paired-end, verification, reads with errors and indels) and
+    with SRCUDA_ACCEL=4 forced onto a sparse gapped table; a repeat-rich genome puts many keys on the several-positions
+    path and tables into the overflow queue.  Bit-exact against the oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    from subread_b200.binding import Mapper
+    from subread_b200.index_build import build_index
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 4, 500000, seed=123, repeats=500)
+    prefix = str(tmp_path / "idx")
+    if force:
+        build_index(fa, prefix, gapped=True, use_gpu=True)
+        os.environ["SRCUDA_ACCEL"] = "4"
+    else:
+        build_index(fa, prefix, gapped=False, buckets=262147, use_gpu=True)
+    try:
+        m = Mapper(0)
+    finally:
+        os.environ.pop("SRCUDA_ACCEL", None)
+    m.index_load(prefix, 0)
+    assert m.describe().accelerators == 4
+    idx = oracle_mod.OracleIndex(prefix)
+    gen_data.write_reads(fa, str(tmp_path / "se"), 20000, 150, 1, False, 0.01, 0.1, False, 0.001)
+    gen_data.write_reads(fa, str(tmp_path / "pe"), 15000, 100, 2, True, 0.01, 0.1, True, 0.001)
+    for r1, r2 in ((str(tmp_path / "se_R1.fastq"), None), (str(tmp_path / "pe_R1.fastq"), str(tmp_path / "pe_R2.fastq"))):
+        chunk = load_fastq(r1, r2)
+        params = VoteParams.defaults(r2 is not None)
+        for verify in (True, False):        # without verification single-end chunks start in tier 0
+            got, ver = m.vote_chunk(chunk, params, want_verify=verify)
+            ora, over, _ = oracle_mod.vote_chunk(idx, params, chunk, want_verify=verify, threads=8)
+            ok, bad = used_slots_equal(got, ora)
+            assert ok, describe_mismatch(got, ora, bad)
+            assert got.tobytes() == ora.tobytes()
+            if verify:
+                assert (ver == over).all()
+    m.close()
