@@ -11,6 +11,7 @@
 #include "sr_index.h"
 #include "sr_scalar.cuh"
 #include "sr_simple.cuh"
+#include "sr_simple_pe.cuh"
 #include "sr_warp.cuh"
 
 #include <cuda_runtime.h>
@@ -314,6 +315,8 @@ struct srcuda_handle {
 	srcuda_timing timing{};
 	bool force_slow = false;
 	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
+	bool use_simple_tier_pe = true;  // SRCUDA_SIMPLE_TIER_PE=0 disables its paired-end form only
+	int simple_pe_smem_set[4][3] = {};
 	int simple_smem_set[4][3] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
 	uint32_t *d_sink = nullptr;
@@ -610,6 +613,44 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		aw.in_list = q0;
 		aw.in_count = bs.counters + 2;
 	}
+	// ... and its paired-end form: one thread per fragment, pair scoring per thread (sr_simple_pe.cuh)
+	const bool tier0_pe = !scalar_only && h->use_simple_tier && h->use_simple_tier_pe && cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	                      cfg.max_vote_combinations <= 3 && cfg.max_vote_simples >= 24 && cfg.multi_best_reads <= sr::kMaxBest;
+	if (tier0_pe) {
+		const int threads = sr::kSimpleThreads;
+		const int64_t blocks = (a.n_frags + threads - 1) / threads;
+		const int clusters = h->ix.direct ? sr::kSimpleClustersDense : sr::kSimpleClusters;
+		const int smem = sr::simple_pe_smem_bytes(max_len, clusters);
+		uint32_t *q0 = (uint32_t *)bs.queue0.p;
+#define SR_LAUNCH_PE_U(G, U)                                                                                                         \
+	do {                                                                                                                             \
+		if (smem > h->simple_pe_smem_set[G][U]) {                                                                                    \
+			CU(h, cudaFuncSetAttribute(sr::k_map_simple_pe<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                \
+			h->simple_pe_smem_set[G][U] = smem;                                                                                      \
+		}                                                                                                                            \
+		sr::k_map_simple_pe<G, U><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, \
+		                                                                 a.len, a.n_frags, max_len, clusters, a.out, q0,           \
+		                                                                 bs.counters + 2, a.bad_reads);                            \
+	} while (0)
+#define SR_LAUNCH_PE(G)                                                                                                              \
+	do {                                                                                                                             \
+		if (h->ix.direct) SR_LAUNCH_PE_U(G, 2);                                                                                      \
+		else SR_LAUNCH_PE_U(G, 0);                                                                                                   \
+	} while (0)
+		if (smem <= 227 * 1024) {
+			switch (h->ix.index_gap) {
+			case 1: SR_LAUNCH_PE(1); break;
+			case 2: SR_LAUNCH_PE(2); break;
+			default: SR_LAUNCH_PE(3); break;
+			}
+			CU(h, cudaGetLastError());
+			h->timing.n_launches++;
+			aw.in_list = q0;
+			aw.in_count = bs.counters + 2;
+		}
+#undef SR_LAUNCH_PE_U
+#undef SR_LAUNCH_PE
+	}
 	if (ev) CU(h, cudaEventRecord(ev[3], s));
 	if (!scalar_only) {
 		int rc = cfg.is_paired ? launch_warp_gap<2>(h, s, cfg, aw, max_len) : launch_warp_gap<1>(h, s, cfg, aw, max_len);
@@ -698,6 +739,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
 	const char *st = getenv("SRCUDA_SIMPLE_TIER");
 	if (st && st[0] == '0') h->use_simple_tier = false;
+	const char *stp = getenv("SRCUDA_SIMPLE_TIER_PE");
+	if (stp && stp[0] == '0') h->use_simple_tier_pe = false;
 	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both, 4 direct filter; default auto
 	if (ac && ac[0] >= '0' && ac[0] <= '4') h->accel_mode = ac[0] - '0';
 	const char *fg = getenv("SRCUDA_L2_FETCH");  // L2 fetch granularity hint in bytes: 32, 64 or 128

@@ -1,0 +1,400 @@
+// sr_simple_pe.cuh -- tier 0 for paired-end fragments: one THREAD per fragment (two mates), one block per 128 fragments.
+//
+// The voting of a mate in a strand pass is tier 0's own (sr_simple.cuh: separable passes have closed-form vote
+// clusters), run four times per fragment -- do_voting's order: for each strand pass, mate 1 then mate 2 into their own
+// tables (core.c:3106-3198), then process_voting_junction_PE_topK (core-junction.c:2199-2530) on the two tables and on
+// what the bigtable already holds for the fragment.  That function is replayed per thread on the cluster lists:
+//   * per mate the top_scores largest distinct vote levels over table and old results (update_top_three, :908) and the
+//     candidate list in the reference's order: level by level, table slots in (row, rank in row) order, then the old
+//     results of that level (:2251-2316);
+//   * every pair (i, j) of candidates is weighed (test_PE_and_same_chro, core.c:4819: 1300 proper pair, 1000 same
+//     chromosome, 800 otherwise) and the max_vote_combinations best kept by (score desc, visiting order asc), put
+//     through the reference's unstable selection sort and consumed from the tail (:2321-2372, core.c:4716-4749, :2405);
+//   * without any pair the mates fall back to their own candidates of at least minimum_subread_for_first_read votes;
+//   * emitted positions are de-duplicated per mate, unused slots get selected_votes = 0 (:2505-2527).
+// A fragment whose pass is not separable, whose candidate list passes kPeCand entries, with a mate shorter than 16 bases
+// or other than A/C/G/T characters is queued for the warp kernel untouched, as in the single-end tier.  The chunk's
+// bigtable slice must be all zero (first index block); verification requests skip the tier.
+#pragma once
+#include "sr_simple.cuh"
+
+namespace sr {
+
+constexpr int kPeCand = 8;        // candidates per mate
+constexpr int kPeResWords = 5;    // SimpleResult in shared memory
+
+SR_HD int simple_pe_warp_bytes(int max_len, int clusters)
+{
+	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
+	int area = 32 * (((ml + 3) & ~3) + 4) + 32;                               // text of 32 reads (half of the warp's 64)
+	const int clus = 2 * clusters * kSimpleClusterWords * 32 * 4;             // both mates' clusters reuse the staging area
+	if (area < clus) area = clus;
+	area = (area + 15) & ~15;
+	return area + 2 * kMaxBest * kPeResWords * 32 * 4;                         // + what the bigtable holds so far
+}
+SR_HD int simple_pe_area_bytes(int max_len, int clusters) { return simple_pe_warp_bytes(max_len, clusters) - 2 * kMaxBest * kPeResWords * 32 * 4; }
+SR_HD int simple_pe_smem_bytes(int max_len, int clusters)
+{
+	return 4 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_pe_warp_bytes(max_len, clusters);
+}
+
+#if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
+
+// The fragment's result slots so far, [mate][k] x 5 words, interleaved over the warp's lanes.
+struct PeResults {
+	uint32_t *base;
+	__device__ __forceinline__ uint32_t &w(int m, int k, int i) const { return base[((m * kMaxBest + k) * kPeResWords + i) * 32]; }
+	__device__ __forceinline__ SimpleResult get(int m, int k) const
+	{
+		SimpleResult r;
+		r.pos = w(m, k, 0); r.votes = (int)w(m, k, 1); r.used = (int)w(m, k, 2); r.meta = w(m, k, 3); r.cov = w(m, k, 4);
+		return r;
+	}
+	__device__ __forceinline__ void put(int m, int k, const SimpleResult &r) const
+	{
+		w(m, k, 0) = r.pos; w(m, k, 1) = (uint32_t)r.votes; w(m, k, 2) = (uint32_t)r.used; w(m, k, 3) = r.meta; w(m, k, 4) = r.cov;
+	}
+};
+
+// process_voting_junction_PE_topK for one strand pass of a paired-end fragment.  Returns false when a candidate list does
+// not fit (the fragment is then queued for the warp kernel).  simple_pass has left every cluster's vote count in word 2.
+template <int GAP>
+__device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteConfig &cfg, const SimpleClusters &C0, const SimpleClusters &C1,
+                                                const PeResults &R, int strand, int applied0, int applied1, int step0, int step1, int len0, int len1)
+{
+	const int mb = cfg.multi_best_reads, ts = cfg.top_scores;
+	// Shortcut for the pass on the wrong strand of a fresh fragment (a handful of one-vote random hits per mate on a large
+	// index): when no table slot and no old result of either mate reaches minimum_subread_for_first_read, every pair fails
+	// the first test of :2333 and the fallback of :2470 emits nothing, so all slots just end with selected_votes = 0.
+	{
+		int top = 0;
+#pragma unroll 1
+		for (int m = 0; m < 2; m++) {
+			const SimpleClusters &C = m ? C1 : C0;
+#pragma unroll 1
+			for (int c = 0; c < C.n; c++) top = max(top, (int)C.w(c, 2));
+#pragma unroll 1
+			for (int k = 0; k < mb; k++) top = max(top, (int)R.w(m, k, 1));
+		}
+		if (top < cfg.min_first) {
+#pragma unroll 1
+			for (int m = 0; m < 2; m++)
+#pragma unroll 1
+				for (int k = 0; k < mb; k++) R.w(m, k, 1) = 0u;
+			return true;
+		}
+	}
+	unsigned long long cl[2] = {0ull, 0ull};       // candidate sources, 8 bits each: cluster index, or 32 + k for an old result
+	int nc[2] = {0, 0};
+#pragma unroll 1
+	for (int m = 0; m < 2; m++) {
+		const SimpleClusters &C = m ? C1 : C0;
+		int t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll 1
+		for (int c = 0; c < C.n + kMaxBest; c++) {
+			int v;
+			if (c < C.n) v = (int)C.w(c, 2);
+			else v = c - C.n < mb ? (int)R.w(m, c - C.n, 1) : 0;
+			if (v > 0) simple_update_top(ts, t0, t1, t2, v);
+		}
+		int n = 0;
+		unsigned long long list = 0ull;
+#pragma unroll 1
+		for (int lv = 0; lv < ts; lv++) {
+			const int want = lv == 0 ? t0 : (lv == 1 ? t1 : t2);
+			if (want < 1 || t0 - want > cfg.max_vote_number_cutoff) break;
+			if (want >= cfg.min_second) {
+				unsigned done = 0;
+#pragma unroll 1
+				for (;;) {                                   // table slots of this level in (row, rank in row) order
+					int best = -1, best_key = 0x7fffffff;
+#pragma unroll 1
+					for (int c = 0; c < C.n; c++)
+						if (!((done >> c) & 1u) && (int)C.w(c, 2) == want) {
+							const int key = C.order(c);
+							if (key < best_key) { best_key = key; best = c; }
+						}
+					if (best < 0) break;
+					done |= 1u << best;
+					if (n == kPeCand) return false;
+					list |= (unsigned long long)best << (8 * n);
+					n++;
+				}
+			}
+#pragma unroll 1
+			for (int k = 0; k < mb; k++)
+				if ((int)R.w(m, k, 1) == want) {
+					if (n == kPeCand) return false;
+					list |= (unsigned long long)(32 + k) << (8 * n);
+					n++;
+				}
+		}
+		cl[m] = list;
+		nc[m] = n;
+	}
+	const int n0 = nc[0], n1 = nc[1];
+	auto cand_src = [&](int m, int i) { return (int)((cl[m] >> (8 * i)) & 0xffull); };
+	auto cand_pos = [&](int m, int src) { return src < 32 ? (m ? C1 : C0).w(src, 0) : R.w(m, src - 32, 0); };
+	auto cand_votes = [&](int m, int src) { return src < 32 ? (int)(m ? C1 : C0).w(src, 2) : (int)R.w(m, src - 32, 1); };
+
+	// ---- pairs (:2321-2372): the best max_vote_combinations by (score desc, visiting order asc) ----
+	uint32_t comb0 = 0, comb1 = 0, comb2 = 0;
+#pragma unroll 1
+	for (int i = 0; i < n0; i++) {
+		const int si = cand_src(0, i), v1 = cand_votes(0, si);
+		int re1 = 0, chr1 = 0, lp1 = 0;
+		bool located = false;
+#pragma unroll 1
+		for (int j = 0; j < n1; j++) {
+			const int sj = cand_src(1, j), v2 = cand_votes(1, sj);
+			if (max(v1, v2) < cfg.min_first) continue;
+			if (!located) { re1 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(0, si), &chr1, &lp1); located = true; }
+			int chr2, lp2, is_pe;
+			const int re2 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(1, sj), &chr2, &lp2);
+			const int weight = pair_weight(re1, chr1, lp1, re2, chr2, lp2, len0, len1, cfg.min_pair_dist, cfg.max_pair_dist, &is_pe);
+			if (!is_pe && min(v1, v2) < cfg.min_first) continue;
+			const uint32_t key = (uint32_t)((v1 + v2) * weight) * 4096u + (uint32_t)(4095 - (i * n1 + j));
+			if (key > comb0) { comb2 = comb1; comb1 = comb0; comb0 = key; }
+			else if (key > comb1) { comb2 = comb1; comb1 = key; }
+			else if (key > comb2) comb2 = key;
+		}
+	}
+	if (cfg.max_vote_combinations < 3) comb2 = 0;
+	if (cfg.max_vote_combinations < 2) comb1 = 0;
+	const int n_comb = (comb0 != 0) + (comb1 != 0) + (comb2 != 0);
+	// merge_sort -> basic_sort_run (core.c:4716-4749): unstable selection sort, ascending score
+	{
+		auto score = [](uint32_t k) { return (int)(k >> 12); };
+		if (n_comb == 2) {
+			if (score(comb0) - score(comb1) > 0) { const uint32_t t = comb0; comb0 = comb1; comb1 = t; }
+		} else if (n_comb == 3) {
+			// i = 0: mn over j = 1, 2
+			int mn = 0;
+			if (score(comb0) - score(comb1) > 0) mn = 1;
+			if (score(mn == 0 ? comb0 : comb1) - score(comb2) > 0) mn = 2;
+			if (mn == 1) { const uint32_t t = comb0; comb0 = comb1; comb1 = t; }
+			else if (mn == 2) { const uint32_t t = comb0; comb0 = comb2; comb2 = t; }
+			// i = 1: j = 2
+			if (score(comb1) - score(comb2) > 0) { const uint32_t t = comb1; comb1 = comb2; comb2 = t; }
+		}
+	}
+
+	// ---- emission (:2386-2527), one mate at a time: the new slots are composed in registers before any is stored ----
+#pragma unroll 1
+	for (int m = 0; m < 2; m++) {
+		const SimpleClusters &C = m ? C1 : C0;
+		const int applied = m ? applied1 : applied0, step = m ? step1 : step0;
+		int cursor = 0;
+		int esrc0 = 0, esrc1 = 0, esrc2 = 0;
+		uint32_t epos0 = 0, epos1 = 0, epos2 = 0;
+		auto try_emit = [&](int src) {
+			const uint32_t pos = cand_pos(m, src);
+			if ((cursor > 0 && epos0 == pos) || (cursor > 1 && epos1 == pos) || (cursor > 2 && epos2 == pos)) return;
+			if (cursor == 0) { epos0 = pos; esrc0 = src; }
+			else if (cursor == 1) { epos1 = pos; esrc1 = src; }
+			else { epos2 = pos; esrc2 = src; }
+			cursor++;
+		};
+		if (n_comb > 0) {
+#pragma unroll 1
+			for (int c = n_comb - 1; c >= 0 && cursor < mb; c--) {
+				const uint32_t key = c == 0 ? comb0 : (c == 1 ? comb1 : comb2);
+				const int q = 4095 - (int)(key & 4095u);
+				const int i = q / n1, j = q - i * n1;
+				try_emit(cand_src(m, m ? j : i));
+			}
+		} else if (n0 > 0 || n1 > 0) {
+#pragma unroll 1
+			for (int s = 0; s < nc[m] && cursor < mb; s++) {
+				const int src = cand_src(m, s);
+				if (cand_votes(m, src) < cfg.min_first) continue;
+				try_emit(src);
+			}
+		}
+		SimpleResult nr[kMaxBest];
+#pragma unroll
+		for (int k = 0; k < kMaxBest; k++) {
+			nr[k].pos = 0; nr[k].votes = 0; nr[k].used = 0; nr[k].meta = 0; nr[k].cov = 0;
+			if (k < cursor) {
+				const int src = k == 0 ? esrc0 : (k == 1 ? esrc1 : esrc2);
+				if (src < 32) {
+					const uint32_t w1 = C.w(src, 1);
+					int s_first, s_last;
+					const int o_first = simple_offset<GAP>((int)(w1 & 255u), step, &s_first);
+					const int o_last = simple_offset<GAP>((int)((w1 >> 8) & 255u), step, &s_last);
+					nr[k].pos = C.w(src, 0); nr[k].votes = (int)C.w(src, 2); nr[k].used = applied;
+					nr[k].meta = 1u | ((uint32_t)strand << 8) | ((uint32_t)(s_first + 1) << 16) | ((uint32_t)(s_last + 1) << 24);
+					nr[k].cov = (uint32_t)o_first | ((uint32_t)(o_last + 16) << 16);
+				} else nr[k] = R.get(m, src - 32);
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < kMaxBest; k++) {
+			if (k < mb) {
+				if (k < cursor) R.put(m, k, nr[k]);
+				else R.w(m, k, 1) = 0u;
+			}
+		}
+	}
+	return true;
+}
+
+// k_map_simple_pe: thread t of block b maps paired-end fragment 128 b + t (reads 2f and 2f + 1 of the chunk) of a chunk
+// whose bigtable slice is all zero.  Dynamic shared memory: simple_pe_smem_bytes(max_len, clusters).
+template <int GAP, int MODE>
+__global__ void __launch_bounds__(kSimpleThreads, 3)
+k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
+                const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int clusters, ResultWords *out, uint32_t *queue,
+                uint32_t *queue_count, uint32_t *bad_reads)
+{
+	extern __shared__ uint4 smem4[];
+	constexpr unsigned kFullMask = 0xffffffffu;
+	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+	const int n_words = simple_words(max_len);
+	const int warp_cap = simple_pe_warp_bytes(max_len, clusters), area_cap = simple_pe_area_bytes(max_len, clusters);
+	uint32_t *pk = reinterpret_cast<uint32_t *>(smem4) + t;                                     // [mate][strand][n_words][128]
+	uint8_t *stage = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem4) + 4 * n_words * kSimpleThreads) + wid * warp_cap;
+	const int64_t fw0 = (int64_t)blockIdx.x * kSimpleThreads + 32 * wid, f = fw0 + lane;
+	const int mb = cfg.multi_best_reads;
+	if (fw0 >= n_frags) return;
+
+	// ---- 1. stage and pack: the warp's 64 reads in two halves of 32 (fragments fw0 + 16 h .. + 15) ----
+	bool active = f < n_frags, punt = false;
+	int L0 = 0, L1 = 0;
+#pragma unroll 1
+	for (int h = 0; h < 2; h++) {
+		const int64_t rr = 2 * (fw0 + 16 * h) + lane;                // the read this lane stages
+		bool have = rr < 2 * n_frags, bad = false;
+		uint64_t o = 0;
+		int L = 0;
+		if (have) {
+			o = off[rr] - text_origin;
+			L = len[rr];
+			if (o > text_bytes || (uint64_t)L > text_bytes - o || L > kMaxReadLen) { atomicAdd(bad_reads, 1u); bad = true; }
+		}
+		const bool too_long = L > kSimpleMaxLen || L > max_len;
+		const bool want = have && !bad && !too_long && L >= 16;
+		unsigned long long lo = want ? o : ~0ull, hi = want ? o + (uint64_t)L : 0ull;
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			lo = min(lo, __shfl_xor_sync(kFullMask, lo, d));
+			hi = max(hi, __shfl_xor_sync(kFullMask, hi, d));
+		}
+		unsigned so = 0;
+		bool staged = want;
+		if (hi > lo) {
+			const uint8_t *g0 = text + lo;
+			const unsigned head = (unsigned)(reinterpret_cast<uintptr_t>(g0) & 15u);
+			if (hi - lo + head <= (unsigned long long)area_cap) {
+				const uint4 *g4 = reinterpret_cast<const uint4 *>(g0 - head);
+				const int n4 = (int)((hi - lo + head + 15) >> 4);
+				uint4 *s4 = reinterpret_cast<uint4 *>(stage);
+#pragma unroll 2
+				for (int i = lane; i < n4; i += 32) s4[i] = __ldcs(g4 + i);
+				so = (unsigned)(o - lo) + head;
+			} else {
+				const int slot = ((area_cap - 16) / 32) & ~3;
+				if (want) {
+					const uint8_t *g = text + o;
+					const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(g) & 3u);
+					const int nw4 = (int)((mis + (unsigned)L + 3u) >> 2);
+					if (nw4 * 4 > slot) staged = false;
+					else {
+						const uint32_t *gw = reinterpret_cast<const uint32_t *>(g - mis);
+						uint32_t *sw = reinterpret_cast<uint32_t *>(stage + lane * slot);
+#pragma unroll 1
+						for (int i = 0; i < nw4; i++) sw[i] = __ldg(gw + i);
+						so = (unsigned)(lane * slot) + mis;
+					}
+				}
+			}
+		}
+		__syncwarp();
+		// the owner of fragment fw0 + lane (lanes 16 h .. 16 h + 15) picks up its two reads from lanes 2 (lane & 15), + 1
+		const int src0 = 2 * (lane & 15);
+		const unsigned so0 = __shfl_sync(kFullMask, so, src0), so1 = __shfl_sync(kFullMask, so, src0 + 1);
+		const int l0 = __shfl_sync(kFullMask, L, src0), l1 = __shfl_sync(kFullMask, L, src0 + 1);
+		const int ok0 = __shfl_sync(kFullMask, (int)staged, src0), ok1 = __shfl_sync(kFullMask, (int)staged, src0 + 1);
+		const int bad0 = __shfl_sync(kFullMask, (int)bad, src0), bad1 = __shfl_sync(kFullMask, (int)bad, src0 + 1);
+		if ((lane >> 4) == h && active) {
+			L0 = l0; L1 = l1;
+			if (bad0 || bad1) active = false;
+			else if (!ok0 || !ok1) punt = true;                       // a mate shorter than 16 bases, longer than the tier takes, ...
+			else {
+				if (!simple_pack(stage, so0, l0, pk, n_words)) punt = true;
+				if (!simple_pack(stage, so1, l1, pk + 2 * n_words * kSimpleThreads, n_words)) punt = true;
+			}
+		}
+		__syncwarp();
+	}
+
+	// ---- 2. four passes (strand x mate), pair scoring after each strand ----
+	PeResults R;
+	R.base = reinterpret_cast<uint32_t *>(stage + area_cap) + lane;
+#pragma unroll 1
+	for (int i = 0; i < 2 * kMaxBest * kPeResWords; i++) R.base[i * 32] = 0u;
+	SimpleClusters C0, C1;
+	C0.base = reinterpret_cast<uint32_t *>(stage) + lane;
+	C1.base = C0.base + clusters * kSimpleClusterWords * 32;
+	C0.n = C1.n = 0;
+	C0.cap = C1.cap = clusters;
+	if (active && !punt) {
+		int step0 = 65536, step1 = 65536;
+		const int applied0 = subread_schedule(L0, GAP, cfg.total_subreads, &step0);
+		const int applied1 = subread_schedule(L1, GAP, cfg.total_subreads, &step1);
+		const int rev0 = cfg.first_reversed ? 1 : 0, rev1 = cfg.second_reversed ? 1 : 0;   // reversed at fetch, core.c:1187-1199
+#pragma unroll 1
+		for (int it = 0; it < 4 && !punt; it++) {                     // one copy of the pass in the instruction cache
+			const int strand = it >> 1, m = it & 1;
+			const uint32_t *pass = pk + (m * 2 + (strand ^ (m ? rev1 : rev0))) * n_words * kSimpleThreads;
+			if (!simple_pass<GAP, MODE>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0)) punt = true;
+			else if (m == 1 && !simple_pe_merge<GAP>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1)) punt = true;
+		}
+	}
+	__syncwarp();
+	const unsigned pm = __ballot_sync(kFullMask, active && punt);
+	if (pm) {
+		uint32_t qb = 0;
+		if (lane == __ffs(pm) - 1) qb = atomicAdd(queue_count, (uint32_t)__popc(pm));
+		qb = __shfl_sync(kFullMask, qb, __ffs(pm) - 1);
+		if (active && punt) queue[qb + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)f;
+	}
+
+	// ---- 3. the warp's bigtable slice: zero-fill, then the few non-zero words on top (see k_map_simple) ----
+	{
+		const int64_t nf = min((int64_t)32, n_frags - fw0);
+		uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)fw0 * 2 * mb);
+		const int total = (int)nf * 2 * mb * kResultWords;
+		if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+			uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+			const int n4 = total >> 2;
+#pragma unroll 2
+			for (int i = lane; i < n4; i += 32) __stcs(d4 + i, make_uint4(0u, 0u, 0u, 0u));
+#pragma unroll 1
+			for (int i = (n4 << 2) + lane; i < total; i += 32) __stcs(dst + i, 0u);
+		} else {
+#pragma unroll 1
+			for (int i = lane; i < total; i += 32) __stcs(dst + i, 0u);
+		}
+	}
+	__syncwarp();
+	if (!active || punt) return;
+#pragma unroll 1
+	for (int m = 0; m < 2; m++)
+#pragma unroll 1
+		for (int k = 0; k < mb; k++) {
+			const SimpleResult r = R.get(m, k);
+			ResultWords *d = out + ((size_t)f * 2 + m) * mb + k;
+			if ((r.meta & 0xffu) == 1u) {
+				__stcs(&d->w[0], r.pos);
+				__stcs(&d->w[1], ((r.meta >> 8) & 0xffu) ? (uint32_t)kCoreNegStrand : 0u);
+				__stcs(&d->w[2], (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16));
+				__stcs(&d->w[4], ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16));
+				__stcs(&d->w[15], r.cov);
+			}
+		}
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sr

@@ -39,7 +39,7 @@ def test_pod_sizes_match_reference_structs():
     assert MAPPING_RESULT.itemsize == 68       # mapping_result_t, reference src/core.h:350-370
     assert SUBJUNC_RESULT.itemsize == 16       # subjunc_result_t, reference src/core.h:397-410
     assert ctypes.sizeof(VoteParams) == 24 * 4
-    assert ctypes.sizeof(binding.IndexDesc) == 56
+    assert ctypes.sizeof(binding.IndexDesc) == 64
     assert MAPPING_RESULT.fields["selected_votes"][1] == 8
     assert MAPPING_RESULT.fields["selected_indel_record"][1] == 16
     assert MAPPING_RESULT.fields["confident_coverage_start"][1] == 60

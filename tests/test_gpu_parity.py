@@ -376,3 +376,78 @@ def test_direct_filter_warp_kernel_pe_and_se(force, oracle_mod, tmp_path):
             if verify:
                 assert (ver == over).all()
     m.close()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "repeats", "dense"])
+def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
+    """The paired-end form of tier 0 (k_map_simple_pe: one thread per fragment, pair scoring per thread) on a zero
+    bigtable: clean, noisy (errors, indels, Ns, mixed lengths) and short pairs, pairs with odd mates (shorter than 16
+    bases, empty, lower case / IUPAC, longer than the tier takes), mates from different contigs and improper distances,
+    non-default pair distance / strand options.  Bit-exact against the oracle, and identical with the tier switched off."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    from subread_b200 import pack_reads
+    from subread_b200.binding import Mapper
+    from subread_b200.index_build import build_index
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 4, 500000, seed=191, repeats=600 if kind == "repeats" else 0)
+    prefix = str(tmp_path / "idx")
+    if kind == "dense":
+        build_index(fa, prefix, gapped=False, buckets=262147, use_gpu=True)
+    else:
+        build_index(fa, prefix, gapped=True, use_gpu=True)
+    tier = Mapper(0)
+    tier.index_load(prefix, 0)
+    os.environ["SRCUDA_SIMPLE_TIER_PE"] = "0"
+    try:
+        plain = Mapper(0)
+    finally:
+        del os.environ["SRCUDA_SIMPLE_TIER_PE"]
+    plain.index_load(prefix, 0)
+    idx = oracle_mod.OracleIndex(prefix)
+    gen_data.write_reads(fa, str(tmp_path / "clean"), 30000, 150, 13, True, 0.0, 0.0, False, 0.0)
+    gen_data.write_reads(fa, str(tmp_path / "noisy"), 20000, 100, 14, True, 0.01, 0.1, True, 0.002)
+    gen_data.write_reads(fa, str(tmp_path / "short"), 6000, 50, 15, True, 0.005, 0.0, False, 0.0)
+    chunks = {n: load_fastq(str(tmp_path / f"{n}_R1.fastq"), str(tmp_path / f"{n}_R2.fastq")) for n in ("clean", "noisy", "short")}
+    rng = np.random.default_rng(18)
+    _, seqs = gen_data.read_fasta(fa)
+    m1, m2 = [], []
+    for i in range(4000):
+        c = int(rng.integers(0, len(seqs)))
+        g = seqs[c]
+        La, Lb = int(rng.integers(14, 301)), int(rng.integers(14, 301))
+        s = int(rng.integers(0, g.shape[0] - 2000))
+        ins = int(rng.integers(max(La, Lb), 900))                      # proper and improper distances (-D 600)
+        a = bytearray(g[s:s + La].tobytes())
+        g2 = seqs[int(rng.integers(0, len(seqs)))] if i % 13 == 0 else g   # mates on different contigs
+        b = bytearray(gen_data.revcomp(g2[s + ins - Lb:s + ins]).tobytes())
+        if i % 7 == 0:
+            a[int(rng.integers(0, La))] = ord("acgtnRYU."[int(rng.integers(0, 9))])
+        if i % 9 == 0:
+            a, b = b, a                                                    # the pair on the other strand
+        if i % 17 == 0:
+            b = bytearray(gen_data.revcomp(np.frombuffer(bytes(b), dtype=np.uint8)).tobytes())   # FF orientation
+        m1.append(bytes(a)); m2.append(bytes(b))
+    m1 += [b"ACGT", b"", seqs[0][100:250].tobytes(), seqs[0][5000:6210].tobytes()]
+    m2 += [seqs[0][300:450].tobytes(), seqs[1][10:160].tobytes(), b"A" * 15, gen_data.revcomp(seqs[0][6300:6450]).tobytes()]
+    chunks["odd"] = pack_reads(m1, m2)
+    variants = [VoteParams.defaults(True)]
+    p2 = VoteParams.defaults(True)
+    p2.minimum_pair_distance, p2.maximum_pair_distance, p2.is_second_read_reversed = 100, 300, 0
+    p2.minimum_subread_for_first_read, p2.minimum_subread_for_second_read = 2, 2
+    variants.append(p2)
+    for name, chunk in chunks.items():
+        for vi, params in enumerate(variants):
+            ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, threads=8)
+            got, _ = tier.vote_chunk(chunk, params)
+            t = tier.timing()
+            ok, bad = used_slots_equal(got, ora)
+            assert ok, f"{name}/{vi}: " + describe_mismatch(got, ora, bad)
+            assert got.tobytes() == ora.tobytes(), f"{name}/{vi}"
+            ref, _ = plain.vote_chunk(chunk, params)
+            assert ref.tobytes() == ora.tobytes(), f"{name}/{vi} (tier off)"
+            assert plain.timing().n_simple_punted == 0
+            if name == "clean" and kind != "repeats" and vi == 0:
+                assert t.n_simple_punted < chunk.n_frags // 10, f"tier 0 queued {t.n_simple_punted} of {chunk.n_frags} clean pairs"
+    tier.close()
+    plain.close()
