@@ -460,12 +460,18 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					kind = simple_probe(ix, r, (int)(int16_t)q, &value);
 					kv = value - (uint32_t)o;
 				}
-				if (kind == 1 && !have_p && C.n == 0) {                  // the first position of the pass founds P
+				if (DIRECT) {
+					// dense table: every fourth random 16-mer has a position, so a pass sees a handful of one-vote clusters
+					// next to the true one and a register-resident primary cluster would diverge the warp (the first hit
+					// is often a random one).  Every single position goes through the cluster list at once -- clusters do
+					// not depend on the order of application -- and the warp stays converged in this loop.
+					if (kind == 1) { if (!simple_hit(C, kv, l, 0, sub, tol, low, high)) ok = false; }
+					else if (kind != 0) defer |= 1u << i;
+				} else if (kind == 1 && !have_p && C.n == 0) {           // the first position of the pass founds P
 					if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
 					P = simple_new_cluster(kv, l, 0, sub, low, high);
 					have_p = true;
 					C.n = 1;
-					if (DIRECT) C.w(0, 0) = kv;                          // simple_hit below measures its distance to P
 				} else if (kind == 1 && have_p && kv == P.kv) {          // the plain branch :1041-1052
 					const unsigned long long bit = 1ull << sub;
 					if (P.w1 >> 31) {
@@ -473,17 +479,79 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 						P.subs |= bit;
 						P.w1 = (P.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);  // lookups come in increasing order here
 					}
-				} else if (DIRECT && kind == 1 && have_p) {
-					// a single position away from P (on a dense table every fourth random 16-mer has one): its own
-					// cluster, applied at once -- clusters do not depend on the order of application
-					if (!simple_hit(C, kv, l, 0, sub, tol, low, high)) ok = false;
 				} else if (kind != 0)
 					defer |= 1u << i;
 			}
 			if (!ok) return false;
 		}
 		// ---- (3) everything else, on the general path ----
-		if (defer) {
+		if (DIRECT) {
+			// Dense table: what is left are the keys with several positions (about one lookup in twenty).  Two phases per
+			// round of up to four of them, so that the warp is converged again when the hits are applied: (a) the bucket
+			// path of each -- header, the reference's binary search, extent of the equal-key run -- with its data-dependent
+			// loops, (b) one flat loop over all their positions in the reference's visit order.
+			while (defer && ok) {
+				uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // first item of the run in vals[]
+				uint32_t me0 = 0, me1 = 0, me2 = 0, me3 = 0;     // h | landing << 8 | lookup << 16
+				int ne = 0;
+#pragma unroll 1
+				while (defer && ne < 4) {
+					const int i = __ffs(defer) - 1;
+					defer &= defer - 1;
+					const int l = base + i;
+					int sub;
+					const int o = simple_offset<GAP>(l, step, &sub);
+					const uint32_t key = simple_key(pk, o);
+					const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
+					const uint32_t b = key - q * nb;
+					const int k16 = (int)(int16_t)q;
+					const uint32_t lo = ld_gather(ix.bucket_start + b);
+					const int items = (int)(ld_gather(ix.bucket_start + b + 1) - lo);
+					int h = 0, land = 0, st = 0;
+					if (items > 0) {
+						const int16_t *kp = ix.keys + lo;
+						int imin = 0, imax = items - 1, at;
+						bool found = false;
+						for (;;) {                                       // sorted-hashtable.c:960-981
+							at = (imin + imax) >> 1;
+							const int kk = (int)__ldg(kp + at);
+							if (kk > k16) imax = at - 1;
+							else if (kk < k16) imin = at + 1;
+							else { found = true; break; }
+							if (imax < imin) break;
+						}
+						if (found) {
+							int e = at + 1;
+							st = at;
+							while (e < items && (int)__ldg(kp + e) == k16) e++;
+							while (st > 0 && (int)__ldg(kp + st - 1) == k16) st--;
+							h = e - st;
+							land = at - st;
+						}
+					}
+					if (h > C.cap || h > 255) ok = false;                // cannot stay separable
+					const uint32_t ra = lo + (uint32_t)st, me = (uint32_t)h | ((uint32_t)land << 8) | ((uint32_t)l << 16);
+					if (ne == 0) { ra0 = ra; me0 = me; } else if (ne == 1) { ra1 = ra; me1 = me; } else if (ne == 2) { ra2 = ra; me2 = me; } else { ra3 = ra; me3 = me; }
+					ne++;
+				}
+				if (!ok) break;
+				int e = 0, u = 0;
+#pragma unroll 1
+				while (e < ne) {
+					const uint32_t ra = e == 0 ? ra0 : (e == 1 ? ra1 : (e == 2 ? ra2 : ra3)), me = e == 0 ? me0 : (e == 1 ? me1 : (e == 2 ? me2 : me3));
+					const int h = (int)(me & 255u), land = (int)((me >> 8) & 255u), l = (int)(me >> 16);
+					if (u >= h) { e++; u = 0; continue; }
+					const int nfwd = h - land;                           // landing .. end of run, then landing-1 .. start (:1109-1119)
+					const int idx = u < nfwd ? land + u : land - 1 - (u - nfwd);
+					const uint32_t v = ld_gather(ix.vals + ra + idx);
+					int sub;
+					const int o = simple_offset<GAP>(l, step, &sub);
+					if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) { ok = false; break; }
+					u++;
+				}
+			}
+			if (!ok) return false;
+		} else if (defer) {
 			if (have_p) C.put(0, P);
 			while (defer) {
 				const int i = __ffs(defer) - 1;
