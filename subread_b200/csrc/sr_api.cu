@@ -223,8 +223,10 @@ __global__ void k_direct_base(uint4 *units, uint32_t n_units, const uint32_t *ba
 {
 	for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) units[u].x = bases[u];
 }
-// (4) the position of every single-position key, by rank
-__global__ void k_direct_fill(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, const uint4 *units, uint32_t *first)
+// (4) one entry per distinct key, by rank: {position, 1}, or for a key with several positions {first item of the run,
+// run length | landing index << 8} -- the landing index of the reference's (imin + imax) / 2 search over the bucket
+// (sorted-hashtable.c:960-981), from which its visit order follows (:1109-1119)
+__global__ void k_direct_fill(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, const uint32_t *units, uint64_t *first)
 {
 	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
 		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
@@ -233,10 +235,25 @@ __global__ void k_direct_fill(const uint32_t *bucket_start, const int16_t *keys,
 			uint32_t j = i + 1;
 			while (j < n && keys[lo + j] == k) j++;
 			const uint64_t key64 = (uint64_t)(uint16_t)k * nb + b;
-			if (j - i == 1 && key64 <= 0xffffffffull) {
+			if (key64 <= 0xffffffffull) {
 				const uint32_t key = (uint32_t)key64, u = direct_unit(key);
 				uint32_t bits;
-				first[direct_rank(units[u], key, u, &bits)] = vals[lo + i];
+				const uint4 unit = make_uint4(units[4 * (size_t)u], units[4 * (size_t)u + 1], units[4 * (size_t)u + 2], units[4 * (size_t)u + 3]);
+				const uint32_t rank = direct_rank(unit, key, u, &bits);
+				if (j - i == 1) first[rank] = (uint64_t)vals[lo + i] | (1ull << 32);
+				else {
+					int imin = 0, imax = (int)n - 1, at;
+					for (;;) {
+						at = (imin + imax) >> 1;
+						if (at >= (int)j) imax = at - 1;
+						else if (at < (int)i) imin = at + 1;
+						else break;
+					}
+					const uint32_t h = j - i, land = (uint32_t)at - i;
+					// runs the 8-bit fields cannot describe are marked h = 255, which no vote cluster list takes: bucket path
+					const uint32_t meta = (h > 254u || land > 254u) ? 255u : (h | (land << 8));
+					first[rank] = (uint64_t)(lo + i) | ((uint64_t)meta << 32);
+				}
 			}
 			i = j;
 		}
@@ -401,14 +418,14 @@ int build_direct(srcuda_handle *h)
 	cudaFree(temp);
 	cudaFree(counts);
 	const uint64_t n_distinct = (uint64_t)last_base + last_count;
-	CU(h, cudaMalloc(&h->d_direct_first, sizeof(uint32_t) * (size_t)(n_distinct + 8)));
-	CU(h, cudaMemset(h->d_direct_first, 0, sizeof(uint32_t) * (size_t)(n_distinct + 8)));
-	sr::k_direct_fill<<<grid, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, (const uint4 *)h->d_direct, (uint32_t *)h->d_direct_first);
+	CU(h, cudaMalloc(&h->d_direct_first, sizeof(uint64_t) * (size_t)(n_distinct + 8)));
+	CU(h, cudaMemset(h->d_direct_first, 0, sizeof(uint64_t) * (size_t)(n_distinct + 8)));
+	sr::k_direct_fill<<<grid, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, (const uint32_t *)h->d_direct, (uint64_t *)h->d_direct_first);
 	CU(h, cudaGetLastError());
 	CU(h, cudaDeviceSynchronize());
 	h->ix.direct = (const uint32_t *)h->d_direct;
-	h->ix.direct_first = (const uint32_t *)h->d_direct_first;
-	h->desc.device_bytes += 16ull * nu + 4ull * (n_distinct + 8);
+	h->ix.direct_first = (const uint64_t *)h->d_direct_first;
+	h->desc.device_bytes += 16ull * nu + 8ull * (n_distinct + 8);
 	h->desc.accelerators = 4;
 	return 0;
 }

@@ -63,7 +63,9 @@ struct DevIndex {
 	uint32_t uniq_n;               // bits in uniq_bits
 	// Dense tables (a human-sized index holds ~64 items per bucket): the direct filter, see below; null = off
 	const uint32_t *direct;        // one 16-byte unit (four words) per kDirectKeys consecutive 32-bit keys
-	const uint32_t *direct_first;  // position of every key with exactly one position, by rank among the present keys
+	const uint64_t *direct_first;  // by rank among the present keys: {position, 1} for a key with one position, else
+	                               // {first item of its run in vals[], h | landing << 8} (low, high word): run length and the index inside the
+	                               // run where the reference's binary search lands (visit order, sorted-hashtable.c:1109-1119)
 };
 
 // The direct filter answers a lookup of a dense table with one 64-byte DRAM fetch when the key is absent and two when it
@@ -74,7 +76,7 @@ struct DevIndex {
 //   w1..w3  two bits per key, key k at bit 2 (k % 16) of word 1 + (k % 48) / 16:  bit 0 = the table holds the key,
 //           bit 1 = with more than one position (those lookups take the bucket path: the reference's visit order
 //           starts at the landing index of its own binary search, sorted-hashtable.c:960-981, 1109-1119).
-// 2^32 / 48 units = 1.43 GB whatever the table; direct_first adds 4 bytes per distinct key.
+// 2^32 / 48 units = 1.43 GB whatever the table; direct_first adds 8 bytes per distinct key.
 constexpr uint32_t kDirectKeys = 48;
 constexpr uint32_t kDirectUnits = 89478486u;   // ceil(2^32 / 48)
 SR_HD uint32_t direct_unit(uint32_t key) { return (uint32_t)(((uint64_t)key * 0xAAAAAAABull) >> 37); }   // key / 48
@@ -145,6 +147,12 @@ __device__ __forceinline__ uint4 ld_direct_unit(const DevIndex &ix, uint32_t u)
 {
 	uint4 v;
 	asm volatile("ld.global.nc" SR_L2PF ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ix.direct + 4 * (size_t)u));
+	return v;
+}
+__device__ __forceinline__ uint2 ld_direct_first(const DevIndex &ix, uint32_t rank)
+{
+	uint2 v;
+	asm volatile("ld.global.nc" SR_L2PF ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ix.direct_first + rank));
 	return v;
 }
 __device__ __forceinline__ uint32_t direct_rank(const uint4 &unit, uint32_t key, uint32_t u, uint32_t *bits_out)

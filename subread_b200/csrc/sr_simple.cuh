@@ -176,11 +176,14 @@ __device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, 
 {
 	if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;           // u32 wrap-around of the probe rows
 	int found = -1;
-	for (int c = 0; c < C.n; c++) {
+	bool near = false;
+#pragma unroll 1
+	for (int c = 0; c < C.n; c++) {                                // (no branch inside: the warp stays together)
 		const int d = (int)(kv - C.w(c, 0));
-		if (d == 0) found = c;
-		else if (d >= -tol && d <= tol) return false;              // within tolerance of another slot: an indel vote
+		found = d == 0 ? c : found;
+		near = near || (d != 0 && (unsigned)(d + tol) <= 2u * (unsigned)tol);
 	}
+	if (near) return false;                                        // within tolerance of another slot: an indel vote
 	if (found >= 0) {
 		SimpleCluster c = C.get(found);
 		if (!(c.w1 >> 31)) return true;                            // no slot for this kv: dropped again
@@ -405,6 +408,9 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 		// words at P.kv + offset.  If the genome shows the survivor's own 16-mer there and the bit says that this 16-mer
 		// has exactly that one position in the table, the lookup is known to return it and the bucket is never read.
 		unsigned defer = mask;
+		uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // dense table: runs of keys with several positions waiting to be applied:
+		uint32_t me0 = 0, me1 = 0, me2 = 0, me3 = 0;     // first item in vals[];  h | landing << 8 | lookup << 16
+		int ne = 0;
 		if (DIRECT || records) {
 			defer = 0;
 			Record8 rn;
@@ -449,11 +455,13 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					proven = ((r.w[0] >> (p & 31u)) & 1u) && gk == key;
 					if (!proven) r = ld_record(records, key - q * nb);
 				}
+				uint2 entry = make_uint2(0u, 0u);
 				if (DIRECT) {
 					uint32_t bits;
 					const uint32_t rank = direct_rank(make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]), key, direct_unit(key), &bits);
 					kind = bits == 1u ? 1 : (bits ? 2 : 0);
-					kv = kind == 1 ? ld_gather(ix.direct_first + rank) - (uint32_t)o : 0u;
+					if (kind) entry = ld_direct_first(ix, rank);
+					kv = entry.x - (uint32_t)o;
 				} else if (proven) { kind = 1; kv = P.kv; }
 				else {
 					uint32_t value = 0;
@@ -466,7 +474,17 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					// is often a random one).  Every single position goes through the cluster list at once -- clusters do
 					// not depend on the order of application -- and the warp stays converged in this loop.
 					if (kind == 1) { if (!simple_hit(C, kv, l, 0, sub, tol, low, high)) ok = false; }
-					else if (kind != 0) defer |= 1u << i;
+					else if (kind != 0) {
+						// several positions: the entry holds the run (first item, length, landing index); up to four wait in
+						// registers for the flat loop below, more go the long way
+						const uint32_t me = (entry.y & 0xffffu) | ((uint32_t)l << 16);
+						if ((entry.y & 255u) > (uint32_t)C.cap) ok = false;       // cannot stay separable
+						else if (ne == 0) { ra0 = entry.x; me0 = me; ne = 1; }
+						else if (ne == 1) { ra1 = entry.x; me1 = me; ne = 2; }
+						else if (ne == 2) { ra2 = entry.x; me2 = me; ne = 3; }
+						else if (ne == 3) { ra3 = entry.x; me3 = me; ne = 4; }
+						else defer |= 1u << i;
+					}
 				} else if (kind == 1 && !have_p && C.n == 0) {           // the first position of the pass founds P
 					if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
 					P = simple_new_cluster(kv, l, 0, sub, low, high);
@@ -486,55 +504,25 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 		}
 		// ---- (3) everything else, on the general path ----
 		if (DIRECT) {
-			// Dense table: what is left are the keys with several positions (about one lookup in twenty).  Two phases per
-			// round of up to four of them, so that the warp is converged again when the hits are applied: (a) the bucket
-			// path of each -- header, the reference's binary search, extent of the equal-key run -- with its data-dependent
-			// loops, (b) one flat loop over all their positions in the reference's visit order.
-			while (defer && ok) {
-				uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // first item of the run in vals[]
-				uint32_t me0 = 0, me1 = 0, me2 = 0, me3 = 0;     // h | landing << 8 | lookup << 16
-				int ne = 0;
+			// Dense table: what is left are the keys with several positions (about one lookup in twenty), their runs already
+			// in registers: one flat loop over all their positions in the reference's visit order, so that the warp stays
+			// converged while the hits are applied.
+			while ((ne || defer) && ok) {
 #pragma unroll 1
-				while (defer && ne < 4) {
+				while (defer && ne < 4) {                                // (rare: a fifth key with several positions in one batch)
 					const int i = __ffs(defer) - 1;
 					defer &= defer - 1;
 					const int l = base + i;
 					int sub;
 					const int o = simple_offset<GAP>(l, step, &sub);
 					const uint32_t key = simple_key(pk, o);
-					const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
-					const uint32_t b = key - q * nb;
-					const int k16 = (int)(int16_t)q;
-					const uint32_t lo = ld_gather(ix.bucket_start + b);
-					const int items = (int)(ld_gather(ix.bucket_start + b + 1) - lo);
-					int h = 0, land = 0, st = 0;
-					if (items > 0) {
-						const int16_t *kp = ix.keys + lo;
-						int imin = 0, imax = items - 1, at;
-						bool found = false;
-						for (;;) {                                       // sorted-hashtable.c:960-981
-							at = (imin + imax) >> 1;
-							const int kk = (int)__ldg(kp + at);
-							if (kk > k16) imax = at - 1;
-							else if (kk < k16) imin = at + 1;
-							else { found = true; break; }
-							if (imax < imin) break;
-						}
-						if (found) {
-							int e = at + 1;
-							st = at;
-							while (e < items && (int)__ldg(kp + e) == k16) e++;
-							while (st > 0 && (int)__ldg(kp + st - 1) == k16) st--;
-							h = e - st;
-							land = at - st;
-						}
-					}
-					if (h > C.cap || h > 255) ok = false;                // cannot stay separable
-					const uint32_t ra = lo + (uint32_t)st, me = (uint32_t)h | ((uint32_t)land << 8) | ((uint32_t)l << 16);
-					if (ne == 0) { ra0 = ra; me0 = me; } else if (ne == 1) { ra1 = ra; me1 = me; } else if (ne == 2) { ra2 = ra; me2 = me; } else { ra3 = ra; me3 = me; }
+					const uint32_t u = direct_unit(key);
+					uint32_t bits;
+					const uint2 entry = ld_direct_first(ix, direct_rank(ld_direct_unit(ix, u), key, u, &bits));
+					const uint32_t me = (entry.y & 0xffffu) | ((uint32_t)l << 16);
+					if (ne == 0) { ra0 = entry.x; me0 = me; } else if (ne == 1) { ra1 = entry.x; me1 = me; } else if (ne == 2) { ra2 = entry.x; me2 = me; } else { ra3 = entry.x; me3 = me; }
 					ne++;
 				}
-				if (!ok) break;
 				int e = 0, u = 0;
 #pragma unroll 1
 				while (e < ne) {
@@ -549,6 +537,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) { ok = false; break; }
 					u++;
 				}
+				ne = 0;
 			}
 			if (!ok) return false;
 		} else if (defer) {

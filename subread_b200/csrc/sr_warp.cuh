@@ -430,7 +430,7 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 					if (bits == 1u) {
 						uint32_t again;
 						h = 1;
-						firstval = ld_gather(ix.direct_first + direct_rank(ld_direct_unit(ix, u), key, u, &again));
+						firstval = ld_direct_first(ix, direct_rank(ld_direct_unit(ix, u), key, u, &again)).x;
 					}
 				}
 				if (maybe) {
