@@ -41,3 +41,31 @@ def test_sanitising_rules(tmp_path):
     assert names == ["c1", "c3|x"]
     assert seqs[0].tobytes() == b"ACGTAAAAAAACGTACGTACGTACGT"
     assert seqs[1].tobytes() == b"G" * 20
+
+
+def test_device_builder_equals_array_builder():
+    """build_index_arrays_device (torch; the builder for human-sized genomes) gives the arrays of build_index_arrays -- whose
+    files are byte-identical to subread-buildindex -B (above) -- on a genome with repeats (ties of both parities, keys
+    sampled more often than the threshold), gapped and full, on the CPU."""
+    import torch
+    from subread_b200.index_build import _CODE, build_index_arrays, build_index_arrays_device
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    unit = acgt[rng.integers(0, 4, size=300)]
+    seqs = []
+    for L in (5000, 777, 12001, 64):
+        s = acgt[rng.integers(0, 4, size=L)]
+        if L > 1000:
+            for k in range(0, L - 400, 900):
+                s[k:k + 300] = unit
+        seqs.append(s)
+    seqs.append(np.tile(acgt[rng.integers(0, 4, size=3)], 400))
+    names = [f"c{i}" for i in range(len(seqs))]
+    for gapped in (True, False):
+        a = build_index_arrays(names, seqs, gapped=gapped, threshold=20, buckets=262147, use_gpu=False)
+        codes = torch.from_numpy(np.concatenate([_CODE[s] for s in seqs]))
+        b = build_index_arrays_device(names, codes, [len(s) for s in seqs], gapped=gapped, threshold=20, buckets=262147, chunk=1000)
+        for k in ("bucket_start", "keys", "vals", "values", "read_offsets"):
+            assert np.array_equal(a[k], b[k]), (gapped, k)
+        assert (a["n_items"], a["length"], a["removed_keys"]) == (b["n_items"], b["length"], b["removed_keys"])
+        assert a["removed_keys"] > 0
