@@ -150,7 +150,7 @@ __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *key
 			uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 			w[0] = n > 0xffffu ? 0xffffu : n;
 			if (n <= (uint32_t)kInlineItems) {
-				uint32_t k[kInlineItems] = {0, 0, 0, 0, 0}, v[kInlineItems] = {0, 0, 0, 0, 0};
+				uint32_t k[kInlineItems] = {kRecordNoKey, kRecordNoKey, kRecordNoKey, kRecordNoKey, kRecordNoKey}, v[kInlineItems] = {0, 0, 0, 0, 0};
 				for (uint32_t i = 0; i < n; i++) { k[i] = (uint16_t)keys[lo + i]; v[i] = vals[lo + i]; }
 				w[0] |= k[0] << 16; w[1] = k[1] | (k[2] << 16); w[2] = k[3] | (k[4] << 16);
 				w[3] = v[0]; w[4] = v[1]; w[5] = v[2]; w[6] = v[3]; w[7] = v[4];
@@ -439,6 +439,7 @@ int build_accelerators(srcuda_handle *h)
 	const double mean = (double)h->desc.n_items / (double)nb;
 	int mode = h->accel_mode;
 	if (mode < 0) mode = mean <= 4.0 ? 3 : 4;
+	if (nb < sr::kRecordMinBuckets) mode &= ~2;      // the records' packed key compares need key16 < 0x7fff
 	h->ix.bloom = nullptr;
 	h->ix.records = nullptr;
 	h->ix.direct = nullptr;

@@ -87,6 +87,9 @@ SR_HD uint32_t direct_unit(uint32_t key) { return (uint32_t)(((uint64_t)key * 0x
 //   larger:             only n is valid; the lookup falls back to bucket_start / keys / vals.
 constexpr int kInlineItems = 5;
 constexpr int kRecordKeys = 12;
+constexpr uint32_t kRecordNoKey = 0x7fffu;   // key16 field of an unused slot of an inline record: above every key16 of a table
+                                             // with at least kRecordMinBuckets buckets (key16 = key / buckets <= 0x7ffe)
+constexpr uint32_t kRecordMinBuckets = 131076u;
 
 // The two bits a key16 sets in its bucket's 16-bit Bloom word (a 2-hash blocked Bloom filter: with two items per
 // bucket a quarter of the bits are set and a foreign key passes about one time in twenty).

@@ -286,11 +286,13 @@ __device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r
 {
 	const int n = (int)(r.w[0] & 0xffffu);
 	if (n <= kInlineItems) {
-		const int k0 = (int)(int16_t)(r.w[0] >> 16), k1 = (int)(int16_t)(r.w[1] & 0xffffu), k2 = (int)(int16_t)(r.w[1] >> 16),
-		          k3 = (int)(int16_t)(r.w[2] & 0xffffu), k4 = (int)(int16_t)(r.w[2] >> 16);
-		// keys are sorted: the equal-key run is [lt, le)
-		const int lt = (n > 0 && k0 < k16) + (n > 1 && k1 < k16) + (n > 2 && k2 < k16) + (n > 3 && k3 < k16) + (n > 4 && k4 < k16);
-		const int le = (n > 0 && k0 <= k16) + (n > 1 && k1 <= k16) + (n > 2 && k2 <= k16) + (n > 3 && k3 <= k16) + (n > 4 && k4 <= k16);
+		// The five key16 fields are sorted and the unused ones hold kRecordNoKey (0x7fff, above every key: records are only
+		// built for tables whose key16 stays below it), so the equal-key run [lt, le) follows from two packed compares per
+		// word: with a, b < 0x8000 bit 15 of (a | 0x8000) - b is clear exactly when a < b, and no borrow crosses the halves.
+		const uint32_t M = 0x80008000u, kk = (uint32_t)k16 * 0x10001u, kk1 = kk + 0x10001u;
+		const uint32_t a0 = (r.w[0] | 0x0000ffffu) & 0xffff7fffu, a1 = r.w[1], a2 = r.w[2];   // (the count's half becomes a no-key)
+		const int lt = __popc(~((a0 | M) - kk) & M) + __popc(~((a1 | M) - kk) & M) + __popc(~((a2 | M) - kk) & M);
+		const int le = __popc(~((a0 | M) - kk1) & M) + __popc(~((a1 | M) - kk1) & M) + __popc(~((a2 | M) - kk1) & M);
 		*value = lt == 0 ? r.w[3] : (lt == 1 ? r.w[4] : (lt == 2 ? r.w[5] : (lt == 3 ? r.w[6] : r.w[7])));
 		return min(le - lt, 2);
 	}
