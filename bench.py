@@ -222,6 +222,22 @@ def reference_arm(args):
 
 # ------------------------------------------------------------------------------ our arm
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Best effort: run this rank (and so first-touch its pinned chunk buffers) on the CPUs next to its GPU, so that the
+    host-buffer leg does not cross the socket interconnect.  Does nothing when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        mine = near & set(os.sched_getaffinity(0))
+        if mine:
+            os.sched_setaffinity(0, mine)
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +262,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
