@@ -94,8 +94,22 @@ SR_HD void sc_go_X(const DevIndex &ix, uint32_t raw_key, int offset, ScalarTable
                    uint32_t low_border, uint32_t high_border, int round, uint32_t *shift_locs, uint32_t *shift_n)
 {
 	uint32_t nb = ix.buckets_number;
+#if defined(__CUDA_ARCH__)
+	// the exact filters of the fast tiers (no false negatives) spare the bucket of most absent keys
+	const uint32_t q = (uint32_t)__umul64hi((uint64_t)raw_key, ix.buckets_magic);
+	int16_t key = (int16_t)q;
+	uint32_t b = raw_key - q * nb;
+	if (ix.direct) {
+		uint32_t u;
+		if (direct_bits(ix, raw_key, &u) == 0u) return;
+	} else if (ix.bloom) {
+		const uint32_t m = bloom_bits((int)key);
+		if (((uint32_t)__ldg(ix.bloom + b) & m) != m) return;
+	}
+#else
 	int16_t key = (int16_t)(raw_key / nb);
 	uint32_t b = raw_key % nb;
+#endif
 	uint32_t base = ix.bucket_start[b];
 	int items = (int)(ix.bucket_start[b + 1] - base);
 	if (!items) return;

@@ -195,7 +195,7 @@ __device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, 
 		C.put(found, c);
 		return true;
 	}
-	if (C.n == C.cap) return false;
+	if (C.n >= C.cap) return false;
 	C.put(C.n++, simple_new_cluster(kv, l, u, sub, low, high));
 	return true;
 }
@@ -204,6 +204,7 @@ __device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, 
 // the read like the reference's NUL) into pk[k * 128], reverse-complement codes into pk[(n_words + k) * 128].
 // Returns false when a character is not one of A, C, G, T (then base2int / reverse_read quirks apply and the
 // fragment is punted).
+template <bool WITH_RC = true>
 __device__ __forceinline__ bool simple_pack(const uint8_t *stage, unsigned so, int L, uint32_t *pk, int n_words)
 {
 	const int nw = (L + 15) / 16 + 1;
@@ -237,6 +238,7 @@ __device__ __forceinline__ bool simple_pack(const uint8_t *stage, unsigned so, i
 		const uint32_t keep = nvalid >= 16 ? 0xffffffffu : ~(0xffffffffu >> (2 * nvalid));
 		pk[k * kSimpleThreads] = (f & keep) | (0xAAAAAAAAu & ~keep);
 	}
+	if (!WITH_RC) return bad == 0;                                 // the caller derives reverse-strand keys from this array
 	// reverse complement of an all-base read: rc base i = 3 - f base (L-1-i)
 	uint32_t *rc = pk + n_words * kSimpleThreads;
 	for (int k = 0; k < nw; k++) {
@@ -277,6 +279,21 @@ __device__ __forceinline__ uint32_t simple_key(const uint32_t *pk, int o)
 {
 	const int w = o >> 4, sh = (o & 15) * 2;
 	return __funnelshift_l(pk[(w + 1) * kSimpleThreads], pk[w * kSimpleThreads], sh);
+}
+// The same for a pass that may run on the reverse strand of a read of which only the forward array is kept (rc_len > 0 =
+// the read's length): the 16-mer at offset o of the reverse complement is the reverse complement of the forward 16-mer at
+// offset L - 16 - o, followed by the reference's padding where it passes the end of the read.
+template <bool RCKEYS>
+__device__ __forceinline__ uint32_t simple_key_at(const uint32_t *pk, int o, int rc_len)
+{
+	if (!RCKEYS || rc_len == 0) return simple_key(pk, o);
+	const int fo = rc_len - 16 - o;
+	uint32_t g = __brev(~simple_key(pk, max(fo, 0)));
+	g = ((g & 0x55555555u) << 1) | ((g >> 1) & 0x55555555u);
+	// A read of 16 or 17 bases is still looked up at offsets 0..2 (core.c:3130: one subread): those keys run past its
+	// end, where the reference's buffer holds NUL = code 2
+	if (fo < 0) g = (g << (-2 * fo)) | (0xAAAAAAAAu >> (32 + 2 * fo));
+	return g;
 }
 
 // What one survivor's bucket record says about key16 = k16.
@@ -326,9 +343,9 @@ __device__ __noinline__ bool simple_hit_call(SimpleClusters &C, uint32_t kv, int
 	return simple_hit(C, kv, l, u, sub, tol, low, high);
 }
 
-template <int GAP, int MODE>
+template <int GAP, int MODE, bool RCKEYS = false>
 __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
-                                            SimpleClusters &C)
+                                            SimpleClusters &C, int rc_len = 0)
 {
 	constexpr bool UNIQ = MODE == 1, DIRECT = MODE == 2;
 	constexpr int kSubsPerBatch = 32 / GAP;                        // whole subreads per batch of <= 32 lookups
@@ -340,6 +357,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 	const uint4 *records = reinterpret_cast<const uint4 *>(ix.records);
 	const uint64_t pol = policy_evict_last();
 	C.n = 0;
+	if (C.cap < 1) return false;      // (paired-end tier: the first mate took the whole cluster pool)
 	SimpleCluster P;                  // cluster 0 while have_p
 	P.kv = 0; P.w1 = 0; P.subs = 0;
 	bool have_p = false, ok = true;
@@ -359,7 +377,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
 #pragma unroll
 					for (int x = 0; x < GAP; x++) {
-						const uint32_t key = simple_key(pk, ob + x);
+						const uint32_t key = simple_key_at<RCKEYS>(pk, ob + x, rc_len);
 						const uint32_t u = direct_unit(key), e = key - u * kDirectKeys;
 						wp[ss * GAP + x] = ix.direct + 4 * (size_t)u + 1 + (e >> 4);
 						sh[ss * GAP + x] = 2 * (e & 15u);
@@ -384,7 +402,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
 #pragma unroll
 					for (int x = 0; x < GAP; x++) {
-						const uint32_t key = simple_key(pk, ob + x);
+						const uint32_t key = simple_key_at<RCKEYS>(pk, ob + x, rc_len);
 						const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
 						bq[ss * GAP + x] = q;
 						bw[ss * GAP + x] = key - q * nb;
@@ -424,7 +442,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 				i_next = __ffs(mask) - 1;
 				mask &= mask - 1;
 				o_next = simple_offset<GAP>(base + i_next, step, &sub_next);
-				key_next = simple_key(pk, o_next);
+				key_next = simple_key_at<RCKEYS>(pk, o_next, rc_len);
 				q_next = (uint32_t)__umul64hi((uint64_t)key_next, magic);
 				mode_next = 0;
 				if (UNIQ && have_p && ix.uniq_bits) {
@@ -517,7 +535,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					const int l = base + i;
 					int sub;
 					const int o = simple_offset<GAP>(l, step, &sub);
-					const uint32_t key = simple_key(pk, o);
+					const uint32_t key = simple_key_at<RCKEYS>(pk, o, rc_len);
 					const uint32_t u = direct_unit(key);
 					uint32_t bits;
 					const uint2 entry = ld_direct_first(ix, direct_rank(ld_direct_unit(ix, u), key, u, &bits));
@@ -550,7 +568,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 				const int l = base + i;
 				int sub;
 				const int o = simple_offset<GAP>(l, step, &sub);
-				const uint32_t key = simple_key(pk, o);
+				const uint32_t key = simple_key_at<RCKEYS>(pk, o, rc_len);
 				const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
 				const uint32_t b = key - q * nb;
 				const int k16 = (int)(int16_t)q;

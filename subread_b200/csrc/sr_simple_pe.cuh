@@ -15,44 +15,51 @@
 // A fragment whose pass is not separable, whose candidate list passes kPeCand entries, with a mate shorter than 16 bases
 // or other than A/C/G/T characters is queued for the warp kernel untouched, as in the single-end tier.  The chunk's
 // bigtable slice must be all zero (first index block); verification requests skip the tier.
+// Shared memory per thread is what bounds the resident warps here, so only the forward strand of each mate is kept packed
+// (reverse-strand keys are derived from it) and the two mates of a strand pass share one pool of vote clusters.
 #pragma once
 #include "sr_simple.cuh"
 
 namespace sr {
 
 constexpr int kPeCand = 8;        // candidates per mate
-constexpr int kPeResWords = 5;    // SimpleResult in shared memory
+constexpr int kPeResWords = 4;    // SimpleResult in shared memory: pos, votes, meta (+ used subreads), coverage
+constexpr int kPePool = 12;       // vote clusters of both mates of one strand pass, shared (the second mate takes what
+constexpr int kPePoolDense = 26;  // the first one left); dense tables: a handful of one-vote random hits per mate
 
-SR_HD int simple_pe_warp_bytes(int max_len, int clusters)
+SR_HD int simple_pe_warp_bytes(int max_len, int pool)
 {
 	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
 	int area = 32 * (((ml + 3) & ~3) + 4) + 32;                               // text of 32 reads (half of the warp's 64)
-	const int clus = 2 * clusters * kSimpleClusterWords * 32 * 4;             // both mates' clusters reuse the staging area
+	const int clus = pool * kSimpleClusterWords * 32 * 4;                     // the cluster pool reuses the staging area
 	if (area < clus) area = clus;
 	area = (area + 15) & ~15;
 	return area + 2 * kMaxBest * kPeResWords * 32 * 4;                         // + what the bigtable holds so far
 }
-SR_HD int simple_pe_area_bytes(int max_len, int clusters) { return simple_pe_warp_bytes(max_len, clusters) - 2 * kMaxBest * kPeResWords * 32 * 4; }
-SR_HD int simple_pe_smem_bytes(int max_len, int clusters)
+SR_HD int simple_pe_area_bytes(int max_len, int pool) { return simple_pe_warp_bytes(max_len, pool) - 2 * kMaxBest * kPeResWords * 32 * 4; }
+// Only the forward strand of each mate is kept packed (reverse-strand keys are derived, simple_key_at).
+SR_HD int simple_pe_smem_bytes(int max_len, int pool)
 {
-	return 4 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_pe_warp_bytes(max_len, clusters);
+	return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_pe_warp_bytes(max_len, pool);
 }
 
 #if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
 
-// The fragment's result slots so far, [mate][k] x 5 words, interleaved over the warp's lanes.
+// The fragment's result slots so far, [mate][k] x 4 words, interleaved over the warp's lanes.  used_subreads_in_vote
+// (<= 63) rides in bits 2-7 of the meta word, whose kind field needs two bits.
 struct PeResults {
 	uint32_t *base;
 	__device__ __forceinline__ uint32_t &w(int m, int k, int i) const { return base[((m * kMaxBest + k) * kPeResWords + i) * 32]; }
 	__device__ __forceinline__ SimpleResult get(int m, int k) const
 	{
 		SimpleResult r;
-		r.pos = w(m, k, 0); r.votes = (int)w(m, k, 1); r.used = (int)w(m, k, 2); r.meta = w(m, k, 3); r.cov = w(m, k, 4);
+		const uint32_t me = w(m, k, 2);
+		r.pos = w(m, k, 0); r.votes = (int)w(m, k, 1); r.used = (int)((me >> 2) & 63u); r.meta = me & ~0xfcu; r.cov = w(m, k, 3);
 		return r;
 	}
 	__device__ __forceinline__ void put(int m, int k, const SimpleResult &r) const
 	{
-		w(m, k, 0) = r.pos; w(m, k, 1) = (uint32_t)r.votes; w(m, k, 2) = (uint32_t)r.used; w(m, k, 3) = r.meta; w(m, k, 4) = r.cov;
+		w(m, k, 0) = r.pos; w(m, k, 1) = (uint32_t)r.votes; w(m, k, 2) = (r.meta & ~0xfcu) | ((uint32_t)r.used << 2); w(m, k, 3) = r.cov;
 	}
 };
 
@@ -242,18 +249,18 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 // k_map_simple_pe: thread t of block b maps paired-end fragment 128 b + t (reads 2f and 2f + 1 of the chunk) of a chunk
 // whose bigtable slice is all zero.  Dynamic shared memory: simple_pe_smem_bytes(max_len, clusters).
 template <int GAP, int MODE>
-__global__ void __launch_bounds__(kSimpleThreads, 3)
+__global__ void __launch_bounds__(kSimpleThreads, 4)
 k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
-                const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int clusters, ResultWords *out, uint32_t *queue,
+                const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int pool, ResultWords *out, uint32_t *queue,
                 uint32_t *queue_count, uint32_t *bad_reads)
 {
 	extern __shared__ uint4 smem4[];
 	constexpr unsigned kFullMask = 0xffffffffu;
 	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
 	const int n_words = simple_words(max_len);
-	const int warp_cap = simple_pe_warp_bytes(max_len, clusters), area_cap = simple_pe_area_bytes(max_len, clusters);
-	uint32_t *pk = reinterpret_cast<uint32_t *>(smem4) + t;                                     // [mate][strand][n_words][128]
-	uint8_t *stage = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem4) + 4 * n_words * kSimpleThreads) + wid * warp_cap;
+	const int warp_cap = simple_pe_warp_bytes(max_len, pool), area_cap = simple_pe_area_bytes(max_len, pool);
+	uint32_t *pk = reinterpret_cast<uint32_t *>(smem4) + t;                                     // [mate][n_words][128], forward strand
+	uint8_t *stage = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem4) + 2 * n_words * kSimpleThreads) + wid * warp_cap;
 	const int64_t fw0 = (int64_t)blockIdx.x * kSimpleThreads + 32 * wid, f = fw0 + lane;
 	const int mb = cfg.multi_best_reads;
 	if (fw0 >= n_frags) return;
@@ -321,8 +328,8 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 			if (bad0 || bad1) active = false;
 			else if (!ok0 || !ok1) punt = true;                       // a mate shorter than 16 bases, longer than the tier takes, ...
 			else {
-				if (!simple_pack(stage, so0, l0, pk, n_words)) punt = true;
-				if (!simple_pack(stage, so1, l1, pk + 2 * n_words * kSimpleThreads, n_words)) punt = true;
+				if (!simple_pack<false>(stage, so0, l0, pk, n_words)) punt = true;
+				if (!simple_pack<false>(stage, so1, l1, pk + n_words * kSimpleThreads, n_words)) punt = true;
 			}
 		}
 		__syncwarp();
@@ -334,10 +341,9 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 #pragma unroll 1
 	for (int i = 0; i < 2 * kMaxBest * kPeResWords; i++) R.base[i * 32] = 0u;
 	SimpleClusters C0, C1;
-	C0.base = reinterpret_cast<uint32_t *>(stage) + lane;
-	C1.base = C0.base + clusters * kSimpleClusterWords * 32;
+	C0.base = C1.base = reinterpret_cast<uint32_t *>(stage) + lane;
 	C0.n = C1.n = 0;
-	C0.cap = C1.cap = clusters;
+	C0.cap = C1.cap = pool;
 	if (active && !punt) {
 		int step0 = 65536, step1 = 65536;
 		const int applied0 = subread_schedule(L0, GAP, cfg.total_subreads, &step0);
@@ -346,8 +352,14 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 #pragma unroll 1
 		for (int it = 0; it < 4 && !punt; it++) {                     // one copy of the pass in the instruction cache
 			const int strand = it >> 1, m = it & 1;
-			const uint32_t *pass = pk + (m * 2 + (strand ^ (m ? rev1 : rev0))) * n_words * kSimpleThreads;
-			if (!simple_pass<GAP, MODE>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0)) punt = true;
+			const bool rc = (strand ^ (m ? rev1 : rev0)) != 0;
+			const uint32_t *pass = pk + m * n_words * kSimpleThreads;
+			if (m == 1) {                                             // the second mate's clusters follow the first one's
+				C1.base = C0.base + C0.n * kSimpleClusterWords * 32;
+				C1.cap = pool - C0.n;
+			}
+			if (!simple_pass<GAP, MODE, true>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0,
+			                                  rc ? (m ? L1 : L0) : 0)) punt = true;
 			else if (m == 1 && !simple_pe_merge<GAP>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1)) punt = true;
 		}
 	}
