@@ -440,9 +440,15 @@ def main():
                 pass
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                        "kernel": "k_map_simple<3> (tier 0, one thread per fragment) + k_map_warp<1,3> (punted fragments)",
+                        "kernel": "k_map_simple<3,0> (tier 0, one thread per fragment) + k_map_warp<1,3> (queued fragments)",
                         "kernel_ms": kern_ms_step, "tier0_ms": simple_ms / args.steps, "tier0_punted_fraction": n_punted / args.steps / R, "algorithmic_bytes_per_read": alg_bytes_per_read,
-                        "gather_peak": gather_gbs, "frac_of_gather": (achieved / gather_gbs) if gather_gbs else None}
+                        # random 32-byte records gathered per second from a table of the index's size, through the lookup's own
+                        # 64-byte-fetch load; a DRAM miss costs one line whatever is taken from it, so this is a rate of lines
+                        # (profiles/r01_t0_k_map_simple.md).  The Bloom words of this workload are served by L2, so only the
+                        # ~16 bucket records per read count against it.
+                        "gather_peak": gather_gbs, "frac_of_gather": (achieved / gather_gbs) if gather_gbs else None,
+                        "gather_records_per_s": (gather_gbs * 1e9 / 32.0) if gather_gbs else None,
+                        "dram_bytes_per_read": (traffic / R) if traffic else None}
         out = {
             "metric": "reads/sec mapped", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
