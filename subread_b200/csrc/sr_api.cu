@@ -56,8 +56,8 @@ struct ChunkArgs {
 	uint16_t *big_margin;      // subjunc only: [frag][mate][27]
 };
 
-template <int MATES, int GAP, bool VERIFY>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, SR_MIN_BLOCKS)
+template <int MATES, int GAP, bool VERIFY, bool JUNC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, SR_MIN_BLOCKS)   // (also with the junction search: 5 x 8 warps beat 3 x 8 with fewer spills)
 k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_words, int warp_bytes)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -88,9 +88,11 @@ k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_wor
 			if (lane == 0) atomicAdd(a.bad_reads, 1u);
 			continue;
 		}
-		bool ok = map_fragment<MATES, GAP, VERIFY>(ix, cfg, ws, area, n_words, lut, a.text + o0, l0, a.text + o1, l1,
-		                                   a.out + (size_t)f * MATES * mb, a.out_zero != 0,
-		                                   a.verify ? a.verify + (size_t)f * MATES * mb : nullptr, lane);
+		bool ok = map_fragment<MATES, GAP, VERIFY, JUNC>(ix, cfg, ws, area, n_words, lut, a.text + o0, l0, a.text + o1, l1,
+		                                         a.out + (size_t)f * MATES * mb, a.out_zero != 0,
+		                                         a.verify ? a.verify + (size_t)f * MATES * mb : nullptr,
+		                                         JUNC ? a.junc + (size_t)f * MATES * mb : nullptr,
+		                                         JUNC ? a.big_margin + (size_t)f * MATES * kBigMarginU16 : nullptr, lane);
 		if (!ok && lane == 0) a.queue[atomicAdd(a.queue_count, 1u)] = (uint32_t)f;
 		__syncwarp();
 	}
@@ -333,6 +335,7 @@ struct srcuda_handle {
 	bool force_slow = false;
 	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
 	bool use_simple_tier_pe = true;  // SRCUDA_SIMPLE_TIER_PE=0 disables its paired-end form only
+	bool use_warp_junc = true;       // SRCUDA_WARP_JUNC=0: subjunc fragments all take the scalar path
 	int simple_pe_smem_set[4][3] = {};
 	int simple_smem_set[4][3] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
@@ -530,7 +533,7 @@ struct LaunchPlan {
 	int n_words, warp_bytes, smem_bytes, grid;
 };
 
-template <int MATES, int GAP, bool VERIFY>
+template <int MATES, int GAP, bool VERIFY, bool JUNC>
 int plan_warp_launch(srcuda_handle *h, int max_len, LaunchPlan *p)
 {
 	p->n_words = (max_len + 15) / 16 + 1;
@@ -538,23 +541,23 @@ int plan_warp_launch(srcuda_handle *h, int max_len, LaunchPlan *p)
 	p->warp_bytes = (int)((wb + 15) & ~size_t(15));
 	p->smem_bytes = 256 + p->warp_bytes * sr::kWarpsPerBlock;
 	if (p->smem_bytes > 227 * 1024) return fail(h, SRCUDA_ERR_UNSUPPORTED, "shared memory plan %d B exceeds 227 KB", p->smem_bytes);
-	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES, GAP, VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES, GAP, VERIFY, JUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
 	int per_sm = 0;
-	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES, GAP, VERIFY>, sr::kWarpsPerBlock * 32, p->smem_bytes));
+	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES, GAP, VERIFY, JUNC>, sr::kWarpsPerBlock * 32, p->smem_bytes));
 	if (per_sm < 1) return fail(h, SRCUDA_ERR_CUDA, "warp kernel does not fit on an SM");
 	p->grid = h->sm_count * per_sm;  // persistent grid: a whole number of resident waves
 	return 0;
 }
 
-template <int MATES, int GAP, bool VERIFY>
+template <int MATES, int GAP, bool VERIFY, bool JUNC>
 int launch_warp_v(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len)
 {
 	LaunchPlan p;
-	int rc = plan_warp_launch<MATES, GAP, VERIFY>(h, max_len, &p);
+	int rc = plan_warp_launch<MATES, GAP, VERIFY, JUNC>(h, max_len, &p);
 	if (rc) return rc;
 	int64_t blocks_needed = (a.n_frags + sr::kWarpsPerBlock - 1) / sr::kWarpsPerBlock;
 	int grid = (int)std::min<int64_t>(p.grid, std::max<int64_t>(blocks_needed, 1));
-	sr::k_map_warp<MATES, GAP, VERIFY><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.warp_bytes);
+	sr::k_map_warp<MATES, GAP, VERIFY, JUNC><<<grid, sr::kWarpsPerBlock * 32, p.smem_bytes, s>>>(h->ix, cfg, a, p.n_words, p.warp_bytes);
 	CU(h, cudaGetLastError());
 	return 0;
 }
@@ -562,7 +565,8 @@ int launch_warp_v(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, c
 template <int MATES, int GAP>
 int launch_warp(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len)
 {
-	return a.verify ? launch_warp_v<MATES, GAP, true>(h, s, cfg, a, max_len) : launch_warp_v<MATES, GAP, false>(h, s, cfg, a, max_len);
+	if (cfg.do_junctions) return launch_warp_v<MATES, GAP, false, true>(h, s, cfg, a, max_len);     // (never with verification)
+	return a.verify ? launch_warp_v<MATES, GAP, true, false>(h, s, cfg, a, max_len) : launch_warp_v<MATES, GAP, false, false>(h, s, cfg, a, max_len);
 }
 
 template <int MATES>
@@ -580,8 +584,9 @@ int launch_warp_gap(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg,
 int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, const sr::ChunkArgs &a, int max_len, BatchSet &bs,
                 cudaEvent_t *ev)
 {
-	// subjunc's minor-half / donor search (K_junc) is built on the exact scalar path only so far
-	const bool scalar_only = h->force_slow || cfg.do_junctions;
+	// subjunc's minor-half / donor search (K_junc) runs in the warp kernel (sr_warp.cuh, warp_minor_half); with a
+	// verification request, or SRCUDA_WARP_JUNC=0, every fragment takes the exact scalar path instead
+	const bool scalar_only = h->force_slow || (cfg.do_junctions && (!h->use_warp_junc || a.verify));
 	int scalar_blocks = scalar_only ? sr::kScalarBlocksPerSMAll : sr::kScalarBlocksPerSM;
 	const char *sb = getenv("SRCUDA_SCALAR_BLOCKS");
 	if (sb && atoi(sb) > 0 && atoi(sb) <= 32) scalar_blocks = atoi(sb);
@@ -595,7 +600,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	if (ev) CU(h, cudaEventRecord(ev[0], s));
 	sr::ChunkArgs aw = a;
 	// tier 0: one thread per single-end fragment of a chunk whose bigtable slice is zero (sr_simple.cuh)
-	const bool tier0 = !scalar_only && h->use_simple_tier && !cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	const bool tier0 = !scalar_only && !cfg.do_junctions && h->use_simple_tier && !cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
 	                   cfg.min_second <= cfg.min_first && cfg.top_scores >= 2 && cfg.max_vote_simples >= 2;
 	if (tier0) {
 		const int threads = sr::kSimpleThreads;
@@ -632,7 +637,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		aw.in_count = bs.counters + 2;
 	}
 	// ... and its paired-end form: one thread per fragment, pair scoring per thread (sr_simple_pe.cuh)
-	const bool tier0_pe = !scalar_only && h->use_simple_tier && h->use_simple_tier_pe && cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	const bool tier0_pe = !scalar_only && !cfg.do_junctions && h->use_simple_tier && h->use_simple_tier_pe && cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
 	                      cfg.max_vote_combinations <= 3 && cfg.max_vote_simples >= 24 && cfg.multi_best_reads <= sr::kMaxBest;
 	if (tier0_pe) {
 		const int threads = sr::kSimpleThreads;
@@ -757,6 +762,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
 	const char *st = getenv("SRCUDA_SIMPLE_TIER");
 	if (st && st[0] == '0') h->use_simple_tier = false;
+	const char *wj = getenv("SRCUDA_WARP_JUNC");
+	if (wj && wj[0] == '0') h->use_warp_junc = false;
 	const char *stp = getenv("SRCUDA_SIMPLE_TIER_PE");
 	if (stp && stp[0] == '0') h->use_simple_tier_pe = false;
 	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both, 4 direct filter; default auto
@@ -1028,7 +1035,7 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	h->timing.ms_kernel_overflow = ms;
 	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[2]));
 	h->timing.ms_total = ms;
-	h->timing.n_overflow = (h->force_slow || cfg.do_junctions) ? (uint64_t)n_frags : counters[0];
+	h->timing.n_overflow = (h->force_slow || (cfg.do_junctions && (!h->use_warp_junc || d_out_verify))) ? (uint64_t)n_frags : counters[0];
 	h->timing.n_batches = 1;
 	if (counters[1]) return fail(h, SRCUDA_ERR_ARG, "%u reads have (off,len) outside the text buffer or len > %d", counters[1], sr::kMaxReadLen);
 	return SRCUDA_OK;
@@ -1149,7 +1156,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		h->timing.ms_kernel_overflow += ms;
 		const uint32_t *c = h->set[bi % kSets].h_counters + 4 * (bi / kSets);
 		h->timing.n_simple_punted += c[2];
-		h->timing.n_overflow += (h->force_slow || cfg.do_junctions) ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
+		h->timing.n_overflow += (h->force_slow || (cfg.do_junctions && (!h->use_warp_junc || out_verify))) ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
 		bad += c[1];
 	}
 	h->timing.n_batches = (uint32_t)n_batches;

@@ -236,9 +236,17 @@ SR_HD int sc_donor_pair(int a0, int a1, int b0, int b1)  // paired_chars_part_co
 	return 0;
 }
 
-SR_HD int sc_donor_score(const DevIndex &ix, const VoteConfig &cfg, uint32_t left_pos, uint32_t right_pos, int left_indel, int right_indel,
-                         int normally_arranged, int guess_start, int guess_end, const uint8_t *text, int rlen, int *split_point,
-                         int *gt_ag_strand, int *donor_found)
+// The read as donor_score sees it: TextT::match(ix, off, pos, len) = bases of read[off, off + len) equal to the genome at pos
+// (match_chro).  ScByteText is the scalar path's character buffer; the warp kernel passes its 2-bit packed array.
+struct ScByteText {
+	const uint8_t *text;
+	SR_HD int match(const DevIndex &ix, int off, uint32_t pos, int len) const { return sc_match_forward(ix, text + off, pos, len); }
+};
+
+template <class TextT>
+SR_HD int sc_donor_score_t(const DevIndex &ix, const VoteConfig &cfg, uint32_t left_pos, uint32_t right_pos, int left_indel, int right_indel,
+                           int normally_arranged, int guess_start, int guess_end, const TextT &text, int rlen, int *split_point,
+                           int *gt_ag_strand, int *donor_found)
 {
 	const int W = kConfirmWindow;
 	int most_likely = (guess_start + guess_end) / 2;
@@ -268,12 +276,12 @@ SR_HD int sc_donor_score(const DevIndex &ix, const VoteConfig &cfg, uint32_t lef
 		}
 		if (!(donor_ok || !cfg.check_donor)) continue;
 		if (normally_arranged) {
-			int lm = sc_match_forward(ix, text + sp - W, left_pos + (uint32_t)sp - W + (uint32_t)left_indel, W);
+			int lm = text.match(ix, sp - W, left_pos + (uint32_t)sp - W + (uint32_t)left_indel, W);
 			if (lm > W - 2) {
-				int rm = sc_match_forward(ix, text + sp, right_pos + (uint32_t)sp + (uint32_t)right_indel, W);
+				int rm = text.match(ix, sp, right_pos + (uint32_t)sp + (uint32_t)right_indel, W);
 				if (rm >= 2 * W - lm - cfg.mismatch_allowed) {
-					int lnm = sc_match_forward(ix, text + sp, left_pos + (uint32_t)sp + (uint32_t)left_indel, W);
-					int rnm = sc_match_forward(ix, text + sp - W, right_pos + (uint32_t)sp + (uint32_t)right_indel - W, W);
+					int lnm = text.match(ix, sp, left_pos + (uint32_t)sp + (uint32_t)left_indel, W);
+					int rnm = text.match(ix, sp - W, right_pos + (uint32_t)sp + (uint32_t)right_indel - W, W);
 					if (lnm <= W - 5 && rnm <= W - 5) {
 						int score = 100 * (donor_ok * 3000 + lm + rm - lnm - rnm);
 						if (score > best) { sel_strand = (dl0 == 'G' || dr1 == 'G') ? 1 : 0; sel_split = sp; best = score; }
@@ -281,10 +289,10 @@ SR_HD int sc_donor_score(const DevIndex &ix, const VoteConfig &cfg, uint32_t lef
 				}
 			}
 		} else {
-			int rm = sc_match_forward(ix, text + sp - W, right_pos + (uint32_t)right_indel + (uint32_t)sp - W, W);
-			int lm = sc_match_forward(ix, text + sp, left_pos + (uint32_t)sp + (uint32_t)left_indel, W);
-			int rnm = sc_match_forward(ix, text + sp, right_pos + (uint32_t)sp + (uint32_t)right_indel, W);
-			int lnm = sc_match_forward(ix, text + sp - W, left_pos + (uint32_t)left_indel + (uint32_t)sp - W, W);
+			int rm = text.match(ix, sp - W, right_pos + (uint32_t)right_indel + (uint32_t)sp - W, W);
+			int lm = text.match(ix, sp, left_pos + (uint32_t)sp + (uint32_t)left_indel, W);
+			int rnm = text.match(ix, sp, right_pos + (uint32_t)sp + (uint32_t)right_indel, W);
+			int lnm = text.match(ix, sp - W, left_pos + (uint32_t)left_indel + (uint32_t)sp - W, W);
 			if (lm + rm >= 2 * W - cfg.mismatch_allowed && lnm <= W - 5 && rnm <= W - 5) {
 				int score = 100 * (donor_ok * 3000 + lm + rm - lnm - rnm);
 				if (score > best) { sel_strand = (dl0 == 'G' || dr1 == 'G') ? 1 : 0; sel_split = sp; best = score; }
@@ -298,6 +306,14 @@ SR_HD int sc_donor_score(const DevIndex &ix, const VoteConfig &cfg, uint32_t lef
 		return (1 + best) / 100;
 	}
 	return 0;
+}
+
+SR_HD int sc_donor_score(const DevIndex &ix, const VoteConfig &cfg, uint32_t left_pos, uint32_t right_pos, int left_indel, int right_indel,
+                         int normally_arranged, int guess_start, int guess_end, const uint8_t *text, int rlen, int *split_point,
+                         int *gt_ag_strand, int *donor_found)
+{
+	return sc_donor_score_t(ix, cfg, left_pos, right_pos, left_indel, right_indel, normally_arranged, guess_start, guess_end, ScByteText{text},
+	                        rlen, split_point, gt_ag_strand, donor_found);
 }
 
 SR_HD void sc_big_margin_insert(const VoteConfig &cfg, uint16_t *rec, int votes, int start, int end, int rlen, bool negative)

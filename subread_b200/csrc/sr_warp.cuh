@@ -20,6 +20,7 @@
 // scalar path (sr_scalar.cuh) and nothing of it is written here.
 #pragma once
 #include "sr_common.cuh"
+#include "sr_scalar.cuh"   // the junction search (donor score, big-margin record) is shared with the scalar path
 
 namespace sr {
 
@@ -54,6 +55,11 @@ struct WarpShared {
 	uint8_t cand_src[MATES][kMaxCand];    // slot lane, or 32+k for old result k
 	int8_t cand_re[MATES][kMaxCand];
 	uint32_t comb[kMaxCombos];            // packed (score, r1, r2) after selection
+	// subjunc (do_breakpoint_detection) only
+	JuncWords jres[MATES][kMaxBest];      // subjunc_result_t of the fragment's slots so far
+	JuncWords jtmp[MATES][kMaxBest];
+	uint16_t bigm[MATES][kBigMarginU16];  // big-margin record of each mate
+	uint8_t order[MATES][kWarpSlots];     // the table's slots in the reference's (row, rank in row) visiting order
 };
 
 // Per-mate packed-read area in shared memory, in words: [pad][X: n_words][pad] [A0][A1][A2], see pack_read.
@@ -551,6 +557,87 @@ __device__ __forceinline__ int vote_mate(const DevIndex &ix, const VoteConfig &c
 	return applied;
 }
 
+// ---- subjunc: minor half / donor search on the shared-memory table -----------------------------
+// The read of one strand pass as 2-bit codes, MSB first, 16 bases per word (pack_read's A0 / A1).  For a read made of
+// A, C, G, T only the codes compare with the genome exactly like the characters do in match_chro's forward branch.
+struct PackedText {
+	const uint32_t *packed;
+	__device__ __forceinline__ int match(const DevIndex &ix, int off, uint32_t pos, int len) const
+	{
+		if ((uint32_t)(pos + (uint32_t)len) >= ix.length + ix.start_point) return 0;
+		if (pos > 0xffff0000u) return 0;
+		uint32_t q = pos - ix.start_base_offset;
+		if ((q >> 2) >= ix.values_bytes) return 0;
+		int ret = 0;
+		for (int i = 0; i < len; i++, q++) {
+			const int g = (int)((ix.genome[q >> 4] >> (2 * (q & 15))) & 3u);
+			const int b = off + i;
+			const int c = (int)((packed[b >> 4] >> (30 - 2 * (b & 15))) & 3u);
+			ret += g == c;
+		}
+		return ret;
+	}
+};
+
+// The do_breakpoint_detection half of copy_vote_to_alignment_res (core-junction.c:1073-1334) for the emitted slot `self`
+// of the table, run by ONE lane: the other slots are screened in the reference's visiting order (test_junction_minor :889,
+// is_better_inner :975) and sc_donor_score_t picks the split.  Same arithmetic as sc_minor_half (sr_scalar.cuh).
+__device__ __noinline__ void warp_minor_half(const DevIndex &ix, const VoteConfig &cfg, ResultWords *r, JuncWords *jr, const WarpTable &T,
+                                             const uint8_t *order, int n_slots, int self, int rlen, const uint32_t *packed)
+{
+	const int sel_votes = (int16_t)(r->w[2] & 0xffffu);
+	const uint32_t pm = T.pos[self];
+	const int cs_m = T.cov_start[self], ce_m = T.cov_end[self];
+	for (int q = 0; q < n_slots; q++) {
+		const int s = order[q];
+		if (s == self) continue;
+		const int mv = T.votes[s];
+		if (sel_votes < mv) continue;
+		const uint32_t pn = T.pos[s];
+		const long long dist = (long long)pm - (long long)pn;
+		const int cs_n = T.cov_start[s], ce_n = T.cov_end[s];
+		if (sc_abs((int)dist) > cfg.maximum_intron_length) continue;
+		if (cs_m == cs_n) continue;
+		if (ce_m == ce_n) continue;
+		if (cs_m > cs_n) { if (pm < pn) continue; } else { if (pm > pn) continue; }
+		const int16_t jr_votes = (int16_t)(jr->w[0] >> 16);
+		const int jcov = (int)(uint16_t)(jr->w[3] >> 16) - (int)(uint16_t)(jr->w[3] & 0xffffu);
+		uint32_t oi = pm - jr->w[2]; if (oi > 0x7fffffffu) oi = (0xffffffffu - oi) + 1;
+		uint32_t ni = pm - pn; if (ni > 0x7fffffffu) ni = (0xffffffffu - ni) + 1;
+		const int mcov = ce_n - cs_n;
+		const bool better = mv > jr_votes || (mv == jr_votes && mcov > jcov) || (mv == jr_votes && mcov == jcov && (int)ni < (int)oi);
+		if (!better) continue;
+		const int overlapped = cs_m > cs_n ? ce_n - cs_m : ce_m - cs_n;
+		if (overlapped > 14) continue;
+		if (sc_abs((int)dist) < 6) continue;
+		const int guess_start = cs_m > cs_n ? ce_n - 8 : ce_m - 8;
+		const int guess_end = cs_m < cs_n ? cs_n + 8 : cs_m + 8;
+		const int normally_arranged = 1 != (cs_m > cs_n) + (pm > pn);
+		int left_indel = 0, major_indels = 0, minor_indel_offset = 0;
+		if (rlen > kLongRead) {
+			for (int k = 0; k < kMaxSections; k++) { if (!T.rec[self][k * 3]) break; major_indels += T.rec[self][k * 3 + 2]; }
+			for (int k = 0; k < kMaxSections; k++) { if (!T.rec[s][k * 3]) break; minor_indel_offset += T.rec[s][k * 3 + 2]; }
+			left_indel = pm < pn ? major_indels : minor_indel_offset;
+		}
+		int split = 0, gt_ag = 0, donor_found = 0;
+		const int replace = sc_donor_score_t(ix, cfg, pm < pn ? pm : pn, pm > pn ? pm : pn, left_indel, 0, normally_arranged,
+		                                     guess_start > 0 ? guess_start : 0, guess_end < rlen ? guess_end : rlen, PackedText{packed}, rlen,
+		                                     &split, &gt_ag, &donor_found);
+		if (!replace) continue;
+		jr->w[0] = (uint32_t)(uint16_t)split | ((uint32_t)(uint16_t)mv << 16);
+		jr->w[1] = (uint32_t)(uint8_t)((minor_indel_offset & 0xf) | ((major_indels & 0xf) << 4)) | (0u << 8) |
+		           ((uint32_t)(uint8_t)(!normally_arranged) << 16) | ((uint32_t)(uint8_t)normally_arranged << 24);
+		jr->w[2] = pn;
+		jr->w[3] = (uint32_t)(uint16_t)cs_n | ((uint32_t)(uint16_t)ce_n << 16);
+		uint32_t flags = r->w[1] & 0xffffu;
+		flags &= ~0x3u;
+		if (!donor_found || gt_ag > 2) flags |= 3u;
+		else flags = gt_ag ? (flags | 1u) : (flags & ~1u);
+		flags &= ~4u;
+		r->w[1] = (r->w[1] & 0xffff0000u) | flags;
+	}
+}
+
 // ---- vote table -> bigtable (top-K) ------------------------------------------------------------
 
 // Build the mapping_result_t image of slot s into dst, word `lane` by lane `lane`
@@ -578,9 +665,9 @@ __device__ __forceinline__ void emit_slot(ResultWords &dst, const WarpTable &T, 
 	}
 }
 
-template <int MATES>
-__device__ __forceinline__ void emit_candidate(WarpShared<MATES> &ws, int m, int s, int &cursor, int used_subreads,
-                                               uint32_t strand_flag, int lane)
+template <int MATES, bool JUNC>
+__device__ __forceinline__ void emit_candidate(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, int m, int s, int &cursor,
+                                               int used_subreads, uint32_t strand_flag, int n_slots, int rlen, const uint32_t *packed, int lane)
 {
 	const uint32_t pos = ws.cand_pos[m][s];
 	bool exist = false;
@@ -589,16 +676,23 @@ __device__ __forceinline__ void emit_candidate(WarpShared<MATES> &ws, int m, int
 		if (ws.tmp[m][k].w[0] == pos) exist = true;
 	if (exist) return;
 	const int src = ws.cand_src[m][s];
-	if (src < 32) emit_slot(ws.tmp[m][cursor], ws.tab[m], src, used_subreads, strand_flag, lane);
-	else if (lane < kResultWords) ws.tmp[m][cursor].w[lane] = ws.res[m][src - 32].w[lane];
+	if (JUNC && lane < 4) ws.jtmp[m][cursor].w[lane] = src < 32 ? 0u : ws.jres[m][src - 32].w[lane];
+	if (src < 32) {
+		emit_slot(ws.tmp[m][cursor], ws.tab[m], src, used_subreads, strand_flag, lane);
+		if (JUNC) {   // the minor half of a junction read: a serial search over the other slots (core-junction.c:1073-1334)
+			__syncwarp();
+			if (lane == 0) warp_minor_half(ix, cfg, &ws.tmp[m][cursor], &ws.jtmp[m][cursor], ws.tab[m], ws.order[m], n_slots, src, rlen, packed);
+		}
+	} else if (lane < kResultWords) ws.tmp[m][cursor].w[lane] = ws.res[m][src - 32].w[lane];
 	cursor++;
 	__syncwarp();
 }
 
 // process_voting_junction_PE_topK, core-junction.c:2199-2530 (DNA mode).
-template <int MATES>
+template <int MATES, bool JUNC>
 __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, int strand,
-                                          const int nslots[2], const int rlen[2], const int all_subreads[2], int lane)
+                                          const int nslots[2], const int rlen[2], const int all_subreads[2], const uint32_t *const packed[2],
+                                          int lane)
 {
 	const int mb = cfg.multi_best_reads;
 	int n_cand[2] = {0, 0};
@@ -618,9 +712,27 @@ __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &
 			bound = top[k] > 0 ? top[k] : 0;  // once 0, nothing more qualifies
 			if (bound == 0) { for (int k2 = k + 1; k2 < kMaxTop; k2++) top[k2] = 0; break; }
 		}
+		const int key = valid ? (int)T.row[lane] * 32 + (int)T.j[lane] : 0x7fffffff;
+		if (JUNC) {
+			// the slots in the reference's visiting order (row, rank in row), for the big-margin record and the minor-half search
+			int rank = 0;
+#pragma unroll 1
+			for (int u = 0; u < kWarpSlots; u++) rank += __shfl_sync(kFull, key, u) < key ? 1 : 0;
+			if (valid) ws.order[m][rank] = (uint8_t)lane;
+			__syncwarp();
+			// insert_big_margin_record on the first level's walk over the table (:2281), which stops with the candidate list
+			if (cfg.big_margin_filtering && lane == 0 && top[0] >= 1) {
+				int seen = 0;
+				for (int q = 0; q < nslots[m] && seen < cfg.max_vote_simples; q++) {
+					const int sl = ws.order[m][q], vv = T.votes[sl];
+					if (vv >= top[cfg.top_scores - 1]) sc_big_margin_insert(cfg, ws.bigm[m], vv, T.cov_start[sl], T.cov_end[sl], rlen[m], strand != 0);
+					if (vv == top[0] && vv >= cfg.min_second) seen++;
+				}
+			}
+			__syncwarp();
+		}
 		// candidate ("simple") list, :2256-2316
 		int n = 0;
-		const int key = valid ? (int)T.row[lane] * 32 + (int)T.j[lane] : 0x7fffffff;
 		for (int lv = 0; lv < cfg.top_scores; lv++) {
 			if (n >= cfg.max_vote_simples) break;
 			const int want = top[lv];
@@ -713,7 +825,7 @@ __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &
 			for (int c = n_comb - 1; c >= 0 && cursor[m] < mb; c--) {
 				int q = 4095 - (int)(ws.comb[c] & 4095u);
 				int i = q / n1, j = q - i * n1;
-				emit_candidate<MATES>(ws, m, m ? j : i, cursor[m], all_subreads[m], strand_flag, lane);
+				emit_candidate<MATES, JUNC>(ix, cfg, ws, m, m ? j : i, cursor[m], all_subreads[m], strand_flag, nslots[m], rlen[m], packed[m], lane);
 			}
 	} else {
 		if (lane == 0) {
@@ -725,7 +837,7 @@ __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &
 			for (int m = 0; m < MATES; m++)
 				for (int s = 0; s < n_cand[m] && cursor[m] < mb; s++) {
 					if (ws.cand_votes[m][s] < cfg.min_first) continue;
-					emit_candidate<MATES>(ws, m, s, cursor[m], all_subreads[m], strand_flag, lane);
+					emit_candidate<MATES, JUNC>(ix, cfg, ws, m, s, cursor[m], all_subreads[m], strand_flag, nslots[m], rlen[m], packed[m], lane);
 				}
 	}
 	__syncwarp();
@@ -735,7 +847,11 @@ __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &
 		for (int k = 0; k < mb; k++) {
 			if (k < cursor[m]) {
 				if (lane < kResultWords) ws.res[m][k].w[lane] = ws.tmp[m][k].w[lane];
-			} else if (lane == 0) ws.res[m][k].w[2] &= 0xffff0000u;
+				if (JUNC && lane < 4) ws.jres[m][k].w[lane] = ws.jtmp[m][k].w[lane];
+			} else if (lane == 0) {
+				ws.res[m][k].w[2] &= 0xffff0000u;
+				if (JUNC) ws.jres[m][k].w[0] &= 0x0000ffffu;      // minor_votes = 0 (core-junction.c:2524)
+			}
 		}
 	__syncwarp();
 }
@@ -768,11 +884,11 @@ __device__ __forceinline__ int match_packed(const DevIndex &ix, const uint32_t *
 // ---- one fragment ------------------------------------------------------------------------------
 // area: MATES * packed_words_per_mate(n_words) words of per-warp shared memory.
 // Returns false when the fragment overflowed the shared-memory table (nothing was written).
-template <int MATES, int GAP, bool VERIFY>
+template <int MATES, int GAP, bool VERIFY, bool JUNC>
 __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfig &cfg, WarpShared<MATES> &ws, uint32_t *area,
                                              int n_words, const uint8_t *lut, const uint8_t *raw0, int len0, const uint8_t *raw1,
                                              int len1, ResultWords *out /* global, this fragment */, bool out_is_zero,
-                                             uint16_t *verify /* global or null */, int lane)
+                                             uint16_t *verify /* global or null */, JuncWords *jout, uint16_t *bmout, int lane)
 {
 	const int mb = cfg.multi_best_reads;
 	const int rlen[2] = {len0, len1};
@@ -792,6 +908,23 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 	}
 	for (int m = 0; m < MATES; m++)
 		pack_read(raw[m], rlen[m], m == 0 ? cfg.first_reversed != 0 : cfg.second_reversed != 0, area + m * per_mate, n_words, lut, lane);
+	if (JUNC) {
+		// The donor search compares read and genome base by base; on the packed codes that equals match_chro's character
+		// compare unless a raw character other than A/C/G/T has code 2 (A2 = "reversed twice" turns those into 3): such
+		// fragments take the scalar path with its character buffer.
+		__syncwarp();
+		bool odd = false;
+		for (int m = 0; m < MATES; m++) {
+			const uint32_t *A0 = area + m * per_mate + n_words + 2, *A2 = A0 + 2 * n_words;
+			for (int k = lane; k < n_words; k += 32) odd = odd || A0[k] != A2[k];
+		}
+		if (__any_sync(kFull, odd)) return false;
+		for (int w = lane; w < MATES * kMaxBest * 4; w += 32) {
+			const int slot = w >> 2, m = slot / kMaxBest, k = slot - m * kMaxBest;
+			(&ws.jres[0][0].w[0])[w] = (out_is_zero || k >= mb) ? 0u : jout[m * mb + k].w[w & 3];
+		}
+		for (int w = lane; w < MATES * kBigMarginU16; w += 32) (&ws.bigm[0][0])[w] = out_is_zero ? (uint16_t)0 : bmout[w];
+	}
 
 	int all_subreads[2] = {0, 0};
 	bool overflow = false;
@@ -812,7 +945,8 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 			if (overflow) return false;
 		}
 		if (MATES == 2 || max_vote[0] >= cfg.min_first) {
-			topk_warp<MATES>(ix, cfg, ws, strand, nslots, rlen, all_subreads, lane);
+			const uint32_t *const packed[2] = {area + n_words + 2 + strand * n_words, area + per_mate + n_words + 2 + strand * n_words};
+			topk_warp<MATES, JUNC>(ix, cfg, ws, strand, nslots, rlen, all_subreads, packed, lane);
 		} else if (lane == 0 && result_votes(ws.res[0][0]) < 1) {  // core.c:3217-3225
 			ws.res[0][0].w[3] &= ~0xffu;
 			int16_t used = (int16_t)(ws.res[0][0].w[2] >> 16);
@@ -829,6 +963,19 @@ __device__ __forceinline__ bool map_fragment(const DevIndex &ix, const VoteConfi
 #pragma unroll 1
 			for (int k = 0; k < mb; k++)
 				if (lane < kResultWords) out[m * mb + k].w[lane] = ws.res[m][k].w[lane];
+	}
+	if (JUNC) {
+		__syncwarp();
+		if (mb == kMaxBest) {
+			for (int w = lane; w < MATES * kMaxBest * 4; w += 32) (&jout[0].w[0])[w] = (&ws.jres[0][0].w[0])[w];
+		} else {
+#pragma unroll 1
+			for (int m = 0; m < MATES; m++)
+#pragma unroll 1
+				for (int k = 0; k < mb; k++)
+					if (lane < 4) jout[m * mb + k].w[lane] = ws.jres[m][k].w[lane];
+		}
+		for (int w = lane; w < MATES * kBigMarginU16; w += 32) bmout[w] = (&ws.bigm[0][0])[w];
 	}
 	if (VERIFY && verify) {
 #pragma unroll 1

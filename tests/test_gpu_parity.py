@@ -451,3 +451,52 @@ def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
                 assert t.n_simple_punted < chunk.n_frags // 10, f"tier 0 queued {t.n_simple_punted} of {chunk.n_frags} clean pairs"
     tier.close()
     plain.close()
+
+
+@pytest.mark.parametrize("paired", [False, True], ids=["se", "pe"])
+def test_subjunc_spliced_reads_warp_and_scalar_paths(paired, oracle_mod, tmp_path):
+    """subjunc on a 2 Mbp genome with planted GT..AG / CT..AC introns and 20 k reads from the spliced transcripts (errors,
+    mixed lengths, reads longer than 160 bp): the warp kernel's junction search (warp_minor_half, big-margin records) and the
+    scalar path (SRCUDA_WARP_JUNC=0) against the oracle -- bigtable, subjunc_result_t and big-margin tables byte for byte;
+    then a second pass over the same tables (read-modify-write)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    from subread_b200.binding import Mapper
+    from subread_b200.index_build import build_index
+    fa, faS = str(tmp_path / "g.fa"), str(tmp_path / "gS.fa")
+    gen_data.write_genome(fa, 4, 500000, seed=77, repeats=100)
+    gen_data.write_spliced(fa, faS, str(tmp_path / "sj"), 14000, 100, 5, paired, mixed_len=True)
+    gen_data.write_spliced(fa, faS, str(tmp_path / "sjl"), 6000, 200, 5, paired)       # same seed: the same introns
+    prefix = str(tmp_path / "idx")
+    build_index(faS, prefix, gapped=True, use_gpu=True)
+    idx = oracle_mod.OracleIndex(prefix)
+    params = VoteParams.defaults(paired, True)
+    mappers = {"warp": Mapper(0)}
+    os.environ["SRCUDA_WARP_JUNC"] = "0"
+    try:
+        mappers["scalar"] = Mapper(0)
+    finally:
+        del os.environ["SRCUDA_WARP_JUNC"]
+    n_junc = 0
+    for name in ("sj", "sjl"):
+        chunk = load_fastq(str(tmp_path / f"{name}_R1.fastq"), str(tmp_path / f"{name}_R2.fastq") if paired else None)
+        jo = {}
+        ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, junc_state=jo, threads=8)
+        n_junc += int((jo["junc"]["minor_votes"] > 0).sum())
+        for which, m in mappers.items():
+            m.index_load(prefix, 0)
+            js = {}
+            got, _ = m.vote_chunk(chunk, params, junc_state=js)
+            t = m.timing()
+            assert got.tobytes() == ora.tobytes(), f"{name}/{which}"
+            assert js["junc"].tobytes() == jo["junc"].tobytes(), f"{name}/{which}"
+            assert (js["big_margin"] == jo["big_margin"]).all(), f"{name}/{which}"
+            assert (t.n_overflow == chunk.n_frags) == (which == "scalar"), f"{name}/{which}: {t.n_overflow} of {chunk.n_frags} on the scalar path"
+            jo2 = {k: v.copy() for k, v in jo.items()}
+            got2, _ = m.vote_chunk(chunk, params, out_align=got.copy().reshape(-1), junc_state=js)
+            ora2, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora.copy(), junc_state=jo2, threads=8)
+            assert got2.tobytes() == ora2.tobytes() and js["junc"].tobytes() == jo2["junc"].tobytes(), f"{name}/{which} second pass"
+            assert (js["big_margin"] == jo2["big_margin"]).all()
+    assert n_junc > 1000, "the spliced reads are meant to exercise the junction search"
+    for m in mappers.values():
+        m.close()
