@@ -31,6 +31,9 @@ constexpr int kWarpsPerBlock = 8;
 #ifndef SR_MIN_BLOCKS
 #define SR_MIN_BLOCKS 5   // resident blocks (x 8 warps) per SM the register allocation is planned for: the kernel is latency-bound, 40 warps beat 24 (A/B in profiles/)
 #endif
+#ifndef SR_JUNC_MIN_BLOCKS
+#define SR_JUNC_MIN_BLOCKS 4   // the warp kernel with subjunc's junction search: 64 registers (A/B against 3 and 5)
+#endif
 constexpr int kScalarThreads = 32;
 constexpr int kScalarBlocksPerSM = 1;        // overflow queue of the warp kernel: a handful of fragments
 constexpr int kScalarBlocksPerSMAll = 16;    // every fragment takes the scalar path (subjunc, forced): fill the SMs
@@ -57,7 +60,7 @@ struct ChunkArgs {
 };
 
 template <int MATES, int GAP, bool VERIFY, bool JUNC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, SR_MIN_BLOCKS)   // (also with the junction search: 5 x 8 warps beat 3 x 8 with fewer spills)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, JUNC ? SR_JUNC_MIN_BLOCKS : SR_MIN_BLOCKS)
 k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_words, int warp_bytes)
 {
 	extern __shared__ __align__(16) uint8_t smem[];

@@ -717,7 +717,7 @@ __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &
 			// the slots in the reference's visiting order (row, rank in row), for the big-margin record and the minor-half search
 			int rank = 0;
 #pragma unroll 1
-			for (int u = 0; u < kWarpSlots; u++) rank += __shfl_sync(kFull, key, u) < key ? 1 : 0;
+			for (int u = 0; u < nslots[m]; u++) rank += __shfl_sync(kFull, key, u) < key ? 1 : 0;   // (the valid slots are lanes 0 .. nslots - 1)
 			if (valid) ws.order[m][rank] = (uint8_t)lane;
 			__syncwarp();
 			// insert_big_margin_record on the first level's walk over the table (:2281), which stops with the candidate list
