@@ -339,6 +339,8 @@ struct srcuda_handle {
 	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
 	bool use_simple_tier_pe = true;  // SRCUDA_SIMPLE_TIER_PE=0 disables its paired-end form only
 	bool use_warp_junc = true;       // SRCUDA_WARP_JUNC=0: subjunc fragments all take the scalar path
+	bool use_tier_junc = true;       // SRCUDA_TIER_JUNC=0: subjunc chunks skip the thread-per-fragment tier
+	int simple_junc_smem_set[4][3] = {};
 	int simple_pe_smem_set[4][3] = {};
 	int simple_smem_set[4][3] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
@@ -603,7 +605,8 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	if (ev) CU(h, cudaEventRecord(ev[0], s));
 	sr::ChunkArgs aw = a;
 	// tier 0: one thread per single-end fragment of a chunk whose bigtable slice is zero (sr_simple.cuh)
-	const bool tier0 = !scalar_only && !cfg.do_junctions && h->use_simple_tier && !cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	const bool tier0 = !scalar_only && (!cfg.do_junctions || (h->use_tier_junc && cfg.big_margin_record_size <= 12)) && h->use_simple_tier &&
+	                   !cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
 	                   cfg.min_second <= cfg.min_first && cfg.top_scores >= 2 && cfg.max_vote_simples >= 2;
 	if (tier0) {
 		const int threads = sr::kSimpleThreads;
@@ -621,9 +624,23 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		                                                              a.len, a.n_frags, max_len, clusters, a.out, q0,              \
 		                                                              bs.counters + 2, a.bad_reads);                               \
 	} while (0)
+#define SR_LAUNCH_SIMPLE_J(G, U)                                                                                                     \
+	do {                                                                                                                             \
+		const int jsmem = sr::simple_junc_smem_bytes(max_len, clusters);                                                              \
+		if (jsmem > h->simple_junc_smem_set[G][U]) {                                                                                 \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, jsmem)));          \
+			h->simple_junc_smem_set[G][U] = jsmem;                                                                                   \
+		}                                                                                                                            \
+		sr::k_map_simple<G, U, true><<<(unsigned)blocks, threads, jsmem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes,    \
+		                                                                     a.off, a.len, a.n_frags, max_len, clusters, a.out, q0, \
+		                                                                     bs.counters + 2, a.bad_reads, a.junc, a.big_margin);  \
+	} while (0)
 #define SR_LAUNCH_SIMPLE(G)                                                                                                          \
 	do {                                                                                                                             \
-		if (h->ix.direct) SR_LAUNCH_SIMPLE_U(G, 2);                                                                                  \
+		if (cfg.do_junctions) {                                                                                                      \
+			if (h->ix.direct) SR_LAUNCH_SIMPLE_J(G, 2);                                                                              \
+			else SR_LAUNCH_SIMPLE_J(G, 0);                                                                                           \
+		} else if (h->ix.direct) SR_LAUNCH_SIMPLE_U(G, 2);                                                                           \
 		else if (h->ix.uniq_bits) SR_LAUNCH_SIMPLE_U(G, 1);                                                                          \
 		else SR_LAUNCH_SIMPLE_U(G, 0);                                                                                               \
 	} while (0)
@@ -633,6 +650,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		default: SR_LAUNCH_SIMPLE(3); break;
 		}
 #undef SR_LAUNCH_SIMPLE_U
+#undef SR_LAUNCH_SIMPLE_J
 #undef SR_LAUNCH_SIMPLE
 		CU(h, cudaGetLastError());
 		h->timing.n_launches++;
@@ -765,6 +783,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
 	const char *st = getenv("SRCUDA_SIMPLE_TIER");
 	if (st && st[0] == '0') h->use_simple_tier = false;
+	const char *tj = getenv("SRCUDA_TIER_JUNC");
+	if (tj && tj[0] == '0') h->use_tier_junc = false;
 	const char *wj = getenv("SRCUDA_WARP_JUNC");
 	if (wj && wj[0] == '0') h->use_warp_junc = false;
 	const char *stp = getenv("SRCUDA_SIMPLE_TIER_PE");

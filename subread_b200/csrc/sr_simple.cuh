@@ -753,15 +753,23 @@ __device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const Simple
 	}
 }
 
+#endif  // __CUDACC__
+}  // namespace sr
+#include "sr_simple_junc.cuh"   // the junction half for subjunc chunks (needs the definitions above)
+namespace sr {
+#if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
+
 // k_map_simple: thread t of block b maps single-end fragment 128 b + t of a chunk whose bigtable slice is all
 // zero.  Writes the fragment's result slots, or queues the fragment for the warp kernel (its slots are then zero).
 // Every warp works on its own 32 fragments and its own slice of shared memory: there is no block-wide barrier.
 // Dynamic shared memory: simple_smem_bytes(max_len, clusters).
-template <int GAP, int MODE>
-__global__ void __launch_bounds__(kSimpleThreads, SR_SIMPLE_MIN_BLOCKS)
+// JUNC (subjunc): also the fragment's subjunc_result_t slots (jout) and big-margin record (bmout), both all zero on entry;
+// dynamic shared memory simple_junc_smem_bytes(max_len, clusters).
+template <int GAP, int MODE, bool JUNC = false>
+__global__ void __launch_bounds__(kSimpleThreads, JUNC ? 4 : SR_SIMPLE_MIN_BLOCKS)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
              const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int clusters, ResultWords *out, uint32_t *queue,
-             uint32_t *queue_count, uint32_t *bad_reads)
+             uint32_t *queue_count, uint32_t *bad_reads, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
 {
 	extern __shared__ uint4 smem4[];
 	constexpr unsigned kFullMask = 0xffffffffu;
@@ -838,13 +846,25 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	C.base = reinterpret_cast<uint32_t *>(stage) + lane;
 	C.n = 0;
 	C.cap = clusters;
+	// subjunc: the fragment's subjunc_result_t slots so far / being built and its big-margin record, behind the block's other areas
+	uint32_t *jblock = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem4) + simple_smem_bytes(max_len, clusters));
+	uint32_t *J = jblock + t, *JT = J + kMaxBest * 4 * kSimpleThreads;
+	uint16_t *bm = reinterpret_cast<uint16_t *>(jblock + 2 * kMaxBest * 4 * kSimpleThreads + 6 * t);
+	if (JUNC) {
+#pragma unroll
+		for (int i = 0; i < kMaxBest * 4; i++) J[i * kSimpleThreads] = 0u;
+#pragma unroll
+		for (int i = 0; i < 12; i++) bm[i] = 0;
+	}
 	if (active && !punt) {
 		// a read shorter than 16 bases goes through two empty passes (core.c:3116)
 		int step = 65536;
 		const int applied = L >= 16 ? subread_schedule(L, GAP, cfg.total_subreads, &step) : 0;
 #pragma unroll 1
 		for (int strand = 0; strand < 2 && !punt; strand++) {        // one copy of the pass in the instruction cache
-			if (!simple_pass<GAP, MODE>(ix, cfg, pk + strand * n_words * kSimpleThreads, L, applied, step, C)) punt = true;
+			const uint32_t *pass = pk + strand * n_words * kSimpleThreads;
+			if (!simple_pass<GAP, MODE>(ix, cfg, pass, L, applied, step, C)) punt = true;
+			else if (JUNC) simple_merge_junc<GAP>(ix, cfg, C, strand, applied, step, res, J, JT, bm, TierText{pass, 0}, L);
 			else simple_merge<GAP>(cfg, C, strand, applied, step, res);
 		}
 	}
@@ -886,7 +906,7 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 					uint32_t *dk = d + k * kResultWords;
 					if (kind == 1) {
 						dk[0] = r.pos;
-						dk[1] = ((r.meta >> 8) & 0xffu) ? (uint32_t)kCoreNegStrand : 0u;
+						dk[1] = ((r.meta >> 8) & 1u) ? (uint32_t)kCoreNegStrand : 0u;
 						dk[2] = (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16);
 						dk[4] = ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16);
 						dk[15] = r.cov;
@@ -926,6 +946,17 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 			for (int i = lane; i < total; i += 32) __stcs(dst + i, 0u);
 		}
 	}
+	if (JUNC) {     // the same for the warp's subjunc_result_t slots and big-margin records
+		const int64_t nf = min((int64_t)32, n_frags - fw0);
+		uint32_t *jd = reinterpret_cast<uint32_t *>(jout + (size_t)fw0 * mb);
+		const int jtotal = (int)nf * mb * 4;
+#pragma unroll 1
+		for (int i = lane; i < jtotal; i += 32) jd[i] = 0u;
+		uint16_t *bd = bmout + (size_t)fw0 * kBigMarginU16;
+		const int btotal = (int)nf * kBigMarginU16;
+#pragma unroll 1
+		for (int i = lane; i < btotal; i += 32) bd[i] = 0;
+	}
 	__syncwarp();   // orders the scattered stores after the zero-fill
 	if (!active || punt) return;
 	ResultWords *dst = out + (size_t)f * mb;
@@ -936,13 +967,25 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 		const uint32_t kind = r.meta & 0xffu;
 		if (kind == 1) {
 			__stcs(&dst[k].w[0], r.pos);
-			__stcs(&dst[k].w[1], ((r.meta >> 8) & 0xffu) ? (uint32_t)kCoreNegStrand : 0u);
+			__stcs(&dst[k].w[1], (((r.meta >> 8) & 1u) ? (uint32_t)kCoreNegStrand : 0u) | (JUNC ? (r.meta >> 12) & 7u : 0u));
 			__stcs(&dst[k].w[2], (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16));
 			__stcs(&dst[k].w[4], ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16));
 			__stcs(&dst[k].w[15], r.cov);
 		} else if (kind == 2) {
 			__stcs(&dst[k].w[2], (uint32_t)(uint16_t)r.used << 16);
 		}
+	}
+	if (JUNC) {
+#pragma unroll 1
+		for (int k = 0; k < mb; k++)
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const uint32_t w = J[(k * 4 + i) * kSimpleThreads];
+				if (w) jout[(size_t)f * mb + k].w[i] = w;
+			}
+#pragma unroll 1
+		for (int i = 0; i < 12; i++)
+			if (bm[i]) bmout[(size_t)f * kBigMarginU16 + i] = bm[i];
 	}
 #endif
 }
