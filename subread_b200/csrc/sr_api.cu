@@ -340,7 +340,7 @@ struct srcuda_handle {
 	bool use_simple_tier_pe = true;  // SRCUDA_SIMPLE_TIER_PE=0 disables its paired-end form only
 	bool use_warp_junc = true;       // SRCUDA_WARP_JUNC=0: subjunc fragments all take the scalar path
 	bool use_tier_junc = true;       // SRCUDA_TIER_JUNC=0: subjunc chunks skip the thread-per-fragment tier
-	int simple_junc_smem_set[4][3] = {};
+	int simple_junc_smem_set[4][3] = {}, simple_pe_junc_smem_set[4][3] = {};
 	int simple_pe_smem_set[4][3] = {};
 	int simple_smem_set[4][3] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
@@ -658,7 +658,8 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		aw.in_count = bs.counters + 2;
 	}
 	// ... and its paired-end form: one thread per fragment, pair scoring per thread (sr_simple_pe.cuh)
-	const bool tier0_pe = !scalar_only && !cfg.do_junctions && h->use_simple_tier && h->use_simple_tier_pe && cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	const bool tier0_pe = !scalar_only && (!cfg.do_junctions || (h->use_tier_junc && cfg.big_margin_record_size <= 12)) && h->use_simple_tier &&
+	                      h->use_simple_tier_pe && cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
 	                      cfg.max_vote_combinations <= 3 && cfg.max_vote_simples >= 24 && cfg.multi_best_reads <= sr::kMaxBest;
 	if (tier0_pe) {
 		const int threads = sr::kSimpleThreads;
@@ -676,12 +677,27 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		                                                                 a.len, a.n_frags, max_len, clusters, a.out, q0,           \
 		                                                                 bs.counters + 2, a.bad_reads);                            \
 	} while (0)
+#define SR_LAUNCH_PE_J(G, U)                                                                                                         \
+	do {                                                                                                                             \
+		if (jsmem > h->simple_pe_junc_smem_set[G][U]) {                                                                              \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<G, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, jsmem)));       \
+			h->simple_pe_junc_smem_set[G][U] = jsmem;                                                                                \
+		}                                                                                                                            \
+		sr::k_map_simple_pe<G, U, true><<<(unsigned)blocks, threads, jsmem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes,  \
+		                                                                        a.off, a.len, a.n_frags, max_len, clusters, a.out,  \
+		                                                                        q0, bs.counters + 2, a.bad_reads, a.junc,           \
+		                                                                        a.big_margin);                                      \
+	} while (0)
 #define SR_LAUNCH_PE(G)                                                                                                              \
 	do {                                                                                                                             \
-		if (h->ix.direct) SR_LAUNCH_PE_U(G, 2);                                                                                      \
+		if (cfg.do_junctions) {                                                                                                      \
+			if (h->ix.direct) SR_LAUNCH_PE_J(G, 2);                                                                                  \
+			else SR_LAUNCH_PE_J(G, 0);                                                                                               \
+		} else if (h->ix.direct) SR_LAUNCH_PE_U(G, 2);                                                                               \
 		else SR_LAUNCH_PE_U(G, 0);                                                                                                   \
 	} while (0)
-		if (smem <= 227 * 1024) {
+		const int jsmem = sr::simple_pe_junc_smem_bytes(max_len, clusters);
+		if ((cfg.do_junctions ? jsmem : smem) <= 227 * 1024) {
 			switch (h->ix.index_gap) {
 			case 1: SR_LAUNCH_PE(1); break;
 			case 2: SR_LAUNCH_PE(2); break;
@@ -693,6 +709,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			aw.in_count = bs.counters + 2;
 		}
 #undef SR_LAUNCH_PE_U
+#undef SR_LAUNCH_PE_J
 #undef SR_LAUNCH_PE
 	}
 	if (ev) CU(h, cudaEventRecord(ev[3], s));

@@ -19,6 +19,7 @@
 // (reverse-strand keys are derived from it) and the two mates of a strand pass share one pool of vote clusters.
 #pragma once
 #include "sr_simple.cuh"
+#include "sr_simple_junc.cuh"
 
 namespace sr {
 
@@ -43,6 +44,11 @@ SR_HD int simple_pe_smem_bytes(int max_len, int pool)
 	return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_pe_warp_bytes(max_len, pool);
 }
 
+// subjunc: per thread the subjunc_result_t slots of both mates so far (24 words), those of the mate being emitted (12) and the
+// two big-margin records (2 x 12 u16)
+constexpr int kPeJuncWordsPerThread = 2 * kMaxBest * 4 + kMaxBest * 4 + 12;
+SR_HD int simple_pe_junc_smem_bytes(int max_len, int pool) { return simple_pe_smem_bytes(max_len, pool) + kSimpleThreads * kPeJuncWordsPerThread * 4; }
+
 #if defined(__CUDACC__) && !defined(SR_HOST_ONLY)
 
 // The fragment's result slots so far, [mate][k] x 4 words, interleaved over the warp's lanes.  used_subreads_in_vote
@@ -65,9 +71,13 @@ struct PeResults {
 
 // process_voting_junction_PE_topK for one strand pass of a paired-end fragment.  Returns false when a candidate list does
 // not fit (the fragment is then queued for the warp kernel).  simple_pass has left every cluster's vote count in word 2.
-template <int GAP>
+// JUNC (subjunc): J = both mates' subjunc_result_t slots ([m][k][4] words at stride kSimpleThreads), JT = the three slots of the
+// mate being emitted, bm = the two big-margin records (12 u16 each), text0 / text1 = the mates' reads of this pass.
+template <int GAP, bool JUNC = false>
 __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteConfig &cfg, const SimpleClusters &C0, const SimpleClusters &C1,
-                                                const PeResults &R, int strand, int applied0, int applied1, int step0, int step1, int len0, int len1)
+                                                const PeResults &R, int strand, int applied0, int applied1, int step0, int step1, int len0, int len1,
+                                                uint32_t *J = nullptr, uint32_t *JT = nullptr, uint16_t *bm = nullptr,
+                                                const TierText *text0 = nullptr, const TierText *text1 = nullptr)
 {
 	const int mb = cfg.multi_best_reads, ts = cfg.top_scores;
 	// Shortcut for the pass on the wrong strand of a fresh fragment (a handful of one-vote random hits per mate on a large
@@ -83,11 +93,14 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 #pragma unroll 1
 			for (int k = 0; k < mb; k++) top = max(top, (int)R.w(m, k, 1));
 		}
-		if (top < cfg.min_first) {
+		if (top < cfg.min_first && (!JUNC || top < 1)) {       // (subjunc walks the table for its big-margin records whenever a slot has votes)
 #pragma unroll 1
 			for (int m = 0; m < 2; m++)
 #pragma unroll 1
-				for (int k = 0; k < mb; k++) R.w(m, k, 1) = 0u;
+				for (int k = 0; k < mb; k++) {
+					R.w(m, k, 1) = 0u;
+					if (JUNC) J[((m * kMaxBest + k) * 4) * kSimpleThreads] &= 0x0000ffffu;
+				}
 			return true;
 		}
 	}
@@ -110,19 +123,28 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 		for (int lv = 0; lv < ts; lv++) {
 			const int want = lv == 0 ? t0 : (lv == 1 ? t1 : t2);
 			if (want < 1 || t0 - want > cfg.max_vote_number_cutoff) break;
-			if (want >= cfg.min_second) {
+			const bool walk_all = JUNC && lv == 0 && cfg.big_margin_filtering;   // insert_big_margin_record visits every slot (:2281)
+			if (want >= cfg.min_second || walk_all) {
+				const int top_last = ts == 1 ? t0 : (ts == 2 ? t1 : t2);
 				unsigned done = 0;
 #pragma unroll 1
 				for (;;) {                                   // table slots of this level in (row, rank in row) order
 					int best = -1, best_key = 0x7fffffff;
 #pragma unroll 1
 					for (int c = 0; c < C.n; c++)
-						if (!((done >> c) & 1u) && (int)C.w(c, 2) == want) {
+						if (!((done >> c) & 1u) && (walk_all ? (C.w(c, 1) >> 31) != 0 : (int)C.w(c, 2) == want)) {
 							const int key = C.order(c);
 							if (key < best_key) { best_key = key; best = c; }
 						}
 					if (best < 0) break;
 					done |= 1u << best;
+					const int vv = (int)C.w(best, 2);
+					if (walk_all && vv >= top_last) {
+						int cs, ce;
+						tier_cluster_cov<GAP>(C.w(best, 1), m ? step1 : step0, &cs, &ce);
+						sc_big_margin_insert(cfg, bm + 12 * m, vv, cs, ce, m ? len1 : len0, strand != 0);
+					}
+					if (vv != want || want < cfg.min_second) continue;
 					if (n == kPeCand) return false;
 					list |= (unsigned long long)best << (8 * n);
 					n++;
@@ -232,14 +254,33 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 					nr[k].pos = C.w(src, 0); nr[k].votes = (int)C.w(src, 2); nr[k].used = applied;
 					nr[k].meta = 1u | ((uint32_t)strand << 8) | ((uint32_t)(s_first + 1) << 16) | ((uint32_t)(s_last + 1) << 24);
 					nr[k].cov = (uint32_t)o_first | ((uint32_t)(o_last + 16) << 16);
-				} else nr[k] = R.get(m, src - 32);
+					if (JUNC) {                              // the slot's subjunc_result_t: minor half / donor search
+						uint32_t *jr = JT + k * 4 * kSimpleThreads;
+						jr[0] = jr[kSimpleThreads] = jr[2 * kSimpleThreads] = jr[3 * kSimpleThreads] = 0u;
+						nr[k].meta |= tier_minor_half<GAP>(ix, cfg, C, src, step, m ? len1 : len0, m ? *text1 : *text0, jr) << 12;
+					}
+				} else {
+					nr[k] = R.get(m, src - 32);
+					if (JUNC) {
+#pragma unroll
+						for (int i = 0; i < 4; i++) JT[(k * 4 + i) * kSimpleThreads] = J[((m * kMaxBest + src - 32) * 4 + i) * kSimpleThreads];
+					}
+				}
 			}
 		}
 #pragma unroll
 		for (int k = 0; k < kMaxBest; k++) {
 			if (k < mb) {
-				if (k < cursor) R.put(m, k, nr[k]);
-				else R.w(m, k, 1) = 0u;
+				if (k < cursor) {
+					R.put(m, k, nr[k]);
+					if (JUNC) {
+#pragma unroll
+						for (int i = 0; i < 4; i++) J[((m * kMaxBest + k) * 4 + i) * kSimpleThreads] = JT[(k * 4 + i) * kSimpleThreads];
+					}
+				} else {
+					R.w(m, k, 1) = 0u;
+					if (JUNC) J[((m * kMaxBest + k) * 4) * kSimpleThreads] &= 0x0000ffffu;   // minor_votes = 0
+				}
 			}
 		}
 	}
@@ -248,11 +289,11 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 
 // k_map_simple_pe: thread t of block b maps paired-end fragment 128 b + t (reads 2f and 2f + 1 of the chunk) of a chunk
 // whose bigtable slice is all zero.  Dynamic shared memory: simple_pe_smem_bytes(max_len, clusters).
-template <int GAP, int MODE>
-__global__ void __launch_bounds__(kSimpleThreads, 4)
+template <int GAP, int MODE, bool JUNC = false>
+__global__ void __launch_bounds__(kSimpleThreads, JUNC ? 3 : 4)
 k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
                 const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int pool, ResultWords *out, uint32_t *queue,
-                uint32_t *queue_count, uint32_t *bad_reads)
+                uint32_t *queue_count, uint32_t *bad_reads, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
 {
 	extern __shared__ uint4 smem4[];
 	constexpr unsigned kFullMask = 0xffffffffu;
@@ -340,6 +381,15 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 	R.base = reinterpret_cast<uint32_t *>(stage + area_cap) + lane;
 #pragma unroll 1
 	for (int i = 0; i < 2 * kMaxBest * kPeResWords; i++) R.base[i * 32] = 0u;
+	uint32_t *jblock = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem4) + simple_pe_smem_bytes(max_len, pool));
+	uint32_t *J = jblock + t, *JT = J + 2 * kMaxBest * 4 * kSimpleThreads;
+	uint16_t *bm = reinterpret_cast<uint16_t *>(jblock + 3 * kMaxBest * 4 * kSimpleThreads + 12 * t);
+	if (JUNC) {
+#pragma unroll 1
+		for (int i = 0; i < 2 * kMaxBest * 4; i++) J[i * kSimpleThreads] = 0u;
+#pragma unroll 1
+		for (int i = 0; i < 24; i++) bm[i] = 0;
+	}
 	SimpleClusters C0, C1;
 	C0.base = C1.base = reinterpret_cast<uint32_t *>(stage) + lane;
 	C0.n = C1.n = 0;
@@ -360,7 +410,12 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 			}
 			if (!simple_pass<GAP, MODE, true>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0,
 			                                  rc ? (m ? L1 : L0) : 0)) punt = true;
-			else if (m == 1 && !simple_pe_merge<GAP>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1)) punt = true;
+			else if (m == 1) {
+				if (JUNC) {
+					const TierText tx0{pk, (strand ^ rev0) ? L0 : 0}, tx1{pk + n_words * kSimpleThreads, (strand ^ rev1) ? L1 : 0};
+					if (!simple_pe_merge<GAP, true>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1, J, JT, bm, &tx0, &tx1)) punt = true;
+				} else if (!simple_pe_merge<GAP>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1)) punt = true;
+			}
 		}
 	}
 	__syncwarp();
@@ -389,8 +444,34 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 			for (int i = lane; i < total; i += 32) __stcs(dst + i, 0u);
 		}
 	}
+	if (JUNC) {     // the same for the warp's subjunc_result_t slots and big-margin records
+		const int64_t nf = min((int64_t)32, n_frags - fw0);
+		uint32_t *jd = reinterpret_cast<uint32_t *>(jout + (size_t)fw0 * 2 * mb);
+		const int jtotal = (int)nf * 2 * mb * 4;
+#pragma unroll 1
+		for (int i = lane; i < jtotal; i += 32) jd[i] = 0u;
+		uint16_t *bd = bmout + (size_t)fw0 * 2 * kBigMarginU16;
+		const int btotal = (int)nf * 2 * kBigMarginU16;
+#pragma unroll 1
+		for (int i = lane; i < btotal; i += 32) bd[i] = 0;
+	}
 	__syncwarp();
 	if (!active || punt) return;
+	if (JUNC) {
+#pragma unroll 1
+		for (int m = 0; m < 2; m++) {
+#pragma unroll 1
+			for (int k = 0; k < mb; k++)
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					const uint32_t w = J[((m * kMaxBest + k) * 4 + i) * kSimpleThreads];
+					if (w) jout[((size_t)f * 2 + m) * mb + k].w[i] = w;
+				}
+#pragma unroll 1
+			for (int i = 0; i < 12; i++)
+				if (bm[12 * m + i]) bmout[((size_t)f * 2 + m) * kBigMarginU16 + i] = bm[12 * m + i];
+		}
+	}
 #pragma unroll 1
 	for (int m = 0; m < 2; m++)
 #pragma unroll 1
@@ -399,7 +480,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 			ResultWords *d = out + ((size_t)f * 2 + m) * mb + k;
 			if ((r.meta & 0xffu) == 1u) {
 				__stcs(&d->w[0], r.pos);
-				__stcs(&d->w[1], ((r.meta >> 8) & 0xffu) ? (uint32_t)kCoreNegStrand : 0u);
+				__stcs(&d->w[1], (((r.meta >> 8) & 1u) ? (uint32_t)kCoreNegStrand : 0u) | (JUNC ? (r.meta >> 12) & 7u : 0u));
 				__stcs(&d->w[2], (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16));
 				__stcs(&d->w[4], ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16));
 				__stcs(&d->w[15], r.cov);

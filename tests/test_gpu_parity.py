@@ -456,8 +456,8 @@ def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
 @pytest.mark.parametrize("paired", [False, True], ids=["se", "pe"])
 def test_subjunc_spliced_reads_warp_and_scalar_paths(paired, oracle_mod, tmp_path):
     """subjunc on a 2 Mbp genome with planted GT..AG / CT..AC introns and 20 k reads from the spliced transcripts (errors,
-    mixed lengths, reads longer than 160 bp): the warp kernel's junction search (warp_minor_half, big-margin records) and the
-    scalar path (SRCUDA_WARP_JUNC=0) against the oracle -- bigtable, subjunc_result_t and big-margin tables byte for byte;
+    mixed lengths, reads longer than 160 bp): the thread-per-fragment tier's and the warp kernel's junction search
+    (tier_minor_half, warp_minor_half, big-margin records) and the scalar path (SRCUDA_WARP_JUNC=0) against the oracle -- bigtable, subjunc_result_t and big-margin tables byte for byte;
     then a second pass over the same tables (read-modify-write)."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_data
@@ -492,6 +492,8 @@ def test_subjunc_spliced_reads_warp_and_scalar_paths(paired, oracle_mod, tmp_pat
             assert js["junc"].tobytes() == jo["junc"].tobytes(), f"{name}/{which}"
             assert (js["big_margin"] == jo["big_margin"]).all(), f"{name}/{which}"
             assert (t.n_overflow == chunk.n_frags) == (which == "scalar"), f"{name}/{which}: {t.n_overflow} of {chunk.n_frags} on the scalar path"
+            if which == "warp" and name == "sj":    # ... after the thread-per-fragment tier took the separable fragments
+                assert 0 < t.n_simple_punted < 0.7 * chunk.n_frags, f"tier queued {t.n_simple_punted} of {chunk.n_frags}"
             jo2 = {k: v.copy() for k, v in jo.items()}
             got2, _ = m.vote_chunk(chunk, params, out_align=got.copy().reshape(-1), junc_state=js)
             ora2, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora.copy(), junc_state=jo2, threads=8)
