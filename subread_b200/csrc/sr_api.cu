@@ -664,7 +664,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	if (tier0_pe) {
 		const int threads = sr::kSimpleThreads;
 		const int64_t blocks = (a.n_frags + threads - 1) / threads;
-		const int clusters = h->ix.direct ? sr::kPePoolDense : sr::kPePool;     // one pool for both mates
+		const int clusters = h->ix.direct ? (cfg.do_junctions ? sr::kPePoolDenseJunc : sr::kPePoolDense) : sr::kPePool;     // one pool for both mates
 		const int smem = sr::simple_pe_smem_bytes(max_len, clusters);
 		uint32_t *q0 = (uint32_t *)bs.queue0.p;
 #define SR_LAUNCH_PE_U(G, U)                                                                                                         \

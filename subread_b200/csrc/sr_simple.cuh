@@ -633,7 +633,10 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 	}
 	if (have_p) C.put(0, P);
 #pragma unroll 1
-	for (int c = 0; c < C.n; c++) C.w(c, 2) = (uint32_t)C.votes(c);   // the subread sets have served: word 2 becomes the vote count
+	for (int c = 0; c < C.n; c++) {                                   // the subread sets have served: word 2 becomes the vote count,
+		C.w(c, 2) = (uint32_t)C.votes(c);                             // word 3 is free for the merge (paired-end tier: chromosome memo)
+		C.w(c, 3) = 0u;
+	}
 	return true;
 }
 

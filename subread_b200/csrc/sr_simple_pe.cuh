@@ -24,6 +24,9 @@
 namespace sr {
 
 constexpr int kPeCand = 8;        // candidates per mate
+constexpr int kPeCandJunc = 16;   // ... in subjunc mode, where minimum_subread_for_first_read = 1 makes every one-vote slot of a
+                                  // dense table's wrong-strand pass a candidate
+constexpr int kPePoolDenseJunc = 32;
 constexpr int kPeResWords = 4;    // SimpleResult in shared memory: pos, votes, meta (+ used subreads), coverage
 constexpr int kPePool = 12;       // vote clusters of both mates of one strand pass, shared (the second mate takes what
 constexpr int kPePoolDense = 26;  // the first one left); dense tables: a handful of one-vote random hits per mate
@@ -104,7 +107,8 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 			return true;
 		}
 	}
-	unsigned long long cl[2] = {0ull, 0ull};       // candidate sources, 8 bits each: cluster index, or 32 + k for an old result
+	constexpr int KC = JUNC ? kPeCandJunc : kPeCand;
+	unsigned long long cl[2] = {0ull, 0ull}, ch[2] = {0ull, 0ull};   // candidate sources, 8 bits each: cluster index, or 32 + k for an old result
 	int nc[2] = {0, 0};
 #pragma unroll 1
 	for (int m = 0; m < 2; m++) {
@@ -118,7 +122,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 			if (v > 0) simple_update_top(ts, t0, t1, t2, v);
 		}
 		int n = 0;
-		unsigned long long list = 0ull;
+		unsigned long long list = 0ull, list_hi = 0ull;
 #pragma unroll 1
 		for (int lv = 0; lv < ts; lv++) {
 			const int want = lv == 0 ? t0 : (lv == 1 ? t1 : t2);
@@ -145,24 +149,27 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 						sc_big_margin_insert(cfg, bm + 12 * m, vv, cs, ce, m ? len1 : len0, strand != 0);
 					}
 					if (vv != want || want < cfg.min_second) continue;
-					if (n == kPeCand) return false;
-					list |= (unsigned long long)best << (8 * n);
+					if (n == KC) return false;
+					if (n < 8) list |= (unsigned long long)best << (8 * n);
+					else list_hi |= (unsigned long long)best << (8 * (n - 8));
 					n++;
 				}
 			}
 #pragma unroll 1
 			for (int k = 0; k < mb; k++)
 				if ((int)R.w(m, k, 1) == want) {
-					if (n == kPeCand) return false;
-					list |= (unsigned long long)(32 + k) << (8 * n);
+					if (n == KC) return false;
+					if (n < 8) list |= (unsigned long long)(32 + k) << (8 * n);
+					else list_hi |= (unsigned long long)(32 + k) << (8 * (n - 8));
 					n++;
 				}
 		}
 		cl[m] = list;
+		ch[m] = list_hi;
 		nc[m] = n;
 	}
 	const int n0 = nc[0], n1 = nc[1];
-	auto cand_src = [&](int m, int i) { return (int)((cl[m] >> (8 * i)) & 0xffull); };
+	auto cand_src = [&](int m, int i) { return (int)(((i < 8 ? cl[m] : ch[m]) >> (8 * (i & 7))) & 0xffull); };
 	auto cand_pos = [&](int m, int src) { return src < 32 ? (m ? C1 : C0).w(src, 0) : R.w(m, src - 32, 0); };
 	auto cand_votes = [&](int m, int src) { return src < 32 ? (int)(m ? C1 : C0).w(src, 2) : (int)R.w(m, src - 32, 1); };
 
@@ -179,7 +186,23 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 			if (max(v1, v2) < cfg.min_first) continue;
 			if (!located) { re1 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(0, si), &chr1, &lp1); located = true; }
 			int chr2, lp2, is_pe;
-			const int re2 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(1, sj), &chr2, &lp2);
+			int re2;
+			// The second mate's candidates are located once per strand pass: the chromosome found by the binary search is
+			// remembered in the cluster's spare word 3 (bit 31 set, re in bits 16-17, chromosome in bits 0-15).
+			const uint32_t memo = sj < 32 ? C1.w(sj, 3) : 0u;
+			if (memo >> 31) {
+				re2 = (int)((memo >> 16) & 3u);
+				if (re2 == 2) re2 = -1;
+				chr2 = (int)(memo & 0xffffu);
+				lp2 = 0;
+				if (re2 == 0) {
+					const uint32_t linear = cand_pos(1, sj);
+					lp2 = (int)(chr2 == 0 ? linear : linear - ix.chr_offsets[chr2 - 1]) - ix.padding;
+				}
+			} else {
+				re2 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(1, sj), &chr2, &lp2);
+				if (sj < 32 && (re2 != 0 || chr2 < 0x10000)) C1.w(sj, 3) = 0x80000000u | ((uint32_t)(re2 < 0 ? 2 : re2) << 16) | (uint32_t)(re2 == 0 ? chr2 : 0);
+			}
 			const int weight = pair_weight(re1, chr1, lp1, re2, chr2, lp2, len0, len1, cfg.min_pair_dist, cfg.max_pair_dist, &is_pe);
 			if (!is_pe && min(v1, v2) < cfg.min_first) continue;
 			const uint32_t key = (uint32_t)((v1 + v2) * weight) * 4096u + (uint32_t)(4095 - (i * n1 + j));
