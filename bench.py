@@ -234,6 +234,17 @@ def bind_to_gpu_numa_node(gpu_index):
         mine = near & set(os.sched_getaffinity(0))
         if mine:
             os.sched_setaffinity(0, mine)
+        # ... and prefer the GPU's memory node for the pinned buffers even when none of its CPUs is ours (set_mempolicy
+        # MPOL_PREFERRED; a no-op on single-node boxes and where the container's memory set forbids it)
+        import ctypes
+        pci = pynvml.nvmlDeviceGetPciInfo(h).busId
+        pci = (pci.decode() if isinstance(pci, bytes) else pci).lower()
+        if pci.startswith("0000") and len(pci.split(":")[0]) == 8:
+            pci = pci[4:]
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read().strip())
+        if node >= 0:
+            mask = ctypes.c_ulong(1 << node)
+            ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))   # x86-64 set_mempolicy
     except Exception:
         pass
 
