@@ -118,14 +118,14 @@ typedef struct {
  * library's own stream). */
 typedef struct {
 	float ms_total;          /* first H2D to last D2H (or kernels only for the device variant) */
-	float ms_kernel_vote;    /* k_map_simple + k_map_warp (pack+lookup+vote+topK(+verify)), summed over batches */
+	float ms_kernel_vote;    /* k_map_simple / k_map_simple_pe + k_map_warp (pack+lookup+vote+topK(+verify)), summed over batches */
 	float ms_kernel_overflow;/* exact slow path for fragments whose vote table left shared memory */
 	uint64_t n_overflow;     /* fragments that took the slow path */
 	uint64_t h2d_bytes;
 	uint64_t d2h_bytes;
 	uint32_t n_launches;     /* kernels launched */
 	uint32_t n_batches;
-	float ms_kernel_simple;  /* part of ms_kernel_vote spent in the one-thread-per-fragment tier (k_map_simple) */
+	float ms_kernel_simple;  /* part of ms_kernel_vote spent in the one-thread-per-fragment tier (k_map_simple, k_map_simple_pe) */
 	uint32_t _pad;
 	uint64_t n_simple_punted;/* fragments that tier handed on to the warp kernel */
 } srcuda_timing;
@@ -219,7 +219,14 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out);
 
 /* Debug/validation switch: route every fragment through the exact slow path (one thread per
- * fragment, full 30x24 table) instead of the warp kernel.  Results must not change. */
+ * fragment, full 30x24 table) instead of the fast tiers.  Results must not change.
+ * Environment switches read at srcuda_open, all for A/B runs and cross-checks (defaults in brackets):
+ *   SRCUDA_SIMPLE_TIER [1]     thread-per-fragment tier (single- and paired-end)
+ *   SRCUDA_SIMPLE_TIER_PE [1]  its paired-end form only
+ *   SRCUDA_TIER_JUNC [1]       subjunc chunks in that tier
+ *   SRCUDA_WARP_JUNC [1]       subjunc fragments in the warp kernel (0: scalar path)
+ *   SRCUDA_ACCEL [auto]        lookup accelerators: 0 none, 1 Bloom words, 2 bucket records, 3 both, 4 direct filter
+ *   SRCUDA_BATCH_FRAGS, SRCUDA_SCALAR_BLOCKS, SRCUDA_L2_PERSIST, SRCUDA_L2_FETCH, SRCUDA_UNIQ   tuning knobs */
 int srcuda_set_force_slow_path(srcuda_handle *h, int on);
 
 /* Measured random 32-byte-sector gather bandwidth over `table_bytes` of HBM (GB/s): the

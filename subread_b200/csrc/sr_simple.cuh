@@ -22,8 +22,9 @@
 // Everything else -- kv values within tolerance of each other (indels), two phases of one subread
 // hitting one kv, more than kSimpleClusters distinct kv, characters that are not A/C/G/T, reads longer
 // than kSimpleMaxLen -- is PUNTED untouched to the warp kernel through a queue, so the tiered path
-// returns the reference's result for every input.  Paired-end and subjunc chunks, chunks merged into a
-// non-zero bigtable, and verification requests skip this tier altogether.
+// returns the reference's result for every input.  Paired-end fragments have their own form of this tier
+// (sr_simple_pe.cuh), subjunc chunks add the junction half (sr_simple_junc.cuh); chunks merged into a non-zero
+// bigtable (later index blocks) and verification requests skip the tier altogether.
 //
 // Data movement is organised per block so that the per-thread work stays in registers and shared memory:
 //   1. the block's read text (contiguous in the chunk) is staged into shared memory with coalesced

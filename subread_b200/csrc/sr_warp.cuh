@@ -15,6 +15,8 @@
 //   top-K     process_voting_junction_PE_topK (core-junction.c:2199-2530) with warp reductions;
 //             pair combinations are scored lane-parallel
 //   verify    XOR + __popc of packed read vs packed genome (match_chro, gene-value-index.c:856)
+//   junction  (subjunc, JUNC) the minor-half / donor search of copy_vote_to_alignment_res on the shared-memory table
+//             and the big-margin records (warp_minor_half; shared with the scalar path through sc_donor_score_t)
 //
 // A table that needs a 33rd slot sets `overflow`; the fragment is then finished by the exact
 // scalar path (sr_scalar.cuh) and nothing of it is written here.
