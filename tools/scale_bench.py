@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", type=int, default=20000, help="fragments compared with the oracle (0 = none)")
     ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--error-rate", type=float, default=0.0, help="per-base substitution rate of the reads (0 = error-free)")
     ap.add_argument("--modes", default="", help="comma-separated list of se, pe, sj-se, sj-pe run on the same index (overrides --paired/--subjunc)")
     args = ap.parse_args()
 
@@ -124,6 +125,14 @@ def run_mode(args, torch, dev, m, a, desc, codes, letters, lin_first, n_chr, L, 
                 t = torch.where(rc[:, None], letters[(3 - fw).flip(1).long()], letters[fw.long()])
                 text[lo:hi, 0] = t
                 truth[lo:hi, 0] = lin_first[c] + s
+        if args.error_rate > 0:      # substitutions: a wrong base is the right one's code + 1..3 (mod 4) in "AGCT"
+            flat = text.reshape(-1)
+            for lo in range(0, flat.numel(), 1 << 28):
+                part = flat[lo:lo + (1 << 28)]
+                hit = torch.rand(part.numel(), generator=g, device=dev) < args.error_rate
+                shift = torch.randint(1, 4, (part.numel(),), generator=g, device=dev, dtype=torch.uint8)
+                code = (part == ord("G")).to(torch.uint8) + 2 * (part == ord("C")).to(torch.uint8) + 3 * (part == ord("T")).to(torch.uint8)
+                part[:] = torch.where(hit, letters[((code + shift) & 3).long()], part)
         return text.reshape(-1), truth
 
     lens = [int(x) for x in args.sweep.split(",")] if args.sweep else [args.read_len]
@@ -171,7 +180,7 @@ def run_mode(args, torch, dev, m, a, desc, codes, letters, lin_first, n_chr, L, 
         line = {"tool": "scale_bench", "workload": f"{args.genome_mbp:g} Mbp synthetic genome ({n_chr}x{L} bp), "
                 f"{'full' if args.full else 'gapped'} one-block index ({desc.n_items} items, {desc.buckets_number} buckets, "
                 f"{desc.n_items / desc.buckets_number:.1f} per bucket), {RL} bp {'PE' if args.paired else 'SE'} reads"
-                f"{', subjunc mode' if args.subjunc else ''}",
+                f"{', subjunc mode' if args.subjunc else ''}{', %.3g substitutions per base' % args.error_rate if args.error_rate else ''}",
                 "fragments_per_step": R, "reads_per_s": R * mates / (ms * 1e-3), "fragments_per_s": R / (ms * 1e-3), "ms_per_step": ms,
                 "kernel_ms": kern / args.steps, "tier0_ms": simple / args.steps, "tier0_punted_fraction": punted / args.steps / R,
                 "overflow_fraction": n_over / args.steps / R, "overflow_ms": over / args.steps, "gpu_launches": launches,
