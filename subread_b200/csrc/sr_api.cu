@@ -340,7 +340,8 @@ struct srcuda_handle {
 	bool use_simple_tier_pe = true;  // SRCUDA_SIMPLE_TIER_PE=0 disables its paired-end form only
 	bool use_warp_junc = true;       // SRCUDA_WARP_JUNC=0: subjunc fragments all take the scalar path
 	bool use_tier_junc = true;       // SRCUDA_TIER_JUNC=0: subjunc chunks skip the thread-per-fragment tier
-	int simple_junc_smem_set[4][3] = {}, simple_pe_junc_smem_set[4][3] = {};
+	int simple_junc_smem_set[4][3] = {}, simple_pe_junc_smem_set[4][3] = {}, simple_rmw_smem_set[4][3] = {}, simple_pe_rmw_smem_set[4][3] = {};
+	bool use_tier_rmw = true;        // SRCUDA_TIER_RMW=0: chunks merged into a non-zero bigtable (later index blocks) skip the thread-per-fragment tier
 	int simple_pe_smem_set[4][3] = {};
 	int simple_smem_set[4][3] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
@@ -606,7 +607,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	sr::ChunkArgs aw = a;
 	// tier 0: one thread per single-end fragment of a chunk whose bigtable slice is zero (sr_simple.cuh)
 	const bool tier0 = !scalar_only && (!cfg.do_junctions || (h->use_tier_junc && cfg.big_margin_record_size <= 12)) && h->use_simple_tier &&
-	                   !cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	                   !cfg.is_paired && (a.out_zero || (h->use_tier_rmw && !cfg.do_junctions)) && !a.verify && bs.queue0.p &&
 	                   cfg.min_second <= cfg.min_first && cfg.top_scores >= 2 && cfg.max_vote_simples >= 2;
 	if (tier0) {
 		const int threads = sr::kSimpleThreads;
@@ -624,6 +625,17 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		                                                              a.len, a.n_frags, max_len, clusters, a.out, q0,              \
 		                                                              bs.counters + 2, a.bad_reads);                               \
 	} while (0)
+#define SR_LAUNCH_SIMPLE_R(G, U)                                                                                                     \
+	do {                                                                                                                             \
+		if (smem > h->simple_rmw_smem_set[G][U]) {                                                                                   \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));    \
+			h->simple_rmw_smem_set[G][U] = smem;                                                                                     \
+		}                                                                                                                            \
+		sr::k_map_simple<G, U, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,              \
+		                                                                           a.text_bytes, a.off, a.len, a.n_frags, max_len,   \
+		                                                                           clusters, a.out, q0, bs.counters + 2,            \
+		                                                                           a.bad_reads);                                    \
+	} while (0)
 #define SR_LAUNCH_SIMPLE_J(G, U)                                                                                                     \
 	do {                                                                                                                             \
 		const int jsmem = sr::simple_junc_smem_bytes(max_len, clusters);                                                              \
@@ -640,6 +652,9 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		if (cfg.do_junctions) {                                                                                                      \
 			if (h->ix.direct) SR_LAUNCH_SIMPLE_J(G, 2);                                                                              \
 			else SR_LAUNCH_SIMPLE_J(G, 0);                                                                                           \
+		} else if (!a.out_zero) {                                                                                                    \
+			if (h->ix.direct) SR_LAUNCH_SIMPLE_R(G, 2);                                                                              \
+			else SR_LAUNCH_SIMPLE_R(G, 0);                                                                                           \
 		} else if (h->ix.direct) SR_LAUNCH_SIMPLE_U(G, 2);                                                                           \
 		else if (h->ix.uniq_bits) SR_LAUNCH_SIMPLE_U(G, 1);                                                                          \
 		else SR_LAUNCH_SIMPLE_U(G, 0);                                                                                               \
@@ -650,6 +665,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		default: SR_LAUNCH_SIMPLE(3); break;
 		}
 #undef SR_LAUNCH_SIMPLE_U
+#undef SR_LAUNCH_SIMPLE_R
 #undef SR_LAUNCH_SIMPLE_J
 #undef SR_LAUNCH_SIMPLE
 		CU(h, cudaGetLastError());
@@ -659,7 +675,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	}
 	// ... and its paired-end form: one thread per fragment, pair scoring per thread (sr_simple_pe.cuh)
 	const bool tier0_pe = !scalar_only && (!cfg.do_junctions || (h->use_tier_junc && cfg.big_margin_record_size <= 12)) && h->use_simple_tier &&
-	                      h->use_simple_tier_pe && cfg.is_paired && a.out_zero && !a.verify && bs.queue0.p &&
+	                      h->use_simple_tier_pe && cfg.is_paired && (a.out_zero || (h->use_tier_rmw && !cfg.do_junctions)) && !a.verify && bs.queue0.p &&
 	                      cfg.max_vote_combinations <= 3 && cfg.max_vote_simples >= 24 && cfg.multi_best_reads <= sr::kMaxBest;
 	if (tier0_pe) {
 		const int threads = sr::kSimpleThreads;
@@ -677,6 +693,17 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		                                                                 a.len, a.n_frags, max_len, clusters, a.out, q0,           \
 		                                                                 bs.counters + 2, a.bad_reads);                            \
 	} while (0)
+#define SR_LAUNCH_PE_R(G, U)                                                                                                         \
+	do {                                                                                                                             \
+		if (smem > h->simple_pe_rmw_smem_set[G][U]) {                                                                                \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<G, U, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			h->simple_pe_rmw_smem_set[G][U] = smem;                                                                                  \
+		}                                                                                                                            \
+		sr::k_map_simple_pe<G, U, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,           \
+		                                                                              a.text_bytes, a.off, a.len, a.n_frags,        \
+		                                                                              max_len, clusters, a.out, q0,                 \
+		                                                                              bs.counters + 2, a.bad_reads);                \
+	} while (0)
 #define SR_LAUNCH_PE_J(G, U)                                                                                                         \
 	do {                                                                                                                             \
 		if (jsmem > h->simple_pe_junc_smem_set[G][U]) {                                                                              \
@@ -693,6 +720,9 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		if (cfg.do_junctions) {                                                                                                      \
 			if (h->ix.direct) SR_LAUNCH_PE_J(G, 2);                                                                                  \
 			else SR_LAUNCH_PE_J(G, 0);                                                                                               \
+		} else if (!a.out_zero) {                                                                                                    \
+			if (h->ix.direct) SR_LAUNCH_PE_R(G, 2);                                                                                  \
+			else SR_LAUNCH_PE_R(G, 0);                                                                                               \
 		} else if (h->ix.direct) SR_LAUNCH_PE_U(G, 2);                                                                               \
 		else SR_LAUNCH_PE_U(G, 0);                                                                                                   \
 	} while (0)
@@ -709,6 +739,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			aw.in_count = bs.counters + 2;
 		}
 #undef SR_LAUNCH_PE_U
+#undef SR_LAUNCH_PE_R
 #undef SR_LAUNCH_PE_J
 #undef SR_LAUNCH_PE
 	}
@@ -800,6 +831,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
 	const char *st = getenv("SRCUDA_SIMPLE_TIER");
 	if (st && st[0] == '0') h->use_simple_tier = false;
+	const char *tr = getenv("SRCUDA_TIER_RMW");
+	if (tr && tr[0] == '0') h->use_tier_rmw = false;
 	const char *tj = getenv("SRCUDA_TIER_JUNC");
 	if (tj && tj[0] == '0') h->use_tier_junc = false;
 	const char *wj = getenv("SRCUDA_WARP_JUNC");

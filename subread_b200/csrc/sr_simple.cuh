@@ -769,7 +769,9 @@ namespace sr {
 // Dynamic shared memory: simple_smem_bytes(max_len, clusters).
 // JUNC (subjunc): also the fragment's subjunc_result_t slots (jout) and big-margin record (bmout), both all zero on entry;
 // dynamic shared memory simple_junc_smem_bytes(max_len, clusters).
-template <int GAP, int MODE, bool JUNC = false>
+// RMW (second and later index blocks): the slice holds the results of the blocks before; a fragment whose used slots all
+// have the plain form this tier produces itself (no indel, no junction bits) merges into them, any other is queued.
+template <int GAP, int MODE, bool JUNC = false, bool RMW = false>
 __global__ void __launch_bounds__(kSimpleThreads, JUNC ? 4 : SR_SIMPLE_MIN_BLOCKS)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
              const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int clusters, ResultWords *out, uint32_t *queue,
@@ -846,6 +848,28 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	SimpleResult res[kMaxBest];
 #pragma unroll
 	for (int k = 0; k < kMaxBest; k++) { res[k].pos = 0; res[k].votes = 0; res[k].used = 0; res[k].meta = 0; res[k].cov = 0; }
+	uint32_t old_w3 = 0;                     // RMW: word 3 of slot 0, for the single-end fall-through (core.c:3220)
+	if (RMW && active && !punt) {
+		const ResultWords *src = out + (size_t)f * mb;
+#pragma unroll
+		for (int k = 0; k < kMaxBest; k++) {
+			if (k >= mb) break;
+			const uint32_t w1 = src[k].w[1], w2 = src[k].w[2], w3 = src[k].w[3];
+			res[k].votes = (int)(int16_t)(w2 & 0xffffu);
+			res[k].used = (int)(int16_t)(w2 >> 16);
+			if (k == 0) { old_w3 = w3; res[0].meta = 2u; }
+			if (res[k].votes >= 1) {
+				uint32_t rest = w3 | src[k].w[16] | (w1 & ~(uint32_t)kCoreNegStrand);
+#pragma unroll
+				for (int w = 5; w < 15; w++) rest |= src[k].w[w];
+				const uint32_t w4 = src[k].w[4], first = w4 & 0xffffu, last = w4 >> 16;
+				if (rest != 0 || first < 1 || first > 63 || last < 1 || last > 63) punt = true;
+				res[k].pos = src[k].w[0];
+				res[k].meta = 1u | ((w1 & (uint32_t)kCoreNegStrand) ? 0x100u : 0u) | (first << 16) | (last << 24);
+				res[k].cov = src[k].w[15];
+			}
+		}
+	}
 	SimpleClusters C;
 	C.base = reinterpret_cast<uint32_t *>(stage) + lane;
 	C.n = 0;
@@ -883,6 +907,34 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	}
 
 	// ---- 4. the warp's bigtable slice (copy_vote_to_alignment_res image of each slot, core-junction.c:1058-1072) ----
+	if (RMW) {
+		// Later index block: nothing is cleared.  An emitted slot is a complete record (the reference copies a zeroed temporary,
+		// :2516); any other slot only gets its selected_votes / used_subreads word, whatever else it holds stays (:2517).
+		if (!active || punt) return;
+		ResultWords *dst = out + (size_t)f * mb;
+#pragma unroll
+		for (int k = 0; k < kMaxBest; k++) {
+			if (k >= mb) break;
+			const SimpleResult &r = res[k];
+			const uint32_t kind = r.meta & 0xffu, w2 = (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16);
+			if (kind == 1) {
+#pragma unroll
+				for (int w = 0; w < kResultWords; w++) {
+					uint32_t v = 0;
+					if (w == 0) v = r.pos;
+					else if (w == 1) v = ((r.meta >> 8) & 1u) ? (uint32_t)kCoreNegStrand : 0u;
+					else if (w == 2) v = w2;
+					else if (w == 4) v = ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16);
+					else if (w == 15) v = r.cov;
+					dst[k].w[w] = v;
+				}
+			} else {
+				dst[k].w[2] = w2;
+				if (k == 0 && kind == 2) dst[0].w[3] = old_w3 & ~0xffu;
+			}
+		}
+		return;
+	}
 #if SR_SIMPLE_SMEM_OUT
 	// Composed in the warp's shared area (the clusters are dead now) and stored as whole 16-byte pieces, half a warp
 	// at a time: no partial-sector writes, so nothing has to be read back from DRAM to merge them.

@@ -312,7 +312,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 
 // k_map_simple_pe: thread t of block b maps paired-end fragment 128 b + t (reads 2f and 2f + 1 of the chunk) of a chunk
 // whose bigtable slice is all zero.  Dynamic shared memory: simple_pe_smem_bytes(max_len, clusters).
-template <int GAP, int MODE, bool JUNC = false>
+template <int GAP, int MODE, bool JUNC = false, bool RMW = false>
 __global__ void __launch_bounds__(kSimpleThreads, JUNC ? 3 : 4)
 k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
                 const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int pool, ResultWords *out, uint32_t *queue,
@@ -404,6 +404,32 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 	R.base = reinterpret_cast<uint32_t *>(stage + area_cap) + lane;
 #pragma unroll 1
 	for (int i = 0; i < 2 * kMaxBest * kPeResWords; i++) R.base[i * 32] = 0u;
+	if (RMW && active && !punt) {
+		// later index block: the slots of the blocks before, if they have the plain form this tier writes itself
+		const ResultWords *src = out + (size_t)f * 2 * mb;
+#pragma unroll 1
+		for (int m = 0; m < 2; m++)
+#pragma unroll 1
+			for (int k = 0; k < mb; k++) {
+				const ResultWords &o = src[m * mb + k];
+				const uint32_t w1 = o.w[1], w2 = o.w[2];
+				SimpleResult r;
+				r.pos = 0; r.meta = 0; r.cov = 0;
+				r.votes = (int)(int16_t)(w2 & 0xffffu);
+				r.used = (int)(w2 >> 16) & 63;
+				if (r.votes >= 1) {
+					uint32_t rest = o.w[3] | o.w[16] | (w1 & ~(uint32_t)kCoreNegStrand) | ((w2 >> 16) & ~63u);
+#pragma unroll 1
+					for (int w = 5; w < 15; w++) rest |= o.w[w];
+					const uint32_t w4 = o.w[4], first = w4 & 0xffffu, last = w4 >> 16;
+					if (rest != 0 || first < 1 || first > 63 || last < 1 || last > 63) punt = true;
+					r.pos = o.w[0];
+					r.meta = 1u | ((w1 & (uint32_t)kCoreNegStrand) ? 0x100u : 0u) | (first << 16) | (last << 24);
+					r.cov = o.w[15];
+				} else if ((w2 >> 16) & ~63u) punt = true;        // (a used_subreads value the packed slot cannot hold)
+				R.put(m, k, r);
+			}
+	}
 	uint32_t *jblock = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem4) + simple_pe_smem_bytes(max_len, pool));
 	uint32_t *J = jblock + t, *JT = J + 2 * kMaxBest * 4 * kSimpleThreads;
 	uint16_t *bm = reinterpret_cast<uint16_t *>(jblock + 3 * kMaxBest * 4 * kSimpleThreads + 12 * t);
@@ -451,6 +477,30 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 	}
 
 	// ---- 3. the warp's bigtable slice: zero-fill, then the few non-zero words on top (see k_map_simple) ----
+	if (RMW) {      // later index block: complete records for the emitted slots, the votes / used word for the others
+		if (!active || punt) return;
+#pragma unroll 1
+		for (int m = 0; m < 2; m++)
+#pragma unroll 1
+			for (int k = 0; k < mb; k++) {
+				const SimpleResult r = R.get(m, k);
+				ResultWords *d = out + ((size_t)f * 2 + m) * mb + k;
+				const uint32_t w2 = (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16);
+				if ((r.meta & 0xffu) == 1u) {
+#pragma unroll
+					for (int w = 0; w < kResultWords; w++) {
+						uint32_t v = 0;
+						if (w == 0) v = r.pos;
+						else if (w == 1) v = ((r.meta >> 8) & 1u) ? (uint32_t)kCoreNegStrand : 0u;
+						else if (w == 2) v = w2;
+						else if (w == 4) v = ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16);
+						else if (w == 15) v = r.cov;
+						d->w[w] = v;
+					}
+				} else d->w[2] = w2;
+			}
+		return;
+	}
 	{
 		const int64_t nf = min((int64_t)32, n_frags - fw0);
 		uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)fw0 * 2 * mb);

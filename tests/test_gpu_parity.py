@@ -209,16 +209,18 @@ def test_multi_block_index_merges_across_blocks(mapper, oracle_mod, tmp_path):
     n_blocks = len([f for f in os.listdir(tmp_path) if f.endswith(".b.tab")])
     assert n_blocks > 1
     gen_data.write_reads(fa, str(tmp_path / "pe"), 5000, 120, 2, True, 0.01, 0.2, True, 0.002)
-    chunk = load_fastq(str(tmp_path / "pe_R1.fastq"), str(tmp_path / "pe_R2.fastq"))
-    params = VoteParams.defaults(True)
-    got, ora = None, None
-    for b in range(n_blocks):
-        mapper.index_load(prefix, b)
-        got, _ = mapper.vote_chunk(chunk, params, out_align=None if got is None else got.reshape(-1))
-        idx = oracle_mod.OracleIndex(prefix, b)
-        ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora)
-        idx.close()
-        assert got.tobytes() == ora.tobytes(), f"block {b}"
+    gen_data.write_reads(fa, str(tmp_path / "se"), 8000, 150, 3, False, 0.005, 0.05, False, 0.001)
+    for paired in (True, False):
+        chunk = load_fastq(str(tmp_path / ("pe_R1.fastq" if paired else "se_R1.fastq")), str(tmp_path / "pe_R2.fastq") if paired else None)
+        params = VoteParams.defaults(paired)
+        got, ora = None, None
+        for b in range(n_blocks):
+            mapper.index_load(prefix, b)
+            got, _ = mapper.vote_chunk(chunk, params, out_align=None if got is None else got.reshape(-1))
+            idx = oracle_mod.OracleIndex(prefix, b)
+            ora, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora)
+            idx.close()
+            assert got.tobytes() == ora.tobytes(), f"block {b} ({'PE' if paired else 'SE'})"
 
 
 def test_index_builder_output_loads_and_maps(mapper, oracle_mod, tmp_path):
@@ -333,6 +335,15 @@ def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_pa
         ref, _ = plain.vote_chunk(chunk, params)
         assert ref.tobytes() == ora.tobytes(), name + " (tier 0 off)"
         assert plain.timing().n_simple_punted == 0
+        # a second pass over the same table, as a later index block would make it (read-modify-write form of the tier)
+        ora2, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora.copy(), threads=8)
+        got2, _ = mapper.vote_chunk(chunk, params, out_align=got.copy().reshape(-1))
+        t2 = mapper.timing()
+        assert got2.tobytes() == ora2.tobytes(), name + " (second pass)"
+        ref2, _ = plain.vote_chunk(chunk, params, out_align=ref.copy().reshape(-1))
+        assert ref2.tobytes() == ora2.tobytes(), name + " (second pass, tier 0 off)"
+        if name in ("clean", "scattered") and not kind.endswith("repeats"):
+            assert t2.ms_kernel_simple > 0 and t2.n_simple_punted < chunk.n_frags // 10, f"{name}: second pass queued {t2.n_simple_punted}"
         if name in ("clean", "scattered") and not kind.endswith("repeats"):
             assert t.n_simple_punted < chunk.n_frags // 20, f"{name}: tier 0 punted {t.n_simple_punted} of {chunk.n_frags}"
     plain.close()
@@ -447,6 +458,11 @@ def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
             ref, _ = plain.vote_chunk(chunk, params)
             assert ref.tobytes() == ora.tobytes(), f"{name}/{vi} (tier off)"
             assert plain.timing().n_simple_punted == 0
+            ora2, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora.copy(), threads=8)
+            got2, _ = tier.vote_chunk(chunk, params, out_align=got.copy().reshape(-1))
+            assert got2.tobytes() == ora2.tobytes(), f"{name}/{vi} (second pass)"
+            if name == "clean" and kind != "repeats" and vi == 0:
+                assert tier.timing().n_simple_punted < chunk.n_frags // 5, "second pass: read-modify-write tier"
             if name == "clean" and kind != "repeats" and vi == 0:
                 assert t.n_simple_punted < chunk.n_frags // 10, f"tier 0 queued {t.n_simple_punted} of {chunk.n_frags} clean pairs"
     tier.close()
