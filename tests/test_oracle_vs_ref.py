@@ -111,3 +111,47 @@ def test_voting_step_against_real_do_voting_multiblock(oracle_mod, tmp_path):
             idx.close()
         ok, bad = used_slots_equal(got, ref_align, ignore_gapped_flag=True)
         assert ok, describe_mismatch(got, ref_align, bad)
+
+
+@pytest.mark.parametrize("blocks", ["one_block", "split_index"])
+def test_subjunc_voting_step_against_real_subjunc(blocks, oracle_mod, tmp_path):
+    """subjunc (do_breakpoint_detection) beyond the golden fixture: a 1.2 Mbp genome with planted GT..AG / CT..AC
+    introns, spliced SE reads of mixed lengths (some > 160 bp) and spliced pairs, through the reference's own subjunc
+    (ref_dump_subjunc: real do_voting + copy_vote_to_alignment_res' junction half, core-junction.c:1073-1334) — alignment
+    table, subjunc_result_t table and big-margin records against the oracle; also with an index split into blocks
+    (-M 1), where every table is merged read-modify-write across blocks (core.c:3567-3613)."""
+    from conftest import junc_tables_equal
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    fa, faS = str(tmp_path / "g.fa"), str(tmp_path / "gS.fa")
+    gen_data.write_genome(fa, 3, 400000, seed=11, repeats=40 if blocks == "split_index" else 0)
+    gen_data.write_spliced(fa, faS, str(tmp_path / "se"), 3000, 180, 21, False, mixed_len=True)   # same seed: same introns
+    gen_data.write_spliced(fa, faS, str(tmp_path / "pe"), 2000, 100, 21, True)
+    prefix = str(tmp_path / "idx")
+    cmd = [os.path.join(REF_DIR, "bin", "subread-buildindex"), "-o", prefix]
+    cmd += ["-M", "1"] if blocks == "split_index" else ["-B"]
+    subprocess.check_call(cmd + [faS], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    n_blocks = len([f for f in os.listdir(tmp_path) if f.endswith(".b.tab")])
+    assert (n_blocks > 1) == (blocks == "split_index")
+    for r1, r2 in ((str(tmp_path / "se_R1.fastq"), None), (str(tmp_path / "pe_R1.fastq"), str(tmp_path / "pe_R2.fastq"))):
+        bt = str(tmp_path / "bt.bin")
+        if os.path.exists(bt):
+            os.remove(bt)
+        cmd = [os.path.join(REF_DIR, "ref_dump_subjunc"), "-T", "1", "-i", prefix, "-r", r1, "--SAMoutput", "-o", str(tmp_path / "o.sam")]
+        if r2:
+            cmd += ["-R", r2]
+        subprocess.check_call(cmd, env=dict(os.environ, SRDUMP_BIGTABLE=bt), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dump = oracle_mod.read_bigtable_dump(bt)
+        assert len(dump) == 1
+        exp, exp_junc, exp_bm = dump[0]["align"], dump[0]["junc"], dump[0]["big_margin"]
+        assert (exp_junc["minor_votes"] > 0).sum() > 100, "the input must exercise the junction search"
+        chunk = load_fastq(r1, r2)
+        params = VoteParams.defaults(r2 is not None, True)
+        got, js = None, {}
+        for b in range(n_blocks):
+            idx = oracle_mod.OracleIndex(prefix, b)
+            got, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=got, junc_state=js)
+            idx.close()
+        ok, bad = used_slots_equal(got, exp, ignore_gapped_flag=True)
+        assert ok, describe_mismatch(got, exp, bad)
+        assert junc_tables_equal(got, js["junc"], js["big_margin"], exp_junc, np.ascontiguousarray(exp_bm[:, :, :9]).reshape(-1, 9))
