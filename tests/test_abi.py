@@ -65,3 +65,29 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle/" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_null_arguments_are_argument_errors(lib):
+    """Every entry point checks its pointers before touching a device: a NULL handle (or out pointer) is
+    SRCUDA_ERR_ARG (5) or a no-op, never a crash -- the error behaviour include/subread_cuda.h documents.
+    No device work is started, so this runs without a GPU."""
+    ERR_ARG = 5
+    null = ctypes.c_void_p(None)
+    assert lib.srcuda_open(0, None) == ERR_ARG
+    assert b"out is NULL" in lib.srcuda_last_error(None)
+    assert lib.srcuda_index_load(null, b"/nonexistent/prefix", 0) == ERR_ARG
+    assert lib.srcuda_index_replicate(null, null) == ERR_ARG
+    blob = ctypes.create_string_buffer(4096)
+    assert lib.srcuda_index_export_ipc(null, blob, ctypes.c_size_t(4096)) == ERR_ARG
+    assert lib.srcuda_index_import_ipc(null, blob, ctypes.c_size_t(4096)) == ERR_ARG
+    desc = binding.IndexDesc()
+    assert lib.srcuda_index_describe(null, ctypes.byref(desc)) == ERR_ARG
+    assert lib.srcuda_set_force_slow_path(null, 1) == ERR_ARG
+    assert lib.srcuda_get_timing(null, None) == ERR_ARG
+    params = VoteParams.defaults(False)
+    assert lib.srcuda_vote_chunk(null, ctypes.byref(params), None, None, None, ctypes.c_int64(0), 0, 1, None, None, None, None) == ERR_ARG
+    gb = ctypes.c_double()
+    assert lib.srcuda_measure_gather_bandwidth(null, ctypes.c_uint64(1 << 22), 1, ctypes.byref(gb)) == ERR_ARG
+    lib.srcuda_index_unload(null)      # no-ops
+    lib.srcuda_close(null)
+    lib.srcuda_host_free(None)
