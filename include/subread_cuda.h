@@ -179,6 +179,43 @@ void srcuda_index_unload(srcuda_handle *h);
 void *srcuda_host_alloc(size_t bytes);
 void srcuda_host_free(void *p);
 
+/* ---- FASTQ batches (host side, no device work) ------------------------------------------ */
+
+#define SRCUDA_FASTQ_MORE 0 /* the buffer ran out inside or between records: refill from buf + consumed and call again */
+#define SRCUDA_FASTQ_FULL 1 /* max_reads records were indexed */
+#define SRCUDA_FASTQ_END 2  /* end of the input (at_eof), or a read that is empty after trimming: the reference ends its
+                             * input there (fetch_next_read_pair, core.c:1168-1208) */
+typedef struct {
+	int64_t n_reads;       /* records indexed by this call */
+	uint64_t consumed;     /* bytes of buf those records span; the next call starts at buf + consumed */
+	int32_t stop;          /* SRCUDA_FASTQ_* */
+	uint32_t max_len;      /* longest read indexed (max_read_len of srcuda_vote_chunk_device) */
+	uint64_t error_offset; /* with SRCUDA_ERR_FORMAT: offset of the byte the reference would report */
+} srcuda_fastq_batch;
+
+/* Indexes every complete record of a buffer of plain FASTQ text: the FASTQ branch of geinput_next_read_trim
+ * (input-files.c:982-1093; read_line_noempty :209, SKIP_LINE :650, trim_read_inner :716) for a whole batch at once
+ * instead of one call per read under the input mutex (core.c:1130).  Nothing is copied: read i of the call gets
+ * off[i*stride] = base_offset + its offset in buf and len[i*stride] (after trimming), so that with text = the
+ * caller's chunk buffer, base_offset = buf - text and stride = 1 the arrays are srcuda_vote_chunk's (single-end);
+ * stride = 2 interleaves the mates of two files (R2 written through off + 1, len + 1) for srcuda_reads_pack or a
+ * device-side gather.  name_off/name_len (cut at the first blank, at most 199 characters) and qual_off/qual_len are
+ * optional (NULL).  at_eof = 0: a record the buffer cuts short is left for the next call; at_eof != 0: the end of
+ * the buffer ends the last line, as EOF does.  max_reads bounds the arrays.  A record that does not start with '@'
+ * or lacks its '+' line returns SRCUDA_ERR_FORMAT (the reference prints "a format issue" and ends the input, :1003,
+ * :1041); the records in front of it are valid in `out`.  gzip input is inflated by the caller (seek-zlib.c). */
+int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof, int trim_5, int trim_3, int64_t max_reads,
+                       uint64_t base_offset, int64_t stride, uint64_t *off, uint16_t *len, uint64_t *name_off,
+                       uint16_t *name_len, uint64_t *qual_off, uint16_t *qual_len, srcuda_fastq_batch *out);
+
+/* Gathers indexed reads into the dense chunk layout of srcuda_vote_chunk: fragment f's mates back to back
+ * (read r = f*mates + m), off[r] non-decreasing from 0, *text_bytes = bytes written.  buf2 = NULL: single-end.
+ * The input half of fetch_next_read_pair (core.c:1121-1175) for a batch; mate strands stay as they are in the files
+ * (the voting step applies is_first/second_read_reversed itself). */
+int srcuda_reads_pack(const char *buf1, const uint64_t *off1, const uint16_t *len1, const char *buf2,
+                      const uint64_t *off2, const uint16_t *len2, int64_t n_frags, char *text, uint64_t text_capacity,
+                      uint64_t *off, uint16_t *len, uint64_t *text_bytes);
+
 /* ---- the voting step -------------------------------------------------------------------- */
 
 /* One chunk of reads against the resident index block: everything do_voting (core.c:3049)

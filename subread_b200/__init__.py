@@ -6,4 +6,4 @@ layouts, read batching and a ctypes binding.  There is no CPU fallback: every co
 point fails loudly when the CUDA library or a GPU is missing.
 """
 from .layout import MAPPING_RESULT, SUBJUNC_RESULT, VoteParams, used_slots_equal  # noqa: F401
-from .reads import ReadChunk, load_fastq, pack_reads, synthetic_reads  # noqa: F401
+from .reads import ReadChunk, load_fastq, load_fastq_indexed, pack_reads, synthetic_reads  # noqa: F401

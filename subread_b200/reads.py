@@ -73,6 +73,27 @@ def load_fastq(path1, path2=None, limit=None) -> ReadChunk:
     return pack_reads(s1, s2, names)
 
 
+def load_fastq_indexed(path1, path2=None, trim_5=0, trim_3=0) -> ReadChunk:
+    """The same chunk as ``load_fastq`` through the library's batch indexer (srcuda_fastq_split + srcuda_reads_pack,
+    subread_b200/csrc/sr_fastq.cpp): one pass over the file's bytes, no per-read Python."""
+    from .binding import fastq_split, reads_pack
+
+    def one(path):
+        with _open(path) as fh:
+            buf = np.frombuffer(fh.read(), dtype=np.uint8)
+        off, ln, _, ex = fastq_split(buf, True, trim_5, trim_3, want_names=True)
+        return buf, off, ln, ex
+
+    b1, o1, l1, ex = one(path1)
+    names = [b1[int(a):int(a) + int(n)].tobytes().decode() for a, n in zip(ex["name_off"], ex["name_len"])]
+    if path2:
+        b2, o2, l2, _ = one(path2)
+        text, off, ln = reads_pack(b1, o1, l1, b2, o2, l2)
+    else:
+        text, off, ln = reads_pack(b1, o1, l1)
+    return ReadChunk(text, off, ln, int(o1.shape[0]), path2 is not None, names)
+
+
 def synthetic_reads(genome: np.ndarray, n_frags: int, read_len: int, seed: int, is_paired=False,
                     insert=(200, 400), error_rate=0.0, indel_rate=0.0) -> ReadChunk:
     """Uniformly sampled reads from a uint8 ACGT genome array (one contig), both strands.

@@ -518,3 +518,26 @@ def test_subjunc_spliced_reads_warp_and_scalar_paths(paired, oracle_mod, tmp_pat
     assert n_junc > 1000, "the spliced reads are meant to exercise the junction search"
     for m in mappers.values():
         m.close()
+
+
+@pytest.mark.gpu
+def test_mapping_straight_from_fastq_bytes(mapper, golden_cases, golden_index_dir):
+    """Row f3: the chunk buffer is the FASTQ file's own bytes -- srcuda_fastq_split indexes the records in place
+    (names, '+' lines and qualities stay between the reads) and srcuda_vote_chunk maps them from there; the bigtable
+    is the golden one of the same reads."""
+    import gzip
+    from conftest import GOLDEN
+    from subread_b200 import ReadChunk
+    from subread_b200.binding import fastq_split
+    case = next(c for c in golden_cases if c["name"] == "se_gapped")
+    prefix, chunk, params, exp = load_case(case, golden_index_dir)
+    with gzip.open(os.path.join(GOLDEN, case["r1"]), "rb") as fh:
+        raw = np.frombuffer(fh.read(), dtype=np.uint8)
+    off, ln, b, _ = fastq_split(raw)
+    assert b.n_reads == chunk.n_frags and np.array_equal(ln, chunk.len)
+    in_place = ReadChunk(raw, np.append(off, np.uint64(raw.shape[0])), ln, chunk.n_frags, False, [])
+    mapper.index_load(prefix, 0)
+    got, _ = mapper.vote_chunk(in_place, params)
+    assert got.tobytes() == exp.tobytes()
+    got, ver = mapper.vote_chunk(in_place, params, want_verify=True)      # the warp kernel reads the same buffer
+    assert got.tobytes() == exp.tobytes()
