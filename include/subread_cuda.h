@@ -208,6 +208,14 @@ int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof, int trim_5
                        uint64_t base_offset, int64_t stride, uint64_t *off, uint16_t *len, uint64_t *name_off,
                        uint16_t *name_len, uint64_t *qual_off, uint16_t *qual_len, srcuda_fastq_batch *out);
 
+/* The same result from n_threads host threads: the buffer is cut at guessed record starts, every piece is parsed as
+ * an input of its own, and the pieces are accepted only if each one ends exactly where the next begins -- otherwise
+ * (blank-line oddities, broken records, a trimmed-empty read) the single-threaded loop above decides, so the outcome
+ * never depends on n_threads. */
+int srcuda_fastq_split_mt(const char *buf, uint64_t n_bytes, int at_eof, int trim_5, int trim_3, int64_t max_reads,
+                          uint64_t base_offset, int64_t stride, uint64_t *off, uint16_t *len, uint64_t *name_off,
+                          uint16_t *name_len, uint64_t *qual_off, uint16_t *qual_len, int n_threads, srcuda_fastq_batch *out);
+
 /* Gathers indexed reads into the dense chunk layout of srcuda_vote_chunk: fragment f's mates back to back
  * (read r = f*mates + m), off[r] non-decreasing from 0, *text_bytes = bytes written.  buf2 = NULL: single-end.
  * The input half of fetch_next_read_pair (core.c:1121-1175) for a batch; mate strands stay as they are in the files
@@ -215,6 +223,10 @@ int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof, int trim_5
 int srcuda_reads_pack(const char *buf1, const uint64_t *off1, const uint16_t *len1, const char *buf2,
                       const uint64_t *off2, const uint16_t *len2, int64_t n_frags, char *text, uint64_t text_capacity,
                       uint64_t *off, uint16_t *len, uint64_t *text_bytes);
+/* The same gather from n_threads host threads (sizes first, then disjoint stretches of text). */
+int srcuda_reads_pack_mt(const char *buf1, const uint64_t *off1, const uint16_t *len1, const char *buf2,
+                         const uint64_t *off2, const uint16_t *len2, int64_t n_frags, char *text, uint64_t text_capacity,
+                         uint64_t *off, uint16_t *len, int n_threads, uint64_t *text_bytes);
 
 /* ---- the voting step -------------------------------------------------------------------- */
 

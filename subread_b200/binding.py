@@ -23,7 +23,7 @@ EXPORTS = [
     "srcuda_index_describe", "srcuda_index_unload",
     "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device",
     "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth",
-    "srcuda_fastq_split", "srcuda_reads_pack",
+    "srcuda_fastq_split", "srcuda_fastq_split_mt", "srcuda_reads_pack", "srcuda_reads_pack_mt",
 ]
 
 
@@ -99,7 +99,10 @@ def load_library():
     L.srcuda_measure_gather_bandwidth.argtypes = [vp, u64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.srcuda_fastq_split.argtypes = [vp, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, u64, i64, vp, vp, vp, vp, vp, vp,
                                      ctypes.POINTER(FastqBatch)]
+    L.srcuda_fastq_split_mt.argtypes = [vp, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, u64, i64, vp, vp, vp, vp, vp, vp,
+                                        ctypes.c_int, ctypes.POINTER(FastqBatch)]
     L.srcuda_reads_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, u64, vp, vp, ctypes.POINTER(u64)]
+    L.srcuda_reads_pack_mt.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, u64, vp, vp, ctypes.c_int, ctypes.POINTER(u64)]
     _LIB = L
     return L
 
@@ -260,8 +263,8 @@ class Mapper:
         return out.value
 
 
-def fastq_split(buf: np.ndarray, at_eof=True, trim_5=0, trim_3=0, max_reads=None, base_offset=0, want_names=False):
-    """srcuda_fastq_split over a uint8 array of plain FASTQ text.  Returns (off, len, batch, extra): offsets into
+def fastq_split(buf: np.ndarray, at_eof=True, trim_5=0, trim_3=0, max_reads=None, base_offset=0, want_names=False, threads=1):
+    """srcuda_fastq_split (threads > 1: srcuda_fastq_split_mt) over a uint8 array of plain FASTQ text.  Returns (off, len, batch, extra): offsets into
     ``buf`` (+ base_offset) and lengths of the records the buffer holds completely, the FastqBatch verdict, and --
     with want_names -- a dict of name_off/name_len/qual_off/qual_len.  Raises SubreadCudaError on a format issue
     (the records in front of it are lost to the caller, as the reference stops there too)."""
@@ -276,16 +279,17 @@ def fastq_split(buf: np.ndarray, at_eof=True, trim_5=0, trim_3=0, max_reads=None
                      qual_off=np.empty(cap, np.uint64), qual_len=np.empty(cap, np.uint16))
     vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     b = FastqBatch()
-    rc = L.srcuda_fastq_split(vp(buf), buf.shape[0], int(bool(at_eof)), int(trim_5), int(trim_3), cap, int(base_offset), 1, vp(off), vp(ln),
-                              vp(extra["name_off"]) if want_names else None, vp(extra["name_len"]) if want_names else None,
-                              vp(extra["qual_off"]) if want_names else None, vp(extra["qual_len"]) if want_names else None, ctypes.byref(b))
+    rc = L.srcuda_fastq_split_mt(vp(buf), buf.shape[0], int(bool(at_eof)), int(trim_5), int(trim_3), cap, int(base_offset), 1, vp(off), vp(ln),
+                                 vp(extra["name_off"]) if want_names else None, vp(extra["name_len"]) if want_names else None,
+                                 vp(extra["qual_off"]) if want_names else None, vp(extra["qual_len"]) if want_names else None,
+                                 int(threads), ctypes.byref(b))
     n = int(b.n_reads)
     if rc:
         raise SubreadCudaError(f"srcuda_fastq_split: format issue at byte {b.error_offset} (rc={rc}, {n} records before it)")
     return off[:n], ln[:n], b, {k: v[:n] for k, v in extra.items()}
 
 
-def reads_pack(buf1, off1, len1, buf2=None, off2=None, len2=None):
+def reads_pack(buf1, off1, len1, buf2=None, off2=None, len2=None, threads=1):
     """srcuda_reads_pack: dense (text, off[n+1], len) of the indexed reads, mates interleaved per fragment."""
     L = load_library()
     vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
@@ -298,8 +302,8 @@ def reads_pack(buf1, off1, len1, buf2=None, off2=None, len2=None):
     off = np.zeros(n_frags * mates + 1, dtype=np.uint64)
     ln = np.empty(n_frags * mates, dtype=np.uint16)
     written = ctypes.c_uint64()
-    rc = L.srcuda_reads_pack(vp(buf1), vp(off1), vp(len1), vp(buf2), vp(off2), vp(len2), n_frags, vp(text), total, vp(off), vp(ln),
-                             ctypes.byref(written))
+    rc = L.srcuda_reads_pack_mt(vp(buf1), vp(off1), vp(len1), vp(buf2), vp(off2), vp(len2), n_frags, vp(text), total, vp(off), vp(ln),
+                                int(threads), ctypes.byref(written))
     if rc or written.value != total:
         raise SubreadCudaError(f"srcuda_reads_pack failed (rc={rc})")
     off[-1] = total

@@ -15,7 +15,11 @@
 //   * a read that is empty after trimming ends the input, as it does in fetch_next_read_pair (core.c:1168-1208).
 // Bytes >= 0x80 are outside the contract (the reference reads them as EOF marks through a plain char).
 #include <algorithm>
+#include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/subread_cuda.h"
 
@@ -44,30 +48,41 @@ inline Line line_noempty(const char *&p, const char *e, int max_len)
 	return l;
 }
 
-}  // namespace
+struct Record {
+	uint64_t seq, name, qual;   // offsets from the start of the parsed range
+	uint16_t len, name_len, qual_len;
+};
 
-extern "C" int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof, int trim_5, int trim_3, int64_t max_reads,
-                                  uint64_t base_offset, int64_t stride, uint64_t *off, uint16_t *len, uint64_t *name_off,
-                                  uint16_t *name_len, uint64_t *qual_off, uint16_t *qual_len, srcuda_fastq_batch *out)
+// What a piece of the multi-threaded split keeps per record until the pieces are known to fit together.
+struct Packed {
+	uint64_t seq;
+	uint32_t name_back, qual_fwd;   // seq - name, qual - seq
+	uint16_t len, name_len, qual_len;
+};
+
+struct ParseEnd {
+	int rc = SRCUDA_OK, stop = SRCUDA_FASTQ_MORE;
+	uint64_t consumed = 0, error_offset = 0;
+};
+
+// The record loop of geinput_next_read_trim over [b, e).  emit(Record) is called for every record the reference
+// would hand out, in order.
+template <class Emit>
+ParseEnd parse_range(const char *b, const char *e, bool at_eof, int trim_5, int trim_3, int64_t max_reads, Emit emit)
 {
-	if (!out) return SRCUDA_ERR_ARG;
-	memset(out, 0, sizeof(*out));
-	if ((!buf && n_bytes) || !off || !len || max_reads < 0 || stride < 1 || trim_5 < 0 || trim_3 < 0) return SRCUDA_ERR_ARG;
-	const char *const b = buf, *const e = buf + n_bytes;
+	ParseEnd r;
 	const char *p = b;
 	int64_t n = 0;
-	uint32_t longest = 0;
-	int stop = SRCUDA_FASTQ_MORE, rc = SRCUDA_OK;
 	while (true) {
-		if (n >= max_reads) { stop = SRCUDA_FASTQ_FULL; break; }
+		if (n >= max_reads) { r.stop = SRCUDA_FASTQ_FULL; break; }
 		const char *rec = p;
 		while (rec < e && *rec == '\n') rec++;
 		if (rec == e) {               // nothing but line ends left
 			p = rec;
-			stop = at_eof ? SRCUDA_FASTQ_END : SRCUDA_FASTQ_MORE;
+			r.stop = at_eof ? SRCUDA_FASTQ_END : SRCUDA_FASTQ_MORE;
 			break;
 		}
-		if (*rec != '@') { out->error_offset = (uint64_t)(rec - b); rc = SRCUDA_ERR_FORMAT; break; }
+		if (*rec != '@') { r.error_offset = (uint64_t)(rec - b); r.rc = SRCUDA_ERR_FORMAT; break; }
 		const char *c = rec + 1;
 		const Line name = line_noempty(c, e, kMaxReadNameLen);
 		if (!name.terminated && !at_eof) break;
@@ -76,11 +91,11 @@ extern "C" int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof,
 		while (c < e && *c == '\n') c++;
 		if (c == e) {
 			if (!at_eof) break;
-			out->error_offset = n_bytes;   // the reference meets EOF where it wants '+': "a format issue" (:1041)
-			rc = SRCUDA_ERR_FORMAT;
+			r.error_offset = (uint64_t)(e - b);   // the reference meets EOF where it wants '+': "a format issue" (:1041)
+			r.rc = SRCUDA_ERR_FORMAT;
 			break;
 		}
-		if (*c != '+') { out->error_offset = (uint64_t)(c - b); rc = SRCUDA_ERR_FORMAT; break; }
+		if (*c != '+') { r.error_offset = (uint64_t)(c - b); r.rc = SRCUDA_ERR_FORMAT; break; }
 		const char *plus_end = static_cast<const char *>(memchr(c, '\n', (size_t)(e - c)));
 		if (!plus_end && !at_eof) break;
 		c = plus_end ? plus_end + 1 : e;
@@ -98,49 +113,245 @@ extern "C" int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof,
 		}
 		if (rlen <= 0) {              // "normally finished" for the reference: the record is not consumed
 			p = rec;
-			stop = SRCUDA_FASTQ_END;
+			r.stop = SRCUDA_FASTQ_END;
 			break;
 		}
 		uint32_t nl = name.kept;
 		for (uint32_t i = 1; i < name.kept; i++)
 			if (name.begin[i] == ' ' || name.begin[i] == '\t') { nl = i; break; }
-		const int64_t at = n * stride;
-		off[at] = base_offset + (uint64_t)(seq.begin - b) + (uint64_t)start;
-		len[at] = (uint16_t)rlen;
-		if (name_off) name_off[at] = base_offset + (uint64_t)(name.begin - b);
-		if (name_len) name_len[at] = (uint16_t)nl;
-		if (qual_off) qual_off[at] = base_offset + (uint64_t)(qual.begin - b) + (uint64_t)start;
-		if (qual_len) qual_len[at] = (uint16_t)qlen;
-		longest = std::max<uint32_t>(longest, (uint32_t)rlen);
+		Record R;
+		R.seq = (uint64_t)(seq.begin - b) + (uint64_t)start;
+		R.name = (uint64_t)(name.begin - b);
+		R.qual = (uint64_t)(qual.begin - b) + (uint64_t)start;
+		R.len = (uint16_t)rlen;
+		R.name_len = (uint16_t)nl;
+		R.qual_len = (uint16_t)qlen;
+		emit(R);
 		n++;
 		p = c;
 	}
+	r.consumed = (uint64_t)(p - b);
+	if (r.rc) r.stop = SRCUDA_FASTQ_END;
+	return r;
+}
+
+struct Sink {
+	uint64_t base;       // added to every offset
+	int64_t stride;
+	uint64_t *off;
+	uint16_t *len;
+	uint64_t *name_off;
+	uint16_t *name_len;
+	uint64_t *qual_off;
+	uint16_t *qual_len;
+	inline void put(int64_t i, const Record &R, uint64_t shift) const
+	{
+		const int64_t at = i * stride;
+		off[at] = base + shift + R.seq;
+		len[at] = R.len;
+		if (name_off) name_off[at] = base + shift + R.name;
+		if (name_len) name_len[at] = R.name_len;
+		if (qual_off) qual_off[at] = base + shift + R.qual;
+		if (qual_len) qual_len[at] = R.qual_len;
+	}
+};
+
+int split_sequential(const char *buf, uint64_t n_bytes, bool at_eof, int trim_5, int trim_3, int64_t max_reads, const Sink &sink,
+                     srcuda_fastq_batch *out)
+{
+	int64_t n = 0;
+	uint32_t longest = 0;
+	const ParseEnd r = parse_range(buf, buf + n_bytes, at_eof, trim_5, trim_3, max_reads, [&](const Record &R) {
+		sink.put(n++, R, 0);
+		longest = std::max<uint32_t>(longest, R.len);
+	});
 	out->n_reads = n;
-	out->consumed = (uint64_t)(p - b);
-	out->stop = rc ? SRCUDA_FASTQ_END : stop;
+	out->consumed = r.consumed;
+	out->stop = r.stop;
 	out->max_len = longest;
-	return rc;
+	out->error_offset = r.error_offset;
+	return r.rc;
+}
+
+// A position >= from where a record very probably starts: a line that begins with '@' whose second next line begins
+// with '+'.  (A quality line may begin with '@' too, but then the second next line is a sequence.)  Only a guess: the
+// caller checks that the piece in front ends exactly here.
+const char *guess_record_start(const char *b, const char *from, const char *e)
+{
+	const char *p = from;
+	for (int tries = 0; tries < 64; tries++) {
+		const char *nl = p < e ? static_cast<const char *>(memchr(p, '\n', (size_t)(e - p))) : nullptr;
+		if (!nl || nl + 1 >= e) return nullptr;
+		p = nl + 1;
+		if (*p != '@') continue;
+		const char *l2 = static_cast<const char *>(memchr(p, '\n', (size_t)(e - p)));
+		if (!l2 || l2 + 1 >= e) return nullptr;
+		const char *l3 = static_cast<const char *>(memchr(l2 + 1, '\n', (size_t)(e - l2 - 1)));
+		if (!l3 || l3 + 1 >= e) return nullptr;
+		if (l3[1] == '+') return p;
+	}
+	return nullptr;
+}
+
+}  // namespace
+
+extern "C" int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof, int trim_5, int trim_3, int64_t max_reads,
+                                  uint64_t base_offset, int64_t stride, uint64_t *off, uint16_t *len, uint64_t *name_off,
+                                  uint16_t *name_len, uint64_t *qual_off, uint16_t *qual_len, srcuda_fastq_batch *out)
+{
+	return srcuda_fastq_split_mt(buf, n_bytes, at_eof, trim_5, trim_3, max_reads, base_offset, stride, off, len, name_off, name_len,
+	                             qual_off, qual_len, 1, out);
+}
+
+extern "C" int srcuda_fastq_split_mt(const char *buf, uint64_t n_bytes, int at_eof, int trim_5, int trim_3, int64_t max_reads,
+                                     uint64_t base_offset, int64_t stride, uint64_t *off, uint16_t *len, uint64_t *name_off,
+                                     uint16_t *name_len, uint64_t *qual_off, uint16_t *qual_len, int n_threads,
+                                     srcuda_fastq_batch *out)
+{
+	if (!out) return SRCUDA_ERR_ARG;
+	memset(out, 0, sizeof(*out));
+	if ((!buf && n_bytes) || !off || !len || max_reads < 0 || stride < 1 || trim_5 < 0 || trim_3 < 0) return SRCUDA_ERR_ARG;
+	const Sink sink{base_offset, stride, off, len, name_off, name_len, qual_off, qual_len};
+	const uint64_t kMinPiece = 1u << 16;
+	int T = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), n_bytes / kMinPiece);
+	if (T <= 1 || max_reads == 0) return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
+
+	// Speculative cut points; piece t = [cut[t], cut[t+1]).
+	const char *const b = buf, *const e = buf + n_bytes;
+	std::vector<const char *> cut;
+	cut.push_back(b);
+	for (int t = 1; t < T; t++) {
+		const char *g = guess_record_start(b, std::max(cut.back(), b + n_bytes / (uint64_t)T * (uint64_t)t), e);
+		if (g && g > cut.back()) cut.push_back(g);
+	}
+	cut.push_back(e);
+	T = (int)cut.size() - 1;
+	if (T <= 1) return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
+
+	// Every piece is parsed as an input of its own.  The pieces together are the sequential parse if and only if every
+	// piece but the last one is consumed entirely without an error and without an early end (induction over the pieces:
+	// piece 0 starts where the sequential parse starts, and a parse that consumes its piece hands over at cut[t+1]).
+	std::vector<std::vector<Packed>> recs((size_t)T);
+	std::vector<char> wide((size_t)T, 0);   // a record whose lines lie more than 4 GB apart: not for the packed form
+	std::vector<ParseEnd> ends((size_t)T);
+	auto work = [&](int t) {
+		const bool last = t == T - 1;
+		recs[(size_t)t].reserve((size_t)(cut[t + 1] - cut[t]) / 128 + 16);
+		ends[(size_t)t] = parse_range(cut[t], cut[t + 1], last ? at_eof != 0 : true, trim_5, trim_3, INT64_MAX,
+		                              [&](const Record &R) {
+			                              const uint64_t nb = R.seq - R.name, qf = R.qual - R.seq;
+			                              if ((nb | qf) >> 32) wide[(size_t)t] = 1;
+			                              recs[(size_t)t].push_back(Packed{R.seq, (uint32_t)nb, (uint32_t)qf, R.len, R.name_len, R.qual_len});
+		                              });
+	};
+	{
+		std::vector<std::thread> th;
+		for (int t = 1; t < T; t++) th.emplace_back(work, t);
+		work(0);
+		for (auto &x : th) x.join();
+	}
+	int64_t total = 0;
+	bool ok = true;
+	for (int t = 0; t < T; t++) {
+		if (t < T - 1 && (ends[(size_t)t].rc || ends[(size_t)t].consumed != (uint64_t)(cut[t + 1] - cut[t]))) ok = false;
+		if (wide[(size_t)t]) ok = false;
+		total += (int64_t)recs[(size_t)t].size();
+	}
+	if (!ok || ends[(size_t)T - 1].rc) {  // odd input: the plain loop decides
+#ifdef SR_FASTQ_TRACE
+		fprintf(stderr, "fastq_split_mt: fallback\n");
+#endif
+		return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
+	}
+#ifdef SR_FASTQ_TRACE
+	fprintf(stderr, "fastq_split_mt: %d pieces accepted\n", T);
+#endif
+
+	std::vector<int64_t> first((size_t)T + 1, 0);
+	for (int t = 0; t < T; t++) first[(size_t)t + 1] = first[(size_t)t] + (int64_t)recs[(size_t)t].size();
+	const int64_t keep = std::min(total, max_reads);
+	std::vector<uint32_t> longest((size_t)T, 0);
+	auto copy = [&](int t) {
+		const uint64_t shift = (uint64_t)(cut[t] - b);
+		int64_t i = first[(size_t)t];
+		uint32_t m = 0;
+		for (const Packed &P : recs[(size_t)t]) {
+			if (i >= keep) break;
+			sink.put(i++, Record{P.seq, P.seq - P.name_back, P.seq + P.qual_fwd, P.len, P.name_len, P.qual_len}, shift);
+			m = std::max<uint32_t>(m, P.len);
+		}
+		longest[(size_t)t] = m;
+	};
+	{
+		std::vector<std::thread> th;
+		for (int t = 1; t < T; t++) th.emplace_back(copy, t);
+		copy(0);
+		for (auto &x : th) x.join();
+	}
+	out->n_reads = keep;
+	out->max_len = *std::max_element(longest.begin(), longest.end());
+	if (total >= max_reads) {            // the arrays are full: stop behind record keep-1, as the plain loop does
+		int t = 0;
+		while (first[(size_t)t + 1] < keep) t++;
+		const ParseEnd cutoff = parse_range(cut[t], cut[t + 1], t == T - 1 ? at_eof != 0 : true, trim_5, trim_3, keep - first[(size_t)t],
+		                                    [](const Record &) {});      // where record keep-1 ends
+		out->consumed = (uint64_t)(cut[t] - b) + cutoff.consumed;
+		out->stop = SRCUDA_FASTQ_FULL;
+		return SRCUDA_OK;
+	}
+	const ParseEnd &le = ends[(size_t)T - 1];
+	out->consumed = (uint64_t)(cut[(size_t)T - 1] - b) + le.consumed;
+	out->stop = le.stop;
+	return SRCUDA_OK;
 }
 
 extern "C" int srcuda_reads_pack(const char *buf1, const uint64_t *off1, const uint16_t *len1, const char *buf2,
                                  const uint64_t *off2, const uint16_t *len2, int64_t n_frags, char *text, uint64_t text_capacity,
                                  uint64_t *off, uint16_t *len, uint64_t *text_bytes)
 {
+	return srcuda_reads_pack_mt(buf1, off1, len1, buf2, off2, len2, n_frags, text, text_capacity, off, len, 1, text_bytes);
+}
+
+extern "C" int srcuda_reads_pack_mt(const char *buf1, const uint64_t *off1, const uint16_t *len1, const char *buf2,
+                                    const uint64_t *off2, const uint16_t *len2, int64_t n_frags, char *text, uint64_t text_capacity,
+                                    uint64_t *off, uint16_t *len, int n_threads, uint64_t *text_bytes)
+{
 	if (n_frags < 0 || !off || !len || (n_frags && (!buf1 || !off1 || !len1 || !text))) return SRCUDA_ERR_ARG;
 	if (buf2 && (!off2 || !len2)) return SRCUDA_ERR_ARG;
-	uint64_t w = 0;
-	int64_t r = 0;
-	for (int64_t f = 0; f < n_frags; f++) {
-		for (int m = 0; m < (buf2 ? 2 : 1); m++, r++) {
-			const char *src = m ? buf2 + off2[f] : buf1 + off1[f];
-			const uint16_t l = m ? len2[f] : len1[f];
-			if (w + l > text_capacity) return SRCUDA_ERR_ARG;
-			memcpy(text + w, src, l);
-			off[r] = w;
-			len[r] = l;
-			w += l;
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n_frags / 4096));
+	const int mates = buf2 ? 2 : 1;
+	// fragments [lo(t), lo(t+1)) per thread: sizes first, then every thread copies to its own stretch of text
+	auto lo = [&](int t) { return n_frags / T * t + std::min<int64_t>(t, n_frags % T); };
+	std::vector<uint64_t> start((size_t)T + 1, 0);
+	auto measure = [&](int t) {
+		uint64_t w = 0;
+		for (int64_t f = lo(t); f < lo(t + 1); f++) w += (uint64_t)len1[f] + (buf2 ? (uint64_t)len2[f] : 0u);
+		start[(size_t)t + 1] = w;
+	};
+	auto copy = [&](int t) {
+		uint64_t w = start[(size_t)t];
+		int64_t r = lo(t) * mates;
+		for (int64_t f = lo(t); f < lo(t + 1); f++) {
+			for (int m = 0; m < mates; m++, r++) {
+				const char *src = m ? buf2 + off2[f] : buf1 + off1[f];
+				const uint16_t l = m ? len2[f] : len1[f];
+				memcpy(text + w, src, l);
+				off[r] = w;
+				len[r] = l;
+				w += l;
+			}
 		}
-	}
-	if (text_bytes) *text_bytes = w;
+	};
+	auto run = [&](auto &&fn) {
+		std::vector<std::thread> th;
+		for (int t = 1; t < T; t++) th.emplace_back(fn, t);
+		fn(0);
+		for (auto &x : th) x.join();
+	};
+	run(measure);
+	for (int t = 0; t < T; t++) start[(size_t)t + 1] += start[(size_t)t];
+	if (start[(size_t)T] > text_capacity) return SRCUDA_ERR_ARG;
+	run(copy);
+	if (text_bytes) *text_bytes = start[(size_t)T];
 	return SRCUDA_OK;
 }

@@ -177,3 +177,67 @@ def test_zero_copy_offsets_point_into_the_file_bytes():
     for i in (0, 1, ref_chunk.n_frags - 1):
         s = int(off[i]) - 4096
         assert data[s:s + int(ln[i])] == ref_chunk.text[int(ref_chunk.off[i]):int(ref_chunk.off[i + 1])].tobytes()
+
+
+def big_files():
+    """Inputs large enough for srcuda_fastq_split_mt to cut (>= 64 KB per piece), tidy and untidy."""
+    rnd = random.Random(5)
+    dna = lambda n: bytes(rnd.choice(b"ACGT") for _ in range(n))  # noqa: E731
+    recs = []
+    for i in range(6000):
+        n = 30 + (i * 7) % 120
+        q = bytes(rnd.choice(b"@+IH#5") for _ in range(n))          # quality lines that look like name and '+' lines
+        recs.append(b"@q%d/1 x\n%s\n+\n%s\n" % (i, dna(n), q))
+    tidy = b"".join(recs)
+    yield "tidy", tidy, None
+    yield "no_final_newline", tidy[:-1], None
+    yield "blank_lines_everywhere", b"\n".join(recs) + b"\n\n", None
+    yield "crlf", tidy.replace(b"\n", b"\r\n"), None
+    yield "two_line_gap_inside_records", tidy.replace(b"\n+\n", b"\n\n+\n"), None
+    broken = recs[:4000] + [b"ACGT\n"] + recs[4000:]
+    yield "broken_in_the_middle", b"".join(broken), 4000
+    yield "short_read_ends_input_when_trimmed", b"".join(recs[:3000] + [b"@tiny\nACG\n+\nIII\n"] + recs[3000:]), None
+
+
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_threads_never_change_the_outcome(threads):
+    for name, data, bad_at in big_files():
+        buf = np.frombuffer(data, dtype=np.uint8)
+        for t5, t3, cap in ((0, 0, None), (2, 3, None), (0, 0, 2500), (0, 0, 6000), (4, 0, 4001)):
+            def run(T):
+                try:
+                    off, ln, b, ex = binding.fastq_split(buf, True, t5, t3, max_reads=cap, want_names=True, threads=T)
+                except binding.SubreadCudaError as err:
+                    return str(err)
+                return (off.tobytes(), ln.tobytes(), b.n_reads, b.consumed, b.stop, b.max_len) + tuple(v.tobytes() for v in ex.values())
+            one, many = run(1), run(threads)
+            assert one == many, f"{name}: trim {t5}/{t3}, max_reads {cap}"
+            if bad_at is not None and (cap is None or cap > bad_at):
+                assert isinstance(one, str) and f"{bad_at} records before it" in one
+        # streaming: a window that is not at the end of the input
+        off1, ln1, b1, _ = binding.fastq_split(buf[:len(data) // 2], False, threads=1)
+        offT, lnT, bT, _ = binding.fastq_split(buf[:len(data) // 2], False, threads=threads)
+        assert np.array_equal(off1, offT) and np.array_equal(ln1, lnT) and (b1.consumed, b1.stop) == (bT.consumed, bT.stop), name
+
+
+def test_threaded_pack_equals_the_plain_one():
+    rnd = np.random.default_rng(3)
+    n = 50_000
+    ln1 = rnd.integers(0, 300, n).astype(np.uint16)
+    ln2 = rnd.integers(0, 300, n).astype(np.uint16)
+    buf1 = rnd.integers(65, 91, int(ln1.sum()) + 1000, dtype=np.uint8)
+    buf2 = rnd.integers(65, 91, int(ln2.sum()) + 1000, dtype=np.uint8)
+    off1 = np.concatenate(([0], np.cumsum(ln1[:-1], dtype=np.uint64))).astype(np.uint64) + np.uint64(7)
+    off2 = np.concatenate(([0], np.cumsum(ln2[:-1], dtype=np.uint64))).astype(np.uint64)
+    for pe in (False, True):
+        second = (buf2, off2, ln2) if pe else ()
+        text, off, ln = binding.reads_pack(buf1, off1, ln1, *second)
+        for T in (2, 5, 16):
+            again = binding.reads_pack(buf1, off1, ln1, *second, threads=T)
+            assert all(np.array_equal(x, y) for x, y in zip((text, off, ln), again)), f"paired={pe}, {T} threads"
+        mates = 2 if pe else 1
+        for f in (0, 123, n - 1):
+            r = f * mates
+            assert text[int(off[r]):int(off[r]) + int(ln[r])].tobytes() == buf1[int(off1[f]):int(off1[f]) + int(ln1[f])].tobytes()
+            if pe:
+                assert text[int(off[r + 1]):int(off[r + 1]) + int(ln[r + 1])].tobytes() == buf2[int(off2[f]):int(off2[f]) + int(ln2[f])].tobytes()
