@@ -15,6 +15,7 @@
 //   * a read that is empty after trimming ends the input, as it does in fetch_next_read_pair (core.c:1168-1208).
 // Bytes >= 0x80 are outside the contract (the reference reads them as EOF marks through a plain char).
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -135,6 +136,30 @@ ParseEnd parse_range(const char *b, const char *e, bool at_eof, int trim_5, int 
 	return r;
 }
 
+// fn(t) for t = 0 .. T-1, t = 0 on the calling thread.  Nothing escapes: a task that throws (out of memory) or a thread
+// that cannot be started makes the call return false after every started thread has been joined (the library never
+// terminates the caller's process); tasks whose thread could not be started run on the calling thread.
+template <class Fn>
+bool run_tasks(int T, Fn fn)
+{
+	std::atomic<bool> ok{true};
+	auto guarded = [&](int t) {
+		try { fn(t); } catch (...) { ok = false; }
+	};
+	std::vector<std::thread> th;
+	try { th.reserve((size_t)T); } catch (...) { ok = false; }
+	for (int t = 1; t < T; t++) {
+		bool started = false;
+		if (th.capacity() > th.size()) {
+			try { th.emplace_back(guarded, t); started = true; } catch (...) {}
+		}
+		if (!started) guarded(t);
+	}
+	guarded(0);
+	for (auto &x : th) x.join();
+	return ok;
+}
+
 struct Sink {
 	uint64_t base;       // added to every offset
 	int64_t stride;
@@ -193,6 +218,9 @@ const char *guess_record_start(const char *b, const char *from, const char *e)
 	return nullptr;
 }
 
+int split_threaded(const char *buf, uint64_t n_bytes, bool at_eof, int trim_5, int trim_3, int64_t max_reads, const Sink &sink, int T,
+                   srcuda_fastq_batch *out);
+
 }  // namespace
 
 extern "C" int srcuda_fastq_split(const char *buf, uint64_t n_bytes, int at_eof, int trim_5, int trim_3, int64_t max_reads,
@@ -215,7 +243,20 @@ extern "C" int srcuda_fastq_split_mt(const char *buf, uint64_t n_bytes, int at_e
 	const uint64_t kMinPiece = 1u << 16;
 	int T = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), n_bytes / kMinPiece);
 	if (T <= 1 || max_reads == 0) return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
+	try {
+		return split_threaded(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, T, out);
+	} catch (...) {      // no memory for the pieces' records: the plain loop needs none
+		memset(out, 0, sizeof(*out));
+		return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
+	}
+}
 
+namespace {
+
+int split_threaded(const char *buf, uint64_t n_bytes, bool at_eof_b, int trim_5, int trim_3, int64_t max_reads, const Sink &sink, int T,
+                   srcuda_fastq_batch *out)
+{
+	const int at_eof = at_eof_b ? 1 : 0;
 	// Speculative cut points; piece t = [cut[t], cut[t+1]).
 	const char *const b = buf, *const e = buf + n_bytes;
 	std::vector<const char *> cut;
@@ -244,14 +285,9 @@ extern "C" int srcuda_fastq_split_mt(const char *buf, uint64_t n_bytes, int at_e
 			                              recs[(size_t)t].push_back(Packed{R.seq, (uint32_t)nb, (uint32_t)qf, R.len, R.name_len, R.qual_len});
 		                              });
 	};
-	{
-		std::vector<std::thread> th;
-		for (int t = 1; t < T; t++) th.emplace_back(work, t);
-		work(0);
-		for (auto &x : th) x.join();
-	}
+	const bool ran = run_tasks(T, work);
 	int64_t total = 0;
-	bool ok = true;
+	bool ok = ran;
 	for (int t = 0; t < T; t++) {
 		if (t < T - 1 && (ends[(size_t)t].rc || ends[(size_t)t].consumed != (uint64_t)(cut[t + 1] - cut[t]))) ok = false;
 		if (wide[(size_t)t]) ok = false;
@@ -282,12 +318,7 @@ extern "C" int srcuda_fastq_split_mt(const char *buf, uint64_t n_bytes, int at_e
 		}
 		longest[(size_t)t] = m;
 	};
-	{
-		std::vector<std::thread> th;
-		for (int t = 1; t < T; t++) th.emplace_back(copy, t);
-		copy(0);
-		for (auto &x : th) x.join();
-	}
+	if (!run_tasks(T, copy)) return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
 	out->n_reads = keep;
 	out->max_len = *std::max_element(longest.begin(), longest.end());
 	if (total >= max_reads) {            // the arrays are full: stop behind record keep-1, as the plain loop does
@@ -304,6 +335,8 @@ extern "C" int srcuda_fastq_split_mt(const char *buf, uint64_t n_bytes, int at_e
 	out->stop = le.stop;
 	return SRCUDA_OK;
 }
+
+}  // namespace
 
 extern "C" int srcuda_reads_pack(const char *buf1, const uint64_t *off1, const uint16_t *len1, const char *buf2,
                                  const uint64_t *off2, const uint16_t *len2, int64_t n_frags, char *text, uint64_t text_capacity,
@@ -342,16 +375,10 @@ extern "C" int srcuda_reads_pack_mt(const char *buf1, const uint64_t *off1, cons
 			}
 		}
 	};
-	auto run = [&](auto &&fn) {
-		std::vector<std::thread> th;
-		for (int t = 1; t < T; t++) th.emplace_back(fn, t);
-		fn(0);
-		for (auto &x : th) x.join();
-	};
-	run(measure);
+	if (!run_tasks(T, measure)) return SRCUDA_ERR_NOMEM;
 	for (int t = 0; t < T; t++) start[(size_t)t + 1] += start[(size_t)t];
 	if (start[(size_t)T] > text_capacity) return SRCUDA_ERR_ARG;
-	run(copy);
+	if (!run_tasks(T, copy)) return SRCUDA_ERR_NOMEM;
 	if (text_bytes) *text_bytes = start[(size_t)T];
 	return SRCUDA_OK;
 }
