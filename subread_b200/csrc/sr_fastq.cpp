@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -54,11 +55,21 @@ struct Record {
 	uint16_t len, name_len, qual_len;
 };
 
-// What a piece of the multi-threaded split keeps per record until the pieces are known to fit together.
-struct Packed {
-	uint64_t seq;
-	uint32_t name_back, qual_fwd;   // seq - name, qual - seq
-	uint16_t len, name_len, qual_len;
+// What a piece of the multi-threaded split keeps until the pieces are known to fit together: its records in the
+// caller's own format, so that accepting them is one block copy per array.
+struct Columns {
+	std::vector<uint64_t> off, name_off, qual_off;
+	std::vector<uint16_t> len, name_len, qual_len;
+	size_t n = 0;
+	void room(size_t want, bool names, bool quals)
+	{
+		if (off.size() >= want && (!names || name_off.size() >= want) && (!quals || qual_off.size() >= want)) return;
+		want += want / 2 + 1024;
+		off.resize(want);
+		len.resize(want);
+		if (names) { name_off.resize(want); name_len.resize(want); }
+		if (quals) { qual_off.resize(want); qual_len.resize(want); }
+	}
 };
 
 struct ParseEnd {
@@ -134,6 +145,43 @@ ParseEnd parse_range(const char *b, const char *e, bool at_eof, int trim_5, int 
 	r.consumed = (uint64_t)(p - b);
 	if (r.rc) r.stop = SRCUDA_FASTQ_END;
 	return r;
+}
+
+// The pieces' arrays of the threaded split are kept between calls (a streaming caller indexes window after window of the same
+// size): fresh memory costs a page fault per 4 KB, and page faults of many threads serialise in the kernel.
+// srcuda_fastq_split_mt(NULL, 0, ...) -- an empty buffer -- gives the memory back.
+class ScratchPool {
+public:
+	Columns take()
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		if (free_.empty()) return {};
+		Columns v = std::move(free_.back());
+		free_.pop_back();
+		v.n = 0;
+		return v;
+	}
+	void give(Columns &&v)
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		if (free_.size() < 64) free_.push_back(std::move(v));
+	}
+	void drop()
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		free_.clear();
+		free_.shrink_to_fit();
+	}
+
+private:
+	std::mutex mu_;
+	std::vector<Columns> free_;
+};
+
+ScratchPool &scratch_pool()
+{
+	static ScratchPool pool;
+	return pool;
 }
 
 // fn(t) for t = 0 .. T-1, t = 0 on the calling thread.  Nothing escapes: a task that throws (out of memory) or a thread
@@ -240,6 +288,7 @@ extern "C" int srcuda_fastq_split_mt(const char *buf, uint64_t n_bytes, int at_e
 	memset(out, 0, sizeof(*out));
 	if ((!buf && n_bytes) || !off || !len || max_reads < 0 || stride < 1 || trim_5 < 0 || trim_3 < 0) return SRCUDA_ERR_ARG;
 	const Sink sink{base_offset, stride, off, len, name_off, name_len, qual_off, qual_len};
+	if (n_bytes == 0) scratch_pool().drop();
 	const uint64_t kMinPiece = 1u << 16;
 	int T = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), n_bytes / kMinPiece);
 	if (T <= 1 || max_reads == 0) return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
@@ -272,26 +321,38 @@ int split_threaded(const char *buf, uint64_t n_bytes, bool at_eof_b, int trim_5,
 	// Every piece is parsed as an input of its own.  The pieces together are the sequential parse if and only if every
 	// piece but the last one is consumed entirely without an error and without an early end (induction over the pieces:
 	// piece 0 starts where the sequential parse starts, and a parse that consumes its piece hands over at cut[t+1]).
-	std::vector<std::vector<Packed>> recs((size_t)T);
-	std::vector<char> wide((size_t)T, 0);   // a record whose lines lie more than 4 GB apart: not for the packed form
+	std::vector<Columns> recs((size_t)T);
+	for (auto &v : recs) v = scratch_pool().take();
+	struct GiveBack {
+		std::vector<Columns> &r;
+		~GiveBack() { for (auto &v : r) if (!v.off.empty()) scratch_pool().give(std::move(v)); }
+	} give_back{recs};
+	const bool names = sink.name_off || sink.name_len, quals = sink.qual_off || sink.qual_len;
 	std::vector<ParseEnd> ends((size_t)T);
+	std::vector<uint32_t> longest((size_t)T, 0);
 	auto work = [&](int t) {
 		const bool last = t == T - 1;
-		recs[(size_t)t].reserve((size_t)(cut[t + 1] - cut[t]) / 128 + 16);
-		ends[(size_t)t] = parse_range(cut[t], cut[t + 1], last ? at_eof != 0 : true, trim_5, trim_3, INT64_MAX,
-		                              [&](const Record &R) {
-			                              const uint64_t nb = R.seq - R.name, qf = R.qual - R.seq;
-			                              if ((nb | qf) >> 32) wide[(size_t)t] = 1;
-			                              recs[(size_t)t].push_back(Packed{R.seq, (uint32_t)nb, (uint32_t)qf, R.len, R.name_len, R.qual_len});
-		                              });
+		Columns &C = recs[(size_t)t];
+		C.room((size_t)(cut[t + 1] - cut[t]) / 256 + 16, names, quals);
+		const uint64_t shift = sink.base + (uint64_t)(cut[t] - b);
+		uint32_t m = 0;
+		ends[(size_t)t] = parse_range(cut[t], cut[t + 1], last ? at_eof != 0 : true, trim_5, trim_3, INT64_MAX, [&](const Record &R) {
+			if (C.n == C.off.size()) C.room(C.n + 1, names, quals);
+			const size_t i = C.n++;
+			C.off[i] = shift + R.seq;
+			C.len[i] = R.len;
+			if (names) { C.name_off[i] = shift + R.name; C.name_len[i] = R.name_len; }
+			if (quals) { C.qual_off[i] = shift + R.qual; C.qual_len[i] = R.qual_len; }
+			m = std::max<uint32_t>(m, R.len);
+		});
+		longest[(size_t)t] = m;
 	};
 	const bool ran = run_tasks(T, work);
 	int64_t total = 0;
 	bool ok = ran;
 	for (int t = 0; t < T; t++) {
 		if (t < T - 1 && (ends[(size_t)t].rc || ends[(size_t)t].consumed != (uint64_t)(cut[t + 1] - cut[t]))) ok = false;
-		if (wide[(size_t)t]) ok = false;
-		total += (int64_t)recs[(size_t)t].size();
+		total += (int64_t)recs[(size_t)t].n;
 	}
 	if (!ok || ends[(size_t)T - 1].rc) {  // odd input: the plain loop decides
 #ifdef SR_FASTQ_TRACE
@@ -304,19 +365,27 @@ int split_threaded(const char *buf, uint64_t n_bytes, bool at_eof_b, int trim_5,
 #endif
 
 	std::vector<int64_t> first((size_t)T + 1, 0);
-	for (int t = 0; t < T; t++) first[(size_t)t + 1] = first[(size_t)t] + (int64_t)recs[(size_t)t].size();
+	for (int t = 0; t < T; t++) first[(size_t)t + 1] = first[(size_t)t] + (int64_t)recs[(size_t)t].n;
 	const int64_t keep = std::min(total, max_reads);
-	std::vector<uint32_t> longest((size_t)T, 0);
+	auto place = [&](auto *dst, const auto &src, int64_t at, int64_t n) {      // dst[(at + i) * stride] = src[i]
+		if (!dst || n <= 0) return;
+		if (sink.stride == 1) memcpy(dst + at, src.data(), (size_t)n * sizeof(*dst));
+		else for (int64_t i = 0; i < n; i++) dst[(at + i) * sink.stride] = src[(size_t)i];
+	};
 	auto copy = [&](int t) {
-		const uint64_t shift = (uint64_t)(cut[t] - b);
-		int64_t i = first[(size_t)t];
-		uint32_t m = 0;
-		for (const Packed &P : recs[(size_t)t]) {
-			if (i >= keep) break;
-			sink.put(i++, Record{P.seq, P.seq - P.name_back, P.seq + P.qual_fwd, P.len, P.name_len, P.qual_len}, shift);
-			m = std::max<uint32_t>(m, P.len);
+		const Columns &C = recs[(size_t)t];
+		const int64_t at = first[(size_t)t], n = std::min<int64_t>((int64_t)C.n, keep - at);
+		place(sink.off, C.off, at, n);
+		place(sink.len, C.len, at, n);
+		place(sink.name_off, C.name_off, at, n);
+		place(sink.name_len, C.name_len, at, n);
+		place(sink.qual_off, C.qual_off, at, n);
+		place(sink.qual_len, C.qual_len, at, n);
+		if (n < (int64_t)C.n) {          // cut short by max_reads: the longest read among the kept ones
+			uint32_t m = 0;
+			for (int64_t i = 0; i < n; i++) m = std::max<uint32_t>(m, C.len[(size_t)i]);
+			longest[(size_t)t] = m;
 		}
-		longest[(size_t)t] = m;
 	};
 	if (!run_tasks(T, copy)) return split_sequential(buf, n_bytes, at_eof != 0, trim_5, trim_3, max_reads, sink, out);
 	out->n_reads = keep;
