@@ -263,7 +263,8 @@ class Mapper:
         return out.value
 
 
-def fastq_split(buf: np.ndarray, at_eof=True, trim_5=0, trim_3=0, max_reads=None, base_offset=0, want_names=False, threads=1):
+def fastq_split(buf: np.ndarray, at_eof=True, trim_5=0, trim_3=0, max_reads=None, base_offset=0, want_names=False, threads=1,
+                partial=False):
     """srcuda_fastq_split (threads > 1: srcuda_fastq_split_mt) over a uint8 array of plain FASTQ text.  Returns (off, len, batch, extra): offsets into
     ``buf`` (+ base_offset) and lengths of the records the buffer holds completely, the FastqBatch verdict, and --
     with want_names -- a dict of name_off/name_len/qual_off/qual_len.  Raises SubreadCudaError on a format issue
@@ -284,6 +285,8 @@ def fastq_split(buf: np.ndarray, at_eof=True, trim_5=0, trim_3=0, max_reads=None
                                  vp(extra["qual_off"]) if want_names else None, vp(extra["qual_len"]) if want_names else None,
                                  int(threads), ctypes.byref(b))
     n = int(b.n_reads)
+    if partial:      # the records in front of a format issue too, with the return code
+        return off[:n], ln[:n], b, {k: v[:n] for k, v in extra.items()}, rc
     if rc:
         raise SubreadCudaError(f"srcuda_fastq_split: format issue at byte {b.error_offset} (rc={rc}, {n} records before it)")
     return off[:n], ln[:n], b, {k: v[:n] for k, v in extra.items()}

@@ -134,7 +134,7 @@ ParseEnd parse_range(const char *b, const char *e, bool at_eof, int trim_5, int 
 		Record R;
 		R.seq = (uint64_t)(seq.begin - b) + (uint64_t)start;
 		R.name = (uint64_t)(name.begin - b);
-		R.qual = (uint64_t)(qual.begin - b) + (uint64_t)start;
+		R.qual = (uint64_t)(qual.begin - b) + (uint64_t)std::min<uint32_t>((uint32_t)start, qual.kept);   // never past its line
 		R.len = (uint16_t)rlen;
 		R.name_len = (uint16_t)nl;
 		R.qual_len = (uint16_t)qlen;

@@ -241,3 +241,56 @@ def test_threaded_pack_equals_the_plain_one():
             assert text[int(off[r]):int(off[r]) + int(ln[r])].tobytes() == buf1[int(off1[f]):int(off1[f]) + int(ln1[f])].tobytes()
             if pe:
                 assert text[int(off[r + 1]):int(off[r + 1]) + int(ln[r + 1])].tobytes() == buf2[int(off2[f]):int(off2[f]) + int(ln2[f])].tobytes()
+
+
+def test_sanitizer_fuzz(tmp_path):
+    """tests/native/fastq_fuzz.cpp: 3000 damaged inputs through the splitter compiled with -fsanitize=address,undefined;
+    one thread and several must agree and nothing may be read or reported outside the buffer."""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "fastq_fuzz")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+           os.path.join(ROOT, "tests", "native", "fastq_fuzz.cpp"), os.path.join(ROOT, "subread_b200", "csrc", "sr_fastq.cpp"), "-pthread"]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + built.stderr[-200:])
+    run = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"), timeout=300)
+    assert run.returncode == 0 and run.stdout.startswith("ok:"), run.stdout[-400:] + run.stderr[-2000:]
+
+
+def test_random_damage_against_the_reference_reader(ref, tmp_path):
+    """Generated FASTQ with random damage: the splitter hands out exactly the records geinput_next_read_trim hands out
+    before it stops, and reports a format issue exactly when the reference stops early on one."""
+    rnd = random.Random(2026)
+    alphabet = b"ACGTN@+\n\n \tIH#r1/"
+    stopped_early = 0
+    for case in range(250):
+        recs = []
+        for i in range(rnd.randrange(1, 25)):
+            n = rnd.randrange(1, 70)
+            recs.append(b"@r%d%s\n%s\n+\n%s\n" % (i, b" x" if rnd.random() < 0.3 else b"", bytes(rnd.choice(b"ACGTN") for _ in range(n)),
+                                                   bytes(rnd.choice(b"IH#@+5") for _ in range(n))))
+        data = bytearray(b"".join(recs))
+        for _ in range(rnd.randrange(0, 3)):
+            p = rnd.randrange(len(data))
+            kind = rnd.randrange(3)
+            if kind == 0:
+                data[p] = rnd.choice(alphabet)
+            elif kind == 1:
+                del data[p:p + rnd.randrange(1, 5)]
+            else:
+                data.insert(p, rnd.choice(alphabet))
+        data = bytes(data)
+        if not data.strip(b"\n").startswith(b"@"):
+            continue                                      # geinput_open would not call it FASTQ
+        path = str(tmp_path / "damaged.fq")
+        with open(path, "wb") as fh:
+            fh.write(data)
+        t5, t3 = (rnd.randrange(0, 4), rnd.randrange(0, 4)) if case % 3 == 0 else (0, 0)
+        exp = reference_records(ref, path, t5, t3)
+        buf = np.frombuffer(data, dtype=np.uint8)
+        off, ln, b, ex, rc = binding.fastq_split(buf, True, t5, t3, want_names=True, partial=True)
+        got = [(data[int(a):int(a) + int(n)], data[int(o):int(o) + int(m)]) for a, n, o, m in zip(ex["name_off"], ex["name_len"], off, ln)]
+        assert got == [(e[0], e[1]) for e in exp], f"case {case}: {data!r}"
+        stopped_early += rc != 0
+    assert stopped_early > 20      # the damage did hit record structure often enough
