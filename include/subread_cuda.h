@@ -228,6 +228,25 @@ int srcuda_reads_pack_mt(const char *buf1, const uint64_t *off1, const uint16_t 
                          const uint64_t *off2, const uint16_t *len2, int64_t n_frags, char *text, uint64_t text_capacity,
                          uint64_t *off, uint16_t *len, int n_threads, uint64_t *text_bytes);
 
+/* ---- chunk reader (host side, no device work) ------------------------------------------- */
+
+typedef struct srcuda_reader srcuda_reader;
+
+/* Opens one (path2 = NULL) or two FASTQ files, plain or gzip: geinput_open (input-files.c:455) for the FASTQ types.
+ * The files are read in windows of window_bytes (0: 64 MB), each indexed by srcuda_fastq_split_mt with n_threads.
+ * *out is set even on failure (srcuda_reader_error says why; close it). */
+int srcuda_reader_open(const char *path1, const char *path2, uint64_t window_bytes, int n_threads, int trim_5, int trim_3,
+                       srcuda_reader **out);
+/* The next batch of at most max_frags fragments, gathered into the caller's buffers in the dense chunk layout of
+ * srcuda_vote_chunk (read r = f*mates + m, off[r] from 0): the read loop of fetch_next_read_pair (core.c:1121-1215) up
+ * to reads_per_chunk, for a batch.  off and len need max_frags * mates entries.  *n_frags = 0: end of input.  Two files
+ * that do not hold the same number of reads are an error where the reference prints one (core.c:1177-1182); a record
+ * without '@' or '+' is SRCUDA_ERR_FORMAT after the records in front of it have been handed out. */
+int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *text, uint64_t text_capacity, uint64_t *off, uint16_t *len,
+                       int64_t *n_frags, uint64_t *text_bytes);
+const char *srcuda_reader_error(const srcuda_reader *r);
+void srcuda_reader_close(srcuda_reader *r);
+
 /* ---- the voting step -------------------------------------------------------------------- */
 
 /* One chunk of reads against the resident index block: everything do_voting (core.c:3049)

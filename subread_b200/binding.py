@@ -24,6 +24,7 @@ EXPORTS = [
     "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device",
     "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth",
     "srcuda_fastq_split", "srcuda_fastq_split_mt", "srcuda_reads_pack", "srcuda_reads_pack_mt",
+    "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_error", "srcuda_reader_close",
 ]
 
 
@@ -103,6 +104,12 @@ def load_library():
                                         ctypes.c_int, ctypes.POINTER(FastqBatch)]
     L.srcuda_reads_pack.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, u64, vp, vp, ctypes.POINTER(u64)]
     L.srcuda_reads_pack_mt.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, u64, vp, vp, ctypes.c_int, ctypes.POINTER(u64)]
+    L.srcuda_reader_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    L.srcuda_reader_next.argtypes = [vp, i64, vp, u64, vp, vp, ctypes.POINTER(i64), ctypes.POINTER(u64)]
+    L.srcuda_reader_error.argtypes = [vp]
+    L.srcuda_reader_error.restype = ctypes.c_char_p
+    L.srcuda_reader_close.argtypes = [vp]
+    L.srcuda_reader_close.restype = None
     _LIB = L
     return L
 
@@ -311,3 +318,43 @@ def reads_pack(buf1, off1, len1, buf2=None, off2=None, len2=None, threads=1):
         raise SubreadCudaError(f"srcuda_reads_pack failed (rc={rc})")
     off[-1] = total
     return text, off, ln
+
+
+class ChunkReader:
+    """srcuda_reader_*: batches of fragments from one or two FASTQ files (plain or gzip) in the chunk layout."""
+
+    def __init__(self, path1, path2=None, window_bytes=0, threads=1, trim_5=0, trim_3=0):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        self.mates = 2 if path2 else 1
+        rc = self.lib.srcuda_reader_open(os.fsencode(path1), os.fsencode(path2) if path2 else None, int(window_bytes), int(threads),
+                                         int(trim_5), int(trim_3), ctypes.byref(self.h))
+        if rc:
+            msg = self.lib.srcuda_reader_error(self.h).decode() if self.h else "bad argument"
+            self.close()
+            raise SubreadCudaError(f"srcuda_reader_open: {msg} (rc={rc})")
+
+    def next(self, max_frags, max_read_len=1210):
+        """(text, off[n+1], len, n_frags) of the next batch; n_frags == 0 at the end of the input."""
+        n_reads = int(max_frags) * self.mates
+        text = np.empty(max(1, n_reads * int(max_read_len)), dtype=np.uint8)
+        off = np.zeros(n_reads + 1, dtype=np.uint64)
+        ln = np.zeros(max(1, n_reads), dtype=np.uint16)
+        n, used = ctypes.c_int64(), ctypes.c_uint64()
+        rc = self.lib.srcuda_reader_next(self.h, int(max_frags), _ptr(text), text.shape[0], _ptr(off), _ptr(ln), ctypes.byref(n), ctypes.byref(used))
+        if rc:
+            raise SubreadCudaError(f"srcuda_reader_next: {self.lib.srcuda_reader_error(self.h).decode()} (rc={rc})")
+        k = n.value * self.mates
+        off[k] = used.value
+        return text[:used.value], off[:k + 1], ln[:k], int(n.value)
+
+    def close(self):
+        if self.h:
+            self.lib.srcuda_reader_close(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,190 @@
+// sr_reader.cpp -- chunk reader in front of the voting step: one or two FASTQ files, plain or
+// gzip, handed out as batches of fragments in the dense chunk layout srcuda_vote_chunk takes.  It stands where the
+// reference has geinput_open + fetch_next_read_pair under the input mutex (input-files.c:455, core.c:1121-1215): the file
+// is read in windows, every window is indexed at once by srcuda_fastq_split_mt and gathered by srcuda_reads_pack_mt
+// (sr_fastq.cpp), and a batch ends after max_frags fragments the way a chunk ends after reads_per_chunk (core.c:1132).
+// The record grammar is sr_fastq.cpp's (= the reference's plain-FASTQ branch); gzip input is inflated by zlib in front of
+// the same grammar (the reference's own gzip branch reads lines with seekgz_gets and does not skip blank lines: the two
+// agree on every file without blank lines).  Host code only.
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/subread_cuda.h"
+
+namespace {
+
+struct Stream {
+	gzFile fp = nullptr;
+	std::vector<char> win;          // window of file bytes
+	size_t have = 0;                // valid bytes in win
+	size_t consumed = 0;            // bytes of win behind the last indexed record
+	bool eof = false;               // the file has no more bytes
+	bool ended = false;             // the grammar ended the input (end of file, or a read trimmed to nothing)
+	uint64_t file_pos = 0;          // file offset (inflated bytes) of win[0]
+	std::vector<uint64_t> off;      // indexed, not yet handed out: records [cursor, n)
+	std::vector<uint16_t> len;
+	int64_t n = 0, cursor = 0;
+	int64_t pending() const { return n - cursor; }
+};
+
+}  // namespace
+
+struct srcuda_reader {
+	Stream s[2];
+	int files = 1;
+	int threads = 1, trim_5 = 0, trim_3 = 0;
+	size_t window = 0;
+	std::string error;
+	int64_t frags_out = 0;
+};
+
+namespace {
+
+int fail(srcuda_reader *r, int rc, const char *fmt, ...)
+{
+	char msg[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(msg, sizeof(msg), fmt, ap);
+	va_end(ap);
+	r->error = msg;
+	return rc;
+}
+
+// Indexes the next window of one file: drops the bytes already handed out, tops the window up, splits it.
+int refill(srcuda_reader *r, int which)
+{
+	Stream &st = r->s[which];
+	if (st.ended) return SRCUDA_OK;
+	if (st.consumed) {
+		memmove(st.win.data(), st.win.data() + st.consumed, st.have - st.consumed);
+		st.have -= st.consumed;
+		st.file_pos += st.consumed;
+		st.consumed = 0;
+	}
+	while (true) {
+		while (!st.eof && st.have < st.win.size()) {
+			const int got = gzread(st.fp, st.win.data() + st.have, (unsigned)std::min<size_t>(st.win.size() - st.have, 1u << 30));
+			if (got < 0) {
+				int errnum = 0;
+				const char *m = gzerror(st.fp, &errnum);
+				return fail(r, SRCUDA_ERR_IO, "read error in input file %d: %s", which + 1, m ? m : "?");
+			}
+			if (got == 0) st.eof = true;
+			st.have += (size_t)got;
+		}
+		const size_t cap = st.have / 6 + 2;
+		if (st.off.size() < cap) { st.off.resize(cap); st.len.resize(cap); }
+		srcuda_fastq_batch b;
+		const int rc = srcuda_fastq_split_mt(st.win.data(), st.have, st.eof ? 1 : 0, r->trim_5, r->trim_3, (int64_t)cap, 0, 1, st.off.data(),
+		                                     st.len.data(), nullptr, nullptr, nullptr, nullptr, r->threads, &b);
+		if (rc == SRCUDA_ERR_FORMAT && b.n_reads == 0)
+			return fail(r, rc, "input file %d: a format issue at byte %llu (a record must start with '@' and have a '+' line)", which + 1,
+			            (unsigned long long)(st.file_pos + b.error_offset));
+		if (rc && rc != SRCUDA_ERR_FORMAT) return fail(r, rc, "srcuda_fastq_split_mt failed (%d)", rc);
+		st.n = b.n_reads;
+		st.cursor = 0;
+		st.consumed = (size_t)b.consumed;
+		if (rc == SRCUDA_ERR_FORMAT) return SRCUDA_OK;   // the records in front of the issue go out first; the next refill reports it
+		if (b.stop == SRCUDA_FASTQ_END) st.ended = true;
+		if (b.n_reads > 0 || st.ended) return SRCUDA_OK;
+		// not one complete record in a full window: a record longer than the window
+		if (st.have == st.win.size()) {
+			if (st.win.size() >= ((size_t)1 << 32)) return fail(r, SRCUDA_ERR_FORMAT, "input file %d: a record longer than 4 GB", which + 1);
+			st.win.resize(st.win.size() * 2);
+		}
+	}
+}
+
+}  // namespace
+
+extern "C" int srcuda_reader_open(const char *path1, const char *path2, uint64_t window_bytes, int n_threads, int trim_5, int trim_3,
+                                  srcuda_reader **out)
+{
+	if (!out) return SRCUDA_ERR_ARG;
+	*out = nullptr;
+	if (!path1 || trim_5 < 0 || trim_3 < 0) return SRCUDA_ERR_ARG;
+	srcuda_reader *r = new (std::nothrow) srcuda_reader;
+	if (!r) return SRCUDA_ERR_NOMEM;
+	*out = r;                       // handed out even on failure so that srcuda_reader_error can say why
+	r->files = path2 ? 2 : 1;
+	r->threads = std::max(1, n_threads);
+	r->trim_5 = trim_5;
+	r->trim_3 = trim_3;
+	r->window = (size_t)std::max<uint64_t>(window_bytes ? window_bytes : (64u << 20), 4096);
+	for (int i = 0; i < r->files; i++) {
+		const char *p = i ? path2 : path1;
+		r->s[i].fp = gzopen(p, "rb");         // reads plain files as they are
+		if (!r->s[i].fp) return fail(r, SRCUDA_ERR_IO, "cannot open '%s'", p);
+		gzbuffer(r->s[i].fp, 1u << 20);
+		try {
+			r->s[i].win.resize(r->window);
+		} catch (...) {
+			return fail(r, SRCUDA_ERR_NOMEM, "no memory for a window of %zu bytes", r->window);
+		}
+	}
+	return SRCUDA_OK;
+}
+
+extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *text, uint64_t text_capacity, uint64_t *off, uint16_t *len,
+                                  int64_t *n_frags, uint64_t *text_bytes)
+{
+	if (!r || !n_frags || max_frags < 0 || (max_frags && (!text || !off || !len))) return SRCUDA_ERR_ARG;
+	*n_frags = 0;
+	if (text_bytes) *text_bytes = 0;
+	try {
+		int64_t done = 0;
+		uint64_t written = 0;
+		const int mates = r->files;
+		while (done < max_frags) {
+			for (int i = 0; i < r->files; i++)
+				if (r->s[i].pending() == 0) {
+					const int rc = refill(r, i);
+					if (rc) return rc;
+				}
+			int64_t take = max_frags - done;
+			for (int i = 0; i < r->files; i++) take = std::min(take, r->s[i].pending());
+			if (take == 0) {
+				// the end: both files must have run out together (core.c:1177-1182)
+				if (r->files == 2 && (r->s[0].pending() > 0) != (r->s[1].pending() > 0))
+					return fail(r, SRCUDA_ERR_FORMAT, "two input files have different amounts of reads");
+				break;
+			}
+			const Stream &a = r->s[0], &b = r->s[1];
+			uint64_t w = 0;
+			const int rc = srcuda_reads_pack_mt(a.win.data(), a.off.data() + a.cursor, a.len.data() + a.cursor, mates == 2 ? b.win.data() : nullptr,
+			                                    mates == 2 ? b.off.data() + b.cursor : nullptr, mates == 2 ? b.len.data() + b.cursor : nullptr, take,
+			                                    text + written, text_capacity - written, off + done * mates, len + done * mates, r->threads, &w);
+			if (rc == SRCUDA_ERR_ARG) return fail(r, rc, "the text buffer (%llu bytes) is too small for %lld fragments", (unsigned long long)text_capacity, (long long)max_frags);
+			if (rc) return fail(r, rc, "srcuda_reads_pack_mt failed (%d)", rc);
+			if (written)
+				for (int64_t k = done * mates; k < (done + take) * mates; k++) off[k] += written;
+			written += w;
+			done += take;
+			for (int i = 0; i < r->files; i++) r->s[i].cursor += take;
+		}
+		*n_frags = done;
+		if (text_bytes) *text_bytes = written;
+		r->frags_out += done;
+		return SRCUDA_OK;
+	} catch (...) {
+		return fail(r, SRCUDA_ERR_NOMEM, "out of memory");
+	}
+}
+
+extern "C" const char *srcuda_reader_error(const srcuda_reader *r) { return r ? r->error.c_str() : "null reader"; }
+
+extern "C" void srcuda_reader_close(srcuda_reader *r)
+{
+	if (!r) return;
+	for (int i = 0; i < 2; i++)
+		if (r->s[i].fp) gzclose(r->s[i].fp);
+	delete r;
+}

@@ -88,6 +88,14 @@ def test_null_arguments_are_argument_errors(lib):
     assert lib.srcuda_vote_chunk(null, ctypes.byref(params), None, None, None, ctypes.c_int64(0), 0, 1, None, None, None, None) == ERR_ARG
     gb = ctypes.c_double()
     assert lib.srcuda_measure_gather_bandwidth(null, ctypes.c_uint64(1 << 22), 1, ctypes.byref(gb)) == ERR_ARG
+    n = ctypes.c_int64()
+    assert lib.srcuda_reader_open(None, None, 0, 1, 0, 0, None) == ERR_ARG
+    assert lib.srcuda_reader_next(null, 1, None, 0, None, None, ctypes.byref(n), None) == ERR_ARG
+    assert lib.srcuda_reader_error(null) == b"null reader"
+    lib.srcuda_reader_close(null)
+    batch = binding.FastqBatch()
+    assert lib.srcuda_fastq_split(None, 10, 1, 0, 0, 1, 0, 1, None, None, None, None, None, None, ctypes.byref(batch)) == ERR_ARG
+    assert lib.srcuda_reads_pack(None, None, None, None, None, None, 1, None, 0, None, None, None) == ERR_ARG
     lib.srcuda_index_unload(null)      # no-ops
     lib.srcuda_close(null)
     lib.srcuda_host_free(None)

@@ -1,0 +1,103 @@
+"""Chunk reader: srcuda_reader_* (subread_b200/csrc/sr_reader.cpp) hands out the fragments
+geinput_next_read_trim / fetch_next_read_pair hand out, batch by batch, from plain and gzip files, for any window size
+and thread count.  Host code only, CPU only."""
+import gzip
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from subread_b200 import load_fastq
+from subread_b200 import binding
+from test_fastq_split import ref, reference_records  # noqa: F401  (the unmodified reference's reader)
+
+
+def read_all(path1, path2=None, batch=1000, **kw):
+    rd = binding.ChunkReader(path1, path2, **kw)
+    reads, sizes = [], []
+    while True:
+        text, off, ln, n = rd.next(batch)
+        if n == 0:
+            break
+        assert n <= batch and off[0] == 0 and off.shape[0] == n * rd.mates + 1
+        assert np.array_equal(np.diff(off.astype(np.int64)), ln.astype(np.int64))      # dense: reads back to back
+        reads += [text[int(o):int(o) + int(k)].tobytes() for o, k in zip(off[:-1], ln)]
+        sizes.append(n)
+    rd.close()
+    return reads, sizes
+
+
+def chunk_reads(chunk):
+    return [chunk.text[int(chunk.off[i]):int(chunk.off[i + 1])].tobytes() for i in range(chunk.off.shape[0] - 1)]
+
+
+@pytest.mark.parametrize("window,threads,batch", [(0, 1, 1000), (4096, 1, 7), (5000, 3, 333), (1 << 20, 4, 100000)])
+def test_golden_files_plain_and_gzip(window, threads, batch, tmp_path):
+    for r1, r2 in (("se_R1.fastq.gz", None), ("pe_R1.fastq.gz", "pe_R2.fastq.gz")):
+        p1, p2 = os.path.join(GOLDEN, r1), os.path.join(GOLDEN, r2) if r2 else None
+        expect = chunk_reads(load_fastq(p1, p2))
+        got, sizes = read_all(p1, p2, batch, window_bytes=window, threads=threads)                  # gzip
+        assert got == expect
+        mates = 2 if r2 else 1
+        assert all(s == batch for s in sizes[:-1]) and sum(sizes) * mates == len(expect)           # full batches but the last
+        plain = []
+        for p in (p1, p2):
+            if p:
+                q = str(tmp_path / (os.path.basename(p)[:-3]))
+                with gzip.open(p, "rb") as a, open(q, "wb") as b:
+                    b.write(a.read())
+                plain.append(q)
+        got, _ = read_all(plain[0], plain[1] if r2 else None, batch, window_bytes=window, threads=threads)
+        assert got == expect
+
+
+def test_reader_against_the_reference_reader(ref, tmp_path):  # noqa: F811
+    rnd = random.Random(4)
+    recs = []
+    for i in range(5000):
+        n = rnd.randrange(1, 260)
+        recs.append(b"@r%d comment\n%s\n+\n%s\n" % (i, bytes(rnd.choice(b"ACGTNacgt") for _ in range(n)), bytes(rnd.choice(b"IH#@+5") for _ in range(n))))
+    recs.insert(2500, b"@long\n" + b"ACGT" * 400 + b"\n+\n" + b"I" * 1600 + b"\n")       # 1600 bases: cut to 1209
+    path = str(tmp_path / "x.fq")
+    with open(path, "wb") as fh:
+        fh.write(b"\n".join(recs))                       # blank line between records, none at the end
+    for t5, t3 in ((0, 0), (3, 2)):
+        exp = [e[1] for e in reference_records(ref, path, t5, t3)]
+        for window, threads in ((0, 1), (4096, 2), (100000, 4)):
+            got, _ = read_all(path, None, 999, window_bytes=window, threads=threads, trim_5=t5, trim_3=t3)
+            assert got == exp, (t5, t3, window, threads)
+
+
+def test_reader_errors(tmp_path):
+    with pytest.raises(binding.SubreadCudaError, match="cannot open"):
+        binding.ChunkReader(str(tmp_path / "missing.fq"))
+    a, b = str(tmp_path / "a.fq"), str(tmp_path / "b.fq")
+    with open(a, "wb") as fh:
+        fh.write(b"@1\nACGT\n+\nIIII\n@2\nACGT\n+\nIIII\n")
+    with open(b, "wb") as fh:
+        fh.write(b"@1\nACGT\n+\nIIII\n")
+    rd = binding.ChunkReader(a, b)
+    with pytest.raises(binding.SubreadCudaError, match="different amounts of reads"):
+        while rd.next(10)[3]:
+            pass
+    rd.close()
+    with open(b, "wb") as fh:
+        fh.write(b"@1\nACGT\n+\nIIII\n@2\nACGT\nIIII\n@3\nAC\n+\nII\n")
+    rd = binding.ChunkReader(b)
+    text, off, ln, n = rd.next(1)
+    assert n == 1 and text.tobytes() == b"ACGT"
+    with pytest.raises(binding.SubreadCudaError, match="format issue at byte 23"):
+        rd.next(10)
+    rd.close()
+    empty = str(tmp_path / "empty.fq")
+    open(empty, "wb").close()
+    rd = binding.ChunkReader(empty)
+    assert rd.next(5)[3] == 0
+    rd.close()
+    # a buffer that cannot hold the batch is an argument error, not an overrun
+    rd = binding.ChunkReader(a)
+    with pytest.raises(binding.SubreadCudaError, match="too small"):
+        rd.next(2, max_read_len=1)
+    rd.close()
