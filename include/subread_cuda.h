@@ -233,7 +233,7 @@ int srcuda_reads_pack_mt(const char *buf1, const uint64_t *off1, const uint16_t 
 typedef struct srcuda_reader srcuda_reader;
 
 /* Opens one (path2 = NULL) or two FASTQ files, plain or gzip: geinput_open (input-files.c:455) for the FASTQ types.
- * The files are read in windows of window_bytes (0: 64 MB), each indexed by srcuda_fastq_split_mt with n_threads.
+ * The files are read in windows of window_bytes (0: 16 MB), each indexed by srcuda_fastq_split_mt with n_threads.
  * *out is set even on failure (srcuda_reader_error says why; close it). */
 int srcuda_reader_open(const char *path1, const char *path2, uint64_t window_bytes, int n_threads, int trim_5, int trim_3,
                        srcuda_reader **out);

@@ -6,14 +6,19 @@
 // The record grammar is sr_fastq.cpp's (= the reference's plain-FASTQ branch); gzip input is inflated by zlib in front of
 // the same grammar (the reference's own gzip branch reads lines with seekgz_gets and does not skip blank lines: the two
 // agree on every file without blank lines).  Host code only.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/subread_cuda.h"
@@ -21,7 +26,9 @@
 namespace {
 
 struct Stream {
-	gzFile fp = nullptr;
+	gzFile fp = nullptr;            // gzip input
+	int fd = -1;                    // plain input: read() straight into the window
+	uint64_t size = 0, read_pos = 0; // regular plain file: its size and the offset of the next unread byte (size 0: a pipe)
 	std::vector<char> win;          // window of file bytes
 	size_t have = 0;                // valid bytes in win
 	size_t consumed = 0;            // bytes of win behind the last indexed record
@@ -71,16 +78,52 @@ int refill(srcuda_reader *r, int which)
 	}
 	while (true) {
 		while (!st.eof && st.have < st.win.size()) {
-			const int got = gzread(st.fp, st.win.data() + st.have, (unsigned)std::min<size_t>(st.win.size() - st.have, 1u << 30));
-			if (got < 0) {
-				int errnum = 0;
-				const char *m = gzerror(st.fp, &errnum);
-				return fail(r, SRCUDA_ERR_IO, "read error in input file %d: %s", which + 1, m ? m : "?");
+			const size_t want = std::min<size_t>(st.win.size() - st.have, 1u << 30);
+			long got;
+			if (st.fp) {
+				got = gzread(st.fp, st.win.data() + st.have, (unsigned)want);
+				if (got < 0) {
+					int errnum = 0;
+					const char *m = gzerror(st.fp, &errnum);
+					return fail(r, SRCUDA_ERR_IO, "read error in input file %d: %s", which + 1, m ? m : "?");
+				}
+			} else if (st.size && r->threads > 1 && std::min<uint64_t>(want, st.size - st.read_pos) >= (8u << 20)) {
+				// a regular file: the threads copy disjoint slices out of the page cache at once
+				const uint64_t total = std::min<uint64_t>(want, st.size - st.read_pos);
+				const int T = (int)std::min<uint64_t>((uint64_t)r->threads, total >> 20);
+				std::vector<long> res((size_t)T, 0);
+				auto slice = [&](int t) {
+					const uint64_t lo = total / T * t, hi = t == T - 1 ? total : total / T * (t + 1);
+					uint64_t at = lo;
+					while (at < hi) {
+						const ssize_t k = pread(st.fd, st.win.data() + st.have + at, hi - at, (off_t)(st.read_pos + at));
+						if (k < 0 && errno == EINTR) continue;
+						if (k <= 0) { res[(size_t)t] = k < 0 ? -(long)errno : -1000000L; return; }   // error, or the file shrank
+						at += (uint64_t)k;
+					}
+				};
+				{
+					std::vector<std::thread> th;
+					for (int t = 1; t < T; t++) th.emplace_back(slice, t);
+					slice(0);
+					for (auto &x : th) x.join();
+				}
+				for (long v : res)
+					if (v) return fail(r, SRCUDA_ERR_IO, "read error in input file %d: %s", which + 1, v == -1000000L ? "the file changed size" : strerror((int)-v));
+				got = (long)total;
+				st.read_pos += total;
+			} else {
+				do got = st.size ? (long)pread(st.fd, st.win.data() + st.have, want, (off_t)st.read_pos) : (long)read(st.fd, st.win.data() + st.have, want);
+				while (got < 0 && errno == EINTR);
+				if (got < 0) return fail(r, SRCUDA_ERR_IO, "read error in input file %d: %s", which + 1, strerror(errno));
+				st.read_pos += (uint64_t)got;
 			}
 			if (got == 0) st.eof = true;
 			st.have += (size_t)got;
 		}
-		const size_t cap = st.have / 6 + 2;
+		// room for records of 32 bytes and more; shorter ones just take another round (SRCUDA_FASTQ_FULL leaves the rest
+		// of the window for the next refill)
+		const size_t cap = st.have / 32 + 1024;
 		if (st.off.size() < cap) { st.off.resize(cap); st.len.resize(cap); }
 		srcuda_fastq_batch b;
 		const int rc = srcuda_fastq_split_mt(st.win.data(), st.have, st.eof ? 1 : 0, r->trim_5, r->trim_3, (int64_t)cap, 0, 1, st.off.data(),
@@ -118,12 +161,25 @@ extern "C" int srcuda_reader_open(const char *path1, const char *path2, uint64_t
 	r->threads = std::max(1, n_threads);
 	r->trim_5 = trim_5;
 	r->trim_3 = trim_3;
-	r->window = (size_t)std::max<uint64_t>(window_bytes ? window_bytes : (64u << 20), 4096);
+	r->window = (size_t)std::max<uint64_t>(window_bytes ? window_bytes : (16u << 20), 4096)   // 16 MB: the window stays in the last-level cache between read, index and gather;
 	for (int i = 0; i < r->files; i++) {
 		const char *p = i ? path2 : path1;
-		r->s[i].fp = gzopen(p, "rb");         // reads plain files as they are
-		if (!r->s[i].fp) return fail(r, SRCUDA_ERR_IO, "cannot open '%s'", p);
-		gzbuffer(r->s[i].fp, 1u << 20);
+		const int fd = open(p, O_RDONLY);
+		if (fd < 0) return fail(r, SRCUDA_ERR_IO, "cannot open '%s': %s", p, strerror(errno));
+		unsigned char magic[2] = {0, 0};
+		const bool gz = pread(fd, magic, 2, 0) == 2 && magic[0] == 31 && magic[1] == 139;   // as geinput_open tells them apart (:473)
+		if (gz) {
+			r->s[i].fp = gzdopen(fd, "rb");
+			if (!r->s[i].fp) { close(fd); return fail(r, SRCUDA_ERR_IO, "cannot open '%s' as gzip", p); }
+			gzbuffer(r->s[i].fp, 1u << 20);
+		} else {
+			r->s[i].fd = fd;
+			struct stat sb;
+			if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode)) r->s[i].size = (uint64_t)sb.st_size;
+#ifdef POSIX_FADV_SEQUENTIAL
+			posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+		}
 		try {
 			r->s[i].win.resize(r->window);
 		} catch (...) {
@@ -186,5 +242,6 @@ extern "C" void srcuda_reader_close(srcuda_reader *r)
 	if (!r) return;
 	for (int i = 0; i < 2; i++)
 		if (r->s[i].fp) gzclose(r->s[i].fp);
+		else if (r->s[i].fd >= 0) close(r->s[i].fd);
 	delete r;
 }
