@@ -161,7 +161,8 @@ extern "C" int srcuda_reader_open(const char *path1, const char *path2, uint64_t
 	r->threads = std::max(1, n_threads);
 	r->trim_5 = trim_5;
 	r->trim_3 = trim_3;
-	r->window = (size_t)std::max<uint64_t>(window_bytes ? window_bytes : (16u << 20), 4096)   // 16 MB: the window stays in the last-level cache between read, index and gather;
+	// default 16 MB: the window stays in the last-level cache between read, index and gather
+	r->window = (size_t)std::max<uint64_t>(window_bytes ? window_bytes : (16u << 20), 4096);
 	for (int i = 0; i < r->files; i++) {
 		const char *p = i ? path2 : path1;
 		const int fd = open(p, O_RDONLY);
