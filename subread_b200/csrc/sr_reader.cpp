@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -49,6 +50,8 @@ struct srcuda_reader {
 	int threads = 1, trim_5 = 0, trim_3 = 0;
 	size_t window = 0;
 	std::string error;
+	std::mutex error_mu;
+	bool error_fresh = false;       // an error was recorded during the current call
 	int64_t frags_out = 0;
 };
 
@@ -61,7 +64,11 @@ int fail(srcuda_reader *r, int rc, const char *fmt, ...)
 	va_start(ap, fmt);
 	vsnprintf(msg, sizeof(msg), fmt, ap);
 	va_end(ap);
-	r->error = msg;
+	std::lock_guard<std::mutex> g(r->error_mu);     // the two files of a pair are refilled side by side
+	if (r->error_fresh) r->error += "; ";
+	else r->error.clear();
+	r->error += msg;
+	r->error_fresh = true;
 	return rc;
 }
 
@@ -196,16 +203,31 @@ extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *tex
 	if (!r || !n_frags || max_frags < 0 || (max_frags && (!text || !off || !len))) return SRCUDA_ERR_ARG;
 	*n_frags = 0;
 	if (text_bytes) *text_bytes = 0;
+	r->error_fresh = false;
 	try {
 		int64_t done = 0;
 		uint64_t written = 0;
 		const int mates = r->files;
 		while (done < max_frags) {
-			for (int i = 0; i < r->files; i++)
-				if (r->s[i].pending() == 0) {
-					const int rc = refill(r, i);
-					if (rc) return rc;
-				}
+			const bool need0 = r->s[0].pending() == 0, need1 = r->files == 2 && r->s[1].pending() == 0;
+			if (need0 && need1) {               // both files at once: two inflates (or two page-cache copies) side by side
+				int rc1 = SRCUDA_OK;
+				bool threaded = true;
+				std::thread other;
+				try {
+					other = std::thread([&] {
+						try { rc1 = refill(r, 1); } catch (...) { rc1 = fail(r, SRCUDA_ERR_NOMEM, "out of memory"); }
+					});
+				} catch (...) { threaded = false; }
+				int rc0;
+				try { rc0 = refill(r, 0); } catch (...) { rc0 = fail(r, SRCUDA_ERR_NOMEM, "out of memory"); }
+				if (threaded) other.join();
+				else rc1 = refill(r, 1);
+				if (rc0 || rc1) return rc0 ? rc0 : rc1;
+			} else if (need0 || need1) {
+				const int rc = refill(r, need0 ? 0 : 1);
+				if (rc) return rc;
+			}
 			int64_t take = max_frags - done;
 			for (int i = 0; i < r->files; i++) take = std::min(take, r->s[i].pending());
 			if (take == 0) {
