@@ -244,6 +244,9 @@ int srcuda_reader_open(const char *path1, const char *path2, uint64_t window_byt
  * without '@' or '+' is SRCUDA_ERR_FORMAT after the records in front of it have been handed out. */
 int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *text, uint64_t text_capacity, uint64_t *off, uint16_t *len,
                        int64_t *n_frags, uint64_t *text_bytes);
+/* Passes over the next n_frags fragments without gathering them (*skipped = how many there were): a process that maps
+ * one slice of every chunk (one GPU of several) skips the slices of the others. */
+int srcuda_reader_skip(srcuda_reader *r, int64_t n_frags, int64_t *skipped);
 const char *srcuda_reader_error(const srcuda_reader *r);
 void srcuda_reader_close(srcuda_reader *r);
 

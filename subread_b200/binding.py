@@ -24,7 +24,7 @@ EXPORTS = [
     "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device",
     "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth",
     "srcuda_fastq_split", "srcuda_fastq_split_mt", "srcuda_reads_pack", "srcuda_reads_pack_mt",
-    "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_error", "srcuda_reader_close",
+    "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_skip", "srcuda_reader_error", "srcuda_reader_close",
 ]
 
 
@@ -106,6 +106,7 @@ def load_library():
     L.srcuda_reads_pack_mt.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, u64, vp, vp, ctypes.c_int, ctypes.POINTER(u64)]
     L.srcuda_reader_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.srcuda_reader_next.argtypes = [vp, i64, vp, u64, vp, vp, ctypes.POINTER(i64), ctypes.POINTER(u64)]
+    L.srcuda_reader_skip.argtypes = [vp, i64, ctypes.POINTER(i64)]
     L.srcuda_reader_error.argtypes = [vp]
     L.srcuda_reader_error.restype = ctypes.c_char_p
     L.srcuda_reader_close.argtypes = [vp]
@@ -347,6 +348,14 @@ class ChunkReader:
         k = n.value * self.mates
         off[k] = used.value
         return text[:used.value], off[:k + 1], ln[:k], int(n.value)
+
+    def skip(self, n_frags):
+        """Passes over the next n_frags fragments; returns how many there were."""
+        n = ctypes.c_int64()
+        rc = self.lib.srcuda_reader_skip(self.h, int(n_frags), ctypes.byref(n))
+        if rc:
+            raise SubreadCudaError(f"srcuda_reader_skip: {self.lib.srcuda_reader_error(self.h).decode()} (rc={rc})")
+        return int(n.value)
 
     def close(self):
         if self.h:

@@ -200,7 +200,8 @@ extern "C" int srcuda_reader_open(const char *path1, const char *path2, uint64_t
 extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *text, uint64_t text_capacity, uint64_t *off, uint16_t *len,
                                   int64_t *n_frags, uint64_t *text_bytes)
 {
-	if (!r || !n_frags || max_frags < 0 || (max_frags && (!text || !off || !len))) return SRCUDA_ERR_ARG;
+	const bool skip = !text && !off && !len;       // srcuda_reader_skip: the fragments are indexed and passed over
+	if (!r || !n_frags || max_frags < 0 || (max_frags && !skip && (!text || !off || !len))) return SRCUDA_ERR_ARG;
 	*n_frags = 0;
 	if (text_bytes) *text_bytes = 0;
 	r->error_fresh = false;
@@ -236,6 +237,11 @@ extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *tex
 					return fail(r, SRCUDA_ERR_FORMAT, "two input files have different amounts of reads");
 				break;
 			}
+			if (skip) {
+				done += take;
+				for (int i = 0; i < r->files; i++) r->s[i].cursor += take;
+				continue;
+			}
 			const Stream &a = r->s[0], &b = r->s[1];
 			uint64_t w = 0;
 			const int rc = srcuda_reads_pack_mt(a.win.data(), a.off.data() + a.cursor, a.len.data() + a.cursor, mates == 2 ? b.win.data() : nullptr,
@@ -256,6 +262,14 @@ extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *tex
 	} catch (...) {
 		return fail(r, SRCUDA_ERR_NOMEM, "out of memory");
 	}
+}
+
+extern "C" int srcuda_reader_skip(srcuda_reader *r, int64_t n_frags, int64_t *skipped)
+{
+	int64_t n = 0;
+	const int rc = srcuda_reader_next(r, n_frags, nullptr, 0, nullptr, nullptr, &n, nullptr);
+	if (skipped) *skipped = n;
+	return rc;
 }
 
 extern "C" const char *srcuda_reader_error(const srcuda_reader *r) { return r ? r->error.c_str() : "null reader"; }

@@ -91,6 +91,7 @@ def test_null_arguments_are_argument_errors(lib):
     n = ctypes.c_int64()
     assert lib.srcuda_reader_open(None, None, 0, 1, 0, 0, None) == ERR_ARG
     assert lib.srcuda_reader_next(null, 1, None, 0, None, None, ctypes.byref(n), None) == ERR_ARG
+    assert lib.srcuda_reader_skip(null, 1, ctypes.byref(n)) == ERR_ARG
     assert lib.srcuda_reader_error(null) == b"null reader"
     lib.srcuda_reader_close(null)
     batch = binding.FastqBatch()

@@ -101,3 +101,37 @@ def test_reader_errors(tmp_path):
     with pytest.raises(binding.SubreadCudaError, match="too small"):
         rd.next(2, max_read_len=1)
     rd.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_ranks_reading_their_slices_cover_the_file(world):
+    """Read sharding: every rank opens the same files, and per chunk gathers only its own contiguous
+    slice (subread_b200.sharding.shard_range) and skips the others'; together the ranks see every fragment once, in order."""
+    from subread_b200.sharding import shard_range
+    p1, p2 = os.path.join(GOLDEN, "pe_R1.fastq.gz"), os.path.join(GOLDEN, "pe_R2.fastq.gz")
+    whole = load_fastq(p1, p2)
+    expect = chunk_reads(whole)
+    chunk_frags = 300                                   # stands for reads_per_chunk
+    per_rank = []
+    for rank in range(world):
+        rd = binding.ChunkReader(p1, p2, window_bytes=20000, threads=2)
+        mine, f0 = [], 0
+        while f0 < whole.n_frags:
+            n_chunk = min(chunk_frags, whole.n_frags - f0)
+            lo, hi = shard_range(n_chunk, world, rank)
+            assert rd.skip(lo) == lo
+            text, off, ln, n = rd.next(hi - lo)
+            assert n == hi - lo
+            mine.append((f0 + lo, [text[int(o):int(o) + int(k)].tobytes() for o, k in zip(off[:-1], ln)]))
+            assert rd.skip(n_chunk - hi) == n_chunk - hi
+            f0 += n_chunk
+        assert rd.skip(10) == 0 and rd.next(10)[3] == 0        # the end
+        rd.close()
+        per_rank.append(mine)
+    got = [None] * len(expect)
+    for mine in per_rank:
+        for first, reads in mine:
+            for i, rtext in enumerate(reads):
+                assert got[2 * first + i] is None
+                got[2 * first + i] = rtext
+    assert got == expect
