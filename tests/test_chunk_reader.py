@@ -135,3 +135,37 @@ def test_ranks_reading_their_slices_cover_the_file(world):
                 assert got[2 * first + i] is None
                 got[2 * first + i] = rtext
     assert got == expect
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("threads", [1, 4])
+def test_damaged_gzip_is_an_error_not_a_hang(threads, tmp_path):
+    """A gzip file cut short or corrupted in the middle: the reader (and its read-ahead thread) reports a read error or the
+    records that were intact followed by a format issue -- it never hangs and never hands out garbage silently."""
+    rnd = random.Random(8)
+    recs = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rnd.choice(b"ACGT") for _ in range(100)), b"I" * 100) for i in range(20000))
+    blob = gzip.compress(recs, compresslevel=1)
+    cut = str(tmp_path / "cut.fq.gz")
+    with open(cut, "wb") as fh:
+        fh.write(blob[:len(blob) // 2])
+    bad = bytearray(blob)
+    for k in range(len(bad) // 2, len(bad) // 2 + 64):
+        bad[k] ^= 0x5A
+    broken = str(tmp_path / "broken.fq.gz")
+    with open(broken, "wb") as fh:
+        fh.write(bytes(bad))
+    for path in (cut, broken):
+        rd = binding.ChunkReader(path, threads=threads, window_bytes=1 << 20)
+        got = 0
+        with pytest.raises(binding.SubreadCudaError):
+            while True:
+                n = rd.next(5000)[3]
+                if n == 0:
+                    break
+                got += n
+        assert got < 20000
+        rd.close()
+    # closing a reader whose read-ahead thread still holds an unread block
+    rd = binding.ChunkReader(os.path.join(GOLDEN, "pe_R1.fastq.gz"), os.path.join(GOLDEN, "pe_R2.fastq.gz"), threads=threads)
+    assert rd.next(10)[3] == 10
+    rd.close()
