@@ -81,11 +81,12 @@ k_map_warp(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int n_wor
 		const int l0 = a.len[r0];
 		uint64_t o1 = 0;
 		int l1 = 0;
-		bool bad = o0 + (uint64_t)l0 > a.text_bytes || l0 > kMaxReadLen;
+		// (overflow-safe: an offset below text_origin wraps to a huge o and must be refused, not added to)
+		bool bad = o0 > a.text_bytes || (uint64_t)l0 > a.text_bytes - o0 || l0 > kMaxReadLen;
 		if (MATES == 2) {
 			o1 = a.off[r0 + 1] - a.text_origin;
 			l1 = a.len[r0 + 1];
-			bad = bad || o1 + (uint64_t)l1 > a.text_bytes || l1 > kMaxReadLen;
+			bad = bad || o1 > a.text_bytes || (uint64_t)l1 > a.text_bytes - o1 || l1 > kMaxReadLen;
 		}
 		if (bad) {
 			if (lane == 0) atomicAdd(a.bad_reads, 1u);
@@ -115,11 +116,11 @@ k_map_scalar(const DevIndex ix, const VoteConfig cfg, const ChunkArgs a, int use
 		const int l0 = a.len[r0];
 		uint64_t o1 = 0;
 		int l1 = 0;
-		bool bad = o0 + (uint64_t)l0 > a.text_bytes || l0 > kMaxReadLen;
+		bool bad = o0 > a.text_bytes || (uint64_t)l0 > a.text_bytes - o0 || l0 > kMaxReadLen;
 		if (mates == 2) {
 			o1 = a.off[r0 + 1] - a.text_origin;
 			l1 = a.len[r0 + 1];
-			bad = bad || o1 + (uint64_t)l1 > a.text_bytes || l1 > kMaxReadLen;
+			bad = bad || o1 > a.text_bytes || (uint64_t)l1 > a.text_bytes - o1 || l1 > kMaxReadLen;
 		}
 		if (bad) {
 			if (!use_queue) atomicAdd(a.bad_reads, 1u);
@@ -1144,48 +1145,74 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		memset(b.h_counters, 0, need);
 	}
 
-	CU(h, cudaEventRecord(h->ev_begin, h->set[0].stream));
-	for (int i = 1; i < kSets; i++) CU(h, cudaStreamWaitEvent(h->set[i].stream, h->ev_begin, 0));
+	// Everything that can be refused is refused before the first copy is enqueued: once a batch is in flight the caller's
+	// buffers are the source and target of asynchronous copies and must stay untouched until the streams have drained.
+	std::vector<int> batch_max_len((size_t)n_batches, 1);
+	for (int64_t bi = 0; bi < n_batches; bi++) {
+		const int64_t f0 = bi * batch, f1 = std::min(n_frags, f0 + batch);
+		const int64_t r0 = f0 * mates, r1 = f1 * mates;
+		int max_len = 1;
+		uint64_t lo = off[r0], end = 0;
+		for (int64_t r = r0; r < r1; r++) {
+			max_len = std::max<int>(max_len, len[r]);
+			lo = std::min(lo, off[r]);
+			end = std::max(end, off[r] + len[r]);
+		}
+		if (max_len > sr::kMaxReadLen) return fail(h, SRCUDA_ERR_ARG, "a read is longer than %d", sr::kMaxReadLen);
+		// the batch's reads must lie in text[off[first] .. off[last] + len[last])
+		if (lo < off[r0] || end > off[r1 - 1] + len[r1 - 1]) return fail(h, SRCUDA_ERR_ARG, "read offsets must be non-decreasing");
+		batch_max_len[(size_t)bi] = max_len;
+	}
+	// any failure from here on waits for the copies already enqueued before it returns
+	auto drain = [&](int rc_in) {
+		for (int i = 0; i < kSets; i++) if (h->set[i].stream) cudaStreamSynchronize(h->set[i].stream);
+		cudaGetLastError();
+		return rc_in;
+	};
+#define CUD(h, call)                                                                                                      \
+	do {                                                                                                                  \
+		cudaError_t e_ = (call);                                                                                          \
+		if (e_ != cudaSuccess) return drain(fail(h, SRCUDA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));     \
+	} while (0)
+
+	CUD(h, cudaEventRecord(h->ev_begin, h->set[0].stream));
+	for (int i = 1; i < kSets; i++) CUD(h, cudaStreamWaitEvent(h->set[i].stream, h->ev_begin, 0));
 	for (int64_t bi = 0; bi < n_batches; bi++) {
 		BatchSet &bs = h->set[bi % kSets];
 		cudaStream_t s = bs.stream;
 		const int64_t f0 = bi * batch, f1 = std::min(n_frags, f0 + batch), nf = f1 - f0;
 		const int64_t r0 = f0 * mates, nr = nf * mates;
-		// the batch's reads must lie in text[off[r0] .. off[last]+len[last]) -- offsets non-decreasing
-		int max_len = 1;
-		for (int64_t r = r0; r < r0 + nr; r++) max_len = std::max<int>(max_len, len[r]);
-		if (max_len > sr::kMaxReadLen) return fail(h, SRCUDA_ERR_ARG, "a read is longer than %d", sr::kMaxReadLen);
+		const int max_len = batch_max_len[(size_t)bi];
 		const uint64_t origin = off[r0];
 		const uint64_t text_bytes = off[r0 + nr - 1] + len[r0 + nr - 1] - origin;
-		if (off[r0 + nr - 1] < origin) return fail(h, SRCUDA_ERR_ARG, "read offsets must be non-decreasing");
 		const size_t n_slots = (size_t)nr * mb;
-		if ((rc = ensure(h, bs.text, text_bytes + 16))) return rc;
-		if ((rc = ensure(h, bs.off, sizeof(uint64_t) * (size_t)nr))) return rc;
-		if ((rc = ensure(h, bs.len, sizeof(uint16_t) * (size_t)nr))) return rc;
-		if ((rc = ensure(h, bs.out, sizeof(srcuda_mapping_result) * n_slots))) return rc;
-		if ((rc = ensure(h, bs.queue, sizeof(uint32_t) * (size_t)nf))) return rc;
-		if ((rc = ensure(h, bs.queue0, sizeof(uint32_t) * (size_t)nf))) return rc;
-		if (out_verify && (rc = ensure(h, bs.verify, sizeof(uint16_t) * n_slots))) return rc;
+		if ((rc = ensure(h, bs.text, text_bytes + 16))) return drain(rc);
+		if ((rc = ensure(h, bs.off, sizeof(uint64_t) * (size_t)nr))) return drain(rc);
+		if ((rc = ensure(h, bs.len, sizeof(uint16_t) * (size_t)nr))) return drain(rc);
+		if ((rc = ensure(h, bs.out, sizeof(srcuda_mapping_result) * n_slots))) return drain(rc);
+		if ((rc = ensure(h, bs.queue, sizeof(uint32_t) * (size_t)nf))) return drain(rc);
+		if ((rc = ensure(h, bs.queue0, sizeof(uint32_t) * (size_t)nf))) return drain(rc);
+		if (out_verify && (rc = ensure(h, bs.verify, sizeof(uint16_t) * n_slots))) return drain(rc);
 		const size_t bm_bytes = sizeof(uint16_t) * sr::kBigMarginU16 * (size_t)nr;
 		if (cfg.do_junctions) {
-			if ((rc = ensure(h, bs.junc, sizeof(srcuda_subjunc_result) * n_slots))) return rc;
-			if ((rc = ensure(h, bs.big_margin, bm_bytes))) return rc;
+			if ((rc = ensure(h, bs.junc, sizeof(srcuda_subjunc_result) * n_slots))) return drain(rc);
+			if ((rc = ensure(h, bs.big_margin, bm_bytes))) return drain(rc);
 		}
 
-		CU(h, cudaMemcpyAsync(bs.text.p, text + origin, text_bytes, cudaMemcpyHostToDevice, s));
-		CU(h, cudaMemcpyAsync(bs.off.p, off + r0, sizeof(uint64_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
-		CU(h, cudaMemcpyAsync(bs.len.p, len + r0, sizeof(uint16_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
+		CUD(h, cudaMemcpyAsync(bs.text.p, text + origin, text_bytes, cudaMemcpyHostToDevice, s));
+		CUD(h, cudaMemcpyAsync(bs.off.p, off + r0, sizeof(uint64_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
+		CUD(h, cudaMemcpyAsync(bs.len.p, len + r0, sizeof(uint16_t) * (size_t)nr, cudaMemcpyHostToDevice, s));
 		h->timing.h2d_bytes += text_bytes + 10 * (uint64_t)nr;
 		if (!out_align_is_zero) {
-			CU(h, cudaMemcpyAsync(bs.out.p, out_align + (size_t)r0 * mb, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyHostToDevice, s));
+			CUD(h, cudaMemcpyAsync(bs.out.p, out_align + (size_t)r0 * mb, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyHostToDevice, s));
 			h->timing.h2d_bytes += sizeof(srcuda_mapping_result) * n_slots;
 			if (cfg.do_junctions) {
-				CU(h, cudaMemcpyAsync(bs.junc.p, out_junc + (size_t)r0 * mb, sizeof(srcuda_subjunc_result) * n_slots, cudaMemcpyHostToDevice, s));
-				CU(h, cudaMemcpyAsync(bs.big_margin.p, out_big_margin + (size_t)r0 * sr::kBigMarginU16, bm_bytes, cudaMemcpyHostToDevice, s));
+				CUD(h, cudaMemcpyAsync(bs.junc.p, out_junc + (size_t)r0 * mb, sizeof(srcuda_subjunc_result) * n_slots, cudaMemcpyHostToDevice, s));
+				CUD(h, cudaMemcpyAsync(bs.big_margin.p, out_big_margin + (size_t)r0 * sr::kBigMarginU16, bm_bytes, cudaMemcpyHostToDevice, s));
 				h->timing.h2d_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 			}
 		}
-		CU(h, cudaMemsetAsync(bs.counters, 0, 4 * sizeof(uint32_t), s));
+		CUD(h, cudaMemsetAsync(bs.counters, 0, 4 * sizeof(uint32_t), s));
 		sr::ChunkArgs a;
 		a.text = (const uint8_t *)bs.text.p; a.text_origin = origin; a.text_bytes = text_bytes;
 		a.off = (const uint64_t *)bs.off.p; a.len = (const uint16_t *)bs.len.p; a.n_frags = nf;
@@ -1195,26 +1222,27 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		a.in_list = nullptr; a.in_count = nullptr;
 		a.junc = cfg.do_junctions ? (sr::JuncWords *)bs.junc.p : nullptr;
 		a.big_margin = cfg.do_junctions ? (uint16_t *)bs.big_margin.p : nullptr;
-		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[4 * bi]))) return rc;
-		CU(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
+		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[4 * bi]))) return drain(rc);
+		CUD(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
 		h->timing.d2h_bytes += sizeof(srcuda_mapping_result) * n_slots;
 		if (out_verify) {
-			CU(h, cudaMemcpyAsync(out_verify + (size_t)r0 * mb, bs.verify.p, sizeof(uint16_t) * n_slots, cudaMemcpyDeviceToHost, s));
+			CUD(h, cudaMemcpyAsync(out_verify + (size_t)r0 * mb, bs.verify.p, sizeof(uint16_t) * n_slots, cudaMemcpyDeviceToHost, s));
 			h->timing.d2h_bytes += sizeof(uint16_t) * n_slots;
 		}
 		if (cfg.do_junctions) {
-			CU(h, cudaMemcpyAsync(out_junc + (size_t)r0 * mb, bs.junc.p, sizeof(srcuda_subjunc_result) * n_slots, cudaMemcpyDeviceToHost, s));
-			CU(h, cudaMemcpyAsync(out_big_margin + (size_t)r0 * sr::kBigMarginU16, bs.big_margin.p, bm_bytes, cudaMemcpyDeviceToHost, s));
+			CUD(h, cudaMemcpyAsync(out_junc + (size_t)r0 * mb, bs.junc.p, sizeof(srcuda_subjunc_result) * n_slots, cudaMemcpyDeviceToHost, s));
+			CUD(h, cudaMemcpyAsync(out_big_margin + (size_t)r0 * sr::kBigMarginU16, bs.big_margin.p, bm_bytes, cudaMemcpyDeviceToHost, s));
 			h->timing.d2h_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 		}
-		CU(h, cudaMemcpyAsync(bs.h_counters + 4 * (bi / kSets), bs.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CUD(h, cudaMemcpyAsync(bs.h_counters + 4 * (bi / kSets), bs.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	}
 	for (int i = 1; i < kSets; i++) {  // join every stream into stream 0, then stamp the end there
-		CU(h, cudaEventRecord(h->ev_join[i], h->set[i].stream));
-		CU(h, cudaStreamWaitEvent(h->set[0].stream, h->ev_join[i], 0));
+		CUD(h, cudaEventRecord(h->ev_join[i], h->set[i].stream));
+		CUD(h, cudaStreamWaitEvent(h->set[0].stream, h->ev_join[i], 0));
 	}
-	CU(h, cudaEventRecord(h->ev_end, h->set[0].stream));
-	for (int i = 0; i < kSets; i++) CU(h, cudaStreamSynchronize(h->set[i].stream));
+	CUD(h, cudaEventRecord(h->ev_end, h->set[0].stream));
+	for (int i = 0; i < kSets; i++) CUD(h, cudaStreamSynchronize(h->set[i].stream));
+#undef CUD
 
 	float ms = 0;
 	CU(h, cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end));

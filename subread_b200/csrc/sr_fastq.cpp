@@ -336,7 +336,10 @@ int split_threaded(const char *buf, uint64_t n_bytes, bool at_eof_b, int trim_5,
 		C.room((size_t)(cut[t + 1] - cut[t]) / 256 + 16, names, quals);
 		const uint64_t shift = sink.base + (uint64_t)(cut[t] - b);
 		uint32_t m = 0;
-		ends[(size_t)t] = parse_range(cut[t], cut[t + 1], last ? at_eof != 0 : true, trim_5, trim_3, INT64_MAX, [&](const Record &R) {
+		// a piece that is not the last one is parsed like a buffer with more to come (at_eof = false): it is only accepted when
+		// its last record ends with its own '\n' inside the piece -- with at_eof a piece that stops right behind a '+' line
+		// would pass with an empty quality line, which the sequential parse never sees
+		ends[(size_t)t] = parse_range(cut[t], cut[t + 1], last ? at_eof != 0 : false, trim_5, trim_3, INT64_MAX, [&](const Record &R) {
 			if (C.n == C.off.size()) C.room(C.n + 1, names, quals);
 			const size_t i = C.n++;
 			C.off[i] = shift + R.seq;
@@ -351,7 +354,7 @@ int split_threaded(const char *buf, uint64_t n_bytes, bool at_eof_b, int trim_5,
 	int64_t total = 0;
 	bool ok = ran;
 	for (int t = 0; t < T; t++) {
-		if (t < T - 1 && (ends[(size_t)t].rc || ends[(size_t)t].consumed != (uint64_t)(cut[t + 1] - cut[t]))) ok = false;
+		if (t < T - 1 && (ends[(size_t)t].rc || ends[(size_t)t].stop != SRCUDA_FASTQ_MORE || ends[(size_t)t].consumed != (uint64_t)(cut[t + 1] - cut[t]))) ok = false;
 		total += (int64_t)recs[(size_t)t].n;
 	}
 	if (!ok || ends[(size_t)T - 1].rc) {  // odd input: the plain loop decides
@@ -393,7 +396,7 @@ int split_threaded(const char *buf, uint64_t n_bytes, bool at_eof_b, int trim_5,
 	if (total >= max_reads) {            // the arrays are full: stop behind record keep-1, as the plain loop does
 		int t = 0;
 		while (first[(size_t)t + 1] < keep) t++;
-		const ParseEnd cutoff = parse_range(cut[t], cut[t + 1], t == T - 1 ? at_eof != 0 : true, trim_5, trim_3, keep - first[(size_t)t],
+		const ParseEnd cutoff = parse_range(cut[t], cut[t + 1], t == T - 1 ? at_eof != 0 : false, trim_5, trim_3, keep - first[(size_t)t],
 		                                    [](const Record &) {});      // where record keep-1 ends
 		out->consumed = (uint64_t)(cut[t] - b) + cutoff.consumed;
 		out->stop = SRCUDA_FASTQ_FULL;

@@ -67,6 +67,7 @@ struct srcuda_reader {
 	std::mutex error_mu;
 	bool error_fresh = false;       // an error was recorded during the current call
 	int64_t frags_out = 0;
+	int deferred_rc = 0;            // a refill failed after fragments had been gathered: they were handed out, the error comes with the next call
 };
 
 namespace {
@@ -96,11 +97,15 @@ bool read_block(Stream &st, int threads, char *dst, size_t want, size_t *n_out, 
 		long got;
 		if (st.fp) {
 			got = gzread(st.fp, dst + have, (unsigned)ask);
-			if (got < 0) {
+			if (got <= 0) {
+				// gzread answers a stream that was cut short with 0 and Z_BUF_ERROR ("unexpected end of file"), not with -1:
+				// only errnum tells a damaged file from a clean end
 				int errnum = 0;
 				const char *m = gzerror(st.fp, &errnum);
-				err = m ? m : "gzip read error";
-				return false;
+				if (got < 0 || (errnum != Z_OK && errnum != Z_STREAM_END)) {
+					err = m && *m ? m : "gzip read error";
+					return false;
+				}
 			}
 		} else if (st.size && threads > 1 && std::min<uint64_t>(ask, st.size - st.read_pos) >= (8u << 20)) {
 			// a regular file: the threads copy disjoint slices out of the page cache at once
@@ -301,11 +306,25 @@ extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *tex
 	if (!r || !n_frags || max_frags < 0 || (max_frags && !skip && (!text || !off || !len))) return SRCUDA_ERR_ARG;
 	*n_frags = 0;
 	if (text_bytes) *text_bytes = 0;
+	if (r->deferred_rc) {               // the error the call before ran into after it had gathered its fragments
+		const int rc = r->deferred_rc;
+		r->deferred_rc = 0;
+		return rc;
+	}
 	r->error_fresh = false;
 	try {
 		int64_t done = 0;
 		uint64_t written = 0;
 		const int mates = r->files;
+		// a failure with fragments already gathered (their cursors have moved on): hand those out now, fail the next call
+		auto stop = [&](int rc) {
+			if (done == 0) return rc;
+			r->deferred_rc = rc;
+			*n_frags = done;
+			if (text_bytes) *text_bytes = written;
+			r->frags_out += done;
+			return (int)SRCUDA_OK;
+		};
 		while (done < max_frags) {
 			const bool need0 = r->s[0].pending() == 0, need1 = r->files == 2 && r->s[1].pending() == 0;
 			if (need0 && need1) {               // both files at once: two inflates (or two page-cache copies) side by side
@@ -321,17 +340,17 @@ extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *tex
 				try { rc0 = refill(r, 0); } catch (...) { rc0 = fail(r, SRCUDA_ERR_NOMEM, "out of memory"); }
 				if (threaded) other.join();
 				else rc1 = refill(r, 1);
-				if (rc0 || rc1) return rc0 ? rc0 : rc1;
+				if (rc0 || rc1) return stop(rc0 ? rc0 : rc1);
 			} else if (need0 || need1) {
 				const int rc = refill(r, need0 ? 0 : 1);
-				if (rc) return rc;
+				if (rc) return stop(rc);
 			}
 			int64_t take = max_frags - done;
 			for (int i = 0; i < r->files; i++) take = std::min(take, r->s[i].pending());
 			if (take == 0) {
 				// the end: both files must have run out together (core.c:1177-1182)
 				if (r->files == 2 && (r->s[0].pending() > 0) != (r->s[1].pending() > 0))
-					return fail(r, SRCUDA_ERR_FORMAT, "two input files have different amounts of reads");
+					return stop(fail(r, SRCUDA_ERR_FORMAT, "two input files have different amounts of reads"));
 				break;
 			}
 			if (skip) {

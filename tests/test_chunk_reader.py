@@ -169,3 +169,39 @@ def test_damaged_gzip_is_an_error_not_a_hang(threads, tmp_path):
     rd = binding.ChunkReader(os.path.join(GOLDEN, "pe_R1.fastq.gz"), os.path.join(GOLDEN, "pe_R2.fastq.gz"), threads=threads)
     assert rd.next(10)[3] == 10
     rd.close()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("where", ["record_boundary", "inside_quality"])
+def test_gzip_cut_at_a_flush_point_is_an_error(threads, where, tmp_path):
+    """A gzip stream that simply stops -- at a Z_FULL_FLUSH point, so that inflate sees no damage -- on a record boundary or
+    inside a quality line.  gzread answers that with 0 and Z_BUF_ERROR, not -1: the reader must report it instead of taking it
+    for the end of the input, and the records in front of the cut are handed out before the error (none is dropped)."""
+    import zlib
+    rnd = random.Random(9)
+    rec = [b"@r%d\n%s\n+\n%s\n" % (i, bytes(rnd.choice(b"ACGT") for _ in range(100)), b"I" * 100) for i in range(20000)]
+    head = b"".join(rec[:10000])
+    if where == "inside_quality":
+        head += rec[10000][:-40]                        # 61 of the 100 quality characters, no newline
+    co = zlib.compressobj(1, zlib.DEFLATED, 31)         # gzip container
+    blob = co.compress(head) + co.flush(zlib.Z_FULL_FLUSH)
+    path = str(tmp_path / "flushcut.fq.gz")
+    with open(path, "wb") as fh:
+        fh.write(blob)                                  # no trailer: the file ends at the flush point
+    rd = binding.ChunkReader(path, threads=threads, window_bytes=1 << 20)
+    got = 0
+    with pytest.raises(binding.SubreadCudaError):
+        while True:
+            n = rd.next(3000)[3]
+            if n == 0:
+                break
+            got += n
+    rd.close()
+    assert got <= 10000
+    # the intact file for comparison: all 20000, no error
+    full = str(tmp_path / "full.fq.gz")
+    with open(full, "wb") as fh:
+        fh.write(gzip.compress(b"".join(rec), compresslevel=1))
+    reads, _ = read_all(full, batch=3000, threads=threads, window_bytes=1 << 20)
+    assert len(reads) == 20000

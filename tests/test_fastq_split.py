@@ -197,6 +197,10 @@ def big_files():
     broken = recs[:4000] + [b"ACGT\n"] + recs[4000:]
     yield "broken_in_the_middle", b"".join(broken), 4000
     yield "short_read_ends_input_when_trimmed", b"".join(recs[:3000] + [b"@tiny\nACG\n+\nIII\n"] + recs[3000:]), None
+    # every quality line looks like a name line and every sequence line like a '+' line: a guessed cut lands on a quality
+    # line, and a piece that ends right behind a '+' line must not pass as complete (fixed records of 100 bases so that
+    # any cut guess that is off is off consistently)
+    yield "qualities_like_names_sequences_like_plus", b"".join(b"@n%05d\n+%s\n+\n@%s\n" % (i, dna(100), b"I" * 100) for i in range(20000)), None
 
 
 @pytest.mark.parametrize("threads", [2, 3, 8])
