@@ -110,7 +110,7 @@ typedef struct {
 	int32_t total_offsets;        /* gene_offset_t.total_offsets (subread.h:395-401) */
 	uint64_t device_bytes;        /* HBM held by this block */
 	uint32_t accelerators;        /* lookup accelerators derived at load time: 1 Bloom words, 2 bucket records,
-	                                 4 direct filter (dense tables), 8 unique-position bitmap */
+	                                 4 direct filter (dense tables) */
 	uint32_t _pad;
 } srcuda_index_desc;
 
@@ -128,6 +128,9 @@ typedef struct {
 	float ms_kernel_simple;  /* part of ms_kernel_vote spent in the one-thread-per-fragment tier (k_map_simple, k_map_simple_pe) */
 	uint32_t _pad;
 	uint64_t n_simple_punted;/* fragments that tier handed on to the warp kernel */
+	uint64_t n_gather_requests; /* random index fetches the one-thread-per-fragment tier issued that miss L2 by construction (bucket
+	                             * records, direct-filter words, direct_first entries, positions): one DRAM line each, the numerator
+	                             * of the line-rate ("HBM-gather") roofline.  The Bloom words (L2-resident) are not counted. */
 } srcuda_timing;
 
 /* ---- life cycle ------------------------------------------------------------------------ */
@@ -287,6 +290,23 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
                              srcuda_mapping_result *d_out_align, srcuda_subjunc_result *d_out_junc,
                              uint16_t *d_out_big_margin, uint16_t *d_out_verify);
 
+/* One chunk over several GPUs: the chunk-level driver the reference's run_maybe_threads(STEP_VOTING) is (core.c:3404-3456:
+ * one chunk handed to N workers that write disjoint slots of one bigtable).  The fragment range [0, n_frags) is cut into
+ * n_handles contiguous slices whose sizes differ by at most one (slice k = [k*base + min(k, extra), ...), SURVEY section
+ * 8e); one host thread per handle runs srcuda_vote_chunk on its slice, reading the caller's text/off/len in place and
+ * writing its own part of out_align (and out_junc, out_big_margin, out_verify).  No collective and no device-to-device
+ * traffic on the data path.  Every handle must hold the same index block (srcuda_index_load on one of them and
+ * srcuda_index_replicate to the others, or srcuda_index_load_all).  Returns the first failure; its message is on
+ * handles[0].  Per-GPU timings stay on the handles (srcuda_get_timing). */
+int srcuda_vote_chunk_multi(srcuda_handle *const *handles, int n_handles, const srcuda_params *params, const char *text,
+                            const uint64_t *off, const uint16_t *len, int64_t n_frags, int is_paired, int out_align_is_zero,
+                            srcuda_mapping_result *out_align, srcuda_subjunc_result *out_junc, uint16_t *out_big_margin,
+                            uint16_t *out_verify);
+
+/* Load one index block on handles[0] (srcuda_index_load) and replicate it to the other handles' GPUs with peer copies over
+ * NVLink (srcuda_index_replicate), all replicas at once: "the index is loaded once and replicated to every GPU". */
+int srcuda_index_load_all(srcuda_handle *const *handles, int n_handles, const char *index_prefix, int block_no);
+
 int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out);
 
 /* Debug/validation switch: route every fragment through the exact slow path (one thread per
@@ -297,12 +317,20 @@ int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out);
  *   SRCUDA_TIER_JUNC [1]       subjunc chunks in that tier
  *   SRCUDA_WARP_JUNC [1]       subjunc fragments in the warp kernel (0: scalar path)
  *   SRCUDA_ACCEL [auto]        lookup accelerators: 0 none, 1 Bloom words, 2 bucket records, 3 both, 4 direct filter
- *   SRCUDA_BATCH_FRAGS, SRCUDA_SCALAR_BLOCKS, SRCUDA_L2_PERSIST, SRCUDA_L2_FETCH, SRCUDA_UNIQ   tuning knobs */
+ *   SRCUDA_BATCH_FRAGS, SRCUDA_SCALAR_BLOCKS, SRCUDA_L2_PERSIST, SRCUDA_L2_FETCH   tuning knobs */
 int srcuda_set_force_slow_path(srcuda_handle *h, int on);
 
 /* Measured random 32-byte-sector gather bandwidth over `table_bytes` of HBM (GB/s): the
  * "HBM-gather roofline" denominator of SURVEY.md section 8(d). */
 int srcuda_measure_gather_bandwidth(srcuda_handle *h, uint64_t table_bytes, int iters, double *gbps_out);
+
+/* The lookup's memory roofline for a mix of accesses, measured without any compute: units of work per second when every unit
+ * makes n_small random 2-byte probes of a table of small_bytes that stays in L2 (the Bloom words' load and cache policy) and
+ * n_big random 32-byte fetches from a table of big_bytes (the bucket records' load: 64 bytes per DRAM miss).  With the counts
+ * of the running workload (lookups and gather requests per fragment) this is the fragment rate the memory system allows: the
+ * denominator of bench.py's gather fraction. */
+int srcuda_measure_lookup_roofline(srcuda_handle *h, uint64_t small_bytes, int n_small, uint64_t big_bytes, int n_big, int iters,
+                                   double *units_per_s);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,11 @@
  *        if has_junc: n_frags*mates*multi_best * subjunc_result_t (16 B) and
  *                     n_frags*mates * 27 * u16 big-margin record
  *   SRDUMP_VOTES=<path>     text dump of vote tables (debugging aid)
+ *   SRDUMP_TIMING=<path>    text, one line per chunk: the reference's OWN accumulated clocks (core.c:3553-3640: miltime()
+ *                           around gehash_load/gvindex_load and around run_maybe_threads(STEP_VOTING)) as they stand when
+ *                           the chunk's voting is over -- "chunk_end frags=<n> voting_s=<timecost_voting>
+ *                           load_index_s=<timecost_load_index>".  bench.py's reference arm reads the voting step's time
+ *                           from it; nothing of the reference is changed or re-timed.
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -35,6 +40,15 @@ int anti_supporting_read_scan(global_context_t *global_context)
 	static int (*real_fn)(global_context_t *) = NULL;
 	if (!real_fn) real_fn = (int (*)(global_context_t *))dlsym(RTLD_NEXT, "anti_supporting_read_scan");
 
+	const char *tpath = getenv("SRDUMP_TIMING");
+	if (tpath) {
+		FILE *tf = fopen(tpath, "a");
+		if (tf) {
+			fprintf(tf, "chunk_end frags=%llu voting_s=%.6f load_index_s=%.6f\n", (unsigned long long)global_context->processed_reads_in_chunk,
+			        global_context->timecost_voting, global_context->timecost_load_index);
+			fclose(tf);
+		}
+	}
 	const char *path = getenv("SRDUMP_BIGTABLE");
 	if (path) {
 		FILE *fp = fopen(path, "ab");

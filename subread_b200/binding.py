@@ -21,8 +21,8 @@ EXPORTS = [
     "srcuda_device_count", "srcuda_open", "srcuda_close", "srcuda_last_error", "srcuda_index_load",
     "srcuda_index_upload", "srcuda_index_replicate", "srcuda_index_export_ipc", "srcuda_index_import_ipc",
     "srcuda_index_describe", "srcuda_index_unload",
-    "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device",
-    "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth",
+    "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device", "srcuda_vote_chunk_multi", "srcuda_index_load_all",
+    "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth", "srcuda_measure_lookup_roofline",
     "srcuda_fastq_split", "srcuda_fastq_split_mt", "srcuda_reads_pack", "srcuda_reads_pack_mt",
     "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_skip", "srcuda_reader_error", "srcuda_reader_close",
 ]
@@ -53,6 +53,7 @@ class Timing(ctypes.Structure):
         ("n_overflow", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
         ("n_launches", ctypes.c_uint32), ("n_batches", ctypes.c_uint32),
         ("ms_kernel_simple", ctypes.c_float), ("_pad", ctypes.c_uint32), ("n_simple_punted", ctypes.c_uint64),
+        ("n_gather_requests", ctypes.c_uint64),
     ]
 
 
@@ -95,9 +96,12 @@ def load_library():
     L.srcuda_host_free.restype = None
     L.srcuda_vote_chunk.argtypes = [vp, ctypes.POINTER(VoteParams), vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     L.srcuda_vote_chunk_device.argtypes = [vp, ctypes.POINTER(VoteParams), vp, u64, vp, vp, i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.srcuda_vote_chunk_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(VoteParams), vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    L.srcuda_index_load_all.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
     L.srcuda_get_timing.argtypes = [vp, ctypes.POINTER(Timing)]
     L.srcuda_set_force_slow_path.argtypes = [vp, ctypes.c_int]
     L.srcuda_measure_gather_bandwidth.argtypes = [vp, u64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    L.srcuda_measure_lookup_roofline.argtypes = [vp, u64, ctypes.c_int, u64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.srcuda_fastq_split.argtypes = [vp, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, u64, i64, vp, vp, vp, vp, vp, vp,
                                      ctypes.POINTER(FastqBatch)]
     L.srcuda_fastq_split_mt.argtypes = [vp, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, u64, i64, vp, vp, vp, vp, vp, vp,
@@ -264,11 +268,76 @@ class Mapper:
     def set_force_slow_path(self, on: bool):
         self.lib.srcuda_set_force_slow_path(self.h, int(bool(on)))
 
+    def lookup_roofline(self, small_bytes: int, n_small: int, big_bytes: int, n_big: int, iters: int = 3) -> float:
+        """Units of work per second the memory system allows for n_small L2-resident probes + n_big DRAM gathers per unit."""
+        out = ctypes.c_double()
+        self._check(self.lib.srcuda_measure_lookup_roofline(self.h, int(small_bytes), int(n_small), int(big_bytes), int(n_big), iters, ctypes.byref(out)),
+                    "srcuda_measure_lookup_roofline")
+        return out.value
+
     def gather_bandwidth(self, table_bytes: int, iters: int = 3) -> float:
         out = ctypes.c_double()
         self._check(self.lib.srcuda_measure_gather_bandwidth(self.h, int(table_bytes), iters, ctypes.byref(out)),
                     "srcuda_measure_gather_bandwidth")
         return out.value
+
+
+class MultiMapper:
+    """Several GPUs behind one chunk call (srcuda_vote_chunk_multi): one handle per entry of ``devices`` (a device may be
+    listed twice -- two handles with their own streams and their own copy of the index -- which is how the driver is
+    exercised on a one-GPU box), the index loaded once and replicated to the others over NVLink, every chunk cut into
+    contiguous fragment slices written into one host bigtable (run_maybe_threads, core.c:3404-3456)."""
+
+    def __init__(self, devices):
+        self.mappers = [Mapper(d) for d in devices]
+        self.lib = self.mappers[0].lib
+        self._arr = (ctypes.c_void_p * len(self.mappers))(*[m.h for m in self.mappers])
+
+    def close(self):
+        for m in self.mappers:
+            m.close()
+        self.mappers = []
+
+    def index_load(self, prefix: str, block: int = 0):
+        rc = self.lib.srcuda_index_load_all(self._arr, len(self.mappers), str(prefix).encode(), block)
+        self.mappers[0]._check(rc, "srcuda_index_load_all")
+
+    def index_replicate(self):
+        """The block resident on the first handle -> every other handle (peer copies)."""
+        for m in self.mappers[1:]:
+            m.index_replicate_from(self.mappers[0])
+
+    def vote_chunk(self, chunk, params: VoteParams, out_align=None, want_verify=False, junc_state=None):
+        """Same contract as Mapper.vote_chunk, the chunk spread over all handles."""
+        from .layout import SUBJUNC_RESULT
+        mb = params.multi_best_reads
+        n = chunk.n_frags * chunk.mates * mb
+        is_zero = out_align is None
+        junc = bm = None
+        if params.do_breakpoint_detection:
+            if junc_state is None:
+                junc_state = {}
+            if "junc" not in junc_state:
+                junc_state["junc"] = np.zeros(n, dtype=SUBJUNC_RESULT)
+                junc_state["big_margin"] = np.zeros(chunk.n_frags * chunk.mates * 27, dtype=np.uint16)
+            junc, bm = junc_state["junc"], junc_state["big_margin"]
+        if out_align is None:
+            out_align = np.zeros(n, dtype=MAPPING_RESULT)
+        out_align = out_align.reshape(-1)
+        assert out_align.flags["C_CONTIGUOUS"] and out_align.shape[0] == n and out_align.dtype == MAPPING_RESULT
+        verify = np.zeros(n, dtype=np.uint16) if want_verify else None
+        text = np.ascontiguousarray(chunk.text, dtype=np.uint8)
+        off = np.ascontiguousarray(chunk.off, dtype=np.uint64)
+        ln = np.ascontiguousarray(chunk.len, dtype=np.uint16)
+        if text.shape[0] == 0:
+            text = np.zeros(1, np.uint8)
+        rc = self.lib.srcuda_vote_chunk_multi(self._arr, len(self.mappers), ctypes.byref(params), _ptr(text), _ptr(off), _ptr(ln), chunk.n_frags,
+                                              int(chunk.is_paired), int(is_zero), _ptr(out_align), _ptr(junc), _ptr(bm), _ptr(verify))
+        self.mappers[0]._check(rc, "srcuda_vote_chunk_multi")
+        return out_align.reshape(chunk.n_frags, chunk.mates, mb), verify
+
+    def timings(self):
+        return [m.timing() for m in self.mappers]
 
 
 def fastq_split(buf: np.ndarray, at_eof=True, trim_5=0, trim_3=0, max_reads=None, base_offset=0, want_names=False, threads=1,

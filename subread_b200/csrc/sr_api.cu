@@ -23,6 +23,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace sr {
@@ -162,38 +163,11 @@ __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *key
 				w[3] = v[0]; w[4] = v[1]; w[5] = v[2]; w[6] = v[3]; w[7] = v[4];
 			} else if (n <= (uint32_t)sr::kRecordKeys) {
 				w[1] = lo;
-				for (uint32_t i = 0; i < n; i++) w[2 + (i >> 1)] |= (uint32_t)(uint16_t)keys[lo + i] << ((i & 1) * 16);
+				for (uint32_t i = 0; i < (uint32_t)sr::kRecordKeys; i++)       // unused slots: the no-key, above every key (packed compares in simple_probe)
+					w[2 + (i >> 1)] |= (i < n ? (uint32_t)(uint16_t)keys[lo + i] : kRecordNoKey) << ((i & 1) * 16);
 			}
 			records[2 * (size_t)b] = make_uint4(w[0], w[1], w[2], w[3]);
 			records[2 * (size_t)b + 1] = make_uint4(w[4], w[5], w[6], w[7]);
-		}
-	}
-}
-
-// Third accelerator, one thread per bucket: the "unique position" bitmap.  Bit v - start_base_offset is set when the
-// table holds exactly one item for the key of the 16-mer that the resident genome array shows at position v, and that
-// item is v.  Then gehash_go_X's lookup of that 16-mer returns the single position v (sorted-hashtable.c:947-981), which
-// the tier-0 kernel may conclude from the genome (25 MB for 100 Mbp, L2 resident) without touching the bucket.  The bit
-// is only set after the key rebuilt from (bucket, key16) has been compared with the genome's 16-mer, so it never says
-// more than the table itself.
-__global__ void k_build_uniq(const sr::DevIndex ix, uint32_t *bits)
-{
-	const uint32_t nb = ix.buckets_number;
-	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
-		const uint32_t lo = ix.bucket_start[b], n = ix.bucket_start[b + 1] - lo;
-		for (uint32_t i = 0; i < n; i++) {
-			const int16_t k = ix.keys[lo + i];
-			if ((i > 0 && ix.keys[lo + i - 1] == k) || (i + 1 < n && ix.keys[lo + i + 1] == k)) continue;
-			const uint32_t v = ix.vals[lo + i];
-			if (v < ix.start_point || v - ix.start_point > ix.length - 16u || ix.length < 16u) continue;
-			const uint32_t p = v - ix.start_base_offset;
-			if (p >= ix.uniq_n) continue;
-			const uint32_t key = (uint32_t)(uint16_t)k * nb + b;
-			if (key / nb != (uint32_t)(uint16_t)k) continue;                  // (only a tiny table can wrap)
-			const uint32_t g = __funnelshift_r(ix.genome[p >> 4], ix.genome[(p >> 4) + 1], (p & 15u) * 2u);
-			uint32_t r = __brev(g);
-			r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);
-			if (r == key) atomicOr(bits + (p >> 5), 1u << (p & 31u));
 		}
 	}
 }
@@ -286,6 +260,41 @@ __global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_t
 	if (acc == 0x12345678u) *sink = acc;
 }
 
+// The lookup's memory roofline for a given mix (no compute): per unit of work n_small random 2-byte probes of a small table
+// that stays in L2 (the Bloom words: same load, same evict-last policy) and n_big random 32-byte records of a big table
+// (the bucket records / direct-filter words / positions: the lookup's own 64-byte-fetch load), six and four in flight.
+__global__ void k_mix_probe(const bloom_t *small_t, uint64_t small_n, const uint4 *big_t, uint64_t big_n, int n_small, int n_big, int units_per_thread,
+                            uint32_t seed, uint32_t *sink)
+{
+	const uint64_t pol = policy_evict_last();
+	uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + seed;
+	uint32_t acc = 0;
+	for (int r = 0; r < units_per_thread; r++) {
+		for (int i = 0; i < n_small; i += 6) {
+			uint32_t v[6];
+#pragma unroll
+			for (int u = 0; u < 6; u++) {
+				x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 29;
+				v[u] = ld_bloom(small_t + x % small_n, pol);
+			}
+#pragma unroll
+			for (int u = 0; u < 6; u++) acc += v[u];
+		}
+		for (int i = 0; i < n_big; i += 4) {
+			uint32_t w[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 29;
+				const Record8 rec = ld_record(big_t, (uint32_t)(x % big_n));
+				w[u] = rec.w[0] ^ rec.w[7];
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) acc += w[u];
+		}
+	}
+	if (acc == 0x12345678u) *sink = acc;
+}
+
 }  // namespace sr
 
 // ------------------------------------------------------------------------------------ handle
@@ -324,10 +333,8 @@ struct srcuda_handle {
 	sr::DevIndex ix{};
 	srcuda_index_desc desc{};
 	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
-	void *d_records = nullptr, *d_bloom = nullptr, *d_uniq = nullptr, *d_direct = nullptr, *d_direct_first = nullptr;
+	void *d_records = nullptr, *d_bloom = nullptr, *d_direct = nullptr, *d_direct_first = nullptr;
 	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both, 4 direct filter (SRCUDA_ACCEL)
-	bool use_uniq = false;         // SRCUDA_UNIQ=1 builds the unique-position bitmap: halves the DRAM traffic of tier 0 but costs more
-	                               // instructions than it saves while the kernel is issue-bound (profiles/), so it is off by default
 	bool l2_persist = true;        // keep the Bloom words resident in L2 (SRCUDA_L2_PERSIST=0 turns it off)
 	size_t l2_persist_max = 0, l2_window_max = 0;
 	const void *l2_policy_for = nullptr;   // Bloom array the streams' access-policy window currently covers
@@ -392,8 +399,8 @@ int ensure(srcuda_handle *h, DeviceBuf &b, size_t bytes)
 void free_index(srcuda_handle *h)
 {
 	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr);
-	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_uniq); cudaFree(h->d_direct); cudaFree(h->d_direct_first);
-	h->d_uniq = h->d_direct = h->d_direct_first = nullptr;
+	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_direct); cudaFree(h->d_direct_first);
+	h->d_direct = h->d_direct_first = nullptr;
 	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = h->d_records = h->d_bloom = nullptr;
 	h->has_index = false;
 	h->l2_policy_for = nullptr;
@@ -454,8 +461,6 @@ int build_accelerators(srcuda_handle *h)
 	h->ix.records = nullptr;
 	h->ix.direct = nullptr;
 	h->ix.direct_first = nullptr;
-	h->ix.uniq_bits = nullptr;
-	h->ix.uniq_n = 0;
 	h->desc.accelerators = 0;
 	if (mode & 4) return build_direct(h);
 	if (mode & 1) CU(h, cudaMalloc(&h->d_bloom, sizeof(sr::bloom_t) * (size_t)nb));
@@ -469,23 +474,6 @@ int build_accelerators(srcuda_handle *h)
 	h->ix.records = h->d_records;
 	h->desc.device_bytes += (mode & 1 ? (uint64_t)sizeof(sr::bloom_t) * nb : 0) + (mode & 2 ? 32ull * nb : 0);
 	h->desc.accelerators = (uint32_t)(mode & 3);
-	h->ix.uniq_bits = nullptr;
-	h->ix.uniq_n = 0;
-	if ((mode & 3) == 3 && h->use_uniq) {
-		const uint64_t n_bits = (uint64_t)h->ix.length + (h->ix.start_point - h->ix.start_base_offset);
-		if (n_bits < 0xffffffffull && (n_bits >> 4) + 2 <= h->genome_words) {
-			const size_t words = (size_t)((n_bits + 31) / 32) + 4;
-			CU(h, cudaMalloc(&h->d_uniq, sizeof(uint32_t) * words));
-			CU(h, cudaMemset(h->d_uniq, 0, sizeof(uint32_t) * words));
-			h->ix.uniq_n = (uint32_t)n_bits;
-			k_build_uniq<<<h->sm_count * 8, 256>>>(h->ix, (uint32_t *)h->d_uniq);
-			CU(h, cudaGetLastError());
-			CU(h, cudaDeviceSynchronize());
-			h->ix.uniq_bits = (const uint32_t *)h->d_uniq;
-			h->desc.device_bytes += sizeof(uint32_t) * words;
-			h->desc.accelerators |= 8;
-		}
-	}
 	return 0;
 }
 
@@ -624,7 +612,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		}                                                                                                                            \
 		sr::k_map_simple<G, U><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off,    \
 		                                                              a.len, a.n_frags, max_len, clusters, a.out, q0,              \
-		                                                              bs.counters + 2, a.bad_reads);                               \
+		                                                              bs.counters + 2, a.bad_reads, bs.counters + 3);                               \
 	} while (0)
 #define SR_LAUNCH_SIMPLE_R(G, U)                                                                                                     \
 	do {                                                                                                                             \
@@ -635,7 +623,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		sr::k_map_simple<G, U, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,              \
 		                                                                           a.text_bytes, a.off, a.len, a.n_frags, max_len,   \
 		                                                                           clusters, a.out, q0, bs.counters + 2,            \
-		                                                                           a.bad_reads);                                    \
+		                                                                           a.bad_reads, bs.counters + 3);                                    \
 	} while (0)
 #define SR_LAUNCH_SIMPLE_J(G, U)                                                                                                     \
 	do {                                                                                                                             \
@@ -646,7 +634,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		}                                                                                                                            \
 		sr::k_map_simple<G, U, true><<<(unsigned)blocks, threads, jsmem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes,    \
 		                                                                     a.off, a.len, a.n_frags, max_len, clusters, a.out, q0, \
-		                                                                     bs.counters + 2, a.bad_reads, a.junc, a.big_margin);  \
+		                                                                     bs.counters + 2, a.bad_reads, bs.counters + 3, a.junc, a.big_margin);  \
 	} while (0)
 #define SR_LAUNCH_SIMPLE(G)                                                                                                          \
 	do {                                                                                                                             \
@@ -657,7 +645,6 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			if (h->ix.direct) SR_LAUNCH_SIMPLE_R(G, 2);                                                                              \
 			else SR_LAUNCH_SIMPLE_R(G, 0);                                                                                           \
 		} else if (h->ix.direct) SR_LAUNCH_SIMPLE_U(G, 2);                                                                           \
-		else if (h->ix.uniq_bits) SR_LAUNCH_SIMPLE_U(G, 1);                                                                          \
 		else SR_LAUNCH_SIMPLE_U(G, 0);                                                                                               \
 	} while (0)
 		switch (h->ix.index_gap) {
@@ -692,7 +679,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		}                                                                                                                            \
 		sr::k_map_simple_pe<G, U><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, \
 		                                                                 a.len, a.n_frags, max_len, clusters, a.out, q0,           \
-		                                                                 bs.counters + 2, a.bad_reads);                            \
+		                                                                 bs.counters + 2, a.bad_reads, bs.counters + 3);                            \
 	} while (0)
 #define SR_LAUNCH_PE_R(G, U)                                                                                                         \
 	do {                                                                                                                             \
@@ -703,7 +690,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		sr::k_map_simple_pe<G, U, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,           \
 		                                                                              a.text_bytes, a.off, a.len, a.n_frags,        \
 		                                                                              max_len, clusters, a.out, q0,                 \
-		                                                                              bs.counters + 2, a.bad_reads);                \
+		                                                                              bs.counters + 2, a.bad_reads, bs.counters + 3);                \
 	} while (0)
 #define SR_LAUNCH_PE_J(G, U)                                                                                                         \
 	do {                                                                                                                             \
@@ -713,7 +700,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		}                                                                                                                            \
 		sr::k_map_simple_pe<G, U, true><<<(unsigned)blocks, threads, jsmem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes,  \
 		                                                                        a.off, a.len, a.n_frags, max_len, clusters, a.out,  \
-		                                                                        q0, bs.counters + 2, a.bad_reads, a.junc,           \
+		                                                                        q0, bs.counters + 2, a.bad_reads, bs.counters + 3, a.junc,           \
 		                                                                        a.big_margin);                                      \
 	} while (0)
 #define SR_LAUNCH_PE(G)                                                                                                              \
@@ -823,8 +810,6 @@ int srcuda_open(int device, srcuda_handle **out)
 	h->sm_count = prop.multiProcessorCount;
 	h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
 	h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-	const char *uq = getenv("SRCUDA_UNIQ");
-	if (uq) h->use_uniq = uq[0] == '1';
 	const char *lp = getenv("SRCUDA_L2_PERSIST");
 	if (lp && lp[0] == '0') h->l2_persist = false;
 	if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SRCUDA_ERR_CUDA, "cudaSetDevice(%d) failed", device); }
@@ -1105,6 +1090,7 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[3]));
 	h->timing.ms_kernel_simple = ms;
 	h->timing.n_simple_punted = counters[2];
+	h->timing.n_gather_requests = counters[3];
 	CU(h, cudaEventElapsedTime(&ms, h->events[1], h->events[2]));
 	h->timing.ms_kernel_overflow = ms;
 	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[2]));
@@ -1257,11 +1243,88 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		h->timing.ms_kernel_overflow += ms;
 		const uint32_t *c = h->set[bi % kSets].h_counters + 4 * (bi / kSets);
 		h->timing.n_simple_punted += c[2];
+		h->timing.n_gather_requests += c[3];
 		h->timing.n_overflow += (h->force_slow || (cfg.do_junctions && (!h->use_warp_junc || out_verify))) ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
 		bad += c[1];
 	}
 	h->timing.n_batches = (uint32_t)n_batches;
 	if (bad) return fail(h, SRCUDA_ERR_ARG, "%llu reads have (off,len) outside the text buffer", (unsigned long long)bad);
+	return SRCUDA_OK;
+}
+
+int srcuda_vote_chunk_multi(srcuda_handle *const *handles, int n_handles, const srcuda_params *params, const char *text,
+                            const uint64_t *off, const uint16_t *len, int64_t n_frags, int is_paired, int out_align_is_zero,
+                            srcuda_mapping_result *out_align, srcuda_subjunc_result *out_junc, uint16_t *out_big_margin,
+                            uint16_t *out_verify)
+{
+	if (!handles || n_handles < 1 || !handles[0]) return fail(nullptr, SRCUDA_ERR_ARG, "srcuda_vote_chunk_multi: no handle");
+	srcuda_handle *h0 = handles[0];
+	for (int k = 0; k < n_handles; k++) {
+		if (!handles[k]) return fail(h0, SRCUDA_ERR_ARG, "srcuda_vote_chunk_multi: handle %d is NULL", k);
+		for (int j = 0; j < k; j++)
+			if (handles[j] == handles[k]) return fail(h0, SRCUDA_ERR_ARG, "srcuda_vote_chunk_multi: handle %d is listed twice", k);
+		if (!handles[k]->has_index) return fail(h0, SRCUDA_ERR_NO_INDEX, "handle %d holds no index block", k);
+		const srcuda_index_desc &a = h0->desc, &b = handles[k]->desc;
+		if (a.n_items != b.n_items || a.buckets_number != b.buckets_number || a.length != b.length || a.start_point != b.start_point ||
+		    a.index_gap != b.index_gap)
+			return fail(h0, SRCUDA_ERR_ARG, "handle %d holds a different index block than handle 0", k);
+	}
+	if (!params || !text || !off || !len || !out_align || n_frags < 0) return fail(h0, SRCUDA_ERR_ARG, "srcuda_vote_chunk_multi: null argument");
+	if (n_handles == 1)
+		return srcuda_vote_chunk(h0, params, text, off, len, n_frags, is_paired, out_align_is_zero, out_align, out_junc, out_big_margin, out_verify);
+	const int mates = is_paired ? 2 : 1;
+	const int mb = params->multi_best_reads;
+	if (mb < 1 || mb > sr::kMaxBest) return fail(h0, SRCUDA_ERR_ARG, "multi_best_reads %d not in 1..%d", mb, sr::kMaxBest);
+	const int64_t base = n_frags / n_handles, extra = n_frags % n_handles;
+	std::vector<int> rcs((size_t)n_handles, SRCUDA_OK);
+	auto work = [&](int k) {
+		const int64_t f0 = k * base + std::min<int64_t>(k, extra), nf = base + (k < extra ? 1 : 0);
+		const int64_t r0 = f0 * mates;
+		rcs[(size_t)k] = srcuda_vote_chunk(handles[k], params, text, off + r0, len + r0, nf, is_paired, out_align_is_zero, out_align + (size_t)r0 * mb,
+		                                   out_junc ? out_junc + (size_t)r0 * mb : nullptr,
+		                                   out_big_margin ? out_big_margin + (size_t)r0 * sr::kBigMarginU16 : nullptr,
+		                                   out_verify ? out_verify + (size_t)r0 * mb : nullptr);
+	};
+	{
+		std::vector<std::thread> th;
+		th.reserve((size_t)n_handles);
+		for (int k = 1; k < n_handles; k++) {
+			bool started = false;
+			try { th.emplace_back(work, k); started = true; } catch (...) {}
+			if (!started) work(k);                       // no thread to be had: the slice is mapped from this one
+		}
+		work(0);
+		for (auto &t : th) t.join();
+	}
+	for (int k = 0; k < n_handles; k++)
+		if (rcs[(size_t)k]) {
+			if (k > 0) return fail(h0, rcs[(size_t)k], "GPU %d (handle %d): %s", handles[k]->device, k, srcuda_last_error(handles[k]));
+			return rcs[0];
+		}
+	return SRCUDA_OK;
+}
+
+int srcuda_index_load_all(srcuda_handle *const *handles, int n_handles, const char *index_prefix, int block_no)
+{
+	if (!handles || n_handles < 1 || !handles[0]) return fail(nullptr, SRCUDA_ERR_ARG, "srcuda_index_load_all: no handle");
+	srcuda_handle *h0 = handles[0];
+	for (int k = 1; k < n_handles; k++)
+		if (!handles[k]) return fail(h0, SRCUDA_ERR_ARG, "srcuda_index_load_all: handle %d is NULL", k);
+	int rc = srcuda_index_load(h0, index_prefix, block_no);
+	if (rc) return rc;
+	std::vector<int> rcs((size_t)n_handles, SRCUDA_OK);
+	{
+		std::vector<std::thread> th;
+		for (int k = 1; k < n_handles; k++) {
+			auto one = [&, k] { rcs[(size_t)k] = srcuda_index_replicate(handles[k], h0); };
+			bool started = false;
+			try { th.emplace_back(one); started = true; } catch (...) {}
+			if (!started) one();
+		}
+		for (auto &t : th) t.join();
+	}
+	for (int k = 1; k < n_handles; k++)
+		if (rcs[(size_t)k]) return fail(h0, rcs[(size_t)k], "replicating the index to GPU %d failed: %s", handles[k]->device, srcuda_last_error(handles[k]));
 	return SRCUDA_OK;
 }
 
@@ -1293,6 +1356,45 @@ int srcuda_measure_gather_bandwidth(srcuda_handle *h, uint64_t table_bytes, int 
 	cudaEventDestroy(e1);
 	cudaFree(table);
 	*gbps_out = best;
+	return SRCUDA_OK;
+}
+
+int srcuda_measure_lookup_roofline(srcuda_handle *h, uint64_t small_bytes, int n_small, uint64_t big_bytes, int n_big, int iters, double *units_per_s)
+{
+	if (!h || !units_per_s || n_small < 0 || n_big < 0 || n_small + n_big < 1 || (n_small && small_bytes < 4096) || (n_big && big_bytes < (1u << 20)))
+		return fail(h, SRCUDA_ERR_ARG, "srcuda_measure_lookup_roofline: bad argument");
+	CU(h, cudaSetDevice(h->device));
+	void *small_t = nullptr, *big_t = nullptr;
+	if (n_small) { CU(h, cudaMalloc(&small_t, small_bytes)); CU(h, cudaMemset(small_t, 1, small_bytes)); }
+	if (n_big) {
+		const uint64_t capped = std::min<uint64_t>(big_bytes, 0xffffffffull * 32ull);        // records are addressed by a 32-bit number
+		big_bytes = capped;
+		cudaError_t e = cudaMalloc(&big_t, big_bytes);
+		if (e != cudaSuccess) { cudaFree(small_t); return fail(h, SRCUDA_ERR_NOMEM, "cudaMalloc of the %.1f GB probe table failed", big_bytes / 1e9); }
+		CU(h, cudaMemset(big_t, 1, big_bytes));
+	}
+	if (!h->d_sink) CU(h, cudaMalloc((void **)&h->d_sink, 4));
+	const int threads = 256, blocks = h->sm_count * 8, per_thread = std::max(1, 1024 / (n_small + n_big));
+	cudaEvent_t e0, e1;
+	CU(h, cudaEventCreate(&e0));
+	CU(h, cudaEventCreate(&e1));
+	double best = 0;
+	for (int it = 0; it < std::max(1, iters) + 1; it++) {
+		CU(h, cudaEventRecord(e0, 0));
+		sr::k_mix_probe<<<blocks, threads>>>((const sr::bloom_t *)small_t, small_bytes / sizeof(sr::bloom_t), (const uint4 *)big_t, big_bytes / 32, n_small, n_big,
+		                                     per_thread, 99u + it, h->d_sink);
+		CU(h, cudaEventRecord(e1, 0));
+		CU(h, cudaEventSynchronize(e1));
+		float ms = 0;
+		CU(h, cudaEventElapsedTime(&ms, e0, e1));
+		const double rate = (double)blocks * threads * per_thread / (ms * 1e-3);
+		if (it > 0 && rate > best) best = rate;          // first iteration is the warm-up
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(small_t);
+	cudaFree(big_t);
+	*units_per_s = best;
 	return SRCUDA_OK;
 }
 

@@ -59,8 +59,6 @@ struct DevIndex {
 	// exact: a filter without false negatives and a re-packed copy of small buckets.
 	const bloom_t *bloom;          // per bucket: bloom_bits(key16) set for every key16 in the bucket; null = off
 	const void *records;           // per bucket 32 B (two uint4): see below; null = off
-	const uint32_t *uniq_bits;     // bit (v - start_base_offset) set: looking up the 16-mer at genome position v returns {v} and nothing else; null = off
-	uint32_t uniq_n;               // bits in uniq_bits
 	// Dense tables (a human-sized index holds ~64 items per bucket): the direct filter, see below; null = off
 	const uint32_t *direct;        // one 16-byte unit (four words) per kDirectKeys consecutive 32-bit keys
 	const uint64_t *direct_first;  // by rank among the present keys: {position, 1} for a key with one position, else

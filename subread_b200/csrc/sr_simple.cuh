@@ -48,6 +48,10 @@
 #ifndef SR_SIMPLE_HIT_INLINE
 #define SR_SIMPLE_HIT_INLINE __forceinline__   // the general-path hit: inlined (a real call costs spills around it; A/B switch)
 #endif
+#ifndef SR_SIMPLE_REORDER
+#define SR_SIMPLE_REORDER 0    // sparse table: every lane takes its fuller strand first.  A/B switch, off: 17 % fewer warp instructions but
+                               // 1.39 instead of 1.55 G reads/s -- the kernel runs at the memory system's request rate, profiles/r02_tier0_experiments.md
+#endif
 #ifndef SR_SIMPLE_SMEM_OUT
 #define SR_SIMPLE_SMEM_OUT 0   // compose the warp's bigtable slice in shared memory and store whole sectors (A/B switch)
 #endif
@@ -56,18 +60,19 @@ namespace sr {
 
 constexpr int kSimpleThreads = 128;                      // fragments (threads) per block
 constexpr int kSimpleMaxLen = 256;                       // longer reads go to the warp kernel
-constexpr int kSimpleClusters = 8;                       // distinct kv per strand pass (sparse table)
+constexpr int kSimpleClusters = 9;                       // distinct kv of both strand passes together (sparse table: the two lists share the pool)
 constexpr int kSimpleClustersDense = 16;                 // ... on a dense table, where a quarter of all 16-mers has some position
 constexpr int kSimpleClusterWords = 4;                   // shared-memory words per cluster
 
 // Shared-memory plan of one block (host and device agree through these functions): the packed reads of the 128
 // threads, then one private area per warp that first stages the warp's text and later holds its vote clusters.
 SR_HD int simple_words(int max_len) { return ((max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen) + 15) / 16 + 1; }
+SR_HD int simple_cluster_bytes(int clusters) { return clusters * kSimpleClusterWords * 32 * 4; }
 SR_HD int simple_warp_bytes(int max_len, int clusters = kSimpleClusters)
 {
 	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
 	int stage = 32 * (((ml + 3) & ~3) + 4) + 32;                             // text of 32 reads (+ alignment slack)
-	const int clus = clusters * kSimpleClusterWords * 32 * 4;         // the vote clusters reuse the staging area
+	const int clus = simple_cluster_bytes(clusters);                         // the vote clusters reuse the staging area
 	if (stage < clus) stage = clus;
 	const int outb = 16 * kMaxBest * kResultWords * 4;                       // ... and later half a warp's bigtable slots
 	if (stage < outb) stage = outb;
@@ -300,14 +305,14 @@ __device__ __forceinline__ uint32_t simple_key_at(const uint32_t *pk, int o, int
 // What one survivor's bucket record says about key16 = k16.
 //   kind 0: the key is absent   1: exactly one position (*value)   2: anything else -- several positions, or a bucket
 //   whose record cannot answer -- which the general path sorts out.
-__device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r, int k16, uint32_t *value)
+__device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r, int k16, uint32_t *value, uint32_t &n_gather)
 {
 	const int n = (int)(r.w[0] & 0xffffu);
+	// The key16 fields of a record are sorted and the unused ones hold kRecordNoKey (0x7fff, above every key: records are only
+	// built for tables whose key16 stays below it), so the equal-key run [lt, le) follows from two packed compares per
+	// word: with a, b < 0x8000 bit 15 of (a | 0x8000) - b is clear exactly when a < b, and no borrow crosses the halves.
+	const uint32_t M = 0x80008000u, kk = (uint32_t)k16 * 0x10001u, kk1 = kk + 0x10001u;
 	if (n <= kInlineItems) {
-		// The five key16 fields are sorted and the unused ones hold kRecordNoKey (0x7fff, above every key: records are only
-		// built for tables whose key16 stays below it), so the equal-key run [lt, le) follows from two packed compares per
-		// word: with a, b < 0x8000 bit 15 of (a | 0x8000) - b is clear exactly when a < b, and no borrow crosses the halves.
-		const uint32_t M = 0x80008000u, kk = (uint32_t)k16 * 0x10001u, kk1 = kk + 0x10001u;
 		const uint32_t a0 = (r.w[0] | 0x0000ffffu) & 0xffff7fffu, a1 = r.w[1], a2 = r.w[2];   // (the count's half becomes a no-key)
 		const int lt = __popc(~((a0 | M) - kk) & M) + __popc(~((a1 | M) - kk) & M) + __popc(~((a2 | M) - kk) & M);
 		const int le = __popc(~((a0 | M) - kk1) & M) + __popc(~((a1 | M) - kk1) & M) + __popc(~((a2 | M) - kk1) & M);
@@ -317,28 +322,183 @@ __device__ __forceinline__ int simple_probe(const DevIndex &ix, const Record8 &r
 	if (n <= kRecordKeys) {                                        // 6..12 items: the record lists the keys, the positions stay in vals[]
 		int lt = 0, le = 0;
 #pragma unroll
-		for (int i = 0; i < kRecordKeys; i++) {
-			const int k = (int)(int16_t)(r.w[2 + (i >> 1)] >> ((i & 1) * 16));
-			lt += (i < n && k < k16) ? 1 : 0;
-			le += (i < n && k <= k16) ? 1 : 0;
+		for (int w = 2; w < 8; w++) {
+			lt += __popc(~((r.w[w] | M) - kk) & M);
+			le += __popc(~((r.w[w] | M) - kk1) & M);
 		}
-		if (le - lt == 1) *value = ld_gather(ix.vals + r.w[1] + lt);
+		if (le - lt == 1) { *value = ld_gather(ix.vals + r.w[1] + lt); n_gather++; }
 		return min(le - lt, 2);
 	}
 	return 2;
 }
 
+// The general path of a sparse table's pass: the lookups of `defer` (bits = lookups base + i), in schedule order, every
+// position in the reference's visit order, through the cluster list.  Returns false when the pass is not separable.
+template <int GAP, bool RCKEYS>
+__device__ __forceinline__ bool simple_general(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int step, int rc_len, int base,
+                                               unsigned defer, SimpleClusters &C, uint32_t low, uint32_t high, uint32_t &n_gather)
+{
+	const uint32_t nb = ix.buckets_number;
+	const uint64_t magic = ix.buckets_magic;
+	const int tol = cfg.indel_tolerance;
+	const uint4 *records = reinterpret_cast<const uint4 *>(ix.records);
+	while (defer) {
+		const int i = __ffs(defer) - 1;
+		defer &= defer - 1;
+		const int l = base + i;
+		int sub;
+		const int o = simple_offset<GAP>(l, step, &sub);
+		const uint32_t key = simple_key_at<RCKEYS>(pk, o, rc_len);
+		const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
+		const uint32_t b = key - q * nb;
+		const int k16 = (int)(int16_t)q;
+		bool in_arrays = true;
+		if (records) {
+			const Record8 r = ld_record(records, b);
+			n_gather++;
+			const int n = (int)(r.w[0] & 0xffffu);
+			if (n <= kInlineItems) {
+				in_arrays = false;
+				const int k0 = (int)(int16_t)(r.w[0] >> 16), k1 = (int)(int16_t)(r.w[1] & 0xffffu), k2 = (int)(int16_t)(r.w[1] >> 16),
+				          k3 = (int)(int16_t)(r.w[2] & 0xffffu), k4 = (int)(int16_t)(r.w[2] >> 16);
+				const int lt = (n > 0 && k0 < k16) + (n > 1 && k1 < k16) + (n > 2 && k2 < k16) + (n > 3 && k3 < k16) + (n > 4 && k4 < k16);
+				const int le = (n > 0 && k0 <= k16) + (n > 1 && k1 <= k16) + (n > 2 && k2 <= k16) + (n > 3 && k3 <= k16) + (n > 4 && k4 <= k16);
+				if (le > lt) {
+					// where the reference's (imin+imax)/2 search lands inside the run (sorted-hashtable.c:960-981)
+					int imin = 0, imax = n - 1, at;
+					for (;;) {
+						at = (imin + imax) >> 1;
+						if (at >= le) imax = at - 1;
+						else if (at < lt) imin = at + 1;
+						else break;
+					}
+					const int h = le - lt, nfwd = le - at;       // landing .. end of run, then landing-1 .. start (:1109-1119)
+					for (int u = 0; u < h; u++) {
+						const int idx = u < nfwd ? at + u : at - 1 - (u - nfwd);
+						const uint32_t v = idx == 0 ? r.w[3] : (idx == 1 ? r.w[4] : (idx == 2 ? r.w[5] : (idx == 3 ? r.w[6] : r.w[7])));
+						if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) return false;
+					}
+				}
+			}
+		}
+		if (in_arrays) {                                         // a bucket with more than 5 items, or no records at all
+			const uint32_t lo = ld_gather(ix.bucket_start + b);
+			const int items = (int)(ld_gather(ix.bucket_start + b + 1) - lo);
+			n_gather++;
+			if (items <= 0) continue;
+			const int16_t *kp = ix.keys + lo;
+			int imin = 0, imax = items - 1, at;
+			bool found = false;
+			n_gather++;
+			for (;;) {                                           // sorted-hashtable.c:960-981
+				at = (imin + imax) >> 1;
+				const int kk = (int)__ldg(kp + at);
+				if (kk > k16) imax = at - 1;
+				else if (kk < k16) imin = at + 1;
+				else { found = true; break; }
+				if (imax < imin) break;
+			}
+			if (!found) continue;
+			int e = at + 1, st = at;
+			while (e < items && (int)__ldg(kp + e) == k16) e++;
+			while (st > 0 && (int)__ldg(kp + st - 1) == k16) st--;
+			const int h = e - st, nfwd = e - at;
+			if (h > C.cap) return false;                         // cannot stay separable
+			for (int u = 0; u < h; u++) {
+				const int idx = u < nfwd ? at + u : at - 1 - (u - nfwd);
+				const uint32_t v = ld_gather(ix.vals + lo + idx);
+				n_gather++;
+				if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) return false;
+			}
+		}
+	}
+	return true;
+}
+
+// The filter of one batch of a strand pass: lookups base .. base + n_sub * GAP - 1 (whole subreads s_base .. s_base + n_sub - 1)
+// of the read packed at pk.  Returns the survivors as a bit mask (bit i = lookup base + i).  All Bloom words (sparse table) or
+// direct-filter words (dense table) of a group of six lookups are requested before any is tested -- memory-level
+// parallelism, no branch between the loads.  Without a filter every lookup survives.
+template <int GAP, int MODE, bool RCKEYS>
+__device__ __forceinline__ unsigned simple_filter(const DevIndex &ix, const uint32_t *pk, int s_base, int n_sub, int step, int rc_len,
+                                                  uint32_t &n_gather)
+{
+	constexpr bool DIRECT = MODE == 2;
+	constexpr int kGroup = GAP == 3 ? 2 : (GAP == 2 ? 3 : 6);     // subreads per group of 6 lookups in flight
+	const int cnt = n_sub * GAP;
+	unsigned mask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+	if (DIRECT) {
+		// dense table: the key's two bits in the direct filter, one 64-byte fetch per lookup
+		mask = 0;
+#pragma unroll 1
+		for (int g = 0; g < n_sub; g += kGroup) {
+			uint32_t sh[kGroup * GAP];
+			const uint32_t *wp[kGroup * GAP];
+#pragma unroll
+			for (int ss = 0; ss < kGroup; ss++) {
+				const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
+#pragma unroll
+				for (int x = 0; x < GAP; x++) {
+					const uint32_t key = simple_key_at<RCKEYS>(pk, ob + x, rc_len);
+					const uint32_t u = direct_unit(key), e = key - u * kDirectKeys;
+					wp[ss * GAP + x] = ix.direct + 4 * (size_t)u + 1 + (e >> 4);
+					sh[ss * GAP + x] = 2 * (e & 15u);
+				}
+			}
+			uint32_t word[kGroup * GAP];
+#pragma unroll
+			for (int u = 0; u < kGroup * GAP; u++) word[u] = ld_gather(wp[u]);
+#pragma unroll
+			for (int u = 0; u < kGroup * GAP; u++) {
+				const bool in = g + u / GAP < n_sub && ((word[u] >> sh[u]) & 1u);
+				mask |= (in ? 1u : 0u) << ((g * GAP + u) & 31);
+			}
+		}
+		n_gather += (uint32_t)cnt;
+	} else if (ix.bloom) {
+		const uint32_t nb = ix.buckets_number;
+		const uint64_t magic = ix.buckets_magic;
+		const uint64_t pol = policy_evict_last();
+		mask = 0;
+#pragma unroll 1
+		for (int g = 0; g < n_sub; g += kGroup) {
+			uint32_t bw[kGroup * GAP], bq[kGroup * GAP];
+#pragma unroll
+			for (int ss = 0; ss < kGroup; ss++) {
+				const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
+#pragma unroll
+				for (int x = 0; x < GAP; x++) {
+					const uint32_t key = simple_key_at<RCKEYS>(pk, ob + x, rc_len);
+					const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
+					bq[ss * GAP + x] = q;
+					bw[ss * GAP + x] = key - q * nb;
+				}
+			}
+			uint32_t word[kGroup * GAP];
+#pragma unroll
+			for (int u = 0; u < kGroup * GAP; u++) word[u] = ld_bloom(ix.bloom + bw[u], pol);
+#pragma unroll
+			for (int u = 0; u < kGroup * GAP; u++) {
+				const uint32_t m = bloom_bits((int)bq[u]);
+				const bool in = g + u / GAP < n_sub && (word[u] & m) == m;
+				mask |= (in ? 1u : 0u) << ((g * GAP + u) & 31);
+			}
+		}
+	}
+	return mask;
+}
+
 // One strand pass.  pk = the pass's packed words of this thread (stride 128).  Leaves the clusters in C (shared
 // memory).  Returns false when the pass is not separable.
 //
-// Per batch of up to 32 lookups: (1) filter -- all Bloom words are requested before any is tested; (2) a uniform loop
-// over the survivors reads each bucket record (the next one is in flight while the current one is applied) and takes
-// the hit if it is a single position that belongs to the "primary" cluster P, which lives in registers (the first such
-// hit creates P); (3) whatever else turned up -- a position away from P, a lookup with several positions, a bucket of
-// more than twelve items -- is replayed on the general path, lookup by lookup in schedule order and position by
-// position in the reference's visit order.  Applying P's hits before the others is exact because a cluster does not
-// depend on the order of application.
-// MODE: 0 sparse table (Bloom word + bucket record), 1 the same with the unique-position bitmap, 2 dense table (direct filter)
+// Per batch of up to 32 lookups: (1) filter (simple_filter; the caller may hand in the first batch's mask, `first_mask`,
+// when it has run that filter already to decide which strand to take first); (2) a uniform loop over the survivors reads each
+// bucket record (the next one is in flight while the current one is applied) and takes the hit if it is a single position
+// that belongs to the "primary" cluster P, which lives in registers (the first such hit creates P); (3) whatever else turned
+// up -- a position away from P, a lookup with several positions, a bucket of more than twelve items -- is replayed on the
+// general path, lookup by lookup in schedule order and position by position in the reference's visit order.  Applying P's
+// hits before the others is exact because a cluster does not depend on the order of application.
+// MODE: 0 sparse table (Bloom word + bucket record), 2 dense table (direct filter)
 __device__ __noinline__ bool simple_hit_call(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
 {
 	return simple_hit(C, kv, l, u, sub, tol, low, high);
@@ -346,88 +506,26 @@ __device__ __noinline__ bool simple_hit_call(SimpleClusters &C, uint32_t kv, int
 
 template <int GAP, int MODE, bool RCKEYS = false>
 __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
-                                            SimpleClusters &C, int rc_len = 0)
+                                            SimpleClusters &C, int rc_len, uint32_t &n_gather, bool have_first_mask = false, unsigned first_mask = 0u)
 {
-	constexpr bool UNIQ = MODE == 1, DIRECT = MODE == 2;
+	constexpr bool DIRECT = MODE == 2;
 	constexpr int kSubsPerBatch = 32 / GAP;                        // whole subreads per batch of <= 32 lookups
-	constexpr int kGroup = GAP == 3 ? 2 : (GAP == 2 ? 3 : 6);     // subreads per group of 6 lookups in flight
 	const uint32_t nb = ix.buckets_number;
 	const uint64_t magic = ix.buckets_magic;
 	const int tol = cfg.indel_tolerance;
 	const uint32_t low = cfg.low_border, high = cfg.high_border - (uint32_t)L;
 	const uint4 *records = reinterpret_cast<const uint4 *>(ix.records);
-	const uint64_t pol = policy_evict_last();
 	C.n = 0;
 	if (C.cap < 1) return false;      // (paired-end tier: the first mate took the whole cluster pool)
 	SimpleCluster P;                  // cluster 0 while have_p
 	P.kv = 0; P.w1 = 0; P.subs = 0;
 	bool have_p = false, ok = true;
 	for (int s_base = 0; s_base < applied; s_base += kSubsPerBatch) {
-		const int n_sub = min(kSubsPerBatch, applied - s_base), cnt = n_sub * GAP, base = s_base * GAP;
+		const int n_sub = min(kSubsPerBatch, applied - s_base), base = s_base * GAP;
 		// ---- (1) filter ----
-		unsigned mask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-		if (DIRECT) {
-			// dense table: the key's two bits in the direct filter, one 64-byte fetch per lookup, all of a group in flight
-			mask = 0;
-#pragma unroll 1
-			for (int g = 0; g < n_sub; g += kGroup) {
-				uint32_t sh[kGroup * GAP];
-				const uint32_t *wp[kGroup * GAP];
-#pragma unroll
-				for (int ss = 0; ss < kGroup; ss++) {
-					const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
-#pragma unroll
-					for (int x = 0; x < GAP; x++) {
-						const uint32_t key = simple_key_at<RCKEYS>(pk, ob + x, rc_len);
-						const uint32_t u = direct_unit(key), e = key - u * kDirectKeys;
-						wp[ss * GAP + x] = ix.direct + 4 * (size_t)u + 1 + (e >> 4);
-						sh[ss * GAP + x] = 2 * (e & 15u);
-					}
-				}
-				uint32_t word[kGroup * GAP];
-#pragma unroll
-				for (int u = 0; u < kGroup * GAP; u++) word[u] = ld_gather(wp[u]);
-#pragma unroll
-				for (int u = 0; u < kGroup * GAP; u++) {
-					const bool in = g + u / GAP < n_sub && ((word[u] >> sh[u]) & 1u);
-					mask |= (in ? 1u : 0u) << ((g * GAP + u) & 31);
-				}
-			}
-		} else if (ix.bloom) {
-			mask = 0;
-#pragma unroll 1
-			for (int g = 0; g < n_sub; g += kGroup) {
-				uint32_t bw[kGroup * GAP], bq[kGroup * GAP];
-#pragma unroll
-				for (int ss = 0; ss < kGroup; ss++) {
-					const int ob = simple_sub_offset<GAP>(s_base + min(g + ss, n_sub - 1), step);
-#pragma unroll
-					for (int x = 0; x < GAP; x++) {
-						const uint32_t key = simple_key_at<RCKEYS>(pk, ob + x, rc_len);
-						const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
-						bq[ss * GAP + x] = q;
-						bw[ss * GAP + x] = key - q * nb;
-					}
-				}
-				uint32_t word[kGroup * GAP];
-#pragma unroll
-				for (int u = 0; u < kGroup * GAP; u++) word[u] = ld_bloom(ix.bloom + bw[u], pol);
-#pragma unroll
-				for (int u = 0; u < kGroup * GAP; u++) {
-					const uint32_t m = bloom_bits((int)bq[u]);
-					const bool in = g + u / GAP < n_sub && (word[u] & m) == m;
-					mask |= (in ? 1u : 0u) << ((g * GAP + u) & 31);
-#if SR_SIMPLE_PREFETCH
-					if (in && records) prefetch_l2(records + 2 * (size_t)bw[u]);
-#endif
-				}
-			}
-		}
+		unsigned mask = (have_first_mask && s_base == 0) ? first_mask : simple_filter<GAP, MODE, RCKEYS>(ix, pk, s_base, n_sub, step, rc_len, n_gather);
 		// ---- (2) survivors: single positions of the primary cluster ----
-		// One step ahead of the survivor being applied, the loads of the next one are already under way: its bucket
-		// record, or -- once P exists and the index has the unique-position bitmap -- the bitmap word and the two genome
-		// words at P.kv + offset.  If the genome shows the survivor's own 16-mer there and the bit says that this 16-mer
-		// has exactly that one position in the table, the lookup is known to return it and the bucket is never read.
+		// One step ahead of the survivor being applied, the load of the next one is already under way.
 		unsigned defer = mask;
 		uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // dense table: runs of keys with several positions waiting to be applied:
 		uint32_t me0 = 0, me1 = 0, me2 = 0, me3 = 0;     // first item in vals[];  h | landing << 8 | lookup << 16
@@ -435,8 +533,8 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 		if (DIRECT || records) {
 			defer = 0;
 			Record8 rn;
-			int i_next = -1, o_next = 0, sub_next = 0, mode_next = 0;
-			uint32_t key_next = 0, q_next = 0, p_next = 0;
+			int i_next = -1, o_next = 0, sub_next = 0;
+			uint32_t key_next = 0, q_next = 0;
 			auto issue = [&]() {
 				i_next = -1;
 				if (!mask) return;
@@ -444,49 +542,33 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 				mask &= mask - 1;
 				o_next = simple_offset<GAP>(base + i_next, step, &sub_next);
 				key_next = simple_key_at<RCKEYS>(pk, o_next, rc_len);
-				q_next = (uint32_t)__umul64hi((uint64_t)key_next, magic);
-				mode_next = 0;
-				if (UNIQ && have_p && ix.uniq_bits) {
-					p_next = P.kv + (uint32_t)o_next - ix.start_base_offset;
-					if (p_next < ix.uniq_n) {
-						mode_next = 1;
-						rn.w[0] = __ldg(ix.uniq_bits + (p_next >> 5));
-						rn.w[1] = __ldg(ix.genome + (p_next >> 4));
-						rn.w[2] = __ldg(ix.genome + (p_next >> 4) + 1);
-					}
-				}
 				if (DIRECT) {
 					const uint4 un = ld_direct_unit(ix, direct_unit(key_next));   // an L2 hit: the filter pass fetched this line
 					rn.w[0] = un.x; rn.w[1] = un.y; rn.w[2] = un.z; rn.w[3] = un.w;
-				} else if (mode_next == 0) rn = ld_record(records, key_next - q_next * nb);
+				} else {
+					q_next = (uint32_t)__umul64hi((uint64_t)key_next, magic);
+					rn = ld_record(records, key_next - q_next * nb);
+					n_gather++;
+				}
 			};
 			issue();
 			while (i_next >= 0) {
-				Record8 r = rn;
-				const int i = i_next, o = o_next, sub = sub_next, l = base + i, mode = mode_next;
-				const uint32_t key = key_next, q = q_next, p = p_next;
+				const Record8 r = rn;
+				const int i = i_next, o = o_next, sub = sub_next, l = base + i;
+				const uint32_t key = key_next, q = q_next;
 				issue();
 				int kind;
 				uint32_t kv;
-				bool proven = false;
-				if (UNIQ && mode == 1) {
-					const uint32_t g = __funnelshift_r(r.w[1], r.w[2], (p & 15u) * 2u);
-					uint32_t gk = __brev(g);
-					gk = ((gk & 0x55555555u) << 1) | ((gk >> 1) & 0x55555555u);
-					proven = ((r.w[0] >> (p & 31u)) & 1u) && gk == key;
-					if (!proven) r = ld_record(records, key - q * nb);
-				}
 				uint2 entry = make_uint2(0u, 0u);
 				if (DIRECT) {
 					uint32_t bits;
 					const uint32_t rank = direct_rank(make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]), key, direct_unit(key), &bits);
 					kind = bits == 1u ? 1 : (bits ? 2 : 0);
-					if (kind) entry = ld_direct_first(ix, rank);
+					if (kind) { entry = ld_direct_first(ix, rank); n_gather++; }
 					kv = entry.x - (uint32_t)o;
-				} else if (proven) { kind = 1; kv = P.kv; }
-				else {
+				} else {
 					uint32_t value = 0;
-					kind = simple_probe(ix, r, (int)(int16_t)q, &value);
+					kind = simple_probe(ix, r, (int)(int16_t)q, &value, n_gather);
 					kv = value - (uint32_t)o;
 				}
 				if (DIRECT) {
@@ -540,6 +622,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					const uint32_t u = direct_unit(key);
 					uint32_t bits;
 					const uint2 entry = ld_direct_first(ix, direct_rank(ld_direct_unit(ix, u), key, u, &bits));
+					n_gather++;
 					const uint32_t me = (entry.y & 0xffffu) | ((uint32_t)l << 16);
 					if (ne == 0) { ra0 = entry.x; me0 = me; } else if (ne == 1) { ra1 = entry.x; me1 = me; } else if (ne == 2) { ra2 = entry.x; me2 = me; } else { ra3 = entry.x; me3 = me; }
 					ne++;
@@ -553,6 +636,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 					const int nfwd = h - land;                           // landing .. end of run, then landing-1 .. start (:1109-1119)
 					const int idx = u < nfwd ? land + u : land - 1 - (u - nfwd);
 					const uint32_t v = ld_gather(ix.vals + ra + idx);
+					n_gather++;
 					int sub;
 					const int o = simple_offset<GAP>(l, step, &sub);
 					if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) { ok = false; break; }
@@ -563,72 +647,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 			if (!ok) return false;
 		} else if (defer) {
 			if (have_p) C.put(0, P);
-			while (defer) {
-				const int i = __ffs(defer) - 1;
-				defer &= defer - 1;
-				const int l = base + i;
-				int sub;
-				const int o = simple_offset<GAP>(l, step, &sub);
-				const uint32_t key = simple_key_at<RCKEYS>(pk, o, rc_len);
-				const uint32_t q = (uint32_t)__umul64hi((uint64_t)key, magic);
-				const uint32_t b = key - q * nb;
-				const int k16 = (int)(int16_t)q;
-				bool in_arrays = true;
-				if (records) {
-					const Record8 r = ld_record(records, b);
-					const int n = (int)(r.w[0] & 0xffffu);
-					if (n <= kInlineItems) {
-						in_arrays = false;
-						const int k0 = (int)(int16_t)(r.w[0] >> 16), k1 = (int)(int16_t)(r.w[1] & 0xffffu), k2 = (int)(int16_t)(r.w[1] >> 16),
-						          k3 = (int)(int16_t)(r.w[2] & 0xffffu), k4 = (int)(int16_t)(r.w[2] >> 16);
-						const int lt = (n > 0 && k0 < k16) + (n > 1 && k1 < k16) + (n > 2 && k2 < k16) + (n > 3 && k3 < k16) + (n > 4 && k4 < k16);
-						const int le = (n > 0 && k0 <= k16) + (n > 1 && k1 <= k16) + (n > 2 && k2 <= k16) + (n > 3 && k3 <= k16) + (n > 4 && k4 <= k16);
-						if (le > lt) {
-							// where the reference's (imin+imax)/2 search lands inside the run (sorted-hashtable.c:960-981)
-							int imin = 0, imax = n - 1, at;
-							for (;;) {
-								at = (imin + imax) >> 1;
-								if (at >= le) imax = at - 1;
-								else if (at < lt) imin = at + 1;
-								else break;
-							}
-							const int h = le - lt, nfwd = le - at;       // landing .. end of run, then landing-1 .. start (:1109-1119)
-							for (int u = 0; u < h; u++) {
-								const int idx = u < nfwd ? at + u : at - 1 - (u - nfwd);
-								const uint32_t v = idx == 0 ? r.w[3] : (idx == 1 ? r.w[4] : (idx == 2 ? r.w[5] : (idx == 3 ? r.w[6] : r.w[7])));
-								if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) return false;
-							}
-						}
-					}
-				}
-				if (in_arrays) {                                         // a bucket with more than 5 items, or no records at all
-					const uint32_t lo = ld_gather(ix.bucket_start + b);
-					const int items = (int)(ld_gather(ix.bucket_start + b + 1) - lo);
-					if (items <= 0) continue;
-					const int16_t *kp = ix.keys + lo;
-					int imin = 0, imax = items - 1, at;
-					bool found = false;
-					for (;;) {                                           // sorted-hashtable.c:960-981
-						at = (imin + imax) >> 1;
-						const int kk = (int)__ldg(kp + at);
-						if (kk > k16) imax = at - 1;
-						else if (kk < k16) imin = at + 1;
-						else { found = true; break; }
-						if (imax < imin) break;
-					}
-					if (!found) continue;
-					int e = at + 1, st = at;
-					while (e < items && (int)__ldg(kp + e) == k16) e++;
-					while (st > 0 && (int)__ldg(kp + st - 1) == k16) st--;
-					const int h = e - st, nfwd = e - at;
-					if (h > C.cap) return false;                         // cannot stay separable
-					for (int u = 0; u < h; u++) {
-						const int idx = u < nfwd ? at + u : at - 1 - (u - nfwd);
-						const uint32_t v = ld_gather(ix.vals + lo + idx);
-						if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) return false;
-					}
-				}
-			}
+			if (!simple_general<GAP, RCKEYS>(ix, cfg, pk, step, rc_len, base, defer, C, low, high, n_gather)) return false;
 			if (have_p) P = C.get(0);
 		}
 	}
@@ -775,7 +794,7 @@ template <int GAP, int MODE, bool JUNC = false, bool RMW = false>
 __global__ void __launch_bounds__(kSimpleThreads, JUNC ? 4 : SR_SIMPLE_MIN_BLOCKS)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
              const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int clusters, ResultWords *out, uint32_t *queue,
-             uint32_t *queue_count, uint32_t *bad_reads, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
+             uint32_t *queue_count, uint32_t *bad_reads, uint32_t *gather_count, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
 {
 	extern __shared__ uint4 smem4[];
 	constexpr unsigned kFullMask = 0xffffffffu;
@@ -884,18 +903,59 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 #pragma unroll
 		for (int i = 0; i < 12; i++) bm[i] = 0;
 	}
+	uint32_t n_gather = 0;
 	if (active && !punt) {
 		// a read shorter than 16 bases goes through two empty passes (core.c:3116)
 		int step = 65536;
 		const int applied = L >= 16 ? subread_schedule(L, GAP, cfg.total_subreads, &step) : 0;
+		// Which strand first?  The result does not depend on it -- the two passes fill separate cluster lists and only the merges
+		// (process_voting_junction_PE_topK, below) have an order -- but the warp's time does: the survivors loop of a pass runs about
+		// eleven times on the read's own strand and once or twice on the other one, and the lanes of a warp hold reads of both
+		// strands, so with a fixed order half of the lanes idle in either pass (17 of 32 threads active in round 1).  On a sparse
+		// table both strands' first batch is filtered up front and every lane takes its fuller strand first: the long loops of all
+		// lanes run side by side, then the short ones.  The lists of both passes then live at the same time and share the
+		// cluster pool (the second list starts where the first one ended).
+		constexpr bool kReorder = MODE == 0 && SR_SIMPLE_REORDER;
+		unsigned m0 = 0, m1 = 0;
+		int first = 0;
+		if (kReorder && applied > 0) {
+			const int n_sub0 = min(32 / GAP, applied);
+			m0 = simple_filter<GAP, MODE, false>(ix, pk, 0, n_sub0, step, 0, n_gather);
+			m1 = simple_filter<GAP, MODE, false>(ix, pk + n_words * kSimpleThreads, 0, n_sub0, step, 0, n_gather);
+			first = __popc(m1) > __popc(m0) ? 1 : 0;
+		}
+		SimpleClusters C0 = C, C1 = C;                                // by strand
 #pragma unroll 1
-		for (int strand = 0; strand < 2 && !punt; strand++) {        // one copy of the pass in the instruction cache
+		for (int k = 0; k < 2 && !punt; k++) {                       // one copy of the pass in the instruction cache
+			const int strand = first ^ k;
 			const uint32_t *pass = pk + strand * n_words * kSimpleThreads;
-			if (!simple_pass<GAP, MODE>(ix, cfg, pass, L, applied, step, C)) punt = true;
-			else if (JUNC) simple_merge_junc<GAP>(ix, cfg, C, strand, applied, step, res, J, JT, bm, TierText{pass, 0}, L);
-			else simple_merge<GAP>(cfg, C, strand, applied, step, res);
+			SimpleClusters Ck = C;
+			if (kReorder && k == 1) {                                 // behind the first pass's list
+				const int used = first ? C1.n : C0.n;
+				Ck.base = C.base + used * kSimpleClusterWords * 32;
+				Ck.cap = C.cap - used;
+			}
+			if (!simple_pass<GAP, MODE>(ix, cfg, pass, L, applied, step, Ck, 0, n_gather, kReorder && applied > 0, strand ? m1 : m0)) punt = true;
+			else if (!kReorder) {                                     // dense table: one list, merged at once
+				if (JUNC) simple_merge_junc<GAP>(ix, cfg, Ck, strand, applied, step, res, J, JT, bm, TierText{pass, 0}, L);
+				else simple_merge<GAP>(cfg, Ck, strand, applied, step, res);
+			}
+			if (strand == 0) C0 = Ck; else C1 = Ck;
+		}
+		if (kReorder && !punt) {
+#pragma unroll 1
+			for (int strand = 0; strand < 2; strand++) {
+				const SimpleClusters &Cs = strand ? C1 : C0;
+				SimpleClusters Cm;
+				Cm.base = Cs.base; Cm.n = Cs.n; Cm.cap = Cs.cap;
+				const uint32_t *pass = pk + strand * n_words * kSimpleThreads;
+				if (JUNC) simple_merge_junc<GAP>(ix, cfg, Cm, strand, applied, step, res, J, JT, bm, TierText{pass, 0}, L);
+				else simple_merge<GAP>(cfg, Cm, strand, applied, step, res);
+			}
 		}
 	}
+	n_gather = __reduce_add_sync(kFullMask, n_gather);
+	if (lane == 0 && n_gather) atomicAdd(gather_count, n_gather);
 	__syncwarp();
 	// queue the punted fragments (one atomic per warp)
 	const unsigned pm = __ballot_sync(kFullMask, active && punt);

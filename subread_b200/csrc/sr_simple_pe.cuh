@@ -35,7 +35,7 @@ SR_HD int simple_pe_warp_bytes(int max_len, int pool)
 {
 	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
 	int area = 32 * (((ml + 3) & ~3) + 4) + 32;                               // text of 32 reads (half of the warp's 64)
-	const int clus = pool * kSimpleClusterWords * 32 * 4;                     // the cluster pool reuses the staging area
+	const int clus = simple_cluster_bytes(pool);                              // the cluster pool reuses the staging area
 	if (area < clus) area = clus;
 	area = (area + 15) & ~15;
 	return area + 2 * kMaxBest * kPeResWords * 32 * 4;                         // + what the bigtable holds so far
@@ -316,7 +316,7 @@ template <int GAP, int MODE, bool JUNC = false, bool RMW = false>
 __global__ void __launch_bounds__(kSimpleThreads, JUNC ? 3 : 4)
 k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
                 const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int pool, ResultWords *out, uint32_t *queue,
-                uint32_t *queue_count, uint32_t *bad_reads, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
+                uint32_t *queue_count, uint32_t *bad_reads, uint32_t *gather_count, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
 {
 	extern __shared__ uint4 smem4[];
 	constexpr unsigned kFullMask = 0xffffffffu;
@@ -443,6 +443,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 	C0.base = C1.base = reinterpret_cast<uint32_t *>(stage) + lane;
 	C0.n = C1.n = 0;
 	C0.cap = C1.cap = pool;
+	uint32_t n_gather = 0;
 	if (active && !punt) {
 		int step0 = 65536, step1 = 65536;
 		const int applied0 = subread_schedule(L0, GAP, cfg.total_subreads, &step0);
@@ -458,7 +459,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 				C1.cap = pool - C0.n;
 			}
 			if (!simple_pass<GAP, MODE, true>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0,
-			                                  rc ? (m ? L1 : L0) : 0)) punt = true;
+			                                  rc ? (m ? L1 : L0) : 0, n_gather)) punt = true;
 			else if (m == 1) {
 				if (JUNC) {
 					const TierText tx0{pk, (strand ^ rev0) ? L0 : 0}, tx1{pk + n_words * kSimpleThreads, (strand ^ rev1) ? L1 : 0};
@@ -467,6 +468,8 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 			}
 		}
 	}
+	n_gather = __reduce_add_sync(kFullMask, n_gather);
+	if (lane == 0 && n_gather) atomicAdd(gather_count, n_gather);
 	__syncwarp();
 	const unsigned pm = __ballot_sync(kFullMask, active && punt);
 	if (pm) {

@@ -165,33 +165,41 @@ def build_index_arrays(names, seqs, gapped=True, threshold=100, buckets=None, us
                 names=list(names), contig_starts=np.array(starts, dtype=np.int64), removed_keys=int(heavy.shape[0]))
 
 
-def write_index_files(prefix, a):
-    """<prefix>.00.b.tab (gehash_dump, sorted-hashtable.c:1700-1908), .00.b.array and .reads."""
-    nb, n_items = a["buckets_number"], a["n_items"]
-    counts = np.diff(a["bucket_start"].astype(np.int64))
+def write_index_files(prefix, a, buckets_per_piece=1 << 20):
+    """<prefix>.00.b.tab (gehash_dump, sorted-hashtable.c:1700-1908), .00.b.array and .reads.  The table is written in
+    pieces of ``buckets_per_piece`` buckets so that a human-sized block (6.3 GB) needs no second copy in memory."""
+    nb, n_items = int(a["buckets_number"]), int(a["n_items"])
+    starts_items = a["bucket_start"].astype(np.int64)
+    counts = np.diff(starts_items)
     head = bytearray(b"2subindx")
     head += np.array([0x0102, 2, a["padding"], 0x0101, 2, a["index_gap"], 0], dtype="<i2").tobytes()
     head += np.array([n_items], dtype="<i8").tobytes() + np.array([nb], dtype="<i4").tobytes()
-    body = np.zeros(8 * nb + 6 * n_items + 1, dtype=np.uint8)  # trailing byte: is_small_table = 0
-    starts_items = a["bucket_start"].astype(np.int64)
-    hdr_at = 8 * np.arange(nb, dtype=np.int64) + 6 * starts_items[:-1]
-    cnt_bytes = counts.astype("<i4").view(np.uint8).reshape(nb, 4)
-    for k in range(4):
-        body[hdr_at + k] = cnt_bytes[:, k]
-        body[hdr_at + 4 + k] = cnt_bytes[:, k]  # space_size == current_items (sorted-hashtable.c:267)
-    item_bucket = a["item_bucket"].astype(np.int64)
-    within = np.arange(n_items, dtype=np.int64) - starts_items[item_bucket]
-    key_at = hdr_at[item_bucket] + 8 + 2 * within
-    val_at = hdr_at[item_bucket] + 8 + 2 * counts[item_bucket] + 4 * within
-    kb = a["keys"].astype("<i2").view(np.uint8).reshape(n_items, 2)
-    vb = a["vals"].astype("<u4").view(np.uint8).reshape(n_items, 4)
-    for k in range(2):
-        body[key_at + k] = kb[:, k]
-    for k in range(4):
-        body[val_at + k] = vb[:, k]
+    keys, vals = a["keys"], a["vals"]
     with open(prefix + ".00.b.tab", "wb") as fh:
         fh.write(bytes(head))
-        fh.write(body.tobytes())
+        for b0 in range(0, nb, buckets_per_piece):
+            b1 = min(nb, b0 + buckets_per_piece)
+            i0, i1 = int(starts_items[b0]), int(starts_items[b1])
+            cnt = counts[b0:b1]
+            body = np.zeros(8 * (b1 - b0) + 6 * (i1 - i0), dtype=np.uint8)
+            hdr_at = 8 * np.arange(b1 - b0, dtype=np.int64) + 6 * (starts_items[b0:b1] - i0)
+            cnt_bytes = cnt.astype("<i4").view(np.uint8).reshape(-1, 4)
+            for k in range(4):
+                body[hdr_at + k] = cnt_bytes[:, k]
+                body[hdr_at + 4 + k] = cnt_bytes[:, k]  # space_size == current_items (sorted-hashtable.c:267)
+            if i1 > i0:
+                item_bucket = np.repeat(np.arange(b1 - b0, dtype=np.int64), cnt)
+                within = np.arange(i1 - i0, dtype=np.int64) - (starts_items[b0:b1] - i0)[item_bucket]
+                key_at = hdr_at[item_bucket] + 8 + 2 * within
+                val_at = hdr_at[item_bucket] + 8 + 2 * cnt[item_bucket] + 4 * within
+                kb = np.ascontiguousarray(keys[i0:i1]).astype("<i2").view(np.uint8).reshape(-1, 2)
+                vb = np.ascontiguousarray(vals[i0:i1]).astype("<u4").view(np.uint8).reshape(-1, 4)
+                for k in range(2):
+                    body[key_at + k] = kb[:, k]
+                for k in range(4):
+                    body[val_at + k] = vb[:, k]
+            fh.write(body.tobytes())
+        fh.write(b"\0")  # trailing byte: is_small_table = 0
     with open(prefix + ".00.b.array", "wb") as fh:
         fh.write(np.array([a["start_point"], a["length"]], dtype="<u4").tobytes())
         fh.write(a["values"].tobytes())

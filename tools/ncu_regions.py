@@ -9,8 +9,10 @@ def find(pat):
         if pat in l:
             return i + 1
 marks = [("structs", 1), ("simple_hit", find("bool simple_hit(")), ("pack", find("bool simple_pack")), ("offsets/key", find("int simple_sub_offset")), ("probe", find("int simple_probe")),
-         ("pass-setup", find("bool simple_pass")), ("filter", find("// ---- (1) filter ----")), ("S1", find("// ---- (2) survivors")), ("S2", find("// ---- (3) everything else")),
+         ("general", find("bool simple_general(")), ("pass-setup", find("bool simple_pass")), ("filter", find("// ---- (1) filter ----")), ("pool", find("// (2a) pool")), ("lookup", find("// (2b) lookup")),
+         ("apply", find("// (3) apply")), ("rest", find("// ---- (4) everything else")),
          ("update_top", find("// update_top_three")), ("merge", find("void simple_merge")), ("kernel", find("k_map_simple(const DevIndex ix"))]
+marks = [m for m in marks if m[1]]
 agg = collections.OrderedDict((m[0], [0, 0, 0]) for m in marks)
 other = [0, 0]
 print(out[0])
