@@ -612,20 +612,22 @@ def main():
             mix = None
             if res["gathers"] and lookups_per_frag:
                 try:
-                    sparse = not (desc.accelerators & 4)
-                    n_small = int(round(lookups_per_frag)) if sparse else 0
+                    sparse, phase = not (desc.accelerators & 4), bool(desc.accelerators & 16)
+                    # small probes: one Bloom word per lookup, or -- with the phase table of a gapped index -- one occupancy bit per subread
+                    n_small = (int(round(lookups_per_frag / 3)) if phase else int(round(lookups_per_frag))) if sparse else 0
+                    small_bytes = (1 << 25) if phase else 2 * desc.buckets_number
                     n_big = max(1, int(round(res["gathers"] / R)))
-                    units = m.lookup_roofline(2 * desc.buckets_number, n_small, max(int(desc.device_bytes), 1 << 28), n_big, 3)
+                    units = m.lookup_roofline(small_bytes, n_small, max(int(desc.device_bytes), 1 << 28), n_big, 3)
                     mix = {"bloom_probes_per_fragment": n_small, "dram_fetches_per_fragment": n_big, "fragments_per_s_allowed": units,
                            "frac": (R / (res["kern_ms"] * 1e-3)) / units,
-                           "probe": "k_mix_probe: that many random Bloom-word loads (evict-last, %.0f MB table) and random 64-byte record fetches (%.1f GB table) "
-                                    "per unit, nothing else" % (2 * desc.buckets_number / 1e6, max(int(desc.device_bytes), 1 << 28) / 1e9)}
+                           "probe": "k_mix_probe: that many random probes of an L2-resident table (evict-last, %.0f MB) and random 64-byte fetches (%.1f GB table) "
+                                    "per unit, nothing else" % (small_bytes / 1e6, max(int(desc.device_bytes), 1 << 28) / 1e9)}
                 except Exception as e:
                     mix = {"error": repr(e)}
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "traffic_source": traffic_note,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                        "kernel": ("k_map_simple_pe" if paired else "k_map_simple") + f"<3,{2 if desc.accelerators & 4 else 0}> (one thread per fragment) + k_map_warp (queued fragments)",
+                        "kernel": ("k_map_simple_pe" if paired else "k_map_simple") + f"<3,{2 if desc.accelerators & 4 else (3 if desc.accelerators & 16 else 0)}> (one thread per fragment) + k_map_warp (queued fragments)",
                         "kernel_ms": res["kern_ms"], "tier0_ms": res["simple_ms"], "algorithmic_bytes_per_fragment": alg_bytes,
                         "tier0_punted_fraction": res["punted"] / R, "warp_kernel_ms": res["kern_ms"] - res["simple_ms"],
                         "scalar_fragments_per_step": res["n_over"], "scalar_kernel_ms": res["over_ms"],

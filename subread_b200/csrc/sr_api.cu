@@ -172,6 +172,110 @@ __global__ void k_build_records(const uint32_t *bucket_start, const int16_t *key
 	}
 }
 
+// The phase table of a gapped index (sr_common.cuh).  (1) one thread per bucket marks every distinct key of its bucket in the
+// three units it belongs to (one per role) and in the units' occupancy bitmap; (2) once all marks are in, the keys with a
+// single position write it into their units' value slots, by rank among the unit's present keys.
+__global__ void k_phase_mark(const uint32_t *bucket_start, const int16_t *keys, uint32_t nb, uint32_t *units, uint32_t *any)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
+		for (uint32_t i = 0; i < n;) {
+			const int16_t k = keys[lo + i];
+			uint32_t j = i + 1;
+			while (j < n && keys[lo + j] == k) j++;
+			const uint64_t key64 = (uint64_t)(uint16_t)k * nb + b;
+			if (key64 <= 0xffffffffull) {                                      // (a key no 16-mer can produce is never looked up)
+				const uint32_t key = (uint32_t)key64;
+#pragma unroll
+				for (int role = 0; role < 3; role++) {
+					const uint32_t c = phase_unit(key, role), v = phase_variant(key, role);
+					atomicOr(units + 8 * (size_t)c + role, (j - i > 1 ? 3u : 1u) << (2 * v));
+					atomicOr(any + (c >> 5), 1u << (c & 31u));
+				}
+			}
+			i = j;
+		}
+	}
+}
+__global__ void k_phase_fill(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, uint32_t *units)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
+		for (uint32_t i = 0; i < n;) {
+			const int16_t k = keys[lo + i];
+			uint32_t j = i + 1;
+			while (j < n && keys[lo + j] == k) j++;
+			const uint64_t key64 = (uint64_t)(uint16_t)k * nb + b;
+			if (key64 <= 0xffffffffull && j - i == 1) {
+				const uint32_t key = (uint32_t)key64;
+#pragma unroll
+				for (int role = 0; role < 3; role++) {
+					const uint32_t c = phase_unit(key, role), v = phase_variant(key, role);
+					uint32_t *u = units + 8 * (size_t)c;
+					uint32_t rank = __popc(u[role] & 0x55555555u & ((1u << (2 * v)) - 1u));
+					if (role > 0) rank += __popc(u[0] & 0x55555555u);
+					if (role > 1) rank += __popc(u[1] & 0x55555555u);
+					if (rank < (uint32_t)kPhaseValues) u[3 + rank] = vals[lo + i];
+				}
+			}
+			i = j;
+		}
+	}
+}
+
+// The same for a dense table (128-byte units, no bitmap; the direct filter must exist: a key with several positions stores the
+// rank of its direct_first entry).
+__global__ void k_phase_mark_dense(const uint32_t *bucket_start, const int16_t *keys, uint32_t nb, uint32_t *units)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
+		for (uint32_t i = 0; i < n;) {
+			const int16_t k = keys[lo + i];
+			uint32_t j = i + 1;
+			while (j < n && keys[lo + j] == k) j++;
+			const uint64_t key64 = (uint64_t)(uint16_t)k * nb + b;
+			if (key64 <= 0xffffffffull) {
+				const uint32_t key = (uint32_t)key64;
+#pragma unroll
+				for (int role = 0; role < 3; role++)
+					atomicOr(units + (size_t)kPhaseDenseWords * phase_unit(key, role) + role, (j - i > 1 ? 3u : 1u) << (2 * phase_variant(key, role)));
+			}
+			i = j;
+		}
+	}
+}
+__global__ void k_phase_fill_dense(const uint32_t *bucket_start, const int16_t *keys, const uint32_t *vals, uint32_t nb, const uint32_t *direct, uint32_t *units)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+		const uint32_t lo = bucket_start[b], n = bucket_start[b + 1] - lo;
+		for (uint32_t i = 0; i < n;) {
+			const int16_t k = keys[lo + i];
+			uint32_t j = i + 1;
+			while (j < n && keys[lo + j] == k) j++;
+			const uint64_t key64 = (uint64_t)(uint16_t)k * nb + b;
+			if (key64 <= 0xffffffffull) {
+				const uint32_t key = (uint32_t)key64;
+				uint32_t value = vals[lo + i];
+				if (j - i > 1) {                                             // several positions: where direct_first describes the run
+					const uint32_t du = direct_unit(key);
+					uint32_t bits;
+					value = direct_rank(make_uint4(direct[4 * (size_t)du], direct[4 * (size_t)du + 1], direct[4 * (size_t)du + 2], direct[4 * (size_t)du + 3]), key, du, &bits);
+				}
+#pragma unroll
+				for (int role = 0; role < 3; role++) {
+					const uint32_t v = phase_variant(key, role);
+					uint32_t *u = units + (size_t)kPhaseDenseWords * phase_unit(key, role);
+					uint32_t rank = __popc(u[role] & 0x55555555u & ((1u << (2 * v)) - 1u));
+					if (role > 0) rank += __popc(u[0] & 0x55555555u);
+					if (role > 1) rank += __popc(u[1] & 0x55555555u);
+					if (rank < (uint32_t)kPhaseDenseValues) u[4 + rank] = value;
+				}
+			}
+			i = j;
+		}
+	}
+}
+
 // Direct filter of a dense table (sr_common.cuh), built in four steps.  (1) one thread per bucket marks every distinct
 // key of its bucket: key = key16 * buckets + bucket, bit 0 present, bit 1 more than one position.
 __global__ void k_direct_mark(const uint32_t *bucket_start, const int16_t *keys, uint32_t nb, uint32_t *words)
@@ -333,7 +437,8 @@ struct srcuda_handle {
 	sr::DevIndex ix{};
 	srcuda_index_desc desc{};
 	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
-	void *d_records = nullptr, *d_bloom = nullptr, *d_direct = nullptr, *d_direct_first = nullptr;
+	void *d_records = nullptr, *d_bloom = nullptr, *d_direct = nullptr, *d_direct_first = nullptr, *d_phase_any = nullptr, *d_phase_units = nullptr, *d_phase_dense = nullptr;
+	bool use_phase = true;         // SRCUDA_PHASE=0: no phase table for gapped sparse indexes (A/B and cross-checks)
 	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both, 4 direct filter (SRCUDA_ACCEL)
 	bool l2_persist = true;        // keep the Bloom words resident in L2 (SRCUDA_L2_PERSIST=0 turns it off)
 	size_t l2_persist_max = 0, l2_window_max = 0;
@@ -348,10 +453,10 @@ struct srcuda_handle {
 	bool use_simple_tier_pe = true;  // SRCUDA_SIMPLE_TIER_PE=0 disables its paired-end form only
 	bool use_warp_junc = true;       // SRCUDA_WARP_JUNC=0: subjunc fragments all take the scalar path
 	bool use_tier_junc = true;       // SRCUDA_TIER_JUNC=0: subjunc chunks skip the thread-per-fragment tier
-	int simple_junc_smem_set[4][3] = {}, simple_pe_junc_smem_set[4][3] = {}, simple_rmw_smem_set[4][3] = {}, simple_pe_rmw_smem_set[4][3] = {};
+	int simple_junc_smem_set[4][5] = {}, simple_pe_junc_smem_set[4][5] = {}, simple_rmw_smem_set[4][5] = {}, simple_pe_rmw_smem_set[4][5] = {};
 	bool use_tier_rmw = true;        // SRCUDA_TIER_RMW=0: chunks merged into a non-zero bigtable (later index blocks) skip the thread-per-fragment tier
-	int simple_pe_smem_set[4][3] = {};
-	int simple_smem_set[4][3] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
+	int simple_pe_smem_set[4][5] = {};
+	int simple_smem_set[4][5] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
 	uint32_t *d_sink = nullptr;
 };
@@ -399,8 +504,8 @@ int ensure(srcuda_handle *h, DeviceBuf &b, size_t bytes)
 void free_index(srcuda_handle *h)
 {
 	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr);
-	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_direct); cudaFree(h->d_direct_first);
-	h->d_direct = h->d_direct_first = nullptr;
+	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_direct); cudaFree(h->d_direct_first); cudaFree(h->d_phase_any); cudaFree(h->d_phase_units); cudaFree(h->d_phase_dense);
+	h->d_direct = h->d_direct_first = h->d_phase_any = h->d_phase_units = h->d_phase_dense = nullptr;
 	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = h->d_records = h->d_bloom = nullptr;
 	h->has_index = false;
 	h->l2_policy_for = nullptr;
@@ -461,8 +566,34 @@ int build_accelerators(srcuda_handle *h)
 	h->ix.records = nullptr;
 	h->ix.direct = nullptr;
 	h->ix.direct_first = nullptr;
+	h->ix.phase_any = nullptr;
+	h->ix.phase_units = nullptr;
+	h->ix.phase_dense = nullptr;
 	h->desc.accelerators = 0;
-	if (mode & 4) return build_direct(h);
+	if (mode & 4) {
+		int rc = build_direct(h);
+		if (rc) return rc;
+		// gapped index, dense table: the 128-byte phase units on top (the thread-per-fragment tiers use them; the warp kernel and
+		// the keys with several positions keep the direct filter)
+		if (h->ix.index_gap == 3 && h->use_phase) {
+			const size_t unit_bytes = 4ull * sr::kPhaseDenseWords * sr::kPhaseUnits;
+			size_t free_b = 0, total_b = 0;
+			cudaMemGetInfo(&free_b, &total_b);
+			if (free_b > unit_bytes + (24ull << 30)) {                       // leave room for the chunk buffers
+				CU(h, cudaMalloc(&h->d_phase_dense, unit_bytes));
+				CU(h, cudaMemset(h->d_phase_dense, 0, unit_bytes));
+				sr::k_phase_mark_dense<<<h->sm_count * 8, 256>>>(h->ix.bucket_start, h->ix.keys, nb, (uint32_t *)h->d_phase_dense);
+				CU(h, cudaGetLastError());
+				sr::k_phase_fill_dense<<<h->sm_count * 8, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, h->ix.direct, (uint32_t *)h->d_phase_dense);
+				CU(h, cudaGetLastError());
+				CU(h, cudaDeviceSynchronize());
+				h->ix.phase_dense = (const uint32_t *)h->d_phase_dense;
+				h->desc.device_bytes += unit_bytes;
+				h->desc.accelerators |= 16;
+			}
+		}
+		return 0;
+	}
 	if (mode & 1) CU(h, cudaMalloc(&h->d_bloom, sizeof(sr::bloom_t) * (size_t)nb));
 	if (mode & 2) CU(h, cudaMalloc(&h->d_records, 32 * (size_t)nb));
 	if (mode) {
@@ -474,6 +605,28 @@ int build_accelerators(srcuda_handle *h)
 	h->ix.records = h->d_records;
 	h->desc.device_bytes += (mode & 1 ? (uint64_t)sizeof(sr::bloom_t) * nb : 0) + (mode & 2 ? 32ull * nb : 0);
 	h->desc.accelerators = (uint32_t)(mode & 3);
+	// gapped index, sparse table: the phase table on top (the thread-per-fragment tiers use it, the warp kernel keeps the
+	// Bloom words and bucket records)
+	if ((mode & 3) == 3 && h->ix.index_gap == 3 && h->use_phase) {
+		const size_t unit_bytes = 32ull * sr::kPhaseUnits, any_bytes = sr::kPhaseUnits / 8;
+		size_t free_b = 0, total_b = 0;
+		cudaMemGetInfo(&free_b, &total_b);
+		if (free_b > unit_bytes + any_bytes + (8ull << 30)) {              // leave room for the chunk buffers
+			CU(h, cudaMalloc(&h->d_phase_units, unit_bytes));
+			CU(h, cudaMalloc(&h->d_phase_any, any_bytes));
+			CU(h, cudaMemset(h->d_phase_units, 0, unit_bytes));
+			CU(h, cudaMemset(h->d_phase_any, 0, any_bytes));
+			sr::k_phase_mark<<<h->sm_count * 8, 256>>>(h->ix.bucket_start, h->ix.keys, nb, (uint32_t *)h->d_phase_units, (uint32_t *)h->d_phase_any);
+			CU(h, cudaGetLastError());
+			sr::k_phase_fill<<<h->sm_count * 8, 256>>>(h->ix.bucket_start, h->ix.keys, h->ix.vals, nb, (uint32_t *)h->d_phase_units);
+			CU(h, cudaGetLastError());
+			CU(h, cudaDeviceSynchronize());
+			h->ix.phase_any = (const uint32_t *)h->d_phase_any;
+			h->ix.phase_units = h->d_phase_units;
+			h->desc.device_bytes += unit_bytes + any_bytes;
+			h->desc.accelerators |= 16;
+		}
+	}
 	return 0;
 }
 
@@ -650,7 +803,17 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		switch (h->ix.index_gap) {
 		case 1: SR_LAUNCH_SIMPLE(1); break;
 		case 2: SR_LAUNCH_SIMPLE(2); break;
-		default: SR_LAUNCH_SIMPLE(3); break;
+		default:
+			if (h->ix.phase_units) {                     // gapped index with a phase table: mode 3 (sparse table), mode 4 (dense)
+				if (cfg.do_junctions) SR_LAUNCH_SIMPLE_J(3, 3);
+				else if (!a.out_zero) SR_LAUNCH_SIMPLE_R(3, 3);
+				else SR_LAUNCH_SIMPLE_U(3, 3);
+			} else if (h->ix.phase_dense) {
+				if (cfg.do_junctions) SR_LAUNCH_SIMPLE_J(3, 4);
+				else if (!a.out_zero) SR_LAUNCH_SIMPLE_R(3, 4);
+				else SR_LAUNCH_SIMPLE_U(3, 4);
+			} else SR_LAUNCH_SIMPLE(3);
+			break;
 		}
 #undef SR_LAUNCH_SIMPLE_U
 #undef SR_LAUNCH_SIMPLE_R
@@ -719,7 +882,17 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			switch (h->ix.index_gap) {
 			case 1: SR_LAUNCH_PE(1); break;
 			case 2: SR_LAUNCH_PE(2); break;
-			default: SR_LAUNCH_PE(3); break;
+			default:
+				if (h->ix.phase_units) {
+					if (cfg.do_junctions) SR_LAUNCH_PE_J(3, 3);
+					else if (!a.out_zero) SR_LAUNCH_PE_R(3, 3);
+					else SR_LAUNCH_PE_U(3, 3);
+				} else if (h->ix.phase_dense) {
+					if (cfg.do_junctions) SR_LAUNCH_PE_J(3, 4);
+					else if (!a.out_zero) SR_LAUNCH_PE_R(3, 4);
+					else SR_LAUNCH_PE_U(3, 4);
+				} else SR_LAUNCH_PE(3);
+				break;
 			}
 			CU(h, cudaGetLastError());
 			h->timing.n_launches++;
@@ -749,20 +922,22 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 // read at random, everything else streams through; a persisting access-policy window keeps them in L2.
 void apply_l2_policy(srcuda_handle *h)
 {
-	if (!h->l2_persist || !h->d_bloom || h->l2_policy_for == h->d_bloom || !h->l2_persist_max || !h->l2_window_max) return;
-	const size_t bytes = sizeof(sr::bloom_t) * (size_t)h->ix.buckets_number;
+	// the table probed at random for every lookup: the phase table's occupancy bitmap when there is one, else the Bloom words
+	const void *hot = h->d_phase_any ? h->d_phase_any : h->d_bloom;
+	if (!h->l2_persist || !hot || h->l2_policy_for == hot || !h->l2_persist_max || !h->l2_window_max) return;
+	const size_t bytes = h->d_phase_any ? (size_t)(sr::kPhaseUnits / 8) : sizeof(sr::bloom_t) * (size_t)h->ix.buckets_number;
 	const size_t carve = std::min(bytes, h->l2_persist_max), window = std::min(bytes, h->l2_window_max);
 	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
 	cudaStreamAttrValue v;
 	memset(&v, 0, sizeof(v));
-	v.accessPolicyWindow.base_ptr = h->d_bloom;
+	v.accessPolicyWindow.base_ptr = const_cast<void *>(hot);
 	v.accessPolicyWindow.num_bytes = window;
 	v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
 	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
 	v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
 	for (int i = 0; i < kSets; i++)
 		if (h->set[i].stream && cudaStreamSetAttribute(h->set[i].stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-	h->l2_policy_for = h->d_bloom;
+	h->l2_policy_for = hot;
 }
 
 int init_sets(srcuda_handle *h)
@@ -817,6 +992,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
 	const char *st = getenv("SRCUDA_SIMPLE_TIER");
 	if (st && st[0] == '0') h->use_simple_tier = false;
+	const char *ph = getenv("SRCUDA_PHASE");
+	if (ph && ph[0] == '0') h->use_phase = false;
 	const char *tr = getenv("SRCUDA_TIER_RMW");
 	if (tr && tr[0] == '0') h->use_tier_rmw = false;
 	const char *tj = getenv("SRCUDA_TIER_JUNC");

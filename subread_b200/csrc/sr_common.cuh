@@ -60,6 +60,10 @@ struct DevIndex {
 	const bloom_t *bloom;          // per bucket: bloom_bits(key16) set for every key16 in the bucket; null = off
 	const void *records;           // per bucket 32 B (two uint4): see below; null = off
 	// Dense tables (a human-sized index holds ~64 items per bucket): the direct filter, see below; null = off
+	// Gapped index (gap 3), sparse table: the phase table, see below; null = off
+	const uint32_t *phase_any;     // bit c set: unit c holds at least one key
+	const void *phase_units;       // 2^28 units of 32 bytes
+	const uint32_t *phase_dense;   // dense table: 2^28 units of 128 bytes; null = off
 	const uint32_t *direct;        // one 16-byte unit (four words) per kDirectKeys consecutive 32-bit keys
 	const uint64_t *direct_first;  // by rank among the present keys: {position, 1} for a key with one position, else
 	                               // {first item of its run in vals[], h | landing << 8} (low, high word): run length and the index inside the
@@ -78,6 +82,31 @@ struct DevIndex {
 constexpr uint32_t kDirectKeys = 48;
 constexpr uint32_t kDirectUnits = 89478486u;   // ceil(2^32 / 48)
 SR_HD uint32_t direct_unit(uint32_t key) { return (uint32_t)(((uint64_t)key * 0xAAAAAAABull) >> 37); }   // key / 48
+
+// The phase table of a gapped index (gap 3).  do_voting looks every subread up at three consecutive offsets o, o+1, o+2
+// (core.c:3169-3171: the index holds every third position, so one of the three phases lines up).  The three 16-mers share 14
+// bases, c = bases o+2 .. o+15 (28 bits): K0 = xx|c, K1 = x|c|y, K2 = c|yy.  For a fixed c there are 16 + 16 + 16 = 48 such
+// keys, and unit c of the table says for each of them whether the index holds it -- so ONE 32-byte fetch answers all three
+// lookups of a subread, instead of three filter probes and a bucket record per survivor.  Unit c (eight words):
+//   w0, w1, w2   role 0, 1, 2: two bits per variant v (bit 0 = the table holds the key, bit 1 = with several positions);
+//                role 0: v = K0 >> 28;  role 1: v = (K1 >> 30) << 2 | (K1 & 3);  role 2: v = K2 & 15
+//   w3 .. w7     the positions of the first five keys present, in (role, v) order (a key with several positions, or one
+//                beyond the fifth, is looked up in its bucket: the reference's visit order needs the bucket anyway)
+// Every index key sits in three units (once per role).  2^28 units = 8.6 GB whatever the index; phase_any (32 MB, kept in L2)
+// tells which units are not empty, so that only those are fetched: on a 100 Mbp genome two thirds of the foreign subreads
+// stop there.
+// Dense tables (a human-sized index: a quarter of all 16-mers present, twelve keys per unit) use units of 128 bytes: w0-w2 as
+// above, w3 spare, w4 .. w31 the values of the first 28 keys present in (role, v) order -- the position of a key with a single
+// one, and for a key with several the rank of its entry in direct_first (run start, length, landing index).  There is no
+// occupancy bitmap (no unit is empty): one 64-byte fetch per subread answers three lookups and, two times out of three, holds
+// the position too.  2^28 units = 34 GB.
+constexpr int kPhaseDenseValues = 28;
+constexpr int kPhaseDenseWords = 32;
+constexpr uint32_t kPhaseMask = 0x0fffffffu;
+constexpr uint32_t kPhaseUnits = 1u << 28;
+constexpr int kPhaseValues = 5;
+SR_HD uint32_t phase_unit(uint32_t key, int role) { return role == 0 ? (key & kPhaseMask) : (role == 1 ? ((key >> 2) & kPhaseMask) : (key >> 4)); }
+SR_HD uint32_t phase_variant(uint32_t key, int role) { return role == 0 ? (key >> 28) : (role == 1 ? (((key >> 30) << 2) | (key & 3u)) : (key & 15u)); }
 
 // 32-byte bucket record (one sector), n = items in the bucket (saturated at 0xffff):
 //   n <= kInlineItems:  bytes 0-1 n   bytes 2-11 key16[5]   bytes 12-31 value[5]        (the whole bucket)

@@ -52,6 +52,10 @@
 #define SR_SIMPLE_REORDER 0    // sparse table: every lane takes its fuller strand first.  A/B switch, off: 17 % fewer warp instructions but
                                // 1.39 instead of 1.55 G reads/s -- the kernel runs at the memory system's request rate, profiles/r02_tier0_experiments.md
 #endif
+#ifndef SR_SIMPLE_DEFER_LIMIT
+#define SR_SIMPLE_DEFER_LIMIT 3    // lookups of one batch a lane may take through the general path before the fragment is queued for the warp kernel
+                                   // (A/B on B200: mixed workload 419 -> 446 M reads/s, clean 1 502 -> 1 533 M)
+#endif
 #ifndef SR_SIMPLE_SMEM_OUT
 #define SR_SIMPLE_SMEM_OUT 0   // compose the warp's bigtable slice in shared memory and store whole sectors (A/B switch)
 #endif
@@ -209,15 +213,18 @@ __device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, 
 // Pack the thread's read from the staging area: forward codes (MSB first, 16 bases per word, code 2 beyond
 // the read like the reference's NUL) into pk[k * 128], reverse-complement codes into pk[(n_words + k) * 128].
 // Returns false when a character is not one of A, C, G, T (then base2int / reverse_read quirks apply and the
-// fragment is punted).
-template <bool WITH_RC = true>
+// fragment is punted) -- except, with ALLOW_N, the letter N, the one odd character real reads are full of: genekey2int
+// reads it as code 3 (base2int, subread.h:238: anything from 'H' up that is not 'G'), and reverse_read (input-files.c:1171-1186)
+// leaves it an 'N', so it is code 3 on the reverse strand as well, where a T would have become an A.  A read with Ns gets its
+// reverse-strand words character by character (the rare path); everything downstream only sees codes.
+template <bool WITH_RC = true, bool ALLOW_N = false>
 __device__ __forceinline__ bool simple_pack(const uint8_t *stage, unsigned so, int L, uint32_t *pk, int n_words)
 {
 	const int nw = (L + 15) / 16 + 1;
 	const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage + (so & ~3u));
 	const unsigned mis = (so & 3u) * 8u;
 	const int last_word = (int)(((so & 3u) + (unsigned)L + 3u) / 4u);    // words [0, last_word) hold characters
-	uint32_t bad = 0;
+	uint32_t bad = 0, any_n = 0;
 	uint32_t wprev = sw[0];
 	for (int k = 0; k < nw; k++) {
 		uint32_t f = 0;
@@ -231,13 +238,20 @@ __device__ __forceinline__ bool simple_pack(const uint8_t *stage, unsigned so, i
 			wprev = wnext;
 			// A 0x41, C 0x43, G 0x47, T 0x54: code bit0 = bit 2, code bit1 = bit 1 ^ bit 2  (A0 G1 C2 T3)
 			const uint32_t b2 = (c4 >> 2) & 0x01010101u, b1 = ((c4 >> 1) ^ (c4 >> 2)) & 0x01010101u;
-			const uint32_t code4 = b2 | (b1 << 1);
+			uint32_t code4 = b2 | (b1 << 1);
 			// validate by rebuilding the characters from the codes: "AGCT"[code]
 			const uint32_t sel = (code4 & 3u) | ((code4 >> 4) & 0x30u) | ((code4 >> 8) & 0x300u) | ((code4 >> 12) & 0x3000u);
 			const uint32_t rebuilt = __byte_perm(0x54434741u, 0u, sel);
 			const int nb = nvalid - 4 * q;  // characters of this group inside the read
 			uint32_t diff = rebuilt ^ c4;
 			if (nb < 4) diff = nb <= 0 ? 0u : (diff & (0xffffffffu >> (8 * (4 - nb))));
+			if (ALLOW_N && diff) {                                       // (rare) forgive the Ns: code 3
+				uint32_t isn = __vcmpeq4(c4, 0x4E4E4E4Eu);
+				if (nb < 4) isn = nb <= 0 ? 0u : (isn & (0xffffffffu >> (8 * (4 - nb))));
+				code4 |= isn & 0x03030303u;
+				diff &= ~isn;
+				any_n |= isn;
+			}
 			bad |= diff;
 			f |= ((code4 * 0x40100401u) >> 24) << (24 - 8 * q);
 		}
@@ -245,8 +259,31 @@ __device__ __forceinline__ bool simple_pack(const uint8_t *stage, unsigned so, i
 		pk[k * kSimpleThreads] = (f & keep) | (0xAAAAAAAAu & ~keep);
 	}
 	if (!WITH_RC) return bad == 0;                                 // the caller derives reverse-strand keys from this array
-	// reverse complement of an all-base read: rc base i = 3 - f base (L-1-i)
 	uint32_t *rc = pk + n_words * kSimpleThreads;
+	if (ALLOW_N && any_n && bad == 0) {
+		// reverse complement with Ns: character by character, rc base i = reverse_read(char L-1-i)
+		const uint8_t *ch = stage + so;
+		for (int k = 0; k < nw; k++) {
+			const int nvalid = min(16, max(0, L - 16 * k));
+			uint32_t r = 0xAAAAAAAAu;
+			if (nvalid > 0) {
+				r = 0;
+#pragma unroll 4
+				for (int j = 0; j < 16; j++) {
+					const int i = 16 * k + j;
+					uint32_t code = 2u;                                  // beyond the read
+					if (i < L) {
+						const int c = (int)ch[L - 1 - i];
+						code = c == 'N' ? 3u : (uint32_t)(3 - base_code(c));
+					}
+					r |= code << (30 - 2 * j);
+				}
+			}
+			rc[k * kSimpleThreads] = r;
+		}
+		return true;
+	}
+	// reverse complement of an all-base read: rc base i = 3 - f base (L-1-i)
 	for (int k = 0; k < nw; k++) {
 		const int nvalid = min(16, max(0, L - 16 * k));
 		uint32_t r = 0xAAAAAAAAu;
@@ -504,10 +541,254 @@ __device__ __noinline__ bool simple_hit_call(SimpleClusters &C, uint32_t kv, int
 	return simple_hit(C, kv, l, u, sub, tol, low, high);
 }
 
+__device__ __forceinline__ uint32_t ld_phase_any(const uint32_t *p, uint64_t pol)
+{
+	uint32_t v;
+	asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+	return v;
+}
+
+// One strand pass over the phase table of a gapped index (MODE 3; gap 3, sparse table; sr_common.cuh): the three lookups of a
+// subread share one 32-byte unit.  Per batch of ten subreads: (1) the units' occupancy bits are requested for all ten (32 MB
+// bitmap, L2-resident) -- a subread whose unit is empty has no hit in any phase; (2) a uniform loop over the subreads left
+// fetches each unit (the next one in flight while this one is applied), reads the two bits of each of the three keys and takes
+// the position of a key with a single one straight from the unit -- into the primary cluster P as in the other modes; (3) a
+// key with several positions, or beyond the unit's five values, or not of P's kv, goes through the general path by its lookup
+// number exactly as before.  The lookups are applied in schedule order (subread by subread, phase 0, 1, 2).
+template <bool RCKEYS>
+__device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
+                                                  SimpleClusters &C, int rc_len, uint32_t &n_gather)
+{
+	constexpr int GAP = 3, kSubs = 10;                             // ten subreads = thirty lookups per batch (the general path's bit mask)
+	const uint32_t low = cfg.low_border, high = cfg.high_border - (uint32_t)L;
+	const uint4 *units = reinterpret_cast<const uint4 *>(ix.phase_units);
+	const uint64_t pol = policy_evict_last();
+	C.n = 0;
+	if (C.cap < 1) return false;
+	SimpleCluster P;
+	P.kv = 0; P.w1 = 0; P.subs = 0;
+	bool have_p = false, ok = true;
+	for (int s_base = 0; s_base < applied; s_base += kSubs) {
+		const int n_sub = min(kSubs, applied - s_base), base = s_base * GAP;
+		// ---- (1) which units hold anything ----
+		unsigned mask = 0;
+#pragma unroll 1
+		for (int g = 0; g < n_sub; g += 5) {
+			uint32_t c[5], w[5];
+#pragma unroll
+			for (int u = 0; u < 5; u++) {
+				const int ob = simple_sub_offset<GAP>(s_base + min(g + u, n_sub - 1), step);
+				c[u] = simple_key_at<RCKEYS>(pk, ob, rc_len) & kPhaseMask;
+			}
+#pragma unroll
+			for (int u = 0; u < 5; u++) w[u] = ld_phase_any(ix.phase_any + (c[u] >> 5), pol);
+#pragma unroll
+			for (int u = 0; u < 5; u++) mask |= ((g + u < n_sub && ((w[u] >> (c[u] & 31u)) & 1u)) ? 1u : 0u) << (g + u);
+		}
+		// ---- (2) the subreads left: one unit each ----
+		unsigned defer = 0;
+		Record8 rn;
+		int si_next = -1, ob_next = 0;
+		uint32_t k0_next = 0, k1_next = 0, k2_next = 0;
+		auto issue = [&]() {
+			si_next = -1;
+			if (!mask) return;
+			si_next = __ffs(mask) - 1;
+			mask &= mask - 1;
+			ob_next = simple_sub_offset<GAP>(s_base + si_next, step);
+			k0_next = simple_key_at<RCKEYS>(pk, ob_next, rc_len);
+			k1_next = simple_key_at<RCKEYS>(pk, ob_next + 1, rc_len);
+			k2_next = simple_key_at<RCKEYS>(pk, ob_next + 2, rc_len);
+			rn = ld_record(units, k0_next & kPhaseMask);
+			n_gather++;
+		};
+		issue();
+		while (si_next >= 0) {
+			const Record8 r = rn;
+			const int si = si_next, ob = ob_next, sub = s_base + si;
+			const uint32_t k0 = k0_next, k1 = k1_next, k2 = k2_next;
+			issue();
+			const uint32_t c = k0 & kPhaseMask;
+			if (((k1 >> 2) & kPhaseMask) != c || (k2 >> 4) != c) {   // (the three keys do not overlap as a read's do: padding of a tiny read's reverse strand)
+				defer |= 7u << (3 * si);
+				continue;
+			}
+			const uint32_t p0 = r.w[0] & 0x55555555u, p1 = r.w[1] & 0x55555555u;
+#pragma unroll
+			for (int x = 0; x < 3; x++) {
+				const uint32_t key = x == 0 ? k0 : (x == 1 ? k1 : k2), v = phase_variant(key, x);
+				const uint32_t wx = x == 0 ? r.w[0] : (x == 1 ? r.w[1] : r.w[2]);
+				const uint32_t two = (wx >> (2 * v)) & 3u;
+				if (!(two & 1u)) continue;                               // the table does not hold this key
+				const int rank = __popc(wx & 0x55555555u & ((1u << (2 * v)) - 1u)) + (x > 0 ? __popc(p0) : 0) + (x > 1 ? __popc(p1) : 0);
+				const int li = 3 * si + x, l = base + li;
+				if ((two & 2u) || rank >= kPhaseValues) { defer |= 1u << li; continue; }
+				const uint32_t value = rank == 0 ? r.w[3] : (rank == 1 ? r.w[4] : (rank == 2 ? r.w[5] : (rank == 3 ? r.w[6] : r.w[7])));
+				const uint32_t kv = value - (uint32_t)(ob + x);
+				if (!have_p && C.n == 0) {                               // the first position of the pass founds P
+					if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
+					P = simple_new_cluster(kv, l, 0, sub, low, high);
+					have_p = true;
+					C.n = 1;
+				} else if (have_p && kv == P.kv) {                       // the plain branch :1041-1052
+					const unsigned long long bit = 1ull << sub;
+					if (P.w1 >> 31) {
+						if (P.subs & bit) ok = false;
+						P.subs |= bit;
+						P.w1 = (P.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);  // lookups come in increasing order here
+					}
+				} else
+					defer |= 1u << li;
+			}
+		}
+		if (!ok) return false;
+		// ---- (3) everything else, on the general path ----
+		if (defer) {
+			if (__popc(defer) > SR_SIMPLE_DEFER_LIMIT) return false;
+			if (have_p) C.put(0, P);
+			if (!simple_general<GAP, RCKEYS>(ix, cfg, pk, step, rc_len, base, defer, C, low, high, n_gather)) return false;
+			if (have_p) P = C.get(0);
+		}
+	}
+	if (have_p) C.put(0, P);
+#pragma unroll 1
+	for (int c = 0; c < C.n; c++) {
+		C.w(c, 2) = (uint32_t)C.votes(c);
+		C.w(c, 3) = 0u;
+	}
+	return true;
+}
+
+// The same over the 128-byte units of a dense table (MODE 4; sr_common.cuh).  No unit is empty, so every subread's unit is
+// fetched: one uniform loop over the subreads of a batch, the next unit's first 32 bytes (the 2-bit codes and four values) in
+// flight while this one is applied; the other values of the unit come from the same 64-byte fetch.  As in MODE 2, every single
+// position goes through the cluster list at once and the keys with several positions (their value is the rank of their
+// direct_first entry) wait in registers for the flat loop over their runs.
+template <bool RCKEYS>
+__device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
+                                                        SimpleClusters &C, int rc_len, uint32_t &n_gather)
+{
+	constexpr int GAP = 3, kSubs = 10;
+	const int tol = cfg.indel_tolerance;
+	const uint32_t low = cfg.low_border, high = cfg.high_border - (uint32_t)L;
+	const uint4 *units4 = reinterpret_cast<const uint4 *>(ix.phase_dense);
+	C.n = 0;
+	if (C.cap < 1) return false;
+	bool ok = true;
+	for (int s_base = 0; s_base < applied && ok; s_base += kSubs) {
+		const int n_sub = min(kSubs, applied - s_base), base = s_base * GAP;
+		uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // runs of keys with several positions waiting to be applied:
+		uint32_t me0 = 0, me1 = 0, me2 = 0, me3 = 0;     // first item in vals[];  h | landing << 8 | lookup << 16
+		int ne = 0;
+		unsigned slow = 0;                               // lookups the unit could not answer (value beyond its 28, a fifth run): the direct filter does
+		Record8 rn;
+		int ob_next = 0;
+		uint32_t k0_next = 0, k1_next = 0, k2_next = 0;
+		auto issue = [&](int si) {
+			ob_next = simple_sub_offset<GAP>(s_base + min(si, n_sub - 1), step);
+			k0_next = simple_key_at<RCKEYS>(pk, ob_next, rc_len);
+			k1_next = simple_key_at<RCKEYS>(pk, ob_next + 1, rc_len);
+			k2_next = simple_key_at<RCKEYS>(pk, ob_next + 2, rc_len);
+			rn = ld_record(units4, 4u * (k0_next & kPhaseMask));         // (ld_record counts in 32-byte records: a unit is four)
+			n_gather++;
+		};
+		issue(0);
+#pragma unroll 1
+		for (int si = 0; si < n_sub; si++) {
+			const Record8 r = rn;
+			const int ob = ob_next, sub = s_base + si;
+			const uint32_t k0 = k0_next, k1 = k1_next, k2 = k2_next;
+			if (si + 1 < n_sub) issue(si + 1);
+			const uint32_t c = k0 & kPhaseMask;
+			if (((k1 >> 2) & kPhaseMask) != c || (k2 >> 4) != c) { slow |= 7u << (3 * si); continue; }
+			const uint32_t p0 = r.w[0] & 0x55555555u, p1 = r.w[1] & 0x55555555u;
+#pragma unroll
+			for (int x = 0; x < 3; x++) {
+				const uint32_t key = x == 0 ? k0 : (x == 1 ? k1 : k2), v = phase_variant(key, x);
+				const uint32_t wx = x == 0 ? r.w[0] : (x == 1 ? r.w[1] : r.w[2]);
+				const uint32_t two = (wx >> (2 * v)) & 3u;
+				if (!(two & 1u)) continue;
+				const int rank = __popc(wx & 0x55555555u & ((1u << (2 * v)) - 1u)) + (x > 0 ? __popc(p0) : 0) + (x > 1 ? __popc(p1) : 0);
+				const int li = 3 * si + x, l = base + li;
+				if (rank >= kPhaseDenseValues) { slow |= 1u << li; continue; }
+				uint32_t value;
+				if (rank < 4) value = rank == 0 ? r.w[4] : (rank == 1 ? r.w[5] : (rank == 2 ? r.w[6] : r.w[7]));
+				else {
+					value = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);       // same unit: as a rule the 64 bytes already fetched
+					if (rank >= 12) n_gather++;                                                    // (the unit's second half: another fetch)
+				}
+				if (!(two & 2u)) { if (!simple_hit(C, value - (uint32_t)(ob + x), l, 0, sub, tol, low, high)) ok = false; }
+				else {
+					const uint2 entry = ld_direct_first(ix, value);
+					n_gather++;
+					const uint32_t me = (entry.y & 0xffffu) | ((uint32_t)l << 16);
+					if ((entry.y & 255u) > (uint32_t)C.cap) ok = false;       // cannot stay separable
+					else if (ne == 0) { ra0 = entry.x; me0 = me; ne = 1; }
+					else if (ne == 1) { ra1 = entry.x; me1 = me; ne = 2; }
+					else if (ne == 2) { ra2 = entry.x; me2 = me; ne = 3; }
+					else if (ne == 3) { ra3 = entry.x; me3 = me; ne = 4; }
+					else slow |= 1u << li;
+				}
+			}
+		}
+		if (!ok) return false;
+		// the keys with several positions: one flat loop over all their positions in the reference's visit order; then, one by
+		// one, what the units left open (through the direct filter, as MODE 2 would)
+		while ((ne || slow) && ok) {
+#pragma unroll 1
+			while (slow && ne < 4 && ok) {
+				const int i = __ffs(slow) - 1;
+				slow &= slow - 1;
+				const int l = base + i;
+				int sub;
+				const int o = simple_offset<GAP>(l, step, &sub);
+				const uint32_t key = simple_key_at<RCKEYS>(pk, o, rc_len);
+				const uint32_t u = direct_unit(key);
+				uint32_t bits;
+				const uint32_t rank = direct_rank(ld_direct_unit(ix, u), key, u, &bits);
+				n_gather++;
+				if (!bits) continue;
+				const uint2 entry = ld_direct_first(ix, rank);
+				n_gather++;
+				if (bits == 1u) { if (!simple_hit(C, entry.x - (uint32_t)o, l, 0, sub, tol, low, high)) ok = false; continue; }
+				const uint32_t me = (entry.y & 0xffffu) | ((uint32_t)l << 16);
+				if ((entry.y & 255u) > (uint32_t)C.cap) { ok = false; break; }
+				if (ne == 0) { ra0 = entry.x; me0 = me; } else if (ne == 1) { ra1 = entry.x; me1 = me; } else if (ne == 2) { ra2 = entry.x; me2 = me; } else { ra3 = entry.x; me3 = me; }
+				ne++;
+			}
+			int e = 0, u = 0;
+#pragma unroll 1
+			while (e < ne && ok) {
+				const uint32_t ra = e == 0 ? ra0 : (e == 1 ? ra1 : (e == 2 ? ra2 : ra3)), me = e == 0 ? me0 : (e == 1 ? me1 : (e == 2 ? me2 : me3));
+				const int h = (int)(me & 255u), land = (int)((me >> 8) & 255u), l = (int)(me >> 16);
+				if (u >= h) { e++; u = 0; continue; }
+				const int nfwd = h - land;                               // landing .. end of run, then landing-1 .. start (:1109-1119)
+				const int idx = u < nfwd ? land + u : land - 1 - (u - nfwd);
+				const uint32_t v = ld_gather(ix.vals + ra + idx);
+				n_gather++;
+				int sub;
+				const int o = simple_offset<GAP>(l, step, &sub);
+				if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) { ok = false; break; }
+				u++;
+			}
+			ne = 0;
+		}
+	}
+	if (!ok) return false;
+#pragma unroll 1
+	for (int c = 0; c < C.n; c++) {
+		C.w(c, 2) = (uint32_t)C.votes(c);
+		C.w(c, 3) = 0u;
+	}
+	return true;
+}
+
 template <int GAP, int MODE, bool RCKEYS = false>
 __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
                                             SimpleClusters &C, int rc_len, uint32_t &n_gather, bool have_first_mask = false, unsigned first_mask = 0u)
 {
+	if (MODE == 3) return simple_pass_phase<RCKEYS>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather);
+	if (MODE == 4) return simple_pass_phase_dense<RCKEYS>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather);
 	constexpr bool DIRECT = MODE == 2;
 	constexpr int kSubsPerBatch = 32 / GAP;                        // whole subreads per batch of <= 32 lookups
 	const uint32_t nb = ix.buckets_number;
@@ -646,6 +927,9 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 			}
 			if (!ok) return false;
 		} else if (defer) {
+			// A lane on the general path holds up its warp: beyond a few lookups the fragment is better off in the warp kernel
+			// (an indel splits the hits over two kv, a repeat answers every lookup with several positions)
+			if (__popc(defer) > SR_SIMPLE_DEFER_LIMIT) return false;
 			if (have_p) C.put(0, P);
 			if (!simple_general<GAP, RCKEYS>(ix, cfg, pk, step, rc_len, base, defer, C, low, high, n_gather)) return false;
 			if (have_p) P = C.get(0);
@@ -860,7 +1144,7 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 
 	// ---- 1b. pack both strands ----
 	const bool run = active && !punt && L >= 16;
-	if (run && !simple_pack(stage, so, L, pk, n_words)) punt = true;
+	if (run && !simple_pack<true, !JUNC>(stage, so, L, pk, n_words)) punt = true;      // (subjunc compares 2-bit codes with the genome: no Ns there)
 	__syncwarp();   // the staging area becomes the cluster store
 
 	// ---- 2./3. two strand passes ----

@@ -105,7 +105,9 @@ def test_full_size_properties(paired, n_frags, world, oracle_mod):
     d_text, truth = make_reads(w, n_frags, paired, 4242 + int(paired))
     whole = run_device(w, w["mapper"], params, d_text, 0, n_frags, paired)
     t = w["mapper"].timing()
-    assert t.n_simple_punted == 0 and t.n_overflow == 0, "error-free reads of a random genome stay in tier 0"
+    # error-free reads of a random genome stay in the fast tier -- but for the few with more than SR_SIMPLE_DEFER_LIMIT chance hits
+    # in a batch, which are handed to the warp kernel rather than holding up their warp (0.8 % at 150 bp on 100 Mbp)
+    assert t.n_simple_punted < n_frags // 50 and t.n_overflow == 0, f"the fast tier queued {t.n_simple_punted} of {n_frags}"
     out = np.frombuffer(whole.cpu().numpy().tobytes(), dtype=MAPPING_RESULT).reshape(n_frags, mates, mb)
     tr = truth.cpu().numpy()
     # every read maps to its own position with all ten subreads (one of the three phases of each hits the gapped index)

@@ -265,7 +265,7 @@ def test_subjunc_junction_voting(name, mapper, golden_cases, golden_index_dir, o
     assert (js["big_margin"] == jo["big_margin"]).all()
 
 
-@pytest.mark.parametrize("kind", ["uniform", "repeats", "full", "dense", "dense_repeats"])
+@pytest.mark.parametrize("kind", ["uniform", "repeats", "full", "dense", "dense_repeats", "dense_gapped", "dense_gapped_repeats"])
 def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_path):
     """Tier 0 (k_map_simple, one thread per fragment) only runs for single-end chunks on a zero bigtable without
     verification -- the shape of the bench.  2 Mbp genome (uniform / repeat-rich / full index); error-free reads,
@@ -280,13 +280,25 @@ def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_pa
     fa = str(tmp_path / "g.fa")
     gen_data.write_genome(fa, 4, 500000, seed=91, repeats=600 if kind.endswith("repeats") else 0)
     prefix = str(tmp_path / "idx")
-    if kind.startswith("dense"):
+    own = None
+    if "gapped" in kind:
+        # a gapped index with the dense-table accelerators forced onto it (SRCUDA_ACCEL=4): direct filter + the 128-byte phase
+        # units, the thread-per-fragment tier's mode 4 -- what a human-sized gapped index gets by itself
+        build_index(fa, prefix, gapped=True, use_gpu=True)
+        os.environ["SRCUDA_ACCEL"] = "4"
+        try:
+            own = mapper = Mapper(0)
+        finally:
+            del os.environ["SRCUDA_ACCEL"]
+    elif kind.startswith("dense"):
         # 2 M items in 262 147 buckets (7.6 per bucket, the shape of a human-sized table): the direct filter is chosen
         build_index(fa, prefix, gapped=False, buckets=262147, use_gpu=True)
     else:
         build_index(fa, prefix, gapped=(kind != "full"), use_gpu=True)
     mapper.index_load(prefix, 0)
-    assert mapper.describe().accelerators == (4 if kind.startswith("dense") else 3), "direct filter on dense tables only"
+    acc = mapper.describe().accelerators
+    assert acc & 7 == (4 if kind.startswith("dense") else 3), "direct filter on dense tables only"
+    assert bool(acc & 16) == (kind in ("uniform", "repeats", "dense_gapped", "dense_gapped_repeats")), "phase table on gapped indexes only"
     idx = oracle_mod.OracleIndex(prefix)
     params = VoteParams.defaults(False)
     gen_data.write_reads(fa, str(tmp_path / "clean"), 40000, 150, 3, False, 0.0, 0.0, False, 0.0)
@@ -347,6 +359,8 @@ def test_tier0_single_end_chunks_against_oracle(kind, mapper, oracle_mod, tmp_pa
         if name in ("clean", "scattered") and not kind.endswith("repeats"):
             assert t.n_simple_punted < chunk.n_frags // 20, f"{name}: tier 0 punted {t.n_simple_punted} of {chunk.n_frags}"
     plain.close()
+    if own is not None:
+        own.close()
 
 
 @pytest.mark.parametrize("force", [False, True], ids=["auto", "forced_on_sparse"])
@@ -371,7 +385,7 @@ def test_direct_filter_warp_kernel_pe_and_se(force, oracle_mod, tmp_path):
     finally:
         os.environ.pop("SRCUDA_ACCEL", None)
     m.index_load(prefix, 0)
-    assert m.describe().accelerators == 4
+    assert m.describe().accelerators & 7 == 4
     idx = oracle_mod.OracleIndex(prefix)
     gen_data.write_reads(fa, str(tmp_path / "se"), 20000, 150, 1, False, 0.01, 0.1, False, 0.001)
     gen_data.write_reads(fa, str(tmp_path / "pe"), 15000, 100, 2, True, 0.01, 0.1, True, 0.001)
@@ -389,7 +403,7 @@ def test_direct_filter_warp_kernel_pe_and_se(force, oracle_mod, tmp_path):
     m.close()
 
 
-@pytest.mark.parametrize("kind", ["uniform", "repeats", "dense"])
+@pytest.mark.parametrize("kind", ["uniform", "repeats", "dense", "dense_gapped"])
 def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
     """The paired-end form of tier 0 (k_map_simple_pe: one thread per fragment, pair scoring per thread) on a zero
     bigtable: clean, noisy (errors, indels, Ns, mixed lengths) and short pairs, pairs with odd mates (shorter than 16
@@ -407,7 +421,12 @@ def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
         build_index(fa, prefix, gapped=False, buckets=262147, use_gpu=True)
     else:
         build_index(fa, prefix, gapped=True, use_gpu=True)
-    tier = Mapper(0)
+    if kind == "dense_gapped":
+        os.environ["SRCUDA_ACCEL"] = "4"                  # dense accelerators on a gapped index: the 128-byte phase units (mode 4)
+    try:
+        tier = Mapper(0)
+    finally:
+        os.environ.pop("SRCUDA_ACCEL", None)
     tier.index_load(prefix, 0)
     os.environ["SRCUDA_SIMPLE_TIER_PE"] = "0"
     try:

@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 STOCK = os.path.join(REF_DIR, "bin", "subread-align")
 CUDA = os.path.join(REF_DIR, "subread-align-cuda")
+BUILDINDEX = os.path.join(REF_DIR, "bin", "subread-buildindex")
 
 
 def sam_body(path):
@@ -26,11 +27,11 @@ def sam_body(path):
 def test_sam_identical_to_stock_subread_align(kind, paired, threads, tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_data
-    from subread_b200.index_build import build_index
     fa = str(tmp_path / "g.fa")
     gen_data.write_genome(fa, 4, 400000, seed=31, repeats=500 if kind == "repeats" else 0)
     prefix = str(tmp_path / "idx")
-    build_index(fa, prefix, gapped=True, use_gpu=True)
+    # the index both binaries read is the reference builder's own (a defect of this repository's builder must not cancel out)
+    subprocess.run([BUILDINDEX, "-B", "-o", prefix, fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     gen_data.write_reads(fa, str(tmp_path / "r"), 20000, 120, 9, paired, 0.01, 0.15, True, 0.002)
     reads = ["-r", str(tmp_path / "r_R1.fastq")] + (["-R", str(tmp_path / "r_R2.fastq")] if paired else [])
     outs = []
