@@ -16,9 +16,11 @@
  *
  * Threading: run_maybe_threads (core.c:3379) starts config.all_threads workers that all enter
  * do_voting.  Worker 0 reads the whole chunk through the reference's own fetch_next_read_pair and
- * makes ONE srcuda_vote_chunk call that writes straight into the bigtable
- * (bigtable_cache_malloc_ptr has exactly the out_align layout); then all workers share the
- * per-read tail of do_voting (find_new_indels / find_new_junctions, core.c:3241-3290).
+ * makes ONE srcuda_vote_chunk_multi call -- the chunk spread over the GPUs of SRCUDA_DEVICES -- that
+ * writes straight into the bigtable (bigtable_cache_malloc_ptr has exactly the out_align layout,
+ * bigtable_cache_malloc_ptr_junc the out_junc one); then all workers share the per-read tail of
+ * do_voting (find_new_indels / find_new_junctions, core.c:3241-3290).  subjunc (do_breakpoint_detection)
+ * is bound as well, for reads up to 160 bases.
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -36,18 +38,47 @@
 
 #include "../include/subread_cuda.h"
 
-static srcuda_handle *g_handle = NULL;
+/* Everything the binding keeps between calls, in one place (the reference itself runs one global_context_t per process).
+ * SRCUDA_DEVICES=0,1,... lists the GPUs to use (default: SRCUDA_DEVICE or device 0): the index block is loaded once and
+ * replicated to the others over NVLink (srcuda_index_load_all), every chunk is cut into one contiguous slice per GPU
+ * (srcuda_vote_chunk_multi). */
+#define BINDING_MAX_GPUS 16
+typedef struct {
+	srcuda_handle *handles[BINDING_MAX_GPUS];
+	int n_handles;
+	int opened;
+} binding_gpus_t;
 
-static srcuda_handle *cuda_handle(void)
+static binding_gpus_t g_gpus;
+
+static binding_gpus_t *cuda_handles(void)
 {
-	if (!g_handle) {
-		const char *dev = getenv("SRCUDA_DEVICE");
-		if (srcuda_open(dev ? atoi(dev) : 0, &g_handle)) {
-			SUBREADprintf("ERROR: cannot open a CUDA device: %s\n", srcuda_last_error(NULL));
-			g_handle = NULL;
+	binding_gpus_t *b = &g_gpus;
+	if (b->opened) return b->n_handles ? b : NULL;
+	b->opened = 1;
+	int devs[BINDING_MAX_GPUS], n = 0;
+	const char *list = getenv("SRCUDA_DEVICES"), *one = getenv("SRCUDA_DEVICE");
+	if (list && *list) {
+		const char *p = list;
+		while (*p && n < BINDING_MAX_GPUS) {
+			char *end;
+			long d = strtol(p, &end, 10);
+			if (end == p) break;
+			devs[n++] = (int)d;
+			p = *end == ',' ? end + 1 : end;
 		}
 	}
-	return g_handle;
+	if (!n) devs[n++] = one ? atoi(one) : 0;
+	for (int k = 0; k < n; k++) {
+		if (srcuda_open(devs[k], &b->handles[b->n_handles])) {
+			SUBREADprintf("ERROR: cannot open CUDA device %d: %s\n", devs[k], srcuda_last_error(NULL));
+			for (int j = 0; j < b->n_handles; j++) srcuda_close(b->handles[j]);
+			b->n_handles = 0;
+			return NULL;
+		}
+		b->n_handles++;
+	}
+	return b;
 }
 
 /* ---- gehash_load: the block goes to HBM instead of host memory -------------------------------- */
@@ -64,9 +95,10 @@ int gehash_load(gehash_t *the_table, const char fname[])
 	strncpy(prefix, fname, sizeof(prefix) - 1);
 	prefix[n - 9] = 0;
 	int block_no = atoi(fname + n - 8);
-	srcuda_handle *h = cuda_handle();
-	if (!h) return 1;
-	if (srcuda_index_load(h, prefix, block_no)) {
+	binding_gpus_t *g = cuda_handles();
+	if (!g) return 1;
+	srcuda_handle *h = g->handles[0];
+	if (srcuda_index_load_all(g->handles, g->n_handles, prefix, block_no)) {
 		SUBREADprintf("ERROR: %s\n", srcuda_last_error(h));
 		return 1;
 	}
@@ -131,7 +163,7 @@ static subread_read_number_t g_n_frags = 0;
 
 static int unsupported_mode(global_context_t *gc)
 {
-	return gc->config.do_breakpoint_detection || gc->config.do_fusion_detection || gc->config.do_long_del_detection ||
+	return gc->config.do_fusion_detection || gc->config.do_long_del_detection ||
 	       gc->config.is_methylation_reads || gc->config.space_type != GENE_SPACE_BASE || gc->config.scRNA_input_mode ||
 	       gc->config.SAM_extra_columns;
 }
@@ -173,11 +205,42 @@ static int vote_chunk_on_gpu(global_context_t *gc, thread_context_t *tc)
 	p.maximum_pair_distance = gc->config.maximum_pair_distance;
 	p.is_first_read_reversed = 0;  /* fetch_next_read_pair already oriented both mates (core.c:1187-1199) */
 	p.is_second_read_reversed = 0;
-	srcuda_handle *h = cuda_handle();
-	if (!h) return 1;
-	int rc = srcuda_vote_chunk(h, &p, c->text, c->off, c->len, (int64_t)g_n_frags, is_paired,
-	                           gc->current_index_block_number == 0, (srcuda_mapping_result *)gc->bigtable_cache_malloc_ptr, NULL, NULL, NULL);
-	if (rc) SUBREADprintf("ERROR: srcuda_vote_chunk: %s\n", srcuda_last_error(h));
+	/* subjunc: the junction half of copy_vote_to_alignment_res (core-junction.c:1073-1334) runs on the GPU too */
+	p.do_breakpoint_detection = gc->config.do_breakpoint_detection;
+	p.do_big_margin_filtering_for_junctions = gc->config.do_big_margin_filtering_for_junctions;
+	p.big_margin_record_size = gc->config.big_margin_record_size;
+	p.maximum_intron_length = (int32_t)gc->config.maximum_intron_length;
+	p.limited_tree_scan = gc->config.limited_tree_scan;
+	p.check_donor_at_junctions = gc->config.check_donor_at_junctions;
+	p.more_accurate_fusions = gc->config.more_accurate_fusions && gc->config.do_fusion_detection;
+	p.max_insertion_at_junctions = gc->config.max_insertion_at_junctions;
+	p.prefer_donor_receptor_junctions = gc->config.prefer_donor_receptor_junctions;
+	binding_gpus_t *g = cuda_handles();
+	if (!g) return 1;
+	srcuda_subjunc_result *junc = NULL;
+	uint16_t *bm = NULL;
+	const int first_block = gc->current_index_block_number == 0;
+	if (p.do_breakpoint_detection) {
+		/* reads beyond 160 bases also feed core_fragile_junction_voting (core.c:3138), which walks the HOST hash table this binding
+		 * never loads: say so instead of mapping them differently */
+		for (size_t r = 0; r < c->n_reads; r++)
+			if (c->len[r] > EXON_LONG_READ_LENGTH) {
+				SUBREADprintf("ERROR: subjunc reads longer than %d bases need core_fragile_junction_voting on the host index; not supported by this binding.\n", EXON_LONG_READ_LENGTH);
+				return 1;
+			}
+		junc = (srcuda_subjunc_result *)gc->bigtable_cache_malloc_ptr_junc;
+		/* the big-margin records live inside bigtable_cached_result_t, one per read: gathered into the dense [read][27] layout of the
+		 * C ABI and scattered back */
+		bm = malloc(sizeof(uint16_t) * 27 * c->n_reads);
+		for (size_t r = 0; r < c->n_reads; r++) memcpy(bm + 27 * r, gc->bigtable_cache[r].big_margin_data, sizeof(uint16_t) * 27);
+	}
+	int rc = srcuda_vote_chunk_multi(g->handles, g->n_handles, &p, c->text, c->off, c->len, (int64_t)g_n_frags, is_paired, first_block,
+	                                 (srcuda_mapping_result *)gc->bigtable_cache_malloc_ptr, junc, bm, NULL);
+	if (rc) SUBREADprintf("ERROR: srcuda_vote_chunk_multi: %s\n", srcuda_last_error(g->handles[0]));
+	if (bm) {
+		if (!rc) for (size_t r = 0; r < c->n_reads; r++) memcpy(gc->bigtable_cache[r].big_margin_data, bm + 27 * r, sizeof(uint16_t) * 27);
+		free(bm);
+	}
 	return rc;
 }
 
@@ -224,13 +287,11 @@ static void discover_events(global_context_t *gc, thread_context_t *tc, subread_
 int do_voting(global_context_t *gc, thread_context_t *tc)
 {
 	if (unsupported_mode(gc)) {
-		/* modes the GPU library refuses (subjunc, fusion, methylation, colour space ...): the
-		 * reference's own do_voting, loudly */
-		static int (*orig)(global_context_t *, thread_context_t *) = NULL;
+		/* modes the GPU library refuses (fusion, long deletions, methylation, colour space ...): refused loudly -- the host hash
+		 * table is not loaded by this binding, so there is no CPU do_voting to fall back to */
 		static int told = 0;
-		if (!orig) orig = (int (*)(global_context_t *, thread_context_t *))dlsym(RTLD_NEXT, "do_voting");
-		if (!told) { told = 1; SUBREADprintf("NOTICE: this mode is not supported by libsubread_cuda; using the reference's CPU do_voting.\n"); }
-		return orig(gc, tc);
+		if (!told) { told = 1; SUBREADprintf("ERROR: this mode is not supported by libsubread_cuda (fusion / long-deletion detection, methylation, colour space, scRNA, --extraColumns).\n"); }
+		return -1;
 	}
 	int n_threads = tc ? gc->config.all_threads : 1;
 	int me = tc ? tc->thread_id : 0;

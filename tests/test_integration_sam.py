@@ -42,3 +42,31 @@ def test_sam_identical_to_stock_subread_align(kind, paired, threads, tmp_path):
         outs.append(sam_body(out))
     assert len(outs[0]) > 1000
     assert outs[0] == outs[1]
+
+
+SUBJUNC = os.path.join(REF_DIR, "bin", "subjunc")
+SUBJUNC_CUDA = os.path.join(REF_DIR, "subjunc-cuda")
+FIX = os.path.join(REF_DIR, "fixtures")
+
+
+@pytest.mark.skipif(not (os.path.exists(SUBJUNC) and os.path.exists(SUBJUNC_CUDA) and os.path.exists(os.path.join(FIX, "chr901.fa"))),
+                    reason="oracle/_ref binaries or fixtures not built")
+@pytest.mark.parametrize("devices", ["0", "0,0"], ids=["one_handle", "two_handles"])
+def test_subjunc_sam_identical_to_stock_subjunc(devices, tmp_path):
+    """subjunc through the binding (do_breakpoint_detection: junction tables and big-margin records from the GPU, find_new_junctions
+    and everything after it the reference's own host code) on the reference's junction fixture, the command of
+    test/subjunc/subjunc-test.sh: SAM and the junction table (.junction.bed) byte-identical to the stock subjunc's.  With
+    SRCUDA_DEVICES=0,0 the chunk is split over two handles (srcuda_vote_chunk_multi behind the reference's CLI)."""
+    prefix = str(tmp_path / "small1")
+    subprocess.run([BUILDINDEX, "-o", prefix, os.path.join(FIX, "chr901.fa")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    outs = []
+    for exe, tag in ((SUBJUNC, "stock"), (SUBJUNC_CUDA, "cuda")):
+        out = str(tmp_path / f"{tag}.sam")
+        subprocess.run([exe, "-T", "4", "-i", prefix, "-r", os.path.join(FIX, "junction-reads-A.fq"), "-R", os.path.join(FIX, "junction-reads-B.fq"),
+                        "--SAMoutput", "-o", out], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=dict(os.environ, SRCUDA_DEVICES=devices))
+        bed = out + ".junction.bed"
+        outs.append((sam_body(out), open(bed, "rb").read() if os.path.exists(bed) else None))
+    assert len(outs[0][0]) > 100000
+    assert outs[0][0] == outs[1][0], "SAM records differ"
+    assert outs[0][1] is not None and outs[0][1] == outs[1][1], "junction tables differ"
+    assert outs[0][1].count(b"\n") > 10
