@@ -131,6 +131,7 @@ typedef struct {
 	uint64_t n_gather_requests; /* random index fetches the one-thread-per-fragment tier issued that miss L2 by construction (bucket
 	                             * records, direct-filter words, direct_first entries, positions): one DRAM line each, the numerator
 	                             * of the line-rate ("HBM-gather") roofline.  The Bloom words (L2-resident) are not counted. */
+	uint64_t n_simple_indel;    /* single-end fragments whose result came from that tier's one-indel closed form */
 } srcuda_timing;
 
 /* ---- life cycle ------------------------------------------------------------------------ */
@@ -315,6 +316,8 @@ int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out);
  *   SRCUDA_SIMPLE_TIER [1]     thread-per-fragment tier (single- and paired-end)
  *   SRCUDA_SIMPLE_TIER_PE [1]  its paired-end form only
  *   SRCUDA_TIER_JUNC [1]       subjunc chunks in that tier
+ *   SRCUDA_TIER_INDEL [auto]   its one-indel closed form: 0 never, 1 always, unset: by the last call's counters
+ *   SRCUDA_PHASE [1]           the phase table of gapped indexes
  *   SRCUDA_WARP_JUNC [1]       subjunc fragments in the warp kernel (0: scalar path)
  *   SRCUDA_ACCEL [auto]        lookup accelerators: 0 none, 1 Bloom words, 2 bucket records, 3 both, 4 direct filter
  *   SRCUDA_BATCH_FRAGS, SRCUDA_SCALAR_BLOCKS, SRCUDA_L2_PERSIST, SRCUDA_L2_FETCH   tuning knobs */

@@ -53,7 +53,7 @@ class Timing(ctypes.Structure):
         ("n_overflow", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
         ("n_launches", ctypes.c_uint32), ("n_batches", ctypes.c_uint32),
         ("ms_kernel_simple", ctypes.c_float), ("_pad", ctypes.c_uint32), ("n_simple_punted", ctypes.c_uint64),
-        ("n_gather_requests", ctypes.c_uint64),
+        ("n_gather_requests", ctypes.c_uint64), ("n_simple_indel", ctypes.c_uint64),
     ]
 
 

@@ -439,6 +439,11 @@ struct srcuda_handle {
 	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
 	void *d_records = nullptr, *d_bloom = nullptr, *d_direct = nullptr, *d_direct_first = nullptr, *d_phase_any = nullptr, *d_phase_units = nullptr, *d_phase_dense = nullptr;
 	bool use_phase = true;         // SRCUDA_PHASE=0: no phase table for gapped sparse indexes (A/B and cross-checks)
+	// The single-end tier's one-indel closed form costs an error-free chunk 13 %, so it is launched only while the chunks hold such
+	// reads: after every call, from that call's counters (fragments queued + fragments it settled) -- the results are the same either way.
+	int tier_indel_mode = -1;      // SRCUDA_TIER_INDEL: 0 never, 1 always, unset: by the last call
+	bool tier_indel = false;
+	int simple_indel_smem_set[4][5] = {}, simple_rmw_indel_smem_set[4][5] = {};
 	int accel_mode = -1;  // -1 auto, 0 off, 1 bloom only, 2 records only, 3 both, 4 direct filter (SRCUDA_ACCEL)
 	bool l2_persist = true;        // keep the Bloom words resident in L2 (SRCUDA_L2_PERSIST=0 turns it off)
 	size_t l2_persist_max = 0, l2_window_max = 0;
@@ -778,6 +783,28 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		                                                                           clusters, a.out, q0, bs.counters + 2,            \
 		                                                                           a.bad_reads, bs.counters + 3);                                    \
 	} while (0)
+#define SR_LAUNCH_SIMPLE_UI(G, U)                                                                                                    \
+	do {                                                                                                                             \
+		if (smem > h->simple_indel_smem_set[G][U]) {                                                                                 \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			h->simple_indel_smem_set[G][U] = smem;                                                                                   \
+		}                                                                                                                            \
+		sr::k_map_simple<G, U, false, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,        \
+		                                                                            a.text_bytes, a.off, a.len, a.n_frags, max_len,   \
+		                                                                            clusters, a.out, q0, bs.counters + 2, a.bad_reads,\
+		                                                                            bs.counters + 3, nullptr, nullptr, bs.counters + 4); \
+	} while (0)
+#define SR_LAUNCH_SIMPLE_RI(G, U)                                                                                                    \
+	do {                                                                                                                             \
+		if (smem > h->simple_rmw_indel_smem_set[G][U]) {                                                                             \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			h->simple_rmw_indel_smem_set[G][U] = smem;                                                                               \
+		}                                                                                                                            \
+		sr::k_map_simple<G, U, false, true, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,         \
+		                                                                           a.text_bytes, a.off, a.len, a.n_frags, max_len,    \
+		                                                                           clusters, a.out, q0, bs.counters + 2, a.bad_reads, \
+		                                                                           bs.counters + 3, nullptr, nullptr, bs.counters + 4); \
+	} while (0)
 #define SR_LAUNCH_SIMPLE_J(G, U)                                                                                                     \
 	do {                                                                                                                             \
 		const int jsmem = sr::simple_junc_smem_bytes(max_len, clusters);                                                              \
@@ -796,8 +823,10 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			else SR_LAUNCH_SIMPLE_J(G, 0);                                                                                           \
 		} else if (!a.out_zero) {                                                                                                    \
 			if (h->ix.direct) SR_LAUNCH_SIMPLE_R(G, 2);                                                                              \
+			else if (h->tier_indel) SR_LAUNCH_SIMPLE_RI(G, 0);                                                                       \
 			else SR_LAUNCH_SIMPLE_R(G, 0);                                                                                           \
 		} else if (h->ix.direct) SR_LAUNCH_SIMPLE_U(G, 2);                                                                           \
+		else if (h->tier_indel) SR_LAUNCH_SIMPLE_UI(G, 0);                                                                           \
 		else SR_LAUNCH_SIMPLE_U(G, 0);                                                                                               \
 	} while (0)
 		switch (h->ix.index_gap) {
@@ -806,7 +835,8 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 		default:
 			if (h->ix.phase_units) {                     // gapped index with a phase table: mode 3 (sparse table), mode 4 (dense)
 				if (cfg.do_junctions) SR_LAUNCH_SIMPLE_J(3, 3);
-				else if (!a.out_zero) SR_LAUNCH_SIMPLE_R(3, 3);
+				else if (!a.out_zero) { if (h->tier_indel) SR_LAUNCH_SIMPLE_RI(3, 3); else SR_LAUNCH_SIMPLE_R(3, 3); }
+				else if (h->tier_indel) SR_LAUNCH_SIMPLE_UI(3, 3);
 				else SR_LAUNCH_SIMPLE_U(3, 3);
 			} else if (h->ix.phase_dense) {
 				if (cfg.do_junctions) SR_LAUNCH_SIMPLE_J(3, 4);
@@ -816,6 +846,8 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			break;
 		}
 #undef SR_LAUNCH_SIMPLE_U
+#undef SR_LAUNCH_SIMPLE_UI
+#undef SR_LAUNCH_SIMPLE_RI
 #undef SR_LAUNCH_SIMPLE_R
 #undef SR_LAUNCH_SIMPLE_J
 #undef SR_LAUNCH_SIMPLE
@@ -946,7 +978,7 @@ int init_sets(srcuda_handle *h)
 		BatchSet &b = h->set[i];
 		if (b.stream) continue;
 		CU(h, cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
-		CU(h, cudaMalloc((void **)&b.counters, 4 * sizeof(uint32_t)));
+		CU(h, cudaMalloc((void **)&b.counters, 8 * sizeof(uint32_t)));
 	}
 	if (!h->ev_begin) {
 		CU(h, cudaEventCreate(&h->ev_begin));
@@ -955,6 +987,16 @@ int init_sets(srcuda_handle *h)
 	}
 	apply_l2_policy(h);
 	return 0;
+}
+
+// Which form of the single-end tier the next call launches (see srcuda_handle::tier_indel): the one-indel closed form once more
+// than 3 % of a call's fragments were either queued for the warp kernel or settled by that form, back to the lean form below 1.5 %.
+void update_tier_policy(srcuda_handle *h, const sr::VoteConfig &cfg, int64_t n_frags)
+{
+	if (h->tier_indel_mode >= 0 || cfg.is_paired || cfg.do_junctions || n_frags < 1000 || h->timing.ms_kernel_simple <= 0) return;
+	const double f = (double)(h->timing.n_simple_punted + h->timing.n_simple_indel) / (double)n_frags;
+	if (f > 0.03) h->tier_indel = true;
+	else if (f < 0.015) h->tier_indel = false;
 }
 
 }  // namespace
@@ -994,6 +1036,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (st && st[0] == '0') h->use_simple_tier = false;
 	const char *ph = getenv("SRCUDA_PHASE");
 	if (ph && ph[0] == '0') h->use_phase = false;
+	const char *ti = getenv("SRCUDA_TIER_INDEL");
+	if (ti && (ti[0] == '0' || ti[0] == '1')) { h->tier_indel_mode = ti[0] - '0'; h->tier_indel = ti[0] == '1'; }
 	const char *tr = getenv("SRCUDA_TIER_RMW");
 	if (tr && tr[0] == '0') h->use_tier_rmw = false;
 	const char *tj = getenv("SRCUDA_TIER_JUNC");
@@ -1246,7 +1290,7 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	rc = ensure(h, bs.queue0, sizeof(uint32_t) * (size_t)n_frags);
 	if (rc) return rc;
 	while (h->events.size() < 4) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
-	CU(h, cudaMemsetAsync(bs.counters, 0, 4 * sizeof(uint32_t), bs.stream));
+	CU(h, cudaMemsetAsync(bs.counters, 0, 8 * sizeof(uint32_t), bs.stream));
 	sr::ChunkArgs a;
 	a.text = (const uint8_t *)d_text; a.text_origin = 0; a.text_bytes = d_text_bytes;
 	a.off = d_off; a.len = d_len; a.n_frags = n_frags;
@@ -1258,7 +1302,7 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	a.big_margin = cfg.do_junctions ? d_out_big_margin : nullptr;
 	rc = launch_vote(h, bs.stream, cfg, a, max_read_len, bs, h->events.data());
 	if (rc) return rc;
-	uint32_t counters[4] = {0, 0, 0, 0};
+	uint32_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	CU(h, cudaMemcpyAsync(counters, bs.counters, sizeof(counters), cudaMemcpyDeviceToHost, bs.stream));
 	CU(h, cudaStreamSynchronize(bs.stream));
 	float ms = 0;
@@ -1268,6 +1312,8 @@ int srcuda_vote_chunk_device(srcuda_handle *h, const srcuda_params *params, cons
 	h->timing.ms_kernel_simple = ms;
 	h->timing.n_simple_punted = counters[2];
 	h->timing.n_gather_requests = counters[3];
+	h->timing.n_simple_indel = counters[4];
+	update_tier_policy(h, cfg, n_frags);
 	CU(h, cudaEventElapsedTime(&ms, h->events[1], h->events[2]));
 	h->timing.ms_kernel_overflow = ms;
 	CU(h, cudaEventElapsedTime(&ms, h->events[0], h->events[2]));
@@ -1302,7 +1348,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 	while ((int64_t)h->events.size() < 4 * n_batches) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
 	for (int i = 0; i < kSets; i++) {
 		BatchSet &b = h->set[i];
-		size_t need = sizeof(uint32_t) * 4 * (size_t)(n_batches / kSets + 2);
+		size_t need = sizeof(uint32_t) * 8 * (size_t)(n_batches / kSets + 2);
 		if (b.h_counters) { cudaFreeHost(b.h_counters); b.h_counters = nullptr; }
 		CU(h, cudaHostAlloc((void **)&b.h_counters, need, cudaHostAllocDefault));
 		memset(b.h_counters, 0, need);
@@ -1375,7 +1421,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 				h->timing.h2d_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 			}
 		}
-		CUD(h, cudaMemsetAsync(bs.counters, 0, 4 * sizeof(uint32_t), s));
+		CUD(h, cudaMemsetAsync(bs.counters, 0, 8 * sizeof(uint32_t), s));
 		sr::ChunkArgs a;
 		a.text = (const uint8_t *)bs.text.p; a.text_origin = origin; a.text_bytes = text_bytes;
 		a.off = (const uint64_t *)bs.off.p; a.len = (const uint16_t *)bs.len.p; a.n_frags = nf;
@@ -1397,7 +1443,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 			CUD(h, cudaMemcpyAsync(out_big_margin + (size_t)r0 * sr::kBigMarginU16, bs.big_margin.p, bm_bytes, cudaMemcpyDeviceToHost, s));
 			h->timing.d2h_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 		}
-		CUD(h, cudaMemcpyAsync(bs.h_counters + 4 * (bi / kSets), bs.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		CUD(h, cudaMemcpyAsync(bs.h_counters + 8 * (bi / kSets), bs.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	}
 	for (int i = 1; i < kSets; i++) {  // join every stream into stream 0, then stamp the end there
 		CUD(h, cudaEventRecord(h->ev_join[i], h->set[i].stream));
@@ -1418,13 +1464,15 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		h->timing.ms_kernel_simple += ms;
 		CU(h, cudaEventElapsedTime(&ms, h->events[4 * bi + 1], h->events[4 * bi + 2]));
 		h->timing.ms_kernel_overflow += ms;
-		const uint32_t *c = h->set[bi % kSets].h_counters + 4 * (bi / kSets);
+		const uint32_t *c = h->set[bi % kSets].h_counters + 8 * (bi / kSets);
 		h->timing.n_simple_punted += c[2];
 		h->timing.n_gather_requests += c[3];
+		h->timing.n_simple_indel += c[4];
 		h->timing.n_overflow += (h->force_slow || (cfg.do_junctions && (!h->use_warp_junc || out_verify))) ? (uint64_t)(std::min(n_frags, (bi + 1) * batch) - bi * batch) : c[0];
 		bad += c[1];
 	}
 	h->timing.n_batches = (uint32_t)n_batches;
+	update_tier_policy(h, cfg, n_frags);
 	if (bad) return fail(h, SRCUDA_ERR_ARG, "%llu reads have (off,len) outside the text buffer", (unsigned long long)bad);
 	return SRCUDA_OK;
 }

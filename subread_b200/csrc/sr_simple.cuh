@@ -76,7 +76,7 @@ SR_HD int simple_warp_bytes(int max_len, int clusters = kSimpleClusters)
 {
 	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
 	int stage = 32 * (((ml + 3) & ~3) + 4) + 32;                             // text of 32 reads (+ alignment slack)
-	const int clus = simple_cluster_bytes(clusters);                         // the vote clusters reuse the staging area
+	const int clus = simple_cluster_bytes(clusters) + 3 * 32 * 4;            // the vote clusters reuse the staging area (+ three words per thread: indel sections, simple_primary_hit)
 	if (stage < clus) stage = clus;
 	const int outb = 16 * kMaxBest * kResultWords * 4;                       // ... and later half a warp's bigtable slots
 	if (stage < outb) stage = outb;
@@ -96,6 +96,8 @@ struct SimpleResult {
 	int used;
 	uint32_t meta;      // kind | strand << 8 | first_sub << 16 | last_sub << 24; kind 0 untouched, 1 record, 2 only `used` is set
 	uint32_t cov;       // confident_coverage_start | end << 16
+	                    // meta bit 9: the slot's indel record has a second section, kept per strand pass by the kernel (`ind` below: first_sub + 1 |
+	                    // (last_sub + 1) << 8 | (indel & 0xff) << 16 | 1 << 31); meta's last_sub is then the last subread of the FIRST section
 };
 
 // One vote cluster = the slot gehash_go_X builds for one kv of a separable pass.  Nothing in it depends on the
@@ -182,7 +184,7 @@ __device__ __forceinline__ SimpleCluster simple_new_cluster(uint32_t kv, int l, 
 
 // One hit on the general path (clusters in shared memory).  Returns false when the pass is not separable.
 // (Rare path: a real call keeps the hot loop small.)
-__device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high)
+__device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high, int *found_out = nullptr)
 {
 	if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;           // u32 wrap-around of the probe rows
 	int found = -1;
@@ -194,6 +196,7 @@ __device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, 
 		near = near || (d != 0 && (unsigned)(d + tol) <= 2u * (unsigned)tol);
 	}
 	if (near) return false;                                        // within tolerance of another slot: an indel vote
+	if (found_out) *found_out = found;
 	if (found >= 0) {
 		SimpleCluster c = C.get(found);
 		if (!(c.w1 >> 31)) return true;                            // no slot for this kv: dropped again
@@ -452,6 +455,68 @@ __device__ __forceinline__ bool simple_general(const DevIndex &ix, const VoteCon
 	return true;
 }
 
+// One single-position hit against the primary cluster P (registers).  Returns true when the hit is not P's business and has to
+// go the general way.  With `p2` (single-end tier) a read with ONE indel stays here too: its hits fall on two offsets, kv and
+// kv + d (|d| within the tolerance), those on kv first.  gehash_go_X puts them all into the slot the first hit opened
+// (sorted-hashtable.c:1007-1072): a hit at distance d from the slot's position with d != current_indel_cursor opens a new
+// section of the indel record {subread + 1, subread + 1, d}, later hits at that distance extend it.  In closed form, for hits in
+// increasing subread order: votes = number of subreads, record = {first1 + 1, last1 + 1, 0, first2 + 1, last2 + 1, d}, coverage
+// from the first hit to the last.  Anything else -- a hit back on the first offset (the reference then marks a shift indel and
+// votes a second round, :1022, core.c:3153-3186), a third offset, a subread voting twice (roll-back, :1027), a slot that was
+// never created -- makes the pass non-separable (ok = false) and the fragment is queued.
+// The second section's state is one word of shared memory per thread (`sec2`, null = not in this tier), touched only by the
+// reads that have one, so that the common path carries no register for it:
+//   first lookup of section 2 | last lookup of section 2 << 8 | (d & 0xff) << 16 | 1 << 31;  0 = no second section
+// P's own last lookup stays that of the FIRST section; simple_indel_close checks after the pass that the two did not interleave.
+__device__ __forceinline__ bool simple_primary_hit(SimpleCluster &P, bool &have_p, SimpleClusters &C, uint32_t *sec2, bool &ok, uint32_t kv, int l,
+                                                   int sub, int tol, uint32_t low, uint32_t high)
+{
+	if (!have_p && C.n == 0) {                                       // the first position of the pass founds P
+		if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
+		P = simple_new_cluster(kv, l, 0, sub, low, high);
+		have_p = true;
+		C.n = 1;
+		return false;
+	}
+	if (!have_p) return true;
+	const int d = (int)(kv - P.kv);
+	const unsigned long long bit = 1ull << sub;
+	if (d == 0) {                                                    // the plain branch :1041-1052
+		if (P.w1 >> 31) {
+			if (P.subs & bit) ok = false;
+			P.subs |= bit;
+			P.w1 = (P.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);       // lookups come in increasing order here
+		}
+		return false;
+	}
+	if (sec2 && d >= -tol && d <= tol) {
+		const uint32_t s2 = *sec2;
+		if (!(P.w1 >> 31) || (P.subs & bit) || (s2 && (int)(int8_t)(s2 >> 16) != d)) { ok = false; return false; }
+		*sec2 = s2 ? ((s2 & ~0x0000ff00u) | ((uint32_t)l << 8)) : (0x80000000u | (uint32_t)l | ((uint32_t)l << 8) | ((uint32_t)(d & 0xff) << 16));
+		P.subs |= bit;
+		return false;
+	}
+	return true;
+}
+
+// After the pass, for a primary cluster with a second section (sec2 != 0): the closed form is the reference's only if every hit of
+// the first section came before the second began (else :1022 marks a shift indel) and no other cluster could have taken the
+// section's hits.  Moves P's last lookup on to the section's (coverage end) and returns the merge's word: last subread of section
+// 1 + 1 | (first subread of section 2 + 1) << 8 | (d & 0xff) << 16 | 1 << 31 -- or 0 when the pass is not separable after all.
+__device__ __forceinline__ uint32_t simple_indel_close(SimpleClusters &C, uint32_t s2, int tol, int gap)
+{
+	const uint32_t kv = C.w(0, 0), w1 = C.w(0, 1);
+	const uint32_t last1 = (w1 >> 8) & 255u, first2 = s2 & 255u, last2 = (s2 >> 8) & 255u;
+	if (first2 <= last1) return 0u;
+#pragma unroll 1
+	for (int c = 1; c < C.n; c++) {
+		const int d = (int)(C.w(c, 0) - kv);
+		if (d >= -2 * tol && d <= 2 * tol) return 0u;
+	}
+	C.w(0, 1) = (w1 & ~0x0000ff00u) | (last2 << 8);
+	return (last1 / (uint32_t)gap + 1u) | ((first2 / (uint32_t)gap + 1u) << 8) | (s2 & 0x80ff0000u);
+}
+
 // The filter of one batch of a strand pass: lookups base .. base + n_sub * GAP - 1 (whole subreads s_base .. s_base + n_sub - 1)
 // of the read packed at pk.  Returns the survivors as a bit mask (bit i = lookup base + i).  All Bloom words (sparse table) or
 // direct-filter words (dense table) of a group of six lookups are requested before any is tested -- memory-level
@@ -557,7 +622,7 @@ __device__ __forceinline__ uint32_t ld_phase_any(const uint32_t *p, uint64_t pol
 // number exactly as before.  The lookups are applied in schedule order (subread by subread, phase 0, 1, 2).
 template <bool RCKEYS>
 __device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
-                                                  SimpleClusters &C, int rc_len, uint32_t &n_gather)
+                                                  SimpleClusters &C, int rc_len, uint32_t &n_gather, uint32_t *sec2)
 {
 	constexpr int GAP = 3, kSubs = 10;                             // ten subreads = thirty lookups per batch (the general path's bit mask)
 	const uint32_t low = cfg.low_border, high = cfg.high_border - (uint32_t)L;
@@ -568,6 +633,7 @@ __device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const Vote
 	SimpleCluster P;
 	P.kv = 0; P.w1 = 0; P.subs = 0;
 	bool have_p = false, ok = true;
+	if (sec2) *sec2 = 0u;                                                       // one-indel reads in closed form (simple_primary_hit)
 	for (int s_base = 0; s_base < applied; s_base += kSubs) {
 		const int n_sub = min(kSubs, applied - s_base), base = s_base * GAP;
 		// ---- (1) which units hold anything ----
@@ -588,26 +654,25 @@ __device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const Vote
 		// ---- (2) the subreads left: one unit each ----
 		unsigned defer = 0;
 		Record8 rn;
-		int si_next = -1, ob_next = 0;
-		uint32_t k0_next = 0, k1_next = 0, k2_next = 0;
+		int si_next = -1;
+		uint32_t k0_next = 0;
 		auto issue = [&]() {
 			si_next = -1;
 			if (!mask) return;
 			si_next = __ffs(mask) - 1;
 			mask &= mask - 1;
-			ob_next = simple_sub_offset<GAP>(s_base + si_next, step);
-			k0_next = simple_key_at<RCKEYS>(pk, ob_next, rc_len);
-			k1_next = simple_key_at<RCKEYS>(pk, ob_next + 1, rc_len);
-			k2_next = simple_key_at<RCKEYS>(pk, ob_next + 2, rc_len);
+			k0_next = simple_key_at<RCKEYS>(pk, simple_sub_offset<GAP>(s_base + si_next, step), rc_len);
 			rn = ld_record(units, k0_next & kPhaseMask);
 			n_gather++;
 		};
 		issue();
 		while (si_next >= 0) {
 			const Record8 r = rn;
-			const int si = si_next, ob = ob_next, sub = s_base + si;
-			const uint32_t k0 = k0_next, k1 = k1_next, k2 = k2_next;
+			const int si = si_next, sub = s_base + si;
+			const uint32_t k0 = k0_next;
 			issue();
+			const int ob = simple_sub_offset<GAP>(sub, step);            // (the other two keys only now: fewer registers across the fetch)
+			const uint32_t k1 = simple_key_at<RCKEYS>(pk, ob + 1, rc_len), k2 = simple_key_at<RCKEYS>(pk, ob + 2, rc_len);
 			const uint32_t c = k0 & kPhaseMask;
 			if (((k1 >> 2) & kPhaseMask) != c || (k2 >> 4) != c) {   // (the three keys do not overlap as a read's do: padding of a tiny read's reverse strand)
 				defer |= 7u << (3 * si);
@@ -625,20 +690,7 @@ __device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const Vote
 				if ((two & 2u) || rank >= kPhaseValues) { defer |= 1u << li; continue; }
 				const uint32_t value = rank == 0 ? r.w[3] : (rank == 1 ? r.w[4] : (rank == 2 ? r.w[5] : (rank == 3 ? r.w[6] : r.w[7])));
 				const uint32_t kv = value - (uint32_t)(ob + x);
-				if (!have_p && C.n == 0) {                               // the first position of the pass founds P
-					if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
-					P = simple_new_cluster(kv, l, 0, sub, low, high);
-					have_p = true;
-					C.n = 1;
-				} else if (have_p && kv == P.kv) {                       // the plain branch :1041-1052
-					const unsigned long long bit = 1ull << sub;
-					if (P.w1 >> 31) {
-						if (P.subs & bit) ok = false;
-						P.subs |= bit;
-						P.w1 = (P.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);  // lookups come in increasing order here
-					}
-				} else
-					defer |= 1u << li;
+				if (simple_primary_hit(P, have_p, C, sec2, ok, kv, l, sub, cfg.indel_tolerance, low, high)) defer |= 1u << li;
 			}
 		}
 		if (!ok) return false;
@@ -646,11 +698,18 @@ __device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const Vote
 		if (defer) {
 			if (__popc(defer) > SR_SIMPLE_DEFER_LIMIT) return false;
 			if (have_p) C.put(0, P);
+			const unsigned long long before = P.subs;
 			if (!simple_general<GAP, RCKEYS>(ix, cfg, pk, step, rc_len, base, defer, C, low, high, n_gather)) return false;
 			if (have_p) P = C.get(0);
+			if (sec2 && *sec2 && P.subs != before) return false;         // (a late hit on the first offset of a read with an indel)
 		}
 	}
 	if (have_p) C.put(0, P);
+	if (sec2 && *sec2) {
+		const uint32_t m = simple_indel_close(C, *sec2, cfg.indel_tolerance, GAP);
+		if (!m) return false;
+		*sec2 = m;
+	}
 #pragma unroll 1
 	for (int c = 0; c < C.n; c++) {
 		C.w(c, 2) = (uint32_t)C.votes(c);
@@ -675,6 +734,42 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 	C.n = 0;
 	if (C.cap < 1) return false;
 	bool ok = true;
+	// A pass over a dense table meets a handful of one-vote chance hits besides the true cluster, and looking every hit up in the
+	// cluster list was a quarter of the kernel's instructions.  Two shortcuts, both exact: `occ` has one bit per 8 consecutive kv
+	// (mod 512) that some cluster of the list falls into -- a hit whose own bit and both neighbours are clear is neither equal to
+	// nor within the tolerance (<= 8) of any cluster and opens a new one unseen; and the cluster the last hit was found equal to
+	// (the true cluster, as a rule) is tried first -- two clusters of the list are never within tolerance of each other, so a hit
+	// that equals one needs no look at the others.
+	unsigned long long occ = 0;
+	uint32_t last_kv = 0;
+	int last_c = -1;
+	auto hit = [&](uint32_t kv, int l, int u, int sub) -> bool {
+		if (last_c >= 0 && kv == last_kv) {
+			SimpleCluster c = C.get(last_c);
+			if (!(c.w1 >> 31)) return true;
+			const unsigned long long bit = 1ull << sub;
+			if (c.subs & bit) return false;
+			c.subs |= bit;
+			if (l < c.first_l()) c.w1 = (c.w1 & ~0x007f00ffu) | (uint32_t)l | ((uint32_t)u << 16);
+			if (l > c.last_l()) c.w1 = (c.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);
+			C.put(last_c, c);
+			return true;
+		}
+		const unsigned b = (kv >> 3) & 63u;
+		const unsigned long long nbr = (1ull << b) | (1ull << ((b + 1u) & 63u)) | (1ull << ((b + 63u) & 63u));
+		if (tol <= 8 && !(occ & nbr)) {
+			if (!(kv >= 32u && kv <= 0xffffffdfu) || C.n >= C.cap) return false;
+			C.put(C.n++, simple_new_cluster(kv, l, u, sub, low, high));
+			occ |= 1ull << b;
+			return true;
+		}
+		int found = -1;
+		const int n0 = C.n;
+		if (!simple_hit(C, kv, l, u, sub, tol, low, high, &found)) return false;
+		if (C.n > n0) occ |= 1ull << b;
+		if (found >= 0) { last_kv = kv; last_c = found; }
+		return true;
+	};
 	for (int s_base = 0; s_base < applied && ok; s_base += kSubs) {
 		const int n_sub = min(kSubs, applied - s_base), base = s_base * GAP;
 		uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // runs of keys with several positions waiting to be applied:
@@ -682,13 +777,9 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		int ne = 0;
 		unsigned slow = 0;                               // lookups the unit could not answer (value beyond its 28, a fifth run): the direct filter does
 		Record8 rn;
-		int ob_next = 0;
-		uint32_t k0_next = 0, k1_next = 0, k2_next = 0;
+		uint32_t k0_next = 0;
 		auto issue = [&](int si) {
-			ob_next = simple_sub_offset<GAP>(s_base + min(si, n_sub - 1), step);
-			k0_next = simple_key_at<RCKEYS>(pk, ob_next, rc_len);
-			k1_next = simple_key_at<RCKEYS>(pk, ob_next + 1, rc_len);
-			k2_next = simple_key_at<RCKEYS>(pk, ob_next + 2, rc_len);
+			k0_next = simple_key_at<RCKEYS>(pk, simple_sub_offset<GAP>(s_base + min(si, n_sub - 1), step), rc_len);
 			rn = ld_record(units4, 4u * (k0_next & kPhaseMask));         // (ld_record counts in 32-byte records: a unit is four)
 			n_gather++;
 		};
@@ -696,9 +787,11 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 #pragma unroll 1
 		for (int si = 0; si < n_sub; si++) {
 			const Record8 r = rn;
-			const int ob = ob_next, sub = s_base + si;
-			const uint32_t k0 = k0_next, k1 = k1_next, k2 = k2_next;
+			const int sub = s_base + si;
+			const uint32_t k0 = k0_next;
 			if (si + 1 < n_sub) issue(si + 1);
+			const int ob = simple_sub_offset<GAP>(sub, step);            // (the other two keys only now: fewer registers across the fetch)
+			const uint32_t k1 = simple_key_at<RCKEYS>(pk, ob + 1, rc_len), k2 = simple_key_at<RCKEYS>(pk, ob + 2, rc_len);
 			const uint32_t c = k0 & kPhaseMask;
 			if (((k1 >> 2) & kPhaseMask) != c || (k2 >> 4) != c) { slow |= 7u << (3 * si); continue; }
 			const uint32_t p0 = r.w[0] & 0x55555555u, p1 = r.w[1] & 0x55555555u;
@@ -717,7 +810,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 					value = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);       // same unit: as a rule the 64 bytes already fetched
 					if (rank >= 12) n_gather++;                                                    // (the unit's second half: another fetch)
 				}
-				if (!(two & 2u)) { if (!simple_hit(C, value - (uint32_t)(ob + x), l, 0, sub, tol, low, high)) ok = false; }
+				if (!(two & 2u)) { if (!hit(value - (uint32_t)(ob + x), l, 0, sub)) ok = false; }
 				else {
 					const uint2 entry = ld_direct_first(ix, value);
 					n_gather++;
@@ -750,7 +843,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 				if (!bits) continue;
 				const uint2 entry = ld_direct_first(ix, rank);
 				n_gather++;
-				if (bits == 1u) { if (!simple_hit(C, entry.x - (uint32_t)o, l, 0, sub, tol, low, high)) ok = false; continue; }
+				if (bits == 1u) { if (!hit(entry.x - (uint32_t)o, l, 0, sub)) ok = false; continue; }
 				const uint32_t me = (entry.y & 0xffffu) | ((uint32_t)l << 16);
 				if ((entry.y & 255u) > (uint32_t)C.cap) { ok = false; break; }
 				if (ne == 0) { ra0 = entry.x; me0 = me; } else if (ne == 1) { ra1 = entry.x; me1 = me; } else if (ne == 2) { ra2 = entry.x; me2 = me; } else { ra3 = entry.x; me3 = me; }
@@ -768,7 +861,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 				n_gather++;
 				int sub;
 				const int o = simple_offset<GAP>(l, step, &sub);
-				if (!simple_hit(C, v - (uint32_t)o, l, u, sub, tol, low, high)) { ok = false; break; }
+				if (!hit(v - (uint32_t)o, l, u, sub)) { ok = false; break; }
 				u++;
 			}
 			ne = 0;
@@ -785,9 +878,10 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 
 template <int GAP, int MODE, bool RCKEYS = false>
 __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
-                                            SimpleClusters &C, int rc_len, uint32_t &n_gather, bool have_first_mask = false, unsigned first_mask = 0u)
+                                            SimpleClusters &C, int rc_len, uint32_t &n_gather, bool have_first_mask = false, unsigned first_mask = 0u,
+                                            uint32_t *sec2 = nullptr /* shared-memory word of the thread: one-indel reads stay in the tier; on return the merge's word */)
 {
-	if (MODE == 3) return simple_pass_phase<RCKEYS>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather);
+	if (MODE == 3) return simple_pass_phase<RCKEYS>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather, sec2);
 	if (MODE == 4) return simple_pass_phase_dense<RCKEYS>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather);
 	constexpr bool DIRECT = MODE == 2;
 	constexpr int kSubsPerBatch = 32 / GAP;                        // whole subreads per batch of <= 32 lookups
@@ -801,6 +895,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 	SimpleCluster P;                  // cluster 0 while have_p
 	P.kv = 0; P.w1 = 0; P.subs = 0;
 	bool have_p = false, ok = true;
+	if (sec2) *sec2 = 0u;                                                       // one-indel reads in closed form (simple_primary_hit; not on dense tables)
 	for (int s_base = 0; s_base < applied; s_base += kSubsPerBatch) {
 		const int n_sub = min(kSubsPerBatch, applied - s_base), base = s_base * GAP;
 		// ---- (1) filter ----
@@ -869,18 +964,8 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 						else if (ne == 3) { ra3 = entry.x; me3 = me; ne = 4; }
 						else defer |= 1u << i;
 					}
-				} else if (kind == 1 && !have_p && C.n == 0) {           // the first position of the pass founds P
-					if (!(kv >= 32u && kv <= 0xffffffdfu)) ok = false;
-					P = simple_new_cluster(kv, l, 0, sub, low, high);
-					have_p = true;
-					C.n = 1;
-				} else if (kind == 1 && have_p && kv == P.kv) {          // the plain branch :1041-1052
-					const unsigned long long bit = 1ull << sub;
-					if (P.w1 >> 31) {
-						if (P.subs & bit) ok = false;
-						P.subs |= bit;
-						P.w1 = (P.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);  // lookups come in increasing order here
-					}
+				} else if (kind == 1) {
+					if (simple_primary_hit(P, have_p, C, DIRECT ? nullptr : sec2, ok, kv, l, sub, tol, low, high)) defer |= 1u << i;
 				} else if (kind != 0)
 					defer |= 1u << i;
 			}
@@ -931,11 +1016,18 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
 			// (an indel splits the hits over two kv, a repeat answers every lookup with several positions)
 			if (__popc(defer) > SR_SIMPLE_DEFER_LIMIT) return false;
 			if (have_p) C.put(0, P);
+			const unsigned long long before = P.subs;
 			if (!simple_general<GAP, RCKEYS>(ix, cfg, pk, step, rc_len, base, defer, C, low, high, n_gather)) return false;
 			if (have_p) P = C.get(0);
+			if (!DIRECT && sec2 && *sec2 && P.subs != before) return false;   // (a late hit on the first offset of a read with an indel)
 		}
 	}
 	if (have_p) C.put(0, P);
+	if (!DIRECT && sec2 && *sec2) {
+		const uint32_t m = simple_indel_close(C, *sec2, tol, GAP);
+		if (!m) return false;
+		*sec2 = m;
+	}
 #pragma unroll 1
 	for (int c = 0; c < C.n; c++) {                                   // the subread sets have served: word 2 becomes the vote count,
 		C.w(c, 2) = (uint32_t)C.votes(c);                             // word 3 is free for the merge (paired-end tier: chromosome memo)
@@ -966,8 +1058,12 @@ __device__ __forceinline__ void simple_update_top(int ts, int &t0, int &t1, int 
 // that it stays in registers; the loops over clusters are kept rolled (small code matters more than their speed).
 // simple_pass has left every cluster's vote count in its word 2.
 template <int GAP>
-__device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const SimpleClusters &C, int strand, int applied, int step, SimpleResult (&res)[kMaxBest])
+__device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const SimpleClusters &C, int strand, int applied, int step, SimpleResult (&res)[kMaxBest],
+                                             uint32_t *p_ind = nullptr /* in: cluster 0's second indel section (simple_primary_hit), 0 = none; out: the
+                                                                          slot's `ind` word if cluster 0 was emitted with it, else 0 */)
 {
+	const uint32_t p_in = p_ind ? *p_ind : 0u;
+	if (p_ind) *p_ind = 0u;
 	const int mb = cfg.multi_best_reads, ts = cfg.top_scores;
 	int max_vote = 0;
 #pragma unroll 1
@@ -1039,6 +1135,10 @@ __device__ __forceinline__ void simple_merge(const VoteConfig &cfg, const Simple
 					r.pos = pos; r.votes = want; r.used = applied;
 					r.meta = 1u | ((uint32_t)strand << 8) | ((uint32_t)(s_first + 1) << 16) | ((uint32_t)(s_last + 1) << 24);
 					r.cov = (uint32_t)o_first | ((uint32_t)(o_last + 16) << 16);
+					if (best == 0 && p_in) {                             // {first1 + 1, last1 + 1, 0, first2 + 1, last2 + 1, d}
+						r.meta = (r.meta & 0x00ffffffu) | ((p_in & 255u) << 24) | 0x200u;
+						*p_ind = ((p_in >> 8) & 255u) | ((uint32_t)(s_last + 1) << 8) | (p_in & 0x80ff0000u);
+					}
 					put(r);
 				}
 			}
@@ -1074,12 +1174,18 @@ namespace sr {
 // dynamic shared memory simple_junc_smem_bytes(max_len, clusters).
 // RMW (second and later index blocks): the slice holds the results of the blocks before; a fragment whose used slots all
 // have the plain form this tier produces itself (no indel, no junction bits) merges into them, any other is queued.
-template <int GAP, int MODE, bool JUNC = false, bool RMW = false>
-__global__ void __launch_bounds__(kSimpleThreads, JUNC ? 4 : SR_SIMPLE_MIN_BLOCKS)
+// INDEL: reads with one indel stay in the tier in closed form (simple_primary_hit; sparse tables, not subjunc).  It costs the
+// error-free chunk 13 % (register pressure in the lookup loop), so the host launches this form only while the chunks it sees
+// actually hold such reads (srcuda_handle::tier_indel, from the last call's counters); the bytes are the same either way.
+// indel_count: fragments whose result came from that closed form.
+template <int GAP, int MODE, bool JUNC = false, bool RMW = false, bool INDEL = false>
+__global__ void __launch_bounds__(kSimpleThreads, JUNC ? 4 : ((MODE == 2 || MODE == 4) ? 5 : SR_SIMPLE_MIN_BLOCKS))   // (dense tables: shared memory allows five blocks anyway)
 k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
              const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int clusters, ResultWords *out, uint32_t *queue,
-             uint32_t *queue_count, uint32_t *bad_reads, uint32_t *gather_count, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
+             uint32_t *queue_count, uint32_t *bad_reads, uint32_t *gather_count, JuncWords *jout = nullptr, uint16_t *bmout = nullptr,
+             uint32_t *indel_count = nullptr)
 {
+	static_assert(!INDEL || (!JUNC && (MODE == 0 || MODE == 3)), "the one-indel closed form lives on the primary cluster of a sparse table");
 	extern __shared__ uint4 smem4[];
 	constexpr unsigned kFullMask = 0xffffffffu;
 	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -1188,6 +1294,10 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 		for (int i = 0; i < 12; i++) bm[i] = 0;
 	}
 	uint32_t n_gather = 0;
+	// per strand pass: second section of the indel record of the slot whose meta bit 9 is set -- in shared memory behind the clusters
+	// (word 0: the running pass's, simple_primary_hit; words 1, 2: what the merges of strand 0 / 1 emitted)
+	uint32_t *const indw = reinterpret_cast<uint32_t *>(stage + simple_cluster_bytes(clusters)) + lane;
+	if (INDEL) { indw[32] = 0u; indw[64] = 0u; }
 	if (active && !punt) {
 		// a read shorter than 16 bases goes through two empty passes (core.c:3116)
 		int step = 65536;
@@ -1219,10 +1329,16 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 				Ck.base = C.base + used * kSimpleClusterWords * 32;
 				Ck.cap = C.cap - used;
 			}
-			if (!simple_pass<GAP, MODE>(ix, cfg, pass, L, applied, step, Ck, 0, n_gather, kReorder && applied > 0, strand ? m1 : m0)) punt = true;
-			else if (!kReorder) {                                     // dense table: one list, merged at once
+			// a read with one indel stays in the tier (not in subjunc mode, not with the strand reordering): its second section's word
+			uint32_t *const sec2 = (!INDEL || kReorder) ? nullptr : indw;
+			if (!simple_pass<GAP, MODE>(ix, cfg, pass, L, applied, step, Ck, 0, n_gather, kReorder && applied > 0, strand ? m1 : m0, sec2)) punt = true;
+			else if (!kReorder) {                                     // one list, merged at once
 				if (JUNC) simple_merge_junc<GAP>(ix, cfg, Ck, strand, applied, step, res, J, JT, bm, TierText{pass, 0}, L);
-				else simple_merge<GAP>(cfg, Ck, strand, applied, step, res);
+				else {
+					uint32_t p_ind = sec2 ? *sec2 : 0u;
+					simple_merge<GAP>(cfg, Ck, strand, applied, step, res, &p_ind);
+					if (sec2) indw[32 + 32 * strand] = p_ind;
+				}
 			}
 			if (strand == 0) C0 = Ck; else C1 = Ck;
 		}
@@ -1240,6 +1356,10 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 	}
 	n_gather = __reduce_add_sync(kFullMask, n_gather);
 	if (lane == 0 && n_gather) atomicAdd(gather_count, n_gather);
+	if (INDEL) {
+		const unsigned im = __ballot_sync(kFullMask, active && !punt && (indw[32] | indw[64]) != 0u);
+		if (lane == 0 && im && indel_count) atomicAdd(indel_count, (uint32_t)__popc(im));
+	}
 	__syncwarp();
 	// queue the punted fragments (one atomic per warp)
 	const unsigned pm = __ballot_sync(kFullMask, active && punt);
@@ -1270,6 +1390,13 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 					else if (w == 2) v = w2;
 					else if (w == 4) v = ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16);
 					else if (w == 15) v = r.cov;
+					else if (INDEL && (r.meta & 0x200u)) {
+						const uint32_t ind = indw[((r.meta >> 8) & 1u) ? 64 : 32];
+						const uint32_t d16 = (uint32_t)(uint16_t)(int16_t)(int8_t)(ind >> 16);
+						if (w == 3) v = (d16 & 0xffu) << 8;
+						else if (w == 5) v = (ind & 0xffu) << 16;
+						else if (w == 6) v = ((ind >> 8) & 0xffu) | (d16 << 16);
+					}
 					dst[k].w[w] = v;
 				}
 			} else {
@@ -1371,6 +1498,13 @@ k_map_simple(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint6
 			__stcs(&dst[k].w[2], (uint32_t)(uint16_t)r.votes | ((uint32_t)(uint16_t)r.used << 16));
 			__stcs(&dst[k].w[4], ((r.meta >> 16) & 0xffu) | (((r.meta >> 24) & 0xffu) << 16));
 			__stcs(&dst[k].w[15], r.cov);
+			if (INDEL && (r.meta & 0x200u)) {                        // second section of the indel record; indels_in_confident_coverage = its indel
+				const uint32_t ind = indw[((r.meta >> 8) & 1u) ? 64 : 32];
+				const uint32_t d16 = (uint32_t)(uint16_t)(int16_t)(int8_t)(ind >> 16);
+				__stcs(&dst[k].w[3], (d16 & 0xffu) << 8);
+				__stcs(&dst[k].w[5], (ind & 0xffu) << 16);
+				__stcs(&dst[k].w[6], ((ind >> 8) & 0xffu) | (d16 << 16));
+			}
 		} else if (kind == 2) {
 			__stcs(&dst[k].w[2], (uint32_t)(uint16_t)r.used << 16);
 		}

@@ -116,7 +116,7 @@ def test_cuda_equals_the_reference_on_its_own_fixtures(index, reads, work, oracl
     prefix, n_blocks = work["index"][index]
     chunk = load_fastq(*work["reads"][reads])
     params = VoteParams.defaults(mates == 2, subjunc)
-    for env in ({}, {"SRCUDA_SIMPLE_TIER": "0"}):
+    for env in ({}, {"SRCUDA_SIMPLE_TIER": "0"}, {"SRCUDA_TIER_INDEL": "1"}):      # default tiers; warp kernel alone; the tier's one-indel form forced on
         os.environ.update(env)
         try:
             m = Mapper(0)
