@@ -417,7 +417,8 @@ struct BatchSet {  // one of two buffer sets; used by one stream
 	cudaStream_t stream = nullptr;
 	DeviceBuf text, off, len, out, verify, queue, queue0, junc, big_margin;
 	uint32_t *counters = nullptr;       // device: [0] queue_count (-> scalar), [1] bad_reads, [2] queue0_count (simple -> warp)
-	uint32_t *h_counters = nullptr;     // pinned host mirror, 2 per batch slot
+	uint32_t *h_counters = nullptr;     // pinned host mirror, 8 per batch slot
+	size_t h_counters_bytes = 0;
 	sr::ScalarScratch *scratch = nullptr;
 	size_t scratch_threads = 0;
 };
@@ -1349,17 +1350,18 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 	for (int i = 0; i < kSets; i++) {
 		BatchSet &b = h->set[i];
 		size_t need = sizeof(uint32_t) * 8 * (size_t)(n_batches / kSets + 2);
-		if (b.h_counters) { cudaFreeHost(b.h_counters); b.h_counters = nullptr; }
-		CU(h, cudaHostAlloc((void **)&b.h_counters, need, cudaHostAllocDefault));
+		if (need > b.h_counters_bytes) {                 // (kept between calls: pinning memory costs more than a chunk's kernels)
+			if (b.h_counters) { cudaFreeHost(b.h_counters); b.h_counters = nullptr; b.h_counters_bytes = 0; }
+			CU(h, cudaHostAlloc((void **)&b.h_counters, need, cudaHostAllocDefault));
+			b.h_counters_bytes = need;
+		}
 		memset(b.h_counters, 0, need);
 	}
 
-	// Everything that can be refused is refused before the first copy is enqueued: once a batch is in flight the caller's
-	// buffers are the source and target of asynchronous copies and must stay untouched until the streams have drained.
-	std::vector<int> batch_max_len((size_t)n_batches, 1);
-	for (int64_t bi = 0; bi < n_batches; bi++) {
-		const int64_t f0 = bi * batch, f1 = std::min(n_frags, f0 + batch);
-		const int64_t r0 = f0 * mates, r1 = f1 * mates;
+	// A batch is checked right before it is enqueued (so that checking batch k + 1 overlaps the copies and kernels of batch k: the
+	// scan of 10 M reads is 12 ms of host time); once a batch is in flight the caller's buffers are the source and target of
+	// asynchronous copies, so a refusal further down drains the streams before it returns.
+	auto check_batch = [&](int64_t r0, int64_t r1, int *max_len_out) -> int {
 		int max_len = 1;
 		uint64_t lo = off[r0], end = 0;
 		for (int64_t r = r0; r < r1; r++) {
@@ -1370,8 +1372,9 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		if (max_len > sr::kMaxReadLen) return fail(h, SRCUDA_ERR_ARG, "a read is longer than %d", sr::kMaxReadLen);
 		// the batch's reads must lie in text[off[first] .. off[last] + len[last])
 		if (lo < off[r0] || end > off[r1 - 1] + len[r1 - 1]) return fail(h, SRCUDA_ERR_ARG, "read offsets must be non-decreasing");
-		batch_max_len[(size_t)bi] = max_len;
-	}
+		*max_len_out = max_len;
+		return SRCUDA_OK;
+	};
 	// any failure from here on waits for the copies already enqueued before it returns
 	auto drain = [&](int rc_in) {
 		for (int i = 0; i < kSets; i++) if (h->set[i].stream) cudaStreamSynchronize(h->set[i].stream);
@@ -1391,7 +1394,8 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		cudaStream_t s = bs.stream;
 		const int64_t f0 = bi * batch, f1 = std::min(n_frags, f0 + batch), nf = f1 - f0;
 		const int64_t r0 = f0 * mates, nr = nf * mates;
-		const int max_len = batch_max_len[(size_t)bi];
+		int max_len = 1;
+		if ((rc = check_batch(r0, r0 + nr, &max_len))) return drain(rc);
 		const uint64_t origin = off[r0];
 		const uint64_t text_bytes = off[r0 + nr - 1] + len[r0 + nr - 1] - origin;
 		const size_t n_slots = (size_t)nr * mb;
