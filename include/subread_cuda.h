@@ -251,6 +251,10 @@ int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *text, uint64_t
 /* Passes over the next n_frags fragments without gathering them (*skipped = how many there were): a process that maps
  * one slice of every chunk (one GPU of several) skips the slices of the others. */
 int srcuda_reader_skip(srcuda_reader *r, int64_t n_frags, int64_t *skipped);
+/* File offsets (in inflated bytes) behind the last fragment handed out: where a reader of its own -- the reference's gene_input_t
+ * under a binding -- has to continue (geinput_seek, input-files.c:699: a plain FASTQ file's position is its byte offset).  pos2 may
+ * be NULL for single-end input. */
+int srcuda_reader_tell(const srcuda_reader *r, uint64_t *pos1, uint64_t *pos2);
 const char *srcuda_reader_error(const srcuda_reader *r);
 void srcuda_reader_close(srcuda_reader *r);
 

@@ -15,7 +15,8 @@
  * stock subread-align (minus @PG).
  *
  * Threading: run_maybe_threads (core.c:3379) starts config.all_threads workers that all enter
- * do_voting.  Worker 0 reads the whole chunk through the reference's own fetch_next_read_pair and
+ * do_voting.  Worker 0 reads the whole chunk -- through the library's chunk reader (srcuda_reader_*) when
+ * the input is plain FASTQ, else through the reference's own fetch_next_read_pair -- and
  * makes ONE srcuda_vote_chunk_multi call -- the chunk spread over the GPUs of SRCUDA_DEVICES -- that
  * writes straight into the bigtable (bigtable_cache_malloc_ptr has exactly the out_align layout,
  * bigtable_cache_malloc_ptr_junc the out_junc one); then all workers share the per-read tail of
@@ -28,6 +29,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 
 #include "subread.h"
 #include "core.h"
@@ -120,6 +122,7 @@ typedef struct {
 	uint64_t *name_off;
 	uint16_t *len;
 	size_t text_cap, text_used, names_cap, names_used, reads_cap, n_reads;
+	int raw_orientation;  /* the reads are as they are in the files (chunk reader): the mate reversal of fetch_next_read_pair is still to come */
 } chunk_buf_t;
 
 static chunk_buf_t g_chunk;
@@ -155,6 +158,89 @@ static void chunk_push(chunk_buf_t *c, const char *name, const char *text, const
 	c->n_reads++;
 }
 
+/* ---- the chunk through the library's own reader (plain FASTQ) ---------------------------------- */
+/* fetch_next_read_pair hands out one read per call under the input lock (0.8 M reads/s); srcuda_reader_* indexes and gathers a
+ * whole chunk from several host threads.  Used when both inputs are plain FASTQ files and the mode needs neither names nor
+ * qualities in the voting step (subread-align: find_new_indels reads neither).  The reference's own gene_input_t is then moved
+ * on to where the library's reader stopped (a plain file's position is its byte offset, geinput_seek, input-files.c:699), so
+ * that locate_read_files / go_chunk_start / go_chunk_nextchunk (core.c:3482-3537) and the later steps, which re-read the chunk
+ * with the reference's reader, see exactly the state fetch_next_read_pair would have left.  SRCUDA_BINDING_READER=0 turns it off. */
+typedef struct {
+	srcuda_reader *rd;
+	int state;            /* 0 not tried, 1 in use, -1 not usable */
+} binding_reader_t;
+static binding_reader_t g_reader;
+
+static int reader_usable(global_context_t *gc)
+{
+	const char *e = getenv("SRCUDA_BINDING_READER");
+	if (e && e[0] == '0') return 0;
+	if (gc->config.do_breakpoint_detection || gc->config.do_fusion_detection || gc->config.do_long_del_detection) return 0;   /* find_new_junctions reads qualities */
+	if (gc->input_reads.first_read_file.file_type != GENE_INPUT_FASTQ) return 0;
+	if (gc->input_reads.is_paired_end_reads && gc->input_reads.second_read_file.file_type != GENE_INPUT_FASTQ) return 0;
+	return 1;
+}
+
+/* Returns 1 when the chunk was read (c filled, *n_frags set), 0 when the reference's reader has to do it, -1 on error. */
+static int read_chunk_with_library(global_context_t *gc, chunk_buf_t *c, subread_read_number_t *n_frags)
+{
+	binding_reader_t *b = &g_reader;
+	const int is_paired = gc->input_reads.is_paired_end_reads, mates = 1 + is_paired;
+	gene_input_t *g1 = &gc->input_reads.first_read_file, *g2 = is_paired ? &gc->input_reads.second_read_file : NULL;
+	if (b->state < 0 || !reader_usable(gc)) return 0;
+	if (b->state == 0) {
+		if (ftello((FILE *)g1->input_fp) != 0 || (g2 && ftello((FILE *)g2->input_fp) != 0)) { b->state = -1; return 0; }   /* not at the start: leave it */
+		if (srcuda_reader_open(gc->config.first_read_file, is_paired ? gc->config.second_read_file : NULL, 0, gc->config.all_threads,
+		                       gc->config.read_trim_5, gc->config.read_trim_3, &b->rd)) {
+			if (b->rd) srcuda_reader_close(b->rd);
+			b->rd = NULL;
+			b->state = -1;
+			return 0;
+		}
+		b->state = 1;
+	}
+	/* both readers must stand at the same place */
+	uint64_t p1 = 0, p2 = 0;
+	srcuda_reader_tell(b->rd, &p1, &p2);
+	if ((uint64_t)ftello((FILE *)g1->input_fp) != p1 || (g2 && (uint64_t)ftello((FILE *)g2->input_fp) != p2)) {
+		SUBREADprintf("ERROR: the chunk reader and the input files are out of step (%llu vs %lld).\n", (unsigned long long)p1, (long long)ftello((FILE *)g1->input_fp));
+		return -1;
+	}
+	const int64_t want = (int64_t)gc->config.reads_per_chunk;
+	struct stat st1, st2;
+	uint64_t cap = 64;
+	if (stat(gc->config.first_read_file, &st1) == 0) cap += (uint64_t)st1.st_size - p1;
+	if (is_paired && stat(gc->config.second_read_file, &st2) == 0) cap += (uint64_t)st2.st_size - p2;
+	const uint64_t worst = (uint64_t)want * mates * (MAX_READ_LENGTH + 1);
+	if (cap > worst) cap = worst;                /* (the reads of a chunk are part of the bytes left in the files) */
+	if (c->text_cap < cap) { free(c->text); free(c->qual); c->text = malloc(cap); c->qual = NULL; c->text_cap = cap; }
+	if (c->reads_cap < (size_t)want * mates + 1) {
+		c->reads_cap = (size_t)want * mates + 1;
+		c->off = realloc(c->off, sizeof(uint64_t) * (c->reads_cap + 1));
+		c->name_off = realloc(c->name_off, sizeof(uint64_t) * (c->reads_cap + 1));
+		c->len = realloc(c->len, sizeof(uint16_t) * c->reads_cap);
+	}
+	if (!c->text || !c->off || !c->len) { SUBREADprintf("ERROR: out of memory for the read chunk.\n"); return -1; }
+	int64_t got = 0;
+	uint64_t bytes = 0;
+	if (srcuda_reader_next(b->rd, want, c->text, c->text_cap, c->off, c->len, &got, &bytes)) {
+		SUBREADprintf("ERROR: %s\n", srcuda_reader_error(b->rd));
+		return -1;
+	}
+	c->n_reads = (size_t)got * mates;
+	c->text_used = bytes;
+	c->raw_orientation = 1;
+	*n_frags = (subread_read_number_t)got;
+	/* the reference's files move on to the end of the chunk, its read counter too (fetch_next_read_pair, core.c:1175) */
+	srcuda_reader_tell(b->rd, &p1, &p2);
+	subread_lock_occupy(&gc->input_reads.input_lock);
+	fseeko((FILE *)g1->input_fp, (off_t)p1, SEEK_SET);
+	if (g2) fseeko((FILE *)g2->input_fp, (off_t)p2, SEEK_SET);
+	gc->running_processed_reads_in_chunk = got;
+	subread_lock_release(&gc->input_reads.input_lock);
+	return 1;
+}
+
 /* ---- worker rendezvous ------------------------------------------------------------------------ */
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
@@ -177,17 +263,33 @@ static int vote_chunk_on_gpu(global_context_t *gc, thread_context_t *tc)
 	char *t1 = malloc(MAX_READ_LENGTH + 1), *t2 = malloc(MAX_READ_LENGTH + 1), *q1 = malloc(MAX_READ_LENGTH + 1), *q2 = malloc(MAX_READ_LENGTH + 1);
 	char n1[MAX_READ_NAME_LEN + 1], n2[MAX_READ_NAME_LEN + 1];
 	chunk_buf_t *c = &g_chunk;
-	c->n_reads = 0; c->text_used = 0; c->names_used = 0;
-	for (;;) {
-		int l1 = 0, l2 = 0;
-		subread_read_number_t no = 0;
-		fetch_next_read_pair(gc, tc, ginp1, ginp2, &l1, &l2, n1, n2, t1, t2, q1, q2, 1, &no);
-		if (no < 0) break;
-		chunk_push(c, n1, t1, q1, l1);
-		if (is_paired) chunk_push(c, n2, t2, q2, l2);
+	int by_library = 0;
+	if (gc->current_index_block_number > 0 && c->raw_orientation && g_reader.state == 1) {
+		/* a later index block of the same chunk: the reads are still here (the reference rewound its files to re-read them) */
+		by_library = 1;
+		subread_lock_occupy(&gc->input_reads.input_lock);
+		gc->running_processed_reads_in_chunk = g_n_frags;
+		subread_lock_release(&gc->input_reads.input_lock);
+	} else {
+		c->n_reads = 0; c->text_used = 0; c->names_used = 0; c->raw_orientation = 0;
+		subread_read_number_t got = 0;
+		by_library = read_chunk_with_library(gc, c, &got);
+		if (by_library < 0) { free(t1); free(t2); free(q1); free(q2); return 1; }
+		if (by_library) g_n_frags = got;
+	}
+	if (!by_library) {
+		if (!c->qual && c->text_cap) c->qual = malloc(c->text_cap);      /* (the library's reader left no quality buffer) */
+		for (;;) {
+			int l1 = 0, l2 = 0;
+			subread_read_number_t no = 0;
+			fetch_next_read_pair(gc, tc, ginp1, ginp2, &l1, &l2, n1, n2, t1, t2, q1, q2, 1, &no);
+			if (no < 0) break;
+			chunk_push(c, n1, t1, q1, l1);
+			if (is_paired) chunk_push(c, n2, t2, q2, l2);
+		}
+		g_n_frags = (subread_read_number_t)(c->n_reads / (1 + is_paired));
 	}
 	free(t1); free(t2); free(q1); free(q2);
-	g_n_frags = (subread_read_number_t)(c->n_reads / (1 + is_paired));
 	if (!g_n_frags) return 0;
 
 	srcuda_params p;
@@ -205,6 +307,10 @@ static int vote_chunk_on_gpu(global_context_t *gc, thread_context_t *tc)
 	p.maximum_pair_distance = gc->config.maximum_pair_distance;
 	p.is_first_read_reversed = 0;  /* fetch_next_read_pair already oriented both mates (core.c:1187-1199) */
 	p.is_second_read_reversed = 0;
+	if (c->raw_orientation) {      /* ... the library's reader did not: the voting step does it itself */
+		p.is_first_read_reversed = gc->config.is_first_read_reversed;
+		p.is_second_read_reversed = gc->config.is_second_read_reversed;
+	}
 	/* subjunc: the junction half of copy_vote_to_alignment_res (core-junction.c:1073-1334) runs on the GPU too */
 	p.do_breakpoint_detection = gc->config.do_breakpoint_detection;
 	p.do_big_margin_filtering_for_junctions = gc->config.do_big_margin_filtering_for_junctions;
@@ -255,8 +361,15 @@ static void discover_events(global_context_t *gc, thread_context_t *tc, subread_
 		for (int m = 0; m < mates; m++) {
 			size_t r = (size_t)f * mates + m;
 			int rlen = c->len[r];
-			memcpy(text, c->text + c->off[r], (size_t)rlen + 1);
-			memcpy(qual, c->qual + c->off[r], (size_t)rlen + 1);
+			memcpy(text, c->text + c->off[r], (size_t)rlen);
+			text[rlen] = 0;
+			if (c->raw_orientation) {
+				/* as fetch_next_read_pair would have handed it over (core.c:1187-1199); no qualities, no name on this path */
+				if (m ? gc->config.is_second_read_reversed : gc->config.is_first_read_reversed) reverse_read(text, rlen, gc->config.space_type);
+				memset(qual, 0, (size_t)rlen + 1);
+			} else
+				memcpy(qual, c->qual + c->off[r], (size_t)rlen + 1);
+			const char *rname = c->raw_orientation ? "" : c->names + c->name_off[r];
 			/* after its two strand passes do_voting holds the read reversed (core.c:3229-3234) and the
 			 * quality string as fetched; read_?_reversed starts at 1 (core.c:3237-3238) */
 			reverse_read(text, rlen, gc->config.space_type);
@@ -274,14 +387,26 @@ static void discover_events(global_context_t *gc, thread_context_t *tc, subread_
 				gene_value_index_t *saved = tc ? tc->current_value_index : gc->current_value_index;
 				locate_current_value_index(gc, tc, cur, rlen);
 				if (!has_better_mapping(gc, tc, f, m, best))
-					find_new_indels(gc, tc, f, c->names + c->name_off[r], text, current_qual, rlen, m, best);
+					find_new_indels(gc, tc, f, (char *)rname, text, current_qual, rlen, m, best);
 				if (need_junction_step)
-					find_new_junctions(gc, tc, f, c->names + c->name_off[r], text, current_qual, rlen, m, best);
+					find_new_junctions(gc, tc, f, (char *)rname, text, current_qual, rlen, m, best);
 				if (tc) tc->current_value_index = saved; else gc->current_value_index = saved;
 			}
 		}
 	free(text);
 	free(qual);
+}
+
+/* TEST KNOB (both oracle/ref_hooks.c and integration/do_voting_cuda.c carry it, so that the stock reference and the bound one can be
+ * run with the same small chunks): SUBREAD_TEST_READS_PER_CHUNK=<n> replaces config.reads_per_chunk (20 M reads divided by
+ * multi_best_reads and mates, core-indel.c:4483, core.c:4092) right before the bigtable is sized from it (core-bigtable.c:84). */
+int init_bigtable_results(global_context_t *global_context, int is_rewinding)
+{
+	static int (*real_fn)(global_context_t *, int) = NULL;
+	if (!real_fn) real_fn = (int (*)(global_context_t *, int))dlsym(RTLD_NEXT, "init_bigtable_results");
+	const char *n = getenv("SUBREAD_TEST_READS_PER_CHUNK");
+	if (n && atoll(n) > 0) global_context->config.reads_per_chunk = (unsigned long long)atoll(n);
+	return real_fn(global_context, is_rewinding);
 }
 
 int do_voting(global_context_t *gc, thread_context_t *tc)

@@ -72,6 +72,18 @@ int anti_supporting_read_scan(global_context_t *global_context)
 	return real_fn(global_context);
 }
 
+/* TEST KNOB (both oracle/ref_hooks.c and integration/do_voting_cuda.c carry it, so that the stock reference and the bound one can be
+ * run with the same small chunks): SUBREAD_TEST_READS_PER_CHUNK=<n> replaces config.reads_per_chunk (20 M reads divided by
+ * multi_best_reads and mates, core-indel.c:4483, core.c:4092) right before the bigtable is sized from it (core-bigtable.c:84). */
+int init_bigtable_results(global_context_t *global_context, int is_rewinding)
+{
+	static int (*real_fn)(global_context_t *, int) = NULL;
+	if (!real_fn) real_fn = (int (*)(global_context_t *, int))dlsym(RTLD_NEXT, "init_bigtable_results");
+	const char *n = getenv("SUBREAD_TEST_READS_PER_CHUNK");
+	if (n && atoll(n) > 0) global_context->config.reads_per_chunk = (unsigned long long)atoll(n);
+	return real_fn(global_context, is_rewinding);
+}
+
 static void dump_vote(FILE *fp, gene_vote_t *v, int mate)
 {
 	int i, j, k;

@@ -24,7 +24,7 @@ EXPORTS = [
     "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device", "srcuda_vote_chunk_multi", "srcuda_index_load_all",
     "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth", "srcuda_measure_lookup_roofline",
     "srcuda_fastq_split", "srcuda_fastq_split_mt", "srcuda_reads_pack", "srcuda_reads_pack_mt",
-    "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_skip", "srcuda_reader_error", "srcuda_reader_close",
+    "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_skip", "srcuda_reader_tell", "srcuda_reader_error", "srcuda_reader_close",
 ]
 
 
@@ -111,6 +111,7 @@ def load_library():
     L.srcuda_reader_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.srcuda_reader_next.argtypes = [vp, i64, vp, u64, vp, vp, ctypes.POINTER(i64), ctypes.POINTER(u64)]
     L.srcuda_reader_skip.argtypes = [vp, i64, ctypes.POINTER(i64)]
+    L.srcuda_reader_tell.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.srcuda_reader_error.argtypes = [vp]
     L.srcuda_reader_error.restype = ctypes.c_char_p
     L.srcuda_reader_close.argtypes = [vp]
@@ -425,6 +426,12 @@ class ChunkReader:
         if rc:
             raise SubreadCudaError(f"srcuda_reader_skip: {self.lib.srcuda_reader_error(self.h).decode()} (rc={rc})")
         return int(n.value)
+
+    def tell(self):
+        """File offsets (inflated bytes) behind the last fragment handed out, one per file."""
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self.lib.srcuda_reader_tell(self.h, ctypes.byref(a), ctypes.byref(b))
+        return (a.value, b.value) if self.mates == 2 else (a.value,)
 
     def close(self):
         if self.h:

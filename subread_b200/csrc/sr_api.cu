@@ -18,6 +18,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -344,6 +345,53 @@ __global__ void k_direct_fill(const uint32_t *bucket_start, const int16_t *keys,
 	}
 }
 
+// The bigtable slice of a batch, compacted for the trip over PCIe: of the 3 x 68 bytes per read a uniquely mapped read uses five
+// words of slot 0, and the host buffer of a chunk's first index block is all zero already (core-bigtable.c:96), so only the slots
+// that hold anything have to travel -- 24 bytes {slot, w0, w1, w2, w4, w15} for a slot of the plain form (one section in the indel
+// record, nothing else), 72 bytes {slot, 17 words} for any other.  The order of the records does not matter (the host scatters them
+// by slot).  counters[5] / [6]: records written; counters[7]: a list was too short (the batch then takes the plain copy).
+__global__ void k_compact_results(const ResultWords *out, uint32_t n_slots, uint32_t *simple, uint32_t cap_simple, uint32_t *full, uint32_t cap_full,
+                                  uint32_t *counters)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n_slots; base += gridDim.x * blockDim.x) {
+		const uint32_t slot = base + lane;
+		uint32_t w[kResultWords];
+		uint32_t any = 0, rest = 0;
+		if (slot < n_slots) {
+#pragma unroll
+			for (int i = 0; i < kResultWords; i++) {
+				w[i] = out[slot].w[i];
+				any |= w[i];
+				if (i == 3 || (i >= 5 && i <= 14) || i == 16) rest |= w[i];
+			}
+		}
+		const unsigned ms = __ballot_sync(0xffffffffu, any != 0 && rest == 0), mf = __ballot_sync(0xffffffffu, any != 0 && rest != 0);
+		uint32_t bs = 0, bf = 0;
+		if (lane == 0) {
+			if (ms) bs = atomicAdd(counters + 5, (uint32_t)__popc(ms));
+			if (mf) bf = atomicAdd(counters + 6, (uint32_t)__popc(mf));
+		}
+		bs = __shfl_sync(0xffffffffu, bs, 0);
+		bf = __shfl_sync(0xffffffffu, bf, 0);
+		if (any != 0 && rest == 0) {
+			const uint32_t at = bs + __popc(ms & ((1u << lane) - 1u));
+			if (at < cap_simple) {
+				uint32_t *r = simple + 6 * (size_t)at;
+				r[0] = slot; r[1] = w[0]; r[2] = w[1]; r[3] = w[2]; r[4] = w[4]; r[5] = w[15];
+			} else counters[7] = 1u;
+		} else if (any != 0) {
+			const uint32_t at = bf + __popc(mf & ((1u << lane) - 1u));
+			if (at < cap_full) {
+				uint32_t *r = full + 18 * (size_t)at;
+				r[0] = slot;
+#pragma unroll
+				for (int i = 0; i < kResultWords; i++) r[1 + i] = w[i];
+			} else counters[7] = 1u;
+		}
+	}
+}
+
 // Random 32-byte-sector gather: the "HBM-gather roofline" probe.
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_thread, uint32_t seed, uint32_t *sink)
 {
@@ -419,6 +467,10 @@ struct BatchSet {  // one of two buffer sets; used by one stream
 	uint32_t *counters = nullptr;       // device: [0] queue_count (-> scalar), [1] bad_reads, [2] queue0_count (simple -> warp)
 	uint32_t *h_counters = nullptr;     // pinned host mirror, 8 per batch slot
 	size_t h_counters_bytes = 0;
+	DeviceBuf c_simple, c_full;         // compacted results of the batch (k_compact_results)
+	uint32_t *h_simple = nullptr, *h_full = nullptr;   // ... their pinned landing buffers
+	size_t h_simple_cap = 0, h_full_cap = 0;           // in records
+	cudaEvent_t ev_counts = nullptr, ev_records = nullptr;
 	sr::ScalarScratch *scratch = nullptr;
 	size_t scratch_threads = 0;
 };
@@ -442,6 +494,11 @@ struct srcuda_handle {
 	bool use_phase = true;         // SRCUDA_PHASE=0: no phase table for gapped sparse indexes (A/B and cross-checks)
 	// The single-end tier's one-indel closed form costs an error-free chunk 13 %, so it is launched only while the chunks hold such
 	// reads: after every call, from that call's counters (fragments queued + fragments it settled) -- the results are the same either way.
+	// Host-buffer entry point, first index block of a chunk (the caller's bigtable is all zero): the results cross PCIe compacted
+	// (k_compact_results) and expand_threads host threads scatter them into the caller's table.  On the bench box (16 host threads)
+	// that scatter runs at 380 M records/s, the DMA engine writes the full table at 250-270 M reads/s (profiles/r02_host_expand.txt).
+	bool compact_d2h = true;       // SRCUDA_COMPACT_D2H=0: always the plain copy
+	int expand_threads = 0;        // SRCUDA_EXPAND_THREADS; default: host threads / visible GPUs
 	int tier_indel_mode = -1;      // SRCUDA_TIER_INDEL: 0 never, 1 always, unset: by the last call
 	bool tier_indel = false;
 	int simple_indel_smem_set[4][5] = {}, simple_rmw_indel_smem_set[4][5] = {};
@@ -1037,6 +1094,11 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (st && st[0] == '0') h->use_simple_tier = false;
 	const char *ph = getenv("SRCUDA_PHASE");
 	if (ph && ph[0] == '0') h->use_phase = false;
+	const char *cd = getenv("SRCUDA_COMPACT_D2H");
+	if (cd && cd[0] == '0') h->compact_d2h = false;
+	const char *et = getenv("SRCUDA_EXPAND_THREADS");
+	h->expand_threads = et && atoi(et) > 0 ? atoi(et) : (int)std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, n));
+	if (h->expand_threads > 64) h->expand_threads = 64;
 	const char *ti = getenv("SRCUDA_TIER_INDEL");
 	if (ti && (ti[0] == '0' || ti[0] == '1')) { h->tier_indel_mode = ti[0] - '0'; h->tier_indel = ti[0] == '1'; }
 	const char *tr = getenv("SRCUDA_TIER_RMW");
@@ -1070,6 +1132,11 @@ void srcuda_close(srcuda_handle *h)
 		cudaFree(b.counters);
 		cudaFree(b.scratch);
 		if (b.h_counters) cudaFreeHost(b.h_counters);
+		cudaFree(b.c_simple.p); cudaFree(b.c_full.p);
+		if (b.h_simple) cudaFreeHost(b.h_simple);
+		if (b.h_full) cudaFreeHost(b.h_full);
+		if (b.ev_counts) cudaEventDestroy(b.ev_counts);
+		if (b.ev_records) cudaEventDestroy(b.ev_records);
 		if (b.stream) cudaStreamDestroy(b.stream);
 	}
 	for (cudaEvent_t e : h->events) cudaEventDestroy(e);
@@ -1358,6 +1425,122 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		memset(b.h_counters, 0, need);
 	}
 
+	// The results cross PCIe compacted when the caller's table is all zero (see srcuda_handle::compact_d2h): a helper thread follows the
+	// batches -- it waits for a batch's record counts, enqueues the copy of exactly that many records behind the batch's kernels,
+	// and scatters them into the caller's table from expand_threads threads while the GPU is busy with the batches behind.
+	const bool compact = h->compact_d2h && out_align_is_zero && !cfg.do_junctions && !out_verify && n_frags >= 256;
+	if (compact) {
+		const size_t nr_max = (size_t)std::min<int64_t>(batch, n_frags) * mates;
+		const size_t cap_s = nr_max + nr_max / 4 + 1024, cap_f = nr_max / 8 + 1024;
+		for (int i = 0; i < kSets && i < n_batches; i++) {
+			BatchSet &b = h->set[i];
+			if ((rc = ensure(h, b.c_simple, 24 * cap_s))) return rc;
+			if ((rc = ensure(h, b.c_full, 72 * cap_f))) return rc;
+			if (b.h_simple_cap < cap_s) {
+				if (b.h_simple) cudaFreeHost(b.h_simple);
+				b.h_simple = nullptr; b.h_simple_cap = 0;
+				CU(h, cudaHostAlloc((void **)&b.h_simple, 24 * cap_s, cudaHostAllocDefault));
+				b.h_simple_cap = cap_s;
+			}
+			if (b.h_full_cap < cap_f) {
+				if (b.h_full) cudaFreeHost(b.h_full);
+				b.h_full = nullptr; b.h_full_cap = 0;
+				CU(h, cudaHostAlloc((void **)&b.h_full, 72 * cap_f, cudaHostAllocDefault));
+				b.h_full_cap = cap_f;
+			}
+			if (!b.ev_counts) CU(h, cudaEventCreateWithFlags(&b.ev_counts, cudaEventDisableTiming));
+			if (!b.ev_records) CU(h, cudaEventCreateWithFlags(&b.ev_records, cudaEventDisableTiming));
+		}
+	}
+	struct Follow {
+		std::mutex mu;
+		std::condition_variable cv;
+		int64_t submitted = -1, enqueued = -1;   // last batch the main thread enqueued / whose record copies the helper enqueued
+		bool stop = false;
+		int rc = SRCUDA_OK;
+		std::string err;
+		uint64_t d2h = 0;
+	} follow;
+	auto expand = [&](const uint32_t *simple, uint32_t n_simple, const uint32_t *full, uint32_t n_full, srcuda_mapping_result *dst) {
+		const int T = std::max(1, std::min<int>(h->expand_threads, (int)((n_simple + n_full) / 4096) + 1));
+		auto part = [&](int t) {
+			for (uint32_t i = (uint32_t)((uint64_t)n_simple * t / T), e = (uint32_t)((uint64_t)n_simple * (t + 1) / T); i < e; i++) {
+				const uint32_t *r = simple + 6 * (size_t)i;
+				uint32_t *d = reinterpret_cast<uint32_t *>(dst + r[0]);
+				d[0] = r[1]; d[1] = r[2]; d[2] = r[3]; d[4] = r[4]; d[15] = r[5];
+			}
+			for (uint32_t i = (uint32_t)((uint64_t)n_full * t / T), e = (uint32_t)((uint64_t)n_full * (t + 1) / T); i < e; i++) {
+				const uint32_t *r = full + 18 * (size_t)i;
+				memcpy(dst + r[0], r + 1, sizeof(srcuda_mapping_result));
+			}
+		};
+		std::vector<std::thread> th;
+		for (int t = 1; t < T; t++) {
+			bool started = false;
+			try { th.emplace_back(part, t); started = true; } catch (...) {}
+			if (!started) part(t);
+		}
+		part(0);
+		for (auto &x : th) x.join();
+	};
+	auto follower = [&]() {
+		cudaSetDevice(h->device);
+		for (int64_t bi = 0; bi < n_batches; bi++) {
+			{
+				std::unique_lock<std::mutex> lk(follow.mu);
+				follow.cv.wait(lk, [&] { return follow.submitted >= bi || follow.stop; });
+				if (follow.submitted < bi) return;           // the main thread gave up
+			}
+			BatchSet &bs = h->set[bi % kSets];
+			const int64_t f0 = bi * batch, nf = std::min(n_frags, f0 + batch) - f0;
+			const size_t r0 = (size_t)f0 * mates, n_slots = (size_t)nf * mates * mb;
+			cudaError_t e = cudaEventSynchronize(bs.ev_counts);
+			const uint32_t *c = bs.h_counters + 8 * (bi / kSets);
+			const uint32_t n_simple = c[5], n_full = c[6];
+			const bool plain = c[7] != 0 || n_simple > bs.h_simple_cap || n_full > bs.h_full_cap;
+			if (e == cudaSuccess) {
+				if (plain) e = cudaMemcpyAsync(out_align + r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, bs.stream);
+				else {
+					if (n_simple) e = cudaMemcpyAsync(bs.h_simple, bs.c_simple.p, 24 * (size_t)n_simple, cudaMemcpyDeviceToHost, bs.stream);
+					if (e == cudaSuccess && n_full) e = cudaMemcpyAsync(bs.h_full, bs.c_full.p, 72 * (size_t)n_full, cudaMemcpyDeviceToHost, bs.stream);
+				}
+			}
+			if (e == cudaSuccess) e = cudaEventRecord(bs.ev_records, bs.stream);
+			{
+				std::lock_guard<std::mutex> g(follow.mu);
+				follow.enqueued = bi;                         // the batch's device buffers may be overwritten by the one kSets further on
+				if (e != cudaSuccess) { follow.rc = SRCUDA_ERR_CUDA; follow.err = cudaGetErrorString(e); follow.stop = true; }
+			}
+			follow.cv.notify_all();
+			if (e != cudaSuccess) return;
+			e = cudaEventSynchronize(bs.ev_records);
+			if (e != cudaSuccess) {
+				std::lock_guard<std::mutex> g(follow.mu);
+				follow.rc = SRCUDA_ERR_CUDA; follow.err = cudaGetErrorString(e); follow.stop = true;
+				follow.cv.notify_all();
+				return;
+			}
+			if (plain) follow.d2h += sizeof(srcuda_mapping_result) * n_slots;
+			else {
+				follow.d2h += 24 * (uint64_t)n_simple + 72 * (uint64_t)n_full;
+				expand(bs.h_simple, n_simple, bs.h_full, n_full, out_align + r0 * mb);
+			}
+		}
+	};
+	std::thread follow_thread;
+	if (compact) {
+		try { follow_thread = std::thread(follower); } catch (...) { return fail(h, SRCUDA_ERR_NOMEM, "cannot start the result thread"); }
+	}
+	auto stop_follower = [&]() {
+		if (!follow_thread.joinable()) return;
+		{
+			std::lock_guard<std::mutex> g(follow.mu);
+			follow.stop = true;
+		}
+		follow.cv.notify_all();
+		follow_thread.join();
+	};
+
 	// A batch is checked right before it is enqueued (so that checking batch k + 1 overlaps the copies and kernels of batch k: the
 	// scan of 10 M reads is 12 ms of host time); once a batch is in flight the caller's buffers are the source and target of
 	// asynchronous copies, so a refusal further down drains the streams before it returns.
@@ -1377,6 +1560,7 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 	};
 	// any failure from here on waits for the copies already enqueued before it returns
 	auto drain = [&](int rc_in) {
+		stop_follower();
 		for (int i = 0; i < kSets; i++) if (h->set[i].stream) cudaStreamSynchronize(h->set[i].stream);
 		cudaGetLastError();
 		return rc_in;
@@ -1396,6 +1580,11 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		const int64_t r0 = f0 * mates, nr = nf * mates;
 		int max_len = 1;
 		if ((rc = check_batch(r0, r0 + nr, &max_len))) return drain(rc);
+		if (compact && bi >= kSets) {                    // the batch that used this set before must have its record copies enqueued
+			std::unique_lock<std::mutex> lk(follow.mu);
+			follow.cv.wait(lk, [&] { return follow.enqueued >= bi - kSets || follow.stop; });
+			if (follow.stop) { lk.unlock(); return drain(fail(h, follow.rc ? follow.rc : SRCUDA_ERR_CUDA, "copying the results failed: %s", follow.err.c_str())); }
+		}
 		const uint64_t origin = off[r0];
 		const uint64_t text_bytes = off[r0 + nr - 1] + len[r0 + nr - 1] - origin;
 		const size_t n_slots = (size_t)nr * mb;
@@ -1436,8 +1625,16 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 		a.junc = cfg.do_junctions ? (sr::JuncWords *)bs.junc.p : nullptr;
 		a.big_margin = cfg.do_junctions ? (uint16_t *)bs.big_margin.p : nullptr;
 		if ((rc = launch_vote(h, s, cfg, a, max_len, bs, &h->events[4 * bi]))) return drain(rc);
-		CUD(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
-		h->timing.d2h_bytes += sizeof(srcuda_mapping_result) * n_slots;
+		if (compact) {
+			sr::k_compact_results<<<h->sm_count * 8, 256, 0, s>>>((const sr::ResultWords *)bs.out.p, (uint32_t)n_slots, (uint32_t *)bs.c_simple.p,
+			                                                      (uint32_t)std::min<size_t>(bs.h_simple_cap, bs.c_simple.cap / 24), (uint32_t *)bs.c_full.p,
+			                                                      (uint32_t)std::min<size_t>(bs.h_full_cap, bs.c_full.cap / 72), bs.counters);
+			CUD(h, cudaGetLastError());
+			h->timing.n_launches++;
+		} else {
+			CUD(h, cudaMemcpyAsync(out_align + (size_t)r0 * mb, bs.out.p, sizeof(srcuda_mapping_result) * n_slots, cudaMemcpyDeviceToHost, s));
+			h->timing.d2h_bytes += sizeof(srcuda_mapping_result) * n_slots;
+		}
 		if (out_verify) {
 			CUD(h, cudaMemcpyAsync(out_verify + (size_t)r0 * mb, bs.verify.p, sizeof(uint16_t) * n_slots, cudaMemcpyDeviceToHost, s));
 			h->timing.d2h_bytes += sizeof(uint16_t) * n_slots;
@@ -1448,6 +1645,19 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 			h->timing.d2h_bytes += sizeof(srcuda_subjunc_result) * n_slots + bm_bytes;
 		}
 		CUD(h, cudaMemcpyAsync(bs.h_counters + 8 * (bi / kSets), bs.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		if (compact) {
+			CUD(h, cudaEventRecord(bs.ev_counts, s));
+			{
+				std::lock_guard<std::mutex> g(follow.mu);
+				follow.submitted = bi;
+			}
+			follow.cv.notify_all();
+		}
+	}
+	if (compact) {                                       // the helper enqueues the last copies and scatters the last records
+		follow_thread.join();
+		if (follow.rc) return drain(fail(h, follow.rc, "copying the results failed: %s", follow.err.c_str()));
+		h->timing.d2h_bytes += follow.d2h;
 	}
 	for (int i = 1; i < kSets; i++) {  // join every stream into stream 0, then stamp the end there
 		CUD(h, cudaEventRecord(h->ev_join[i], h->set[i].stream));

@@ -51,7 +51,8 @@ struct Stream {
 	bool ended = false;             // the grammar ended the input (end of file, or a read trimmed to nothing)
 	uint64_t file_pos = 0;          // file offset (inflated bytes) of win[0]
 	std::vector<uint64_t> off;      // indexed, not yet handed out: records [cursor, n)
-	std::vector<uint16_t> len;
+	std::vector<uint64_t> name_off; // ... and where their names begin (srcuda_reader_tell: a record starts one byte earlier, at its '@')
+	std::vector<uint16_t> len, name_len;
 	int64_t n = 0, cursor = 0;
 	int64_t pending() const { return n - cursor; }
 };
@@ -223,10 +224,10 @@ int refill(srcuda_reader *r, int which)
 		// room for records of 32 bytes and more; shorter ones just take another round (SRCUDA_FASTQ_FULL leaves the rest
 		// of the window for the next refill)
 		const size_t cap = st.have / 32 + 1024;
-		if (st.off.size() < cap) { st.off.resize(cap); st.len.resize(cap); }
+		if (st.off.size() < cap) { st.off.resize(cap); st.len.resize(cap); st.name_off.resize(cap); st.name_len.resize(cap); }
 		srcuda_fastq_batch b;
 		const int rc = srcuda_fastq_split_mt(st.win.data(), st.have, st.eof ? 1 : 0, r->trim_5, r->trim_3, (int64_t)cap, 0, 1, st.off.data(),
-		                                     st.len.data(), nullptr, nullptr, nullptr, nullptr, r->threads, &b);
+		                                     st.len.data(), st.name_off.data(), st.name_len.data(), nullptr, nullptr, r->threads, &b);
 		if (rc == SRCUDA_ERR_FORMAT && b.n_reads == 0)
 			return fail(r, rc, "input file %d: a format issue at byte %llu (a record must start with '@' and have a '+' line)", which + 1,
 			            (unsigned long long)(st.file_pos + b.error_offset));
@@ -386,6 +387,19 @@ extern "C" int srcuda_reader_skip(srcuda_reader *r, int64_t n_frags, int64_t *sk
 	const int rc = srcuda_reader_next(r, n_frags, nullptr, 0, nullptr, nullptr, &n, nullptr);
 	if (skipped) *skipped = n;
 	return rc;
+}
+
+extern "C" int srcuda_reader_tell(const srcuda_reader *r, uint64_t *pos1, uint64_t *pos2)
+{
+	if (!r || !pos1) return SRCUDA_ERR_ARG;
+	uint64_t *out[2] = {pos1, pos2};
+	for (int i = 0; i < r->files; i++) {
+		const Stream &st = r->s[i];
+		// behind the last record handed out: where the next one begins (its '@'), or the end of what has been indexed
+		const uint64_t in_win = st.cursor < st.n ? st.name_off[(size_t)st.cursor] - 1 : (uint64_t)st.consumed;
+		if (out[i]) *out[i] = st.file_pos + in_win;
+	}
+	return SRCUDA_OK;
 }
 
 extern "C" const char *srcuda_reader_error(const srcuda_reader *r) { return r ? r->error.c_str() : "null reader"; }

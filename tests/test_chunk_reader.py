@@ -205,3 +205,36 @@ def test_gzip_cut_at_a_flush_point_is_an_error(threads, where, tmp_path):
         fh.write(gzip.compress(b"".join(rec), compresslevel=1))
     reads, _ = read_all(full, batch=3000, threads=threads, window_bytes=1 << 20)
     assert len(reads) == 20000
+
+
+@pytest.mark.parametrize("window,threads", [(4096, 1), (1 << 16, 3)])
+def test_tell_points_behind_the_last_fragment_handed_out(window, threads, tmp_path):
+    """srcuda_reader_tell: after every batch the offsets are where a second reader -- the reference's gene_input_t under the
+    binding -- has to continue: parsing the files from there yields exactly the fragments not handed out yet."""
+    rnd = random.Random(12)
+    recs1, recs2 = [], []
+    for i in range(3000):
+        n = 20 + (i * 13) % 140
+        recs1.append(b"@a%d\n%s\n+\n%s\n%s" % (i, bytes(rnd.choice(b"ACGT") for _ in range(n)), b"I" * n, b"\n" if i % 17 == 0 else b""))
+        recs2.append(b"@b%d/2 x\n%s\n+b%d\n%s\n" % (i, bytes(rnd.choice(b"ACGT") for _ in range(n + 3)), i, b"H" * (n + 3)))
+    p1, p2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    d1, d2 = b"".join(recs1), b"".join(recs2)
+    open(p1, "wb").write(d1)
+    open(p2, "wb").write(d2)
+    rd = binding.ChunkReader(p1, p2, window_bytes=window, threads=threads)
+    assert rd.tell() == (0, 0)
+    done = 0
+    for batch in (1, 7, 500, 123, 1000, 5000):
+        n = rd.next(batch)[3]
+        done += n
+        a, b = rd.tell()
+        for data, pos, tag in ((d1, a, b"@a"), (d2, b, b"@b")):
+            rest = data[pos:]
+            if done < 3000:
+                assert rest.startswith(tag + str(done).encode()), (batch, done, rest[:20])
+            else:
+                assert rest.strip(b"\n") == b""
+            left = binding.fastq_split(np.frombuffer(rest, dtype=np.uint8))[2].n_reads if rest else 0
+            assert left == 3000 - done
+    assert done == 3000
+    rd.close()

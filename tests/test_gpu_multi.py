@@ -48,7 +48,9 @@ def test_chunk_over_several_handles_equals_one_handle(case_name, n_handles, gold
     ts = mm.timings()
     for k, t in enumerate(ts):
         f0, f1 = shard_range(chunk.n_frags, n_handles, k)
-        assert t.d2h_bytes >= (f1 - f0) * chunk.mates * params.multi_best_reads * 68
+        n_reads = (f1 - f0) * chunk.mates
+        assert t.h2d_bytes >= int(chunk.len[f0 * chunk.mates:f1 * chunk.mates].sum()) + 10 * n_reads      # its reads, offsets and lengths went up
+        assert 0 < t.d2h_bytes <= n_reads * params.multi_best_reads * 68 * (2 if subjunc else 1) + 64 * n_reads   # ... its results came down (compacted on a zero table)
         assert t.n_batches >= 1
     # a second pass over the same table (later index block): read-modify-write through the slices
     again, _ = mm.vote_chunk(chunk, params, out_align=got.copy().reshape(-1), junc_state=jsm)

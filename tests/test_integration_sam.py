@@ -70,3 +70,35 @@ def test_subjunc_sam_identical_to_stock_subjunc(devices, tmp_path):
     assert outs[0][0] == outs[1][0], "SAM records differ"
     assert outs[0][1] is not None and outs[0][1] == outs[1][1], "junction tables differ"
     assert outs[0][1].count(b"\n") > 10
+
+
+REF_DUMP = os.path.join(REF_DIR, "ref_dump")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_DUMP) and os.path.exists(CUDA)), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("paired,gz,reader", [(False, False, "1"), (True, False, "1"), (True, True, "1"), (True, False, "0")],
+                         ids=["se_plain_library_reader", "pe_plain_library_reader", "pe_gzip_reference_reader", "pe_plain_reference_reader"])
+def test_sam_identical_over_several_chunks(paired, gz, reader, tmp_path):
+    """The chunk loop (read_chunk_circles, core.c:3539): 20 000 fragments in chunks of 6 000 (a test knob both binaries carry, since
+    the real chunk is 7 M reads), so that the bound binary goes through chunk start / chunk end / next chunk several times.  With
+    plain FASTQ input it reads every chunk through the library's own reader (srcuda_reader_*) and moves the reference's files on
+    to where that reader stopped; with gzip input (or SRCUDA_BINDING_READER=0) through fetch_next_read_pair.  SAM identical to the
+    unmodified reference's either way."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 4, 400000, seed=77, repeats=100)
+    prefix = str(tmp_path / "idx")
+    subprocess.run([BUILDINDEX, "-B", "-o", prefix, fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    gen_data.write_reads(fa, str(tmp_path / "r"), 20000, 110, 19, paired, 0.01, 0.15, True, 0.002, gz=gz)
+    ext = ".fastq.gz" if gz else ".fastq"
+    reads = ["-r", str(tmp_path / ("r_R1" + ext))] + (["-R", str(tmp_path / ("r_R2" + ext))] if paired else [])
+    env = dict(os.environ, SUBREAD_TEST_READS_PER_CHUNK="6000", SRCUDA_BINDING_READER=reader)
+    outs = []
+    for exe, tag in ((REF_DUMP, "stock"), (CUDA, "cuda")):
+        out = str(tmp_path / f"{tag}.sam")
+        subprocess.run([exe, "-t", "1", "-T", "3", "-i", prefix] + reads + ["--SAMoutput", "-o", out], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+        outs.append(sam_body(out))
+    assert outs[0].count(b"\n") >= 20000 * (2 if paired else 1)
+    assert outs[0] == outs[1]

@@ -1,13 +1,19 @@
 #!/bin/bash
-# tools/gpu_round.sh TAG -- the evidence set of one kernel version on a B200 box (run under gpurun):
-# GPU parity tests, default bench (both arms), ncu launch list and one ncu --set full capture of the voting kernels.
-TAG=${1:-r01}
+# tools/gpu_round.sh TAG -- the evidence set of one kernel version on a B200 box (run under gpurun): GPU parity tests, the bench
+# workloads (both arms on the default one), ncu launch list and ncu --set full captures of the fast tier's kernels, host-expand micro.
+TAG=${1:-r02}
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/gpu.txt; nproc > gpurun_out/host.txt
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu_$TAG.log
-python bench.py > gpurun_out/bench_$TAG.log 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; tail -c 2500 gpurun_out/bench_$TAG.log
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; echo "ref rc=$?"; tail -c 900 gpurun_out/bench_ref_$TAG.log
+nvidia-smi -L > gpurun_out/gpu_$TAG.txt; nproc >> gpurun_out/gpu_$TAG.txt; free -g | head -2 >> gpurun_out/gpu_$TAG.txt
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu_$TAG.log
+python bench.py > gpurun_out/bench_cfg2_se_$TAG.log 2> gpurun_out/bench_cfg2_se_$TAG.err; echo "bench rc=$?"; tail -c 300 gpurun_out/bench_cfg2_se_$TAG.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_cfg2_se_$TAG.log 2>&1; echo "ref rc=$?"
+for wl in mixed human_pe human_subjunc; do
+  python bench.py --workload $wl --no-cpu-baseline --steps 3 > gpurun_out/bench_${wl}_$TAG.log 2> gpurun_out/bench_${wl}_$TAG.err; echo "$wl rc=$?"; tail -c 200 gpurun_out/bench_${wl}_$TAG.err
+done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:k_map_ -s 3 -c 2 -f -o gpurun_out/prof_$TAG \
-    python bench.py --reads 2000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_map_simple -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_cfg2_se \
+    python bench.py --reads 2000000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_cfg2_se_$TAG.log 2>&1; echo "ncu full cfg2_se rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_map_simple_pe -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_human_pe \
+    python bench.py --workload human_pe --reads 1000000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full_human_pe_$TAG.log 2>&1; echo "ncu full human_pe rc=$?"
+g++ -O2 -pthread -o /tmp/host_expand tools/micro/host_expand.cpp && (/tmp/host_expand 10000000 $(nproc) 0; /tmp/host_expand 10000000 $(nproc) 1) > gpurun_out/host_expand_$TAG.txt 2>&1

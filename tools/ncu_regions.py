@@ -9,8 +9,10 @@ def find(pat):
         if pat in l:
             return i + 1
 marks = [("structs", 1), ("simple_hit", find("bool simple_hit(")), ("pack", find("bool simple_pack")), ("offsets/key", find("int simple_sub_offset")), ("probe", find("int simple_probe")),
-         ("general", find("bool simple_general(")), ("pass-setup", find("bool simple_pass")), ("filter", find("// ---- (1) filter ----")), ("pool", find("// (2a) pool")), ("lookup", find("// (2b) lookup")),
-         ("apply", find("// (3) apply")), ("rest", find("// ---- (4) everything else")),
+         ("general", find("bool simple_general(")), ("primary/indel", find("bool simple_primary_hit(")), ("filter(mode 0/2)", find("unsigned simple_filter(")),
+         ("phase: occupancy bits", find("// ---- (1) which units hold anything ----")), ("phase: units", find("// ---- (2) the subreads left: one unit each ----")),
+         ("phase: general", find("// ---- (3) everything else, on the general path ----")), ("phase dense", find("bool simple_pass_phase_dense(")),
+         ("pass (mode 0/2)", find("bool simple_pass(const DevIndex")),
          ("update_top", find("// update_top_three")), ("merge", find("void simple_merge")), ("kernel", find("k_map_simple(const DevIndex ix"))]
 marks = [m for m in marks if m[1]]
 agg = collections.OrderedDict((m[0], [0, 0, 0]) for m in marks)
