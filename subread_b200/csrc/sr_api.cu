@@ -514,6 +514,7 @@ struct srcuda_handle {
 	bool force_slow = false;
 	bool use_simple_tier = true;   // SRCUDA_SIMPLE_TIER=0 disables tier 0 (A/B and cross-checks)
 	bool use_simple_tier_pe = true;  // SRCUDA_SIMPLE_TIER_PE=0 disables its paired-end form only
+	int pe_pool_dense = 0;           // SRCUDA_PE_POOL: vote clusters of both mates of a strand pass on a dense table (A/B: shared memory per thread bounds the resident warps); 0 = kPePoolDense
 	bool use_warp_junc = true;       // SRCUDA_WARP_JUNC=0: subjunc fragments all take the scalar path
 	bool use_tier_junc = true;       // SRCUDA_TIER_JUNC=0: subjunc chunks skip the thread-per-fragment tier
 	int simple_junc_smem_set[4][5] = {}, simple_pe_junc_smem_set[4][5] = {}, simple_rmw_smem_set[4][5] = {}, simple_pe_rmw_smem_set[4][5] = {};
@@ -921,7 +922,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	if (tier0_pe) {
 		const int threads = sr::kSimpleThreads;
 		const int64_t blocks = (a.n_frags + threads - 1) / threads;
-		const int clusters = h->ix.direct ? (cfg.do_junctions ? sr::kPePoolDenseJunc : sr::kPePoolDense) : sr::kPePool;     // one pool for both mates
+		const int clusters = h->ix.direct ? (cfg.do_junctions ? sr::kPePoolDenseJunc : (h->pe_pool_dense ? h->pe_pool_dense : sr::kPePoolDense)) : sr::kPePool;     // one pool for both mates
 		const int smem = sr::simple_pe_smem_bytes(max_len, clusters);
 		uint32_t *q0 = (uint32_t *)bs.queue0.p;
 #define SR_LAUNCH_PE_U(G, U)                                                                                                         \
@@ -1109,6 +1110,8 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (wj && wj[0] == '0') h->use_warp_junc = false;
 	const char *stp = getenv("SRCUDA_SIMPLE_TIER_PE");
 	if (stp && stp[0] == '0') h->use_simple_tier_pe = false;
+	const char *pp = getenv("SRCUDA_PE_POOL");
+	if (pp && atoi(pp) >= 4 && atoi(pp) <= 32) h->pe_pool_dense = atoi(pp);
 	const char *ac = getenv("SRCUDA_ACCEL");  // 0 off, 1 bloom, 2 records, 3 both, 4 direct filter; default auto
 	if (ac && ac[0] >= '0' && ac[0] <= '4') h->accel_mode = ac[0] - '0';
 	const char *fg = getenv("SRCUDA_L2_FETCH");  // L2 fetch granularity hint in bytes: 32, 64 or 128

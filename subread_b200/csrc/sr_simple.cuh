@@ -56,6 +56,27 @@
 #define SR_SIMPLE_DEFER_LIMIT 3    // lookups of one batch a lane may take through the general path before the fragment is queued for the warp kernel
                                    // (A/B on B200: mixed workload 419 -> 446 M reads/s, clean 1 502 -> 1 533 M)
 #endif
+#ifndef SR_DENSE_PF_DIST
+#define SR_DENSE_PF_DIST 0     // (measured: 3 and 6 cost 7 % -- the extra key extraction and the doubled DRAM bytes outweigh what they hide) dense phase units (MODE 4): how many subreads beyond the register fetch their units are asked for (prefetch.global.L2); 0 = off
+#endif
+#ifndef SR_DENSE_PF_NEXT
+#define SR_DENSE_PF_NEXT 0     // ... and how many units of the NEXT pass the paired-end tier asks for before it starts a pass; 0 = off
+#endif
+#ifndef SR_DENSE_HIT_V2
+#define SR_DENSE_HIT_V2 1      // ... two sieves in front of the cluster list and one body for "last cluster" / "new cluster".  A/B switch
+#endif
+#ifndef SR_DENSE_R64
+#define SR_DENSE_R64 0         // ... 64 bytes of a unit in registers (values 0 .. 11 picked by selects) instead of 32 + a second load.  A/B switch
+#endif
+#ifndef SR_DENSE_FLAT_PIPE
+#define SR_DENSE_FLAT_PIPE 1   // ... positions of keys with several: the next one's load under way while this one is applied.  A/B switch
+#endif
+#ifndef SR_DENSE_PROBE3
+#define SR_DENSE_PROBE3 1      // ... the first three clusters tried before the walk over the list.  A/B switch
+#endif
+#ifndef SR_DENSE_TWO_PHASE
+#define SR_DENSE_TWO_PHASE 1   // ... the three roles of a unit in two steps (loads first), direct_first entries read behind the subread loop.  A/B switch
+#endif
 #ifndef SR_SIMPLE_SMEM_OUT
 #define SR_SIMPLE_SMEM_OUT 0   // compose the warp's bigtable slice in shared memory and store whole sectors (A/B switch)
 #endif
@@ -117,7 +138,7 @@ struct SimpleCluster {
 	__device__ __forceinline__ int votes() const { return (w1 >> 31) ? __popcll(subs) : 0; }
 	__device__ __forceinline__ int first_l() const { return (int)(w1 & 255u); }
 	__device__ __forceinline__ int last_l() const { return (int)((w1 >> 8) & 255u); }
-	__device__ __forceinline__ int order() const { return (int)(((w1 >> 24) & 31u) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u)); }
+	__device__ __forceinline__ int order() const { return (int)(vote_row(kv) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u)); }
 };
 
 // The clusters of the running pass in shared memory, four words each, interleaved over the warp's lanes.
@@ -129,7 +150,7 @@ struct SimpleClusters {
 	__device__ __forceinline__ int order(int c) const
 	{
 		const uint32_t w1 = w(c, 1);
-		return (int)(((w1 >> 24) & 31u) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u));
+		return (int)(vote_row(w(c, 0)) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u));   // (the row from kv itself: w1's row field is not always filled)
 	}
 	__device__ __forceinline__ SimpleCluster get(int c) const
 	{
@@ -740,6 +761,70 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 	// nor within the tolerance (<= 8) of any cluster and opens a new one unseen; and the cluster the last hit was found equal to
 	// (the true cluster, as a rule) is tried first -- two clusters of the list are never within tolerance of each other, so a hit
 	// that equals one needs no look at the others.
+#if SR_DENSE_HIT_V2
+	// (round 2, second version) Three 32-bit sieves in front of the cluster list.  occ_a / occ_b: one bit per 16 consecutive kv, at
+	// two alignments 8 apart -- two kv within the tolerance (<= 8) of each other share a bin in one of them; occ_f: one bit per 512.
+	// A cluster near the hit shows in (a or b) AND in f; a chance cluster of a 3 Gbp table does so one time in 500, so the walk over
+	// the list (a quarter of the kernel's instructions, two lanes of 32 at a time) is left to the hits that do have a neighbour.
+	// The two common cases, "the cluster of the last hit" and "a new cluster", share one body that touches only the words it
+	// changes, so the lanes of a warp that hold either run it together (155 -> ~40 instructions per hit).
+	uint32_t occ_a = 0, occ_b = 0, occ_f = 0;
+	uint32_t last_kv = 0;
+	int last_c = -1;
+	auto hit = [&](uint32_t kv, int l, int u, int sub) -> bool {
+		bool same = last_c >= 0 && kv == last_kv;
+		const uint32_t ba = 1u << ((kv >> 4) & 31u), bb = 1u << (((kv + 8u) >> 4) & 31u);
+		const uint32_t bf = (1u << (((kv - 8u) >> 9) & 31u)) | (1u << (((kv + 8u) >> 9) & 31u));
+		const bool clear = (tol <= 8) & ((((occ_a & ba) | (occ_b & bb)) == 0u) | ((occ_f & bf) == 0u));
+#if SR_DENSE_PROBE3
+		// The second hit of the true cluster finds no `last` yet and the sieves set: as a rule that cluster was opened by the read's
+		// first subread, so the first three of the list are tried before the walk (an equal one settles it: no two clusters of the
+		// list are within tolerance of each other).
+		if (!same && !clear && last_c < 0) {
+			const int np = min(C.n, 3);
+			int j = -1;
+			if (np > 0 && C.w(0, 0) == kv) j = 0;
+			else if (np > 1 && C.w(1, 0) == kv) j = 1;
+			else if (np > 2 && C.w(2, 0) == kv) j = 2;
+			if (j >= 0) { last_c = j; last_kv = kv; same = true; }
+		}
+#endif
+		// (bitwise on purpose: with && / || the compiler sends the `same` lanes into the body ahead of the others and the body runs twice)
+		const bool fresh = (!same) & clear;
+		if (same | fresh) {
+			if (fresh && (!(kv >= 32u && kv <= 0xffffffdfu) || C.n >= C.cap)) return false;
+			const int idx = same ? last_c : C.n;
+			const int wi = 2 + (sub >> 5);
+			const uint32_t bit = 1u << (sub & 31);
+			uint32_t w1 = (kv >= low && kv <= high) ? ((uint32_t)l | ((uint32_t)l << 8) | ((uint32_t)u << 16) | 0x80000000u) : 0u;   // :1074
+			uint32_t sw = 0u;
+			if (same) { w1 = C.w(idx, 1); sw = C.w(idx, wi); }
+			if (w1 >> 31) {
+				if (sw & bit) return false;                            // one subread twice: the reference opens a duplicate slot
+				sw |= bit;
+				if ((uint32_t)l < (w1 & 255u)) w1 = (w1 & ~0x007f00ffu) | (uint32_t)l | ((uint32_t)u << 16);
+				if ((uint32_t)l > ((w1 >> 8) & 255u)) w1 = (w1 & ~0x0000ff00u) | ((uint32_t)l << 8);
+			}
+			if (fresh) {
+				C.w(idx, 0) = kv;
+				C.w(idx, 5 - wi) = 0u;
+				C.n++;
+				occ_a |= ba;
+				occ_b |= bb;
+				occ_f |= 1u << ((kv >> 9) & 31u);
+			}
+			C.w(idx, 1) = w1;
+			C.w(idx, wi) = sw;
+			return true;
+		}
+		int found = -1;
+		const int n0 = C.n;
+		if (!simple_hit(C, kv, l, u, sub, tol, low, high, &found)) return false;
+		if (C.n > n0) { occ_a |= ba; occ_b |= bb; occ_f |= 1u << ((kv >> 9) & 31u); }
+		if (found >= 0) { last_kv = kv; last_c = found; }
+		return true;
+	};
+#else
 	unsigned long long occ = 0;
 	uint32_t last_kv = 0;
 	int last_c = -1;
@@ -770,6 +855,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		if (found >= 0) { last_kv = kv; last_c = found; }
 		return true;
 	};
+#endif
 	for (int s_base = 0; s_base < applied && ok; s_base += kSubs) {
 		const int n_sub = min(kSubs, applied - s_base), base = s_base * GAP;
 		uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // runs of keys with several positions waiting to be applied:
@@ -777,24 +863,99 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		int ne = 0;
 		unsigned slow = 0;                               // lookups the unit could not answer (value beyond its 28, a fifth run): the direct filter does
 		Record8 rn;
+#if SR_DENSE_R64
+		Record8 rn2;                                     // the second 32 bytes of the same 64-byte fetch: values 4 .. 11
+#endif
 		uint32_t k0_next = 0;
 		auto issue = [&](int si) {
 			k0_next = simple_key_at<RCKEYS>(pk, simple_sub_offset<GAP>(s_base + min(si, n_sub - 1), step), rc_len);
 			rn = ld_record(units4, 4u * (k0_next & kPhaseMask));         // (ld_record counts in 32-byte records: a unit is four)
+#if SR_DENSE_R64
+			rn2 = ld_record(units4, 4u * (k0_next & kPhaseMask) + 1u);
+#endif
 			n_gather++;
 		};
+#if SR_DENSE_PF_DIST > 0
+		// Every address of the pass follows from the read alone, so the units further down are asked for now (whole 128-byte lines
+		// into L2, no register held): the register fetch one iteration ahead then meets L2, and so do the values past the unit's
+		// first 32 bytes.  Without it a warp met DRAM latency three times per subread (profiles/r02_human_pe_tier.md).
+		auto ask = [&](int si) {
+			if (si < n_sub) prefetch_l2(units4 + 8u * (size_t)(simple_key_at<RCKEYS>(pk, simple_sub_offset<GAP>(s_base + si, step), rc_len) & kPhaseMask));
+		};
+#pragma unroll
+		for (int i = 2; i <= SR_DENSE_PF_DIST; i++) ask(i);
+#endif
 		issue(0);
 #pragma unroll 1
 		for (int si = 0; si < n_sub; si++) {
 			const Record8 r = rn;
+#if SR_DENSE_R64
+			const Record8 r2 = rn2;
+#endif
 			const int sub = s_base + si;
 			const uint32_t k0 = k0_next;
 			if (si + 1 < n_sub) issue(si + 1);
+#if SR_DENSE_PF_DIST > 0
+			ask(si + 1 + SR_DENSE_PF_DIST);
+#endif
 			const int ob = simple_sub_offset<GAP>(sub, step);            // (the other two keys only now: fewer registers across the fetch)
 			const uint32_t k1 = simple_key_at<RCKEYS>(pk, ob + 1, rc_len), k2 = simple_key_at<RCKEYS>(pk, ob + 2, rc_len);
 			const uint32_t c = k0 & kPhaseMask;
 			if (((k1 >> 2) & kPhaseMask) != c || (k2 >> 4) != c) { slow |= 7u << (3 * si); continue; }
 			const uint32_t p0 = r.w[0] & 0x55555555u, p1 = r.w[1] & 0x55555555u;
+#if SR_DENSE_TWO_PHASE
+			// (a) what the unit says about the three keys, the loads of the values it does not hold in its first 32 bytes all under
+			// way before any is used; (b) the entries of keys with several positions asked for (they are read after the loop);
+			// (c) the single positions applied
+			uint32_t val[3];
+			int st[3];                                                   // 0 nothing, 1 one position, 2 several
+#pragma unroll
+			for (int x = 0; x < 3; x++) {
+				const uint32_t key = x == 0 ? k0 : (x == 1 ? k1 : k2), v = phase_variant(key, x);
+				const uint32_t wx = x == 0 ? r.w[0] : (x == 1 ? r.w[1] : r.w[2]);
+				const uint32_t two = (wx >> (2 * v)) & 3u;
+				st[x] = 0;
+				val[x] = 0;
+				if (!(two & 1u)) continue;
+				const int rank = __popc(wx & 0x55555555u & ((1u << (2 * v)) - 1u)) + (x > 0 ? __popc(p0) : 0) + (x > 1 ? __popc(p1) : 0);
+				if (rank >= kPhaseDenseValues) { slow |= 1u << (3 * si + x); continue; }
+				st[x] = 1 + (int)((two >> 1) & 1u);
+#if SR_DENSE_R64
+				if (rank < 12) {                                         // out of the 64 bytes in registers: no second trip
+					const int j = rank & 3;
+					const uint32_t v0 = j == 0 ? r.w[4] : (j == 1 ? r.w[5] : (j == 2 ? r.w[6] : r.w[7]));
+					const uint32_t v1 = j == 0 ? r2.w[0] : (j == 1 ? r2.w[1] : (j == 2 ? r2.w[2] : r2.w[3]));
+					const uint32_t v2 = j == 0 ? r2.w[4] : (j == 1 ? r2.w[5] : (j == 2 ? r2.w[6] : r2.w[7]));
+					val[x] = rank < 4 ? v0 : (rank < 8 ? v1 : v2);
+				} else {
+					val[x] = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);
+					n_gather++;                                                                    // (the unit's second half: another fetch)
+				}
+#else
+				if (rank < 4) val[x] = rank == 0 ? r.w[4] : (rank == 1 ? r.w[5] : (rank == 2 ? r.w[6] : r.w[7]));
+				else {
+					val[x] = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);
+					if (rank >= 12) n_gather++;                                                    // (the unit's second half: another fetch)
+				}
+#endif
+			}
+#pragma unroll
+			for (int x = 0; x < 3; x++)
+				if (st[x] == 2) { prefetch_l2(ix.direct_first + val[x]); n_gather++; }
+#pragma unroll
+			for (int x = 0; x < 3; x++) {
+				const int li = 3 * si + x, l = base + li;
+				if (st[x] == 1) { if (!hit(val[x] - (uint32_t)(ob + x), l, 0, sub)) ok = false; }
+				else if (st[x] == 2) {                                       // rank of its direct_first entry; read behind the loop
+					const uint32_t me = (uint32_t)l << 16;
+					if (ne == 0) { ra0 = val[x]; me0 = me; ne = 1; }
+					else if (ne == 1) { ra1 = val[x]; me1 = me; ne = 2; }
+					else if (ne == 2) { ra2 = val[x]; me2 = me; ne = 3; }
+					else if (ne == 3) { ra3 = val[x]; me3 = me; ne = 4; }
+					else slow |= 1u << li;
+				}
+			}
+#else
 #pragma unroll
 			for (int x = 0; x < 3; x++) {
 				const uint32_t key = x == 0 ? k0 : (x == 1 ? k1 : k2), v = phase_variant(key, x);
@@ -823,7 +984,26 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 					else slow |= 1u << li;
 				}
 			}
+#endif
 		}
+#if SR_DENSE_TWO_PHASE
+		// the entries asked for in the loop (ra = their rank so far): all four loads under way, then run start, length and landing
+		// index in place of the rank, and the runs' positions asked for in turn
+		if (ok && ne) {
+			uint2 e0 = make_uint2(0u, 0u), e1 = e0, e2 = e0, e3 = e0;
+			e0 = ld_direct_first(ix, ra0);
+			if (ne > 1) e1 = ld_direct_first(ix, ra1);
+			if (ne > 2) e2 = ld_direct_first(ix, ra2);
+			if (ne > 3) e3 = ld_direct_first(ix, ra3);
+			uint32_t longest = e0.y & 255u;
+			ra0 = e0.x; me0 = (e0.y & 0xffffu) | (me0 & 0xffff0000u);
+			prefetch_l2(ix.vals + ra0); prefetch_l2(ix.vals + ra0 + (e0.y & 255u) - 1u);
+			if (ne > 1) { ra1 = e1.x; me1 = (e1.y & 0xffffu) | (me1 & 0xffff0000u); longest = max(longest, e1.y & 255u); prefetch_l2(ix.vals + ra1); prefetch_l2(ix.vals + ra1 + (e1.y & 255u) - 1u); }
+			if (ne > 2) { ra2 = e2.x; me2 = (e2.y & 0xffffu) | (me2 & 0xffff0000u); longest = max(longest, e2.y & 255u); prefetch_l2(ix.vals + ra2); prefetch_l2(ix.vals + ra2 + (e2.y & 255u) - 1u); }
+			if (ne > 3) { ra3 = e3.x; me3 = (e3.y & 0xffffu) | (me3 & 0xffff0000u); longest = max(longest, e3.y & 255u); prefetch_l2(ix.vals + ra3); prefetch_l2(ix.vals + ra3 + (e3.y & 255u) - 1u); }
+			if (longest > (uint32_t)C.cap) ok = false;                // cannot stay separable
+		}
+#endif
 		if (!ok) return false;
 		// the keys with several positions: one flat loop over all their positions in the reference's visit order; then, one by
 		// one, what the units left open (through the direct filter, as MODE 2 would)
@@ -849,6 +1029,40 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 				if (ne == 0) { ra0 = entry.x; me0 = me; } else if (ne == 1) { ra1 = entry.x; me1 = me; } else if (ne == 2) { ra2 = entry.x; me2 = me; } else { ra3 = entry.x; me3 = me; }
 				ne++;
 			}
+#if SR_DENSE_FLAT_PIPE
+			{
+				// positions t = 0 .. total-1 of all runs in a row; the load of position t + 1 under way while t is applied
+				const int h0 = ne > 0 ? (int)(me0 & 255u) : 0, h1 = ne > 1 ? (int)(me1 & 255u) : 0, h2 = ne > 2 ? (int)(me2 & 255u) : 0, h3 = ne > 3 ? (int)(me3 & 255u) : 0;
+				const int total = h0 + h1 + h2 + h3;
+				uint32_t me_t = 0;
+				int u_t = 0;
+				auto fetch = [&](int t) -> uint32_t {
+					uint32_t ra;
+					if (t < h0) { ra = ra0; me_t = me0; u_t = t; }
+					else if (t < h0 + h1) { ra = ra1; me_t = me1; u_t = t - h0; }
+					else if (t < h0 + h1 + h2) { ra = ra2; me_t = me2; u_t = t - h0 - h1; }
+					else { ra = ra3; me_t = me3; u_t = t - h0 - h1 - h2; }
+					const int h = (int)(me_t & 255u), land = (int)((me_t >> 8) & 255u);
+					const int nfwd = h - land;                           // landing .. end of run, then landing-1 .. start (:1109-1119)
+					const int idx = u_t < nfwd ? land + u_t : land - 1 - (u_t - nfwd);
+					return ld_gather(ix.vals + ra + idx);
+				};
+				uint32_t v_next = total > 0 ? fetch(0) : 0u;
+				n_gather += (uint32_t)total;
+#pragma unroll 1
+				for (int t = 0; t < total; t++) {
+					const uint32_t v = v_next, me = me_t;
+					const int u = u_t;
+					if (t + 1 < total) v_next = fetch(t + 1);
+					const int l = (int)(me >> 16);
+					int sub;
+					const int o = simple_offset<GAP>(l, step, &sub);
+					if (!hit(v - (uint32_t)o, l, u, sub)) { ok = false; break; }
+				}
+			}
+			ne = 0;
+		}
+#else
 			int e = 0, u = 0;
 #pragma unroll 1
 			while (e < ne && ok) {
@@ -866,6 +1080,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 			}
 			ne = 0;
 		}
+#endif
 	}
 	if (!ok) return false;
 #pragma unroll 1
@@ -874,6 +1089,17 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		C.w(c, 3) = 0u;
 	}
 	return true;
+}
+
+// Asks for the dense units of subreads [s0, s0 + count) of a pass ahead of time (whole lines into L2): a caller that knows its next
+// pass hides that pass's first fetches behind the work of this one.
+template <bool RCKEYS>
+__device__ __forceinline__ void simple_dense_ask(const DevIndex &ix, const uint32_t *pk, int applied, int step, int rc_len, int s0, int count)
+{
+	const uint4 *units4 = reinterpret_cast<const uint4 *>(ix.phase_dense);
+#pragma unroll
+	for (int i = 0; i < count; i++)
+		if (s0 + i < applied) prefetch_l2(units4 + 8u * (size_t)(simple_key_at<RCKEYS>(pk, simple_sub_offset<3>(s0 + i, step), rc_len) & kPhaseMask));
 }
 
 template <int GAP, int MODE, bool RCKEYS = false>

@@ -21,6 +21,10 @@
 #include "sr_simple.cuh"
 #include "sr_simple_junc.cuh"
 
+#ifndef SR_PE_PACK_ALL
+#define SR_PE_PACK_ALL 1       // the 32 lanes of a warp pack the 32 staged reads at once (instead of 16 lanes packing two each).  A/B switch
+#endif
+
 namespace sr {
 
 constexpr int kPeCand = 8;        // candidates per mate
@@ -313,7 +317,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 // k_map_simple_pe: thread t of block b maps paired-end fragment 128 b + t (reads 2f and 2f + 1 of the chunk) of a chunk
 // whose bigtable slice is all zero.  Dynamic shared memory: simple_pe_smem_bytes(max_len, clusters).
 template <int GAP, int MODE, bool JUNC = false, bool RMW = false>
-__global__ void __launch_bounds__(kSimpleThreads, JUNC ? 3 : 4)
+__global__ void __launch_bounds__(kSimpleThreads, (JUNC || MODE == 4) ? 3 : 4)   // (dense tables: the cluster pool in shared memory allows three blocks anyway)
 k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
                 const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int pool, ResultWords *out, uint32_t *queue,
                 uint32_t *queue_count, uint32_t *bad_reads, uint32_t *gather_count, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
@@ -381,6 +385,21 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 			}
 		}
 		__syncwarp();
+#if SR_PE_PACK_ALL
+		// every lane packs the read it staged -- all 32 at once -- into the column of the fragment's owner (thread 16 h + lane / 2 of
+		// the warp, mate lane & 1), who then only picks up lengths and flags
+		bool unpacked = false;
+		if (staged) unpacked = !simple_pack<false>(stage, so, L, reinterpret_cast<uint32_t *>(smem4) + 32 * wid + 16 * h + (lane >> 1) + (lane & 1) * n_words * kSimpleThreads, n_words);
+		const int src0 = 2 * (lane & 15);
+		const int l0 = __shfl_sync(kFullMask, L, src0), l1 = __shfl_sync(kFullMask, L, src0 + 1);
+		const int ok0 = __shfl_sync(kFullMask, (int)(staged && !unpacked), src0), ok1 = __shfl_sync(kFullMask, (int)(staged && !unpacked), src0 + 1);
+		const int bad0 = __shfl_sync(kFullMask, (int)bad, src0), bad1 = __shfl_sync(kFullMask, (int)bad, src0 + 1);
+		if ((lane >> 4) == h && active) {
+			L0 = l0; L1 = l1;
+			if (bad0 || bad1) active = false;
+			else if (!ok0 || !ok1) punt = true;                       // a mate shorter than 16 bases, longer than the tier takes, odd characters, ...
+		}
+#else
 		// the owner of fragment fw0 + lane (lanes 16 h .. 16 h + 15) picks up its two reads from lanes 2 (lane & 15), + 1
 		const int src0 = 2 * (lane & 15);
 		const unsigned so0 = __shfl_sync(kFullMask, so, src0), so1 = __shfl_sync(kFullMask, so, src0 + 1);
@@ -396,6 +415,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 				if (!simple_pack<false>(stage, so1, l1, pk + n_words * kSimpleThreads, n_words)) punt = true;
 			}
 		}
+#endif
 		__syncwarp();
 	}
 
@@ -458,6 +478,12 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 				C1.base = C0.base + C0.n * kSimpleClusterWords * 32;
 				C1.cap = pool - C0.n;
 			}
+#if SR_DENSE_PF_NEXT > 0
+			if (MODE == 4 && it < 3) {                                // the first units of the next pass: under way while this one runs
+				const int m2 = (it + 1) & 1, rc2 = (((it + 1) >> 1) ^ (m2 ? rev1 : rev0)) != 0;
+				simple_dense_ask<true>(ix, pk + m2 * n_words * kSimpleThreads, m2 ? applied1 : applied0, m2 ? step1 : step0, rc2 ? (m2 ? L1 : L0) : 0, 0, SR_DENSE_PF_NEXT);
+			}
+#endif
 			if (!simple_pass<GAP, MODE, true>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0,
 			                                  rc ? (m ? L1 : L0) : 0, n_gather)) punt = true;
 			else if (m == 1) {

@@ -10,7 +10,7 @@ fname, hdr, agg, total = None, None, {}, 0
 for r in rows:
     if not r:
         continue
-    if r[0] == "File Name":
+    if r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
         continue
     if r[0] == "Line No":
