@@ -141,7 +141,7 @@ struct SimpleCluster {
 	__device__ __forceinline__ int votes() const { return (w1 >> 31) ? __popcll(subs) : 0; }
 	__device__ __forceinline__ int first_l() const { return (int)(w1 & 255u); }
 	__device__ __forceinline__ int last_l() const { return (int)((w1 >> 8) & 255u); }
-	__device__ __forceinline__ int order() const { return (int)(vote_row(kv) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u)); }
+	__device__ __forceinline__ int order() const { return (int)(((w1 >> 24) & 31u) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u)); }
 };
 
 // The clusters of the running pass in shared memory, four words each, interleaved over the warp's lanes.
@@ -153,7 +153,7 @@ struct SimpleClusters {
 	__device__ __forceinline__ int order(int c) const
 	{
 		const uint32_t w1 = w(c, 1);
-		return (int)(vote_row(w(c, 0)) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u));   // (the row from kv itself: w1's row field is not always filled)
+		return (int)(((w1 >> 24) & 31u) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u));
 	}
 	__device__ __forceinline__ SimpleCluster get(int c) const
 	{
@@ -1115,6 +1115,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 	for (int c = 0; c < C.n; c++) {
 		C.w(c, 2) = (uint32_t)C.votes(c);
 		C.w(c, 3) = 0u;
+		C.w(c, 1) |= vote_row(C.w(c, 0)) << 24;                    // (hit() leaves the row field to this loop: once per cluster, all lanes together)
 	}
 	C_out.n = C.n;
 	return true;
