@@ -56,29 +56,11 @@
 #define SR_SIMPLE_DEFER_LIMIT 3    // lookups of one batch a lane may take through the general path before the fragment is queued for the warp kernel
                                    // (A/B on B200: mixed workload 419 -> 446 M reads/s, clean 1 502 -> 1 533 M)
 #endif
-#ifndef SR_DENSE_PF_DIST
-#define SR_DENSE_PF_DIST 0     // (measured: 3 and 6 cost 7 % -- the extra key extraction and the doubled DRAM bytes outweigh what they hide) dense phase units (MODE 4): how many subreads beyond the register fetch their units are asked for (prefetch.global.L2); 0 = off
-#endif
-#ifndef SR_DENSE_PF_NEXT
-#define SR_DENSE_PF_NEXT 0     // ... and how many units of the NEXT pass the paired-end tier asks for before it starts a pass; 0 = off
-#endif
-#ifndef SR_DENSE_HIT_V2
-#define SR_DENSE_HIT_V2 1      // ... two sieves in front of the cluster list and one body for "last cluster" / "new cluster".  A/B switch
-#endif
-#ifndef SR_DENSE_R64
-#define SR_DENSE_R64 0         // ... 64 bytes of a unit in registers (values 0 .. 11 picked by selects) instead of 32 + a second load.  A/B switch
-#endif
-#ifndef SR_DENSE_FLAT_PIPE
-#define SR_DENSE_FLAT_PIPE 1   // ... positions of keys with several: the next one's load under way while this one is applied.  A/B switch
+#ifndef SR_DENSE_PIPE
+#define SR_DENSE_PIPE 1        // dense phase units (MODE 4): a unit is applied one iteration after it was read (its value loads overlap the unit before).  A/B switch
 #endif
 #ifndef SR_DENSE_PROBE3
 #define SR_DENSE_PROBE3 1      // ... the first three clusters tried before the walk over the list.  A/B switch
-#endif
-#ifndef SR_DENSE_COMPACT_HITS
-#define SR_DENSE_COMPACT_HITS 1   // ... one copy of hit() per unit, looped over the unit's single positions.  A/B switch
-#endif
-#ifndef SR_DENSE_TWO_PHASE
-#define SR_DENSE_TWO_PHASE 1   // ... the three roles of a unit in two steps (loads first), direct_first entries read behind the subread loop.  A/B switch
 #endif
 #ifndef SR_SIMPLE_SMEM_OUT
 #define SR_SIMPLE_SMEM_OUT 0   // compose the warp's bigtable slice in shared memory and store whole sectors (A/B switch)
@@ -743,10 +725,15 @@ __device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const Vote
 }
 
 // The same over the 128-byte units of a dense table (MODE 4; sr_common.cuh).  No unit is empty, so every subread's unit is
-// fetched: one uniform loop over the subreads of a batch, the next unit's first 32 bytes (the 2-bit codes and four values) in
-// flight while this one is applied; the other values of the unit come from the same 64-byte fetch.  As in MODE 2, every single
-// position goes through the cluster list at once and the keys with several positions (their value is the rank of their
-// direct_first entry) wait in registers for the flat loop over their runs.
+// fetched: one uniform loop over the subreads of a batch, software-pipelined in three stages -- the next unit's first 32 bytes
+// (the 2-bit codes and four values) in flight; this unit read (which keys it holds, the loads of the values beyond its first
+// four under way); the unit before applied to the vote clusters.  Single positions go through the cluster list at once, the
+// keys with several positions (their value is the rank of their direct_first entry) wait in registers: their entries are asked
+// for as they turn up, read behind the loop, and their runs are walked in one flat loop, the next position's load under way.
+// What round 2 measured on the human-sized paired-end workload (profiles/r02_human_pe_tier.md): 306 -> 481 M reads/s from the
+// sieves and the convergent hit(), the two-step unit, the entries behind the loop, the pipelined runs and the compacted hits;
+// prefetch.global.L2 of the units further down (3 or 6 ahead, or the next pass's first two) cost 7 %; 64 bytes of a unit in
+// registers changed nothing.
 template <bool RCKEYS>
 __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
                                                         SimpleClusters &C_out, int rc_len, uint32_t &n_gather)
@@ -760,18 +747,13 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 	if (C.cap < 1) return false;
 	bool ok = true;
 	// A pass over a dense table meets a handful of one-vote chance hits besides the true cluster, and looking every hit up in the
-	// cluster list was a quarter of the kernel's instructions.  Two shortcuts, both exact: `occ` has one bit per 8 consecutive kv
-	// (mod 512) that some cluster of the list falls into -- a hit whose own bit and both neighbours are clear is neither equal to
-	// nor within the tolerance (<= 8) of any cluster and opens a new one unseen; and the cluster the last hit was found equal to
-	// (the true cluster, as a rule) is tried first -- two clusters of the list are never within tolerance of each other, so a hit
-	// that equals one needs no look at the others.
-#if SR_DENSE_HIT_V2
-	// (round 2, second version) Three 32-bit sieves in front of the cluster list.  occ_a / occ_b: one bit per 16 consecutive kv, at
-	// two alignments 8 apart -- two kv within the tolerance (<= 8) of each other share a bin in one of them; occ_f: one bit per 512.
-	// A cluster near the hit shows in (a or b) AND in f; a chance cluster of a 3 Gbp table does so one time in 500, so the walk over
-	// the list (a quarter of the kernel's instructions, two lanes of 32 at a time) is left to the hits that do have a neighbour.
-	// The two common cases, "the cluster of the last hit" and "a new cluster", share one body that touches only the words it
-	// changes, so the lanes of a warp that hold either run it together (155 -> ~40 instructions per hit).
+	// cluster list was half of the kernel's instructions.  Three 32-bit sieves stand in front of the list.  occ_a / occ_b: one bit
+	// per 16 consecutive kv, at two alignments 8 apart -- two kv within the tolerance (<= 8) of each other share a bin in one of
+	// them; occ_f: one bit per 512.  A cluster near the hit shows in (a or b) AND in f; a hit that does not is neither equal to nor
+	// within the tolerance of any cluster and opens a new one unseen.  The cluster the last hit was found equal to (the true
+	// cluster, as a rule) is tried first -- two clusters of the list are never within tolerance of each other, so a hit that
+	// equals one needs no look at the others.  These two common cases share ONE body that touches only the words it changes, so
+	// the lanes of a warp that hold either run it together; the walk over the list is left to the hits that do have a neighbour.
 	uint32_t occ_a = 0, occ_b = 0, occ_f = 0;
 	uint32_t last_kv = 0;
 	int last_c = -1;
@@ -782,8 +764,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		const bool clear = (tol <= 8) & ((((occ_a & ba) | (occ_b & bb)) == 0u) | ((occ_f & bf) == 0u));
 #if SR_DENSE_PROBE3
 		// The second hit of the true cluster finds no `last` yet and the sieves set: as a rule that cluster was opened by the read's
-		// first subread, so the first three of the list are tried before the walk (an equal one settles it: no two clusters of the
-		// list are within tolerance of each other).
+		// first subread, so the first three of the list are tried before the walk.
 		if (!same && !clear && last_c < 0) {
 			const int np = min(C.n, 3);
 			int j = -1;
@@ -796,7 +777,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		// (bitwise on purpose: with && / || the compiler sends the `same` lanes into the body ahead of the others and the body runs twice)
 		const bool fresh = (!same) & clear;
 		if (same | fresh) {
-			if (fresh && (!(kv >= 32u && kv <= 0xffffffdfu) || C.n >= C.cap)) return false;
+			if (fresh && (!(kv >= 32u && kv <= 0xffffffdfu) || C.n >= C.cap)) return false;   // u32 wrap-around of the probe rows; list full
 			const int idx = same ? last_c : C.n;
 			uint32_t *cw = C.base + idx * (kSimpleClusterWords * 32), *cs = cw + (2 + (sub >> 5)) * 32;   // the cluster's words; the one with the subread's bit
 			const uint32_t bit = 1u << (sub & 31);
@@ -828,193 +809,106 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		if (found >= 0) { last_kv = kv; last_c = found; }
 		return true;
 	};
-#else
-	unsigned long long occ = 0;
-	uint32_t last_kv = 0;
-	int last_c = -1;
-	auto hit = [&](uint32_t kv, int l, int u, int sub) -> bool {
-		if (last_c >= 0 && kv == last_kv) {
-			SimpleCluster c = C.get(last_c);
-			if (!(c.w1 >> 31)) return true;
-			const unsigned long long bit = 1ull << sub;
-			if (c.subs & bit) return false;
-			c.subs |= bit;
-			if (l < c.first_l()) c.w1 = (c.w1 & ~0x007f00ffu) | (uint32_t)l | ((uint32_t)u << 16);
-			if (l > c.last_l()) c.w1 = (c.w1 & ~0x0000ff00u) | ((uint32_t)l << 8);
-			C.put(last_c, c);
-			return true;
-		}
-		const unsigned b = (kv >> 3) & 63u;
-		const unsigned long long nbr = (1ull << b) | (1ull << ((b + 1u) & 63u)) | (1ull << ((b + 63u) & 63u));
-		if (tol <= 8 && !(occ & nbr)) {
-			if (!(kv >= 32u && kv <= 0xffffffdfu) || C.n >= C.cap) return false;
-			C.put(C.n++, simple_new_cluster(kv, l, u, sub, low, high));
-			occ |= 1ull << b;
-			return true;
-		}
-		int found = -1;
-		const int n0 = C.n;
-		if (!simple_hit(C, kv, l, u, sub, tol, low, high, &found)) return false;
-		if (C.n > n0) occ |= 1ull << b;
-		if (found >= 0) { last_kv = kv; last_c = found; }
-		return true;
-	};
-#endif
 	for (int s_base = 0; s_base < applied && ok; s_base += kSubs) {
 		const int n_sub = min(kSubs, applied - s_base), base = s_base * GAP;
 		uint32_t ra0 = 0, ra1 = 0, ra2 = 0, ra3 = 0;     // runs of keys with several positions waiting to be applied:
-		uint32_t me0 = 0, me1 = 0, me2 = 0, me3 = 0;     // first item in vals[];  h | landing << 8 | lookup << 16
+		uint32_t me0 = 0, me1 = 0, me2 = 0, me3 = 0;     // first item in vals[] (until read: the rank of the entry);  h | landing << 8 | lookup << 16
 		int ne = 0;
 		unsigned slow = 0;                               // lookups the unit could not answer (value beyond its 28, a fifth run): the direct filter does
 		Record8 rn;
-#if SR_DENSE_R64
-		Record8 rn2;                                     // the second 32 bytes of the same 64-byte fetch: values 4 .. 11
-#endif
 		uint32_t k0_next = 0;
 		auto issue = [&](int si) {
 			k0_next = simple_key_at<RCKEYS>(pk, simple_sub_offset<GAP>(s_base + min(si, n_sub - 1), step), rc_len);
 			rn = ld_record(units4, 4u * (k0_next & kPhaseMask));         // (ld_record counts in 32-byte records: a unit is four)
-#if SR_DENSE_R64
-			rn2 = ld_record(units4, 4u * (k0_next & kPhaseMask) + 1u);
-#endif
 			n_gather++;
 		};
-#if SR_DENSE_PF_DIST > 0
-		// Every address of the pass follows from the read alone, so the units further down are asked for now (whole 128-byte lines
-		// into L2, no register held): the register fetch one iteration ahead then meets L2, and so do the values past the unit's
-		// first 32 bytes.  Without it a warp met DRAM latency three times per subread (profiles/r02_human_pe_tier.md).
-		auto ask = [&](int si) {
-			if (si < n_sub) prefetch_l2(units4 + 8u * (size_t)(simple_key_at<RCKEYS>(pk, simple_sub_offset<GAP>(s_base + si, step), rc_len) & kPhaseMask));
-		};
-#pragma unroll
-		for (int i = 2; i <= SR_DENSE_PF_DIST; i++) ask(i);
-#endif
-		issue(0);
-#pragma unroll 1
-		for (int si = 0; si < n_sub; si++) {
+		// stage 2: what the unit says about its three keys.  st: two bits per role (0 nothing, 1 one position, 2 several); the
+		// values the unit holds past its first four are loaded here and used a stage later
+		auto look = [&](int si, uint32_t (&val)[3], int &st) {
 			const Record8 r = rn;
-#if SR_DENSE_R64
-			const Record8 r2 = rn2;
-#endif
-			const int sub = s_base + si;
 			const uint32_t k0 = k0_next;
 			if (si + 1 < n_sub) issue(si + 1);
-#if SR_DENSE_PF_DIST > 0
-			ask(si + 1 + SR_DENSE_PF_DIST);
-#endif
-			const int ob = simple_sub_offset<GAP>(sub, step);            // (the other two keys only now: fewer registers across the fetch)
+			const int ob = simple_sub_offset<GAP>(s_base + si, step);    // (the other two keys only now: fewer registers across the fetch)
 			const uint32_t k1 = simple_key_at<RCKEYS>(pk, ob + 1, rc_len), k2 = simple_key_at<RCKEYS>(pk, ob + 2, rc_len);
 			const uint32_t c = k0 & kPhaseMask;
-			if (((k1 >> 2) & kPhaseMask) != c || (k2 >> 4) != c) { slow |= 7u << (3 * si); continue; }
+			st = 0;
+			val[0] = val[1] = val[2] = 0u;
+			if (((k1 >> 2) & kPhaseMask) != c || (k2 >> 4) != c) { slow |= 7u << (3 * si); return; }
 			const uint32_t p0 = r.w[0] & 0x55555555u, p1 = r.w[1] & 0x55555555u;
-#if SR_DENSE_TWO_PHASE
-			// (a) what the unit says about the three keys, the loads of the values it does not hold in its first 32 bytes all under
-			// way before any is used; (b) the entries of keys with several positions asked for (they are read after the loop);
-			// (c) the single positions applied
-			uint32_t val[3];
-			int st[3];                                                   // 0 nothing, 1 one position, 2 several
 #pragma unroll
 			for (int x = 0; x < 3; x++) {
 				const uint32_t key = x == 0 ? k0 : (x == 1 ? k1 : k2), v = phase_variant(key, x);
 				const uint32_t wx = x == 0 ? r.w[0] : (x == 1 ? r.w[1] : r.w[2]);
 				const uint32_t two = (wx >> (2 * v)) & 3u;
-				st[x] = 0;
-				val[x] = 0;
 				if (!(two & 1u)) continue;
 				const int rank = __popc(wx & 0x55555555u & ((1u << (2 * v)) - 1u)) + (x > 0 ? __popc(p0) : 0) + (x > 1 ? __popc(p1) : 0);
 				if (rank >= kPhaseDenseValues) { slow |= 1u << (3 * si + x); continue; }
-				st[x] = 1 + (int)((two >> 1) & 1u);
-#if SR_DENSE_R64
-				if (rank < 12) {                                         // out of the 64 bytes in registers: no second trip
-					const int j = rank & 3;
-					const uint32_t v0 = j == 0 ? r.w[4] : (j == 1 ? r.w[5] : (j == 2 ? r.w[6] : r.w[7]));
-					const uint32_t v1 = j == 0 ? r2.w[0] : (j == 1 ? r2.w[1] : (j == 2 ? r2.w[2] : r2.w[3]));
-					const uint32_t v2 = j == 0 ? r2.w[4] : (j == 1 ? r2.w[5] : (j == 2 ? r2.w[6] : r2.w[7]));
-					val[x] = rank < 4 ? v0 : (rank < 8 ? v1 : v2);
-				} else {
-					val[x] = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);
-					n_gather++;                                                                    // (the unit's second half: another fetch)
-				}
-#else
+				st |= (1 + (int)((two >> 1) & 1u)) << (2 * x);
 				if (rank < 4) val[x] = rank == 0 ? r.w[4] : (rank == 1 ? r.w[5] : (rank == 2 ? r.w[6] : r.w[7]));
 				else {
-					val[x] = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);
+					val[x] = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);       // same unit: as a rule the 64 bytes already fetched
 					if (rank >= 12) n_gather++;                                                    // (the unit's second half: another fetch)
 				}
-#endif
+			}
+		};
+		// stage 3: the entries of keys with several positions asked for (read behind the loop); the unit's single positions side
+		// by side (role order) in front of ONE copy of hit(), run as often as the fullest lane needs -- 2.4 times per unit on
+		// average instead of once per role
+		auto apply = [&](int si, const uint32_t (&val)[3], int st) {
+			const int sub = s_base + si, ob = simple_sub_offset<GAP>(sub, step);
+#pragma unroll
+			for (int x = 0; x < 3; x++)
+				if (((st >> (2 * x)) & 3) == 2) { prefetch_l2(ix.direct_first + val[x]); n_gather++; }
+			uint32_t h0 = 0, h1 = 0, h2 = 0;
+			int hx = 0, nh = 0;                                          // roles, two bits each
+#pragma unroll
+			for (int x = 0; x < 3; x++)
+				if (((st >> (2 * x)) & 3) == 1) {
+					const uint32_t kvx = val[x] - (uint32_t)(ob + x);
+					if (nh == 0) h0 = kvx; else if (nh == 1) h1 = kvx; else h2 = kvx;
+					hx |= x << (2 * nh);
+					nh++;
+				}
+#pragma unroll 1
+			for (int j = 0; j < nh; j++) {
+				const uint32_t kvj = j == 0 ? h0 : (j == 1 ? h1 : h2);
+				if (!hit(kvj, base + 3 * si + ((hx >> (2 * j)) & 3), 0, sub)) { ok = false; break; }
 			}
 #pragma unroll
 			for (int x = 0; x < 3; x++)
-				if (st[x] == 2) { prefetch_l2(ix.direct_first + val[x]); n_gather++; }
-#if SR_DENSE_COMPACT_HITS
-			// the unit's single positions side by side (role order), then ONE copy of hit() run as often as the fullest lane needs:
-			// 2.4 times per unit on average instead of once per role
-			{
-				uint32_t h0 = 0, h1 = 0, h2 = 0;                          // kv | role in a side word
-				int hx = 0, nh = 0;                                       // roles, two bits each
-#pragma unroll
-				for (int x = 0; x < 3; x++)
-					if (st[x] == 1) {
-						const uint32_t kvx = val[x] - (uint32_t)(ob + x);
-						if (nh == 0) h0 = kvx; else if (nh == 1) h1 = kvx; else h2 = kvx;
-						hx |= x << (2 * nh);
-						nh++;
-					}
-#pragma unroll 1
-				for (int j = 0; j < nh; j++) {
-					const uint32_t kvj = j == 0 ? h0 : (j == 1 ? h1 : h2);
-					if (!hit(kvj, base + 3 * si + ((hx >> (2 * j)) & 3), 0, sub)) { ok = false; break; }
-				}
-			}
-#endif
-#pragma unroll
-			for (int x = 0; x < 3; x++) {
-				const int li = 3 * si + x, l = base + li;
-#if !SR_DENSE_COMPACT_HITS
-				if (st[x] == 1) { if (!hit(val[x] - (uint32_t)(ob + x), l, 0, sub)) ok = false; }
-				else
-#endif
-				if (st[x] == 2) {                                            // rank of its direct_first entry; read behind the loop
-					const uint32_t me = (uint32_t)l << 16;
+				if (((st >> (2 * x)) & 3) == 2) {                            // rank of its direct_first entry; read behind the loop
+					const int li = 3 * si + x;
+					const uint32_t me = (uint32_t)(base + li) << 16;
 					if (ne == 0) { ra0 = val[x]; me0 = me; ne = 1; }
 					else if (ne == 1) { ra1 = val[x]; me1 = me; ne = 2; }
 					else if (ne == 2) { ra2 = val[x]; me2 = me; ne = 3; }
 					else if (ne == 3) { ra3 = val[x]; me3 = me; ne = 4; }
 					else slow |= 1u << li;
 				}
-			}
-#else
-#pragma unroll
-			for (int x = 0; x < 3; x++) {
-				const uint32_t key = x == 0 ? k0 : (x == 1 ? k1 : k2), v = phase_variant(key, x);
-				const uint32_t wx = x == 0 ? r.w[0] : (x == 1 ? r.w[1] : r.w[2]);
-				const uint32_t two = (wx >> (2 * v)) & 3u;
-				if (!(two & 1u)) continue;
-				const int rank = __popc(wx & 0x55555555u & ((1u << (2 * v)) - 1u)) + (x > 0 ? __popc(p0) : 0) + (x > 1 ? __popc(p1) : 0);
-				const int li = 3 * si + x, l = base + li;
-				if (rank >= kPhaseDenseValues) { slow |= 1u << li; continue; }
-				uint32_t value;
-				if (rank < 4) value = rank == 0 ? r.w[4] : (rank == 1 ? r.w[5] : (rank == 2 ? r.w[6] : r.w[7]));
-				else {
-					value = ld_gather(ix.phase_dense + (size_t)kPhaseDenseWords * c + 4 + rank);       // same unit: as a rule the 64 bytes already fetched
-					if (rank >= 12) n_gather++;                                                    // (the unit's second half: another fetch)
-				}
-				if (!(two & 2u)) { if (!hit(value - (uint32_t)(ob + x), l, 0, sub)) ok = false; }
-				else {
-					const uint2 entry = ld_direct_first(ix, value);
-					n_gather++;
-					const uint32_t me = (entry.y & 0xffffu) | ((uint32_t)l << 16);
-					if ((entry.y & 255u) > (uint32_t)C.cap) ok = false;       // cannot stay separable
-					else if (ne == 0) { ra0 = entry.x; me0 = me; ne = 1; }
-					else if (ne == 1) { ra1 = entry.x; me1 = me; ne = 2; }
-					else if (ne == 2) { ra2 = entry.x; me2 = me; ne = 3; }
-					else if (ne == 3) { ra3 = entry.x; me3 = me; ne = 4; }
-					else slow |= 1u << li;
-				}
-			}
-#endif
+		};
+		issue(0);
+#if SR_DENSE_PIPE
+		uint32_t pv[3] = {0u, 0u, 0u};
+		int pst = 0;
+#pragma unroll 1
+		for (int si = 0; si < n_sub; si++) {
+			uint32_t cv[3];
+			int cst;
+			look(si, cv, cst);
+			if (pst) apply(si - 1, pv, pst);
+			pv[0] = cv[0]; pv[1] = cv[1]; pv[2] = cv[2];
+			pst = cst;
 		}
-#if SR_DENSE_TWO_PHASE
+		if (pst) apply(n_sub - 1, pv, pst);
+#else
+#pragma unroll 1
+		for (int si = 0; si < n_sub; si++) {
+			uint32_t cv[3];
+			int cst;
+			look(si, cv, cst);
+			if (cst) apply(si, cv, cst);
+		}
+#endif
 		// the entries asked for in the loop (ra = their rank so far): all four loads under way, then run start, length and landing
 		// index in place of the rank, and the runs' positions asked for in turn
 		if (ok && ne) {
@@ -1031,7 +925,6 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 			if (ne > 3) { ra3 = e3.x; me3 = (e3.y & 0xffffu) | (me3 & 0xffff0000u); longest = max(longest, e3.y & 255u); prefetch_l2(ix.vals + ra3); prefetch_l2(ix.vals + ra3 + (e3.y & 255u) - 1u); }
 			if (longest > (uint32_t)C.cap) ok = false;                // cannot stay separable
 		}
-#endif
 		if (!ok) return false;
 		// the keys with several positions: one flat loop over all their positions in the reference's visit order; then, one by
 		// one, what the units left open (through the direct filter, as MODE 2 would)
@@ -1057,58 +950,37 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 				if (ne == 0) { ra0 = entry.x; me0 = me; } else if (ne == 1) { ra1 = entry.x; me1 = me; } else if (ne == 2) { ra2 = entry.x; me2 = me; } else { ra3 = entry.x; me3 = me; }
 				ne++;
 			}
-#if SR_DENSE_FLAT_PIPE
-			{
-				// positions t = 0 .. total-1 of all runs in a row; the load of position t + 1 under way while t is applied
-				const int h0 = ne > 0 ? (int)(me0 & 255u) : 0, h1 = ne > 1 ? (int)(me1 & 255u) : 0, h2 = ne > 2 ? (int)(me2 & 255u) : 0, h3 = ne > 3 ? (int)(me3 & 255u) : 0;
-				const int total = h0 + h1 + h2 + h3;
-				uint32_t me_t = 0;
-				int u_t = 0;
-				auto fetch = [&](int t) -> uint32_t {
-					uint32_t ra;
-					if (t < h0) { ra = ra0; me_t = me0; u_t = t; }
-					else if (t < h0 + h1) { ra = ra1; me_t = me1; u_t = t - h0; }
-					else if (t < h0 + h1 + h2) { ra = ra2; me_t = me2; u_t = t - h0 - h1; }
-					else { ra = ra3; me_t = me3; u_t = t - h0 - h1 - h2; }
-					const int h = (int)(me_t & 255u), land = (int)((me_t >> 8) & 255u);
-					const int nfwd = h - land;                           // landing .. end of run, then landing-1 .. start (:1109-1119)
-					const int idx = u_t < nfwd ? land + u_t : land - 1 - (u_t - nfwd);
-					return ld_gather(ix.vals + ra + idx);
-				};
-				uint32_t v_next = total > 0 ? fetch(0) : 0u;
-				n_gather += (uint32_t)total;
-#pragma unroll 1
-				for (int t = 0; t < total; t++) {
-					const uint32_t v = v_next, me = me_t;
-					const int u = u_t;
-					if (t + 1 < total) v_next = fetch(t + 1);
-					const int l = (int)(me >> 16);
-					int sub;
-					const int o = simple_offset<GAP>(l, step, &sub);
-					if (!hit(v - (uint32_t)o, l, u, sub)) { ok = false; break; }
-				}
-			}
-			ne = 0;
-		}
-#else
-			int e = 0, u = 0;
-#pragma unroll 1
-			while (e < ne && ok) {
-				const uint32_t ra = e == 0 ? ra0 : (e == 1 ? ra1 : (e == 2 ? ra2 : ra3)), me = e == 0 ? me0 : (e == 1 ? me1 : (e == 2 ? me2 : me3));
-				const int h = (int)(me & 255u), land = (int)((me >> 8) & 255u), l = (int)(me >> 16);
-				if (u >= h) { e++; u = 0; continue; }
+			if (!ok) break;
+			// positions t = 0 .. total-1 of all runs in a row; the load of position t + 1 under way while t is applied
+			const int h0 = ne > 0 ? (int)(me0 & 255u) : 0, h1 = ne > 1 ? (int)(me1 & 255u) : 0, h2 = ne > 2 ? (int)(me2 & 255u) : 0, h3 = ne > 3 ? (int)(me3 & 255u) : 0;
+			const int total = h0 + h1 + h2 + h3;
+			uint32_t me_t = 0;
+			int u_t = 0;
+			auto fetch = [&](int t) -> uint32_t {
+				uint32_t ra;
+				if (t < h0) { ra = ra0; me_t = me0; u_t = t; }
+				else if (t < h0 + h1) { ra = ra1; me_t = me1; u_t = t - h0; }
+				else if (t < h0 + h1 + h2) { ra = ra2; me_t = me2; u_t = t - h0 - h1; }
+				else { ra = ra3; me_t = me3; u_t = t - h0 - h1 - h2; }
+				const int h = (int)(me_t & 255u), land = (int)((me_t >> 8) & 255u);
 				const int nfwd = h - land;                               // landing .. end of run, then landing-1 .. start (:1109-1119)
-				const int idx = u < nfwd ? land + u : land - 1 - (u - nfwd);
-				const uint32_t v = ld_gather(ix.vals + ra + idx);
-				n_gather++;
+				const int idx = u_t < nfwd ? land + u_t : land - 1 - (u_t - nfwd);
+				return ld_gather(ix.vals + ra + idx);
+			};
+			uint32_t v_next = total > 0 ? fetch(0) : 0u;
+			n_gather += (uint32_t)total;
+#pragma unroll 1
+			for (int t = 0; t < total; t++) {
+				const uint32_t v = v_next, me = me_t;
+				const int u = u_t;
+				if (t + 1 < total) v_next = fetch(t + 1);
+				const int l = (int)(me >> 16);
 				int sub;
 				const int o = simple_offset<GAP>(l, step, &sub);
 				if (!hit(v - (uint32_t)o, l, u, sub)) { ok = false; break; }
-				u++;
 			}
 			ne = 0;
 		}
-#endif
 	}
 	if (!ok) return false;
 #pragma unroll 1
@@ -1119,17 +991,6 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 	}
 	C_out.n = C.n;
 	return true;
-}
-
-// Asks for the dense units of subreads [s0, s0 + count) of a pass ahead of time (whole lines into L2): a caller that knows its next
-// pass hides that pass's first fetches behind the work of this one.
-template <bool RCKEYS>
-__device__ __forceinline__ void simple_dense_ask(const DevIndex &ix, const uint32_t *pk, int applied, int step, int rc_len, int s0, int count)
-{
-	const uint4 *units4 = reinterpret_cast<const uint4 *>(ix.phase_dense);
-#pragma unroll
-	for (int i = 0; i < count; i++)
-		if (s0 + i < applied) prefetch_l2(units4 + 8u * (size_t)(simple_key_at<RCKEYS>(pk, simple_sub_offset<3>(s0 + i, step), rc_len) & kPhaseMask));
 }
 
 template <int GAP, int MODE, bool RCKEYS = false>

@@ -478,12 +478,6 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 				C1.base = C0.base + C0.n * kSimpleClusterWords * 32;
 				C1.cap = pool - C0.n;
 			}
-#if SR_DENSE_PF_NEXT > 0
-			if (MODE == 4 && it < 3) {                                // the first units of the next pass: under way while this one runs
-				const int m2 = (it + 1) & 1, rc2 = (((it + 1) >> 1) ^ (m2 ? rev1 : rev0)) != 0;
-				simple_dense_ask<true>(ix, pk + m2 * n_words * kSimpleThreads, m2 ? applied1 : applied0, m2 ? step1 : step0, rc2 ? (m2 ? L1 : L0) : 0, 0, SR_DENSE_PF_NEXT);
-			}
-#endif
 			if (!simple_pass<GAP, MODE, true>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0,
 			                                  rc ? (m ? L1 : L0) : 0, n_gather)) punt = true;
 			else if (m == 1) {
