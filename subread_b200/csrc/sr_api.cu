@@ -392,6 +392,21 @@ __global__ void k_compact_results(const ResultWords *out, uint32_t n_slots, uint
 	}
 }
 
+// chr_hint[b] = the first chromosome whose cumulative end offset lies above b << kChrHintShift (total when there is none):
+// where locate_position may start its scan for any position of that 64 Kbp block.
+__global__ void k_chr_hint(const uint32_t *offs, int total, uint32_t *hint, uint32_t n_blocks)
+{
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += gridDim.x * blockDim.x) {
+		const uint32_t x = b << kChrHintShift;
+		int lo = 0, hi = total;                          // first n with offs[n] > x
+		while (lo < hi) {
+			const int mid = (lo + hi) >> 1;
+			if (offs[mid] > x) hi = mid; else lo = mid + 1;
+		}
+		hint[b] = (uint32_t)lo;
+	}
+}
+
 // Random 32-byte-sector gather: the "HBM-gather roofline" probe.
 __global__ void k_gather_probe(const uint4 *table, uint64_t n_sectors, int per_thread, uint32_t seed, uint32_t *sink)
 {
@@ -489,7 +504,7 @@ struct srcuda_handle {
 	bool has_index = false;
 	sr::DevIndex ix{};
 	srcuda_index_desc desc{};
-	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr;
+	void *d_bucket_start = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_genome = nullptr, *d_chr = nullptr, *d_chr_hint = nullptr;
 	void *d_records = nullptr, *d_bloom = nullptr, *d_direct = nullptr, *d_direct_first = nullptr, *d_phase_any = nullptr, *d_phase_units = nullptr, *d_phase_dense = nullptr;
 	bool use_phase = true;         // SRCUDA_PHASE=0: no phase table for gapped sparse indexes (A/B and cross-checks)
 	// The single-end tier's one-indel closed form costs an error-free chunk 13 %, so it is launched only while the chunks hold such
@@ -522,6 +537,10 @@ struct srcuda_handle {
 	int simple_pe_smem_set[4][5] = {};
 	int simple_smem_set[4][5] = {};  // dynamic shared memory already granted to k_map_simple<GAP, MODE>
 	int64_t batch_frags = 1 << 20;
+	bool batch_frags_set = false;    // SRCUDA_BATCH_FRAGS given: taken as is
+	bool pe_cw3 = true;              // SRCUDA_PE_CW3=0: always four-word clusters in the paired-end tier
+	int simple_pe_cw3_smem_set[2] = {0, 0};
+	int pe_pad_smem = 0;             // SRCUDA_PE_PAD_SMEM: extra dynamic shared memory per block of the paired-end tier (occupancy experiments)
 	uint32_t *d_sink = nullptr;
 };
 
@@ -567,7 +586,8 @@ int ensure(srcuda_handle *h, DeviceBuf &b, size_t bytes)
 
 void free_index(srcuda_handle *h)
 {
-	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr);
+	cudaFree(h->d_bucket_start); cudaFree(h->d_keys); cudaFree(h->d_vals); cudaFree(h->d_genome); cudaFree(h->d_chr); cudaFree(h->d_chr_hint);
+	h->d_chr_hint = nullptr;
 	cudaFree(h->d_records); cudaFree(h->d_bloom); cudaFree(h->d_direct); cudaFree(h->d_direct_first); cudaFree(h->d_phase_any); cudaFree(h->d_phase_units); cudaFree(h->d_phase_dense);
 	h->d_direct = h->d_direct_first = h->d_phase_any = h->d_phase_units = h->d_phase_dense = nullptr;
 	h->d_bucket_start = h->d_keys = h->d_vals = h->d_genome = h->d_chr = h->d_records = h->d_bloom = nullptr;
@@ -634,6 +654,16 @@ int build_accelerators(srcuda_handle *h)
 	h->ix.phase_units = nullptr;
 	h->ix.phase_dense = nullptr;
 	h->desc.accelerators = 0;
+	{   // where locate_position starts (sr_common.cuh): one entry per 64 Kbp of the 32-bit coordinate space, 256 KB
+		const uint32_t n_blocks = 1u << (32 - sr::kChrHintShift);
+		h->ix.chr_hint = nullptr;
+		cudaFree(h->d_chr_hint);
+		h->d_chr_hint = nullptr;
+		CU(h, cudaMalloc(&h->d_chr_hint, sizeof(uint32_t) * (size_t)n_blocks));
+		sr::k_chr_hint<<<(n_blocks + 255) / 256, 256>>>(h->ix.chr_offsets, h->ix.total_offsets, (uint32_t *)h->d_chr_hint, n_blocks);
+		CU(h, cudaGetLastError());
+		h->ix.chr_hint = (const uint32_t *)h->d_chr_hint;
+	}
 	if (mode & 4) {
 		int rc = build_direct(h);
 		if (rc) return rc;
@@ -922,8 +952,10 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	if (tier0_pe) {
 		const int threads = sr::kSimpleThreads;
 		const int64_t blocks = (a.n_frags + threads - 1) / threads;
-		const int clusters = h->ix.direct ? (cfg.do_junctions ? sr::kPePoolDenseJunc : (h->pe_pool_dense ? h->pe_pool_dense : sr::kPePoolDense)) : sr::kPePool;     // one pool for both mates
-		const int smem = sr::simple_pe_smem_bytes(max_len, clusters);
+		// dense phase units, reads of at most kLongRead bases (at most 32 subreads): three-word clusters, a fourth block per SM
+		const bool cw3 = h->pe_cw3 && h->ix.phase_dense && h->ix.index_gap == 3 && !cfg.do_junctions && max_len <= sr::kLongRead && cfg.total_subreads <= 32;
+		const int clusters = h->ix.direct ? (cfg.do_junctions ? sr::kPePoolDenseJunc : (h->pe_pool_dense ? h->pe_pool_dense : (cw3 ? sr::kPePoolDense3 : sr::kPePoolDense))) : sr::kPePool;     // one pool for both mates
+		const int smem = sr::simple_pe_smem_bytes(max_len, clusters, cw3 ? 3 : sr::kSimpleClusterWords) + h->pe_pad_smem;
 		uint32_t *q0 = (uint32_t *)bs.queue0.p;
 #define SR_LAUNCH_PE_U(G, U)                                                                                                         \
 	do {                                                                                                                             \
@@ -942,6 +974,17 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			h->simple_pe_rmw_smem_set[G][U] = smem;                                                                                  \
 		}                                                                                                                            \
 		sr::k_map_simple_pe<G, U, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,           \
+		                                                                              a.text_bytes, a.off, a.len, a.n_frags,        \
+		                                                                              max_len, clusters, a.out, q0,                 \
+		                                                                              bs.counters + 2, a.bad_reads, bs.counters + 3);                \
+	} while (0)
+#define SR_LAUNCH_PE_3(RMW_, SET_)                                                                                                   \
+	do {                                                                                                                             \
+		if (smem > h->simple_pe_cw3_smem_set[SET_]) {                                                                                \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<3, 4, false, RMW_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			h->simple_pe_cw3_smem_set[SET_] = smem;                                                                                  \
+		}                                                                                                                            \
+		sr::k_map_simple_pe<3, 4, false, RMW_, 3><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,         \
 		                                                                              a.text_bytes, a.off, a.len, a.n_frags,        \
 		                                                                              max_len, clusters, a.out, q0,                 \
 		                                                                              bs.counters + 2, a.bad_reads, bs.counters + 3);                \
@@ -980,6 +1023,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 					else SR_LAUNCH_PE_U(3, 3);
 				} else if (h->ix.phase_dense) {
 					if (cfg.do_junctions) SR_LAUNCH_PE_J(3, 4);
+					else if (cw3) { if (!a.out_zero) SR_LAUNCH_PE_3(true, 1); else SR_LAUNCH_PE_3(false, 0); }
 					else if (!a.out_zero) SR_LAUNCH_PE_R(3, 4);
 					else SR_LAUNCH_PE_U(3, 4);
 				} else SR_LAUNCH_PE(3);
@@ -991,6 +1035,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 			aw.in_count = bs.counters + 2;
 		}
 #undef SR_LAUNCH_PE_U
+#undef SR_LAUNCH_PE_3
 #undef SR_LAUNCH_PE_R
 #undef SR_LAUNCH_PE_J
 #undef SR_LAUNCH_PE
@@ -1090,7 +1135,11 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (lp && lp[0] == '0') h->l2_persist = false;
 	if (cudaSetDevice(device) != cudaSuccess) { delete h; return fail(nullptr, SRCUDA_ERR_CUDA, "cudaSetDevice(%d) failed", device); }
 	const char *bf = getenv("SRCUDA_BATCH_FRAGS");
-	if (bf && atoll(bf) > 0) h->batch_frags = atoll(bf);
+	if (bf && atoll(bf) > 0) { h->batch_frags = atoll(bf); h->batch_frags_set = true; }
+	const char *c3 = getenv("SRCUDA_PE_CW3");
+	if (c3 && c3[0] == '0') h->pe_cw3 = false;
+	const char *ps = getenv("SRCUDA_PE_PAD_SMEM");
+	if (ps && atoi(ps) > 0) h->pe_pad_smem = atoi(ps);
 	const char *st = getenv("SRCUDA_SIMPLE_TIER");
 	if (st && st[0] == '0') h->use_simple_tier = false;
 	const char *ph = getenv("SRCUDA_PHASE");
@@ -1414,7 +1463,15 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 	if (n_frags == 0) return SRCUDA_OK;
 
 	const int mates = 1 + (is_paired ? 1 : 0), mb = cfg.multi_best_reads;
-	const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->batch_frags, 0x7fffffffLL));
+	// Batches: up to batch_frags fragments (SRCUDA_BATCH_FRAGS; default 1 Mi reads), but at least eight per chunk while they stay above
+	// 256 Ki reads -- the first copy up and the last results down are not overlapped with anything, so a chunk of 3.5 M pairs in four
+	// batches spent a third of its time filling and draining (human_pe end to end: 177 -> 232 M reads/s with eight)
+	int64_t batch = std::max<int64_t>(1, std::min<int64_t>(h->batch_frags, 0x7fffffffLL));
+	if (!h->batch_frags_set) {
+		batch = std::max<int64_t>(1, batch / mates);
+		const int64_t eighth = ((n_frags + 7) / 8 + 65535) / 65536 * 65536, floor_frags = std::max<int64_t>(1, (256 << 10) / mates);
+		batch = std::min(batch, std::max(eighth, floor_frags));
+	}
 	const int64_t n_batches = (n_frags + batch - 1) / batch;
 	while ((int64_t)h->events.size() < 4 * n_batches) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->events.push_back(e); }
 	for (int i = 0; i < kSets; i++) {

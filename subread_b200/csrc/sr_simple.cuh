@@ -77,7 +77,7 @@ constexpr int kSimpleClusterWords = 4;                   // shared-memory words 
 // Shared-memory plan of one block (host and device agree through these functions): the packed reads of the 128
 // threads, then one private area per warp that first stages the warp's text and later holds its vote clusters.
 SR_HD int simple_words(int max_len) { return ((max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen) + 15) / 16 + 1; }
-SR_HD int simple_cluster_bytes(int clusters) { return clusters * kSimpleClusterWords * 32 * 4; }
+SR_HD int simple_cluster_bytes(int clusters, int words = kSimpleClusterWords) { return clusters * words * 32 * 4; }
 SR_HD int simple_warp_bytes(int max_len, int clusters = kSimpleClusters)
 {
 	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
@@ -126,12 +126,16 @@ struct SimpleCluster {
 	__device__ __forceinline__ int order() const { return (int)(((w1 >> 24) & 31u) << 15 | (w1 & 255u) << 7 | ((w1 >> 16) & 127u)); }
 };
 
-// The clusters of the running pass in shared memory, four words each, interleaved over the warp's lanes.
-struct SimpleClusters {
+// The clusters of the running pass in shared memory, CW words each, interleaved over the warp's lanes.  CW = 4 everywhere but in
+// the paired-end tier on dense tables with reads of at most kLongRead bases (at most 32 subreads, so one word of subread bits
+// does): there shared memory per thread bounds the resident warps, and three words per cluster make room for a fourth block.
+template <int CW>
+struct SimpleClustersT {
+	static constexpr int kWords = CW;
 	uint32_t *base;     // &clusters[0][0][lane] in the warp's private area
 	int n, cap;
-	__device__ __forceinline__ uint32_t &w(int c, int i) const { return base[(c * kSimpleClusterWords + i) * 32]; }
-	__device__ __forceinline__ int votes(int c) const { return (w(c, 1) >> 31) ? __popc(w(c, 2)) + __popc(w(c, 3)) : 0; }
+	__device__ __forceinline__ uint32_t &w(int c, int i) const { return base[(c * CW + i) * 32]; }
+	__device__ __forceinline__ int votes(int c) const { return (w(c, 1) >> 31) ? __popc(w(c, 2)) + (CW > 3 ? __popc(w(c, CW - 1)) : 0) : 0; }
 	__device__ __forceinline__ int order(int c) const
 	{
 		const uint32_t w1 = w(c, 1);
@@ -141,14 +145,17 @@ struct SimpleClusters {
 	{
 		SimpleCluster r;
 		r.kv = w(c, 0); r.w1 = w(c, 1);
-		r.subs = (unsigned long long)w(c, 2) | ((unsigned long long)w(c, 3) << 32);
+		r.subs = (unsigned long long)w(c, 2);
+		if (CW > 3) r.subs |= (unsigned long long)w(c, CW - 1) << 32;
 		return r;
 	}
 	__device__ __forceinline__ void put(int c, const SimpleCluster &r) const
 	{
-		w(c, 0) = r.kv; w(c, 1) = r.w1; w(c, 2) = (uint32_t)r.subs; w(c, 3) = (uint32_t)(r.subs >> 32);
+		w(c, 0) = r.kv; w(c, 1) = r.w1; w(c, 2) = (uint32_t)r.subs;
+		if (CW > 3) w(c, CW - 1) = (uint32_t)(r.subs >> 32);
 	}
 };
+using SimpleClusters = SimpleClustersT<kSimpleClusterWords>;
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -190,7 +197,8 @@ __device__ __forceinline__ SimpleCluster simple_new_cluster(uint32_t kv, int l, 
 
 // One hit on the general path (clusters in shared memory).  Returns false when the pass is not separable.
 // (Rare path: a real call keeps the hot loop small.)
-__device__ SR_SIMPLE_HIT_INLINE bool simple_hit(SimpleClusters &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high, int *found_out = nullptr)
+template <class CL>
+__device__ SR_SIMPLE_HIT_INLINE bool simple_hit(CL &C, uint32_t kv, int l, int u, int sub, int tol, uint32_t low, uint32_t high, int *found_out = nullptr)
 {
 	if (!(kv >= 32u && kv <= 0xffffffdfu)) return false;           // u32 wrap-around of the probe rows
 	int found = -1;
@@ -734,12 +742,12 @@ __device__ __forceinline__ bool simple_pass_phase(const DevIndex &ix, const Vote
 // sieves and the convergent hit(), the two-step unit, the entries behind the loop, the pipelined runs and the compacted hits;
 // prefetch.global.L2 of the units further down (3 or 6 ahead, or the next pass's first two) cost 7 %; 64 bytes of a unit in
 // registers changed nothing.
-template <bool RCKEYS>
+template <bool RCKEYS, class CL>
 __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, const VoteConfig &cfg, const uint32_t *pk, int L, int applied, int step,
-                                                        SimpleClusters &C_out, int rc_len, uint32_t &n_gather)
+                                                        CL &C_out, int rc_len, uint32_t &n_gather)
 {
 	constexpr int GAP = 3, kSubs = 10;
-	SimpleClusters C = C_out;         // (the caller hands over one of two lists picked at run time: a copy keeps base / n / cap in plain registers)
+	CL C = C_out;         // (the caller hands over one of two lists picked at run time: a copy keeps base / n / cap in plain registers)
 	const int tol = cfg.indel_tolerance;
 	const uint32_t low = cfg.low_border, high = cfg.high_border - (uint32_t)L;
 	const uint4 *units4 = reinterpret_cast<const uint4 *>(ix.phase_dense);
@@ -779,7 +787,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		if (same | fresh) {
 			if (fresh && (!(kv >= 32u && kv <= 0xffffffdfu) || C.n >= C.cap)) return false;   // u32 wrap-around of the probe rows; list full
 			const int idx = same ? last_c : C.n;
-			uint32_t *cw = C.base + idx * (kSimpleClusterWords * 32), *cs = cw + (2 + (sub >> 5)) * 32;   // the cluster's words; the one with the subread's bit
+			uint32_t *cw = C.base + idx * (CL::kWords * 32), *cs = cw + (2 + (sub >> 5)) * 32;   // the cluster's words; the one with the subread's bit (three-word clusters: sub < 32)
 			const uint32_t bit = 1u << (sub & 31);
 			uint32_t w1 = (kv >= low && kv <= high) ? ((uint32_t)l | ((uint32_t)l << 8) | ((uint32_t)u << 16) | 0x80000000u) : 0u;   // :1074
 			uint32_t sw = 0u;
@@ -792,7 +800,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 			}
 			if (fresh) {
 				cw[0] = kv;
-				cw[(3 - (sub >> 5)) * 32] = 0u;
+				if (CL::kWords > 3) cw[(3 - (sub >> 5)) * 32] = 0u;
 				C.n++;
 				occ_a |= ba;
 				occ_b |= bb;
@@ -986,7 +994,7 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 #pragma unroll 1
 	for (int c = 0; c < C.n; c++) {
 		C.w(c, 2) = (uint32_t)C.votes(c);
-		C.w(c, 3) = 0u;
+		if (CL::kWords > 3) C.w(c, 3) = 0u;
 		C.w(c, 1) |= vote_row(C.w(c, 0)) << 24;                    // (hit() leaves the row field to this loop: once per cluster, all lanes together)
 	}
 	C_out.n = C.n;
@@ -999,7 +1007,7 @@ __device__ __forceinline__ bool simple_pass(const DevIndex &ix, const VoteConfig
                                             uint32_t *sec2 = nullptr /* shared-memory word of the thread: one-indel reads stay in the tier; on return the merge's word */)
 {
 	if (MODE == 3) return simple_pass_phase<RCKEYS>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather, sec2);
-	if (MODE == 4) return simple_pass_phase_dense<RCKEYS>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather);
+	if (MODE == 4) return simple_pass_phase_dense<RCKEYS, SimpleClusters>(ix, cfg, pk, L, applied, step, C, rc_len, n_gather);
 	constexpr bool DIRECT = MODE == 2;
 	constexpr int kSubsPerBatch = 32 / GAP;                        // whole subreads per batch of <= 32 lookups
 	const uint32_t nb = ix.buckets_number;

@@ -34,21 +34,22 @@ constexpr int kPePoolDenseJunc = 32;
 constexpr int kPeResWords = 4;    // SimpleResult in shared memory: pos, votes, meta (+ used subreads), coverage
 constexpr int kPePool = 12;       // vote clusters of both mates of one strand pass, shared (the second mate takes what
 constexpr int kPePoolDense = 26;  // the first one left); dense tables: a handful of one-vote random hits per mate
+constexpr int kPePoolDense3 = 22; // ... with three-word clusters (reads <= kLongRead): 448 bytes of shared memory per thread, four blocks per SM
 
-SR_HD int simple_pe_warp_bytes(int max_len, int pool)
+SR_HD int simple_pe_warp_bytes(int max_len, int pool, int cw = kSimpleClusterWords)
 {
 	const int ml = max_len < kSimpleMaxLen ? max_len : kSimpleMaxLen;
 	int area = 32 * (((ml + 3) & ~3) + 4) + 32;                               // text of 32 reads (half of the warp's 64)
-	const int clus = simple_cluster_bytes(pool);                              // the cluster pool reuses the staging area
+	const int clus = simple_cluster_bytes(pool, cw);                          // the cluster pool reuses the staging area
 	if (area < clus) area = clus;
 	area = (area + 15) & ~15;
 	return area + 2 * kMaxBest * kPeResWords * 32 * 4;                         // + what the bigtable holds so far
 }
-SR_HD int simple_pe_area_bytes(int max_len, int pool) { return simple_pe_warp_bytes(max_len, pool) - 2 * kMaxBest * kPeResWords * 32 * 4; }
+SR_HD int simple_pe_area_bytes(int max_len, int pool, int cw = kSimpleClusterWords) { return simple_pe_warp_bytes(max_len, pool, cw) - 2 * kMaxBest * kPeResWords * 32 * 4; }
 // Only the forward strand of each mate is kept packed (reverse-strand keys are derived, simple_key_at).
-SR_HD int simple_pe_smem_bytes(int max_len, int pool)
+SR_HD int simple_pe_smem_bytes(int max_len, int pool, int cw = kSimpleClusterWords)
 {
-	return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_pe_warp_bytes(max_len, pool);
+	return 2 * simple_words(max_len) * kSimpleThreads * 4 + (kSimpleThreads / 32) * simple_pe_warp_bytes(max_len, pool, cw);
 }
 
 // subjunc: per thread the subjunc_result_t slots of both mates so far (24 words), those of the mate being emitted (12) and the
@@ -80,8 +81,8 @@ struct PeResults {
 // not fit (the fragment is then queued for the warp kernel).  simple_pass has left every cluster's vote count in word 2.
 // JUNC (subjunc): J = both mates' subjunc_result_t slots ([m][k][4] words at stride kSimpleThreads), JT = the three slots of the
 // mate being emitted, bm = the two big-margin records (12 u16 each), text0 / text1 = the mates' reads of this pass.
-template <int GAP, bool JUNC = false>
-__device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteConfig &cfg, const SimpleClusters &C0, const SimpleClusters &C1,
+template <int GAP, bool JUNC = false, class CL = SimpleClusters>
+__device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteConfig &cfg, const CL &C0, const CL &C1,
                                                 const PeResults &R, int strand, int applied0, int applied1, int step0, int step1, int len0, int len1,
                                                 uint32_t *J = nullptr, uint32_t *JT = nullptr, uint16_t *bm = nullptr,
                                                 const TierText *text0 = nullptr, const TierText *text1 = nullptr)
@@ -94,7 +95,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 		int top = 0;
 #pragma unroll 1
 		for (int m = 0; m < 2; m++) {
-			const SimpleClusters &C = m ? C1 : C0;
+			const CL &C = m ? C1 : C0;
 #pragma unroll 1
 			for (int c = 0; c < C.n; c++) top = max(top, (int)C.w(c, 2));
 #pragma unroll 1
@@ -116,7 +117,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 	int nc[2] = {0, 0};
 #pragma unroll 1
 	for (int m = 0; m < 2; m++) {
-		const SimpleClusters &C = m ? C1 : C0;
+		const CL &C = m ? C1 : C0;
 		int t0 = 0, t1 = 0, t2 = 0;
 #pragma unroll 1
 		for (int c = 0; c < C.n + kMaxBest; c++) {
@@ -188,12 +189,13 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 		for (int j = 0; j < n1; j++) {
 			const int sj = cand_src(1, j), v2 = cand_votes(1, sj);
 			if (max(v1, v2) < cfg.min_first) continue;
-			if (!located) { re1 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(0, si), &chr1, &lp1); located = true; }
+			if (!located) { re1 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(0, si), &chr1, &lp1, ix.chr_hint); located = true; }
 			int chr2, lp2, is_pe;
 			int re2;
 			// The second mate's candidates are located once per strand pass: the chromosome found by the binary search is
 			// remembered in the cluster's spare word 3 (bit 31 set, re in bits 16-17, chromosome in bits 0-15).
-			const uint32_t memo = sj < 32 ? C1.w(sj, 3) : 0u;
+			uint32_t memo = 0u;
+			if constexpr (CL::kWords > 3) memo = sj < 32 ? C1.w(sj, 3) : 0u;       // (three-word clusters: no spare word, and the hint table made the lookup cheap)
 			if (memo >> 31) {
 				re2 = (int)((memo >> 16) & 3u);
 				if (re2 == 2) re2 = -1;
@@ -204,8 +206,9 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 					lp2 = (int)(chr2 == 0 ? linear : linear - ix.chr_offsets[chr2 - 1]) - ix.padding;
 				}
 			} else {
-				re2 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(1, sj), &chr2, &lp2);
-				if (sj < 32 && (re2 != 0 || chr2 < 0x10000)) C1.w(sj, 3) = 0x80000000u | ((uint32_t)(re2 < 0 ? 2 : re2) << 16) | (uint32_t)(re2 == 0 ? chr2 : 0);
+				re2 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(1, sj), &chr2, &lp2, ix.chr_hint);
+				if constexpr (CL::kWords > 3)
+					if (sj < 32 && (re2 != 0 || chr2 < 0x10000)) C1.w(sj, 3) = 0x80000000u | ((uint32_t)(re2 < 0 ? 2 : re2) << 16) | (uint32_t)(re2 == 0 ? chr2 : 0);
 			}
 			const int weight = pair_weight(re1, chr1, lp1, re2, chr2, lp2, len0, len1, cfg.min_pair_dist, cfg.max_pair_dist, &is_pe);
 			if (!is_pe && min(v1, v2) < cfg.min_first) continue;
@@ -238,7 +241,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 	// ---- emission (:2386-2527), one mate at a time: the new slots are composed in registers before any is stored ----
 #pragma unroll 1
 	for (int m = 0; m < 2; m++) {
-		const SimpleClusters &C = m ? C1 : C0;
+		const CL &C = m ? C1 : C0;
 		const int applied = m ? applied1 : applied0, step = m ? step1 : step0;
 		int cursor = 0;
 		int esrc0 = 0, esrc1 = 0, esrc2 = 0;
@@ -281,7 +284,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 					nr[k].pos = C.w(src, 0); nr[k].votes = (int)C.w(src, 2); nr[k].used = applied;
 					nr[k].meta = 1u | ((uint32_t)strand << 8) | ((uint32_t)(s_first + 1) << 16) | ((uint32_t)(s_last + 1) << 24);
 					nr[k].cov = (uint32_t)o_first | ((uint32_t)(o_last + 16) << 16);
-					if (JUNC) {                              // the slot's subjunc_result_t: minor half / donor search
+					if constexpr (JUNC) {                    // the slot's subjunc_result_t: minor half / donor search
 						uint32_t *jr = JT + k * 4 * kSimpleThreads;
 						jr[0] = jr[kSimpleThreads] = jr[2 * kSimpleThreads] = jr[3 * kSimpleThreads] = 0u;
 						nr[k].meta |= tier_minor_half<GAP>(ix, cfg, C, src, step, m ? len1 : len0, m ? *text1 : *text0, jr) << 12;
@@ -316,8 +319,8 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 
 // k_map_simple_pe: thread t of block b maps paired-end fragment 128 b + t (reads 2f and 2f + 1 of the chunk) of a chunk
 // whose bigtable slice is all zero.  Dynamic shared memory: simple_pe_smem_bytes(max_len, clusters).
-template <int GAP, int MODE, bool JUNC = false, bool RMW = false>
-__global__ void __launch_bounds__(kSimpleThreads, (JUNC || MODE == 4) ? 3 : 4)   // (dense tables: the cluster pool in shared memory allows three blocks anyway)
+template <int GAP, int MODE, bool JUNC = false, bool RMW = false, int CW = kSimpleClusterWords>
+__global__ void __launch_bounds__(kSimpleThreads, (JUNC || (MODE == 4 && CW > 3)) ? 3 : 4)   // (dense tables, four-word clusters: the pool in shared memory allows three blocks anyway)
 k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, uint64_t text_origin, uint64_t text_bytes,
                 const uint64_t *off, const uint16_t *len, int64_t n_frags, int max_len, int pool, ResultWords *out, uint32_t *queue,
                 uint32_t *queue_count, uint32_t *bad_reads, uint32_t *gather_count, JuncWords *jout = nullptr, uint16_t *bmout = nullptr)
@@ -326,7 +329,9 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 	constexpr unsigned kFullMask = 0xffffffffu;
 	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
 	const int n_words = simple_words(max_len);
-	const int warp_cap = simple_pe_warp_bytes(max_len, pool), area_cap = simple_pe_area_bytes(max_len, pool);
+	static_assert(CW == kSimpleClusterWords || (MODE == 4 && !JUNC), "three-word clusters: dense phase pass without the junction half only");
+	using CL = SimpleClustersT<CW>;
+	const int warp_cap = simple_pe_warp_bytes(max_len, pool, CW), area_cap = simple_pe_area_bytes(max_len, pool, CW);
 	uint32_t *pk = reinterpret_cast<uint32_t *>(smem4) + t;                                     // [mate][n_words][128], forward strand
 	uint8_t *stage = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem4) + 2 * n_words * kSimpleThreads) + wid * warp_cap;
 	const int64_t fw0 = (int64_t)blockIdx.x * kSimpleThreads + 32 * wid, f = fw0 + lane;
@@ -450,7 +455,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 				R.put(m, k, r);
 			}
 	}
-	uint32_t *jblock = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem4) + simple_pe_smem_bytes(max_len, pool));
+	uint32_t *jblock = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem4) + simple_pe_smem_bytes(max_len, pool, CW));
 	uint32_t *J = jblock + t, *JT = J + 2 * kMaxBest * 4 * kSimpleThreads;
 	uint16_t *bm = reinterpret_cast<uint16_t *>(jblock + 3 * kMaxBest * 4 * kSimpleThreads + 12 * t);
 	if (JUNC) {
@@ -459,7 +464,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 #pragma unroll 1
 		for (int i = 0; i < 24; i++) bm[i] = 0;
 	}
-	SimpleClusters C0, C1;
+	CL C0, C1;
 	C0.base = C1.base = reinterpret_cast<uint32_t *>(stage) + lane;
 	C0.n = C1.n = 0;
 	C0.cap = C1.cap = pool;
@@ -475,16 +480,44 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 			const bool rc = (strand ^ (m ? rev1 : rev0)) != 0;
 			const uint32_t *pass = pk + m * n_words * kSimpleThreads;
 			if (m == 1) {                                             // the second mate's clusters follow the first one's
-				C1.base = C0.base + C0.n * kSimpleClusterWords * 32;
+				C1.base = C0.base + C0.n * CW * 32;
 				C1.cap = pool - C0.n;
 			}
-			if (!simple_pass<GAP, MODE, true>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0,
-			                                  rc ? (m ? L1 : L0) : 0, n_gather)) punt = true;
-			else if (m == 1) {
-				if (JUNC) {
-					const TierText tx0{pk, (strand ^ rev0) ? L0 : 0}, tx1{pk + n_words * kSimpleThreads, (strand ^ rev1) ? L1 : 0};
-					if (!simple_pe_merge<GAP, true>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1, J, JT, bm, &tx0, &tx1)) punt = true;
-				} else if (!simple_pe_merge<GAP>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1)) punt = true;
+			bool pass_ok;
+			if constexpr (MODE == 4) pass_ok = simple_pass_phase_dense<true, CL>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0, rc ? (m ? L1 : L0) : 0, n_gather);
+			else pass_ok = simple_pass<GAP, MODE, true>(ix, cfg, pass, m ? L1 : L0, m ? applied1 : applied0, m ? step1 : step0, m ? C1 : C0, rc ? (m ? L1 : L0) : 0, n_gather);
+			if (!pass_ok) punt = true;
+			else {
+				if constexpr (MODE == 4 && !JUNC) {
+					// Dense table: most of a mate's clusters are one-vote chance hits.  process_voting_junction_PE_topK only looks at the
+					// slots of a mate whose votes lie within max_vote_number_cutoff of that mate's best (table or earlier results,
+					// core-junction.c:2251-2316) -- the others neither become candidates nor move a vote level that could -- so they are
+					// dropped here, before the second mate takes what is left of the pool and before the merge walks the lists.
+					CL &C = m ? C1 : C0;
+					int best = 0;
+#pragma unroll 1
+					for (int c = 0; c < C.n; c++) best = max(best, (int)C.w(c, 2));
+#pragma unroll 1
+					for (int k = 0; k < mb; k++) best = max(best, (int)R.w(m, k, 1));
+					const int least = max(1, best - cfg.max_vote_number_cutoff);
+					int kept = 0;
+#pragma unroll 1
+					for (int c = 0; c < C.n; c++)
+						if ((int)C.w(c, 2) >= least) {
+							if (kept != c) {
+#pragma unroll
+								for (int i = 0; i < CW; i++) C.w(kept, i) = C.w(c, i);
+							}
+							kept++;
+						}
+					C.n = kept;
+				}
+				if (m == 1) {
+					if constexpr (JUNC) {
+						const TierText tx0{pk, (strand ^ rev0) ? L0 : 0}, tx1{pk + n_words * kSimpleThreads, (strand ^ rev1) ? L1 : 0};
+						if (!simple_pe_merge<GAP, true>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1, J, JT, bm, &tx0, &tx1)) punt = true;
+					} else if (!simple_pe_merge<GAP, false, CL>(ix, cfg, C0, C1, R, strand, applied0, applied1, step0, step1, L0, L1)) punt = true;
+				}
 			}
 		}
 	}

@@ -773,7 +773,7 @@ __device__ __forceinline__ void topk_warp(const DevIndex &ix, const VoteConfig &
 		const int n0 = n_cand[0], n1 = n_cand[1];
 		for (int c = lane; c < n0 + n1; c += 32) {
 			int m = c >= n0 ? 1 : 0, i = c - (m ? n0 : 0), chr, lp;
-			int re = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, ws.cand_pos[m][i], &chr, &lp);
+			int re = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, ws.cand_pos[m][i], &chr, &lp, ix.chr_hint);
 			ws.cand_re[m][i] = (int8_t)re;
 			ws.cand_chr[m][i] = (int16_t)chr;
 			ws.cand_lpos[m][i] = lp;
