@@ -637,7 +637,7 @@ def main():
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "traffic_source": traffic_note,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                        "kernel": ("k_map_simple_pe" if paired else "k_map_simple") + f"<3,{2 if desc.accelerators & 4 else (3 if desc.accelerators & 16 else 0)}> (one thread per fragment) + k_map_warp (queued fragments)",
+                        "kernel": ("k_map_simple_pe" if paired else "k_map_simple") + f"<3,{(4 if desc.accelerators & 16 else 2) if desc.accelerators & 4 else (3 if desc.accelerators & 16 else 0)}> (one thread per fragment; mode 3 / 4 = phase units of a sparse / dense table) + k_map_warp (queued fragments)",
                         "kernel_ms": res["kern_ms"], "tier0_ms": res["simple_ms"], "algorithmic_bytes_per_fragment": alg_bytes,
                         "tier0_punted_fraction": res["punted"] / R, "warp_kernel_ms": res["kern_ms"] - res["simple_ms"],
                         "scalar_fragments_per_step": res["n_over"], "scalar_kernel_ms": res["over_ms"],
