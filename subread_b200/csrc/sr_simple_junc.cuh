@@ -66,28 +66,41 @@ __device__ __noinline__ uint32_t tier_minor_half(const DevIndex &ix, const VoteC
 	int cs_m, ce_m;
 	tier_cluster_cov<GAP>(C.w(self, 1), step, &cs_m, &ce_m);
 	uint32_t flags = 0;
-	unsigned done = 1u << self;
+	// Which of the other slots can take part at all: every screen that does not look at the running best (test_junction_minor :889,
+	// the overlap and distance limits) in one pass over the list, all lanes together -- on a human-sized index nearly every slot is
+	// a one-vote chance hit gigabases away.  The ordered walk below (quadratic in the slots it visits) then sees one or two.
+	unsigned done = ~0u;
 #pragma unroll 1
-	for (;;) {                                                     // the other slots in (row, rank in row) order
+	for (int c = 0; c < C.n; c++) {
+		if (c == self || !(C.w(c, 1) >> 31)) continue;
+		const int mv = (int)C.w(c, 2);
+		const uint32_t pn = C.w(c, 0);
+		const long long dist = (long long)pm - (long long)pn;
+		int cs_n, ce_n;
+		tier_cluster_cov<GAP>(C.w(c, 1), step, &cs_n, &ce_n);
+		bool in = sel_votes >= mv && sc_abs((int)dist) <= cfg.maximum_intron_length && cs_m != cs_n && ce_m != ce_n;
+		if (cs_m > cs_n) { if (pm < pn) in = false; } else { if (pm > pn) in = false; }
+		const int overlapped = cs_m > cs_n ? ce_n - cs_m : ce_m - cs_n;
+		if (overlapped > 14 || sc_abs((int)dist) < 6) in = false;
+		if (in) done &= ~(1u << c);
+	}
+#pragma unroll 1
+	for (;;) {                                                     // the slots left, in (row, rank in row) order
 		int s = -1, best_key = 0x7fffffff;
+		if (done == ~0u) break;
 #pragma unroll 1
 		for (int c = 0; c < C.n; c++)
-			if (!((done >> c) & 1u) && (C.w(c, 1) >> 31)) {
+			if (!((done >> c) & 1u)) {
 				const int key = C.order(c);
 				if (key < best_key) { best_key = key; s = c; }
 			}
 		if (s < 0) break;
 		done |= 1u << s;
 		const int mv = (int)C.w(s, 2);
-		if (sel_votes < mv) continue;
 		const uint32_t pn = C.w(s, 0);
 		const long long dist = (long long)pm - (long long)pn;
 		int cs_n, ce_n;
 		tier_cluster_cov<GAP>(C.w(s, 1), step, &cs_n, &ce_n);
-		if (sc_abs((int)dist) > cfg.maximum_intron_length) continue;
-		if (cs_m == cs_n) continue;
-		if (ce_m == ce_n) continue;
-		if (cs_m > cs_n) { if (pm < pn) continue; } else { if (pm > pn) continue; }
 		const uint32_t j0 = jr[0], j2 = jr[2 * kSimpleThreads], j3 = jr[3 * kSimpleThreads];
 		const int16_t jr_votes = (int16_t)(j0 >> 16);
 		const int jcov = (int)(uint16_t)(j3 >> 16) - (int)(uint16_t)(j3 & 0xffffu);
