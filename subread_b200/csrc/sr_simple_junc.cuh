@@ -40,6 +40,29 @@ struct TierText {
 		if (pos > 0xffff0000u) return 0;
 		uint32_t q = pos - ix.start_base_offset;
 		if ((q >> 2) >= ix.values_bytes) return 0;
+		if (len <= 17 && off >= 0 && (rc_len == 0 || off + len <= rc_len)) {
+			// Packed: the window of the genome (2 bits per base, base 0 lowest) against the window of the read in the same layout,
+			// XOR, fold the pairs, count.  34 bits at a bit offset of at most 30 fit two words on either side.
+			const uint32_t gw = q >> 4;
+			const unsigned long long g = (((unsigned long long)ix.genome[gw + 1] << 32) | ix.genome[gw]) >> (2 * (q & 15));
+			unsigned long long r;
+			if (rc_len == 0) {
+				// forward strand: bases off .. off + len - 1, first base highest -> reverse the order of the pairs
+				const int w = off >> 4;
+				const unsigned long long v = (((unsigned long long)pk[w * kSimpleThreads] << 32) | pk[(w + 1) * kSimpleThreads]) << (2 * (off & 15));
+				unsigned long long x = __brevll(v >> (64 - 2 * len)) >> (64 - 2 * len);
+				r = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+			} else {
+				// reverse strand: base i is the complement of forward base rc_len - 1 - i, so the forward window [f0, f0 + len) read
+				// with its first base highest already has reverse-strand base off + i at bits 2 i
+				const int f0 = rc_len - off - len, w = f0 >> 4;
+				const unsigned long long v = (((unsigned long long)pk[w * kSimpleThreads] << 32) | pk[(w + 1) * kSimpleThreads]) << (2 * (f0 & 15));
+				r = ~(v >> (64 - 2 * len));
+			}
+			unsigned long long d = r ^ g;
+			d = (d | (d >> 1)) & 0x5555555555555555ull & ((1ull << (2 * len)) - 1ull);
+			return len - __popcll(d);
+		}
 		int ret = 0;
 		for (int i = 0; i < len; i++, q++) ret += (int)((ix.genome[q >> 4] >> (2 * (q & 15))) & 3u) == code(off + i);
 		return ret;

@@ -128,6 +128,27 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 		}
 		int n = 0;
 		unsigned long long list = 0ull, list_hi = 0ull;
+		// subjunc walks every slot of the table in (row, rank in row) order, once per level and again per emitted slot; picking
+		// the next one by a scan over the list is quadratic (a sixth of the kernel's instructions on a dense table with its
+		// sixteen one-vote slots), so the visiting order is laid down once: word 3 of list position p = order key << 5 | index
+		// of the p-th slot to visit (insertion sort in place; the keys of a pass are distinct).
+		int n_sorted = 0;
+		if constexpr (JUNC) {
+#pragma unroll 1
+			for (int c = 0; c < C.n; c++)
+				if (C.w(c, 1) >> 31) {
+					const uint32_t e = ((uint32_t)C.order(c) << 5) | (uint32_t)c;
+					int p = n_sorted;
+#pragma unroll 1
+					for (; p > 0; p--) {
+						const uint32_t before = C.w(p - 1, 3);
+						if (before < e) break;
+						C.w(p, 3) = before;
+					}
+					C.w(p, 3) = e;
+					n_sorted++;
+				}
+		}
 #pragma unroll 1
 		for (int lv = 0; lv < ts; lv++) {
 			const int want = lv == 0 ? t0 : (lv == 1 ? t1 : t2);
@@ -136,15 +157,25 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 			if (want >= cfg.min_second || walk_all) {
 				const int top_last = ts == 1 ? t0 : (ts == 2 ? t1 : t2);
 				unsigned done = 0;
+				int p_sorted = 0;
 #pragma unroll 1
 				for (;;) {                                   // table slots of this level in (row, rank in row) order
-					int best = -1, best_key = 0x7fffffff;
+					int best = -1;
+					if constexpr (JUNC) {
 #pragma unroll 1
-					for (int c = 0; c < C.n; c++)
-						if (!((done >> c) & 1u) && (walk_all ? (C.w(c, 1) >> 31) != 0 : (int)C.w(c, 2) == want)) {
-							const int key = C.order(c);
-							if (key < best_key) { best_key = key; best = c; }
+						for (; p_sorted < n_sorted && best < 0; p_sorted++) {
+							const int c = (int)(C.w(p_sorted, 3) & 31u);
+							if (walk_all || (int)C.w(c, 2) == want) best = c;
 						}
+					} else {
+						int best_key = 0x7fffffff;
+#pragma unroll 1
+						for (int c = 0; c < C.n; c++)
+							if (!((done >> c) & 1u) && (int)C.w(c, 2) == want) {
+								const int key = C.order(c);
+								if (key < best_key) { best_key = key; best = c; }
+							}
+					}
 					if (best < 0) break;
 					done |= 1u << best;
 					const int vv = (int)C.w(best, 2);
@@ -195,7 +226,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 			// The second mate's candidates are located once per strand pass: the chromosome found by the binary search is
 			// remembered in the cluster's spare word 3 (bit 31 set, re in bits 16-17, chromosome in bits 0-15).
 			uint32_t memo = 0u;
-			if constexpr (CL::kWords > 3) memo = sj < 32 ? C1.w(sj, 3) : 0u;       // (three-word clusters: no spare word, and the hint table made the lookup cheap)
+			if constexpr (CL::kWords > 3 && !JUNC) memo = sj < 32 ? C1.w(sj, 3) : 0u;   // (three-word clusters: no spare word; subjunc: word 3 holds the visiting order; the hint table made the lookup cheap)
 			if (memo >> 31) {
 				re2 = (int)((memo >> 16) & 3u);
 				if (re2 == 2) re2 = -1;
@@ -207,7 +238,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 				}
 			} else {
 				re2 = locate_position(ix.chr_offsets, ix.total_offsets, ix.padding, cand_pos(1, sj), &chr2, &lp2, ix.chr_hint);
-				if constexpr (CL::kWords > 3)
+				if constexpr (CL::kWords > 3 && !JUNC)
 					if (sj < 32 && (re2 != 0 || chr2 < 0x10000)) C1.w(sj, 3) = 0x80000000u | ((uint32_t)(re2 < 0 ? 2 : re2) << 16) | (uint32_t)(re2 == 0 ? chr2 : 0);
 			}
 			const int weight = pair_weight(re1, chr1, lp1, re2, chr2, lp2, len0, len1, cfg.min_pair_dist, cfg.max_pair_dist, &is_pe);
