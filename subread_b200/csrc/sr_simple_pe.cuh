@@ -31,10 +31,10 @@ constexpr int kPeCand = 8;        // candidates per mate
 constexpr int kPeCandJunc = 16;   // ... in subjunc mode, where minimum_subread_for_first_read = 1 makes every one-vote slot of a
                                   // dense table's wrong-strand pass a candidate
 constexpr int kPePoolDenseJunc = 32;
-constexpr int kPeResWords = 4;    // SimpleResult in shared memory: pos, votes, meta (+ used subreads), coverage
+constexpr int kPeResWords = 3;    // SimpleResult in shared memory: pos | votes (8 bits) + coverage start, end (12 bits each) | meta (+ used subreads)
 constexpr int kPePool = 12;       // vote clusters of both mates of one strand pass, shared (the second mate takes what
 constexpr int kPePoolDense = 26;  // the first one left); dense tables: a handful of one-vote random hits per mate
-constexpr int kPePoolDense3 = 22; // ... with three-word clusters (reads <= kLongRead): 448 bytes of shared memory per thread, four blocks per SM
+constexpr int kPePoolDense3 = 24; // ... with three-word clusters (reads <= kLongRead): 448 bytes of shared memory per thread, four blocks per SM
 
 SR_HD int simple_pe_warp_bytes(int max_len, int pool, int cw = kSimpleClusterWords)
 {
@@ -64,17 +64,23 @@ SR_HD int simple_pe_junc_smem_bytes(int max_len, int pool) { return simple_pe_sm
 struct PeResults {
 	uint32_t *base;
 	__device__ __forceinline__ uint32_t &w(int m, int k, int i) const { return base[((m * kMaxBest + k) * kPeResWords + i) * 32]; }
+	__device__ __forceinline__ int votes(int m, int k) const { return (int)(w(m, k, 1) & 255u); }
+	__device__ __forceinline__ void clear_votes(int m, int k) const { w(m, k, 1) &= ~255u; }     // (a record that lost its place keeps its other bytes)
 	__device__ __forceinline__ SimpleResult get(int m, int k) const
 	{
 		SimpleResult r;
-		const uint32_t me = w(m, k, 2);
-		r.pos = w(m, k, 0); r.votes = (int)w(m, k, 1); r.used = (int)((me >> 2) & 63u); r.meta = me & ~0xfcu; r.cov = w(m, k, 3);
+		const uint32_t vc = w(m, k, 1), me = w(m, k, 2);
+		r.pos = w(m, k, 0); r.votes = (int)(vc & 255u); r.used = (int)((me >> 2) & 63u); r.meta = me & ~0xfcu;
+		r.cov = ((vc >> 8) & 0xfffu) | ((vc >> 20) << 16);
 		return r;
 	}
 	__device__ __forceinline__ void put(int m, int k, const SimpleResult &r) const
 	{
-		w(m, k, 0) = r.pos; w(m, k, 1) = (uint32_t)r.votes; w(m, k, 2) = (r.meta & ~0xfcu) | ((uint32_t)r.used << 2); w(m, k, 3) = r.cov;
+		w(m, k, 0) = r.pos; w(m, k, 1) = ((uint32_t)r.votes & 255u) | ((r.cov & 0xfffu) << 8) | ((r.cov >> 16) << 20);
+		w(m, k, 2) = (r.meta & ~0xfcu) | ((uint32_t)r.used << 2);
 	}
+	// what the packed form can hold (the read-modify-write form loads records of earlier index blocks)
+	static __device__ __forceinline__ bool fits(const SimpleResult &r) { return (unsigned)r.votes <= 255u && (r.cov & 0xffffu) < 4096u && (r.cov >> 16) < 4096u; }
 };
 
 // process_voting_junction_PE_topK for one strand pass of a paired-end fragment.  Returns false when a candidate list does
@@ -99,14 +105,14 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 #pragma unroll 1
 			for (int c = 0; c < C.n; c++) top = max(top, (int)C.w(c, 2));
 #pragma unroll 1
-			for (int k = 0; k < mb; k++) top = max(top, (int)R.w(m, k, 1));
+			for (int k = 0; k < mb; k++) top = max(top, R.votes(m, k));
 		}
 		if (top < cfg.min_first && (!JUNC || top < 1)) {       // (subjunc walks the table for its big-margin records whenever a slot has votes)
 #pragma unroll 1
 			for (int m = 0; m < 2; m++)
 #pragma unroll 1
 				for (int k = 0; k < mb; k++) {
-					R.w(m, k, 1) = 0u;
+					R.clear_votes(m, k);
 					if (JUNC) J[((m * kMaxBest + k) * 4) * kSimpleThreads] &= 0x0000ffffu;
 				}
 			return true;
@@ -123,7 +129,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 		for (int c = 0; c < C.n + kMaxBest; c++) {
 			int v;
 			if (c < C.n) v = (int)C.w(c, 2);
-			else v = c - C.n < mb ? (int)R.w(m, c - C.n, 1) : 0;
+			else v = c - C.n < mb ? R.votes(m, c - C.n) : 0;
 			if (v > 0) simple_update_top(ts, t0, t1, t2, v);
 		}
 		int n = 0;
@@ -193,7 +199,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 			}
 #pragma unroll 1
 			for (int k = 0; k < mb; k++)
-				if ((int)R.w(m, k, 1) == want) {
+				if (R.votes(m, k) == want) {
 					if (n == KC) return false;
 					if (n < 8) list |= (unsigned long long)(32 + k) << (8 * n);
 					else list_hi |= (unsigned long long)(32 + k) << (8 * (n - 8));
@@ -207,7 +213,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 	const int n0 = nc[0], n1 = nc[1];
 	auto cand_src = [&](int m, int i) { return (int)(((i < 8 ? cl[m] : ch[m]) >> (8 * (i & 7))) & 0xffull); };
 	auto cand_pos = [&](int m, int src) { return src < 32 ? (m ? C1 : C0).w(src, 0) : R.w(m, src - 32, 0); };
-	auto cand_votes = [&](int m, int src) { return src < 32 ? (int)(m ? C1 : C0).w(src, 2) : (int)R.w(m, src - 32, 1); };
+	auto cand_votes = [&](int m, int src) { return src < 32 ? (int)(m ? C1 : C0).w(src, 2) : R.votes(m, src - 32); };
 
 	// ---- pairs (:2321-2372): the best max_vote_combinations by (score desc, visiting order asc) ----
 	uint32_t comb0 = 0, comb1 = 0, comb2 = 0;
@@ -339,7 +345,7 @@ __device__ __forceinline__ bool simple_pe_merge(const DevIndex &ix, const VoteCo
 						for (int i = 0; i < 4; i++) J[((m * kMaxBest + k) * 4 + i) * kSimpleThreads] = JT[(k * 4 + i) * kSimpleThreads];
 					}
 				} else {
-					R.w(m, k, 1) = 0u;
+					R.clear_votes(m, k);
 					if (JUNC) J[((m * kMaxBest + k) * 4) * kSimpleThreads] &= 0x0000ffffu;   // minor_votes = 0
 				}
 			}
@@ -483,6 +489,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 					r.meta = 1u | ((w1 & (uint32_t)kCoreNegStrand) ? 0x100u : 0u) | (first << 16) | (last << 24);
 					r.cov = o.w[15];
 				} else if ((w2 >> 16) & ~63u) punt = true;        // (a used_subreads value the packed slot cannot hold)
+				if (r.votes < 0 || !PeResults::fits(r)) { punt = true; r.votes = 0; r.cov = 0; }
 				R.put(m, k, r);
 			}
 	}
@@ -529,7 +536,7 @@ k_map_simple_pe(const DevIndex ix, const VoteConfig cfg, const uint8_t *text, ui
 #pragma unroll 1
 					for (int c = 0; c < C.n; c++) best = max(best, (int)C.w(c, 2));
 #pragma unroll 1
-					for (int k = 0; k < mb; k++) best = max(best, (int)R.w(m, k, 1));
+					for (int k = 0; k < mb; k++) best = max(best, R.votes(m, k));
 					const int least = max(1, best - cfg.max_vote_number_cutoff);
 					int kept = 0;
 #pragma unroll 1
