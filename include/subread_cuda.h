@@ -324,7 +324,12 @@ int srcuda_get_timing(const srcuda_handle *h, srcuda_timing *out);
  *   SRCUDA_PHASE [1]           the phase table of gapped indexes
  *   SRCUDA_WARP_JUNC [1]       subjunc fragments in the warp kernel (0: scalar path)
  *   SRCUDA_ACCEL [auto]        lookup accelerators: 0 none, 1 Bloom words, 2 bucket records, 3 both, 4 direct filter
- *   SRCUDA_BATCH_FRAGS, SRCUDA_SCALAR_BLOCKS, SRCUDA_L2_PERSIST, SRCUDA_L2_FETCH   tuning knobs */
+ *   SRCUDA_PE_CW3 [1]          paired-end tier on dense tables: three-word vote clusters for reads of at most 160 bases
+ *   SRCUDA_PE_POOL [auto]      ... its cluster pool per strand pass (both mates); SRCUDA_PE_PAD_SMEM: extra shared memory per block
+ *   SRCUDA_COMPACT_D2H [1]     host-buffer entry point, first index block: results cross PCIe compacted and are scattered into the
+ *                              caller's table by SRCUDA_EXPAND_THREADS [host threads / GPUs] host threads
+ *   SRCUDA_BATCH_FRAGS [auto]  fragments per batch of a chunk (default: at least eight batches, 256 Ki to 1 Mi reads each)
+ *   SRCUDA_SCALAR_BLOCKS, SRCUDA_L2_PERSIST, SRCUDA_L2_FETCH   tuning knobs */
 int srcuda_set_force_slow_path(srcuda_handle *h, int on);
 
 /* Measured random 32-byte-sector gather bandwidth over `table_bytes` of HBM (GB/s): the

@@ -434,6 +434,17 @@ def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
     finally:
         del os.environ["SRCUDA_SIMPLE_TIER_PE"]
     plain.index_load(prefix, 0)
+    alt = None
+    if kind == "dense_gapped":
+        # the other forms of the same tier: four-word clusters for every read length (the default takes three-word clusters for
+        # reads of at most 160 bases), a small cluster pool (more fragments queued), results copied down uncompacted
+        os.environ.update(SRCUDA_ACCEL="4", SRCUDA_PE_CW3="0", SRCUDA_PE_POOL="12", SRCUDA_COMPACT_D2H="0")
+        try:
+            alt = Mapper(0)
+        finally:
+            for k in ("SRCUDA_ACCEL", "SRCUDA_PE_CW3", "SRCUDA_PE_POOL", "SRCUDA_COMPACT_D2H"):
+                os.environ.pop(k, None)
+        alt.index_load(prefix, 0)
     idx = oracle_mod.OracleIndex(prefix)
     gen_data.write_reads(fa, str(tmp_path / "clean"), 30000, 150, 13, True, 0.0, 0.0, False, 0.0)
     gen_data.write_reads(fa, str(tmp_path / "noisy"), 20000, 100, 14, True, 0.01, 0.1, True, 0.002)
@@ -477,6 +488,9 @@ def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
             ref, _ = plain.vote_chunk(chunk, params)
             assert ref.tobytes() == ora.tobytes(), f"{name}/{vi} (tier off)"
             assert plain.timing().n_simple_punted == 0
+            if alt is not None:
+                other, _ = alt.vote_chunk(chunk, params)
+                assert other.tobytes() == ora.tobytes(), f"{name}/{vi} (four-word clusters, small pool, plain copy)"
             ora2, _, _ = oracle_mod.vote_chunk(idx, params, chunk, out_align=ora.copy(), threads=8)
             got2, _ = tier.vote_chunk(chunk, params, out_align=got.copy().reshape(-1))
             assert got2.tobytes() == ora2.tobytes(), f"{name}/{vi} (second pass)"
@@ -486,6 +500,8 @@ def test_tier0_paired_end_chunks_against_oracle(kind, oracle_mod, tmp_path):
                 assert t.n_simple_punted < chunk.n_frags // 10, f"tier 0 queued {t.n_simple_punted} of {chunk.n_frags} clean pairs"
     tier.close()
     plain.close()
+    if alt is not None:
+        alt.close()
 
 
 @pytest.mark.parametrize("paired", [False, True], ids=["se", "pe"])
