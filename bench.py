@@ -459,6 +459,29 @@ def main():
         res["crc"] = zlib.crc32(out[:K].tobytes())
         res["prefix_text"] = d_text[: K * mates * RL]
         res["K"] = K
+        # ---- K_verify (match_chro / gvindex_get on the packed genome), measured on a bounded sample: the same chunk
+        # prefix with per-slot matched-base counts requested -- the request takes every fragment through the warp kernel ----
+        res["verify"] = None
+        if rank == 0 and not subjunc and not args.no_e2e:
+            try:
+                V = min(R, 1_000_000)
+                d_ver = torch.zeros(V * mates * mb, dtype=torch.int16, device=dev)
+                v_out = torch.zeros(V * mates * mb * 68, dtype=torch.uint8, device=dev)
+                torch.cuda.synchronize()
+                ms = []
+                for i in range(3):
+                    m.vote_chunk_device(params, d_text.data_ptr(), d_text.numel(), d_off.data_ptr(), d_len.data_ptr(), V, paired, RL, v_out.data_ptr(),
+                                        d_verify=d_ver.data_ptr(), out_is_zero=True)
+                    ms.append(m.timing().ms_total)
+                ver = d_ver.cpu().numpy().reshape(V, mates, mb)
+                full = (ver[:, :, 0] == RL).all(1)                  # every base of the best candidate of a clean read matches the genome
+                same = bool((v_out.cpu().numpy() == d_out[: V * mates * mb * 68].cpu().numpy()).all())
+                res["verify"] = {"reads_per_s": V * mates / (min(ms[1:]) * 1e-3), "sample": "%d fragments of the same chunk, best of 2 timed launches" % V,
+                                 "kernel": "k_map_warp<..., VERIFY> (packed XOR + popc over the 2-bit genome, 32-bit loads)",
+                                 "clean_reads_fully_matched": float(full[cl[:V]].mean()) if cl[:V].any() else None, "bigtable_same_as_unverified": same}
+                del d_ver, v_out
+            except Exception as e:      # a measurement, not a gate
+                res["verify"] = {"error": repr(e)}
         # ---- end to end through the host-buffer entry point ----
         if want_e2e:
             h_text = PinnedArray(nr * RL, np.uint8)
@@ -480,7 +503,7 @@ def main():
                 m._check(rc, "srcuda_vote_chunk")
                 return m.timing()
 
-            for _ in range(max(1, warmup // 2)):
+            for _ in range(max(2, warmup)):
                 step_e2e()
             # the caller's table of a chunk's first index block is all zero (the reference clears it per chunk, core-bigtable.c:96); the
             # timed steps then write the same records over each other
@@ -659,7 +682,7 @@ def main():
                      "ms_per_step_wall": res["e2e_wall_ms"], "ms_per_step_events": res["e2e_ev_ms"], "matches_device_result": res["e2e_same"]}
                     if "e2e_wall_ms" in res else None),
             "gpu_launches": int(res["launches"] + res.get("e2e_launches", 0) * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "whole_program": whole, "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "whole_program": whole, "verify": res.get("verify"), "clocks": clk,
             "mapped_fraction": res["mapped"], "clean_fraction": res["clean_fraction"], "slot0_is_true_position": res["slot0_true"],
             "ranks": rank_rows, "sweep": sweep_rows,
             "index_replication_s": t_rep if world > 1 else None,

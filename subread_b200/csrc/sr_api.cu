@@ -499,6 +499,10 @@ constexpr int kSets = 4;
 struct srcuda_handle {
 	int device = -1;
 	int sm_count = 0;
+	// The kernels' dynamic shared memory limit is a property of the function on the device, not of a handle: every handle raises it to
+	// the device's opt-in maximum (never to the size of its own launch -- a second handle with shorter reads or a smaller pool would
+	// lower it under the first one's feet); the bytes a launch asks for still decide how many blocks fit an SM.
+	int smem_optin = 227 * 1024;
 	mutable std::mutex mu;
 	std::string err;
 	bool has_index = false;
@@ -783,7 +787,7 @@ int plan_warp_launch(srcuda_handle *h, int max_len, LaunchPlan *p)
 	p->warp_bytes = (int)((wb + 15) & ~size_t(15));
 	p->smem_bytes = 256 + p->warp_bytes * sr::kWarpsPerBlock;
 	if (p->smem_bytes > 227 * 1024) return fail(h, SRCUDA_ERR_UNSUPPORTED, "shared memory plan %d B exceeds 227 KB", p->smem_bytes);
-	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES, GAP, VERIFY, JUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+	CU(h, cudaFuncSetAttribute(sr::k_map_warp<MATES, GAP, VERIFY, JUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
 	int per_sm = 0;
 	CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sr::k_map_warp<MATES, GAP, VERIFY, JUNC>, sr::kWarpsPerBlock * 32, p->smem_bytes));
 	if (per_sm < 1) return fail(h, SRCUDA_ERR_CUDA, "warp kernel does not fit on an SM");
@@ -854,7 +858,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_SIMPLE_U(G, U)                                                                                                     \
 	do {                                                                                                                             \
 		if (smem > h->simple_smem_set[G][U]) {                                                                                       \
-			CU(h, cudaFuncSetAttribute(sr::k_map_simple<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
+			CU(h, cudaFuncSetAttribute(sr::k_map_simple<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));                   \
 			h->simple_smem_set[G][U] = smem;                                                                                         \
 		}                                                                                                                            \
 		sr::k_map_simple<G, U><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off,    \
@@ -864,7 +868,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_SIMPLE_R(G, U)                                                                                                     \
 	do {                                                                                                                             \
 		if (smem > h->simple_rmw_smem_set[G][U]) {                                                                                   \
-			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));    \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin)));    \
 			h->simple_rmw_smem_set[G][U] = smem;                                                                                     \
 		}                                                                                                                            \
 		sr::k_map_simple<G, U, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,              \
@@ -875,7 +879,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_SIMPLE_UI(G, U)                                                                                                    \
 	do {                                                                                                                             \
 		if (smem > h->simple_indel_smem_set[G][U]) {                                                                                 \
-			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin))); \
 			h->simple_indel_smem_set[G][U] = smem;                                                                                   \
 		}                                                                                                                            \
 		sr::k_map_simple<G, U, false, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,        \
@@ -886,7 +890,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_SIMPLE_RI(G, U)                                                                                                    \
 	do {                                                                                                                             \
 		if (smem > h->simple_rmw_indel_smem_set[G][U]) {                                                                             \
-			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin))); \
 			h->simple_rmw_indel_smem_set[G][U] = smem;                                                                               \
 		}                                                                                                                            \
 		sr::k_map_simple<G, U, false, true, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,         \
@@ -898,7 +902,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 	do {                                                                                                                             \
 		const int jsmem = sr::simple_junc_smem_bytes(max_len, clusters);                                                              \
 		if (jsmem > h->simple_junc_smem_set[G][U]) {                                                                                 \
-			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, jsmem)));          \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple<G, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin)));          \
 			h->simple_junc_smem_set[G][U] = jsmem;                                                                                   \
 		}                                                                                                                            \
 		sr::k_map_simple<G, U, true><<<(unsigned)blocks, threads, jsmem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes,    \
@@ -960,7 +964,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_PE_U(G, U)                                                                                                         \
 	do {                                                                                                                             \
 		if (smem > h->simple_pe_smem_set[G][U]) {                                                                                    \
-			CU(h, cudaFuncSetAttribute(sr::k_map_simple_pe<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                \
+			CU(h, cudaFuncSetAttribute(sr::k_map_simple_pe<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));                \
 			h->simple_pe_smem_set[G][U] = smem;                                                                                      \
 		}                                                                                                                            \
 		sr::k_map_simple_pe<G, U><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes, a.off, \
@@ -970,7 +974,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_PE_R(G, U)                                                                                                         \
 	do {                                                                                                                             \
 		if (smem > h->simple_pe_rmw_smem_set[G][U]) {                                                                                \
-			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<G, U, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<G, U, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin))); \
 			h->simple_pe_rmw_smem_set[G][U] = smem;                                                                                  \
 		}                                                                                                                            \
 		sr::k_map_simple_pe<G, U, false, true><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,           \
@@ -981,7 +985,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_PE_3(RMW_, SET_)                                                                                                   \
 	do {                                                                                                                             \
 		if (smem > h->simple_pe_cw3_smem_set[SET_]) {                                                                                \
-			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<3, 4, false, RMW_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))); \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<3, 4, false, RMW_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin))); \
 			h->simple_pe_cw3_smem_set[SET_] = smem;                                                                                  \
 		}                                                                                                                            \
 		sr::k_map_simple_pe<3, 4, false, RMW_, 3><<<(unsigned)blocks, threads, smem, s>>>(h->ix, cfg, a.text, a.text_origin,         \
@@ -992,7 +996,7 @@ int launch_vote(srcuda_handle *h, cudaStream_t s, const sr::VoteConfig &cfg, con
 #define SR_LAUNCH_PE_J(G, U)                                                                                                         \
 	do {                                                                                                                             \
 		if (jsmem > h->simple_pe_junc_smem_set[G][U]) {                                                                              \
-			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<G, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, jsmem)));       \
+			CU(h, (cudaFuncSetAttribute(sr::k_map_simple_pe<G, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin)));       \
 			h->simple_pe_junc_smem_set[G][U] = jsmem;                                                                                \
 		}                                                                                                                            \
 		sr::k_map_simple_pe<G, U, true><<<(unsigned)blocks, threads, jsmem, s>>>(h->ix, cfg, a.text, a.text_origin, a.text_bytes,  \
@@ -1129,6 +1133,7 @@ int srcuda_open(int device, srcuda_handle **out)
 	srcuda_handle *h = new srcuda_handle();
 	h->device = device;
 	h->sm_count = prop.multiProcessorCount;
+	if (prop.sharedMemPerBlockOptin > 0) h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 	h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
 	h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
 	const char *lp = getenv("SRCUDA_L2_PERSIST");
@@ -1146,9 +1151,14 @@ int srcuda_open(int device, srcuda_handle **out)
 	if (ph && ph[0] == '0') h->use_phase = false;
 	const char *cd = getenv("SRCUDA_COMPACT_D2H");
 	if (cd && cd[0] == '0') h->compact_d2h = false;
+	const bool compact_forced = cd && cd[0] == '1';
 	const char *et = getenv("SRCUDA_EXPAND_THREADS");
 	h->expand_threads = et && atoi(et) > 0 ? atoi(et) : (int)std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, n));
 	if (h->expand_threads > 64) h->expand_threads = 64;
+	// measured on the bench box: with 16 scatter threads the compacted copy wins (cfg2_se end to end 239 vs 221-229 M reads/s), with 8 it
+	// loses (211) -- the scatter then is slower than the DMA engine writing the whole table -- so a process that shares the host with
+	// seven others (one per GPU, 4 threads each) keeps the plain copy unless SRCUDA_COMPACT_D2H=1 asks for it
+	if (h->expand_threads < 12 && !compact_forced) h->compact_d2h = false;
 	const char *ti = getenv("SRCUDA_TIER_INDEL");
 	if (ti && (ti[0] == '0' || ti[0] == '1')) { h->tier_indel_mode = ti[0] - '0'; h->tier_indel = ti[0] == '1'; }
 	const char *tr = getenv("SRCUDA_TIER_RMW");

@@ -94,6 +94,32 @@ def test_many_small_batches_and_ragged_input(golden_cases, golden_index_dir, ora
     m.close()
 
 
+@pytest.mark.parametrize("compact", ["1", "0"], ids=["compacted", "plain"])
+def test_result_copy_forms_agree(compact, golden_cases, golden_index_dir):
+    """The host-buffer entry point brings a zero table's results down either whole or compacted (k_compact_results: 24-byte records of
+    plain slots, 72-byte records of the others -- the golden cases hold reads with indels -- scattered by host threads behind a
+    follower thread).  Forced either way, over several batches, with few scatter threads: the golden bigtables, byte for byte;
+    the compacted form moves fewer bytes."""
+    from subread_b200.binding import Mapper
+    os.environ.update(SRCUDA_BATCH_FRAGS="300", SRCUDA_COMPACT_D2H=compact, SRCUDA_EXPAND_THREADS="3")
+    try:
+        m = Mapper(0)
+    finally:
+        for k in ("SRCUDA_BATCH_FRAGS", "SRCUDA_COMPACT_D2H", "SRCUDA_EXPAND_THREADS"):
+            del os.environ[k]
+    for name in ("se_gapped", "pe_gapped"):
+        case = next(c for c in golden_cases if c["name"] == name)
+        prefix, chunk, params, exp = load_case(case, golden_index_dir)
+        m.index_load(prefix, 0)
+        got, _ = m.vote_chunk(chunk, params)
+        assert got.tobytes() == exp.tobytes(), name
+        t = m.timing()
+        whole = chunk.n_frags * chunk.mates * params.multi_best_reads * 68
+        assert t.n_batches == (chunk.n_frags + 299) // 300
+        assert (0 < t.d2h_bytes < whole) if compact == "1" else t.d2h_bytes >= whole, (name, t.d2h_bytes, whole)
+    m.close()
+
+
 def test_read_modify_write_merges_like_the_oracle(mapper, golden_cases, golden_index_dir, oracle_mod):
     """Second pass over the same block with the first pass's table as input (multi-block merge path)."""
     for name in ("se_gapped", "pe_gapped"):
