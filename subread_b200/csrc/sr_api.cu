@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -496,6 +497,69 @@ struct BatchSet {  // one of two buffer sets; used by one stream
 // with k sets up to k batches are in different stages at once (PCIe up, SMs, PCIe down all busy).
 constexpr int kSets = 4;
 
+// Host threads that scatter compacted result records into the caller's table (srcuda_vote_chunk): started once per handle and kept --
+// starting fifteen threads per batch cost as much as the scatter of a small batch.  run(n_parts, fn) executes fn(0 .. n_parts-1) on
+// the workers and the calling thread and returns when all parts are done.
+struct ScatterPool {
+	std::vector<std::thread> workers;
+	std::mutex mu;
+	std::condition_variable cv_job, cv_done;
+	std::function<void(int)> job;
+	int n_parts = 0, next_part = 0, running = 0;
+	uint64_t generation = 0;
+	bool quit = false;
+	void worker()
+	{
+		uint64_t seen = 0;
+		std::unique_lock<std::mutex> lk(mu);
+		for (;;) {
+			cv_job.wait(lk, [&] { return quit || generation != seen; });
+			if (quit) return;
+			seen = generation;
+			while (next_part < n_parts) {
+				const int t = next_part++;
+				running++;
+				lk.unlock();
+				job(t);
+				lk.lock();
+				running--;
+			}
+			if (running == 0) cv_done.notify_all();
+		}
+	}
+	void ensure(int n_workers)
+	{
+		while ((int)workers.size() < n_workers) {
+			try { workers.emplace_back([this] { worker(); }); } catch (...) { break; }   // fewer workers: the caller takes the parts left
+		}
+	}
+	void run(int parts, const std::function<void(int)> &fn)
+	{
+		std::unique_lock<std::mutex> lk(mu);
+		job = fn; n_parts = parts; next_part = 0;
+		generation++;
+		cv_job.notify_all();
+		while (next_part < n_parts) {            // the caller works too
+			const int t = next_part++;
+			running++;
+			lk.unlock();
+			fn(t);
+			lk.lock();
+			running--;
+		}
+		cv_done.wait(lk, [&] { return running == 0 && next_part >= n_parts; });
+	}
+	~ScatterPool()
+	{
+		{
+			std::lock_guard<std::mutex> g(mu);
+			quit = true;
+		}
+		cv_job.notify_all();
+		for (auto &t : workers) t.join();
+	}
+};
+
 struct srcuda_handle {
 	int device = -1;
 	int sm_count = 0;
@@ -518,6 +582,7 @@ struct srcuda_handle {
 	// that scatter runs at 380 M records/s, the DMA engine writes the full table at 250-270 M reads/s (profiles/r02_host_expand.txt).
 	bool compact_d2h = true;       // SRCUDA_COMPACT_D2H=0: always the plain copy
 	int expand_threads = 0;        // SRCUDA_EXPAND_THREADS; default: host threads / visible GPUs
+	ScatterPool *scatter = nullptr;
 	int tier_indel_mode = -1;      // SRCUDA_TIER_INDEL: 0 never, 1 always, unset: by the last call
 	bool tier_indel = false;
 	int simple_indel_smem_set[4][5] = {}, simple_rmw_indel_smem_set[4][5] = {};
@@ -1185,6 +1250,8 @@ int srcuda_open(int device, srcuda_handle **out)
 void srcuda_close(srcuda_handle *h)
 {
 	if (!h) return;
+	delete h->scatter;
+	h->scatter = nullptr;
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
 	free_index(h);
@@ -1544,14 +1611,10 @@ int srcuda_vote_chunk(srcuda_handle *h, const srcuda_params *params, const char 
 				memcpy(dst + r[0], r + 1, sizeof(srcuda_mapping_result));
 			}
 		};
-		std::vector<std::thread> th;
-		for (int t = 1; t < T; t++) {
-			bool started = false;
-			try { th.emplace_back(part, t); started = true; } catch (...) {}
-			if (!started) part(t);
-		}
-		part(0);
-		for (auto &x : th) x.join();
+		if (T == 1) { part(0); return; }
+		if (!h->scatter) h->scatter = new ScatterPool();
+		h->scatter->ensure(h->expand_threads - 1);
+		h->scatter->run(T, part);
 	};
 	auto follower = [&]() {
 		cudaSetDevice(h->device);
