@@ -34,7 +34,7 @@ regions("sr_simple.cuh", [("cluster accessors", "struct SimpleCluster {"), ("sim
     ("offsets / keys", "// Offset of the first lookup of subread s"), ("(sparse-table code)", "// What one survivor's bucket record says"),
     ("dense: setup", "bool simple_pass_phase_dense("), ("dense: hit()", "auto hit = [&](uint32_t kv, int l, int u, int sub) -> bool {"),
     ("dense: batch setup, issue", "		const int n_sub = min(kSubs, applied - s_base), base = s_base * GAP;\n"), ("dense: unit loop head", "			const Record8 r = rn;"),
-    ("dense: (a) what the unit says", "			uint32_t val[3];"), ("dense: (b) ask for entries", "				if (st[x] == 2) { prefetch_l2"), ("dense: (c) apply singles", "				if (st[x] == 1) { if (!hit(val[x]"),
+    ("dense: look (stage 2)", "		auto look = [&]"), ("dense: apply (stage 3)", "		auto apply = [&]"), ("dense: pipelined loop", "		issue(0);"),
     ("dense: read entries", "		if (ok && ne) {"), ("dense: slow lookups + runs", "		// the keys with several positions: one flat loop"), ("rest of sr_simple.cuh", "// Asks for the dense units of subreads")])
 regions("sr_simple_pe.cuh", [("pe merge", "__device__ __forceinline__ bool simple_pe_merge("), ("pe kernel: stage + pack", "k_map_simple_pe(const DevIndex ix"), ("pe kernel: passes", "	// ---- 2. four passes"), ("pe kernel: output", "	// ---- 3. the warp's bigtable slice")])
 regions("sr_common.cuh", [("sr_common.cuh", "#pragma once")])
