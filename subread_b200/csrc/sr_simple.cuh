@@ -864,9 +864,24 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 		// average instead of once per role
 		auto apply = [&](int si, const uint32_t (&val)[3], int st) {
 			const int sub = s_base + si, ob = simple_sub_offset<GAP>(sub, step);
-#pragma unroll
-			for (int x = 0; x < 3; x++)
-				if (((st >> (2 * x)) & 3) == 2) { prefetch_l2(ix.direct_first + val[x]); n_gather++; }
+			// keys with several positions (one unit in four holds one): ONE copy of the stash code, looped over the roles that have
+			// one -- the entry is asked for here and read behind the subread loop
+			int multi = ((st >> 1) & 1 & ~st) | ((st >> 2) & 2 & ~(st >> 1)) | ((st >> 3) & 4 & ~(st >> 2));   // bit x: role x holds code 2
+#pragma unroll 1
+			while (multi) {
+				const int x = __ffs(multi) - 1;
+				multi &= multi - 1;
+				const uint32_t v = x == 0 ? val[0] : (x == 1 ? val[1] : val[2]);
+				prefetch_l2(ix.direct_first + v);
+				n_gather++;
+				const int li = 3 * si + x;
+				const uint32_t me = (uint32_t)(base + li) << 16;
+				if (ne == 0) { ra0 = v; me0 = me; ne = 1; }
+				else if (ne == 1) { ra1 = v; me1 = me; ne = 2; }
+				else if (ne == 2) { ra2 = v; me2 = me; ne = 3; }
+				else if (ne == 3) { ra3 = v; me3 = me; ne = 4; }
+				else slow |= 1u << li;
+			}
 			uint32_t h0 = 0, h1 = 0, h2 = 0;
 			int hx = 0, nh = 0;                                          // roles, two bits each
 #pragma unroll
@@ -882,17 +897,6 @@ __device__ __forceinline__ bool simple_pass_phase_dense(const DevIndex &ix, cons
 				const uint32_t kvj = j == 0 ? h0 : (j == 1 ? h1 : h2);
 				if (!hit(kvj, base + 3 * si + ((hx >> (2 * j)) & 3), 0, sub)) { ok = false; break; }
 			}
-#pragma unroll
-			for (int x = 0; x < 3; x++)
-				if (((st >> (2 * x)) & 3) == 2) {                            // rank of its direct_first entry; read behind the loop
-					const int li = 3 * si + x;
-					const uint32_t me = (uint32_t)(base + li) << 16;
-					if (ne == 0) { ra0 = val[x]; me0 = me; ne = 1; }
-					else if (ne == 1) { ra1 = val[x]; me1 = me; ne = 2; }
-					else if (ne == 2) { ra2 = val[x]; me2 = me; ne = 3; }
-					else if (ne == 3) { ra3 = val[x]; me3 = me; ne = 4; }
-					else slow |= 1u << li;
-				}
 		};
 		issue(0);
 #if SR_DENSE_PIPE
