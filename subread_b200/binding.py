@@ -25,6 +25,10 @@ EXPORTS = [
     "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth", "srcuda_measure_lookup_roofline",
     "srcuda_fastq_split", "srcuda_fastq_split_mt", "srcuda_reads_pack", "srcuda_reads_pack_mt",
     "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_skip", "srcuda_reader_tell", "srcuda_reader_error", "srcuda_reader_close",
+    # include/subread_output.h (row f2)
+    "srcuda_out_open", "srcuda_out_add_header", "srcuda_out_add_chromosome", "srcuda_out_finish_header", "srcuda_out_add_read",
+    "srcuda_out_add_reads", "srcuda_out_add_sam_lines", "srcuda_out_add_fragment", "srcuda_out_flush", "srcuda_out_close",
+    "srcuda_out_error", "srcuda_sam_calc_flags", "srcuda_sam_calc_tlen",
 ]
 
 
@@ -45,6 +49,36 @@ class FastqBatch(ctypes.Structure):
 
 
 FASTQ_MORE, FASTQ_FULL, FASTQ_END = 0, 1, 2
+
+
+class SamRecord(ctypes.Structure):
+    """srcuda_sam_record (include/subread_output.h)."""
+    _fields_ = [("name", ctypes.c_char_p), ("flags", ctypes.c_uint32), ("chro", ctypes.c_char_p), ("pos", ctypes.c_uint32),
+                ("mapping_quality", ctypes.c_int32), ("cigar", ctypes.c_char_p), ("next_chro", ctypes.c_char_p),
+                ("next_pos", ctypes.c_uint32), ("tlen", ctypes.c_int64), ("read_len", ctypes.c_int32), ("seq", ctypes.c_char_p),
+                ("qual", ctypes.c_char_p), ("additional", ctypes.c_char_p)]
+
+
+class SamConfig(ctypes.Structure):
+    """srcuda_sam_config."""
+    _fields_ = [("is_paired_end", ctypes.c_int32), ("minimum_pair_distance", ctypes.c_int32), ("maximum_pair_distance", ctypes.c_int32),
+                ("is_first_read_reversed", ctypes.c_int32), ("is_second_read_reversed", ctypes.c_int32), ("_pad", ctypes.c_int32),
+                ("read_group_id", ctypes.c_char_p)]
+
+
+class SamMate(ctypes.Structure):
+    """srcuda_sam_mate."""
+    _fields_ = [("present", ctypes.c_int32), ("ok", ctypes.c_int32), ("chro_id", ctypes.c_int32), ("offset", ctypes.c_int32),
+                ("strand", ctypes.c_int32), ("mapping_quality", ctypes.c_int32), ("mismatched_bases", ctypes.c_int32),
+                ("read_len", ctypes.c_int32), ("cigar", ctypes.c_char_p), ("additional", ctypes.c_char_p),
+                ("name", ctypes.c_void_p), ("text", ctypes.c_void_p), ("qual", ctypes.c_void_p)]
+
+
+class SamCounters(ctypes.Structure):
+    """srcuda_sam_counters."""
+    _fields_ = [(n, ctypes.c_uint64) for n in ("all_mapped_reads", "all_correct_PE_reads", "not_properly_pairs_different_chro",
+                                               "not_properly_different_strands", "not_properly_pairs_TLEN_wrong",
+                                               "not_properly_pairs_wrong_arrangement")]
 
 
 class Timing(ctypes.Structure):
@@ -116,6 +150,23 @@ def load_library():
     L.srcuda_reader_error.restype = ctypes.c_char_p
     L.srcuda_reader_close.argtypes = [vp]
     L.srcuda_reader_close.restype = None
+    cp = ctypes.c_char_p
+    L.srcuda_out_open.argtypes = [cp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    L.srcuda_out_add_header.argtypes = [vp, cp, ctypes.c_int]
+    L.srcuda_out_add_chromosome.argtypes = [vp, cp, u32, ctypes.c_int]
+    L.srcuda_out_finish_header.argtypes = [vp]
+    L.srcuda_out_add_read.argtypes = [vp, ctypes.POINTER(SamRecord), ctypes.c_int]
+    L.srcuda_out_add_reads.argtypes = [vp, ctypes.POINTER(SamRecord), i64, ctypes.c_int]
+    L.srcuda_out_add_sam_lines.argtypes = [vp, cp, ctypes.c_size_t, ctypes.c_int]
+    L.srcuda_out_add_fragment.argtypes = [vp, ctypes.POINTER(SamConfig), ctypes.POINTER(SamMate), ctypes.POINTER(SamMate),
+                                          ctypes.c_int, ctypes.c_int, ctypes.POINTER(SamCounters)]
+    L.srcuda_out_flush.argtypes = [vp]
+    L.srcuda_out_close.argtypes = [vp, ctypes.POINTER(u64)]
+    L.srcuda_out_error.argtypes = [vp]
+    L.srcuda_out_error.restype = cp
+    L.srcuda_sam_calc_flags.argtypes = [ctypes.POINTER(SamConfig), ctypes.POINTER(SamMate), ctypes.POINTER(SamMate), ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.POINTER(SamCounters)]
+    L.srcuda_sam_calc_tlen.argtypes = [i32, cp, ctypes.c_int, i32, cp, ctypes.c_int]
     _LIB = L
     return L
 
@@ -443,3 +494,58 @@ class ChunkReader:
             self.close()
         except Exception:
             pass
+
+
+OUT_SAM, OUT_BAM = 0, 1
+
+
+class OutputWriter:
+    """ctypes mirror of the srcuda_out_* writer (include/subread_output.h): SAM text or BAM, host side only."""
+
+    def __init__(self, path, fmt=OUT_BAM, threads=1, no_compression=False):
+        self.L = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.L.srcuda_out_open(os.fsencode(path) if path is not None else None, fmt, threads, int(no_compression), ctypes.byref(self.h))
+        if rc:
+            raise SubreadCudaError(f"srcuda_out_open: {self.L.srcuda_out_error(None).decode()} (code {rc})")
+
+    def _check(self, rc, what):
+        if rc:
+            raise SubreadCudaError(f"{what}: {self.L.srcuda_out_error(self.h).decode()} (code {rc})")
+
+    def add_header(self, line, add_chro=False):
+        self._check(self.L.srcuda_out_add_header(self.h, line.encode() if isinstance(line, str) else line, int(add_chro)), "add_header")
+
+    def add_chromosome(self, name, length, add_header=True):
+        self._check(self.L.srcuda_out_add_chromosome(self.h, name.encode() if isinstance(name, str) else name, length, int(add_header)), "add_chromosome")
+
+    def finish_header(self):
+        self._check(self.L.srcuda_out_finish_header(self.h), "finish_header")
+
+    def add_read(self, rec: SamRecord, committable=True):
+        self._check(self.L.srcuda_out_add_read(self.h, ctypes.byref(rec), int(committable)), "add_read")
+
+    def add_reads(self, recs, records_per_fragment=1):
+        arr = (SamRecord * len(recs))(*recs)
+        self._check(self.L.srcuda_out_add_reads(self.h, arr, len(recs), records_per_fragment), "add_reads")
+
+    def add_sam_lines(self, text: bytes, records_per_fragment=1):
+        self._check(self.L.srcuda_out_add_sam_lines(self.h, text, len(text), records_per_fragment), "add_sam_lines")
+
+    def add_fragment(self, cfg: SamConfig, m1: SamMate, m2, all_locations=1, current_location=0, counters=None):
+        self._check(self.L.srcuda_out_add_fragment(self.h, ctypes.byref(cfg), ctypes.byref(m1), ctypes.byref(m2) if m2 is not None else None,
+                                                   all_locations, current_location, ctypes.byref(counters) if counters is not None else None),
+                    "add_fragment")
+
+    def flush(self):
+        self._check(self.L.srcuda_out_flush(self.h), "flush")
+
+    def close(self):
+        if self.h:
+            n = ctypes.c_uint64()
+            h, self.h = self.h, None
+            rc = self.L.srcuda_out_close(h, ctypes.byref(n))
+            if rc:
+                raise SubreadCudaError(f"srcuda_out_close: {self.L.srcuda_out_error(None).decode()} (code {rc})")
+            return n.value
+        return 0

@@ -21,7 +21,7 @@ def lib():
 
 
 def declared_functions():
-    src = open(os.path.join(ROOT, "include", "subread_cuda.h")).read()
+    src = "".join(open(os.path.join(ROOT, "include", f)).read() for f in sorted(os.listdir(os.path.join(ROOT, "include"))) if f.endswith(".h"))
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(srcuda_[a-z_]+)\s*\(", src)))
 

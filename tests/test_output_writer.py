@@ -1,0 +1,290 @@
+"""Row f2 (SAM / BAM writer, include/subread_output.h) against the UNMODIFIED reference's writer.
+
+Record level: the same records go through the reference's SamBam_writer_* (libsubread_ref.so, single stream = thread_no -1,
+sambam-file.c:1097-1797) and through srcuda_out_*; the two BAM files must be equal byte for byte, compressed blocks included,
+whatever the number of deflate threads.  CPU only; skipped where oracle/_ref has not been built."""
+import ctypes
+import gzip
+import os
+import random
+import zlib
+
+import pytest
+
+from conftest import REF_DIR, have_ref
+from subread_b200 import binding
+from subread_b200.binding import OUT_BAM, OUT_SAM, OutputWriter, SamRecord
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference binaries) not built")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    L = ctypes.CDLL(os.path.join(REF_DIR, "libsubread_ref.so"))
+    cp, vp, ci, cu = ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint
+    L.SamBam_writer_create.argtypes = [vp, cp, ci, ci, ci, cp]
+    L.SamBam_writer_add_header.argtypes = [vp, cp, ci]
+    L.SamBam_writer_add_chromosome.argtypes = [vp, cp, cu, ci]
+    L.SamBam_writer_finish_header.argtypes = [vp]
+    L.SamBam_writer_add_read.argtypes = [vp, ci, cp, cu, cp, cu, ci, cp, cp, cu, ci, ci, cp, cp, cp, ci]
+    L.SamBam_writer_close.argtypes = [vp]
+    return L
+
+
+def bgzf_payload(path):
+    """Concatenated uncompressed payload of a BGZF file and the list of its block sizes."""
+    raw = open(path, "rb").read()
+    out, sizes, at = [], [], 0
+    while at < len(raw):
+        assert raw[at:at + 4] == b"\x1f\x8b\x08\x04"
+        bsize = int.from_bytes(raw[at + 16:at + 18], "little") + 1
+        data = zlib.decompress(raw[at + 18:at + bsize - 8], -15)
+        assert zlib.crc32(data) == int.from_bytes(raw[at + bsize - 8:at + bsize - 4], "little")
+        out.append(data)
+        sizes.append(len(data))
+        at += bsize
+    return b"".join(out), sizes
+
+
+def random_cigar(rng, read_len):
+    if rng.random() < 0.5:
+        return f"{read_len}M"
+    left = rng.randrange(1, read_len - 1)
+    kind = rng.choice("IDNS")
+    if kind == "S":
+        return f"{left}S{read_len - left}M"
+    if kind == "I":
+        ins = rng.randrange(1, min(6, read_len - left))
+        return f"{left}M{ins}I{read_len - left - ins}M"
+    return f"{left}M{rng.randrange(1, 5000)}{kind}{read_len - left}M"
+
+
+def random_columns(rng):
+    cols = [f"HI:i:{rng.randrange(1, 4)}", f"NH:i:{rng.randrange(1, 4)}"]
+    if rng.random() < 0.3:
+        cols.append("RG:Z:" + "".join(rng.choice("abcXYZ019._-") for _ in range(rng.randrange(1, 12))))
+    if rng.random() < 0.3:
+        cols.append("XS:A:" + rng.choice("+-"))
+    if rng.random() < 0.2:
+        cols.append(f"XF:f:{rng.random() * 100:.3f}")
+    if rng.random() < 0.2:
+        cols.append("XB:B:i," + ",".join(str(rng.randrange(-500, 500)) for _ in range(rng.randrange(1, 6))))
+    if rng.random() < 0.1:
+        cols.append("XG:B:f," + ",".join(f"{rng.random():.2f}" for _ in range(rng.randrange(1, 4))))
+    if rng.random() < 0.05:
+        cols.append("XL:Z:" + "Q" * rng.randrange(700, 900))          # runs into the reference's 780 / 750 byte marks
+    cols.append(f"NM:i:{rng.randrange(0, 9)}")
+    text = "\t".join(cols)
+    if rng.random() < 0.1:
+        text = "\t" + text                                              # a leading tab, as write_single_fragment can produce
+    return text
+
+
+def make_records(seed, n, chromosomes, paired):
+    rng = random.Random(seed)
+    recs = []
+    for i in range(n):
+        L = rng.choice([36, 75, 100, 101, 150, 151, 250])
+        name = f"read{seed}_{i}" + ("x" * rng.randrange(0, 30))
+        seq = "".join(rng.choice("ACGTACGTACGTN" + ("RYKMacgtn" if rng.random() < 0.05 else "")) for _ in range(L))
+        qual = "".join(chr(33 + rng.randrange(0, 42)) for _ in range(L))
+        mapped = rng.random() < 0.9
+        if mapped:
+            chro, clen = rng.choice(chromosomes)
+            pos = rng.randrange(1, clen)
+            cigar = random_cigar(rng, L)
+            cols = random_columns(rng)
+        else:
+            chro, pos, cigar, cols = "*", 0, "*", ("" if rng.random() < 0.5 else "RG:Z:grp")
+        flags = rng.randrange(0, 1 << 11)
+        if paired:
+            nxt = rng.choice(["=", "*", rng.choice(chromosomes)[0]])
+            npos = rng.randrange(0, 1 << 28)
+            tlen = rng.randrange(-100000, 100000)
+        else:
+            nxt, npos, tlen = "*", 0, 0
+        if rng.random() < 0.02:
+            chro = "not_in_the_table"                                    # refID -1 in both writers
+        recs.append(dict(name=name, flags=flags, chro=chro, pos=pos, mapq=rng.randrange(0, 60), cigar=cigar, next_chro=nxt, next_pos=npos,
+                         tlen=tlen, read_len=L, seq=seq, qual=qual, additional=cols))
+    return recs
+
+
+def write_with_reference(ref, path, header_lines, chromosomes, recs, paired):
+    w = ctypes.create_string_buffer(1 << 20)                            # SamBam_Writer (sambam-file.h:110-149), a few KB
+    assert ref.SamBam_writer_create(w, os.fsencode(path), 1, 0, 0, b"") == 0
+    for line in header_lines:
+        ref.SamBam_writer_add_header(w, ctypes.create_string_buffer(line.encode()), 0)   # the reference tokenises the line in place
+    for name, length in chromosomes:
+        ref.SamBam_writer_add_chromosome(w, name.encode(), length, 1)
+    ref.SamBam_writer_finish_header(w)
+    for i, r in enumerate(recs):
+        committable = (not paired) or (i & 1)
+        ref.SamBam_writer_add_read(w, -1, r["name"].encode(), r["flags"], r["chro"].encode(), r["pos"], r["mapq"], r["cigar"].encode(),
+                                   r["next_chro"].encode(), r["next_pos"], r["tlen"], r["read_len"], r["seq"].encode(), r["qual"].encode(),
+                                   r["additional"].encode(), int(committable))
+    ref.SamBam_writer_close(w)
+
+
+def to_struct(r):
+    return SamRecord(r["name"].encode(), r["flags"], r["chro"].encode(), r["pos"], r["mapq"], r["cigar"].encode(), r["next_chro"].encode(),
+                     r["next_pos"], r["tlen"], r["read_len"], r["seq"].encode(), r["qual"].encode(), r["additional"].encode())
+
+
+def write_native(path, fmt, header_lines, chromosomes, recs, paired, threads, batch=False):
+    w = OutputWriter(path, fmt, threads)
+    for line in header_lines:
+        w.add_header(line)
+    for name, length in chromosomes:
+        w.add_chromosome(name, length, True)
+    w.finish_header()
+    if batch:
+        w.add_reads([to_struct(r) for r in recs], 2 if paired else 1)
+    else:
+        for i, r in enumerate(recs):
+            w.add_read(to_struct(r), (not paired) or bool(i & 1))
+    return w.close()
+
+
+CHROMS = [("chr1", 248956422), ("chr2", 242193529), ("chrX", 156040895), ("scaffold_with_a_long_name.1", 5000), ("chrM", 16569)]
+
+
+@pytest.mark.parametrize("paired", [False, True])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_bam_bytes_equal_reference_writer(ref, tmp_path, paired, threads):
+    recs = make_records(11 + paired, 6000, CHROMS, paired)
+    header = ["@HD\tVN:1.0\tSO:unsorted"]
+    tail = ["@PG\tID:subread\tPN:subread\tVN:2.0.6\tCL:\"subread-align\" \"-i\" \"idx\""]
+    a, b = str(tmp_path / "ref.bam"), str(tmp_path / "native.bam")
+    # the reference writes @HD, the @SQ lines, then @PG (core.c:3850-3870)
+    w = ctypes.create_string_buffer(1 << 20)
+    assert ref.SamBam_writer_create(w, os.fsencode(a), 1, 0, 0, b"") == 0
+    ref.SamBam_writer_add_header(w, ctypes.create_string_buffer(header[0].encode()), 0)
+    for name, length in CHROMS:
+        ref.SamBam_writer_add_chromosome(w, name.encode(), length, 1)
+    ref.SamBam_writer_add_header(w, ctypes.create_string_buffer(tail[0].encode()), 0)
+    ref.SamBam_writer_finish_header(w)
+    for i, r in enumerate(recs):
+        ref.SamBam_writer_add_read(w, -1, r["name"].encode(), r["flags"], r["chro"].encode(), r["pos"], r["mapq"], r["cigar"].encode(),
+                                   r["next_chro"].encode(), r["next_pos"], r["tlen"], r["read_len"], r["seq"].encode(), r["qual"].encode(),
+                                   r["additional"].encode(), int((not paired) or (i & 1)))
+    ref.SamBam_writer_close(w)
+
+    nw = OutputWriter(b, OUT_BAM, threads)
+    nw.add_header(header[0])
+    for name, length in CHROMS:
+        nw.add_chromosome(name, length, True)
+    nw.add_header(tail[0])
+    nw.finish_header()
+    half = len(recs) // 2
+    for i, r in enumerate(recs[:half]):
+        nw.add_read(to_struct(r), (not paired) or bool(i & 1))
+    nw.add_reads([to_struct(r) for r in recs[half:]], 2 if paired else 1)
+    size = nw.close()
+    assert size == os.path.getsize(b)
+    ra, rb = open(a, "rb").read(), open(b, "rb").read()
+    if ra != rb:
+        pa, sa = bgzf_payload(a)
+        pb, sb = bgzf_payload(b)
+        assert sa == sb, "block cuts differ"
+        assert pa == pb, "record bytes differ"
+    assert ra == rb
+    payload, sizes = bgzf_payload(b)
+    assert payload[:4] == b"BAM\x01" and sizes[-1] == 0 and len(sizes) > 10
+
+
+def test_long_header_is_cut_like_the_reference(ref, tmp_path):
+    """6 200 contigs (BASELINE configs[2]): header text and reference list both span several blocks."""
+    chroms = [(f"contig_{i:05d}_of_the_synthetic_genome", 500000 + i) for i in range(6200)]
+    recs = make_records(5, 300, chroms, False)
+    a, b = str(tmp_path / "ref.bam"), str(tmp_path / "native.bam")
+    write_with_reference(ref, a, ["@HD\tVN:1.0\tSO:unsorted"], chroms, recs, False)
+    write_native(b, OUT_BAM, ["@HD\tVN:1.0\tSO:unsorted"], chroms, recs, False, 3, batch=True)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert len(bgzf_payload(b)[1]) > 8
+
+
+def test_header_lines_with_sq_fill_the_chromosome_table(ref, tmp_path):
+    """add_header(.., add_chro=1) takes SN / LN from an @SQ line (sambam-file.c:1375-1393)."""
+    a, b = str(tmp_path / "ref.bam"), str(tmp_path / "native.bam")
+    lines = ["@HD\tVN:1.0", "@SQ\tSN:alpha\tLN:1000", "@SQ\tLN:2000\tSN:beta\tM5:abc", "@CO\tcomment"]
+    recs = make_records(9, 50, [("alpha", 1000), ("beta", 2000)], True)
+    w = ctypes.create_string_buffer(1 << 20)
+    assert ref.SamBam_writer_create(w, os.fsencode(a), 1, 0, 0, b"") == 0
+    for line in lines:
+        ref.SamBam_writer_add_header(w, ctypes.create_string_buffer(line.encode()), 1)
+    ref.SamBam_writer_finish_header(w)
+    for i, r in enumerate(recs):
+        ref.SamBam_writer_add_read(w, -1, r["name"].encode(), r["flags"], r["chro"].encode(), r["pos"], r["mapq"], r["cigar"].encode(),
+                                   r["next_chro"].encode(), r["next_pos"], r["tlen"], r["read_len"], r["seq"].encode(), r["qual"].encode(),
+                                   r["additional"].encode(), i & 1)
+    ref.SamBam_writer_close(w)
+    nw = OutputWriter(b, OUT_BAM, 2)
+    for line in lines:
+        nw.add_header(line, add_chro=True)
+    nw.add_reads([to_struct(r) for r in recs], 2)
+    nw.close()
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_sam_lines_to_bam_and_back(ref, tmp_path):
+    """SAM text written by the native writer, fed back through add_sam_lines, gives the BAM of the records themselves
+    (SamBam_writer_add_read_line, sambam-file.c:1668) -- and the text is the reference's record line (core.c:2156)."""
+    recs = [r for r in make_records(21, 3000, CHROMS, True) if not r["additional"].startswith("\t")]
+    recs = recs[: len(recs) & ~1]
+    sam, bam1, bam2 = str(tmp_path / "o.sam"), str(tmp_path / "direct.bam"), str(tmp_path / "via_text.bam")
+    write_native(sam, OUT_SAM, ["@HD\tVN:1.0\tSO:unsorted"], CHROMS, recs, True, 1)
+    text = open(sam, "rb").read()
+    lines = text.split(b"\n")
+    n_header = 1 + len(CHROMS)
+    assert lines[0] == b"@HD\tVN:1.0\tSO:unsorted" and lines[1] == b"@SQ\tSN:chr1\tLN:248956422"
+    r = recs[0]
+    expect = "%s\t%d\t%s\t%u\t%d\t%s\t%s\t%u\t%d\t%s\t%s%s%s" % (r["name"], r["flags"], r["chro"], r["pos"], r["mapq"], r["cigar"], r["next_chro"],
+                                                            r["next_pos"], r["tlen"], r["seq"], r["qual"], "\t" if r["additional"] else "",
+                                                            r["additional"])
+    assert lines[n_header].decode() == expect
+    write_native(bam1, OUT_BAM, ["@HD\tVN:1.0\tSO:unsorted"], CHROMS, recs, True, 2)
+    w = OutputWriter(bam2, OUT_BAM, 2)
+    w.add_header("@HD\tVN:1.0\tSO:unsorted")
+    for name, length in CHROMS:
+        w.add_chromosome(name, length, True)
+    body = b"\n".join(lines[n_header:])
+    w.add_sam_lines(body, 2)
+    w.close()
+    assert open(bam1, "rb").read() == open(bam2, "rb").read()
+    a = str(tmp_path / "ref.bam")
+    write_with_reference(ref, a, ["@HD\tVN:1.0\tSO:unsorted"], CHROMS, recs, True)
+    assert open(a, "rb").read() == open(bam1, "rb").read()
+
+
+def test_no_compression_blocks(tmp_path):
+    """fastest_compression of the reference's temporary files: stored blocks (sambam-file.h:42), still valid BGZF."""
+    recs = make_records(3, 500, CHROMS, False)
+    a, b = str(tmp_path / "stored.bam"), str(tmp_path / "deflated.bam")
+    w = OutputWriter(a, OUT_BAM, 2, no_compression=True)
+    w.add_header("@HD\tVN:1.0")
+    for name, length in CHROMS:
+        w.add_chromosome(name, length)
+    w.add_reads([to_struct(r) for r in recs], 1)
+    w.close()
+    write_native(b, OUT_BAM, ["@HD\tVN:1.0"], CHROMS, recs, False, 1)
+    assert bgzf_payload(a)[0] == bgzf_payload(b)[0]
+    assert os.path.getsize(a) > os.path.getsize(b)
+    assert gzip.open(a, "rb").read() == bgzf_payload(b)[0]           # any gzip reader takes the file
+
+
+def test_error_paths(tmp_path):
+    L = binding.load_library()
+    h = ctypes.c_void_p()
+    assert L.srcuda_out_open(os.fsencode(str(tmp_path / "no_such_dir" / "x.bam")), OUT_BAM, 1, 0, ctypes.byref(h)) == 3   # SRCUDA_ERR_IO
+    assert b"cannot create" in L.srcuda_out_error(None)
+    assert L.srcuda_out_open(None, 7, 1, 0, ctypes.byref(h)) == 5
+    assert L.srcuda_out_add_read(None, None, 1) == 5
+    assert L.srcuda_out_close(None, None) == 5
+    w = OutputWriter(str(tmp_path / "e.bam"), OUT_BAM, 1)
+    w.add_chromosome("a", 10)
+    with pytest.raises(binding.SubreadCudaError, match="twice"):
+        w.add_chromosome("a", 10)
+    w = OutputWriter(str(tmp_path / "f.bam"), OUT_BAM, 1)
+    with pytest.raises(binding.SubreadCudaError, match="bad read format"):
+        w.add_sam_lines(b"name\t0\tchr1\t1\n", 1)
