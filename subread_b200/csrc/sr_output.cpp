@@ -11,6 +11,10 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -20,14 +24,12 @@
 #include <unordered_map>
 #include <vector>
 
-namespace {
-
 constexpr size_t kBlockCut = 55000;     // sambam-file.c:1793 / :1253: a block is sealed once it is past this
 constexpr size_t kDeflateRoom = 70000;  // sambam-file.c:1209: room the reference gives deflate
 constexpr int kMaxCigarOps = 96;        // FC_MAX_CIGAR_SECTIONS, sambam-file.c:1603
 constexpr size_t kSamBuffer = 4u << 20;
 
-thread_local std::string g_open_error;
+static thread_local std::string g_open_error;
 
 struct Chromosome {
 	std::string name;
@@ -38,8 +40,6 @@ struct Deflated {
 	std::vector<unsigned char> bytes;  // the whole BGZF block: header, payload, CRC, size
 	bool ok = true;
 };
-
-}  // namespace
 
 struct srcuda_writer {
 	FILE *fp = nullptr;
@@ -54,7 +54,18 @@ struct srcuda_writer {
 	std::vector<Chromosome> chromosomes;
 	std::unordered_map<std::string, int> chromosome_id;
 	std::string block;                 // the block under construction (BAM) or the text buffer (SAM)
-	std::vector<std::string> sealed;   // complete blocks waiting for the deflate team
+	// complete blocks on their way through the deflate team, in file order
+	struct Job {
+		std::string plain;
+		Deflated out;
+		bool done = false;
+	};
+	std::deque<std::unique_ptr<Job>> jobs;
+	uint64_t front_seq = 0, claim_seq = 0;  // sequence number of jobs.front() / of the next job a worker takes
+	std::mutex mu;
+	std::condition_variable cv_work, cv_done;
+	std::vector<std::thread> team;
+	bool stop = false;
 	uint64_t bytes_written = 0;
 
 	int fail(int code, const char *fmt, ...) {
@@ -116,46 +127,86 @@ int write_bytes(srcuda_writer *w, const void *p, size_t n) {
 	return SRCUDA_OK;
 }
 
-// Deflate every sealed block on the team and write them in order.
-int drain(srcuda_writer *w) {
-	size_t n = w->sealed.size();
-	if (!n) return SRCUDA_OK;
-	std::vector<Deflated> out(n);
-	std::atomic<size_t> next{0};
-	auto work = [&]() {
-		for (;;) {
-			size_t i = next.fetch_add(1);
-			if (i >= n) break;
-			deflate_block(w->sealed[i], w->level, out[i]);
-		}
-	};
-	size_t team = std::min<size_t>((size_t)w->threads, n);
-	std::vector<std::thread> pool;
-	for (size_t t = 1; t < team; t++) {
+// The team: a worker takes the oldest block nobody has taken, deflates it and marks it done.
+void team_worker(srcuda_writer *w) {
+	std::unique_lock<std::mutex> lk(w->mu);
+	for (;;) {
+		w->cv_work.wait(lk, [&] { return w->stop || w->claim_seq < w->front_seq + w->jobs.size(); });
+		if (w->claim_seq >= w->front_seq + w->jobs.size()) return;  // stop, and nothing left to take
+		srcuda_writer::Job *job = w->jobs[(size_t)(w->claim_seq - w->front_seq)].get();
+		w->claim_seq++;
+		lk.unlock();
+		deflate_block(job->plain, w->level, job->out);
+		lk.lock();
+		job->done = true;
+		w->cv_done.notify_all();
+	}
+}
+
+void start_team(srcuda_writer *w) {
+	if (w->threads < 2 || !w->team.empty()) return;
+	for (int t = 0; t < w->threads; t++) {
 		try {
-			pool.emplace_back(work);
+			w->team.emplace_back(team_worker, w);
 		} catch (...) {
-			break;  // fewer helpers: the caller's thread does the rest
+			break;  // fewer workers; with none the caller's thread deflates (harvest)
 		}
 	}
-	work();
-	for (auto &t : pool) t.join();
-	for (size_t i = 0; i < n; i++) {
-		if (!out[i].ok) return w->fail(SRCUDA_ERR_FORMAT, "a block of %zu bytes does not fit a BGZF block", w->sealed[i].size());
-		int rc = write_bytes(w, out[i].bytes.data(), out[i].bytes.size());
-		if (rc) return rc;
+}
+
+void stop_team(srcuda_writer *w) {
+	{
+		std::lock_guard<std::mutex> lk(w->mu);
+		w->stop = true;
 	}
-	w->sealed.clear();
+	w->cv_work.notify_all();
+	for (auto &t : w->team) t.join();
+	w->team.clear();
+}
+
+// Write the blocks at the head of the line that are done; wait for more while more than `leave` blocks are in the line.
+int harvest(srcuda_writer *w, size_t leave) {
+	std::unique_lock<std::mutex> lk(w->mu);
+	while (!w->jobs.empty() && (w->jobs.front()->done || w->jobs.size() > leave)) {
+		srcuda_writer::Job *front = w->jobs.front().get();
+		if (!front->done) {
+			if (w->team.empty() || w->claim_seq == w->front_seq) {  // nobody has it: deflate it here
+				if (w->claim_seq == w->front_seq) w->claim_seq++;
+				lk.unlock();
+				deflate_block(front->plain, w->level, front->out);
+				lk.lock();
+				front->done = true;
+			} else {
+				w->cv_done.wait(lk);
+			}
+			continue;
+		}
+		std::unique_ptr<srcuda_writer::Job> job = std::move(w->jobs.front());
+		w->jobs.pop_front();
+		w->front_seq++;
+		lk.unlock();
+		if (!job->out.ok) return w->fail(SRCUDA_ERR_FORMAT, "a block of %zu bytes does not fit a BGZF block", job->plain.size());
+		int rc = write_bytes(w, job->out.bytes.data(), job->out.bytes.size());
+		if (rc) return rc;
+		lk.lock();
+	}
 	return SRCUDA_OK;
 }
 
+int drain(srcuda_writer *w) { return harvest(w, 0); }
+
 int seal_block(srcuda_writer *w) {
 	if (w->block.empty()) return SRCUDA_OK;
-	w->sealed.emplace_back();
-	w->sealed.back().swap(w->block);
+	std::unique_ptr<srcuda_writer::Job> job(new srcuda_writer::Job());
+	job->plain.swap(w->block);
 	w->block.reserve(kDeflateRoom);
-	if (w->sealed.size() >= (size_t)w->threads * 16) return drain(w);
-	return SRCUDA_OK;
+	start_team(w);
+	{
+		std::lock_guard<std::mutex> lk(w->mu);
+		w->jobs.push_back(std::move(job));
+	}
+	w->cv_work.notify_one();
+	return harvest(w, w->team.empty() ? 0 : (size_t)w->threads * 8);
 }
 
 // Header text and reference list of a BAM file, cut into blocks the way SamBam_writer_write_header does (sambam-file.c:1248-1303):
@@ -849,6 +900,7 @@ int srcuda_out_close(srcuda_writer *w, uint64_t *bytes_written) {
 	} else {
 		fflush(w->fp);
 	}
+	stop_team(w);
 	if (bytes_written) *bytes_written = w->bytes_written;
 	if (rc != SRCUDA_OK) g_open_error = w->error.empty() ? "write failed" : w->error;
 	delete w;
