@@ -102,3 +102,30 @@ def test_sam_identical_over_several_chunks(paired, gz, reader, tmp_path):
         outs.append(sam_body(out))
     assert outs[0].count(b"\n") >= 20000 * (2 if paired else 1)
     assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(not (os.path.exists(STOCK) and os.path.exists(CUDA) and os.path.exists(os.path.join(FIX, "chr901.fa"))),
+                    reason="oracle/_ref binaries or fixtures not built")
+@pytest.mark.parametrize("out_name,extra", [("o.sam", ["--SAMoutput"]), ("o.bam", ["--keepReadOrder"])])
+def test_gpu_voting_with_the_librarys_writer(out_name, extra, tmp_path):
+    """Both halves of the library behind the reference's CLI: STEP_VOTING on the GPU (integration/do_voting_cuda.c) and the SAM /
+    BAM file written by srcuda_out_* (integration/output_native.c, SRCUDA_NATIVE_OUTPUT=1), on the reference's paired-end fixture
+    (test-err-mut).  Alignment records identical to the stock subread-align's: the SAM text minus @PG, the BAM records one by one."""
+    from test_output_program import bam_records, no_pg
+    prefix = str(tmp_path / "chr901")
+    subprocess.run([BUILDINDEX, "-o", prefix, os.path.join(FIX, "chr901.fa")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    reads = ["-r", os.path.join(FIX, "test-err-mut-r1.fq.gz"), "-R", os.path.join(FIX, "test-err-mut-r2.fq.gz")]
+    outs = []
+    for exe, tag, native in ((STOCK, "stock", "0"), (CUDA, "cuda", "1")):
+        out = str(tmp_path / f"{tag}_{out_name}")
+        p = subprocess.run([exe, "-t", "1", "-T", "4", "-i", prefix] + reads + extra + ["-o", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           env=dict(os.environ, SRCUDA_NATIVE_OUTPUT=native))
+        assert p.returncode == 0, p.stdout.decode()[-2000:]
+        assert (b"written by libsubread_cuda" in p.stdout) == (native == "1")
+        outs.append(open(out, "rb").read())
+    if out_name.endswith(".sam"):
+        assert no_pg(outs[0]) == no_pg(outs[1]) and len(outs[0]) > 1000000
+    else:
+        (ta, ra), (tb, rb) = bam_records(outs[0]), bam_records(outs[1])
+        assert no_pg(ta) == no_pg(tb)
+        assert ra == rb and len(ra) > 40000
