@@ -294,6 +294,40 @@ def whole_program(g, index_arrays, name, sample_frags, tmp):
     return out
 
 
+def output_writer_measure(tmp, n_records=400_000, read_len=150):
+    """Row f2 on this box's host cores: the library's BAM writer (srcuda_out_*, one producer + a team of deflate threads) against
+    the reference's single stream (SamBam_writer_add_read_line) on the same synthetic SAM records, timed by
+    oracle/_ref/ref_writer_bench (the reference half is the baseline, like cpu_baseline); the two files are compared."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_writer_bench")
+    if not os.path.exists(exe):
+        return None
+    rng = np.random.default_rng(5)
+    seqs = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, (n_records, read_len))]
+    quals = (33 + rng.integers(2, 41, (n_records, read_len))).astype(np.uint8)
+    pos = rng.integers(1, 400_000, n_records)
+    sam = os.path.join(tmp, "writer_bench.sam")
+    with open(sam, "wb") as fh:
+        fh.write(b"@HD\tVN:1.0\tSO:unsorted\n" + b"".join(b"@SQ\tSN:chr%d\tLN:500000\n" % c for c in range(200)))
+        for i in range(n_records):
+            fh.write(b"read%d\t%d\tchr%d\t%d\t40\t%dM\t*\t0\t0\t%s\t%s\tHI:i:1\tNH:i:1\tNM:i:%d\n" % (
+                i, 16 * (i & 1), i % 200, pos[i], read_len, seqs[i].tobytes(), quals[i].tobytes(), i % 3))
+    threads = [t for t in (1, 4, 8, 16) if t <= max(1, host_threads())]
+    p = subprocess.run([exe, sam, "1", tmp] + [str(t) for t in threads], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    out = {"records": n_records, "read_len": read_len, "unit": "records/s", "library": {}}
+    for line in p.stdout.decode().splitlines():
+        if line.startswith("reference writer"):
+            out["reference_single_stream"] = float(line.split("=")[-1].split()[0]) * 1e6
+        elif line.startswith("library writer"):
+            out["library"]["%d_deflate_threads" % int(line.split(",")[1].split()[0])] = float(line.split("=")[-1].split()[0]) * 1e6
+    ref_bam = os.path.join(tmp, "ref.bam")
+    if os.path.exists(ref_bam):
+        raw = open(ref_bam, "rb").read()
+        out["files_identical"] = all(open(os.path.join(tmp, "native_%d.bam" % t), "rb").read() == raw for t in threads)
+    if p.returncode != 0:
+        out["error"] = "ref_writer_bench exit %d" % p.returncode
+    return out
+
+
 # ------------------------------------------------------------------------------ our arm
 
 def bind_to_gpu_numa_node(gpu_index):
@@ -588,7 +622,7 @@ def main():
             gather_gbs = None
 
     # ---- cpu baseline + algorithmic bytes (rank 0; the one place oracle/ is executed) -------
-    cpu_baseline, alg_bytes, whole, lookups_per_frag = None, None, None, None
+    cpu_baseline, alg_bytes, whole, lookups_per_frag, output_writer = None, None, None, None, None
     if rank == 0:
         try:
             from oracle import oracle
@@ -613,6 +647,11 @@ def main():
                     whole = whole_program(g, index_arrays, name, sample, tmp)
             except Exception as e:  # the baseline is reporting, never the product path
                 cpu_baseline = {"error": repr(e)}
+            try:
+                if name == "cfg2_se":
+                    output_writer = output_writer_measure(tmp)
+            except Exception as e:
+                output_writer = {"error": repr(e)}
             finally:
                 shutil.rmtree(tmp, ignore_errors=True)
 
@@ -682,7 +721,7 @@ def main():
                      "ms_per_step_wall": res["e2e_wall_ms"], "ms_per_step_events": res["e2e_ev_ms"], "matches_device_result": res["e2e_same"]}
                     if "e2e_wall_ms" in res else None),
             "gpu_launches": int(res["launches"] + res.get("e2e_launches", 0) * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "whole_program": whole, "verify": res.get("verify"), "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "whole_program": whole, "output_writer": output_writer, "verify": res.get("verify"), "clocks": clk,
             "mapped_fraction": res["mapped"], "clean_fraction": res["clean_fraction"], "slot0_is_true_position": res["slot0_true"],
             "ranks": rank_rows, "sweep": sweep_rows,
             "index_replication_s": t_rep if world > 1 else None,

@@ -70,7 +70,7 @@ int main(int argc, char **argv)
 		}
 	SamBam_writer_close(w);
 	double dt = now() - t0;
-	printf("reference writer (one stream): %ld records, %.1f MB of SAM in %.3f s = %.2f M records/s\n", n_lines * repeat, body * (double)repeat / 1e6, dt,
+	printf("reference writer (one stream): %ld records, %.1f MB of SAM in %.3f s = %.4f M records/s\n", n_lines * repeat, body * (double)repeat / 1e6, dt,
 	       n_lines * repeat / dt / 1e6);
 
 	for (int a = 4; a < argc; a++) {
@@ -91,7 +91,7 @@ int main(int argc, char **argv)
 			if (srcuda_out_add_sam_lines(nw, all + head, body, 1)) return 3;
 		if (srcuda_out_close(nw, NULL)) return 4;
 		dt = now() - t0;
-		printf("library writer, %2d deflate threads: %.3f s = %.2f M records/s\n", threads, dt, n_lines * repeat / dt / 1e6);
+		printf("library writer, %2d deflate threads: %.3f s = %.4f M records/s\n", threads, dt, n_lines * repeat / dt / 1e6);
 	}
 	return 0;
 }
