@@ -137,6 +137,17 @@ int srcuda_sam_calc_tlen(int32_t offset1, const char *cigar1, int read_len_1, in
 int srcuda_out_add_fragment(srcuda_writer *w, const srcuda_sam_config *cfg, srcuda_sam_mate *m1, srcuda_sam_mate *m2,
                             int all_locations, int current_location, srcuda_sam_counters *counters);
 
+/* The same in two steps, for callers that build records on several threads (the reference's workers do, core.c:2436):
+ * srcuda_out_format_fragment does everything srcuda_out_add_fragment does up to the encoded bytes (SAM text or BAM records of
+ * the one or two mates) and may run on any number of threads at once -- it only reads the writer, whose header must be
+ * finished; srcuda_out_append hands such bytes to the stream, one caller at a time, in the order the file shall have.
+ * *bytes receives the encoded size; SRCUDA_ERR_NOMEM when it exceeds `capacity` (nothing is copied then).  Failures of
+ * srcuda_out_format_fragment leave their message in srcuda_out_error(NULL) of the calling thread. */
+int srcuda_out_format_fragment(const srcuda_writer *w, const srcuda_sam_config *cfg, srcuda_sam_mate *m1, srcuda_sam_mate *m2,
+                               int all_locations, int current_location, srcuda_sam_counters *counters, void *buffer, size_t capacity,
+                               size_t *bytes);
+int srcuda_out_append(srcuda_writer *w, const void *encoded, size_t bytes, int committable);
+
 /* Everything appended so far is compressed and handed to the file. */
 int srcuda_out_flush(srcuda_writer *w);
 

@@ -280,14 +280,30 @@ void write_single_fragment(global_context_t *global_context, thread_context_t *t
 	srcuda_sam_counters c;
 	memset(&c, 0, sizeof c);
 
-	int rc;
+	/* the records are built here, on the worker's own thread; only handing the bytes over takes a turn */
+	static __thread char *encoded;
+	static __thread size_t encoded_room;
+	size_t bytes = 0, room = 4096 + 2 * strlen(global_context->config.read_group_id);
+	room += 4 * (size_t)read_len_1 + strlen(read_name_1) + (is_R1_OK ? strlen(rec1->cigar) + strlen(rec1->additional_information) : 0);
+	if (paired) room += 4 * (size_t)read_len_2 + strlen(read_name_2) + (is_R2_OK ? strlen(rec2->cigar) + strlen(rec2->additional_information) : 0);
+	if (room > encoded_room) {
+		free(encoded);
+		encoded = malloc(encoded_room = 2 * room);
+	}
+	int rc = encoded ? srcuda_out_format_fragment(g_out.writer, &cfg, &m1, paired ? &m2 : NULL, all_locations, current_location, &c, encoded,
+	                                              encoded_room, &bytes)
+	                 : SRCUDA_ERR_NOMEM;
+	if (rc) {
+		SUBREADprintf("ERROR: cannot build a record: %s\n", srcuda_out_error(NULL));
+		bytes = 0; /* the turn below is still taken, or the workers behind would wait for ever */
+	}
 	int in_turns = thread_context && !(global_context->config.is_BAM_output && !global_context->config.is_input_read_order_required);
 	if (in_turns) { /* input order: wait for the fragment in front (add_buffered_fragment, core.c:1855-1881) */
 		for (;;) {
 			int done = 0;
 			subread_lock_occupy(&global_context->output_lock);
 			if (global_context->last_written_fragment_number == pair_number - 1) {
-				rc = srcuda_out_add_fragment(g_out.writer, &cfg, &m1, paired ? &m2 : NULL, all_locations, current_location, &c);
+				if (bytes && srcuda_out_append(g_out.writer, encoded, bytes, 1)) rc = SRCUDA_ERR_IO;
 				if (all_locations <= current_location + 1) global_context->last_written_fragment_number = pair_number;
 				done = 1;
 			}
@@ -295,9 +311,9 @@ void write_single_fragment(global_context_t *global_context, thread_context_t *t
 			if (done) break;
 			usleep(2);
 		}
-	} else {
+	} else if (bytes) {
 		pthread_mutex_lock(&g_out.lock);
-		rc = srcuda_out_add_fragment(g_out.writer, &cfg, &m1, paired ? &m2 : NULL, all_locations, current_location, &c);
+		if (srcuda_out_append(g_out.writer, encoded, bytes, 1)) rc = SRCUDA_ERR_IO;
 		pthread_mutex_unlock(&g_out.lock);
 	}
 	if (rc) {

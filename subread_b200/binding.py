@@ -27,7 +27,7 @@ EXPORTS = [
     "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_skip", "srcuda_reader_tell", "srcuda_reader_error", "srcuda_reader_close",
     # include/subread_output.h (row f2)
     "srcuda_out_open", "srcuda_out_add_header", "srcuda_out_add_chromosome", "srcuda_out_finish_header", "srcuda_out_add_read",
-    "srcuda_out_add_reads", "srcuda_out_add_sam_lines", "srcuda_out_add_fragment", "srcuda_out_flush", "srcuda_out_close",
+    "srcuda_out_add_reads", "srcuda_out_add_sam_lines", "srcuda_out_add_fragment", "srcuda_out_format_fragment", "srcuda_out_append", "srcuda_out_flush", "srcuda_out_close",
     "srcuda_out_error", "srcuda_sam_calc_flags", "srcuda_sam_calc_tlen",
 ]
 
@@ -160,6 +160,9 @@ def load_library():
     L.srcuda_out_add_sam_lines.argtypes = [vp, cp, ctypes.c_size_t, ctypes.c_int]
     L.srcuda_out_add_fragment.argtypes = [vp, ctypes.POINTER(SamConfig), ctypes.POINTER(SamMate), ctypes.POINTER(SamMate),
                                           ctypes.c_int, ctypes.c_int, ctypes.POINTER(SamCounters)]
+    L.srcuda_out_format_fragment.argtypes = [vp, ctypes.POINTER(SamConfig), ctypes.POINTER(SamMate), ctypes.POINTER(SamMate), ctypes.c_int,
+                                             ctypes.c_int, ctypes.POINTER(SamCounters), vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    L.srcuda_out_append.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
     L.srcuda_out_flush.argtypes = [vp]
     L.srcuda_out_close.argtypes = [vp, ctypes.POINTER(u64)]
     L.srcuda_out_error.argtypes = [vp]

@@ -389,13 +389,25 @@ int pack_additional(const char *a, unsigned char *bin) {
 	return used;
 }
 
+// The encoders below only read the writer (format, chromosome table): several threads may run them at once.  Their failures
+// are returned as text.
+int encode_error(std::string &err, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	err = buf;
+	return code;
+}
+
 int lookup_chromosome(const srcuda_writer *w, const char *name) {
 	auto it = w->chromosome_id.find(name);
 	return it == w->chromosome_id.end() ? -1 : it->second;
 }
 
-// One record into the block under construction (SamBam_writer_add_read, sambam-file.c:1704-1797).
-int bam_append(srcuda_writer *w, const srcuda_sam_record *r) {
+// One record in BAM form at the end of `b` (SamBam_writer_add_read, sambam-file.c:1704-1797).
+int bam_encode(const srcuda_writer *w, const srcuda_sam_record *r, std::string &b, std::string &err) {
 	uint32_t ops[kMaxCigarOps];
 	int covered = 0;
 	int n_ops = pack_cigar(r->cigar, ops, &covered);
@@ -403,15 +415,14 @@ int bam_append(srcuda_writer *w, const srcuda_sam_record *r) {
 	unsigned char extra[1100];
 	int extra_len = 0;
 	if (r->additional) {
-		if (strlen(r->additional) > 100000) return w->fail(SRCUDA_ERR_ARG, "optional columns of %s are too long", r->name);
+		if (strlen(r->additional) > 100000) return encode_error(err, SRCUDA_ERR_ARG, "optional columns of %s are too long", r->name);
 		extra_len = pack_additional(r->additional, extra);
-		if (extra_len < 0) return w->fail(SRCUDA_ERR_FORMAT, "optional columns of %s: unknown type in '%.20s'", r->name, r->additional);
+		if (extra_len < 0) return encode_error(err, SRCUDA_ERR_FORMAT, "optional columns of %s: unknown type in '%.20s'", r->name, r->additional);
 	}
 	int read_len = r->read_len;
 	if (read_len < 0 || strlen(r->seq) < (size_t)read_len || strlen(r->qual) < (size_t)read_len)
-		return w->fail(SRCUDA_ERR_ARG, "record %s: sequence or qualities shorter than read_len %d", r->name, read_len);
+		return encode_error(err, SRCUDA_ERR_ARG, "record %s: sequence or qualities shorter than read_len %d", r->name, read_len);
 	uint32_t record_len = 32 + (uint32_t)name_len + 4 * (uint32_t)n_ops + (uint32_t)(read_len + 1) / 2 + (uint32_t)read_len + (uint32_t)extra_len;
-	std::string &b = w->block;
 	put32(b, record_len);
 	int bin = reg2bin((int)(r->pos - 1), (int)(r->pos - 1) + covered);
 	int ref_id = lookup_chromosome(w, r->chro);
@@ -447,8 +458,7 @@ void append_number(std::string &b, long long v) {
 }
 
 // The record line of core.c:2156-2164: "%s\t%d\t%s\t%u\t%d\t%s\t%s\t%u\t%lld\t%s\t%s%s%s\n".
-void sam_append(srcuda_writer *w, const srcuda_sam_record *r) {
-	std::string &b = w->block;
+void sam_encode(const srcuda_sam_record *r, std::string &b) {
 	b.append(r->name).push_back('\t');
 	append_number(b, (int)r->flags);
 	b.push_back('\t');
@@ -478,22 +488,36 @@ int sam_flush(srcuda_writer *w) {
 	return rc;
 }
 
+int encode_record(const srcuda_writer *w, const srcuda_sam_record *r, std::string &b, std::string &err) {
+	if (!r->name || !r->chro || !r->cigar || !r->next_chro || !r->seq || !r->qual) return encode_error(err, SRCUDA_ERR_ARG, "record with a NULL column");
+	if (w->format == SRCUDA_OUT_SAM) {
+		sam_encode(r, b);
+		return SRCUDA_OK;
+	}
+	return bam_encode(w, r, b, err);
+}
+
+// Behind every committable record: a BAM block past the mark is sealed, a full text buffer is written.
+int after_records(srcuda_writer *w, int committable) {
+	if (w->format == SRCUDA_OUT_SAM) return w->block.size() > kSamBuffer ? sam_flush(w) : SRCUDA_OK;
+	if (w->block.size() > kBlockCut && committable) return seal_block(w);
+	return SRCUDA_OK;
+}
+
 int add_read(srcuda_writer *w, const srcuda_sam_record *r, int committable) {
 	if (w->failed) return SRCUDA_ERR_IO;
-	if (!r->name || !r->chro || !r->cigar || !r->next_chro || !r->seq || !r->qual) return w->fail(SRCUDA_ERR_ARG, "record with a NULL column");
 	if (!w->header_done) {
 		int rc = finish_header(w);
 		if (rc) return rc;
 	}
-	if (w->format == SRCUDA_OUT_SAM) {
-		sam_append(w, r);
-		if (w->block.size() > kSamBuffer) return sam_flush(w);
-		return SRCUDA_OK;
+	std::string err;
+	size_t before = w->block.size();
+	int rc = encode_record(w, r, w->block, err);
+	if (rc) {
+		w->block.resize(before);
+		return w->fail(rc, "%s", err.c_str());
 	}
-	int rc = bam_append(w, r);
-	if (rc) return rc;
-	if (w->block.size() > kBlockCut && committable) return seal_block(w);
-	return SRCUDA_OK;
+	return after_records(w, committable);
 }
 
 // ---- fragment level ---------------------------------------------------------------------------------------------------
@@ -772,11 +796,15 @@ int srcuda_sam_calc_tlen(int32_t offset1, const char *cigar1, int read_len_1, in
 	return tlen;
 }
 
-int srcuda_out_add_fragment(srcuda_writer *w, const srcuda_sam_config *cfg, srcuda_sam_mate *m1, srcuda_sam_mate *m2,
-                            int all_locations, int current_location, srcuda_sam_counters *counters) {
-	if (!w || !cfg || !m1) return SRCUDA_ERR_ARG;
+}  // extern "C"
+
+namespace {
+
+// write_single_fragment (core.c:1888-2170) up to the encoded records, appended to `dst`.  Reads the writer only.
+int build_fragment(const srcuda_writer *w, const srcuda_sam_config *cfg, srcuda_sam_mate *m1, srcuda_sam_mate *m2, int all_locations,
+                   int current_location, srcuda_sam_counters *counters, std::string &dst, std::string &err) {
 	bool paired = cfg->is_paired_end != 0;
-	if (paired && !m2) return w->fail(SRCUDA_ERR_ARG, "paired-end output needs both mates");
+	if (paired && !m2) return encode_error(err, SRCUDA_ERR_ARG, "paired-end output needs both mates");
 	if (!paired) m2 = nullptr;
 	srcuda_sam_counters scratch;
 	memset(&scratch, 0, sizeof scratch);
@@ -785,12 +813,12 @@ int srcuda_out_add_fragment(srcuda_writer *w, const srcuda_sam_config *cfg, srcu
 	int n_mates = paired ? 2 : 1;
 	for (int i = 0; i < n_mates; i++) {
 		srcuda_sam_mate *m = mates[i];
-		if (!m->name || !m->text || !m->qual || m->read_len < 0) return w->fail(SRCUDA_ERR_ARG, "mate %d: NULL read columns", i + 1);
+		if (!m->name || !m->text || !m->qual || m->read_len < 0) return encode_error(err, SRCUDA_ERR_ARG, "mate %d: NULL read columns", i + 1);
 		if (m->ok && (!m->cigar || m->chro_id < 0 || (size_t)m->chro_id >= w->chromosomes.size()))
-			return w->fail(SRCUDA_ERR_ARG, "mate %d: mapped without a CIGAR or a chromosome of the table", i + 1);
+			return encode_error(err, SRCUDA_ERR_ARG, "mate %d: mapped without a CIGAR or a chromosome of the table", i + 1);
 	}
 	const char *rg = cfg->read_group_id ? cfg->read_group_id : "";
-	if (strlen(rg) > 300) return w->fail(SRCUDA_ERR_ARG, "read group id longer than 300 characters");
+	if (strlen(rg) > 300) return encode_error(err, SRCUDA_ERR_ARG, "read group id longer than 300 characters");
 	bool ok1 = m1->ok != 0, ok2 = m2 && m2->ok;
 
 	int tlen = 0;
@@ -868,9 +896,66 @@ int srcuda_out_add_fragment(srcuda_writer *w, const srcuda_sam_config *cfg, srcu
 		rec[1].next_chro = one_chromosome ? "=" : rec[0].chro;
 		rec[1].next_pos = rec[0].pos;
 	}
-	int rc = add_read(w, &rec[0], !paired);
-	if (rc == SRCUDA_OK && paired) rc = add_read(w, &rec[1], 1);
+	size_t before = dst.size();
+	int rc = encode_record(w, &rec[0], dst, err);
+	if (rc == SRCUDA_OK && paired) rc = encode_record(w, &rec[1], dst, err);
+	if (rc) dst.resize(before);
 	return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int srcuda_out_add_fragment(srcuda_writer *w, const srcuda_sam_config *cfg, srcuda_sam_mate *m1, srcuda_sam_mate *m2,
+                            int all_locations, int current_location, srcuda_sam_counters *counters) {
+	if (!w || !cfg || !m1) return SRCUDA_ERR_ARG;
+	if (w->failed) return SRCUDA_ERR_IO;
+	if (!w->header_done) {
+		int rc = finish_header(w);
+		if (rc) return rc;
+	}
+	std::string err;
+	int rc = build_fragment(w, cfg, m1, m2, all_locations, current_location, counters, w->block, err);
+	if (rc) return w->fail(rc, "%s", err.c_str());
+	return after_records(w, 1);
+}
+
+int srcuda_out_format_fragment(const srcuda_writer *w, const srcuda_sam_config *cfg, srcuda_sam_mate *m1, srcuda_sam_mate *m2,
+                               int all_locations, int current_location, srcuda_sam_counters *counters, void *buffer, size_t capacity,
+                               size_t *bytes) {
+	if (!w || !cfg || !m1 || !bytes || (capacity && !buffer)) return SRCUDA_ERR_ARG;
+	*bytes = 0;
+	if (!w->header_done) {
+		g_open_error = "srcuda_out_format_fragment: the header is still open (srcuda_out_finish_header first)";
+		return SRCUDA_ERR_ARG;
+	}
+	static thread_local std::string scratch;
+	scratch.clear();
+	std::string err;
+	int rc = build_fragment(w, cfg, m1, m2, all_locations, current_location, counters, scratch, err);
+	if (rc) {
+		g_open_error = err;
+		return rc;
+	}
+	*bytes = scratch.size();
+	if (scratch.size() > capacity) {
+		g_open_error = "srcuda_out_format_fragment: the buffer is too small";
+		return SRCUDA_ERR_NOMEM;
+	}
+	memcpy(buffer, scratch.data(), scratch.size());
+	return SRCUDA_OK;
+}
+
+int srcuda_out_append(srcuda_writer *w, const void *encoded, size_t bytes, int committable) {
+	if (!w || (bytes && !encoded)) return SRCUDA_ERR_ARG;
+	if (w->failed) return SRCUDA_ERR_IO;
+	if (!w->header_done) {
+		int rc = finish_header(w);
+		if (rc) return rc;
+	}
+	w->block.append((const char *)encoded, bytes);
+	return after_records(w, committable);
 }
 
 int srcuda_out_flush(srcuda_writer *w) {

@@ -288,3 +288,68 @@ def test_error_paths(tmp_path):
     w = OutputWriter(str(tmp_path / "f.bam"), OUT_BAM, 1)
     with pytest.raises(binding.SubreadCudaError, match="bad read format"):
         w.add_sam_lines(b"name\t0\tchr1\t1\n", 1)
+
+
+def _mate(ok, chro_id, offset, strand, cigar, name, text, qual, additional=b"", mm=0, mapq=40):
+    bufs = [ctypes.create_string_buffer(x, len(x) + 8) for x in (name, text, qual)]
+    m = binding.SamMate(1, int(ok), chro_id, offset, strand, mapq, mm, len(text), cigar, additional,
+                        ctypes.cast(bufs[0], ctypes.c_void_p), ctypes.cast(bufs[1], ctypes.c_void_p), ctypes.cast(bufs[2], ctypes.c_void_p))
+    m._keep = bufs
+    return m
+
+
+def test_fragment_records_and_two_step_form(tmp_path):
+    """srcuda_out_add_fragment against hand-checked records (flags, TLEN sign, mate columns, NM = mismatches + indel bases, reverse
+    strand printed reverse-complemented), and srcuda_out_format_fragment + srcuda_out_append give the same file."""
+    cfg = binding.SamConfig(1, 50, 600, 0, 1, 0, b"")
+    seq1, seq2 = b"ACGTTGCANN" * 5, b"TTGACCAGTA" * 5
+    q1, q2 = bytes(range(40, 90)), bytes(range(89, 39, -1))
+    paths = [str(tmp_path / "one.sam"), str(tmp_path / "two.sam")]
+    L = binding.load_library()
+    for two_step, path in enumerate(paths):
+        w = OutputWriter(path, OUT_SAM, 1)
+        w.add_chromosome("chrA", 100000)
+        w.add_chromosome("chrB", 50000)
+        w.finish_header()
+        cases = [
+            # a proper pair: mate 1 forward at 1000, mate 2 (stored strand 0 = reverse of the fragment) at 1200 with a deletion
+            (_mate(1, 0, 1000, 0, b"50M", b"frag1/1", seq1, q1, b"\tSB:i:7", 2), _mate(1, 0, 1200, 0, b"20M3D30M", b"frag1/2", seq2, q2, b"", 1)),
+            # mate 2 unmapped
+            (_mate(1, 1, 77, 1, b"10S40M", b"frag2", seq1, q1), _mate(0, -1, 0, 0, None, b"frag2", seq2, q2)),
+            # different chromosomes
+            (_mate(1, 0, 5, 0, b"50M", b"frag3", seq1, q1), _mate(1, 1, 9, 1, b"25M2I23M", b"frag3", seq2, q2, b"", 3)),
+            # both unmapped
+            (_mate(0, -1, 0, 0, None, b"frag4", seq1, q1), _mate(0, -1, 0, 0, None, b"frag4", seq2, q2)),
+        ]
+        counters = binding.SamCounters()
+        for m1, m2 in cases:
+            if two_step:
+                buf = ctypes.create_string_buffer(8192)
+                n = ctypes.c_size_t()
+                assert L.srcuda_out_format_fragment(w.h, ctypes.byref(cfg), ctypes.byref(m1), ctypes.byref(m2), 1, 0, ctypes.byref(counters), buf, 8192,
+                                                    ctypes.byref(n)) == 0
+                assert L.srcuda_out_append(w.h, buf, n.value, 1) == 0
+            else:
+                w.add_fragment(cfg, m1, m2, 1, 0, counters)
+        w.close()
+        assert counters.all_mapped_reads == 3 and counters.all_correct_PE_reads == 1 and counters.not_properly_pairs_different_chro == 2   # frag2 (a record without a position counts, as in the reference) and frag3
+    a, b = open(paths[0], "rb").read(), open(paths[1], "rb").read()
+    assert a == b
+    rows = [l.split("\t") for l in a.decode().splitlines() if not l.startswith("@")]
+    assert len(rows) == 8
+    r1, r2 = rows[0], rows[1]
+    assert r1[:9] == ["frag1", str(0x1 | 0x2 | 0x20 | 0x40), "chrA", "1000", "40", "50M", "=", "1200", "250"]   # calc_tlen walks the left mate only: 1200 - 1050 + 50 + 50
+    assert r2[:9] == ["frag1", str(0x1 | 0x2 | 0x10 | 0x80), "chrA", "1200", "40", "20M3D30M", "=", "1000", "-250"]
+    assert r1[9] == seq1.decode() and r1[11:] == ["HI:i:1", "NH:i:1", "SB:i:7", "NM:i:2"]
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    # a second mate on stored strand 0 is printed as it came in (the input step has turned it already), flag 0x10 notwithstanding
+    assert r2[9] == seq2.decode() and r2[10] == q2.decode() and r2[11:] == ["HI:i:1", "NH:i:1", "NM:i:4"]
+    assert rows[2][9] == seq1.translate(comp)[::-1].decode() and rows[2][10] == q1[::-1].decode()      # strand 1: reverse-complemented
+    assert rows[2][1] == str(0x1 | 0x8 | 0x10 | 0x40) and rows[2][6:9] == ["*", "0", "0"] and rows[2][2:4] == ["chrB", "77"]
+    assert rows[3][1] == str(0x1 | 0x4 | 0x20 | 0x80) and rows[3][2:9] == ["*", "0", "0", "*", "chrB", "77", "0"] and rows[3][11:] == ["HI:i:1", "NH:i:1"]
+    assert rows[4][6:9] == ["chrB", "9", "0"] and rows[5][6:9] == ["chrA", "5", "0"] and rows[5][11:] == ["HI:i:1", "NH:i:1", "NM:i:5"]
+    assert len(rows[6]) == 11 and rows[6][1] == str(0x1 | 0x4 | 0x8 | 0x40) and len(rows[7]) == 11
+    # calc_tlen on its own: equal starts -> the longer read; a gap between the mates -> both reads plus the gap
+    assert L.srcuda_sam_calc_tlen(100, b"50M", 50, 100, b"75M", 75) == 75
+    assert L.srcuda_sam_calc_tlen(100, b"50M", 50, 400, b"50M", 50) == 350
+    assert L.srcuda_sam_calc_tlen(400, b"50M", 50, 100, b"20M200N30M", 50) == 150   # the fallback counts from the last matched section, intron left out (core.c:1783)
