@@ -10,7 +10,9 @@ byte-identical to the reference builder's (tests/test_index_build.py); the sort 
 when one is visible (torch, plumbing only) and in numpy otherwise.
 
 It exists so that benchmarks and tests can make indexes for synthetic genomes without the
-reference; multi-block indexes (no ``-B``) are still built by the reference's own tool.
+reference.  ``build_index_blocks`` is the builder without ``-B``: the index is cut into blocks of
+``-M`` megabytes the way ``build_gene_index`` cuts it (:255-330, :353), every block's files
+byte-identical to the reference builder's as well.
 """
 import gzip
 import os
@@ -165,8 +167,8 @@ def build_index_arrays(names, seqs, gapped=True, threshold=100, buckets=None, us
                 names=list(names), contig_starts=np.array(starts, dtype=np.int64), removed_keys=int(heavy.shape[0]))
 
 
-def write_index_files(prefix, a, buckets_per_piece=1 << 20):
-    """<prefix>.00.b.tab (gehash_dump, sorted-hashtable.c:1700-1908), .00.b.array and .reads.  The table is written in
+def write_index_files(prefix, a, buckets_per_piece=1 << 20, block_no=0, write_reads=True):
+    """<prefix>.NN.b.tab (gehash_dump, sorted-hashtable.c:1700-1908), .NN.b.array and .reads.  The table is written in
     pieces of ``buckets_per_piece`` buckets so that a human-sized block (6.3 GB) needs no second copy in memory."""
     nb, n_items = int(a["buckets_number"]), int(a["n_items"])
     starts_items = a["bucket_start"].astype(np.int64)
@@ -175,7 +177,7 @@ def write_index_files(prefix, a, buckets_per_piece=1 << 20):
     head += np.array([0x0102, 2, a["padding"], 0x0101, 2, a["index_gap"], 0], dtype="<i2").tobytes()
     head += np.array([n_items], dtype="<i8").tobytes() + np.array([nb], dtype="<i4").tobytes()
     keys, vals = a["keys"], a["vals"]
-    with open(prefix + ".00.b.tab", "wb") as fh:
+    with open(prefix + ".%02d.b.tab" % block_no, "wb") as fh:
         fh.write(bytes(head))
         for b0 in range(0, nb, buckets_per_piece):
             b1 = min(nb, b0 + buckets_per_piece)
@@ -200,9 +202,11 @@ def write_index_files(prefix, a, buckets_per_piece=1 << 20):
                     body[val_at + k] = vb[:, k]
             fh.write(body.tobytes())
         fh.write(b"\0")  # trailing byte: is_small_table = 0
-    with open(prefix + ".00.b.array", "wb") as fh:
+    with open(prefix + ".%02d.b.array" % block_no, "wb") as fh:
         fh.write(np.array([a["start_point"], a["length"]], dtype="<u4").tobytes())
         fh.write(a["values"].tobytes())
+    if not write_reads:
+        return
     with open(prefix + ".reads", "wb") as fh:  # index-builder.c:189-194
         for e, nm in zip(a["read_offsets"], a["names"]):
             fh.write(b"%d\t%s\n" % (int(e), nm.encode()))
@@ -215,6 +219,136 @@ def build_index(fasta_path, prefix, gapped=True, threshold=100, buckets=None, us
     write_index_files(prefix, a)
     return dict(buckets=a["buckets_number"], items=a["n_items"], gap=a["index_gap"], removed_keys=a["removed_keys"],
                 length=a["length"], contigs=len(seqs))
+
+
+MIN_READ_SPLICING = 2000000  # index-builder.c:41
+
+
+def expected_items_for_memory(memory_mb: int) -> int:
+    """``-M``: items per block, index-builder.c:1269 (8000 MB by default, :1026)."""
+    return (int(memory_mb * 1024.0 / 8.0) * 1024) & 0xFFFFFFFF
+
+
+def plan_blocks(read_len, inserted, first_window_of_contig, contig_of_window, expected_items, gap):
+    """Where ``build_gene_index`` cuts the index (index-builder.c:255-330, :353), as ranges of sampled windows.
+
+    The builder walks the windows in order; behind every window it looks at the number of items the current table holds and
+    at how far into its contig it is (``read_len``): a table that has reached ``expected_items`` is closed as soon as the
+    walk is more than 2 Mbp into a contig or within the first 32 bases of one.  It then steps BACK -- to the contig's first
+    window in the second case, by 1 999 990 bases (+16) in the first -- so consecutive blocks overlap.  Returns
+    [(first_window, last_window)] inclusive."""
+    n = read_len.shape[0]
+    cum = np.concatenate(([0], np.cumsum(inserted, dtype=np.int64)))
+    may_cut = (read_len > MIN_READ_SPLICING) | (read_len < 32)
+    cut_at = np.flatnonzero(may_cut)
+    back = MIN_READ_SPLICING - 10
+    back = back - back % 3 + 1                       # :269-271
+    blocks, first = [], 0
+    while True:
+        # first window j >= first with cum[j + 1] - cum[first] >= expected_items and may_cut[j]
+        need = cum[first] + expected_items
+        j_items = int(np.searchsorted(cum, need, side="left")) - 1       # smallest j with cum[j + 1] >= need
+        j_items = max(j_items, first)
+        k = int(np.searchsorted(cut_at, j_items, side="left"))
+        if j_items >= n or k >= cut_at.shape[0]:
+            blocks.append((first, n - 1))
+            return blocks
+        j = int(cut_at[k])
+        blocks.append((first, j))
+        if read_len[j] < MIN_READ_SPLICING:
+            first = int(first_window_of_contig[contig_of_window[j]])
+        else:
+            if (back - 16) % gap:
+                raise ValueError("the step back does not land on a sampled window")   # 1 999 974 is a multiple of 3 (and of 1)
+            first = j - (back - 16) // gap
+        if len(blocks) > 99:
+            raise ValueError("more than 99 index blocks")
+
+
+def build_index_blocks(names, seqs, gapped=True, threshold=100, memory_mb=8000, use_gpu=False):
+    """The blocks of an index built WITHOUT ``-B`` (subread-buildindex -M memory_mb [-F]): a list of the dicts
+    ``build_index_arrays`` returns, one per block, each with its own table, its own stretch of the 2-bit genome
+    (``start_point`` = linear position of its first window) and the shared contig table."""
+    gap = 3 if gapped else 1
+    expected = expected_items_for_memory(memory_mb)
+    nb = calculate_buckets_by_size(expected, gap)
+    if not seqs:
+        raise ValueError("no contig longer than 16 bases")
+    keys_l, vals_l, rl_l, cw_l, first_w, starts, ends = [], [], [], [], [], [], []
+    start, n_w = PADDING, 0
+    for c, s in enumerate(seqs):
+        L = s.shape[0]
+        codes = _CODE[s].astype(np.uint32)
+        p = np.arange(0, L - 15, gap, dtype=np.int64)
+        key = np.zeros(p.shape[0], dtype=np.uint32)
+        for i in range(16):
+            key |= codes[p + i] << np.uint32(30 - 2 * i)
+        keys_l.append(key)
+        vals_l.append((p + start).astype(np.uint32))
+        rl_l.append(p + 16)
+        cw_l.append(np.full(p.shape[0], c, dtype=np.int32))
+        first_w.append(n_w)
+        n_w += p.shape[0]
+        starts.append(start)
+        ends.append(start + L - 16 + PADDING)
+        start = start + (L - 16) + 2 * PADDING
+    total_end = starts[-1] + seqs[-1].shape[0]
+    if total_end + PADDING > 0xFFFFFFFD:
+        raise ValueError("the reference sequences include more than 4 billion bases")
+    key, val = np.concatenate(keys_l), np.concatenate(vals_l)
+    read_len, contig_of_window = np.concatenate(rl_l), np.concatenate(cw_l)
+    del keys_l, vals_l, rl_l, cw_l
+    # scan_gene_index runs once over the whole genome: a 16-mer sampled more than `threshold` times is in no block
+    srt = np.sort(key)
+    edge = np.flatnonzero(np.concatenate(([True], srt[1:] != srt[:-1], [True])))
+    heavy = srt[edge[:-1][np.diff(edge) > threshold]]
+    del srt
+    inserted = ~np.isin(key, heavy) if heavy.shape[0] else np.ones(key.shape[0], dtype=bool)
+    # the whole 2-bit genome once; a block's array is a stretch of it with the bases outside the block cleared
+    n_bases = ((total_end + PADDING) >> 2) * 4 + 8
+    bases = np.zeros(n_bases, dtype=np.uint8)
+    for s, st in zip(seqs, starts):
+        bases[st:st + s.shape[0]] = _CODE[s]
+
+    out = []
+    for first, last in plan_blocks(read_len, inserted, np.array(first_w, dtype=np.int64), contig_of_window, expected, gap):
+        sel = np.flatnonzero(inserted[first:last + 1]) + first
+        k, v = key[sel], val[sel]
+        bucket = (k % np.uint32(nb)).astype(np.uint32)
+        key16 = (k // np.uint32(nb)).astype(np.uint16).view(np.int16)
+        parity = ((k % np.uint32(791)) % np.uint32(2)).astype(np.uint8)
+        order = _sort_order(bucket, key16, v, parity, use_gpu)
+        bucket, key16, v = bucket[order], key16[order], v[order]
+        bucket_start = np.zeros(nb + 1, dtype=np.int64)
+        np.cumsum(np.bincount(bucket, minlength=nb).astype(np.int64), out=bucket_start[1:])
+        # gvindex_init(offset of the block's first window) / gvindex_set up to the last window (or the contig's last base when
+        # the block ends with the input) / gvindex_dump (gene-value-index.c:29-41,135-187)
+        start_point = 0 if not out else int(val[first])
+        last_base = total_end if last == key.shape[0] - 1 else int(val[last]) + 16
+        length = last_base - start_point + PADDING
+        base0 = start_point - start_point % 4
+        n_bytes = ((length + start_point - base0) >> 2) + 1
+        piece = np.zeros(n_bytes * 4, dtype=np.uint8)
+        lo, hi = start_point, min(last_base, base0 + n_bytes * 4)
+        piece[lo - base0:hi - base0] = bases[lo:hi]
+        b4 = piece.reshape(-1, 4)
+        packed = (b4[:, 0] | (b4[:, 1] << 2) | (b4[:, 2] << 4) | (b4[:, 3] << 6)).astype(np.uint8)
+        out.append(dict(index_gap=gap, padding=PADDING, buckets_number=nb, n_items=int(key16.shape[0]),
+                        bucket_start=bucket_start.astype(np.uint32), keys=key16, vals=v.astype(np.uint32), item_bucket=bucket,
+                        start_point=start_point, length=int(length), values=packed, read_offsets=np.array(ends, dtype=np.uint32),
+                        names=list(names), contig_starts=np.array(starts, dtype=np.int64), removed_keys=int(heavy.shape[0]),
+                        windows=(int(first), int(last))))
+    return out
+
+
+def build_index_multiblock(fasta_path, prefix, gapped=True, threshold=100, memory_mb=8000, use_gpu=False):
+    """FASTA -> <prefix>.NN.b.tab / .NN.b.array for every block and <prefix>.reads: ``subread-buildindex -M memory_mb [-F]``."""
+    names, seqs = read_fasta_sanitised(fasta_path)
+    blocks = build_index_blocks(names, seqs, gapped, threshold, memory_mb, use_gpu)
+    for n, a in enumerate(blocks):
+        write_index_files(prefix, a, block_no=n, write_reads=(n == len(blocks) - 1))
+    return dict(blocks=len(blocks), buckets=blocks[0]["buckets_number"], items=[a["n_items"] for a in blocks], gap=blocks[0]["index_gap"],
+                contigs=len(seqs))
 
 
 def build_index_arrays_device(names, codes, contig_lens, gapped=True, threshold=100, buckets=None, device=None,

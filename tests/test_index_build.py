@@ -69,3 +69,43 @@ def test_device_builder_equals_array_builder():
             assert np.array_equal(a[k], b[k]), (gapped, k)
         assert (a["n_items"], a["length"], a["removed_keys"]) == (b["n_items"], b["length"], b["removed_keys"])
         assert a["removed_keys"] > 0
+
+
+def _write_random_genome(path, lens, seed):
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    with open(path, "w") as fh:
+        for i, L in enumerate(lens):
+            s = acgt[rng.integers(0, 4, L)].tobytes().decode()
+            fh.write(f">contig{i} made up\n")
+            for k in range(0, L, 70):
+                fh.write(s[k:k + 70] + "\n")
+
+
+@pytest.mark.parametrize("tag,lens,full,memory_mb", [
+    ("cuts_at_contig_starts", [420000] * 4 + [100000, 17, 500000], False, 1),       # a block per contig: the cut waits for a contig's first 32 bases
+    ("cuts_at_contig_starts_full", [150000] * 3 + [40], True, 1),
+    ("cuts_inside_a_long_contig", [5500003, 30000], False, 8),                        # past 2 Mbp into a contig: cut there, step 1 999 990 bases back
+])
+def test_multiblock_builder_is_byte_identical_to_reference(tag, lens, full, memory_mb, tmp_path):
+    """subread-buildindex WITHOUT -B cuts the index into blocks (index-builder.c:255-330, :353); build_index_multiblock follows the
+    same cuts -- the overlap between consecutive blocks included -- and every .NN.b.tab / .NN.b.array / .reads is byte-identical
+    to the reference builder's, run here on the same FASTA."""
+    import glob
+    import subprocess
+    from conftest import REF_DIR
+    from subread_b200.index_build import build_index_multiblock
+    exe = os.path.join(REF_DIR, "bin", "subread-buildindex")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref (reference binaries) not built")
+    fa = str(tmp_path / "g.fa")
+    _write_random_genome(fa, lens, 3)
+    subprocess.run([exe, "-o", str(tmp_path / "ref"), "-M", str(memory_mb)] + (["-F"] if full else []) + [fa], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    info = build_index_multiblock(fa, str(tmp_path / "mine"), gapped=not full, memory_mb=memory_mb)
+    assert info["blocks"] >= 3
+    ref_files = sorted(os.path.basename(f)[len("ref"):] for f in glob.glob(str(tmp_path / "ref.*")) if f.endswith((".tab", ".array", ".reads")))
+    my_files = sorted(os.path.basename(f)[len("mine"):] for f in glob.glob(str(tmp_path / "mine.*")))
+    assert ref_files == my_files and len(ref_files) == 2 * info["blocks"] + 1
+    for f in ref_files:
+        assert open(str(tmp_path / ("ref" + f)), "rb").read() == open(str(tmp_path / ("mine" + f)), "rb").read(), f
