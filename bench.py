@@ -294,7 +294,7 @@ def whole_program(g, index_arrays, name, sample_frags, tmp):
     return out
 
 
-def output_writer_measure(tmp, n_records=400_000, read_len=150):
+def output_writer_measure(tmp, n_records=200_000, read_len=150):
     """Row f2 on this box's host cores: the library's BAM writer (srcuda_out_*, one producer + a team of deflate threads) against
     the reference's single stream (SamBam_writer_add_read_line) on the same synthetic SAM records, timed by
     oracle/_ref/ref_writer_bench (the reference half is the baseline, like cpu_baseline); the two files are compared."""
