@@ -48,6 +48,7 @@ struct srcuda_writer {
 	int threads = 1;
 	int level = Z_BEST_SPEED;
 	bool header_done = false;
+	bool header_done_writing = false;  // the header blocks are out: blocks from here on hold records
 	bool failed = false;
 	std::string error;
 	std::string header_text;  // BAM: kept until finish_header
@@ -200,7 +201,10 @@ int seal_block(srcuda_writer *w) {
 	std::unique_ptr<srcuda_writer::Job> job(new srcuda_writer::Job());
 	job->plain.swap(w->block);
 	w->block.reserve(kDeflateRoom);
-	start_team(w);
+	// The team starts with the first block of RECORDS, not with the header: a process that has ever started a thread pays for
+	// locked stdio from then on, and the reference's index loader (millions of small fread calls, sorted-hashtable.c:1390)
+	// runs between the header and the first record -- 2 s of 5 on the build container.
+	if (w->header_done_writing) start_team(w);
 	{
 		std::lock_guard<std::mutex> lk(w->mu);
 		w->jobs.push_back(std::move(job));
@@ -247,8 +251,9 @@ int bam_write_header(srcuda_writer *w) {
 int finish_header(srcuda_writer *w) {
 	if (w->header_done) return SRCUDA_OK;
 	w->header_done = true;
-	if (w->format == SRCUDA_OUT_BAM) return bam_write_header(w);
-	return SRCUDA_OK;
+	int rc = w->format == SRCUDA_OUT_BAM ? bam_write_header(w) : SRCUDA_OK;
+	w->header_done_writing = true;
+	return rc;
 }
 
 // CIGAR text -> BAM operations (SamBam_compress_cigar, sambam-file.c:1426-1458): operation codes from "MIDNSHP=X", anything
