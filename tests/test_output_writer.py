@@ -402,3 +402,20 @@ def test_optional_columns_follow_the_reference_converter(ref, tmp_path):
         assert aux == out.raw[:m], (i, t[:80])
         at += 4 + n
     assert at == len(payload)
+
+
+@pytest.mark.parametrize("sanitizer", ["address,undefined", "thread"])
+def test_sanitizer_fuzz(sanitizer, tmp_path):
+    """tests/native/output_fuzz.cpp: 40 000 damaged SAM lines through srcuda_out_add_sam_lines and fragments formatted on four
+    threads at once, with the writer compiled under AddressSanitizer + UBSan and under ThreadSanitizer: damaged lines may be
+    refused, nothing may crash, touch memory outside its buffers, or race."""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "output_fuzz")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=" + sanitizer, "-fno-sanitize-recover=all", "-fno-omit-frame-pointer", "-o", exe,
+           os.path.join(ROOT, "tests", "native", "output_fuzz.cpp"), os.path.join(ROOT, "subread_b200", "csrc", "sr_output.cpp"), "-lz", "-pthread"]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + built.stderr[-200:])
+    run = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"), timeout=600)
+    assert run.returncode == 0 and run.stdout.startswith("lines taken"), run.stdout[-400:] + run.stderr[-2000:]
