@@ -345,6 +345,9 @@ void write_single_fragment(global_context_t *global_context, thread_context_t *t
 
 int destroy_global_context(global_context_t *context)
 {
+	if (getenv("SRCUDA_PHASE_TIMES")) /* the reference's own clocks (core.c:3552-3640), for the whole-program breakdown in DESIGN.md */
+		fprintf(stderr, "PHASES load_index=%.2f voting=%.2f before_realign=%.2f realign=%.2f\n", context->timecost_load_index, context->timecost_voting,
+		        context->timecost_before_realign, context->timecost_for_realign);
 	if (native_output() && g_out.writer && !context->config.is_BAM_output) {
 		srcuda_writer *w = g_out.writer;
 		g_out.writer = NULL;

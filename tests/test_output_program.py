@@ -165,3 +165,49 @@ def test_single_end_reads_with_and_without_qualities(index, tmp_path):
         assert len(a) > 100000 and a == b, (tag, out)
         if tag == "fasta":
             assert b.split(b"\n")[-2].split(b"\t")[10] == b"I" * 100
+
+
+def run_cached(exe, args, cwd, cache, out_name, extra_env=None):
+    """One run with the later passes read from memory (integration/read_cache.c, SRCUDA_READ_CACHE=1) or through the original."""
+    os.makedirs(cwd, exist_ok=True)
+    env = dict(os.environ, SRCUDA_NATIVE_OUTPUT="0", SRCUDA_READ_CACHE="1" if cache else "0", **(extra_env or {}))
+    p = subprocess.run([exe] + args + ["-o", out_name], cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert p.returncode == 0, p.stdout.decode()[-2000:]
+    assert (b"read their chunks from memory" in p.stdout) == bool(cache), "which reader ran?"
+    return open(os.path.join(cwd, out_name), "rb").read()
+
+
+@pytest.mark.parametrize("tag,args,env", [
+    ("pe", ["-t", "1", "-T", "4", "--SAMoutput"], {}),
+    ("pe_three_chunks", ["-t", "1", "-T", "3", "--SAMoutput"], {"SUBREAD_TEST_READS_PER_CHUNK": "2500"}),
+    ("pe_trimmed_ff", ["-t", "1", "-T", "4", "--SAMoutput", "--trim5", "3", "--trim3", "2", "-S", "ff"], {}),
+    ("pe_bam_ordered", ["-t", "1", "-T", "4", "--keepReadOrder"], {"SUBREAD_TEST_READS_PER_CHUNK": "4000"}),
+])
+def test_later_passes_read_from_memory(index, pe_cut, tmp_path, tag, args, env):
+    """fetch_next_read_pair served from the chunk's bytes in memory (row f3 for the passes after voting): the files are the same,
+    @PG line included, as with the reference's read-at-a-time reader -- over several chunks (a test knob sizes them), with trimming
+    and with both mates on the forward strand."""
+    out = "o.bam" if "bam" in tag else "o.sam"
+    a = run_cached(ALIGN_OUT, args + ["-i", index] + pe_cut, str(tmp_path / "original"), 0, out, env)
+    b = run_cached(ALIGN_OUT, args + ["-i", index] + pe_cut, str(tmp_path / "cached"), 1, out, env)
+    assert len(a) > 100000 and a == b
+
+
+def test_later_passes_read_from_memory_subjunc_and_single_end(index, tmp_path):
+    """The same for subjunc on the reference's junction fixture (plain FASTQ, paired) and for a single-end run of its first file."""
+    reads = ["-r", os.path.join(FIX, "junction-reads-A.fq"), "-R", os.path.join(FIX, "junction-reads-B.fq")]
+    a = run_cached(SUBJUNC_OUT, ["-T", "4", "-i", index, "--SAMoutput"] + reads, str(tmp_path / "original"), 0, "o.sam")
+    b = run_cached(SUBJUNC_OUT, ["-T", "4", "-i", index, "--SAMoutput"] + reads, str(tmp_path / "cached"), 1, "o.sam")
+    assert len(a) > 100000 and a == b
+    a = run_cached(ALIGN_OUT, ["-t", "1", "-T", "4", "-i", index, "--SAMoutput"] + reads[:2], str(tmp_path / "original_se"), 0, "o.sam")
+    b = run_cached(ALIGN_OUT, ["-t", "1", "-T", "4", "-i", index, "--SAMoutput"] + reads[:2], str(tmp_path / "cached_se"), 1, "o.sam")
+    assert len(a) > 100000 and a == b
+
+
+def test_gzip_input_is_left_to_the_original_reader(index, tmp_path):
+    """gzip input is not plain FASTQ: with SRCUDA_READ_CACHE=1 the original reader still serves every pass (and says nothing)."""
+    env = dict(os.environ, SRCUDA_READ_CACHE="1", SRCUDA_NATIVE_OUTPUT="0")
+    p = subprocess.run([ALIGN_OUT, "-t", "1", "-T", "2", "-i", index] + PE + ["--SAMoutput", "-o", str(tmp_path / "o.sam")], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert p.returncode == 0 and b"read their chunks from memory" not in p.stdout
+    assert os.path.getsize(str(tmp_path / "o.sam")) > 1000000
