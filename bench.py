@@ -182,7 +182,7 @@ def reference_files(tmp, g, index_arrays, name, sample_frags, seed):
     return prefix, fqs, reads
 
 
-def run_reference(prefix, fqs, threads, out_dir, subjunc, exe=None):
+def run_reference(prefix, fqs, threads, out_dir, subjunc, exe=None, env_extra=None):
     """One run of the unmodified reference on the sample (default BAM output).  Uses the instrumented build (ref_dump: the same
     sources compiled -fPIC with oracle/ref_hooks.c reading the reference's own clocks) when it is there.  Returns
     {"wall_s", "voting_s" | None, "load_index_s" | None}."""
@@ -199,7 +199,7 @@ def run_reference(prefix, fqs, threads, out_dir, subjunc, exe=None):
     if len(fqs) > 1:
         cmd += ["-R", fqs[1]]
     t0 = time.perf_counter()
-    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=dict(os.environ, SRDUMP_TIMING=tfile))
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=dict(os.environ, SRDUMP_TIMING=tfile, **(env_extra or {})))
     res = {"wall_s": time.perf_counter() - t0, "voting_s": None, "load_index_s": None, "exe": os.path.basename(exe)}
     if os.path.exists(tfile):
         for line in open(tfile):
@@ -291,6 +291,15 @@ def whole_program(g, index_arrays, name, sample_frags, tmp):
         out["speedup"] = out["stock_s"] / out["cuda_s"]
         out["note"] = ("subread-align-cuda = the reference's own main, chunk loop, realignment and BAM writer with do_voting replaced "
                        "(integration/do_voting_cuda.c); everything but the voting step still runs on the host")
+    # ... and with the passes after voting reading their chunk from memory (integration/read_cache.c, row f3 behind the voting step)
+    try:
+        cache = {"SRCUDA_READ_CACHE": "1"}
+        run_reference(prefix, fqs, threads, tmp, False, CUDA_BIN, cache)
+        out["cuda_read_cache_s"] = run_reference(prefix, fqs, threads, tmp, False, CUDA_BIN, cache)["wall_s"]
+        if "stock_s" in out:
+            out["speedup_read_cache"] = out["stock_s"] / out["cuda_read_cache_s"]
+    except Exception as e:
+        out["cuda_read_cache_error"] = repr(e)
     return out
 
 

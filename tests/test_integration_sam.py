@@ -129,3 +129,29 @@ def test_gpu_voting_with_the_librarys_writer(out_name, extra, tmp_path):
         (ta, ra), (tb, rb) = bam_records(outs[0]), bam_records(outs[1])
         assert no_pg(ta) == no_pg(tb)
         assert ra == rb and len(ra) > 40000
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_DUMP) and os.path.exists(CUDA)), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("paired", [False, True], ids=["se", "pe"])
+def test_sam_identical_with_later_passes_read_from_memory(paired, tmp_path):
+    """The GPU-bound binary with integration/read_cache.c switched on (SRCUDA_READ_CACHE=1): the voting pass reads each chunk
+    through the library's reader, the realignment pass copies its reads out of the chunk's bytes in memory instead of parsing the
+    file a character at a time under input_lock.  Several chunks; SAM identical to the unmodified reference's."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_data
+    fa = str(tmp_path / "g.fa")
+    gen_data.write_genome(fa, 4, 400000, seed=78, repeats=100)
+    prefix = str(tmp_path / "idx")
+    subprocess.run([BUILDINDEX, "-B", "-o", prefix, fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    gen_data.write_reads(fa, str(tmp_path / "r"), 20000, 110, 21, paired, 0.01, 0.15, True, 0.002)
+    reads = ["-r", str(tmp_path / "r_R1.fastq")] + (["-R", str(tmp_path / "r_R2.fastq")] if paired else [])
+    outs = []
+    for exe, tag, cache in ((REF_DUMP, "stock", "0"), (CUDA, "cuda", "1")):
+        out = str(tmp_path / f"{tag}.sam")
+        p = subprocess.run([exe, "-t", "1", "-T", "3", "-i", prefix] + reads + ["--SAMoutput", "-o", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           env=dict(os.environ, SUBREAD_TEST_READS_PER_CHUNK="6000", SRCUDA_READ_CACHE=cache))
+        assert p.returncode == 0, p.stdout.decode()[-2000:]
+        assert (b"read their chunks from memory" in p.stdout) == (cache == "1")
+        outs.append(sam_body(out))
+    assert outs[0].count(b"\n") >= 20000 * (2 if paired else 1)
+    assert outs[0] == outs[1]
