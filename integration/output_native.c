@@ -13,9 +13,10 @@
  * RTLD_NEXT), and for what the library does not write (coordinate-sorted BAM, colour-space reads) it forwards too.
  * tests/test_output_program.py: SAM and BAM byte-identical to the stock programs' (apart from @PG).
  *
- * Order: SAM output and BAM output with --keepReadOrder are written in input order, as in the reference (the workers take
- * turns by fragment number, add_buffered_fragment core.c:1855-1881); plain multi-thread BAM output is written in the order
- * the workers arrive -- the reference's own order there is per-thread and changes from run to run.
+ * Order: SAM output and BAM output with --keepReadOrder are written in input order, as in the reference -- but no worker waits
+ * for its turn (hand_over_in_order below; the reference's relay is add_buffered_fragment, core.c:1855-1881); plain multi-thread
+ * BAM output is written in the order the workers arrive -- the reference's own order there is per-thread and changes from run
+ * to run.
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -230,6 +231,92 @@ void write_sam_headers(global_context_t *context)
 	}
 }
 
+/* ---- input order without waiting ---------------------------------------------------------------------------------------
+ * The reference keeps SAM output and --keepReadOrder BAM output in input order by making every worker WAIT, with the finished
+ * records in its hands, until the fragment in front has been written (add_buffered_fragment, core.c:1855-1881: a 2 us sleep per
+ * look, one fragment per turn) -- the realignment step runs at the speed of that relay.  Here a worker never waits: a fragment
+ * that is next in line goes to the stream at once, together with every parked fragment behind it; any other fragment is parked
+ * (its encoded bytes, one piece per reported location so that the blocks are cut where the reference cuts them) and its worker
+ * goes on with the next read.  last_written_fragment_number is the reference's own counter (reset for every step, core.c:3385). */
+typedef struct {
+	long long pair;
+	char *bytes; /* pieces: u32 length + payload, one per location */
+	size_t used, room;
+	int complete;
+} parked_t;
+
+static struct {
+	pthread_mutex_t mu;
+	parked_t *ring;
+	size_t cap;
+} g_order = {PTHREAD_MUTEX_INITIALIZER, NULL, 0};
+
+static __thread parked_t t_mine; /* the fragment this worker is collecting (a multi-mapped read arrives location by location) */
+
+static int write_pieces(const char *bytes, size_t used)
+{
+	int rc = 0;
+	for (size_t at = 0; at + 4 <= used;) {
+		unsigned int n;
+		memcpy(&n, bytes + at, 4);
+		if (n && srcuda_out_append(g_out.writer, bytes + at + 4, n, 1)) rc = 1;
+		at += 4 + n;
+	}
+	return rc;
+}
+
+static int hand_over_in_order(global_context_t *gc, long long pair_number, const char *encoded, size_t bytes, int last_location)
+{
+	parked_t *m = &t_mine;
+	if (m->used + 4 + bytes > m->room) {
+		m->room = 2 * (m->used + 4 + bytes) + 4096;
+		m->bytes = realloc(m->bytes, m->room);
+		if (!m->bytes) { m->room = m->used = 0; return 1; }
+	}
+	unsigned int n = (unsigned int)bytes;
+	memcpy(m->bytes + m->used, &n, 4);
+	memcpy(m->bytes + m->used + 4, encoded, bytes);
+	m->used += 4 + bytes;
+	if (!last_location) return 0;
+	int rc = 0;
+	pthread_mutex_lock(&g_order.mu);
+	long long next = (long long)gc->last_written_fragment_number + 1;
+	if (pair_number == next) {
+		rc |= write_pieces(m->bytes, m->used);
+		next++;
+		while (g_order.cap) { /* everybody who was waiting right behind */
+			parked_t *p = &g_order.ring[(size_t)next % g_order.cap];
+			if (!p->complete || p->pair != next) break;
+			rc |= write_pieces(p->bytes, p->used);
+			free(p->bytes);
+			memset(p, 0, sizeof *p);
+			next++;
+		}
+		gc->last_written_fragment_number = next - 1;
+		m->used = 0;
+	} else {
+		size_t ahead = (size_t)(pair_number - next);
+		if (ahead >= g_order.cap) { /* a ring that holds every fragment between the next one and this one */
+			size_t cap = g_order.cap ? g_order.cap : 1024;
+			while (cap <= ahead) cap *= 2;
+			parked_t *ring = calloc(cap, sizeof(parked_t));
+			if (!ring) { pthread_mutex_unlock(&g_order.mu); return 1; }
+			for (size_t i = 0; i < g_order.cap; i++)
+				if (g_order.ring[i].complete) ring[(size_t)g_order.ring[i].pair % cap] = g_order.ring[i];
+			free(g_order.ring);
+			g_order.ring = ring;
+			g_order.cap = cap;
+		}
+		parked_t *p = &g_order.ring[(size_t)pair_number % g_order.cap];
+		*p = *m; /* the worker's buffer moves into the ring; it starts a new one */
+		p->pair = pair_number;
+		p->complete = 1;
+		memset(m, 0, sizeof *m);
+	}
+	pthread_mutex_unlock(&g_order.mu);
+	return rc;
+}
+
 /* ---- write_single_fragment (core.c:1888-2170) ------------------------------------------------------------------------- */
 
 static void fill_mate(global_context_t *g, srcuda_sam_mate *m, output_tmp_t *rec, realignment_result_t *raw, int ok, char *name, char *text, char *qual,
@@ -297,8 +384,9 @@ void write_single_fragment(global_context_t *global_context, thread_context_t *t
 		SUBREADprintf("ERROR: cannot build a record: %s\n", srcuda_out_error(NULL));
 		bytes = 0; /* the turn below is still taken, or the workers behind would wait for ever */
 	}
-	int in_turns = thread_context && !(global_context->config.is_BAM_output && !global_context->config.is_input_read_order_required);
-	if (in_turns) { /* input order: wait for the fragment in front (add_buffered_fragment, core.c:1855-1881) */
+	int in_order = thread_context && !(global_context->config.is_BAM_output && !global_context->config.is_input_read_order_required);
+	if (in_order && global_context->config.ignore_unmapped_reads) {
+		/* fragments may be missing from the sequence: keep the original's turn-taking (add_buffered_fragment, core.c:1855-1881) */
 		for (;;) {
 			int done = 0;
 			subread_lock_occupy(&global_context->output_lock);
@@ -311,6 +399,8 @@ void write_single_fragment(global_context_t *global_context, thread_context_t *t
 			if (done) break;
 			usleep(2);
 		}
+	} else if (in_order) {
+		if (hand_over_in_order(global_context, pair_number, encoded, bytes, all_locations <= current_location + 1)) rc = SRCUDA_ERR_IO;
 	} else if (bytes) {
 		pthread_mutex_lock(&g_out.lock);
 		if (srcuda_out_append(g_out.writer, encoded, bytes, 1)) rc = SRCUDA_ERR_IO;
