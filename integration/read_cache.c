@@ -15,9 +15,14 @@
  * Memory: the chunk's bytes (a full chunk of 7 M reads of 150 bases is 2.4 GB per file) plus 30 bytes per read, freed when the next
  * chunk is loaded.
  *
- * Used for plain FASTQ input in base space when SRCUDA_READ_CACHE=1; gzip / SAM / BAM / FASTA input, colour space, and any
- * chunk whose bytes the splitter does not account for exactly (a damaged record, a read that is empty after trimming, a
- * quality line of another length than its read) go through the original.  Linked into oracle/_ref/subread-align-cuda,
+ * Used in base space when SRCUDA_READ_CACHE=1.  Plain FASTQ input goes the way described above.  Every other input (gzip
+ * FASTQ -- the seekable inflater re-inflates the chunk under the same lock --, FASTA, SAM / BAM) cannot be indexed from a byte
+ * range, so its reads are KEPT as the chunk's first voting pass fetches them through the original (one allocation per fragment:
+ * names, bases and qualities of its mates as the original returned them, mates already oriented) and the later passes are
+ * served from that record.  locate_read_files (core.c:3482; called when a chunk starts and when its first voting pass is over)
+ * tells the two phases apart.  Colour space, scRNA input, and any plain-FASTQ chunk whose bytes the splitter does not account
+ * for exactly (a damaged record, a read that is empty after trimming, a quality line of another length than its read) go
+ * through the original.  Linked into oracle/_ref/subread-align-cuda,
  * subjunc-cuda, subread-align-out and subjunc-out; tests/test_output_program.py compares SAM files with and without it.
  */
 #define _GNU_SOURCE
@@ -151,12 +156,116 @@ static void copy_read(const cached_file_t *f, int64_t k, char *name, char *text,
 	*len = f->len[k];
 }
 
+/* ---- inputs that are not plain FASTQ: the first voting pass is recorded ------------------------------------------------ */
+typedef struct {
+	char *blob; /* name1 \0 text1 \0 qual1 \0 [name2 \0 text2 \0 qual2 \0] */
+	int len1, len2;
+} kept_fragment_t;
+
+static struct {
+	int phase; /* 0 nothing, 1 the chunk's first voting pass is running (keep what it fetches), 2 later passes */
+	int usable;
+	kept_fragment_t *frag;
+	long long cap, kept;
+	int without_quality;
+} g_kept;
+
+static int keeps_reads(global_context_t *gc, gene_input_t *g1)
+{
+	return cache_enabled() && gc->config.space_type == GENE_SPACE_BASE && !gc->config.scRNA_input_mode && g1->file_type != GENE_INPUT_FASTQ &&
+	       g1->file_type != GENE_INPUT_BCL;
+}
+
+static void drop_kept(void)
+{
+	for (long long i = 0; i < g_kept.cap && g_kept.frag; i++) free(g_kept.frag[i].blob);
+	free(g_kept.frag);
+	g_kept.frag = NULL;
+	g_kept.cap = g_kept.kept = 0;
+	g_kept.usable = g_kept.without_quality = 0;
+}
+
+void locate_read_files(global_context_t *global_context, int type)
+{
+	static void (*original)(global_context_t *, int);
+	if (!original) original = (void (*)(global_context_t *, int))dlsym(RTLD_NEXT, "locate_read_files");
+	original(global_context, type);
+	if (!keeps_reads(global_context, &global_context->input_reads.first_read_file)) return;
+	if (type == SEEK_SET) { /* a chunk starts (core.c:3566) */
+		drop_kept();
+		g_kept.cap = (long long)global_context->config.reads_per_chunk;
+		g_kept.frag = calloc((size_t)g_kept.cap, sizeof(kept_fragment_t));
+		g_kept.phase = g_kept.frag ? 1 : 0;
+	} else if (g_kept.phase == 1) { /* its first voting pass is over (core.c:3598) */
+		g_kept.phase = 2;
+		g_kept.usable = g_kept.kept > 0 && g_kept.kept == (long long)global_context->running_processed_reads_in_chunk && !g_kept.without_quality;
+		if (g_kept.usable && !g_cache.told) {
+			g_cache.told = 1;
+			SUBREADprintf("Input: the passes after voting read their chunks from memory (libsubread_cuda, reads kept from the first pass)\n");
+		}
+		if (!g_kept.usable) drop_kept();
+	}
+}
+
+static void keep_fragment(subread_read_number_t k, int paired, const char *n1, const char *t1, const char *q1, int l1, const char *n2, const char *t2,
+                          const char *q2, int l2)
+{
+	if (k < 0 || k >= g_kept.cap) return;
+	if (!q1 || (paired && !q2)) {
+		__atomic_store_n(&g_kept.without_quality, 1, __ATOMIC_RELAXED);
+		return;
+	}
+	size_t a = strlen(n1) + 1, b = strlen(t1) + 1, c = strlen(q1) + 1, d = 0, e = 0, f = 0;
+	if (paired) { d = strlen(n2) + 1; e = strlen(t2) + 1; f = strlen(q2) + 1; }
+	char *blob = malloc(a + b + c + d + e + f);
+	if (!blob) return;
+	memcpy(blob, n1, a); memcpy(blob + a, t1, b); memcpy(blob + a + b, q1, c);
+	if (paired) { memcpy(blob + a + b + c, n2, d); memcpy(blob + a + b + c + d, t2, e); memcpy(blob + a + b + c + d + e, q2, f); }
+	kept_fragment_t *kf = &g_kept.frag[k];
+	kf->blob = blob;
+	kf->len1 = l1;
+	kf->len2 = l2;
+	__atomic_fetch_add(&g_kept.kept, 1, __ATOMIC_RELAXED);
+}
+
+static const char *take(const char *p, char *to)
+{
+	size_t n = strlen(p) + 1;
+	if (to) memcpy(to, p, n);
+	return p + n;
+}
+
 int fetch_next_read_pair(global_context_t *global_context, thread_context_t *thread_context, gene_input_t *ginp1, gene_input_t *ginp2, int *read_len_1,
                          int *read_len_2, char *read_name_1, char *read_name_2, char *read_text_1, char *read_text_2, char *qual_text_1,
                          char *qual_text_2, int remove_color_head, subread_read_number_t *read_no_in_chunk)
 {
 	static fetch_fn original;
 	if (!original) original = (fetch_fn)dlsym(RTLD_NEXT, "fetch_next_read_pair");
+	if (keeps_reads(global_context, ginp1)) {
+		if (g_kept.phase == 2 && g_kept.usable) { /* a later pass over a kept chunk */
+			subread_read_number_t k = __atomic_load_n(&global_context->running_processed_reads_in_chunk, __ATOMIC_RELAXED);
+			for (;;) {
+				if (k >= g_kept.kept) {
+					*read_no_in_chunk = -1;
+					return 1;
+				}
+				if (__atomic_compare_exchange_n(&global_context->running_processed_reads_in_chunk, &k, k + 1, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
+			}
+			const kept_fragment_t *kf = &g_kept.frag[k];
+			const char *p = take(take(take(kf->blob, read_name_1), read_text_1), qual_text_1);
+			if (ginp2) take(take(take(p, read_name_2), read_text_2), qual_text_2);
+			*read_no_in_chunk = k;
+			*read_len_1 = kf->len1;
+			if (ginp2) *read_len_2 = kf->len2;
+			return 0;
+		}
+		int rc = original(global_context, thread_context, ginp1, ginp2, read_len_1, read_len_2, read_name_1, read_name_2, read_text_1, read_text_2,
+		                  qual_text_1, qual_text_2, remove_color_head, read_no_in_chunk);
+		if (g_kept.phase == 1 && rc == 0 && *read_no_in_chunk >= 0)
+			keep_fragment(*read_no_in_chunk, ginp2 != NULL, read_name_1, read_text_1, qual_text_1, *read_len_1, read_name_2, read_text_2, qual_text_2,
+			              ginp2 ? *read_len_2 : 0);
+		return rc;
+	}
 	if (!chunk_ready(global_context, ginp1, ginp2))
 		return original(global_context, thread_context, ginp1, ginp2, read_len_1, read_len_2, read_name_1, read_name_2, read_text_1, read_text_2,
 		                qual_text_1, qual_text_2, remove_color_head, read_no_in_chunk);

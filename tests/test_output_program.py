@@ -207,10 +207,28 @@ def test_later_passes_read_from_memory_subjunc_and_single_end(index, tmp_path):
     assert len(a) > 100000 and a == b
 
 
-def test_gzip_input_is_left_to_the_original_reader(index, tmp_path):
-    """gzip input is not plain FASTQ: with SRCUDA_READ_CACHE=1 the original reader still serves every pass (and says nothing)."""
-    env = dict(os.environ, SRCUDA_READ_CACHE="1", SRCUDA_NATIVE_OUTPUT="0")
-    p = subprocess.run([ALIGN_OUT, "-t", "1", "-T", "2", "-i", index] + PE + ["--SAMoutput", "-o", str(tmp_path / "o.sam")], env=env,
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    assert p.returncode == 0 and b"read their chunks from memory" not in p.stdout
-    assert os.path.getsize(str(tmp_path / "o.sam")) > 1000000
+@pytest.mark.parametrize("tag,args,env", [
+    ("gz_pe", ["-t", "1", "-T", "4", "--SAMoutput"], {}),
+    ("gz_pe_chunks_multimapping", ["-t", "1", "-T", "3", "--SAMoutput", "--multiMapping", "-B", "2", "-S", "ff"], {"SUBREAD_TEST_READS_PER_CHUNK": "7000"}),
+])
+def test_gzip_input_is_kept_from_the_first_pass(index, tmp_path, tag, args, env):
+    """gzip FASTQ cannot be indexed from a byte range: with SRCUDA_READ_CACHE=1 the fragments are kept as the chunk's first voting
+    pass fetches them and the later passes are served from that record (the reference's test-err-mut fixture, 20 000 pairs, also in
+    three chunks).  Same file as with the original reader."""
+    a = run_cached(ALIGN_OUT, args + ["-i", index] + PE, str(tmp_path / "original"), 0, "o.sam", env)
+    b = run_cached(ALIGN_OUT, args + ["-i", index] + PE, str(tmp_path / "cached"), 1, "o.sam", env)
+    assert len(a) > 1000000 and a == b
+
+
+def test_fasta_input_is_kept_from_the_first_pass(index, tmp_path):
+    """FASTA input (no qualities) through the same record."""
+    import gzip
+    lines = gzip.open(os.path.join(FIX, "test-err-mut-r1.fq.gz"), "rb").read().split(b"\n")[:16000]
+    fa = str(tmp_path / "r.fa")
+    with open(fa, "wb") as fh:
+        for i in range(0, len(lines) - 3, 4):
+            fh.write(b">" + lines[i][1:] + b"\n" + lines[i + 1] + b"\n")
+    args = ["-t", "1", "-T", "4", "-i", index, "-r", fa, "--SAMoutput"]
+    a = run_cached(ALIGN_OUT, args, str(tmp_path / "original"), 0, "o.sam")
+    b = run_cached(ALIGN_OUT, args, str(tmp_path / "cached"), 1, "o.sam")
+    assert len(a) > 100000 and a == b
