@@ -248,6 +248,13 @@ int srcuda_reader_open(const char *path1, const char *path2, uint64_t window_byt
  * without '@' or '+' is SRCUDA_ERR_FORMAT after the records in front of it have been handed out. */
 int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *text, uint64_t text_capacity, uint64_t *off, uint16_t *len,
                        int64_t *n_frags, uint64_t *text_bytes);
+/* The same batch with the names (cut at the first blank, at most 199 characters, not terminated) and the quality lines (trimmed like
+ * the reads; not terminated) of its reads gathered as well: read k's name is names[name_off[k] .. + name_len[k]), its qualities
+ * quals[qual_off[k] .. + qual_len[k]).  What a caller needs to stand in for fetch_next_read_pair (core.c:1121) in every pass over a
+ * chunk, not only the voting step.  Capacities too small for the batch are SRCUDA_ERR_ARG. */
+int srcuda_reader_next_full(srcuda_reader *r, int64_t max_frags, char *text, uint64_t text_capacity, uint64_t *off, uint16_t *len,
+                            char *names, uint64_t names_capacity, uint64_t *name_off, uint16_t *name_len, char *quals,
+                            uint64_t quals_capacity, uint64_t *qual_off, uint16_t *qual_len, int64_t *n_frags, uint64_t *text_bytes);
 /* Passes over the next n_frags fragments without gathering them (*skipped = how many there were): a process that maps
  * one slice of every chunk (one GPU of several) skips the slices of the others. */
 int srcuda_reader_skip(srcuda_reader *r, int64_t n_frags, int64_t *skipped);

@@ -24,7 +24,7 @@ EXPORTS = [
     "srcuda_host_alloc", "srcuda_host_free", "srcuda_vote_chunk", "srcuda_vote_chunk_device", "srcuda_vote_chunk_multi", "srcuda_index_load_all",
     "srcuda_get_timing", "srcuda_set_force_slow_path", "srcuda_measure_gather_bandwidth", "srcuda_measure_lookup_roofline",
     "srcuda_fastq_split", "srcuda_fastq_split_mt", "srcuda_reads_pack", "srcuda_reads_pack_mt",
-    "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_skip", "srcuda_reader_tell", "srcuda_reader_error", "srcuda_reader_close",
+    "srcuda_reader_open", "srcuda_reader_next", "srcuda_reader_next_full", "srcuda_reader_skip", "srcuda_reader_tell", "srcuda_reader_error", "srcuda_reader_close",
     # include/subread_output.h (row f2)
     "srcuda_out_open", "srcuda_out_add_header", "srcuda_out_add_chromosome", "srcuda_out_finish_header", "srcuda_out_add_read",
     "srcuda_out_add_reads", "srcuda_out_add_sam_lines", "srcuda_out_add_fragment", "srcuda_out_format_fragment", "srcuda_out_append", "srcuda_out_flush", "srcuda_out_close",
@@ -144,6 +144,7 @@ def load_library():
     L.srcuda_reads_pack_mt.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, u64, vp, vp, ctypes.c_int, ctypes.POINTER(u64)]
     L.srcuda_reader_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.srcuda_reader_next.argtypes = [vp, i64, vp, u64, vp, vp, ctypes.POINTER(i64), ctypes.POINTER(u64)]
+    L.srcuda_reader_next_full.argtypes = [vp, i64, vp, u64, vp, vp, vp, u64, vp, vp, vp, u64, vp, vp, ctypes.POINTER(i64), ctypes.POINTER(u64)]
     L.srcuda_reader_skip.argtypes = [vp, i64, ctypes.POINTER(i64)]
     L.srcuda_reader_tell.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.srcuda_reader_error.argtypes = [vp]

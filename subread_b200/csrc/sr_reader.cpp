@@ -52,7 +52,8 @@ struct Stream {
 	uint64_t file_pos = 0;          // file offset (inflated bytes) of win[0]
 	std::vector<uint64_t> off;      // indexed, not yet handed out: records [cursor, n)
 	std::vector<uint64_t> name_off; // ... and where their names begin (srcuda_reader_tell: a record starts one byte earlier, at its '@')
-	std::vector<uint16_t> len, name_len;
+	std::vector<uint64_t> qual_off; // ... and their quality lines (srcuda_reader_next_full)
+	std::vector<uint16_t> len, name_len, qual_len;
 	int64_t n = 0, cursor = 0;
 	int64_t pending() const { return n - cursor; }
 };
@@ -69,6 +70,13 @@ struct srcuda_reader {
 	bool error_fresh = false;       // an error was recorded during the current call
 	int64_t frags_out = 0;
 	int deferred_rc = 0;            // a refill failed after fragments had been gathered: they were handed out, the error comes with the next call
+	// srcuda_reader_next_full: where the names and quality lines of the call in progress go (null otherwise)
+	struct Extra {
+		char *names, *quals;
+		uint64_t names_cap, quals_cap, names_used, quals_used;
+		uint64_t *name_off, *qual_off;
+		uint16_t *name_len, *qual_len;
+	} *extra = nullptr;
 };
 
 namespace {
@@ -224,10 +232,12 @@ int refill(srcuda_reader *r, int which)
 		// room for records of 32 bytes and more; shorter ones just take another round (SRCUDA_FASTQ_FULL leaves the rest
 		// of the window for the next refill)
 		const size_t cap = st.have / 32 + 1024;
-		if (st.off.size() < cap) { st.off.resize(cap); st.len.resize(cap); st.name_off.resize(cap); st.name_len.resize(cap); }
+		if (st.off.size() < cap) {
+			st.off.resize(cap); st.len.resize(cap); st.name_off.resize(cap); st.name_len.resize(cap); st.qual_off.resize(cap); st.qual_len.resize(cap);
+		}
 		srcuda_fastq_batch b;
 		const int rc = srcuda_fastq_split_mt(st.win.data(), st.have, st.eof ? 1 : 0, r->trim_5, r->trim_3, (int64_t)cap, 0, 1, st.off.data(),
-		                                     st.len.data(), st.name_off.data(), st.name_len.data(), nullptr, nullptr, r->threads, &b);
+		                                     st.len.data(), st.name_off.data(), st.name_len.data(), st.qual_off.data(), st.qual_len.data(), r->threads, &b);
 		if (rc == SRCUDA_ERR_FORMAT && b.n_reads == 0)
 			return fail(r, rc, "input file %d: a format issue at byte %llu (a record must start with '@' and have a '+' line)", which + 1,
 			            (unsigned long long)(st.file_pos + b.error_offset));
@@ -368,6 +378,24 @@ extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *tex
 			if (rc) return fail(r, rc, "srcuda_reads_pack_mt failed (%d)", rc);
 			if (written)
 				for (int64_t k = done * mates; k < (done + take) * mates; k++) off[k] += written;
+			if (r->extra) {              // names and quality lines of the same fragments, in the same order (read = fragment * mates + mate)
+				srcuda_reader::Extra &x = *r->extra;
+				for (int64_t f = 0; f < take; f++)
+					for (int m = 0; m < mates; m++) {
+						const Stream &st = r->s[m];
+						const size_t i = (size_t)(st.cursor + f), k = (size_t)((done + f) * mates + m);
+						if (x.names_used + st.name_len[i] > x.names_cap || x.quals_used + st.qual_len[i] > x.quals_cap)
+							return fail(r, SRCUDA_ERR_ARG, "the name or quality buffer is too small for %lld fragments", (long long)max_frags);
+						memcpy(x.names + x.names_used, st.win.data() + st.name_off[i], st.name_len[i]);
+						x.name_off[k] = x.names_used;
+						x.name_len[k] = st.name_len[i];
+						x.names_used += st.name_len[i];
+						memcpy(x.quals + x.quals_used, st.win.data() + st.qual_off[i], st.qual_len[i]);
+						x.qual_off[k] = x.quals_used;
+						x.qual_len[k] = st.qual_len[i];
+						x.quals_used += st.qual_len[i];
+					}
+			}
 			written += w;
 			done += take;
 			for (int i = 0; i < r->files; i++) r->s[i].cursor += take;
@@ -379,6 +407,18 @@ extern "C" int srcuda_reader_next(srcuda_reader *r, int64_t max_frags, char *tex
 	} catch (...) {
 		return fail(r, SRCUDA_ERR_NOMEM, "out of memory");
 	}
+}
+
+extern "C" int srcuda_reader_next_full(srcuda_reader *r, int64_t max_frags, char *text, uint64_t text_capacity, uint64_t *off, uint16_t *len,
+                                       char *names, uint64_t names_capacity, uint64_t *name_off, uint16_t *name_len, char *quals,
+                                       uint64_t quals_capacity, uint64_t *qual_off, uint16_t *qual_len, int64_t *n_frags, uint64_t *text_bytes)
+{
+	if (!r || !names || !name_off || !name_len || !quals || !qual_off || !qual_len || !text || !off || !len) return SRCUDA_ERR_ARG;
+	srcuda_reader::Extra x{names, quals, names_capacity, quals_capacity, 0, 0, name_off, qual_off, name_len, qual_len};
+	r->extra = &x;
+	const int rc = srcuda_reader_next(r, max_frags, text, text_capacity, off, len, n_frags, text_bytes);
+	r->extra = nullptr;
+	return rc;
 }
 
 extern "C" int srcuda_reader_skip(srcuda_reader *r, int64_t n_frags, int64_t *skipped)

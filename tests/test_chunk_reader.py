@@ -238,3 +238,50 @@ def test_tell_points_behind_the_last_fragment_handed_out(window, threads, tmp_pa
             assert left == 3000 - done
     assert done == 3000
     rd.close()
+
+
+def test_next_full_hands_out_names_and_qualities(tmp_path):
+    """srcuda_reader_next_full: the batch of srcuda_reader_next plus the names (cut at the first blank) and the quality lines
+    (trimmed like the reads) of its reads, for a paired gzip input read in several batches with small windows."""
+    import ctypes
+    import gzip
+    import random
+    from subread_b200 import binding
+    rnd = random.Random(5)
+    recs = [[], []]
+    for m in range(2):
+        for i in range(5000):
+            n = rnd.randrange(30, 160)
+            recs[m].append((b"frag%d/%d some comment" % (i, m + 1) if i % 3 else b"frag%d" % i, bytes(rnd.choice(b"ACGTN") for _ in range(n)),
+                            bytes(33 + rnd.randrange(0, 41) for _ in range(n))))
+        with gzip.open(str(tmp_path / f"r{m + 1}.fq.gz"), "wb") as fh:
+            for name, seq, qual in recs[m]:
+                fh.write(b"@" + name + b"\n" + seq + b"\n+\n" + qual + b"\n")
+    L = binding.load_library()
+    rd = ctypes.c_void_p()
+    trim5, trim3 = 2, 3
+    assert L.srcuda_reader_open(str(tmp_path / "r1.fq.gz").encode(), str(tmp_path / "r2.fq.gz").encode(), 1 << 16, 3, trim5, trim3, ctypes.byref(rd)) == 0
+    seen = 0
+    while True:
+        want = 1700
+        text = ctypes.create_string_buffer(want * 2 * 200)
+        names = ctypes.create_string_buffer(want * 2 * 200)
+        quals = ctypes.create_string_buffer(want * 2 * 200)
+        off, noff, qoff = ((ctypes.c_uint64 * (want * 2))() for _ in range(3))
+        ln, nlen, qlen = ((ctypes.c_uint16 * (want * 2))() for _ in range(3))
+        got, used = ctypes.c_int64(), ctypes.c_uint64()
+        rc = L.srcuda_reader_next_full(rd, want, text, len(text), off, ln, names, len(names), noff, nlen, quals, len(quals), qoff, qlen,
+                                       ctypes.byref(got), ctypes.byref(used))
+        assert rc == 0, L.srcuda_reader_error(rd)
+        if got.value == 0:
+            break
+        for f in range(got.value):
+            for m in range(2):
+                k = 2 * f + m
+                name, seq, qual = recs[m][seen + f]
+                assert names.raw[noff[k]:noff[k] + nlen[k]] == name.split(b" ")[0]
+                assert text.raw[off[k]:off[k] + ln[k]] == seq[trim5:len(seq) - trim3]
+                assert quals.raw[qoff[k]:qoff[k] + qlen[k]] == qual[trim5:len(qual) - trim3]
+        seen += got.value
+    assert seen == 5000
+    L.srcuda_reader_close(rd)
